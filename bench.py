@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""Benchmark of the GCN-layer hot path (BASELINE.json metric: layer fwd+bwd edges/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cbg]
+
+One "step" = one GraphConvolution forward + backward (pygcn/layers.py:32-38 + autograd) over
+the whole synthetic graph.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: ~100K nodes, ~10M edges, 64 feats; hidden 32
+    "cbg": dict(n=100_000, avg_deg=100, fin=64, fout=32,
+                name="synthetic CBG mobility-graph shape: N=100000 uniform graph, nnz~10.1M (sym+I, row-normalised), 64->32"),
+    # configs[2]: Reddit-shaped
+    "reddit": dict(n=232_965, avg_deg=492, fin=602, fout=256,
+                   name="synthetic Reddit shape: N=232965, nnz~114.6M, 602->256"),
+    # configs[3]: ogbn-products-shaped, hidden layer
+    "products": dict(n=2_449_029, avg_deg=25, fin=100, fout=256,
+                     name="synthetic ogbn-products shape: N=2449029, nnz~62M, 100->256"),
+}
+L2_FLUSH_BYTES = 512 << 20  # > 126 MB L2
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons with NVML in a thread while the timed region runs."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []  # (t, sm_mhz, reasons_bitmask, in_region)
+        self.in_region = False
+        self._stop = threading.Event()
+        self._thr = None
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                except Exception:
+                    reasons = 0
+                    mhz = 0
+            self.samples.append((time.perf_counter(), mhz, reasons, self.in_region))
+            time.sleep(0.002)
+
+    def start(self):
+        if self.ok:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr:
+            self._stop.set()
+            self._thr.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        nv = self.nv
+        region = [s for s in self.samples if s[3]]
+        scope = "timed_region"
+        if len(region) < 3:
+            region, scope = self.samples, "warmup+timed"
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        mask = 0
+        for s in region:
+            mask |= int(s[2])
+        reasons = sorted(v for k, v in names.items() if k and (mask & k))
+        return {"sm_mhz": statistics.median(s[1] for s in region), "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(region), "scope": scope}
+
+
+# --------------------------------------------------------------------------- helpers
+def algorithmic_bytes_spmm(nnz, n, f):
+    """int32 col + fp32 val per stored entry, rowptr, read the dense operand once,
+    write the output once (fp32)."""
+    return nnz * 8 + (n + 1) * 4 + n * f * 4 + n * f * 4
+
+
+def make_graph(P, torch, wl, dev, seed=0):
+    n = wl["n"]
+    n_raw = n * wl["avg_deg"] // 2
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    src = torch.randint(0, n, (n_raw,), generator=gen, device=dev, dtype=torch.int32)
+    dst = torch.randint(0, n, (n_raw,), generator=gen, device=dev, dtype=torch.int32)
+    g = P.Graph.from_edges(src, dst, n)  # sym (max) + I + D^-1: the reference's pipeline, on device
+    del src, dst
+    return g
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy burst)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args, wl):
+    """`--impl reference`: the reference layer's own CPU path (torch.mm + torch.spmm on the COO
+    tensor utils.py builds + bias, autograd backward), restated in oracle/ref_layer_torch.py
+    because /root/reference is not on the GPU box.  Host cores only."""
+    import torch
+
+    from oracle import gcn_oracle as O
+    from oracle import ref_layer_torch as R
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    import numpy as np
+
+    n, fin, fout = wl["n"], wl["fin"], wl["fout"]
+    t0 = time.perf_counter()
+    rs = np.random.default_rng(0)
+    n_raw = n * wl["avg_deg"] // 2
+    src = rs.integers(0, n, n_raw)
+    dst = rs.integers(0, n, n_raw)
+    idx, val = O.build_normalized_adjacency(src, dst, n)  # host pipeline (oracle restatement)
+    build_s = time.perf_counter() - t0
+    nnz = int(val.shape[0])
+    adj = R.make_reference_adj(torch.from_numpy(idx), torch.from_numpy(val), (n, n), "coo_as_written")
+    torch.manual_seed(42)
+    w = torch.empty(fin, fout)
+    torch.nn.init.kaiming_uniform_(w)
+    b = torch.empty(fout).uniform_(-1.0 / fout ** 0.5, 1.0 / fout ** 0.5)
+    x = torch.from_numpy(np.random.default_rng(1).standard_normal((n, fin), dtype=np.float32))
+    g = torch.from_numpy(np.random.default_rng(2).standard_normal((n, fout), dtype=np.float32))
+    sec = R.time_reference(x, w, b, adj, g, args.steps, args.warmup)
+    value = nnz / sec
+    # torch's best CPU path on the same matrix, a few steps, reported beside
+    csr = R.make_reference_adj(torch.from_numpy(idx), torch.from_numpy(val), (n, n), "csr")
+    sec_csr = R.time_reference(x, w, b, csr, g, max(2, min(args.steps, 5)), 1)
+    sample = "%d steps of the full %s workload (nnz=%d) after %d warm-up" % (args.steps, args.workload, nnz, args.warmup)
+    line = {
+        "impl": "reference", "metric": "gcn_layer_fwd_bwd_edges_per_sec", "value": value, "unit": "edges/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "nnz": nnz, "in_features": fin, "out_features": fout,
+                   "adj_form": "uncoalesced fp32 COO, int64 indices (utils.py:407-414), torch CPU",
+                   "input_requires_grad": False},
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample,
+                         "torch_threads": torch.get_num_threads(),
+                         "alt_csr_edges_per_s": nnz / sec_csr, "host_graph_build_s": build_s},
+        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args, wl):
+    import torch
+
+    import pygcn_b200 as P
+    from pygcn_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from pygcn_b200 import dist as D
+
+        return D.bench_main(args, wl)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    _lib.check(lib.gcnb_check_device(), "gcnb_check_device")
+    sampler = ClockSampler(torch.cuda.current_device() if os.environ.get("CUDA_VISIBLE_DEVICES") is None
+                           else int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+
+    n, fin, fout = wl["n"], wl["fin"], wl["fout"]
+    t0 = time.perf_counter()
+    graph = make_graph(P, torch, wl, dev)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    nnz = graph.nnz
+
+    torch.manual_seed(42)
+    layer = P.GraphConvolution(fin, fout).to(dev)
+    gen = torch.Generator(device="cpu")
+    x_host = torch.randn(n, fin, generator=gen.manual_seed(1)).pin_memory()
+    g_host = torch.randn(n, fout, generator=gen.manual_seed(2)).pin_memory()
+    x = x_host.to(dev)
+    g = g_host.to(dev)
+    flush_buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def flush():
+        _lib.check(lib.gcnb_l2_flush(ctypes.c_void_p(flush_buf.data_ptr()), flush_buf.numel(),
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "l2_flush")
+
+    def step_eager():
+        layer.weight.grad = None
+        layer.bias.grad = None
+        out = layer(x, graph)
+        out.backward(g)
+        return out
+
+    sampler.start()
+    # ---- warm-up (eager, public API)
+    for _ in range(max(args.warmup, 3)):
+        step_eager()
+    torch.cuda.synchronize()
+
+    # ---- capture the step in a CUDA graph (removes Python/launch gaps from the device time)
+    use_graph = not args.no_cuda_graph
+    cg = None
+    if use_graph:
+        try:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    step_eager()
+            torch.cuda.current_stream().wait_stream(s)
+            layer.weight.grad = None
+            layer.bias.grad = None
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                out_static = layer(x, graph)
+                out_static.backward(g)
+            torch.cuda.synchronize()
+        except Exception as e:  # pragma: no cover
+            sys.stderr.write("CUDA graph capture failed (%r); timing eager launches\n" % (e,))
+            cg = None
+            torch.cuda.synchronize()
+
+    def step():
+        if cg is not None:
+            cg.replay()
+        else:
+            step_eager()
+
+    for _ in range(max(args.warmup, 3)):
+        flush()
+        step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, L2 flushed between steps, CUDA events on the launching stream
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    sampler.in_region = True
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush()
+        ev[i][0].record()
+        step()
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    sampler.in_region = False
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+    ms_per_step = total_ms / args.steps
+    value = nnz / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel (CSR SpMM, forward and transposed launch) timed alone, same inputs
+    support = torch.randn(n, fout, device=dev)
+    outbuf = torch.empty(n, fout, device=dev)
+    sp_ms = []
+    for tflag in (0, _lib.SPMM_TRANSPOSE):
+        wsb = lib.gcnb_spmm_workspace_bytes(graph._h, tflag, fout)
+        ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=dev)
+        for it in range(3 + args.steps):
+            flush()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(lib.gcnb_spmm(graph._h, tflag, ctypes.c_void_p(support.data_ptr()), fout, fout, None,
+                                     ctypes.c_void_p(outbuf.data_ptr()), fout, ctypes.c_void_p(ws.data_ptr()),
+                                     ws.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "spmm")
+            b_.record()
+            if it >= 3:
+                sp_ms.append((a, b_))
+    torch.cuda.synchronize()
+    sp_ms = [a.elapsed_time(b_) for a, b_ in sp_ms]
+    spmm_ms = sum(sp_ms) / len(sp_ms)
+    peak, peak_src = peaks()
+    alg_bytes = algorithmic_bytes_spmm(nnz, n, fout)
+    achieved = alg_bytes / (spmm_ms * 1e-3) / 1e9
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timing
+    e2e_s = 0.0
+    h2d = x_host.numel() * 4 + g_host.numel() * 4
+    d2h = (fin * fout + fout) * 4
+    for i in range(2 + args.steps):
+        flush()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        xd = x_host.to(dev, non_blocking=True)
+        gd = g_host.to(dev, non_blocking=True)
+        layer.weight.grad = None
+        layer.bias.grad = None
+        o = layer(xd, graph)
+        o.backward(gd)
+        dw_h = layer.weight.grad.cpu()
+        db_h = layer.bias.grad.cpu()
+        torch.cuda.synchronize()
+        if i >= 2:
+            e2e_s += time.perf_counter() - t0
+    e2e_value = nnz / (e2e_s / args.steps)
+    sampler.stop()
+
+    # ---- CPU baseline on the host cores (bounded sample), N=1 only
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_baseline(torch, graph, layer, x_host, g_host, wl)
+
+    launches_per_step = 7  # gemm XW, spmm | colsum x2, spmm^T, gemm dW partial + split-K reduce
+    line = {
+        "metric": "gcn_layer_fwd_bwd_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "nnz": nnz, "n": n, "in_features": fin, "out_features": fout,
+                   "input_requires_grad": False, "l2": "flushed between timed steps (512 MiB write)",
+                   "cuda_graph": cg is not None, "graph_build_s": build_s,
+                   "bins": graph.bin_rows, "long_chunks": graph.n_long_chunks},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s / args.steps * 1e3},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "spmm_rows_vec_kernel<8,1> (CSR SpMM, fwd and A^T launches)",
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": spmm_ms, "peak_source": peak_src,
+                     "frac_of_8TBs_nominal": achieved / 8000.0,
+                     "how": "CUDA events around gcnb_spmm alone, L2 flushed before each launch, mean of %d launches" % len(sp_ms)},
+        "wall_s_timed_region": wall,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    return 0
+
+
+def cpu_baseline(torch, graph, layer, x_host, g_host, wl):
+    """The reference layer's CPU path (oracle/ref_layer_torch.py) on this box's host cores."""
+    from oracle import ref_layer_torch as R
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    coo = graph.to_sparse_coo()
+    idx = coo._indices().cpu()
+    val = coo._values().cpu()
+    n = graph.n_rows
+    adj = R.make_reference_adj(idx, val, (n, n), "coo_as_written")
+    w = layer.weight.detach().cpu()
+    b = layer.bias.detach().cpu()
+    x = x_host.clone()
+    g = g_host.clone()
+    # bounded sample: aim at ~15 s of CPU work
+    t1 = R.time_reference(x, w, b, adj, g, 1, 1)
+    steps = max(2, min(10, int(15.0 / max(t1, 1e-3))))
+    sec = R.time_reference(x, w, b, adj, g, steps, 0)
+    csr = R.make_reference_adj(idx, val, (n, n), "csr")
+    sec_csr = R.time_reference(x, w, b, csr, g, 3, 1)
+    return {"value": graph.nnz / sec, "unit": "edges/s", "cores": cores, "kind": "port",
+            "sample": "%d fwd+bwd steps of the full workload (nnz=%d) after 2 warm-up, torch CPU %d threads, "
+                      "adj = uncoalesced COO as utils.py:407-414 builds it" % (steps, graph.nnz, torch.get_num_threads()),
+            "ms_per_step": sec * 1e3, "alt_csr_edges_per_s": graph.nnz / sec_csr}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cbg", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+    return run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,193 @@
+/*
+ * gcnb200.h -- C ABI of libgcnb200.so: the B200 (sm_100a) implementation of the
+ * graph-convolution layer hot path of LinChen-65/pygcn.
+ *
+ * The reference has no FFI of its own: its boundary for this path is the Python class
+ * `GraphConvolution` (pygcn/layers.py:7-43) plus `torch.spmm`, and the host-side graph
+ * helpers `normalize` / `sparse_mx_to_torch_sparse_tensor` (pygcn/utils.py:390-397,
+ * 407-414).  Every entry point below names the reference line(s) it replaces; the Python
+ * binding a pygcn maintainer would add is in INTEGRATION.md and shipped in
+ * pygcn_b200/_lib.py.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer on the current CUDA device; the library
+ *     never frees or keeps caller memory past the call.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises unless stated ("sync" in the comment).
+ *   - return value 0 = ok, otherwise one of GCNB_E_*; gcnb_last_error() returns a
+ *     thread-local message for the last failing call on this thread.
+ *   - dense matrices are fp32 row-major with an explicit leading dimension in ELEMENTS.
+ *   - thread-safe: the only shared mutable state is inside a graph handle and is written
+ *     only by the build call that creates it.
+ */
+#ifndef GCNB200_H_
+#define GCNB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCNB_VERSION 100
+
+#define GCNB_OK 0
+#define GCNB_E_INVALID 1  /* bad argument (shape, null pointer, alignment, overflow)  */
+#define GCNB_E_CUDA 2     /* a CUDA runtime call failed; message has the CUDA error    */
+#define GCNB_E_NOMEM 3    /* device allocation failed                                  */
+#define GCNB_E_UNSUPPORTED 4
+
+typedef struct gcnb_graph gcnb_graph; /* opaque: CSR + CSR^T + row-length-binned schedule */
+
+int gcnb_version(void);
+const char* gcnb_last_error(void);
+/* 0 when the current device is compute capability 10.x (the only target of this build). */
+int gcnb_check_device(void);
+
+/* ------------------------------------------------------------------------------------
+ * Graph construction.  One-off per adjacency; the handle is reused by every layer call.
+ * ---------------------------------------------------------------------------------- */
+
+/* flags for gcnb_graph_from_edges */
+#define GCNB_BUILD_SYMMETRIZE 1    /* A <- max(A, A^T)                 pygcn/utils.py:365 */
+#define GCNB_BUILD_SELF_LOOPS 2    /* A <- A + I (fp64)                pygcn/utils.py:368 */
+#define GCNB_BUILD_ROW_NORMALIZE 4 /* A <- D^-1 A, fp64, inf -> 0      pygcn/utils.py:390-397 */
+#define GCNB_BUILD_CORA_PIPELINE 7
+
+/* Row-length bins of the schedule (deg = stored entries in the row):
+ *   0: deg == 0   1: 1..8   2: 9..32   3: 33..1024   4: > 1024 (split across warps)   */
+#define GCNB_NUM_BINS 5
+#define GCNB_BIN_EDGE_1 1
+#define GCNB_BIN_EDGE_2 9
+#define GCNB_BIN_EDGE_3 33
+#define GCNB_BIN_EDGE_4 1025
+
+/* Edge list -> normalised adjacency, on the device.  Replaces the Cora loader's graph
+ * statements pygcn/utils.py:360-368 (duplicate edges summed, symmetrise by element-wise
+ * max, + I), `normalize` (utils.py:390-397) and `sparse_mx_to_torch_sparse_tensor`
+ * (utils.py:407-414).  Stored entries come out row-major with ascending columns, values
+ * rounded fp64 -> fp32 exactly as `.astype(np.float32)` does.  sync. */
+int gcnb_graph_from_edges(int64_t n, int64_t n_edges, const int32_t* d_src, const int32_t* d_dst,
+                          int flags, void* stream, gcnb_graph** out);
+
+/* torch sparse COO adjacency (int64 indices [2,nnz] given as two rows, fp32 values), any
+ * order, duplicates allowed (they stay separate stored entries, which sums them exactly as
+ * torch.spmm does for an uncoalesced tensor).  Replaces the per-call coalesce / COO->CSR that
+ * `torch.spmm(adj, .)` (pygcn/layers.py:34) performs inside ATen.  sync. */
+int gcnb_graph_from_coo(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* d_row,
+                        const int64_t* d_col, const float* d_val, void* stream, gcnb_graph** out);
+
+/* torch sparse CSR adjacency (int64 crow [n_rows+1], int64 col [nnz]).  sync. */
+int gcnb_graph_from_csr(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* d_crow,
+                        const int64_t* d_col, const float* d_val, void* stream, gcnb_graph** out);
+
+/* Dense strided adjacency as the fork's live scripts pass it (pygcn/utils.py:124-132,
+ * policy-generator.py:339): non-zeros are scanned into CSR on the device.  sync. */
+int gcnb_graph_from_dense(int64_t n_rows, int64_t n_cols, const float* d_a, int64_t lda,
+                          void* stream, gcnb_graph** out);
+
+void gcnb_graph_free(gcnb_graph* g);
+
+typedef struct {
+  int64_t n_rows, n_cols, nnz;
+  int64_t bin_rows[GCNB_NUM_BINS]; /* rows per degree bin (forward CSR)            */
+  int64_t t_bin_rows[GCNB_NUM_BINS];
+  int64_t max_degree, t_max_degree;
+  int64_t n_long_chunks, t_n_long_chunks; /* work items the long-row bin was split into */
+  int32_t pattern_symmetric;       /* 1: CSR^T shares rowptr/col with CSR (values differ) */
+  int32_t reserved;
+  int64_t device_bytes;            /* HBM held by the handle                       */
+  const int32_t* d_rowptr;         /* [n_rows+1]                                   */
+  const int32_t* d_col;            /* [nnz]                                        */
+  const float* d_val;              /* [nnz]                                        */
+  const int32_t* d_t_rowptr;       /* [n_cols+1]  CSR of A^T                       */
+  const int32_t* d_t_col;          /* [nnz]                                        */
+  const float* d_t_val;            /* [nnz]                                        */
+} gcnb_graph_info;
+
+int gcnb_graph_get_info(const gcnb_graph* g, gcnb_graph_info* info);
+
+/* Write the adjacency in the exact layout `sparse_mx_to_torch_sparse_tensor` returns
+ * (pygcn/utils.py:407-414): d_indices int64 [2, nnz] (row 0 = row ids, row 1 = col ids),
+ * d_values fp32 [nnz], row-major / columns ascending. */
+int gcnb_graph_export_coo(const gcnb_graph* g, int64_t* d_indices, float* d_values, void* stream);
+
+/* Copy the device CSR (transpose = 0) or the CSR of A^T (transpose = 1) into caller
+ * buffers: d_rowptr int32 [rows+1], d_col int32 [nnz], d_val fp32 [nnz]. */
+int gcnb_graph_export_csr(const gcnb_graph* g, int transpose, int32_t* d_rowptr, int32_t* d_col,
+                          float* d_val, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Hot path kernels
+ * ---------------------------------------------------------------------------------- */
+
+#define GCNB_SPMM_TRANSPOSE 1 /* use A^T (backward of pygcn/layers.py:34)               */
+#define GCNB_SPMM_RELU 2      /* fuse the caller's F.relu (pygcn/models.py:49,53,56)    */
+
+/* out[r, 0:f] = sum_e val[e] * b[col[e], 0:f]  (+ bias[0:f]) (then max(.,0))
+ * `torch.spmm(adj, support)` + `output + self.bias` (pygcn/layers.py:34-36).
+ * d_bias may be NULL.  b is [n_cols, f] (or [n_rows, f] with TRANSPOSE), ld in elements. */
+int gcnb_spmm(const gcnb_graph* g, int flags, const float* d_b, int64_t ldb, int64_t f,
+              const float* d_bias, float* d_out, int64_t ldo, void* d_ws, size_t ws_bytes,
+              void* stream);
+/* scratch for the partial rows of the split long-row bin (0 when the graph has none) */
+size_t gcnb_spmm_workspace_bytes(const gcnb_graph* g, int flags, int64_t f);
+
+#define GCNB_GEMM_FP32 0    /* CUDA-core fp32 FMA (bit-faithful fp32 accumulate)          */
+#define GCNB_GEMM_TF32X3 1  /* tcgen05 kind::tf32, 3-term split: fp32-level accuracy      */
+#define GCNB_GEMM_AUTO 2    /* TF32X3 when the shape is tensor-core friendly, else FP32   */
+
+/* c[m,n] = sum_k A(i,k) B(k,j) with element (i,k) of A at d_a[i*a_rs + k*a_cs] and (k,j) of
+ * B at d_b[k*b_rs + j*b_cs]; c row-major with ldc.  Covers `torch.mm(input, weight)`
+ * (pygcn/layers.py:33) and both MmBackward products (dW = X^T dS, dX = dS W^T).
+ * d_ws / ws_bytes: scratch for split-K (see gcnb_gemm_workspace_bytes), may be NULL/0 when
+ * that returns 0. */
+int gcnb_gemm(int64_t m, int64_t n, int64_t k, const float* d_a, int64_t a_rs, int64_t a_cs,
+              const float* d_b, int64_t b_rs, int64_t b_cs, float* d_c, int64_t ldc, int precision,
+              void* d_ws, size_t ws_bytes, void* stream);
+size_t gcnb_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k, int precision);
+
+/* d_out[0:f] = sum_rows g[r, 0:f]  (AddBackward0 of `output + self.bias`, layers.py:36).
+ * If d_y != NULL the ReLU mask of the fused epilogue is applied first and the masked
+ * gradient is written to d_gm (may alias d_g):  gm = g * [y > 0]. */
+int gcnb_colsum(int64_t n_rows, int64_t f, const float* d_g, int64_t ldg, const float* d_y,
+                int64_t ldy, float* d_gm, int64_t ldgm, float* d_out, void* d_ws, size_t ws_bytes,
+                void* stream);
+size_t gcnb_colsum_workspace_bytes(int64_t n_rows, int64_t f);
+
+/* ------------------------------------------------------------------------------------
+ * Layer-level entry points: what GraphConvolution.forward / its autograd backward bind to.
+ * ---------------------------------------------------------------------------------- */
+
+#define GCNB_LAYER_RELU 1     /* fused ReLU epilogue + mask in backward */
+#define GCNB_LAYER_NEED_DX 2  /* compute dX (ctx.needs_input_grad[0])   */
+#define GCNB_LAYER_NEED_DW 4
+#define GCNB_LAYER_NEED_DB 8
+
+/* forward of pygcn/layers.py:32-38:  support = X W ; out = A support (+ bias) (relu)
+ *   d_x [n_cols, fin] ld ldx ; d_w [fin, fout] contiguous ; d_bias [fout] or NULL
+ *   d_support [n_cols, ld4(fout)] scratch, ld4(f) = 4*ceil(f/4) (rows stay 16-byte aligned)
+ *   d_out [n_rows, fout] contiguous ; d_ws: gcnb_layer_workspace_bytes() bytes */
+int gcnb_layer_forward(const gcnb_graph* g, const float* d_x, int64_t ldx, const float* d_w,
+                       const float* d_bias, int64_t fin, int64_t fout, int flags, int precision,
+                       float* d_support, float* d_out, void* d_ws, size_t ws_bytes, void* stream);
+
+/* backward: db = colsum(G) ; dS = A^T G ; dW = X^T dS ; dX = dS W^T
+ *   d_g [n_rows, fout] ld ldg ; d_y = forward output (only read with GCNB_LAYER_RELU)
+ *   d_ds [n_cols, ld4(fout)] scratch ; d_gm [n_rows, fout] scratch (only with RELU)
+ *   d_dw [fin, fout], d_db [fout], d_dx [n_cols, fin] ld lddx: written when requested */
+int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_t ldx, const float* d_w,
+                        const float* d_g, int64_t ldg, const float* d_y, int64_t fin, int64_t fout,
+                        int flags, int precision, float* d_gm, float* d_ds, float* d_dw,
+                        float* d_db, float* d_dx, int64_t lddx, void* d_ws, size_t ws_bytes,
+                        void* stream);
+size_t gcnb_layer_workspace_bytes(const gcnb_graph* g, int64_t fin, int64_t fout, int precision);
+
+/* L2 flush helper for benchmarks: writes `bytes` of d_buf. */
+int gcnb_l2_flush(void* d_buf, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCNB200_H_ */

@@ -1,0 +1,193 @@
+// extern "C" entry points of libgcnb200.so (see include/gcnb200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace gcnb {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+int gemm_dispatch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs, int64_t a_cs,
+                  const float* b, int64_t b_rs, int64_t b_cs, float* c, int64_t ldc, int precision,
+                  void* ws, size_t ws_bytes, cudaStream_t st) {
+  GCNB_REQUIRE(precision == GCNB_GEMM_FP32 || precision == GCNB_GEMM_TF32X3 || precision == GCNB_GEMM_AUTO,
+               "gemm: unknown precision %d", precision);
+  // The tcgen05 3xTF32 tier is dispatched here once enabled; until then every tier is the
+  // exact fp32 kernel (a superset of the accuracy contract).
+  return gemm_fp32_launch(m, n, k, a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, ws, ws_bytes, st);
+}
+
+size_t gemm_ws(int64_t m, int64_t n, int64_t k, int precision) {
+  (void)precision;
+  return gemm_fp32_workspace_bytes(m, n, k);
+}
+
+}  // namespace
+}  // namespace gcnb
+
+using namespace gcnb;
+
+extern "C" int gcnb_version(void) { return GCNB_VERSION; }
+
+extern "C" const char* gcnb_last_error(void) { return g_error; }
+
+extern "C" int gcnb_check_device(void) {
+  int dev = 0;
+  GCNB_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  GCNB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("libgcnb200 is built for sm_100a only; device %d has compute capability major %d", dev, major);
+    return GCNB_E_UNSUPPORTED;
+  }
+  return GCNB_OK;
+}
+
+extern "C" int gcnb_spmm(const gcnb_graph* g, int flags, const float* d_b, int64_t ldb, int64_t f,
+                         const float* d_bias, float* d_out, int64_t ldo, void* d_ws, size_t ws_bytes,
+                         void* stream) {
+  GCNB_REQUIRE(g != nullptr, "spmm: null graph");
+  const CsrView& v = (flags & GCNB_SPMM_TRANSPOSE) ? g->bwd : g->fwd;
+  return spmm_launch(v, d_b, ldb, f, d_bias, (flags & GCNB_SPMM_RELU) != 0, d_out, ldo, d_ws, ws_bytes,
+                     (cudaStream_t)stream);
+}
+
+extern "C" size_t gcnb_spmm_workspace_bytes(const gcnb_graph* g, int flags, int64_t f) {
+  if (!g) return 0;
+  const CsrView& v = (flags & GCNB_SPMM_TRANSPOSE) ? g->bwd : g->fwd;
+  return spmm_workspace_bytes(v, f);
+}
+
+extern "C" int gcnb_gemm(int64_t m, int64_t n, int64_t k, const float* d_a, int64_t a_rs, int64_t a_cs,
+                         const float* d_b, int64_t b_rs, int64_t b_cs, float* d_c, int64_t ldc,
+                         int precision, void* d_ws, size_t ws_bytes, void* stream) {
+  return gemm_dispatch(m, n, k, d_a, a_rs, a_cs, d_b, b_rs, b_cs, d_c, ldc, precision, d_ws, ws_bytes,
+                       (cudaStream_t)stream);
+}
+
+extern "C" size_t gcnb_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k, int precision) {
+  return gemm_ws(m, n, k, precision);
+}
+
+extern "C" int gcnb_colsum(int64_t n_rows, int64_t f, const float* d_g, int64_t ldg, const float* d_y,
+                           int64_t ldy, float* d_gm, int64_t ldgm, float* d_out, void* d_ws,
+                           size_t ws_bytes, void* stream) {
+  return colsum_launch(n_rows, f, d_g, ldg, d_y, ldy, d_gm, ldgm, d_out, d_ws, ws_bytes,
+                       (cudaStream_t)stream);
+}
+
+extern "C" size_t gcnb_colsum_workspace_bytes(int64_t n_rows, int64_t f) {
+  return colsum_workspace_bytes(n_rows, f);
+}
+
+// ------------------------------------------------------------------------ layer level
+
+extern "C" size_t gcnb_layer_workspace_bytes(const gcnb_graph* g, int64_t fin, int64_t fout, int precision) {
+  if (!g) return 0;
+  size_t a = spmm_workspace_bytes(g->fwd, fout);
+  size_t b = spmm_workspace_bytes(g->bwd, fout);
+  size_t s = a > b ? a : b;
+  size_t c = colsum_workspace_bytes(g->n_rows, fout);
+  size_t d0 = gemm_ws(g->n_cols, fout, fin, precision);  // X W
+  size_t d1 = gemm_ws(fin, fout, g->n_cols, precision);  // X^T dS
+  size_t d2 = gemm_ws(g->n_cols, fin, fout, precision);  // dS W^T
+  size_t d = d0 > d1 ? d0 : d1;
+  d = d > d2 ? d : d2;
+  // regions are used by different kernels of one call that run back to back on one stream,
+  // but colsum / spmm / gemm scratch never overlap in time with themselves only -- keep them
+  // disjoint to stay safe under future multi-stream use.
+  return align256(s) + align256(c) + align256(d) + 256;
+}
+
+extern "C" int gcnb_layer_forward(const gcnb_graph* g, const float* d_x, int64_t ldx, const float* d_w,
+                                  const float* d_bias, int64_t fin, int64_t fout, int flags, int precision,
+                                  float* d_support, float* d_out, void* d_ws, size_t ws_bytes,
+                                  void* stream) {
+  GCNB_REQUIRE(g != nullptr, "layer_forward: null graph");
+  GCNB_REQUIRE(fin > 0 && fout > 0, "layer_forward: bad feature sizes %lld -> %lld", (long long)fin, (long long)fout);
+  GCNB_REQUIRE(ldx >= fin, "layer_forward: ldx < in_features");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = reinterpret_cast<char*>(d_ws);
+  const size_t s_bytes = align256(spmm_workspace_bytes(g->fwd, fout));
+  const size_t d_bytes = gemm_ws(g->n_cols, fout, fin, precision);
+  GCNB_REQUIRE(ws_bytes >= s_bytes + d_bytes && (s_bytes + d_bytes == 0 || ws != nullptr),
+               "layer_forward: workspace too small");
+  // support = X W                                   (pygcn/layers.py:33)
+  const int64_t lds = ceil_div(fout, 4) * 4;
+  GCNB_TRY(gemm_dispatch(g->n_cols, fout, fin, d_x, ldx, 1, d_w, fout, 1, d_support, lds, precision,
+                         ws + s_bytes, d_bytes, st));
+  // out = A support (+ bias) (relu)                  (pygcn/layers.py:34-36, models.py:49)
+  return spmm_launch(g->fwd, d_support, lds, fout, d_bias, (flags & GCNB_LAYER_RELU) != 0, d_out, fout, ws,
+                     s_bytes, st);
+}
+
+extern "C" int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_t ldx, const float* d_w,
+                                   const float* d_g, int64_t ldg, const float* d_y, int64_t fin,
+                                   int64_t fout, int flags, int precision, float* d_gm, float* d_ds,
+                                   float* d_dw, float* d_db, float* d_dx, int64_t lddx, void* d_ws,
+                                   size_t ws_bytes, void* stream) {
+  GCNB_REQUIRE(g != nullptr, "layer_backward: null graph");
+  GCNB_REQUIRE(fin > 0 && fout > 0, "layer_backward: bad feature sizes");
+  GCNB_REQUIRE(ldg >= fout, "layer_backward: ldg < out_features");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool relu = (flags & GCNB_LAYER_RELU) != 0;
+  const bool need_dx = (flags & GCNB_LAYER_NEED_DX) != 0;
+  const bool need_dw = (flags & GCNB_LAYER_NEED_DW) != 0;
+  const bool need_db = (flags & GCNB_LAYER_NEED_DB) != 0;
+  GCNB_REQUIRE(!relu || (d_y != nullptr && d_gm != nullptr), "layer_backward: relu needs y and gm");
+  GCNB_REQUIRE(ws_bytes >= gcnb_layer_workspace_bytes(g, fin, fout, precision) && d_ws != nullptr,
+               "layer_backward: workspace too small");
+  char* ws = reinterpret_cast<char*>(d_ws);
+  const size_t s_bytes = align256(spmm_workspace_bytes(g->bwd, fout) > spmm_workspace_bytes(g->fwd, fout)
+                                      ? spmm_workspace_bytes(g->bwd, fout)
+                                      : spmm_workspace_bytes(g->fwd, fout));
+  const size_t c_bytes = align256(colsum_workspace_bytes(g->n_rows, fout));
+  void* ws_spmm = ws;
+  void* ws_col = ws + s_bytes;
+  void* ws_gemm = ws + s_bytes + c_bytes;
+  const size_t g_bytes = ws_bytes - s_bytes - c_bytes;
+
+  const float* gsrc = d_g;
+  int64_t gld = ldg;
+  // db = colsum(G) ; with the fused ReLU the mask is applied first: G <- G * [y > 0]
+  if (relu || need_db) {
+    float* db = d_db;
+    GCNB_REQUIRE(db != nullptr || !need_db, "layer_backward: db requested but null");
+    if (db == nullptr) db = reinterpret_cast<float*>(ws_gemm);  // discard
+    GCNB_TRY(colsum_launch(g->n_rows, fout, d_g, ldg, relu ? d_y : nullptr, fout, relu ? d_gm : nullptr,
+                           fout, db, ws_col, c_bytes, st));
+    if (relu) {
+      gsrc = d_gm;
+      gld = fout;
+    }
+  }
+  if (!need_dw && !need_dx) return GCNB_OK;
+  // dS = A^T G                                      (MmBackward0 of torch.spmm)
+  const int64_t lds = ceil_div(fout, 4) * 4;
+  GCNB_TRY(spmm_launch(g->bwd, gsrc, gld, fout, nullptr, false, d_ds, lds, ws_spmm, s_bytes, st));
+  // dW = X^T dS                                     (MmBackward0 of torch.mm)
+  if (need_dw) {
+    GCNB_REQUIRE(d_dw != nullptr, "layer_backward: dW requested but null");
+    GCNB_TRY(gemm_dispatch(fin, fout, g->n_cols, d_x, 1, ldx, d_ds, lds, 1, d_dw, fout, precision, ws_gemm,
+                           g_bytes, st));
+  }
+  // dX = dS W^T
+  if (need_dx) {
+    GCNB_REQUIRE(d_dx != nullptr && lddx >= fin, "layer_backward: dX requested but null / lddx < in_features");
+    GCNB_TRY(gemm_dispatch(g->n_cols, fin, fout, d_ds, lds, 1, d_w, 1, fout, d_dx, lddx, precision, ws_gemm,
+                           g_bytes, st));
+  }
+  return GCNB_OK;
+}

@@ -1,0 +1,94 @@
+// Shared helpers for libgcnb200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "gcnb200.h"
+
+namespace gcnb {
+
+void set_error(const char* fmt, ...);
+
+#define GCNB_CUDA(expr)                                                                     \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::gcnb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                        __LINE__);                                                          \
+      return (_e == cudaErrorMemoryAllocation) ? GCNB_E_NOMEM : GCNB_E_CUDA;                \
+    }                                                                                       \
+  } while (0)
+
+#define GCNB_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::gcnb::set_error(__VA_ARGS__);  \
+      return GCNB_E_INVALID;           \
+    }                                  \
+  } while (0)
+
+#define GCNB_TRY(expr)              \
+  do {                              \
+    int _s = (expr);                \
+    if (_s != GCNB_OK) return _s;   \
+  } while (0)
+
+#define GCNB_LAUNCH_CHECK() GCNB_CUDA(cudaGetLastError())
+
+constexpr int kNumSMs = 148;  // B200
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// One CSR (either the adjacency or its transpose) plus its row-length-binned schedule.
+struct CsrView {
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  const int32_t* rowptr = nullptr;
+  const int32_t* col = nullptr;
+  const float* val = nullptr;
+  // schedule: rows whose degree exceeds the long-row threshold are split into chunks of
+  // kLongChunk stored entries; each chunk is one warp work item writing a partial row.
+  int64_t n_long_rows = 0;
+  int64_t n_long_chunks = 0;
+  const int32_t* long_rows = nullptr;       // [n_long_rows] row ids (ascending)
+  const int32_t* long_chunk_ptr = nullptr;  // [n_long_rows+1] prefix of chunks per long row
+  int64_t max_degree = 0;
+  int64_t bin_rows[GCNB_NUM_BINS] = {0, 0, 0, 0, 0};
+};
+
+constexpr int kLongRowThreshold = GCNB_BIN_EDGE_4;  // deg >= this -> split
+constexpr int kLongChunk = 1024;
+
+int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const float* bias,
+                bool relu, float* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t spmm_workspace_bytes(const CsrView& a, int64_t f);
+
+int gemm_fp32_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs, int64_t a_cs,
+                     const float* b, int64_t b_rs, int64_t b_cs, float* c, int64_t ldc, void* ws,
+                     size_t ws_bytes, cudaStream_t stream);
+size_t gemm_fp32_workspace_bytes(int64_t m, int64_t n, int64_t k);
+
+int colsum_launch(int64_t n_rows, int64_t f, const float* g, int64_t ldg, const float* y,
+                  int64_t ldy, float* gm, int64_t ldgm, float* out, void* ws, size_t ws_bytes,
+                  cudaStream_t stream);
+size_t colsum_workspace_bytes(int64_t n_rows, int64_t f);
+
+}  // namespace gcnb
+
+struct gcnb_graph {
+  int device = 0;
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  int32_t* rowptr = nullptr;
+  int32_t* col = nullptr;
+  float* val = nullptr;
+  int32_t* t_rowptr = nullptr;  // may alias rowptr when the pattern is symmetric
+  int32_t* t_col = nullptr;     // may alias col
+  float* t_val = nullptr;
+  bool pattern_symmetric = false;
+  int32_t* long_rows = nullptr;
+  int32_t* long_chunk_ptr = nullptr;
+  int32_t* t_long_rows = nullptr;
+  int32_t* t_long_chunk_ptr = nullptr;
+  gcnb::CsrView fwd, bwd;
+  int64_t device_bytes = 0;
+};

@@ -1,0 +1,117 @@
+// Column sum of the upstream gradient (db of `output + self.bias`, pygcn/layers.py:36), with
+// the ReLU mask of the fused epilogue applied on the fly when requested, plus the L2 flush
+// helper the benchmark uses.  Two-phase deterministic reduction (no atomics).
+#include "common.cuh"
+
+namespace gcnb {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxBlocks = 4 * kNumSMs;
+
+// Phase 1: block b reduces rows [b*rows_per_block, ...) -> partial[b][0:f]
+__global__ void __launch_bounds__(kThreads)
+colsum_partial_kernel(int64_t n_rows, int f, int cw, int64_t rows_per_block,
+                      const float* __restrict__ g, int64_t ldg, const float* __restrict__ y,
+                      int64_t ldy, float* __restrict__ gm, int64_t ldgm,
+                      float* __restrict__ partial) {
+  __shared__ float red[kThreads];
+  const int tx = threadIdx.x % cw;  // column lane
+  const int ty = threadIdx.x / cw;  // row lane
+  const int rl = kThreads / cw;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = (r0 + rows_per_block < n_rows) ? (r0 + rows_per_block) : n_rows;
+  for (int j0 = 0; j0 < f; j0 += cw) {
+    const int j = j0 + tx;
+    float acc = 0.f;
+    if (j < f) {
+      for (int64_t r = r0 + ty; r < r1; r += rl) {
+        float v = g[r * ldg + j];
+        if (y != nullptr) {
+          v = (y[r * ldy + j] > 0.f) ? v : 0.f;
+          gm[r * ldgm + j] = v;
+        }
+        acc += v;
+      }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (ty == 0 && j < f) {
+      float s = 0.f;
+      for (int t = 0; t < rl; ++t) s += red[t * cw + tx];
+      partial[(int64_t)blockIdx.x * f + j] = s;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+colsum_final_kernel(int f, int n_blocks, const float* __restrict__ partial, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= f) return;
+  float s = 0.f;
+  for (int b = 0; b < n_blocks; ++b) s += partial[(int64_t)b * f + j];
+  out[j] = s;
+}
+
+__global__ void __launch_bounds__(kThreads) zero_kernel(float* out, int f) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < f) out[j] = 0.f;
+}
+
+__global__ void __launch_bounds__(kThreads) flush_kernel(float4* buf, size_t n4, float v) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+    buf[i] = make_float4(v, v, v, v);
+}
+
+int colsum_blocks(int64_t n_rows) {
+  int64_t b = ceil_div(n_rows, 64);
+  if (b > kMaxBlocks) b = kMaxBlocks;
+  return (int)(b < 1 ? 1 : b);
+}
+
+}  // namespace
+
+size_t colsum_workspace_bytes(int64_t n_rows, int64_t f) {
+  return (size_t)colsum_blocks(n_rows) * (size_t)f * sizeof(float);
+}
+
+int colsum_launch(int64_t n_rows, int64_t f, const float* g, int64_t ldg, const float* y,
+                  int64_t ldy, float* gm, int64_t ldgm, float* out, void* ws, size_t ws_bytes,
+                  cudaStream_t st) {
+  GCNB_REQUIRE(f > 0 && f < (1 << 24), "colsum: width out of range");
+  GCNB_REQUIRE(out != nullptr, "colsum: null output");
+  if (n_rows == 0) {
+    zero_kernel<<<(unsigned)ceil_div(f, kThreads), kThreads, 0, st>>>(out, (int)f);
+    GCNB_LAUNCH_CHECK();
+    return GCNB_OK;
+  }
+  GCNB_REQUIRE(g != nullptr && ldg >= f, "colsum: bad gradient operand");
+  GCNB_REQUIRE(y == nullptr || (gm != nullptr && ldy >= f && ldgm >= f), "colsum: bad mask operands");
+  const int nb = colsum_blocks(n_rows);
+  const size_t need = colsum_workspace_bytes(n_rows, f);
+  GCNB_REQUIRE(ws != nullptr && ws_bytes >= need, "colsum: workspace too small (%zu < %zu)", ws_bytes, need);
+  int cw = 32;
+  while (cw < f && cw < kThreads) cw <<= 1;
+  const int64_t rows_per_block = ceil_div(n_rows, nb);
+  colsum_partial_kernel<<<nb, kThreads, 0, st>>>(n_rows, (int)f, cw, rows_per_block, g, ldg, y, ldy, gm,
+                                                 ldgm, reinterpret_cast<float*>(ws));
+  GCNB_LAUNCH_CHECK();
+  colsum_final_kernel<<<(unsigned)ceil_div(f, kThreads), kThreads, 0, st>>>(
+      (int)f, nb, reinterpret_cast<const float*>(ws), out);
+  GCNB_LAUNCH_CHECK();
+  return GCNB_OK;
+}
+
+}  // namespace gcnb
+
+extern "C" int gcnb_l2_flush(void* d_buf, size_t bytes, void* stream) {
+  using namespace gcnb;
+  GCNB_REQUIRE(d_buf != nullptr && bytes >= 16, "l2_flush: bad buffer");
+  static unsigned tick = 0;
+  flush_kernel<<<4 * kNumSMs, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(d_buf),
+                                                              bytes / 16, (float)(++tick));
+  GCNB_LAUNCH_CHECK();
+  return GCNB_OK;
+}

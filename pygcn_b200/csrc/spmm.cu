@@ -1,0 +1,350 @@
+// CSR SpMM for the GCN layer:  out = A * B (+ bias) (ReLU)     -- pygcn/layers.py:34-36,
+// and, on the CSR of A^T, the backward product dS = A^T * G     -- SURVEY.md 3.2.
+//
+// HBM/L2-bound gather kernel, no tensor cores (the work is nnz*F FMAs on gathered rows):
+//   * one warp per row for rows below the long-row threshold; the warp's 32 lanes are split
+//     into G = 32/LPR "slots" of LPR lanes, every slot gathers a different stored entry's
+//     feature row with 128-bit loads (LPR = lanes needed to cover F floats as float4),
+//     so one LDG.128 instruction moves G feature rows;
+//   * col/val of 32 stored entries are fetched with one coalesced load per lane and
+//     broadcast with shuffles;
+//   * rows in the long bin (deg >= GCNB_BIN_EDGE_4) are split into chunks of kLongChunk
+//     entries, one warp per chunk writes a partial row to scratch, a fix-up kernel adds the
+//     partials in chunk order (atomic-free, run-to-run deterministic);
+//   * bias add and ReLU are fused in the epilogue.
+#include "common.cuh"
+
+namespace gcnb {
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+__device__ __forceinline__ void fma4(float4& acc, float v, const float4& x) {
+  acc.x = fmaf(v, x.x, acc.x);
+  acc.y = fmaf(v, x.y, acc.y);
+  acc.z = fmaf(v, x.z, acc.z);
+  acc.w = fmaf(v, x.w, acc.w);
+}
+
+// U gathered rows per lane in flight: all loads are issued before the first FMA (memory-level
+// parallelism is what this kernel lives on).  Entry s = (j + u) * G + slot of the current block
+// of 32; lanes past the end of the row carry v = 0 / c = 0 and are never asked for here.
+template <int LPR, int CH, int U>
+__device__ __forceinline__ void gather_batch(float4 (&acc)[CH], int c, float v, int j, int slot,
+                                             const float* __restrict__ b, const int (&qoff)[CH],
+                                             int64_t ldb) {
+  constexpr int G = 32 / LPR;
+  int cc[U];
+  float vv[U];
+  float4 x[U][CH];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int s = (j + u) * G + slot;
+    cc[u] = __shfl_sync(kFull, c, s);
+    vv[u] = __shfl_sync(kFull, v, s);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const float* rowp = b + (int64_t)cc[u] * ldb;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) x[u][k] = ldg_f4(rowp + qoff[k]);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+#pragma unroll
+    for (int k = 0; k < CH; ++k) fma4(acc[k], vv[u], x[u][k]);
+}
+
+// Accumulate stored entries [start, end) of one row into acc (per-lane partial sums).
+// LPR lanes cover one gathered row; CH float4 chunks per lane (CH > 1 only when LPR == 32).
+// Lanes whose float4 index is past the row width read a clamped (valid) address and build a
+// value that is never stored.
+template <int LPR, int CH>
+__device__ __forceinline__ void accumulate_range(float4 (&acc)[CH], int start, int end,
+                                                 const int32_t* __restrict__ col,
+                                                 const float* __restrict__ val,
+                                                 const float* __restrict__ b, int64_t ldb, int f4,
+                                                 int lane) {
+  constexpr int G = 32 / LPR;
+  constexpr int U = (LPR * CH >= 64) ? (8 / CH > 0 ? 8 / CH : 1) : (LPR < 8 ? LPR : 8);
+  const int slot = lane / LPR;
+  const int sub = lane % LPR;
+  // chunk k of this lane is float4 index k*LPR + sub; clamp so that every chunk is readable
+  int qoff[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) qoff[k] = 4 * min(k * LPR + sub, f4 - 1);
+  int c = 0;
+  float v = 0.f;
+  if (start + lane < end) {
+    c = __ldg(col + start + lane);
+    v = __ldg(val + start + lane);
+  }
+  for (int base = start; base < end; base += 32) {
+    // prefetch the next block of 32 (col, val) pairs while this one is consumed
+    int cn = 0;
+    float vn = 0.f;
+    if (base + 32 + lane < end) {
+      cn = __ldg(col + base + 32 + lane);
+      vn = __ldg(val + base + 32 + lane);
+    }
+    const int cnt = min(32, end - base);
+    const int jmax = (cnt + G - 1) / G;  // entries past cnt have v = 0, c = 0: harmless
+    int j = 0;
+    for (; j + U <= jmax; j += U) gather_batch<LPR, CH, U>(acc, c, v, j, slot, b, qoff, ldb);
+    if (U > 4 && j + 4 <= jmax) { gather_batch<LPR, CH, (U > 4 ? 4 : 1)>(acc, c, v, j, slot, b, qoff, ldb); j += 4; }
+    if (U > 2 && j + 2 <= jmax) { gather_batch<LPR, CH, (U > 2 ? 2 : 1)>(acc, c, v, j, slot, b, qoff, ldb); j += 2; }
+    if (U > 1 && j < jmax) { gather_batch<LPR, CH, 1>(acc, c, v, j, slot, b, qoff, ldb); j += 1; }
+    c = cn;
+    v = vn;
+  }
+}
+
+template <int LPR, int CH>
+__device__ __forceinline__ void reduce_slots(float4 (&acc)[CH]) {
+#pragma unroll
+  for (int off = LPR; off < 32; off <<= 1) {
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      acc[k].x += __shfl_xor_sync(kFull, acc[k].x, off);
+      acc[k].y += __shfl_xor_sync(kFull, acc[k].y, off);
+      acc[k].z += __shfl_xor_sync(kFull, acc[k].z, off);
+      acc[k].w += __shfl_xor_sync(kFull, acc[k].w, off);
+    }
+  }
+}
+
+__device__ __forceinline__ void store_row_chunk(float* out_row, int q, int f, bool vec_out,
+                                                float4 a, const float* __restrict__ bias,
+                                                bool relu) {
+  float r[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int c = 4 * q + t;
+    if (c < f) {
+      if (bias) r[t] += __ldg(bias + c);
+      if (relu) r[t] = fmaxf(r[t], 0.f);
+    }
+  }
+  if (vec_out) {
+    *reinterpret_cast<float4*>(out_row + 4 * q) = make_float4(r[0], r[1], r[2], r[3]);
+  } else {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (4 * q + t < f) out_row[4 * q + t] = r[t];
+  }
+}
+
+// One warp per row.  Rows of the long bin are skipped when skip_long is set.
+template <int LPR, int CH>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+spmm_rows_vec_kernel(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                     const float* __restrict__ val, const float* __restrict__ b, int64_t ldb, int f,
+                     const float* __restrict__ bias, int relu, float* __restrict__ out, int64_t ldo,
+                     int vec_out, int skip_long) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int start = __ldg(rowptr + row);
+  const int end = __ldg(rowptr + row + 1);
+  if (skip_long && end - start >= kLongRowThreshold) return;
+  const int f4 = (f + 3) >> 2;
+  float4 acc[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  accumulate_range<LPR, CH>(acc, start, end, col, val, b, ldb, f4, lane);
+  reduce_slots<LPR, CH>(acc);
+  if (lane < LPR) {
+    float* out_row = out + (int64_t)row * ldo;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int q = k * LPR + lane;
+      if (q < f4) store_row_chunk(out_row, q, f, vec_out, acc[k], bias, relu);
+    }
+  }
+}
+
+// Long-row bin, phase 1: one warp per chunk of kLongChunk stored entries -> partial row.
+template <int LPR, int CH>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+spmm_long_partial_kernel(int n_long_rows, int n_chunks, const int32_t* __restrict__ long_rows,
+                         const int32_t* __restrict__ long_chunk_ptr,
+                         const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                         const float* __restrict__ val, const float* __restrict__ b, int64_t ldb,
+                         int f, float* __restrict__ partial, int ldp) {
+  const int lane = threadIdx.x & 31;
+  const int ch = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (ch >= n_chunks) return;
+  int lo = 0, hi = n_long_rows;  // last li with long_chunk_ptr[li] <= ch
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(long_chunk_ptr + mid) <= ch) lo = mid; else hi = mid;
+  }
+  const int row = __ldg(long_rows + lo);
+  const int local = ch - __ldg(long_chunk_ptr + lo);
+  const int row_start = __ldg(rowptr + row);
+  const int row_end = __ldg(rowptr + row + 1);
+  const int start = row_start + local * kLongChunk;
+  const int end = min(start + kLongChunk, row_end);
+  const int f4 = (f + 3) >> 2;
+  float4 acc[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  accumulate_range<LPR, CH>(acc, start, end, col, val, b, ldb, f4, lane);
+  reduce_slots<LPR, CH>(acc);
+  if (lane < LPR) {
+    float* prow = partial + (int64_t)ch * ldp;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int q = k * LPR + lane;
+      if (q < f4) *reinterpret_cast<float4*>(prow + 4 * q) = acc[k];
+    }
+  }
+}
+
+// Long-row bin, phase 2: one warp per long row adds its partial rows in chunk order.
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+spmm_long_fixup_kernel(int n_long_rows, const int32_t* __restrict__ long_rows,
+                       const int32_t* __restrict__ long_chunk_ptr, const float* __restrict__ partial,
+                       int ldp, int f, const float* __restrict__ bias, int relu,
+                       float* __restrict__ out, int64_t ldo) {
+  const int lane = threadIdx.x & 31;
+  const int li = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (li >= n_long_rows) return;
+  const int row = __ldg(long_rows + li);
+  const int c0 = __ldg(long_chunk_ptr + li);
+  const int c1 = __ldg(long_chunk_ptr + li + 1);
+  for (int j = lane; j < f; j += 32) {
+    float acc = 0.f;
+    for (int c = c0; c < c1; ++c) acc += partial[(int64_t)c * ldp + j];
+    if (bias) acc += __ldg(bias + j);
+    if (relu) acc = fmaxf(acc, 0.f);
+    out[(int64_t)row * ldo + j] = acc;
+  }
+}
+
+// Fully generic fallback: any f / ld / alignment.  One warp per row, lanes over columns.
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+spmm_rows_scalar_kernel(int n_rows, const int32_t* __restrict__ rowptr,
+                        const int32_t* __restrict__ col, const float* __restrict__ val,
+                        const float* __restrict__ b, int64_t ldb, int f,
+                        const float* __restrict__ bias, int relu, float* __restrict__ out,
+                        int64_t ldo) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int start = __ldg(rowptr + row);
+  const int end = __ldg(rowptr + row + 1);
+  for (int f0 = 0; f0 < f; f0 += 32) {
+    const int j = f0 + lane;
+    float acc = 0.f;
+    for (int base = start; base < end; base += 32) {
+      const int e = base + lane;
+      int c = 0;
+      float v = 0.f;
+      if (e < end) {
+        c = __ldg(col + e);
+        v = __ldg(val + e);
+      }
+      const int cnt = min(32, end - base);
+      for (int s = 0; s < cnt; ++s) {
+        const int cc = __shfl_sync(kFull, c, s);
+        const float vv = __shfl_sync(kFull, v, s);
+        if (j < f) acc = fmaf(vv, __ldg(b + (int64_t)cc * ldb + j), acc);
+      }
+    }
+    if (j < f) {
+      if (bias) acc += __ldg(bias + j);
+      if (relu) acc = fmaxf(acc, 0.f);
+      out[(int64_t)row * ldo + j] = acc;
+    }
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <int LPR, int CH>
+int launch_vec(const CsrView& a, const float* b, int64_t ldb, int f, const float* bias, bool relu,
+               float* out, int64_t ldo, bool vec_out, float* partial, int ldp, cudaStream_t st) {
+  const bool has_long = a.n_long_rows > 0;
+  const int grid = (int)ceil_div(a.n_rows, kWarpsPerCta);
+  if (grid > 0) {
+    spmm_rows_vec_kernel<LPR, CH><<<grid, kWarpsPerCta * 32, 0, st>>>(
+        (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, f, bias, relu ? 1 : 0, out, ldo,
+        vec_out ? 1 : 0, has_long ? 1 : 0);
+    GCNB_LAUNCH_CHECK();
+  }
+  if (has_long) {
+    const int g1 = (int)ceil_div(a.n_long_chunks, kWarpsPerCta);
+    spmm_long_partial_kernel<LPR, CH><<<g1, kWarpsPerCta * 32, 0, st>>>(
+        (int)a.n_long_rows, (int)a.n_long_chunks, a.long_rows, a.long_chunk_ptr, a.rowptr, a.col,
+        a.val, b, ldb, f, partial, ldp);
+    GCNB_LAUNCH_CHECK();
+    const int g2 = (int)ceil_div(a.n_long_rows, kWarpsPerCta);
+    spmm_long_fixup_kernel<<<g2, kWarpsPerCta * 32, 0, st>>>(
+        (int)a.n_long_rows, a.long_rows, a.long_chunk_ptr, partial, ldp, f, bias, relu ? 1 : 0, out,
+        ldo);
+    GCNB_LAUNCH_CHECK();
+  }
+  return GCNB_OK;
+}
+
+inline int partial_ld(int64_t f) { return (int)(ceil_div(f, 4) * 4); }
+
+}  // namespace
+
+size_t spmm_workspace_bytes(const CsrView& a, int64_t f) {
+  if (a.n_long_chunks == 0) return 0;
+  return (size_t)a.n_long_chunks * (size_t)partial_ld(f) * sizeof(float);
+}
+
+int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const float* bias,
+                bool relu, float* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st) {
+  GCNB_REQUIRE(f > 0 && f <= (1 << 20), "spmm: feature width %lld out of range", (long long)f);
+  GCNB_REQUIRE(ldb >= f && ldo >= f, "spmm: leading dimension smaller than width");
+  GCNB_REQUIRE(a.n_rows < (1ll << 31), "spmm: too many rows");
+  if (a.n_rows == 0) return GCNB_OK;
+  GCNB_REQUIRE(b != nullptr && out != nullptr, "spmm: null operand");
+  const size_t need = spmm_workspace_bytes(a, f);
+  GCNB_REQUIRE(need == 0 || (ws != nullptr && ws_bytes >= need && aligned16(ws)),
+               "spmm: workspace too small (%zu < %zu) or unaligned", ws_bytes, need);
+  float* partial = reinterpret_cast<float*>(ws);
+  const int ldp = partial_ld(f);
+  const int f4 = (int)ceil_div(f, 4);
+  // vector gathers need 16-byte aligned rows of b that are readable up to f4*4 floats
+  const bool vec_in = aligned16(b) && (ldb % 4 == 0) && (ldb >= (int64_t)f4 * 4);
+  const bool vec_out = aligned16(out) && (ldo % 4 == 0) && (f % 4 == 0);
+  if (!vec_in) {
+    // generic path handles long rows too (a warp walks the whole row)
+    const int grid = (int)ceil_div(a.n_rows, kWarpsPerCta);
+    spmm_rows_scalar_kernel<<<grid, kWarpsPerCta * 32, 0, st>>>(
+        (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, (int)f, bias, relu ? 1 : 0, out, ldo);
+    GCNB_LAUNCH_CHECK();
+    return GCNB_OK;
+  }
+#define GCNB_SPMM_CASE(LPR, CH) \
+  return launch_vec<LPR, CH>(a, b, ldb, (int)f, bias, relu, out, ldo, vec_out, partial, ldp, st)
+  if (f4 <= 1) GCNB_SPMM_CASE(1, 1);
+  if (f4 <= 2) GCNB_SPMM_CASE(2, 1);
+  if (f4 <= 4) GCNB_SPMM_CASE(4, 1);
+  if (f4 <= 8) GCNB_SPMM_CASE(8, 1);
+  if (f4 <= 16) GCNB_SPMM_CASE(16, 1);
+  if (f4 <= 32) GCNB_SPMM_CASE(32, 1);
+  if (f4 <= 64) GCNB_SPMM_CASE(32, 2);
+  if (f4 <= 128) GCNB_SPMM_CASE(32, 4);
+#undef GCNB_SPMM_CASE
+  // wider than 512 floats: column panels of 512
+  for (int64_t f0 = 0; f0 < f; f0 += 512) {
+    const int64_t fw = (f - f0 < 512) ? (f - f0) : 512;
+    GCNB_TRY(spmm_launch(a, b + f0, ldb, fw, bias ? bias + f0 : nullptr, relu, out + f0, ldo, ws,
+                         ws_bytes, st));
+  }
+  return GCNB_OK;
+}
+
+}  // namespace gcnb

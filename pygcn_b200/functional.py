@@ -1,0 +1,218 @@
+"""autograd wrappers around the C ABI: the GCN layer and the `torch.spmm` drop-in.
+
+Forward  : pygcn/layers.py:32-38   support = mm(input, W); out = spmm(adj, support) (+ bias)
+Backward : the autograd graph of those lines, hand-written here:
+           db = colsum(G); dS = adj^T G; dW = X^T dS; dX = dS W^T  (only what
+           ctx.needs_input_grad asks for).
+All arithmetic happens in libgcnb200.so on the current CUDA stream; nothing here falls back
+to PyTorch ops.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from .graph import Graph, _require_cuda, _stream_ptr, as_graph
+
+_PRECISIONS = {"fp32": _lib.GEMM_FP32, "tf32x3": _lib.GEMM_TF32X3, "auto": _lib.GEMM_AUTO}
+
+
+def _ld4(f):
+    return (f + 3) // 4 * 4
+
+
+def _rowmajor(t):
+    """fp32 2-D tensor with unit column stride (row stride may exceed the width:
+    the fork passes column-slice views, pygcn/models.py:345)."""
+    if t.dim() != 2:
+        raise RuntimeError("expected a 2-D tensor, got %d-D" % t.dim())
+    if t.dtype != torch.float32:
+        raise RuntimeError("expected float32, got %s" % t.dtype)
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    if t.shape[0] > 1 and t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
+def _ld(t):
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+
+
+def _ws(nbytes, device):
+    return torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=device)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class _GCNLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, graph, relu, precision):
+        lib = _lib.load()
+        dev = x.device
+        fin, fout = weight.shape
+        xr = _rowmajor(x)
+        w = weight.contiguous()
+        b = bias.contiguous() if bias is not None else None
+        support = torch.empty((graph.n_cols, _ld4(fout)), dtype=torch.float32, device=dev)
+        out = torch.empty((graph.n_rows, fout), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nws = lib.gcnb_layer_workspace_bytes(graph._h, fin, fout, precision)
+            ws = _ws(nws, dev)
+            st = lib.gcnb_layer_forward(
+                graph._h, _ptr(xr), _ld(xr), _ptr(w), _ptr(b), fin, fout, _lib.LAYER_RELU if relu else 0, precision,
+                _ptr(support), _ptr(out), _ptr(ws), ws.numel(), _stream_ptr(dev),
+            )
+        _lib.check(st, "gcnb_layer_forward")
+        ctx.graph = graph
+        ctx.relu = relu
+        ctx.precision = precision
+        ctx.has_bias = bias is not None
+        ctx.x_shape = tuple(x.shape)
+        ctx.save_for_backward(xr, w, out if relu else None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        lib = _lib.load()
+        xr, w, y = ctx.saved_tensors
+        graph = ctx.graph
+        dev = g.device
+        fin, fout = w.shape
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_db = ctx.has_bias and ctx.needs_input_grad[2]
+        gr = _rowmajor(g)
+        flags = (_lib.LAYER_RELU if ctx.relu else 0) | (_lib.LAYER_NEED_DX if need_dx else 0) | (
+            _lib.LAYER_NEED_DW if need_dw else 0) | (_lib.LAYER_NEED_DB if need_db else 0)
+        ds = torch.empty((graph.n_cols, _ld4(fout)), dtype=torch.float32, device=dev)
+        gm = torch.empty((graph.n_rows, fout), dtype=torch.float32, device=dev) if ctx.relu else None
+        dw = torch.empty((fin, fout), dtype=torch.float32, device=dev) if need_dw else None
+        db = torch.empty((fout,), dtype=torch.float32, device=dev) if need_db else None
+        dx = torch.empty((graph.n_cols, fin), dtype=torch.float32, device=dev) if need_dx else None
+        with torch.cuda.device(dev):
+            nws = lib.gcnb_layer_workspace_bytes(graph._h, fin, fout, ctx.precision)
+            ws = _ws(nws, dev)
+            st = lib.gcnb_layer_backward(
+                graph._h, _ptr(xr), _ld(xr), _ptr(w), _ptr(gr), _ld(gr), _ptr(y), fin, fout, flags, ctx.precision,
+                _ptr(gm), _ptr(ds), _ptr(dw), _ptr(db), _ptr(dx), fin, _ptr(ws), ws.numel(), _stream_ptr(dev),
+            )
+        _lib.check(st, "gcnb_layer_backward")
+        return dx, dw, db, None, None, None
+
+
+def _check_layer_args(x, graph, weight, bias):
+    _require_cuda(x, "input")
+    _require_cuda(weight, "weight")
+    if x.dim() != 2 or weight.dim() != 2:
+        raise RuntimeError("input and weight must be matrices")
+    if x.shape[1] != weight.shape[0]:
+        raise RuntimeError(
+            "mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)" % (*x.shape, *weight.shape)
+        )
+    if x.shape[0] != graph.n_cols:
+        raise RuntimeError(
+            "size mismatch: adj is %dx%d but input has %d rows" % (graph.n_rows, graph.n_cols, x.shape[0])
+        )
+    if x.dtype != torch.float32 or weight.dtype != torch.float32:
+        raise RuntimeError("expected float32 input and weight (the reference layer is fp32)")
+    if x.device != graph.device or weight.device != graph.device:
+        raise RuntimeError("input (%s), weight (%s) and adj (%s) must be on the same device" %
+                           (x.device, weight.device, graph.device))
+    if bias is not None:
+        if bias.shape != (weight.shape[1],) or bias.dtype != torch.float32 or bias.device != graph.device:
+            raise RuntimeError("bias must be a float32 [%d] tensor on %s" % (weight.shape[1], graph.device))
+
+
+def gcn_layer(input, adj, weight, bias=None, relu=False, precision="fp32"):
+    """`adj @ (input @ weight) + bias` (optionally followed by ReLU) -- pygcn/layers.py:32-38.
+
+    adj: torch sparse COO / sparse CSR / dense tensor, or a `Graph`.
+    relu=True fuses the `F.relu` the reference's models apply to every layer output
+    (pygcn/models.py:49,53,56); applying F.relu again on the result is a no-op, so unchanged
+    callers stay correct.
+    """
+    graph = as_graph(adj)
+    _check_layer_args(input, graph, weight, bias)
+    return _GCNLayerFn.apply(input, weight, bias, graph, bool(relu), _PRECISIONS[precision])
+
+
+class _SpmmFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dense, graph):
+        lib = _lib.load()
+        dev = dense.device
+        d = _rowmajor(dense)
+        f = d.shape[1]
+        out = torch.empty((graph.n_rows, f), dtype=torch.float32, device=dev)
+        if f == 0 or graph.n_rows == 0:
+            ctx.graph = graph
+            return out
+        with torch.cuda.device(dev):
+            ws = _ws(lib.gcnb_spmm_workspace_bytes(graph._h, 0, f), dev)
+            st = lib.gcnb_spmm(graph._h, 0, _ptr(d), _ld(d), f, None, _ptr(out), f, _ptr(ws), ws.numel(),
+                               _stream_ptr(dev))
+        _lib.check(st, "gcnb_spmm")
+        ctx.graph = graph
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        lib = _lib.load()
+        graph = ctx.graph
+        dev = g.device
+        gr = _rowmajor(g)
+        f = gr.shape[1]
+        out = torch.empty((graph.n_cols, f), dtype=torch.float32, device=dev)
+        if f == 0 or graph.n_cols == 0:
+            return out, None
+        with torch.cuda.device(dev):
+            ws = _ws(lib.gcnb_spmm_workspace_bytes(graph._h, _lib.SPMM_TRANSPOSE, f), dev)
+            st = lib.gcnb_spmm(graph._h, _lib.SPMM_TRANSPOSE, _ptr(gr), _ld(gr), f, None, _ptr(out), f, _ptr(ws),
+                               ws.numel(), _stream_ptr(dev))
+        _lib.check(st, "gcnb_spmm(transpose)")
+        return out, None
+
+
+def spmm(adj, dense):
+    """Drop-in for `torch.spmm(adj, dense)` as the layer uses it (pygcn/layers.py:34).
+
+    Differentiable w.r.t. `dense`; `adj` never requires grad in the reference.
+    """
+    graph = as_graph(adj)
+    _require_cuda(dense, "dense")
+    if isinstance(adj, torch.Tensor) and adj.requires_grad:
+        raise NotImplementedError("gradients w.r.t. the adjacency are not part of the GCN hot path")
+    if dense.dim() != 2 or dense.shape[0] != graph.n_cols:
+        raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %s)" %
+                           (graph.n_rows, graph.n_cols, "x".join(str(s) for s in dense.shape)))
+    if dense.dtype != torch.float32:
+        raise RuntimeError("expected float32 dense operand, got %s" % dense.dtype)
+    if dense.device != graph.device:
+        raise RuntimeError("adj (%s) and dense (%s) must be on the same device" % (graph.device, dense.device))
+    return _SpmmFn.apply(dense, graph)
+
+
+def mm(a, b, precision="fp32"):
+    """`torch.mm(a, b)` through gcnb_gemm (no autograd); used by tests and the benchmark."""
+    lib = _lib.load()
+    _require_cuda(a, "a")
+    _require_cuda(b, "b")
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[0]:
+        raise RuntimeError("mat1 and mat2 shapes cannot be multiplied")
+    m, k = a.shape
+    n = b.shape[1]
+    out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    prec = _PRECISIONS[precision]
+    with torch.cuda.device(a.device):
+        ws = _ws(lib.gcnb_gemm_workspace_bytes(m, n, k, prec), a.device)
+        st = lib.gcnb_gemm(m, n, k, _ptr(a), a.stride(0), a.stride(1), _ptr(b), b.stride(0), b.stride(1), _ptr(out),
+                           max(n, 1), prec, _ptr(ws), ws.numel(), _stream_ptr(a.device))
+    _lib.check(st, "gcnb_gemm")
+    return out

@@ -1,0 +1,53 @@
+"""Drop-in for `pygcn/layers.py::GraphConvolution` backed by libgcnb200.so.
+
+Same constructor, attribute and parameter names (`weight` [in, out], `bias` [out]),
+same initialisation calls in the same RNG order (pygcn/layers.py:23-29), same `forward(input,
+adj)` contract and `__repr__` (pygcn/layers.py:40-43), so `models.GCN`, `GeneratorGCN`, ...
+(pygcn/models.py:17-177) and state dicts / whole-model pickles keep working.  The arithmetic
+of forward and backward runs in hand-written sm_100a kernels; CPU tensors raise.
+"""
+import math
+
+import torch
+from torch.nn.modules.module import Module
+from torch.nn.parameter import Parameter
+
+from .functional import gcn_layer
+
+
+class GraphConvolution(Module):
+    """GCN layer `adj @ (input @ weight) + bias` (https://arxiv.org/abs/1609.02907).
+
+    Extra keyword-only options (defaults reproduce the reference exactly):
+      fuse_relu  -- apply the ReLU every caller in pygcn/models.py applies, inside the SpMM
+                    epilogue (a following F.relu is then a no-op, results are identical)
+      precision  -- "fp32" (default), "tf32x3" or "auto" for the dense products
+    """
+
+    def __init__(self, in_features, out_features, bias=True, *, fuse_relu=False, precision="fp32"):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.fuse_relu = fuse_relu
+        self.precision = precision
+        self.weight = Parameter(torch.empty(in_features, out_features, dtype=torch.float32))
+        if bias:
+            self.bias = Parameter(torch.empty(out_features, dtype=torch.float32))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        # same two draws, same order, same bounds as pygcn/layers.py:23-29:
+        # kaiming_uniform_ on a [in, out] tensor takes fan_in = size(1) = out_features
+        bound = 1.0 / math.sqrt(self.weight.size(1))
+        torch.nn.init.kaiming_uniform_(self.weight)
+        if self.bias is not None:
+            self.bias.data.uniform_(-bound, bound)
+
+    def forward(self, input, adj):
+        return gcn_layer(input, adj, self.weight, self.bias,
+                         relu=getattr(self, "fuse_relu", False), precision=getattr(self, "precision", "fp32"))
+
+    def __repr__(self):
+        return "%s (%s -> %s)" % (self.__class__.__name__, self.in_features, self.out_features)

@@ -1,0 +1,118 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol the header
+declares; the host-side mirror of the reference interface behaves like the reference's
+(init draws, repr, state-dict keys, pickling under the module path `layers`, error
+behaviour on CPU tensors).  No kernel is launched here."""
+import io
+import os
+import pickle
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pygcn_b200 import _lib
+
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from pygcn_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "gcnb200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(gcnb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libgcnb200.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.gcnb_version() == int(re.search(r"#define GCNB_VERSION (\d+)", header).group(1))
+
+
+def test_library_is_sm100a_with_lineinfo():
+    from pygcn_b200 import _lib
+
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_header_constants_match_binding():
+    from pygcn_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "gcnb200.h")).read()
+    consts = dict(re.findall(r"#define (GCNB_[A-Z0-9_]+) (\d+)", header))
+    assert int(consts["GCNB_NUM_BINS"]) == _lib.NUM_BINS
+    assert tuple(int(consts["GCNB_BIN_EDGE_%d" % i]) for i in range(1, 5)) == _lib.BIN_EDGES[1:]
+    assert int(consts["GCNB_SPMM_TRANSPOSE"]) == _lib.SPMM_TRANSPOSE and int(consts["GCNB_SPMM_RELU"]) == _lib.SPMM_RELU
+    assert int(consts["GCNB_LAYER_NEED_DB"]) == _lib.LAYER_NEED_DB
+    # the oracle's schedule bins use the same edges
+    from oracle import gcn_oracle as O
+    import inspect
+
+    assert inspect.signature(O.degree_bins).parameters["edges"].default == _lib.BIN_EDGES
+
+
+def test_init_draws_match_reference(golden):
+    import pygcn_b200 as P
+
+    g = golden("init.npz")
+    torch.manual_seed(42)
+    gc = P.GraphConvolution(64, 32)
+    assert np.array_equal(gc.weight.detach().numpy(), g["w_64_32"])
+    assert np.array_equal(gc.bias.detach().numpy(), g["b_64_32"])
+    assert repr(gc) == str(g["repr"])
+    assert sorted(gc.state_dict().keys()) == list(g["state_keys"])
+    torch.manual_seed(42)
+    stack = [P.GraphConvolution(8, 32), P.GraphConvolution(32, 32), P.GraphConvolution(32, 32, bias=False)]
+    for i, gg in enumerate(stack):
+        assert np.array_equal(gg.weight.detach().numpy(), g["stack_w%d" % i])
+        if gg.bias is not None:
+            assert np.array_equal(gg.bias.detach().numpy(), g["stack_b%d" % i])
+    assert stack[2].bias is None and "bias" in dict(stack[2].named_parameters(recurse=False)) or stack[2].bias is None
+
+
+def test_cpu_tensors_raise_not_fallback():
+    import pygcn_b200 as P
+
+    gc = P.GraphConvolution(4, 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gc(torch.zeros(5, 4), torch.eye(5))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.spmm(torch.eye(5).to_sparse(), torch.zeros(5, 2))
+    with pytest.raises(TypeError):
+        P.spmm([[1.0]], torch.zeros(1, 1))
+
+
+def test_whole_model_pickle_under_reference_module_path():
+    import pygcn_b200 as P
+
+    mod = P.install_as_pygcn()
+    assert sys.modules["layers"] is mod
+    import layers  # what pygcn/models.py:4 does
+
+    gc = layers.GraphConvolution(5, 2)
+    buf = io.BytesIO()
+    torch.save(gc, buf)  # gnn-over-mlp.py:489 saves whole modules
+    buf.seek(0)
+    back = torch.load(buf, weights_only=False)
+    assert isinstance(back, P.GraphConvolution) and torch.equal(back.weight, gc.weight)
+    # a state dict from the reference layer loads (same keys / shapes)
+    sd = {"weight": torch.ones(5, 2), "bias": torch.zeros(2)}
+    gc.load_state_dict(sd)
+    assert pickle.loads(pickle.dumps(gc)).in_features == 5
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from pygcn_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.GcnbError, match="no CPU/PyTorch fallback"):
+        _lib.load(build_if_missing=False)

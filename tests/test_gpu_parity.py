@@ -1,0 +1,384 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's goldens.
+
+Bars: index / byte work bit-exact; float work max|a-b|/max|b| <= 1e-5.
+Everything here needs a B200: run with `pytest -m gpu`.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rng_inputs
+from oracle import gcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(dev())
+
+
+def err(a, b):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return O.normwise_err(a, b)
+
+
+@pytest.fixture(scope="module")
+def P():
+    import pygcn_b200
+
+    assert pygcn_b200._lib.load().gcnb_check_device() == 0, pygcn_b200._lib.last_error()
+    return pygcn_b200
+
+
+# ------------------------------------------------------------------ graph build: bit-exact
+def _edges_graph(P, e, n, **kw):
+    return P.Graph.from_edges(cu(e[:, 0]), cu(e[:, 1]), n, **kw)
+
+
+def test_cora_pipeline_bit_exact(P, golden):
+    g = golden("cora_pipeline.npz")
+    n = int(g["n"])
+    gr = _edges_graph(P, g["edges"], n)
+    coo = gr.to_sparse_coo()
+    idx = coo._indices().cpu().numpy()
+    val = coo._values().cpu().numpy()
+    assert idx.dtype == np.int64 and val.dtype == np.float32
+    assert np.array_equal(idx, g["indices"])
+    assert np.array_equal(val.view(np.uint32), g["values"].view(np.uint32))
+    assert not coo.is_coalesced()  # same flag the reference's constructor leaves
+    # CSR and CSR^T against the oracle's restatement
+    rowptr, col, v = (t.cpu().numpy() for t in gr.csr())
+    assert np.array_equal(rowptr, O.coo_to_csr(g["indices"], n))
+    assert np.array_equal(col, g["indices"][1]) and np.array_equal(v, g["values"])
+    t_rowptr, t_col, t_val = O.transpose_csr(g["indices"], g["values"], n, n)
+    rp, c, vv = (t.cpu().numpy() for t in gr.csr(transpose=True))
+    assert np.array_equal(rp, t_rowptr) and np.array_equal(c, t_col)
+    assert np.array_equal(vv.view(np.uint32), t_val.view(np.uint32))
+    assert gr.pattern_symmetric
+    _, counts = O.degree_bins(O.coo_to_csr(g["indices"], n))
+    assert gr.bin_rows == list(counts) and gr.max_degree == 169
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_small_pipelines_bit_exact(P, golden, k):
+    g = golden("pipeline_small.npz")
+    gr = _edges_graph(P, g[f"edges{k}"], int(g[f"n{k}"]))
+    coo = gr.to_sparse_coo()
+    assert np.array_equal(coo._indices().cpu().numpy(), g[f"indices{k}"])
+    assert np.array_equal(coo._values().cpu().numpy().view(np.uint32), g[f"values{k}"].view(np.uint32))
+
+
+def test_pipeline_flag_subsets_and_empty(P):
+    rs = np.random.default_rng(5)
+    n = 50
+    e = rs.integers(0, n, size=(200, 2)).astype(np.int32)
+    # no symmetrise / no self loops / no normalise: plain multiplicity matrix
+    gr = _edges_graph(P, e, n, symmetrize=False, self_loops=False, row_normalize=False)
+    r, c, v = O.edges_to_counts(e[:, 0], e[:, 1], n)
+    coo = gr.to_sparse_coo()
+    assert np.array_equal(coo._indices().cpu().numpy(), np.vstack([r, c]))
+    assert np.array_equal(coo._values().cpu().numpy(), v)
+    # symmetrise only
+    gr = _edges_graph(P, e, n, symmetrize=True, self_loops=False, row_normalize=False)
+    r2, c2, v2 = O.symmetrize_max(r, c, v, n)
+    coo = gr.to_sparse_coo()
+    assert np.array_equal(coo._indices().cpu().numpy(), np.vstack([r2, c2]))
+    assert np.array_equal(coo._values().cpu().numpy(), v2)
+    # empty edge list: identity after + I and normalisation
+    gr = P.Graph.from_edges(torch.empty(0, dtype=torch.int32, device=dev()),
+                            torch.empty(0, dtype=torch.int32, device=dev()), 7)
+    coo = gr.to_sparse_coo()
+    assert np.array_equal(coo._indices().cpu().numpy(), np.vstack([np.arange(7), np.arange(7)]))
+    assert np.array_equal(coo._values().cpu().numpy(), np.ones(7, np.float32))
+    # n = 0
+    gr = P.Graph.from_edges(torch.empty(0, dtype=torch.int32, device=dev()),
+                            torch.empty(0, dtype=torch.int32, device=dev()), 0)
+    assert gr.nnz == 0 and gr.n_rows == 0
+    with pytest.raises(RuntimeError):
+        _edges_graph(P, np.array([[0, 99]], np.int32), 10)
+
+
+def test_coo_unsorted_duplicates_layout(P, golden):
+    c = golden("layer_cases.npz")
+    n = int(c["ragged/n"])
+    rows, cols, vals = c["ragged/rows"], c["ragged/cols"], c["ragged/vals"]
+    adj = torch.sparse_coo_tensor(cu(np.vstack([rows, cols])), cu(vals), (n, n))
+    gr = P.Graph.from_torch(adj)
+    order = np.lexsort((np.arange(rows.size), cols, rows))  # (row, col) stable
+    rowptr, col, v = (t.cpu().numpy() for t in gr.csr())
+    assert np.array_equal(col, cols[order]) and np.array_equal(v, vals[order])
+    assert np.array_equal(rowptr, O.coo_to_csr(np.vstack([rows[order], cols[order]]), n))
+    assert gr.nnz == rows.size and gr.bin_rows[0] > 0  # empty rows exist
+    # CSR input gives the same handle contents as the coalesced COO
+    csr = adj.coalesce().to_sparse_csr()
+    g2 = P.Graph.from_torch(csr)
+    assert np.array_equal(g2.csr()[0].cpu().numpy(), csr.crow_indices().cpu().numpy())
+    assert np.array_equal(g2.csr()[1].cpu().numpy(), csr.col_indices().cpu().numpy())
+    # out-of-range index is an error, not a crash
+    bad = torch.sparse_coo_tensor(cu(np.array([[0], [5]])), cu(np.ones(1, np.float32)), (4, 4),
+                                  check_invariants=False)
+    with pytest.raises(RuntimeError):
+        P.Graph.from_torch(bad)
+
+
+# ------------------------------------------------------------------ layer vs the reference's goldens
+def _run_layer(P, w, b, x, adj, g, relu=False, x_grad=True):
+    layer = P.GraphConvolution(w.shape[0], w.shape[1], bias=b is not None, fuse_relu=relu).to(dev())
+    with torch.no_grad():
+        layer.weight.copy_(cu(w))
+        if b is not None:
+            layer.bias.copy_(cu(b))
+    xt = x.clone().requires_grad_(x_grad)
+    out = layer(xt, adj)
+    out.backward(g)
+    return layer, xt, out
+
+
+def test_layer_cora_golden(P, golden):
+    p = golden("cora_pipeline.npz")
+    c = golden("layer_cases.npz")
+    n = int(p["n"])
+    gr = _edges_graph(P, p["edges"], n)
+    layer, xt, out = _run_layer(P, c["cora_l1/weight"], c["cora_l1/bias"], cu(rng_inputs(1, (n, 1433))), gr,
+                                cu(rng_inputs(2, (n, 16))))
+    assert err(out, c["cora_l1/out"]) < TOL
+    assert err(layer.weight.grad, c["cora_l1/dW"]) < TOL
+    assert err(layer.bias.grad, c["cora_l1/db"]) < TOL
+    assert err(xt.grad[:32], c["cora_l1/dX_head"]) < TOL
+    # the same adjacency passed as the torch sparse tensor the reference builds
+    adj = torch.sparse_coo_tensor(cu(p["indices"]), cu(p["values"]), (n, n))
+    layer, xt, out = _run_layer(P, c["cora_l2/weight"], c["cora_l2/bias"], cu(rng_inputs(3, (n, 16))), adj,
+                                cu(rng_inputs(4, (n, 7))))
+    assert err(out, c["cora_l2/out"]) < TOL
+    assert err(layer.weight.grad, c["cora_l2/dW"]) < TOL
+    assert err(layer.bias.grad, c["cora_l2/db"]) < TOL
+    assert err(xt.grad, c["cora_l2/dX"]) < TOL
+
+
+def test_layer_ragged_noncontiguous_golden(P, golden):
+    c = golden("layer_cases.npz")
+    n = int(c["ragged/n"])
+    adj = torch.sparse_coo_tensor(cu(np.vstack([c["ragged/rows"], c["ragged/cols"]])), cu(c["ragged/vals"]), (n, n))
+    xw = cu(rng_inputs(12, (n, 40))).requires_grad_(True)
+    layer = P.GraphConvolution(33, 7).to(dev())
+    with torch.no_grad():
+        layer.weight.copy_(cu(c["ragged/weight"]))
+        layer.bias.copy_(cu(c["ragged/bias"]))
+    out = layer(xw[:, :33], adj)  # column-slice view, as pygcn/models.py:345 passes it
+    out.backward(cu(rng_inputs(13, (n, 7))))
+    assert err(out, c["ragged/out"]) < TOL
+    assert err(layer.weight.grad, c["ragged/dW"]) < TOL
+    assert err(layer.bias.grad, c["ragged/db"]) < TOL
+    assert err(xw.grad, c["ragged/dXfull"]) < TOL
+
+
+def test_layer_dense_adj_golden(P, golden):
+    c = golden("layer_cases.npz")
+    layer, xt, out = _run_layer(P, c["dense/weight"], c["dense/bias"], cu(rng_inputs(22, (96, 8))),
+                                cu(c["dense/adj"]), cu(rng_inputs(23, (96, 32))))
+    assert err(out, c["dense/out"]) < TOL
+    assert err(layer.weight.grad, c["dense/dW"]) < TOL
+    assert err(layer.bias.grad, c["dense/db"]) < TOL
+    assert err(xt.grad, c["dense/dX"]) < TOL
+
+
+def test_layer_nobias_csr_golden(P, golden):
+    c = golden("layer_cases.npz")
+    n = int(c["ragged/n"])
+    adj = torch.sparse_coo_tensor(cu(np.vstack([c["ragged/rows"], c["ragged/cols"]])), cu(c["ragged/vals"]),
+                                  (n, n)).coalesce().to_sparse_csr()
+    layer, xt, out = _run_layer(P, c["nobias_csr/weight"], None, cu(rng_inputs(31, (n, 16))), adj,
+                                cu(rng_inputs(32, (n, 16))), x_grad=False)
+    assert layer.bias is None and xt.grad is None
+    assert err(out, c["nobias_csr/out"]) < TOL
+    assert err(layer.weight.grad, c["nobias_csr/dW"]) < TOL
+
+
+def test_spmm_functional_golden(P, golden):
+    c = golden("layer_cases.npz")
+    m, k, f = (int(v) for v in c["spmm_rect/shape"])
+    adj = torch.sparse_coo_tensor(cu(np.vstack([c["spmm_rect/rows"], c["spmm_rect/cols"]])), cu(c["spmm_rect/vals"]),
+                                  (m, k))
+    d = cu(rng_inputs(42, (k, f))).requires_grad_(True)
+    out = P.spmm(adj, d)
+    out.backward(cu(rng_inputs(43, (m, f))))
+    assert err(out, c["spmm_rect/out"]) < TOL
+    assert err(d.grad, c["spmm_rect/dB"]) < TOL
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_stack3_unchanged_caller_golden(P, golden, fused):
+    """relu(gc(x, adj)) x3 exactly as models.GeneratorGCN.forward (pygcn/models.py:103-111)."""
+    p = golden("pipeline_small.npz")
+    c = golden("layer_cases.npz")
+    gr = _edges_graph(P, p["edges1"], 257)
+    torch.manual_seed(42)
+    gcs = [P.GraphConvolution(8, 32, fuse_relu=fused), P.GraphConvolution(32, 32, fuse_relu=fused),
+           P.GraphConvolution(32, 32, fuse_relu=fused)]
+    for k, gc in enumerate(gcs, 1):  # same seed, same draw order as the reference model
+        assert np.array_equal(gc.weight.detach().numpy(), c[f"stack3/param:gc{k}.weight"])
+        assert np.array_equal(gc.bias.detach().numpy(), c[f"stack3/param:gc{k}.bias"])
+        gc.to(dev())
+    x = cu(rng_inputs(51, (257, 8))).requires_grad_(True)
+    h = x
+    with torch.autograd.set_detect_anomaly(True):  # policy-generator.py:419
+        for gc in gcs:
+            h = F.relu(gc(h, gr))
+        h.backward(cu(rng_inputs(52, (257, 32))), retain_graph=True)  # policy-generator.py:420
+    assert err(h, c["stack3/out"]) < TOL
+    assert err(x.grad, c["stack3/dX"]) < TOL
+    for k, gc in enumerate(gcs, 1):
+        assert err(gc.weight.grad, c[f"stack3/grad:gc{k}.weight"]) < TOL
+        assert err(gc.bias.grad, c[f"stack3/grad:gc{k}.bias"]) < TOL
+    assert sorted(gcs[0].state_dict().keys()) == ["bias", "weight"]
+
+
+# ------------------------------------------------------------------ CUDA path vs the oracle on seeded inputs
+def _powerlaw_graph(n, n_edges, seed, hub_deg=0):
+    rs = np.random.default_rng(seed)
+    src = (n * rs.random(n_edges) ** 3).astype(np.int64)  # skewed: low ids are hubs
+    dst = rs.integers(0, n, n_edges)
+    if hub_deg:
+        src = np.concatenate([src, np.full(hub_deg, 3)])
+        dst = np.concatenate([dst, rs.choice(n, hub_deg, replace=False)])
+    return src.astype(np.int32), dst.astype(np.int32)
+
+
+@pytest.mark.parametrize("fin,fout", [(64, 32), (5, 1), (9, 3), (16, 7), (33, 47), (100, 256), (20, 600)])
+def test_layer_vs_oracle_widths_and_long_rows(P, fin, fout):
+    n = 6000
+    src, dst = _powerlaw_graph(n, 60000, seed=fin * 1000 + fout, hub_deg=3000)
+    idx, val = O.build_normalized_adjacency(src, dst, n)
+    gr = P.Graph.from_edges(cu(src), cu(dst), n)
+    assert gr.nnz == idx.shape[1] and gr.n_long_chunks > 0 and gr.max_degree >= 3000
+    x = rng_inputs(1, (n, fin))
+    g = rng_inputs(2, (n, fout))
+    torch.manual_seed(42)
+    layer = P.GraphConvolution(fin, fout).to(dev())
+    w = layer.weight.detach().cpu().numpy()
+    b = layer.bias.detach().cpu().numpy()
+    xt = cu(x).requires_grad_(True)
+    out = layer(xt, gr)
+    out.backward(cu(g))
+    _, o_ref = O.c_layer_forward(x, w, b, idx, val, n)
+    dw, db, dx, _ = O.c_layer_backward(x, w, True, idx, val, n, g)
+    _, o64 = O.c_layer_forward(x, w, b, idx, val, n, dtype=np.float64)
+    assert err(out, o_ref) < TOL and err(out, o64) < TOL
+    assert err(layer.weight.grad, dw) < TOL
+    assert err(layer.bias.grad, db) < TOL
+    assert err(xt.grad, dx) < TOL
+    # fused ReLU epilogue + masked backward against relu() composed on the oracle
+    layer2 = P.GraphConvolution(fin, fout, fuse_relu=True).to(dev())
+    layer2.load_state_dict(layer.state_dict())
+    xt2 = cu(x).requires_grad_(True)
+    out2 = layer2(xt2, gr)
+    out2.backward(cu(g))
+    assert err(out2, np.maximum(o_ref, 0)) < TOL
+    # the mask comes from the CUDA output itself (entries within rounding of zero may differ in
+    # sign from the oracle's); it must agree with the oracle's everywhere else
+    o2 = out2.detach().cpu().numpy()
+    flips = (o2 > 0) != (o_ref > 0)
+    assert flips.sum() <= 4 and (flips.sum() == 0 or np.abs(o_ref[flips]).max() < 1e-5 * np.abs(o_ref).max())
+    gm = O.relu_backward(g, o2)
+    dw2, db2, dx2, _ = O.c_layer_backward(x, w, True, idx, val, n, gm)
+    assert err(layer2.weight.grad, dw2) < TOL and err(layer2.bias.grad, db2) < TOL and err(xt2.grad, dx2) < TOL
+
+
+def test_gemm_generic_strides(P):
+    rs = np.random.default_rng(7)
+    for (m, n, k) in [(1, 1, 1), (130, 33, 70), (64, 32, 20000), (257, 100, 16), (1000, 7, 1433)]:
+        a = rs.standard_normal((m, k)).astype(np.float32)
+        b = rs.standard_normal((k, n)).astype(np.float32)
+        ref = a.astype(np.float64) @ b.astype(np.float64)
+        assert err(P.mm(cu(a), cu(b)), ref) < TOL
+        assert err(P.mm(cu(a.T.copy()).t(), cu(b)), ref) < TOL  # A given transposed (dW = X^T dS)
+        assert err(P.mm(cu(a), cu(b.T.copy()).t()), ref) < TOL  # B given transposed (dX = dS W^T)
+        assert err(P.mm(cu(np.hstack([a, a]))[:, :k], cu(b)), ref) < TOL  # row stride > width
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE config 1)
+@pytest.fixture(scope="module")
+def cbg(P):
+    n, deg = 100_000, 100
+    gen = torch.Generator(device=dev()).manual_seed(0)
+    src = torch.randint(0, n, (n * deg // 2,), generator=gen, device=dev(), dtype=torch.int32)
+    dst = torch.randint(0, n, (n * deg // 2,), generator=gen, device=dev(), dtype=torch.int32)
+    return P.Graph.from_edges(src, dst, n), n
+
+
+def test_cbg_full_size_properties(P, cbg):
+    gr, n = cbg
+    assert 9_900_000 < gr.nnz < 10_200_000 and gr.pattern_symmetric
+    gen = torch.Generator(device=dev()).manual_seed(1)
+    ones = torch.ones(n, 32, device=dev())
+    # rows of D^-1(A+I) sum to one
+    assert (P.spmm(gr, ones) - 1).abs().max().item() < 1e-5
+    # adjoint identity <A x, y> == <x, A^T y>: ties the backward SpMM to the forward one
+    x = torch.randn(n, 32, generator=gen, device=dev(), requires_grad=True)
+    y = torch.randn(n, 32, generator=gen, device=dev())
+    ax = P.spmm(gr, x)
+    ax.backward(y)
+    lhs = (ax.double() * y.double()).sum().item()
+    rhs = (x.detach().double() * x.grad.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs), 1.0) * 10
+    # linearity of the layer without bias
+    layer = P.GraphConvolution(64, 32, bias=False).to(dev())
+    a = torch.randn(n, 64, generator=gen, device=dev())
+    b = torch.randn(n, 64, generator=gen, device=dev())
+    with torch.no_grad():
+        lin = layer(2.0 * a - 3.0 * b, gr)
+        comb = 2.0 * layer(a, gr) - 3.0 * layer(b, gr)
+    assert ((lin - comb).abs().max() / comb.abs().max()).item() < TOL
+    # run-to-run determinism (atomic-free accumulation)
+    with torch.no_grad():
+        assert torch.equal(layer(a, gr), layer(a, gr))
+    # against torch's own CUDA spmm on the exported tensor (library cross-check, not the oracle)
+    coo = gr.to_sparse_coo()
+    ref = torch.spmm(coo, x.detach())
+    assert ((ax.detach() - ref).abs().max() / ref.abs().max()).item() < TOL
+
+
+def test_cbg_backward_matches_torch_autograd(P, cbg):
+    gr, n = cbg
+    coo = gr.to_sparse_coo().coalesce()
+    gen = torch.Generator(device=dev()).manual_seed(3)
+    x = torch.randn(n, 64, generator=gen, device=dev())
+    g = torch.randn(n, 32, generator=gen, device=dev())
+    torch.manual_seed(42)
+    layer = P.GraphConvolution(64, 32).to(dev())
+    xt = x.clone().requires_grad_(True)
+    layer(xt, gr).backward(g)
+    w = layer.weight.detach().clone().requires_grad_(True)
+    b = layer.bias.detach().clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    (torch.spmm(coo, torch.mm(xr, w)) + b).backward(g)  # the reference's three lines on CUDA
+    for mine, ref in ((layer.weight.grad, w.grad), (layer.bias.grad, b.grad), (xt.grad, xr.grad)):
+        assert ((mine - ref).abs().max() / ref.abs().max()).item() < TOL
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_errors(P, golden):
+    layer = P.GraphConvolution(4, 3)
+    with pytest.raises(RuntimeError):  # CPU tensors: explicit error, no fallback
+        layer(torch.zeros(5, 4), torch.eye(5))
+    layer = layer.to(dev())
+    adj = torch.eye(5, device=dev())
+    with pytest.raises(RuntimeError):  # inner dimension mismatch
+        layer(torch.zeros(5, 6, device=dev()), adj)
+    with pytest.raises(RuntimeError):  # rows of x vs adj
+        layer(torch.zeros(6, 4, device=dev()), adj)
+    with pytest.raises(RuntimeError):  # dtype
+        layer(torch.zeros(5, 4, device=dev(), dtype=torch.float64), adj)
+    out = layer(torch.zeros(5, 4, device=dev()), adj)
+    assert out.shape == (5, 3) and torch.allclose(out, layer.bias.expand(5, 3))

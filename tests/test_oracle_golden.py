@@ -142,3 +142,27 @@ def test_stack3_relu(golden):
         assert O.normwise_err(db, c[f"stack3/grad:gc{k}.bias"]) < TOL
         grad = dx
     assert O.normwise_err(grad, c["stack3/dX"]) < TOL
+
+
+def test_ref_port_matches_golden(golden):
+    """oracle/ref_layer_torch.py (what the reference arm of bench.py times) reproduces the
+    reference's own outputs."""
+    import torch
+
+    from oracle import ref_layer_torch as R
+
+    c = golden("layer_cases.npz")
+    p = golden("cora_pipeline.npz")
+    n = int(p["n"])
+    adj = R.make_reference_adj(torch.from_numpy(p["indices"]), torch.from_numpy(p["values"]), (n, n))
+    out, dw, db = R.reference_layer_fwdbwd(
+        torch.from_numpy(rng_inputs(3, (n, 16))), torch.from_numpy(c["cora_l2/weight"]),
+        torch.from_numpy(c["cora_l2/bias"]), adj, torch.from_numpy(rng_inputs(4, (n, 7))))
+    # same library calls as the reference; only the BLAS thread count may differ from the golden run
+    assert O.normwise_err(out.numpy(), c["cora_l2/out"]) < 1e-6
+    assert O.normwise_err(dw.numpy(), c["cora_l2/dW"]) < 1e-6 and O.normwise_err(db.numpy(), c["cora_l2/db"]) < 1e-6
+    csr = R.make_reference_adj(torch.from_numpy(p["indices"]), torch.from_numpy(p["values"]), (n, n), "csr")
+    out2, _, _ = R.reference_layer_fwdbwd(
+        torch.from_numpy(rng_inputs(3, (n, 16))), torch.from_numpy(c["cora_l2/weight"]),
+        torch.from_numpy(c["cora_l2/bias"]), csr, torch.from_numpy(rng_inputs(4, (n, 7))))
+    assert O.normwise_err(out2.numpy(), c["cora_l2/out"]) < TOL
