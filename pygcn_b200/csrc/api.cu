@@ -19,19 +19,46 @@ namespace {
 
 inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
+constexpr double kTcMinWork = 1.0e7;  // m*n*k below this: launch overhead dominates, keep the CUDA-core kernel
+
+// which kernel serves a product: 0 = CUDA-core fp32, 1 = tcgen05 rows, 2 = tcgen05 tn
+int gemm_route(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs, int64_t a_cs, const float* b,
+               int64_t b_rs, int64_t b_cs, const float* c, int64_t ldc, int precision) {
+  if (precision == GCNB_GEMM_FP32) return 0;
+  if (precision == GCNB_GEMM_AUTO && (double)m * (double)n * (double)k < kTcMinWork) return 0;
+  if (gemm_tc_rows_eligible(m, n, k, a, a_rs, a_cs, c, ldc)) return 1;
+  if (a_rs == 1 && b_cs == 1 && gemm_tc_tn_eligible(m, n, k, a, a_cs, b, b_rs)) return 2;
+  return 0;
+}
+
 int gemm_dispatch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs, int64_t a_cs,
                   const float* b, int64_t b_rs, int64_t b_cs, float* c, int64_t ldc, int precision,
                   void* ws, size_t ws_bytes, cudaStream_t st) {
   GCNB_REQUIRE(precision == GCNB_GEMM_FP32 || precision == GCNB_GEMM_TF32X3 || precision == GCNB_GEMM_AUTO,
                "gemm: unknown precision %d", precision);
-  // The tcgen05 3xTF32 tier is dispatched here once enabled; until then every tier is the
-  // exact fp32 kernel (a superset of the accuracy contract).
-  return gemm_fp32_launch(m, n, k, a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, ws, ws_bytes, st);
+  GCNB_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm: negative dimension");
+  GCNB_REQUIRE(ldc >= n, "gemm: ldc < n");
+  if (m == 0 || n == 0) return GCNB_OK;
+  switch (gemm_route(m, n, k, a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, precision)) {
+    case 1:
+      return gemm_tc_rows_launch(m, n, k, a, a_rs, b, b_rs, b_cs, c, ldc, ws, ws_bytes, st);
+    case 2:
+      return gemm_tc_tn_launch(m, n, k, a, a_cs, b, b_rs, c, ldc, ws, ws_bytes, st);
+    default:
+      return gemm_fp32_launch(m, n, k, a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, ws, ws_bytes, st);
+  }
 }
 
+// conservative: large enough for whichever kernel the route picks at call time
 size_t gemm_ws(int64_t m, int64_t n, int64_t k, int precision) {
-  (void)precision;
-  return gemm_fp32_workspace_bytes(m, n, k);
+  size_t w = gemm_fp32_workspace_bytes(m, n, k);
+  if (precision != GCNB_GEMM_FP32 && m > 0 && n > 0 && k > 0) {
+    const size_t r = gemm_tc_rows_workspace_bytes(m, n, k);
+    const size_t t = (n <= 256) ? gemm_tc_tn_workspace_bytes(m, n, k) : 0;
+    if (r > w) w = r;
+    if (t > w) w = t;
+  }
+  return (w + 255) & ~(size_t)255;
 }
 
 }  // namespace

@@ -68,10 +68,28 @@ int gemm_fp32_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_
                      size_t ws_bytes, cudaStream_t stream);
 size_t gemm_fp32_workspace_bytes(int64_t m, int64_t n, int64_t k);
 
+// tcgen05 3xTF32 kernels (gemm_tc.cu)
+bool gemm_tc_rows_eligible(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs, int64_t a_cs,
+                           const float* c, int64_t ldc);
+size_t gemm_tc_rows_workspace_bytes(int64_t m, int64_t n, int64_t k);
+int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b,
+                        int64_t b_rs, int64_t b_cs, float* c, int64_t ldc, void* ws, size_t ws_bytes,
+                        cudaStream_t stream);
+bool gemm_tc_tn_eligible(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y,
+                         int64_t ldy);
+size_t gemm_tc_tn_workspace_bytes(int64_t m, int64_t n, int64_t r);
+int gemm_tc_tn_launch(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y,
+                      int64_t ldy, float* c, int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t stream);
+
 int colsum_launch(int64_t n_rows, int64_t f, const float* g, int64_t ldg, const float* y,
                   int64_t ldy, float* gm, int64_t ldgm, float* out, void* ws, size_t ws_bytes,
                   cudaStream_t stream);
 size_t colsum_workspace_bytes(int64_t n_rows, int64_t f);
+
+// out[(i / n) * ldo + i % n] = sum_{s < n_parts} partial[s * total + i], s ascending inside a fixed
+// 8-lane tree (deterministic).  total = m * n.
+int reduce_partials_launch(int64_t m, int64_t n, int n_parts, const float* partial, float* out,
+                           int64_t ldo, cudaStream_t stream);
 
 }  // namespace gcnb
 

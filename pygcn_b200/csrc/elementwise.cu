@@ -45,13 +45,25 @@ colsum_partial_kernel(int64_t n_rows, int f, int cw, int64_t rows_per_block,
   }
 }
 
+// out[i] = sum over parts of partial[s][i]: 32 outputs x 8 part-lanes per CTA, fixed-order tree.
 __global__ void __launch_bounds__(kThreads)
-colsum_final_kernel(int f, int n_blocks, const float* __restrict__ partial, float* __restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= f) return;
-  float s = 0.f;
-  for (int b = 0; b < n_blocks; ++b) s += partial[(int64_t)b * f + j];
-  out[j] = s;
+reduce_partials_kernel(int64_t total, int64_t n, int n_parts, const float* __restrict__ partial,
+                       float* __restrict__ out, int64_t ldo) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31;
+  const int ty = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (i < total)
+    for (int s = ty; s < n_parts; s += 8) acc += partial[(int64_t)s * total + i];
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && i < total) {
+    float v = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v += red[t][tx];
+    out[(i / n) * ldo + (i % n)] = v;
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) zero_kernel(float* out, int f) {
@@ -98,8 +110,15 @@ int colsum_launch(int64_t n_rows, int64_t f, const float* g, int64_t ldg, const 
   colsum_partial_kernel<<<nb, kThreads, 0, st>>>(n_rows, (int)f, cw, rows_per_block, g, ldg, y, ldy, gm,
                                                  ldgm, reinterpret_cast<float*>(ws));
   GCNB_LAUNCH_CHECK();
-  colsum_final_kernel<<<(unsigned)ceil_div(f, kThreads), kThreads, 0, st>>>(
-      (int)f, nb, reinterpret_cast<const float*>(ws), out);
+  return reduce_partials_launch(1, f, nb, reinterpret_cast<const float*>(ws), out, f, st);
+}
+
+int reduce_partials_launch(int64_t m, int64_t n, int n_parts, const float* partial, float* out,
+                           int64_t ldo, cudaStream_t st) {
+  const int64_t total = m * n;
+  if (total == 0) return GCNB_OK;
+  reduce_partials_kernel<<<(unsigned)ceil_div(total, 32), kThreads, 0, st>>>(total, n, n_parts, partial,
+                                                                            out, ldo);
   GCNB_LAUNCH_CHECK();
   return GCNB_OK;
 }

@@ -90,17 +90,6 @@ gemm_fp32_kernel(int m, int n, int64_t k, const float* __restrict__ a, int64_t a
   }
 }
 
-// c[i] = sum_s partial[s][i], s ascending.
-__global__ void __launch_bounds__(256)
-splitk_reduce_kernel(int64_t m, int64_t n, int splits, const float* __restrict__ partial,
-                     float* __restrict__ c, int64_t ldc) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m * n) return;
-  float acc = 0.f;
-  for (int s = 0; s < splits; ++s) acc += partial[(int64_t)s * m * n + i];
-  c[(i / n) * ldc + (i % n)] = acc;
-}
-
 int num_splits(int64_t m, int64_t n, int64_t k) {
   // split only when the output is small and the reduction long (dW = X^T dS)
   const int64_t tiles = ceil_div(m, 64) * ceil_div(n, 64);
@@ -161,9 +150,7 @@ int gemm_fp32_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_
 #undef GCNB_GEMM_LAUNCH
   GCNB_LAUNCH_CHECK();
   if (splits > 1) {
-    const int64_t total = m * n;
-    splitk_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(m, n, real_splits, dst, c, ldc);
-    GCNB_LAUNCH_CHECK();
+    GCNB_TRY(reduce_partials_launch(m, n, real_splits, dst, c, ldc, st));
   }
   return GCNB_OK;
 }

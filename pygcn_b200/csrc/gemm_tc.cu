@@ -1,0 +1,578 @@
+// tcgen05 (5th-gen tensor core) GEMMs for the dense contractions of the GCN layer, fp32 in /
+// fp32 out with fp32-level accuracy through the 3-term TF32 split ("3xTF32"):
+//     a = a_hi + a_lo,  b = b_hi + b_lo   (hi = cvt.rna.tf32, lo = a - hi, exact)
+//     a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi          (fp32 accumulate in TMEM)
+//
+//   mode R ("rows"):  C[M,N] = A[M,K] * B[K,N], A row-major with K contiguous, M huge, K/N small
+//                     support = X W (pygcn/layers.py:33) and dX = dS W^T (MmBackward0).
+//                     B is tiny: a pre-pass packs it once into hi/lo images that already have the
+//                     UMMA shared-memory layout, the main kernel pulls them with cp.async.bulk
+//                     (TMA, mbarrier complete_tx); A streams HBM -> registers -> split -> smem.
+//   mode T ("tn"):    C[M,N] = sum_r X[r,M]^T * Y[r,N]: both operands row-major with the
+//                     reduction index outermost (dW = X^T dS).  Rows are split across CTAs
+//                     (split-K); tiles are transposed into K-major smem on the fly; partial
+//                     tiles are reduced in a fixed order (deterministic).
+//
+// Every operand tile in shared memory is the canonical K-major SWIZZLE_128B layout
+// (rows of 32 tf32 = 128 B, 16-byte chunk c of row r stored at chunk c ^ (r & 7), 8-row groups
+// 1024 B apart), accumulators live in TMEM (128 lanes x N columns fp32), tcgen05.mma is issued
+// by one thread, completion is tracked with tcgen05.commit -> mbarrier, the epilogue reads TMEM
+// with tcgen05.ld.  Two smem stages; 2 CTAs per SM give the inter-tile overlap.
+#include "common.cuh"
+
+namespace gcnb {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int BM = 128;        // UMMA M
+constexpr int BKF = 32;        // floats per K block (one 128-byte swizzle row)
+constexpr int kTileBytes = BM * 128;  // one 128-row operand tile (hi or lo)
+constexpr uint32_t kSpinLimit = 1u << 28;
+constexpr int kChunkBlocks = 8;  // K blocks (of 32) accumulated inside TMEM before a drain
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+  v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused) | SBO>>4 [32,46) (=1024 B) | version=1 [46,48) | layout=2 [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, K-major both
+__host__ __device__ inline uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+  hi = __uint_as_float(h);
+  lo = v - hi;
+}
+
+// byte offset of (row r, float column k) inside a K-major SW128 tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int k) {
+  return (uint32_t)(r * 128 + ((((k >> 2) ^ (r & 7)) << 4) | ((k & 3) << 2)));
+}
+
+struct Smem {
+  // offsets (bytes) into the 1024-aligned dynamic shared memory block
+  uint32_t a_hi[2], a_lo[2], b_hi[2], b_lo[2];
+  uint32_t bars;  // mma_done[2], b_full[2], accum_full  (5 x 8 bytes) then tmem slot
+};
+
+__host__ __device__ inline uint32_t smem_layout(int npad, Smem* s) {
+  uint32_t off = 0;
+  const uint32_t bt = (uint32_t)npad * 128;
+  for (int i = 0; i < 2; ++i) { s->a_hi[i] = off; off += kTileBytes; s->a_lo[i] = off; off += kTileBytes; }
+  for (int i = 0; i < 2; ++i) { s->b_hi[i] = off; off += bt; s->b_lo[i] = off; off += bt; }
+  off = (off + 1023) & ~1023u;
+  s->bars = off;
+  off += 64;
+  return off;
+}
+
+// One K block: 4 K-steps of 8 tf32, 3 MMAs each.  first = first K block of the tile.
+__device__ __forceinline__ void issue_kblock(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                             uint32_t b_lo, uint32_t idesc, bool first) {
+  const uint64_t dah = make_desc(a_hi), dal = make_desc(a_lo), dbh = make_desc(b_hi), dbl = make_desc(b_lo);
+#pragma unroll
+  for (int ks = 0; ks < BKF / 8; ++ks) {
+    const uint64_t adv = (uint64_t)((ks * 32) >> 4);  // 32 bytes per K step inside the swizzle row
+    umma_tf32(tmem_d, dal + adv, dbh + adv, idesc, (first && ks == 0) ? 0u : 1u);
+    umma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+    umma_tf32(tmem_d, dah + adv, dbh + adv, idesc, 1u);
+  }
+}
+
+// Epilogue: TMEM accumulator (128 lanes x npad columns) -> global rows.  Warp w owns lane quarter
+// w & 3 and column half w >> 2.
+__device__ __forceinline__ void epilogue_store(uint32_t tmem_d, int npad, float* __restrict__ c, int64_t ldc,
+                                               int64_t row0, int64_t m_rows, int n0, int n_cols, bool vec_ok,
+                                               bool add = false) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3, h = warp >> 2;
+  const int64_t row = row0 + q * 32 + lane;
+  const int half = npad >> 1;
+  for (int cb = h * half; cb < (h + 1) * half; cb += 8) {
+    float v[8];
+    __syncwarp();  // tcgen05.ld is .sync.aligned: the spin-wait above may have split the warp
+    tmem_ld8(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);  // warp-collective
+    if (row < m_rows) {
+      float* dst = c + row * ldc + n0 + cb;
+      if (vec_ok && cb + 8 <= n_cols) {
+        if (add) {  // later K chunk of the same tile: fp32 round-to-nearest add outside the tensor core
+          const float4 p0 = *reinterpret_cast<const float4*>(dst);
+          const float4 p1 = *reinterpret_cast<const float4*>(dst + 4);
+          v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
+          v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+        }
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          if (cb + t < n_cols) dst[t] = add ? dst[t] + v[t] : v[t];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ B packing (mode R)
+// image[(nt * nkb + kb)][n][32 floats, swizzled]; zero padded in n and k.
+__global__ void __launch_bounds__(256)
+pack_b_kernel(int64_t K, int64_t N, int npad, int n_tiles, int nkb, const float* __restrict__ b, int64_t b_rs,
+              int64_t b_cs, float* __restrict__ img_hi, float* __restrict__ img_lo) {
+  const int64_t total = (int64_t)n_tiles * nkb * npad * BKF;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % BKF);
+    const int n = (int)((i / BKF) % npad);
+    const int64_t blk = i / ((int64_t)BKF * npad);
+    const int kb = (int)(blk % nkb);
+    const int nt = (int)(blk / nkb);
+    const int64_t gk = (int64_t)kb * BKF + kk;
+    const int64_t gn = (int64_t)nt * npad + n;
+    float v = 0.f;
+    if (gk < K && gn < N) v = __ldg(b + gk * b_rs + gn * b_cs);
+    float hi, lo;
+    split_tf32(v, hi, lo);
+    const int64_t dst = blk * ((int64_t)npad * BKF) + (sw128_off(n, kk) >> 2);
+    img_hi[dst] = hi;
+    img_lo[dst] = lo;
+  }
+}
+
+// ------------------------------------------------------------------ mode R kernel
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_rows_kernel(int64_t M, int N, int K, const float* __restrict__ a, int64_t lda,
+                    const float* __restrict__ img_hi, const float* __restrict__ img_lo, float* __restrict__ c,
+                    int64_t ldc, int npad, int nkb, int tmem_cols, int vec_ok) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  Smem L;
+  smem_layout(npad, &L);
+  const uint32_t bar_mma[2] = {base + L.bars, base + L.bars + 8};
+  const uint32_t bar_b[2] = {base + L.bars + 16, base + L.bars + 24};
+  const uint32_t bar_acc = base + L.bars + 32;
+  const uint32_t tmem_slot = base + L.bars + 40;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));  // generic pointer to the aligned block
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(bar_mma[0], 1); mbar_init(bar_mma[1], 1);
+    mbar_init(bar_b[0], 1); mbar_init(bar_b[1], 1);
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (tid < 32) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *reinterpret_cast<volatile uint32_t*>(gen + L.bars + 40);
+  const uint32_t idesc = make_idesc(npad);
+  const uint32_t b_bytes = (uint32_t)npad * 128;
+
+  const int nt = blockIdx.y;           // N tile (npad columns)
+  const int n0 = nt * npad;
+  const int n_cols = min(npad, N - n0);
+  const int64_t m_tiles = (M + BM - 1) / BM;
+
+  // thread -> (row, 16-byte chunk) of the A tile: 8 threads cover one 128-byte row segment
+  const int chunk = tid & 7;
+  const int row_in = tid >> 3;  // 0..31, +32*j
+  uint32_t it = 0;              // K-block iteration counter across tiles (stage = it & 1)
+  uint32_t acc_parity = 0;
+
+  for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+    const int64_t m0 = mt * BM;
+    float4 cur[4];
+    auto load_a = [&](int kb, float4 (&dst)[4]) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t r = m0 + row_in + 32 * j;
+        const int k = kb * BKF + chunk * 4;
+        dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < M && k < K) dst[j] = __ldg(reinterpret_cast<const float4*>(a + r * lda + k));
+      }
+    };
+    load_a(0, cur);
+    for (int kb = 0; kb < nkb; ++kb, ++it) {
+      const int s = it & 1;
+      const uint32_t use = it >> 1;  // n-th use of stage s
+      float4 nxt[4];
+      if (kb + 1 < nkb) load_a(kb + 1, nxt);  // prefetch next K block while this one is split/stored
+      if (use > 0) mbar_wait(bar_mma[s], (use - 1) & 1);  // MMAs that read stage s have retired
+      if (tid == 0) {
+        mbar_expect_tx(bar_b[s], 2 * b_bytes);
+        const int64_t blk = (int64_t)nt * nkb + kb;
+        bulk_g2s(base + L.b_hi[s], img_hi + blk * ((int64_t)npad * BKF), b_bytes, bar_b[s]);
+        bulk_g2s(base + L.b_lo[s], img_lo + blk * ((int64_t)npad * BKF), b_bytes, bar_b[s]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = row_in + 32 * j;
+        float4 hi, lo;
+        split_tf32(cur[j].x, hi.x, lo.x); split_tf32(cur[j].y, hi.y, lo.y);
+        split_tf32(cur[j].z, hi.z, lo.z); split_tf32(cur[j].w, hi.w, lo.w);
+        const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
+        *reinterpret_cast<float4*>(gen + L.a_hi[s] + off) = hi;
+        *reinterpret_cast<float4*>(gen + L.a_lo[s] + off) = lo;
+      }
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        mbar_wait(bar_b[s], use & 1);
+        tc_fence_after();
+        issue_kblock(tmem_d, base + L.a_hi[s], base + L.a_lo[s], base + L.b_hi[s], base + L.b_lo[s], idesc,
+                     kb % kChunkBlocks == 0);
+        umma_commit(bar_mma[s]);
+        if (kb == nkb - 1 || kb % kChunkBlocks == kChunkBlocks - 1) umma_commit(bar_acc);
+      }
+      if (kb + 1 < nkb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+      }
+      if (kb == nkb - 1 || kb % kChunkBlocks == kChunkBlocks - 1) {
+        // drain the accumulator every kChunkBlocks K blocks: the tensor core adds into TMEM with
+        // truncation, so long reductions are finished with fp32 RN adds in the epilogue instead
+        mbar_wait(bar_acc, acc_parity);
+        acc_parity ^= 1;
+        tc_fence_after();
+        epilogue_store(tmem_d, npad, c, ldc, m0, M, n0, n_cols, vec_ok != 0, kb >= kChunkBlocks);
+        tc_fence_before();
+        __syncthreads();
+      }
+    }
+  }
+  if (tid < 32) {
+    __syncwarp();
+    tmem_dealloc(tmem_d, (uint32_t)tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------ mode T kernel
+// C_partial[split][M tile rows][N] = sum over rows r in the split of X[r, m] * Y[r, n]
+// NBQ = float4 loads of Y per thread per K block (npad <= 32*NBQ).
+template <int NBQ>
+__global__ void __launch_bounds__(kThreads, (NBQ <= 2) ? 2 : 1)
+gemm_tc_tn_kernel(int64_t R, int M, int N, const float* __restrict__ x, int64_t ldx, const float* __restrict__ y,
+                  int64_t ldy, float* __restrict__ c, int64_t ldc, int64_t split_stride, int64_t rows_per_split,
+                  int npad, int tmem_cols, int vec_ok) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  Smem L;
+  smem_layout(npad, &L);
+  const uint32_t bar_mma[2] = {base + L.bars, base + L.bars + 8};
+  const uint32_t bar_acc = base + L.bars + 32;
+  const uint32_t tmem_slot = base + L.bars + 40;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(bar_mma[0], 1); mbar_init(bar_mma[1], 1);
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (tid < 32) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *reinterpret_cast<volatile uint32_t*>(gen + L.bars + 40);
+  const uint32_t idesc = make_idesc(npad);
+
+  const int m0 = blockIdx.y * BM;
+  const int m_cols = min(BM, M - m0);          // valid rows of the C tile (= columns of X used)
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_split;
+  const int64_t r_end = min(R, r_begin + rows_per_split);
+  const int nkb = (r_end > r_begin) ? (int)((r_end - r_begin + BKF - 1) / BKF) : 0;
+  const int a_q = (m_cols + 3) >> 2;  // float4 per X row inside this tile
+  const int b_q = (N + 3) >> 2;       // float4 per Y row
+
+  // lane <-> reduction row k inside the block; warps stride over the float4 columns:
+  // the transposing STS.32 below are bank-conflict free with this mapping.
+  auto load_block = [&](int kb, float4 (&av)[4], float4 (&bv)[NBQ]) {
+    const int64_t r = r_begin + (int64_t)kb * BKF + lane;
+    const bool r_ok = r < r_end;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = warp + 8 * j;
+      av[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r_ok && q < a_q) av[j] = __ldg(reinterpret_cast<const float4*>(x + r * ldx + m0 + 4 * q));
+    }
+#pragma unroll
+    for (int j = 0; j < NBQ; ++j) {
+      const int q = warp + 8 * j;
+      bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r_ok && q < b_q) bv[j] = __ldg(reinterpret_cast<const float4*>(y + r * ldy + 4 * q));
+    }
+  };
+  auto store_t = [&](uint32_t tile_hi, uint32_t tile_lo, int row4, const float4& v) {
+    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float hi, lo;
+      split_tf32(e[t], hi, lo);
+      const uint32_t off = sw128_off(row4 + t, lane);
+      *reinterpret_cast<float*>(gen + tile_hi + off) = hi;
+      *reinterpret_cast<float*>(gen + tile_lo + off) = lo;
+    }
+  };
+
+  float4 av[4], bv[NBQ];
+  if (nkb > 0) load_block(0, av, bv);
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb & 1;
+    const uint32_t use = (uint32_t)kb >> 1;
+    float4 an[4], bn[NBQ];
+    if (kb + 1 < nkb) load_block(kb + 1, an, bn);  // prefetch while this block is transposed
+    if (use > 0) mbar_wait(bar_mma[s], (use - 1) & 1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) store_t(L.a_hi[s], L.a_lo[s], 4 * (warp + 8 * j), av[j]);
+#pragma unroll
+    for (int j = 0; j < NBQ; ++j)
+      if (4 * (warp + 8 * j) < npad) store_t(L.b_hi[s], L.b_lo[s], 4 * (warp + 8 * j), bv[j]);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_kblock(tmem_d, base + L.a_hi[s], base + L.a_lo[s], base + L.b_hi[s], base + L.b_lo[s], idesc, kb == 0);
+      umma_commit(bar_mma[s]);
+      if (kb == nkb - 1) umma_commit(bar_acc);
+    }
+    if (kb + 1 < nkb) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) av[j] = an[j];
+#pragma unroll
+      for (int j = 0; j < NBQ; ++j) bv[j] = bn[j];
+    }
+  }
+  float* cdst = c + (int64_t)blockIdx.x * split_stride;
+  if (nkb > 0) {
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    epilogue_store(tmem_d, npad, cdst, ldc, m0, M, 0, N, vec_ok != 0);
+    tc_fence_before();
+  } else {
+    for (int i = tid; i < m_cols * N; i += kThreads) cdst[(int64_t)(m0 + i / N) * ldc + (i % N)] = 0.f;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    __syncwarp();
+    tmem_dealloc(tmem_d, (uint32_t)tmem_cols);
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int pad16(int64_t n) { return (int)(ceil_div(n, 16) * 16); }
+inline int tmem_cols_for(int npad) {
+  int c = 32;
+  while (c < npad) c <<= 1;
+  return c;
+}
+
+struct RowsPlan { int npad, n_tiles, nkb; size_t img_floats; };
+RowsPlan rows_plan(int64_t n, int64_t k) {
+  RowsPlan p;
+  p.npad = n >= 256 ? 256 : pad16(n);
+  p.n_tiles = (int)ceil_div(n, p.npad);
+  p.nkb = (int)ceil_div(k, BKF);
+  p.img_floats = (size_t)p.n_tiles * p.nkb * p.npad * BKF;
+  return p;
+}
+
+struct TnPlan { int npad, m_tiles; int64_t splits, rows_per_split; };
+TnPlan tn_plan(int64_t m, int64_t n, int64_t r) {
+  TnPlan p;
+  p.npad = pad16(n);
+  p.m_tiles = (int)ceil_div(m, BM);
+  int64_t s = ceil_div(2 * kNumSMs, p.m_tiles);
+  const int64_t max_s = ceil_div(r, 4 * BKF);  // at least 4 K blocks per split
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  p.rows_per_split = ceil_div(ceil_div(r, s), BKF) * BKF;
+  p.splits = ceil_div(r, p.rows_per_split);
+  if (p.splits < 1) p.splits = 1;
+  return p;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host side
+bool gemm_tc_rows_eligible(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs, int64_t a_cs,
+                           const float* c, int64_t ldc) {
+  (void)c; (void)ldc;
+  return m > 0 && n > 0 && k > 0 && a_cs == 1 && (a_rs % 4 == 0) && (k % 4 == 0) && aligned16(a) &&
+         k <= (1 << 20) && n <= (1 << 20);
+}
+
+size_t gemm_tc_rows_workspace_bytes(int64_t m, int64_t n, int64_t k) {
+  (void)m;
+  const RowsPlan p = rows_plan(n, k);
+  return 2 * p.img_floats * sizeof(float) + 256;
+}
+
+int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t b_rs,
+                        int64_t b_cs, float* c, int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const RowsPlan p = rows_plan(n, k);
+  GCNB_REQUIRE(ws != nullptr && ws_bytes >= gemm_tc_rows_workspace_bytes(m, n, k) && aligned16(ws),
+               "gemm(tc rows): workspace too small or unaligned");
+  float* img_hi = reinterpret_cast<float*>(ws);
+  float* img_lo = img_hi + ((p.img_floats + 31) & ~(size_t)31);
+  GCNB_REQUIRE((size_t)((char*)(img_lo + p.img_floats) - (char*)ws) <= ws_bytes, "gemm(tc rows): workspace layout");
+  const int64_t total = (int64_t)p.img_floats;
+  int pgrid = (int)ceil_div(total, 256);
+  if (pgrid > 4 * kNumSMs) pgrid = 4 * kNumSMs;
+  pack_b_kernel<<<pgrid, 256, 0, st>>>(k, n, p.npad, p.n_tiles, p.nkb, b, b_rs, b_cs, img_hi, img_lo);
+  GCNB_LAUNCH_CHECK();
+  Smem L;
+  const uint32_t smem = smem_layout(p.npad, &L) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCNB_CUDA(cudaFuncSetAttribute(gemm_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int64_t m_tiles = ceil_div(m, BM);
+  const int ctas_per_sm = (smem <= 110 * 1024) ? 2 : 1;
+  int64_t gx = (int64_t)kNumSMs * ctas_per_sm / p.n_tiles;
+  if (gx < 1) gx = 1;
+  if (gx > m_tiles) gx = m_tiles;
+  dim3 grid((unsigned)gx, (unsigned)p.n_tiles);
+  const int vec_ok = (ldc % 4 == 0) && aligned16(c) && (p.npad % 4 == 0);
+  gemm_tc_rows_kernel<<<grid, kThreads, smem, st>>>(m, (int)n, (int)k, a, lda, img_hi, img_lo, c, ldc, p.npad, p.nkb,
+                                                    tmem_cols_for(p.npad), vec_ok);
+  GCNB_LAUNCH_CHECK();
+  return GCNB_OK;
+}
+
+// dW-shaped product: C[M,N] = sum_r X[r, 0:M]^T Y[r, 0:N]
+bool gemm_tc_tn_eligible(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y, int64_t ldy) {
+  return m > 0 && n > 0 && r > 0 && n <= 256 && (ldx % 4 == 0) && (ldy % 4 == 0) && (m % 4 == 0) && (n % 4 == 0) &&
+         aligned16(x) && aligned16(y);
+}
+
+size_t gemm_tc_tn_workspace_bytes(int64_t m, int64_t n, int64_t r) {
+  const TnPlan p = tn_plan(m, n, r);
+  return p.splits > 1 ? (size_t)p.splits * (size_t)m * (size_t)n * sizeof(float) : 0;
+}
+
+int gemm_tc_tn_launch(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y, int64_t ldy,
+                      float* c, int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const TnPlan p = tn_plan(m, n, r);
+  const size_t need = gemm_tc_tn_workspace_bytes(m, n, r);
+  GCNB_REQUIRE(need == 0 || (ws != nullptr && ws_bytes >= need && aligned16(ws)), "gemm(tc tn): workspace too small");
+  Smem L;
+  const uint32_t smem = smem_layout(p.npad, &L) + 1024;
+  float* dst = (p.splits > 1) ? reinterpret_cast<float*>(ws) : c;
+  const int64_t dst_ld = (p.splits > 1) ? n : ldc;
+  const int64_t stride = (p.splits > 1) ? m * n : 0;
+  const int vec_ok = (dst_ld % 4 == 0) && aligned16(dst);
+  dim3 grid((unsigned)p.splits, (unsigned)p.m_tiles);
+#define GCNB_TN_LAUNCH(NBQ_)                                                                                       \
+  do {                                                                                                             \
+    static bool attr_set = false;                                                                                  \
+    if (!attr_set) {                                                                                               \
+      GCNB_CUDA(cudaFuncSetAttribute(gemm_tc_tn_kernel<NBQ_>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                     227 * 1024));                                                                 \
+      attr_set = true;                                                                                             \
+    }                                                                                                              \
+    gemm_tc_tn_kernel<NBQ_><<<grid, kThreads, smem, st>>>(r, (int)m, (int)n, x, ldx, y, ldy, dst, dst_ld, stride,  \
+                                                          p.rows_per_split, p.npad, tmem_cols_for(p.npad), vec_ok);\
+  } while (0)
+  if (p.npad <= 32) GCNB_TN_LAUNCH(1);
+  else if (p.npad <= 64) GCNB_TN_LAUNCH(2);
+  else if (p.npad <= 128) GCNB_TN_LAUNCH(4);
+  else GCNB_TN_LAUNCH(8);
+#undef GCNB_TN_LAUNCH
+  GCNB_LAUNCH_CHECK();
+  if (p.splits > 1) GCNB_TRY(reduce_partials_launch(m, n, (int)p.splits, dst, c, ldc, st));
+  return GCNB_OK;
+}
+
+}  // namespace gcnb

@@ -129,7 +129,7 @@ def _check_layer_args(x, graph, weight, bias):
             raise RuntimeError("bias must be a float32 [%d] tensor on %s" % (weight.shape[1], graph.device))
 
 
-def gcn_layer(input, adj, weight, bias=None, relu=False, precision="fp32"):
+def gcn_layer(input, adj, weight, bias=None, relu=False, precision="auto"):
     """`adj @ (input @ weight) + bias` (optionally followed by ReLU) -- pygcn/layers.py:32-38.
 
     adj: torch sparse COO / sparse CSR / dense tensor, or a `Graph`.
@@ -199,7 +199,7 @@ def spmm(adj, dense):
     return _SpmmFn.apply(dense, graph)
 
 
-def mm(a, b, precision="fp32"):
+def mm(a, b, precision="auto"):
     """`torch.mm(a, b)` through gcnb_gemm (no autograd); used by tests and the benchmark."""
     lib = _lib.load()
     _require_cuda(a, "a")

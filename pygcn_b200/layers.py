@@ -21,10 +21,11 @@ class GraphConvolution(Module):
     Extra keyword-only options (defaults reproduce the reference exactly):
       fuse_relu  -- apply the ReLU every caller in pygcn/models.py applies, inside the SpMM
                     epilogue (a following F.relu is then a no-op, results are identical)
-      precision  -- "fp32" (default), "tf32x3" or "auto" for the dense products
+      precision  -- "auto" (default: tcgen05 3xTF32 when the product is large enough, fp32 CUDA
+                    cores otherwise), "tf32x3" or "fp32" for the dense products
     """
 
-    def __init__(self, in_features, out_features, bias=True, *, fuse_relu=False, precision="fp32"):
+    def __init__(self, in_features, out_features, bias=True, *, fuse_relu=False, precision="auto"):
         super().__init__()
         self.in_features = in_features
         self.out_features = out_features
@@ -47,7 +48,7 @@ class GraphConvolution(Module):
 
     def forward(self, input, adj):
         return gcn_layer(input, adj, self.weight, self.bias,
-                         relu=getattr(self, "fuse_relu", False), precision=getattr(self, "precision", "fp32"))
+                         relu=getattr(self, "fuse_relu", False), precision=getattr(self, "precision", "auto"))
 
     def __repr__(self):
         return "%s (%s -> %s)" % (self.__class__.__name__, self.in_features, self.out_features)

@@ -307,6 +307,48 @@ def test_gemm_generic_strides(P):
         assert err(P.mm(cu(np.hstack([a, a]))[:, :k], cu(b)), ref) < TOL  # row stride > width
 
 
+def test_gemm_tcgen05_3xtf32(P):
+    """tcgen05 kind::tf32 kernels with the 3-term split hold the fp32 bar (1e-5 norm-wise) on every
+    product shape of the layer: X W ("rows"), dS W^T ("rows", B transposed), X^T dS ("tn")."""
+    gen = torch.Generator(device=dev()).manual_seed(5)
+
+    def rnd(*shape):
+        return torch.randn(*shape, generator=gen, device=dev())
+
+    def nerr(c, ref):
+        return ((c.double() - ref).abs().max() / ref.abs().max()).item()
+
+    for (m, n, k, bt) in [(128, 32, 32, False), (100_000, 32, 64, False), (100_000, 64, 32, True), (5000, 47, 100, False),
+                          (3000, 600, 16, False), (2708, 16, 1432, False), (20_000, 256, 608, False), (333, 7, 16, True)]:
+        a = rnd(m, k)
+        b = rnd(n, k).t() if bt else rnd(k, n)
+        ref = a.double() @ b.double()
+        assert nerr(P.mm(a, b, precision="tf32x3"), ref) < TOL, (m, n, k, bt)
+        a2 = rnd(m, k + 8)[:, :k]  # row stride > K (column-slice view, pygcn/models.py:345)
+        assert nerr(P.mm(a2, b, precision="tf32x3"), a2.double() @ b.double()) < TOL
+    for (r, m, n) in [(32, 128, 32), (100_000, 64, 32), (2708, 1432, 16), (30_000, 256, 256), (4097, 100, 48), (7, 8, 4)]:
+        x, y = rnd(r, m), rnd(r, n)
+        ref = x.double().t() @ y.double()
+        c = P.mm(x.t(), y, precision="tf32x3")
+        assert nerr(c, ref) < TOL, (r, m, n)
+        assert torch.equal(c, P.mm(x.t(), y, precision="tf32x3"))  # fixed-order split-K reduction
+    # the layer on the tensor-core path against the CUDA-core path
+    n = 50_000
+    gr = P.Graph.from_edges(torch.randint(0, n, (n * 10,), generator=gen, device=dev(), dtype=torch.int32),
+                            torch.randint(0, n, (n * 10,), generator=gen, device=dev(), dtype=torch.int32), n)
+    x, g = rnd(n, 64), rnd(n, 32)
+    res = {}
+    for prec in ("fp32", "tf32x3"):
+        torch.manual_seed(42)
+        layer = P.GraphConvolution(64, 32, precision=prec).to(dev())
+        xt = x.clone().requires_grad_(True)
+        out = layer(xt, gr)
+        out.backward(g)
+        res[prec] = (out.detach(), layer.weight.grad, layer.bias.grad, xt.grad)
+    for a_, b_ in zip(res["fp32"], res["tf32x3"]):
+        assert ((a_ - b_).abs().max() / a_.abs().max()).item() < TOL
+
+
 # ------------------------------------------------------------------ full-size properties (BASELINE config 1)
 @pytest.fixture(scope="module")
 def cbg(P):
