@@ -124,6 +124,17 @@ def make_graph(P, torch, wl, dev, seed=0):
     return g
 
 
+def ncu_traffic(wl_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per SpMM launch from the committed ncu capture
+    (profiles/, CBG workload only); None when no capture matches the workload."""
+    p = os.path.join(ROOT, "profiles", "spmm_ncu_latest.json")
+    if wl_key != "cbg" or not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        d = json.load(f)
+    return d.get("dram_bytes_per_launch"), d.get("xbar2l1_read_bytes_per_launch")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -319,6 +330,7 @@ def run_ours(args, wl):
     peak, peak_src = peaks()
     alg_bytes = algorithmic_bytes_spmm(nnz, n, fout)
     achieved = alg_bytes / (spmm_ms * 1e-3) / 1e9
+    traffic, xbar_bytes = ncu_traffic(args.workload)
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timing
     e2e_s = 0.0
@@ -361,9 +373,12 @@ def run_ours(args, wl):
                 "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "spmm_rows_vec_kernel<8,1> (CSR SpMM, fwd and A^T launches)",
+                     "traffic": traffic, "kernel": "spmm_rows_vec_kernel<8,1> (CSR SpMM, fwd and A^T launches)",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": spmm_ms, "peak_source": peak_src,
                      "frac_of_8TBs_nominal": achieved / 8000.0,
+                     "l2_to_sm_gather_GBps": (xbar_bytes / (spmm_ms * 1e-3) / 1e9) if xbar_bytes else None,
+                     "note": "the gathered feature rows (nnz*F*4 B per launch) are L2 hits but L1 misses; the kernel "
+                             "runs at the L2->SM fabric limit (DESIGN.md section 3), DRAM traffic = algorithmic bytes",
                      "how": "CUDA events around gcnb_spmm alone, L2 flushed before each launch, mean of %d launches" % len(sp_ms)},
         "wall_s_timed_region": wall,
     }
