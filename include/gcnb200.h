@@ -113,6 +113,13 @@ int gcnb_graph_get_info(const gcnb_graph* g, gcnb_graph_info* info);
  * d_values fp32 [nnz], row-major / columns ascending. */
 int gcnb_graph_export_coo(const gcnb_graph* g, int64_t* d_indices, float* d_values, void* stream);
 
+/* Sub-matrix of A (transpose = 0) or of A^T (transpose = 1): rows [r0, r1) x columns [c0, c1) as a
+ * new handle with local row ids 0..r1-r0 and column ids shifted by -c0 (+ col_shift).  Used by the
+ * 1-D row partition across GPUs (one block per source rank).  n_cols_out >= c1-c0+col_shift is the
+ * column count recorded in the new handle.  sync. */
+int gcnb_graph_block(const gcnb_graph* g, int transpose, int64_t r0, int64_t r1, int64_t c0, int64_t c1,
+                     int64_t col_shift, int64_t n_cols_out, void* stream, gcnb_graph** out);
+
 /* Copy the device CSR (transpose = 0) or the CSR of A^T (transpose = 1) into caller
  * buffers: d_rowptr int32 [rows+1], d_col int32 [nnz], d_val fp32 [nnz]. */
 int gcnb_graph_export_csr(const gcnb_graph* g, int transpose, int32_t* d_rowptr, int32_t* d_col,
@@ -124,6 +131,7 @@ int gcnb_graph_export_csr(const gcnb_graph* g, int transpose, int32_t* d_rowptr,
 
 #define GCNB_SPMM_TRANSPOSE 1 /* use A^T (backward of pygcn/layers.py:34)               */
 #define GCNB_SPMM_RELU 2      /* fuse the caller's F.relu (pygcn/models.py:49,53,56)    */
+#define GCNB_SPMM_ACCUMULATE 4 /* out += A*b before bias/relu (column-blocked multi-GPU SpMM) */
 
 /* out[r, 0:f] = sum_e val[e] * b[col[e], 0:f]  (+ bias[0:f]) (then max(.,0))
  * `torch.spmm(adj, support)` + `output + self.bias` (pygcn/layers.py:34-36).

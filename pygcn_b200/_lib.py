@@ -23,7 +23,7 @@ BIN_EDGES = (0, 1, 9, 33, 1025)
 
 # flags (mirror include/gcnb200.h)
 BUILD_SYMMETRIZE, BUILD_SELF_LOOPS, BUILD_ROW_NORMALIZE = 1, 2, 4
-SPMM_TRANSPOSE, SPMM_RELU = 1, 2
+SPMM_TRANSPOSE, SPMM_RELU, SPMM_ACCUMULATE = 1, 2, 4
 GEMM_FP32, GEMM_TF32X3, GEMM_AUTO = 0, 1, 2
 LAYER_RELU, LAYER_NEED_DX, LAYER_NEED_DW, LAYER_NEED_DB = 1, 2, 4, 8
 
@@ -52,6 +52,7 @@ SIGNATURES = {
     "gcnb_graph_from_dense": (c_int, [c_i64, c_i64, c_vp, c_i64, c_vp, ctypes.POINTER(c_vp)]),
     "gcnb_graph_free": (None, [c_vp]),
     "gcnb_graph_get_info": (c_int, [c_vp, ctypes.POINTER(GraphInfo)]),
+    "gcnb_graph_block": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, ctypes.POINTER(c_vp)]),
     "gcnb_graph_export_coo": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "gcnb_graph_export_csr": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "gcnb_spmm": (c_int, [c_vp, c_int, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),

@@ -86,9 +86,10 @@ extern "C" int gcnb_spmm(const gcnb_graph* g, int flags, const float* d_b, int64
                          const float* d_bias, float* d_out, int64_t ldo, void* d_ws, size_t ws_bytes,
                          void* stream) {
   GCNB_REQUIRE(g != nullptr, "spmm: null graph");
+  GCNB_REQUIRE(!(flags & GCNB_SPMM_TRANSPOSE) || g->has_transpose, "spmm: this handle is a block without a transpose");
   const CsrView& v = (flags & GCNB_SPMM_TRANSPOSE) ? g->bwd : g->fwd;
   return spmm_launch(v, d_b, ldb, f, d_bias, (flags & GCNB_SPMM_RELU) != 0, d_out, ldo, d_ws, ws_bytes,
-                     (cudaStream_t)stream);
+                     (cudaStream_t)stream, (flags & GCNB_SPMM_ACCUMULATE) != 0);
 }
 
 extern "C" size_t gcnb_spmm_workspace_bytes(const gcnb_graph* g, int flags, int64_t f) {
@@ -166,6 +167,7 @@ extern "C" int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_
                                    float* d_dw, float* d_db, float* d_dx, int64_t lddx, void* d_ws,
                                    size_t ws_bytes, void* stream) {
   GCNB_REQUIRE(g != nullptr, "layer_backward: null graph");
+  GCNB_REQUIRE(g->has_transpose, "layer_backward: this handle is a block without a transpose");
   GCNB_REQUIRE(fin > 0 && fout > 0, "layer_backward: bad feature sizes");
   GCNB_REQUIRE(ldg >= fout, "layer_backward: ldg < out_features");
   cudaStream_t st = (cudaStream_t)stream;

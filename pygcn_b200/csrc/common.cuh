@@ -60,7 +60,8 @@ constexpr int kLongRowThreshold = GCNB_BIN_EDGE_4;  // deg >= this -> split
 constexpr int kLongChunk = 1024;
 
 int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const float* bias,
-                bool relu, float* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t stream);
+                bool relu, float* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t stream,
+                bool accumulate = false);
 size_t spmm_workspace_bytes(const CsrView& a, int64_t f);
 
 int gemm_fp32_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs, int64_t a_cs,
@@ -103,6 +104,7 @@ struct gcnb_graph {
   int32_t* t_col = nullptr;     // may alias col
   float* t_val = nullptr;
   bool pattern_symmetric = false;
+  bool has_transpose = true;  // false for row/column blocks cut by gcnb_graph_block
   int32_t* long_rows = nullptr;
   int32_t* long_chunk_ptr = nullptr;
   int32_t* t_long_rows = nullptr;

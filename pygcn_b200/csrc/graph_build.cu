@@ -175,6 +175,39 @@ __global__ void long_rows_fill_kernel(int64_t n, const int32_t* __restrict__ lon
   }
 }
 
+// rows [r0, r1) x cols [c0, c1) of a CSR: count, then fill (storage order preserved)
+__global__ void block_count_kernel(int64_t r0, int64_t n_rows, int32_t c0, int32_t c1,
+                                   const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                   int32_t* __restrict__ counts) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int cnt = 0;
+  for (int e = rowptr[r0 + r]; e < rowptr[r0 + r + 1]; ++e) {
+    const int c = col[e];
+    cnt += (c >= c0 && c < c1);
+  }
+  counts[r] = cnt;
+}
+
+__global__ void block_fill_kernel(int64_t r0, int64_t n_rows, int32_t c0, int32_t c1, int32_t shift,
+                                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                  const float* __restrict__ val, const int32_t* __restrict__ new_rowptr,
+                                  int32_t* __restrict__ new_col, float* __restrict__ new_val,
+                                  int32_t* __restrict__ new_rows) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int o = new_rowptr[r];
+  for (int e = rowptr[r0 + r]; e < rowptr[r0 + r + 1]; ++e) {
+    const int c = col[e];
+    if (c >= c0 && c < c1) {
+      new_col[o] = c - c0 + shift;
+      new_val[o] = val[e];
+      new_rows[o] = (int32_t)r;
+      ++o;
+    }
+  }
+}
+
 __global__ void sum_i32_kernel(const int32_t* __restrict__ v, int64_t n, unsigned long long* out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && v[i] != 0) atomicAdd(out, (unsigned long long)v[i]);
@@ -379,8 +412,18 @@ int build_schedule(gcnb_graph* g, const int32_t* rowptr, int64_t n, CsrView* vie
 }
 
 // g->rowptr/col/val hold a CSR whose rows are in order; `rows` = expanded row ids (device, nnz).
-int finalize(gcnb_graph* g, const int32_t* rows, cudaStream_t st) {
+int finalize(gcnb_graph* g, const int32_t* rows, cudaStream_t st, bool with_transpose = true) {
   const int64_t nnz = g->nnz;
+  if (!with_transpose) {
+    g->has_transpose = false;
+    g->pattern_symmetric = false;
+    g->fwd.n_rows = g->n_rows; g->fwd.n_cols = g->n_cols; g->fwd.nnz = nnz;
+    g->fwd.rowptr = g->rowptr; g->fwd.col = g->col; g->fwd.val = g->val;
+    g->bwd = CsrView();
+    GCNB_TRY(build_schedule(g, g->rowptr, g->n_rows, &g->fwd, &g->long_rows, &g->long_chunk_ptr, st));
+    GCNB_CUDA(cudaStreamSynchronize(st));
+    return GCNB_OK;
+  }
   // ---- transpose: stable radix sort of entry ids by column
   DevBuf key_out, perm_in, perm_out, temp, differs;
   GCNB_TRY(key_out.alloc((size_t)nnz * 4));
@@ -760,6 +803,61 @@ extern "C" int gcnb_graph_from_dense(int64_t n_rows, int64_t n_cols, const float
   GCNB_TRY(check_dims(n_rows, n_cols, 0));
   GCNB_TRY(gcnb_check_device());
   const int s = from_dense_impl(out, n_rows, n_cols, d_a, lda, (cudaStream_t)stream);
+  GCNB_BUILD_EPILOGUE(s);
+}
+
+extern "C" int gcnb_graph_block(const gcnb_graph* g, int transpose, int64_t r0, int64_t r1, int64_t c0,
+                                int64_t c1, int64_t col_shift, int64_t n_cols_out, void* stream,
+                                gcnb_graph** out) {
+  GCNB_REQUIRE(out != nullptr, "graph_block: out is null");
+  *out = nullptr;
+  GCNB_REQUIRE(g != nullptr, "graph_block: null graph");
+  GCNB_REQUIRE(!transpose || g->has_transpose, "graph_block: handle has no transpose");
+  const CsrView& v = transpose ? g->bwd : g->fwd;
+  GCNB_REQUIRE(0 <= r0 && r0 <= r1 && r1 <= v.n_rows, "graph_block: bad row range");
+  GCNB_REQUIRE(0 <= c0 && c0 <= c1 && c1 <= v.n_cols, "graph_block: bad column range");
+  GCNB_REQUIRE(col_shift >= 0 && n_cols_out >= (c1 - c0) + col_shift, "graph_block: bad column shift");
+  GCNB_TRY(check_dims(r1 - r0, n_cols_out, 0));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nr = r1 - r0;
+  auto impl = [&]() -> int {
+    DevBuf counts, rowptr, temp, total;
+    GCNB_TRY(counts.alloc((size_t)(nr + 1) * 4));
+    GCNB_TRY(rowptr.alloc((size_t)(nr + 1) * 4));
+    GCNB_TRY(total.alloc(8));
+    GCNB_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)(nr + 1) * 4, st));
+    GCNB_CUDA(cudaMemsetAsync(total.p, 0, 8, st));
+    if (nr > 0) {
+      block_count_kernel<<<blocks_for(nr), kT, 0, st>>>(r0, nr, (int32_t)c0, (int32_t)c1, v.rowptr, v.col,
+                                                        counts.as<int32_t>());
+      sum_i32_kernel<<<blocks_for(nr), kT, 0, st>>>(counts.as<int32_t>(), nr, total.as<unsigned long long>());
+      GCNB_LAUNCH_CHECK();
+    }
+    size_t tb = 0;
+    GCNB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.as<int32_t>(), rowptr.as<int32_t>(), (int)(nr + 1), st));
+    GCNB_TRY(temp.alloc(tb));
+    GCNB_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tb, counts.as<int32_t>(), rowptr.as<int32_t>(), (int)(nr + 1), st));
+    int64_t nnz = 0;
+    GCNB_CUDA(cudaMemcpyAsync(&nnz, total.p, 8, cudaMemcpyDeviceToHost, st));
+    GCNB_CUDA(cudaStreamSynchronize(st));
+    gcnb_graph* b = new_graph(nr, n_cols_out, nnz);
+    GCNB_REQUIRE(b != nullptr, "graph: host allocation failed");
+    *out = b;
+    DevBuf rows32;
+    GCNB_TRY(rows32.alloc((size_t)nnz * 4));
+    GCNB_TRY(graph_alloc(b, &b->rowptr, nr + 1));
+    GCNB_TRY(graph_alloc(b, &b->col, nnz));
+    GCNB_TRY(graph_alloc(b, &b->val, nnz));
+    GCNB_CUDA(cudaMemcpyAsync(b->rowptr, rowptr.p, (size_t)(nr + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    if (nr > 0 && nnz > 0) {
+      block_fill_kernel<<<blocks_for(nr), kT, 0, st>>>(r0, nr, (int32_t)c0, (int32_t)c1, (int32_t)col_shift,
+                                                       v.rowptr, v.col, v.val, b->rowptr, b->col, b->val,
+                                                       rows32.as<int32_t>());
+      GCNB_LAUNCH_CHECK();
+    }
+    return finalize(b, rows32.as<int32_t>(), st, /*with_transpose=*/false);
+  };
+  const int s = impl();
   GCNB_BUILD_EPILOGUE(s);
 }
 

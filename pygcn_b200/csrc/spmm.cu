@@ -121,8 +121,18 @@ __device__ __forceinline__ void reduce_slots(float4 (&acc)[CH]) {
 
 __device__ __forceinline__ void store_row_chunk(float* out_row, int q, int f, bool vec_out,
                                                 float4 a, const float* __restrict__ bias,
-                                                bool relu) {
+                                                bool relu, bool accumulate) {
   float r[4] = {a.x, a.y, a.z, a.w};
+  if (accumulate) {  // out += A*B (column-blocked multi-GPU SpMM adds one source block at a time)
+    if (vec_out) {
+      const float4 o = *reinterpret_cast<const float4*>(out_row + 4 * q);
+      r[0] += o.x; r[1] += o.y; r[2] += o.z; r[3] += o.w;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (4 * q + t < f) r[t] += out_row[4 * q + t];
+    }
+  }
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     const int c = 4 * q + t;
@@ -146,7 +156,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 spmm_rows_vec_kernel(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                      const float* __restrict__ val, const float* __restrict__ b, int64_t ldb, int f,
                      const float* __restrict__ bias, int relu, float* __restrict__ out, int64_t ldo,
-                     int vec_out, int skip_long) {
+                     int vec_out, int skip_long, int accumulate) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (row >= n_rows) return;
@@ -164,7 +174,7 @@ spmm_rows_vec_kernel(int n_rows, const int32_t* __restrict__ rowptr, const int32
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
       const int q = k * LPR + lane;
-      if (q < f4) store_row_chunk(out_row, q, f, vec_out, acc[k], bias, relu);
+      if (q < f4) store_row_chunk(out_row, q, f, vec_out, acc[k], bias, relu, accumulate);
     }
   }
 }
@@ -212,7 +222,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 spmm_long_fixup_kernel(int n_long_rows, const int32_t* __restrict__ long_rows,
                        const int32_t* __restrict__ long_chunk_ptr, const float* __restrict__ partial,
                        int ldp, int f, const float* __restrict__ bias, int relu,
-                       float* __restrict__ out, int64_t ldo) {
+                       float* __restrict__ out, int64_t ldo, int accumulate) {
   const int lane = threadIdx.x & 31;
   const int li = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (li >= n_long_rows) return;
@@ -222,6 +232,7 @@ spmm_long_fixup_kernel(int n_long_rows, const int32_t* __restrict__ long_rows,
   for (int j = lane; j < f; j += 32) {
     float acc = 0.f;
     for (int c = c0; c < c1; ++c) acc += partial[(int64_t)c * ldp + j];
+    if (accumulate) acc += out[(int64_t)row * ldo + j];
     if (bias) acc += __ldg(bias + j);
     if (relu) acc = fmaxf(acc, 0.f);
     out[(int64_t)row * ldo + j] = acc;
@@ -234,7 +245,7 @@ spmm_rows_scalar_kernel(int n_rows, const int32_t* __restrict__ rowptr,
                         const int32_t* __restrict__ col, const float* __restrict__ val,
                         const float* __restrict__ b, int64_t ldb, int f,
                         const float* __restrict__ bias, int relu, float* __restrict__ out,
-                        int64_t ldo) {
+                        int64_t ldo, int accumulate) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (row >= n_rows) return;
@@ -259,6 +270,7 @@ spmm_rows_scalar_kernel(int n_rows, const int32_t* __restrict__ rowptr,
       }
     }
     if (j < f) {
+      if (accumulate) acc += out[(int64_t)row * ldo + j];
       if (bias) acc += __ldg(bias + j);
       if (relu) acc = fmaxf(acc, 0.f);
       out[(int64_t)row * ldo + j] = acc;
@@ -270,13 +282,14 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 template <int LPR, int CH>
 int launch_vec(const CsrView& a, const float* b, int64_t ldb, int f, const float* bias, bool relu,
-               float* out, int64_t ldo, bool vec_out, float* partial, int ldp, cudaStream_t st) {
+               bool accumulate, float* out, int64_t ldo, bool vec_out, float* partial, int ldp,
+               cudaStream_t st) {
   const bool has_long = a.n_long_rows > 0;
   const int grid = (int)ceil_div(a.n_rows, kWarpsPerCta);
   if (grid > 0) {
     spmm_rows_vec_kernel<LPR, CH><<<grid, kWarpsPerCta * 32, 0, st>>>(
         (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, f, bias, relu ? 1 : 0, out, ldo,
-        vec_out ? 1 : 0, has_long ? 1 : 0);
+        vec_out ? 1 : 0, has_long ? 1 : 0, accumulate ? 1 : 0);
     GCNB_LAUNCH_CHECK();
   }
   if (has_long) {
@@ -288,7 +301,7 @@ int launch_vec(const CsrView& a, const float* b, int64_t ldb, int f, const float
     const int g2 = (int)ceil_div(a.n_long_rows, kWarpsPerCta);
     spmm_long_fixup_kernel<<<g2, kWarpsPerCta * 32, 0, st>>>(
         (int)a.n_long_rows, a.long_rows, a.long_chunk_ptr, partial, ldp, f, bias, relu ? 1 : 0, out,
-        ldo);
+        ldo, accumulate ? 1 : 0);
     GCNB_LAUNCH_CHECK();
   }
   return GCNB_OK;
@@ -304,7 +317,8 @@ size_t spmm_workspace_bytes(const CsrView& a, int64_t f) {
 }
 
 int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const float* bias,
-                bool relu, float* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st) {
+                bool relu, float* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st,
+                bool accumulate) {
   GCNB_REQUIRE(f > 0 && f <= (1 << 20), "spmm: feature width %lld out of range", (long long)f);
   GCNB_REQUIRE(ldb >= f && ldo >= f, "spmm: leading dimension smaller than width");
   GCNB_REQUIRE(a.n_rows < (1ll << 31), "spmm: too many rows");
@@ -323,12 +337,13 @@ int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const 
     // generic path handles long rows too (a warp walks the whole row)
     const int grid = (int)ceil_div(a.n_rows, kWarpsPerCta);
     spmm_rows_scalar_kernel<<<grid, kWarpsPerCta * 32, 0, st>>>(
-        (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, (int)f, bias, relu ? 1 : 0, out, ldo);
+        (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, (int)f, bias, relu ? 1 : 0, out, ldo,
+        accumulate ? 1 : 0);
     GCNB_LAUNCH_CHECK();
     return GCNB_OK;
   }
 #define GCNB_SPMM_CASE(LPR, CH) \
-  return launch_vec<LPR, CH>(a, b, ldb, (int)f, bias, relu, out, ldo, vec_out, partial, ldp, st)
+  return launch_vec<LPR, CH>(a, b, ldb, (int)f, bias, relu, accumulate, out, ldo, vec_out, partial, ldp, st)
   if (f4 <= 1) GCNB_SPMM_CASE(1, 1);
   if (f4 <= 2) GCNB_SPMM_CASE(2, 1);
   if (f4 <= 4) GCNB_SPMM_CASE(4, 1);
@@ -342,7 +357,7 @@ int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const 
   for (int64_t f0 = 0; f0 < f; f0 += 512) {
     const int64_t fw = (f - f0 < 512) ? (f - f0) : 512;
     GCNB_TRY(spmm_launch(a, b + f0, ldb, fw, bias ? bias + f0 : nullptr, relu, out + f0, ldo, ws,
-                         ws_bytes, st));
+                         ws_bytes, st, accumulate));
   }
   return GCNB_OK;
 }

@@ -1,0 +1,409 @@
+"""Multi-GPU GCN layer: 1-D row partition of A-hat over the GPUs of one node.
+
+The reference is single-process / single-GPU (no torch.distributed anywhere); this is the
+B200-native scaling of its hot path (pygcn/layers.py:32-38 + autograd):
+
+  * rank p owns the contiguous row block p of A-hat (and the matching rows of X, out, G), block
+    boundaries balance stored entries (nnz), W and b are replicated;
+  * the row block is cut into P column blocks A[p,q], one per source rank, with column ids local
+    to the source block, so the SpMM consumes the exchanged panel one source block at a time:
+        out_p = sum_q A[p,q] . S_q ,      S_q = X_q W  computed on rank q
+    the diagonal block runs first while the P-1 remote panels are in flight (NCCL send/recv over
+    NVLink on the communicator's stream); block q is accumulated as soon as its panel has landed;
+    bias/ReLU are applied by the last accumulation;
+  * backward uses the same scheme on the row block of A-hat^T with G as the exchanged panel
+    (atomic-free, deterministic), then dW/db are summed with one all-reduce.
+
+One process per GPU (`torchrun`), `torch.distributed` for the plumbing.  The arithmetic is behind
+an `ops` object: `CudaOps` (libgcnb200.so) in production; the CPU tests of the host logic
+(tests/test_dist_gloo.py, gloo, world size 2) inject a numpy implementation.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+from torch.autograd.function import once_differentiable
+
+
+# ---------------------------------------------------------------------------- host logic
+def partition_rows_by_nnz(rowptr, world):
+    """Row-block boundaries [b_0=0, ..., b_world=N] with ~equal stored entries per block.
+
+    rowptr: 1-D integer tensor/array of length N+1 (host).  Boundaries are non-decreasing; a block
+    may be empty when there are fewer rows than ranks.
+    """
+    rp = torch.as_tensor(rowptr, dtype=torch.int64).cpu()
+    n = rp.numel() - 1
+    nnz = int(rp[-1])
+    bounds = [0]
+    for k in range(1, world):
+        target = (nnz * k) // world
+        r = int(torch.searchsorted(rp, torch.tensor([target], dtype=torch.int64), right=False)[0])
+        r = min(max(r, bounds[-1]), n)
+        bounds.append(r)
+    bounds.append(n)
+    return bounds
+
+
+def exchange_order(rank, world):
+    """Source blocks in the order rank `rank` consumes them: own block first, then the block of
+    rank+1, rank+2, ... (step k: receive from (rank+k) % world, send own panel to (rank-k) % world).
+    Every step is a perfect matching, so all NVLink ports are busy in every step."""
+    return [(rank + k) % world for k in range(world)]
+
+
+class DistGraph:
+    """Row block `rank` of A-hat and of A-hat^T, each cut into `world` column blocks."""
+
+    def __init__(self, rank, world, bounds, fwd_blocks, bwd_blocks, nnz_local, nnz_global):
+        self.rank, self.world = rank, world
+        self.bounds = list(bounds)
+        self.fwd_blocks = fwd_blocks  # [q] -> block of shape [n_rank, n_q]
+        self.bwd_blocks = bwd_blocks
+        self.nnz_local, self.nnz_global = nnz_local, nnz_global
+
+    def n_rows(self, q=None):
+        q = self.rank if q is None else q
+        return self.bounds[q + 1] - self.bounds[q]
+
+    @classmethod
+    def from_graph(cls, graph, rank, world, bounds=None):
+        """Cut the row block of `rank` out of a full device `Graph` (CUDA)."""
+        from . import _lib
+        from .graph import Graph, _stream_ptr
+
+        lib = _lib.load()
+        if bounds is None:
+            bounds = partition_rows_by_nnz(graph.csr()[0].cpu(), world)
+        r0, r1 = bounds[rank], bounds[rank + 1]
+
+        def cut(transpose):
+            blocks = []
+            with torch.cuda.device(graph.device):
+                for q in range(world):
+                    c0, c1 = bounds[q], bounds[q + 1]
+                    out = ctypes.c_void_p()
+                    st = lib.gcnb_graph_block(graph._h, 1 if transpose else 0, r0, r1, c0, c1, 0, max(c1 - c0, 0),
+                                              _stream_ptr(graph.device), ctypes.byref(out))
+                    _lib.check(st, "gcnb_graph_block")
+                    blocks.append(Graph(out.value, graph.device, "block[%d,%d]%s" % (rank, q, "^T" if transpose else "")))
+            return blocks
+
+        fwd = cut(False)
+        bwd = cut(True)
+        return cls(rank, world, bounds, fwd, bwd, sum(b.nnz for b in fwd), graph.nnz)
+
+
+# ---------------------------------------------------------------------------- arithmetic backends
+class CudaOps:
+    """The product backend: every call is a kernel of libgcnb200.so on the current stream."""
+
+    def __init__(self, precision="auto"):
+        from . import _lib
+        from . import functional as F_
+
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.F = F_
+        self.precision = F_._PRECISIONS[precision]
+
+    def _sp(self, dev):
+        return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def gemm(self, a, b):
+        """a [m,k] @ b [k,n] (any strides)."""
+        m, k = a.shape
+        n = b.shape[1]
+        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            ws = self.F._ws(self.lib.gcnb_gemm_workspace_bytes(m, n, k, self.precision), a.device)
+            st = self.lib.gcnb_gemm(m, n, k, a.data_ptr(), a.stride(0), a.stride(1), b.data_ptr(), b.stride(0),
+                                    b.stride(1), out.data_ptr(), max(n, 1), self.precision, ws.data_ptr(), ws.numel(),
+                                    self._sp(a.device))
+        self._lib.check(st, "gcnb_gemm")
+        return out
+
+    def spmm_block(self, block, dense, out, accumulate, bias=None, relu=False):
+        """out (+)= block @ dense (+ bias) (relu)."""
+        f = dense.shape[1]
+        flags = (self._lib.SPMM_ACCUMULATE if accumulate else 0) | (self._lib.SPMM_RELU if relu else 0)
+        with torch.cuda.device(dense.device):
+            ws = self.F._ws(self.lib.gcnb_spmm_workspace_bytes(block._h, 0, f), dense.device)
+            st = self.lib.gcnb_spmm(block._h, flags, dense.data_ptr(), dense.stride(0) if dense.shape[0] > 1 else f, f,
+                                    bias.data_ptr() if bias is not None else None, out.data_ptr(), out.stride(0)
+                                    if out.shape[0] > 1 else f, ws.data_ptr(), ws.numel(), self._sp(dense.device))
+        self._lib.check(st, "gcnb_spmm")
+        return out
+
+    def colsum(self, g, y=None):
+        """(column sums of g [masked by y > 0], masked g or g itself)."""
+        n, f = g.shape
+        out = torch.empty((f,), dtype=torch.float32, device=g.device)
+        gm = torch.empty_like(g) if y is not None else None
+        with torch.cuda.device(g.device):
+            ws = self.F._ws(self.lib.gcnb_colsum_workspace_bytes(n, f), g.device)
+            st = self.lib.gcnb_colsum(n, f, g.data_ptr(), g.stride(0) if n > 1 else f,
+                                      y.data_ptr() if y is not None else None, f,
+                                      gm.data_ptr() if gm is not None else None, f, out.data_ptr(), ws.data_ptr(),
+                                      ws.numel(), self._sp(g.device))
+        self._lib.check(st, "gcnb_colsum")
+        return out, (gm if gm is not None else g)
+
+    def empty(self, shape, like):
+        return torch.empty(shape, dtype=torch.float32, device=like.device)
+
+
+# ---------------------------------------------------------------------------- the exchange + layer
+def _exchange_panels(panel, dgraph, group, empty):
+    """Post the P-1 send/recv steps for `panel` (this rank's [n_p, F] block).  Returns
+    {source q: (buffer, work)}; wait on `work` before reading `buffer`."""
+    p, world = dgraph.rank, dgraph.world
+    f = panel.shape[1]
+    pending = {}
+    for k in range(1, world):
+        src = (p + k) % world
+        dst = (p - k) % world
+        buf = empty((dgraph.n_rows(src), f), panel)
+        works = dist.batch_isend_irecv([dist.P2POp(dist.isend, panel, dst, group),
+                                        dist.P2POp(dist.irecv, buf, src, group)])
+        pending[src] = (buf, works)
+    return pending
+
+
+def _wait(works):
+    for w in works:
+        w.wait()
+
+
+def dist_spmm(ops, dgraph, blocks, panel, bias=None, relu=False, group=None):
+    """out_p = sum_q blocks[q] @ panel_q (+ bias) (relu), panels exchanged while the diagonal block runs."""
+    p, world = dgraph.rank, dgraph.world
+    out = ops.empty((dgraph.n_rows(), panel.shape[1]), panel)
+    if world == 1:
+        return ops.spmm_block(blocks[0], panel, out, False, bias, relu)
+    pending = _exchange_panels(panel, dgraph, group, ops.empty)
+    order = exchange_order(p, world)
+    ops.spmm_block(blocks[p], panel, out, False)
+    for i, q in enumerate(order[1:], start=1):
+        buf, works = pending[q]
+        _wait(works)
+        last = i == world - 1
+        ops.spmm_block(blocks[q], buf, out, True, bias if last else None, relu and last)
+    return out
+
+
+def dist_layer_forward(ops, dgraph, x, w, b, relu=False, group=None):
+    """Row block of  A (X W) + b  (pygcn/layers.py:33-36) for this rank."""
+    support = ops.gemm(x, w)
+    return dist_spmm(ops, dgraph, dgraph.fwd_blocks, support, b, relu, group)
+
+
+def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=True, group=None):
+    """(dX rows of this rank or None, dW, db): dW/db are already summed over ranks."""
+    fin, fout = w.shape
+    db, gm = ops.colsum(g, y)                        # local part of db (+ ReLU mask when y is given)
+    ds = dist_spmm(ops, dgraph, dgraph.bwd_blocks, gm, None, False, group)   # rows p of A^T G
+    dw = ops.gemm(x.t(), ds)                         # local part of X^T dS
+    if dgraph.world > 1:
+        flat = torch.cat([dw.reshape(-1), db.reshape(-1)])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        dw = flat[: fin * fout].reshape(fin, fout)
+        db = flat[fin * fout:]
+    dx = ops.gemm(ds, w.t()) if need_dx else None
+    return dx, dw, (db if has_bias else None)
+
+
+class _DistGCNLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, dgraph, relu, ops, group):
+        out = dist_layer_forward(ops, dgraph, x, weight, bias, relu, group)
+        ctx.dgraph, ctx.relu, ctx.ops, ctx.group = dgraph, relu, ops, group
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight, out if relu else None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w, y = ctx.saved_tensors
+        dx, dw, db = dist_layer_backward(ctx.ops, ctx.dgraph, x, w, g.contiguous(), y, ctx.needs_input_grad[0],
+                                         ctx.has_bias, ctx.group)
+        return dx, dw, db, None, None, None, None
+
+
+class DistGraphConvolution(torch.nn.Module):
+    """`GraphConvolution` over a row-partitioned graph: forward(x_local, dist_graph) -> out_local.
+    Parameters are replicated (same seed on every rank = same init as the reference layer);
+    `.grad` of weight/bias comes out already all-reduced."""
+
+    def __init__(self, in_features, out_features, bias=True, *, fuse_relu=False, precision="auto", group=None):
+        super().__init__()
+        from .layers import GraphConvolution
+
+        self.inner = GraphConvolution(in_features, out_features, bias, fuse_relu=fuse_relu, precision=precision)
+        self.group = group
+        self._ops = None
+
+    @property
+    def weight(self):
+        return self.inner.weight
+
+    @property
+    def bias(self):
+        return self.inner.bias
+
+    def forward(self, input, dgraph):
+        if self._ops is None:
+            self._ops = CudaOps(self.inner.precision)
+        if not input.is_cuda:
+            raise RuntimeError("DistGraphConvolution runs on CUDA devices only (no CPU fallback)")
+        return _DistGCNLayerFn.apply(input.contiguous(), self.inner.weight, self.inner.bias, dgraph,
+                                     self.inner.fuse_relu, self._ops, self.group)
+
+
+# ---------------------------------------------------------------------------- bench entry (N > 1)
+def bench_main(args, wl):
+    """`bench.py --gpus N` under torchrun: weak scaling, N x the single-GPU CBG graph, row-partitioned."""
+    import bench as B
+    import pygcn_b200 as P
+    from . import _lib
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    _lib.check(lib.gcnb_check_device(), "gcnb_check_device")
+    sampler = B.ClockSampler(local_rank) if rank == 0 else None
+
+    n_global = wl["n"] * world
+    wlg = dict(wl, n=n_global)
+    t0 = time.perf_counter()
+    full = B.make_graph(P, torch, wlg, dev)          # same seed on every rank: identical global graph
+    dgraph = DistGraph.from_graph(full, rank, world)
+    nnz_global = full.nnz
+    del full
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    n_local = dgraph.n_rows()
+    fin, fout = wl["fin"], wl["fout"]
+
+    torch.manual_seed(42)
+    layer = DistGraphConvolution(fin, fout).to(dev)
+    gen = torch.Generator(device="cpu")
+    x_host = torch.randn(n_local, fin, generator=gen.manual_seed(1 + rank)).pin_memory()
+    g_host = torch.randn(n_local, fout, generator=gen.manual_seed(100 + rank)).pin_memory()
+    x, g = x_host.to(dev), g_host.to(dev)
+    flush_buf = torch.empty(B.L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def flush():
+        _lib.check(lib.gcnb_l2_flush(ctypes.c_void_p(flush_buf.data_ptr()), flush_buf.numel(),
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "l2_flush")
+
+    def step():
+        layer.inner.weight.grad = None
+        layer.inner.bias.grad = None
+        out = layer(x, dgraph)
+        out.backward(g)
+
+    if sampler:
+        sampler.start()
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        flush()
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if sampler:
+        sampler.in_region = True
+    for i in range(args.steps):
+        flush()
+        ev[i][0].record()
+        step()
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.in_region = False
+    total_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev, dtype=torch.float64)
+    dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = total_ms.item() / args.steps
+    value = nnz_global / (ms_per_step * 1e-3)
+
+    # end to end from pinned host buffers, per rank; max over ranks
+    e2e_s = 0.0
+    for i in range(2 + args.steps):
+        flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        xd = x_host.to(dev, non_blocking=True)
+        gd = g_host.to(dev, non_blocking=True)
+        layer.inner.weight.grad = None
+        layer.inner.bias.grad = None
+        o = layer(xd, dgraph)
+        o.backward(gd)
+        layer.inner.weight.grad.cpu()
+        layer.inner.bias.grad.cpu()
+        torch.cuda.synchronize()
+        if i >= 2:
+            e2e_s += time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = nnz_global / (e2e_t.item() / args.steps)
+    if sampler:
+        sampler.stop()
+
+    # dominant kernel on rank 0: the SpMM over its diagonal block, timed alone
+    blk = dgraph.fwd_blocks[rank]
+    ops = CudaOps()
+    sup = torch.randn(n_local, fout, device=dev)
+    outb = torch.empty(n_local, fout, device=dev)
+    tms = []
+    for it in range(3 + args.steps):
+        flush()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.spmm_block(blk, sup, outb, False)
+        b_.record()
+        if it >= 3:
+            tms.append((a, b_))
+    torch.cuda.synchronize()
+    spmm_ms = sum(a.elapsed_time(b_) for a, b_ in tms) / len(tms)
+    alg = B.algorithmic_bytes_spmm(blk.nnz, n_local, fout)
+    peak, peak_src = B.peaks()
+    achieved = alg / (spmm_ms * 1e-3) / 1e9
+    if rank == 0:
+        line = {
+            "metric": "gcn_layer_fwd_bwd_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"] + " x %d GPUs (N=%d, row-partitioned by nnz)" % (world, n_global),
+                       "nnz": nnz_global, "n": n_global, "in_features": fin, "out_features": fout,
+                       "input_requires_grad": False, "l2": "flushed between timed steps (512 MiB write)",
+                       "cuda_graph": False, "graph_build_s": build_s, "bounds": dgraph.bounds,
+                       "exchange": "P-1 NCCL send/recv steps of the X.W / G panels overlapped with per-source-block SpMM; "
+                                   "all-reduce of dW,db"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": (x_host.numel() + g_host.numel()) * 4,
+                    "d2h_bytes_per_step": (fin * fout + fout) * 4, "ms_per_step": e2e_t.item() / args.steps * 1e3},
+            "gpu_launches": (3 + 2 * world + 4) * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "spmm_rows_vec_kernel<8,1> on rank 0's diagonal block A[0,0]",
+                         "algorithmic_bytes_per_launch": alg, "kernel_ms": spmm_ms, "peak_source": peak_src},
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

@@ -1,0 +1,128 @@
+"""World-size-2 (and 3) CPU tests of the multi-GPU host logic in pygcn_b200/dist.py over gloo:
+nnz-balanced row partition, per-source column blocks, the P-1 step panel exchange, accumulation
+order, dW/db all-reduce.  The arithmetic backend injected here is numpy (the oracle's formulas);
+the product backend (CudaOps) is exercised on GPUs by bench.py --gpus N and test_gpu_parity.py."""
+import os
+import socket
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import gcn_oracle as O
+from pygcn_b200 import dist as D
+
+
+class HostBlock:
+    def __init__(self, idx, val, r0, r1, c0, c1):
+        m = (idx[0] >= r0) & (idx[0] < r1) & (idx[1] >= c0) & (idx[1] < c1)
+        self.row = idx[0][m] - r0
+        self.col = idx[1][m] - c0
+        self.val = val[m]
+        self.shape = (r1 - r0, c1 - c0)
+        self.nnz = int(m.sum())
+
+
+class NumpyOps:
+    def gemm(self, a, b):
+        return torch.from_numpy(a.numpy() @ b.numpy())
+
+    def spmm_block(self, block, dense, out, accumulate, bias=None, relu=False):
+        acc = out.numpy().copy() if accumulate else np.zeros(out.shape, np.float32)
+        np.add.at(acc, block.row, block.val[:, None] * dense.numpy()[block.col])
+        if bias is not None:
+            acc = acc + bias.numpy()
+        if relu:
+            acc = np.maximum(acc, 0)
+        out.copy_(torch.from_numpy(acc.astype(np.float32)))
+        return out
+
+    def colsum(self, g, y=None):
+        gm = g if y is None else torch.where(y > 0, g, torch.zeros_like(g))
+        return gm.sum(0), gm
+
+    def empty(self, shape, like):
+        return torch.empty(shape, dtype=torch.float32)
+
+
+def _problem(n=300, seed=3):
+    rs = np.random.default_rng(seed)
+    src = (n * rs.random(4000) ** 2).astype(np.int64)  # skewed degrees: nnz balance != row balance
+    dst = rs.integers(0, n, 4000)
+    idx, val = O.build_normalized_adjacency(src, dst, n)
+    x = rs.standard_normal((n, 12)).astype(np.float32)
+    g = rs.standard_normal((n, 5)).astype(np.float32)
+    w = rs.standard_normal((12, 5)).astype(np.float32)
+    b = rs.standard_normal(5).astype(np.float32)
+    return n, idx, val, x, g, w, b
+
+
+def _worker(rank, world, port, outdir, relu):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n, idx, val, x, g, w, b = _problem()
+        bounds = D.partition_rows_by_nnz(O.coo_to_csr(idx, n), world)
+        r0, r1 = bounds[rank], bounds[rank + 1]
+        tidx = np.vstack([idx[1], idx[0]])
+        fwd = [HostBlock(idx, val, r0, r1, bounds[q], bounds[q + 1]) for q in range(world)]
+        bwd = [HostBlock(tidx, val, r0, r1, bounds[q], bounds[q + 1]) for q in range(world)]
+        dg = D.DistGraph(rank, world, bounds, fwd, bwd, sum(f.nnz for f in fwd), idx.shape[1])
+        ops = NumpyOps()
+        xt, gt = torch.from_numpy(x[r0:r1].copy()), torch.from_numpy(g[r0:r1].copy())
+        wt, bt = torch.from_numpy(w), torch.from_numpy(b)
+        out = D.dist_layer_forward(ops, dg, xt, wt, bt, relu=relu)
+        dx, dw, db = D.dist_layer_backward(ops, dg, xt, wt, gt, out if relu else None, True, True)
+        np.savez(os.path.join(outdir, "r%d.npz" % rank), out=out.numpy(), dx=dx.numpy(), dw=dw.numpy(), db=db.numpy(),
+                 bounds=np.array(bounds))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world,relu", [(2, False), (2, True), (3, False)])
+def test_row_partitioned_layer_matches_single_process_oracle(world, relu):
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(world, _free_port(), d, relu), nprocs=world, join=True)
+        parts = [np.load(os.path.join(d, "r%d.npz" % r)) for r in range(world)]
+    n, idx, val, x, g, w, b = _problem()
+    _, o_ref = O.c_layer_forward(x, w, b, idx, val, n)
+    gm = g
+    if relu:
+        gm = O.relu_backward(g, o_ref)
+        o_ref = np.maximum(o_ref, 0)
+    dw, db, dx, _ = O.c_layer_backward(x, w, True, idx, val, n, gm)
+    out = np.concatenate([p["out"] for p in parts])
+    dxs = np.concatenate([p["dx"] for p in parts])
+    assert out.shape == o_ref.shape
+    assert O.normwise_err(out, o_ref) < 1e-5
+    assert O.normwise_err(dxs, dx) < 1e-5
+    for p in parts:  # all-reduced: every rank holds the full gradient
+        assert O.normwise_err(p["dw"], dw) < 1e-5 and O.normwise_err(p["db"], db) < 1e-5
+    assert list(parts[0]["bounds"]) == list(parts[-1]["bounds"])
+
+
+def test_partition_balances_nnz_and_exchange_is_a_matching():
+    n, idx, val, *_ = _problem()
+    rowptr = O.coo_to_csr(idx, n)
+    for world in (1, 2, 4, 8):
+        b = D.partition_rows_by_nnz(rowptr, world)
+        assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(world))
+        per = [rowptr[b[i + 1]] - rowptr[b[i]] for i in range(world)]
+        assert max(per) - min(per) <= 2 * np.diff(rowptr).max()  # within one (long) row of perfect balance
+        for k in range(1, world):  # step k: sends and receives form a permutation
+            assert sorted((p - k) % world for p in range(world)) == list(range(world))
+            assert all(D.exchange_order(p, world)[k] == (p + k) % world for p in range(world))
+    # more ranks than rows: empty blocks allowed
+    assert D.partition_rows_by_nnz(np.array([0, 2, 5]), 4)[-1] == 2

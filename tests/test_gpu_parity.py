@@ -409,6 +409,54 @@ def test_cbg_backward_matches_torch_autograd(P, cbg):
         assert ((mine - ref).abs().max() / ref.abs().max()).item() < TOL
 
 
+# ------------------------------------------------------------------ multi-GPU building blocks on one GPU
+@pytest.mark.parametrize("world", [1, 3, 8])
+def test_row_partition_blocks_emulated_on_one_gpu(P, world):
+    """All ranks of the 1-D row partition emulated sequentially on one device (pygcn_b200/dist.py):
+    sum_q A[p,q] S_q with the ACCUMULATE epilogue must equal the rows of the full SpMM, forward and
+    transposed, and the full layer backward must equal the sum of the ranks' contributions."""
+    from pygcn_b200 import dist as D
+
+    n = 5000
+    src, dst = _powerlaw_graph(n, 40000, seed=world, hub_deg=2000)
+    gr = P.Graph.from_edges(cu(src), cu(dst), n)
+    bounds = D.partition_rows_by_nnz(gr.csr()[0].cpu(), world)
+    gen = torch.Generator(device=dev()).manual_seed(world)
+    x = torch.randn(n, 24, generator=gen, device=dev())
+    g = torch.randn(n, 12, generator=gen, device=dev())
+    torch.manual_seed(42)
+    layer = P.GraphConvolution(24, 12, precision="fp32").to(dev())
+    xt = x.clone().requires_grad_(True)
+    ref_out = layer(xt, gr)
+    ref_out.backward(g)
+    ops = D.CudaOps("fp32")
+    w, b = layer.weight.detach(), layer.bias.detach()
+    dgs = [D.DistGraph.from_graph(gr, p, world, bounds) for p in range(world)]
+    assert sum(dg.nnz_local for dg in dgs) == gr.nnz
+    support = [ops.gemm(x[bounds[q]:bounds[q + 1]], w) for q in range(world)]
+    dw_sum = torch.zeros_like(w)
+    db_sum = torch.zeros_like(b)
+    for p, dg in enumerate(dgs):
+        r0, r1 = bounds[p], bounds[p + 1]
+        out = torch.empty(r1 - r0, 12, device=dev())
+        order = D.exchange_order(p, world)
+        for i, q in enumerate(order):
+            last = i == world - 1
+            ops.spmm_block(dg.fwd_blocks[q], support[q], out, i > 0, b if last else None, False)
+        assert ((out - ref_out[r0:r1].detach()).abs().max() / ref_out.abs().max()).item() < TOL
+        ds = torch.empty(r1 - r0, 12, device=dev())
+        for i, q in enumerate(order):
+            ops.spmm_block(dg.bwd_blocks[q], g[bounds[q]:bounds[q + 1]], ds, i > 0)
+        dw_sum += ops.gemm(x[r0:r1].t(), ds)
+        db_sum += ops.colsum(g[r0:r1].contiguous())[0]
+        dx = ops.gemm(ds, w.t())
+        assert ((dx - xt.grad[r0:r1]).abs().max() / xt.grad.abs().max()).item() < TOL
+    assert ((dw_sum - layer.weight.grad).abs().max() / layer.weight.grad.abs().max()).item() < TOL
+    assert ((db_sum - layer.bias.grad).abs().max() / layer.bias.grad.abs().max()).item() < TOL
+    with pytest.raises(RuntimeError):  # blocks carry no transpose
+        P.spmm(dgs[0].fwd_blocks[0], torch.zeros(bounds[1] - bounds[0], 4, device=dev(), requires_grad=True)).sum().backward()
+
+
 # ------------------------------------------------------------------ error behaviour (SURVEY.md 8b)
 def test_errors(P, golden):
     layer = P.GraphConvolution(4, 3)
