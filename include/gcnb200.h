@@ -120,6 +120,15 @@ int gcnb_graph_export_coo(const gcnb_graph* g, int64_t* d_indices, float* d_valu
 int gcnb_graph_block(const gcnb_graph* g, int transpose, int64_t r0, int64_t r1, int64_t c0, int64_t c1,
                      int64_t col_shift, int64_t n_cols_out, void* stream, gcnb_graph** out);
 
+/* Rows [r0, r1) of A (or A^T) restricted to the columns owned by OTHER ranks, with column ids
+ * remapped to the layout of an all-gathered panel of equal-sized (padded) blocks:
+ *     col in [bounds[q], bounds[q+1])  ->  q * pad_rows + (col - bounds[q]),   q != exclude_part
+ * h_bounds is a HOST array of n_parts+1 row boundaries.  The new handle has n_parts*pad_rows
+ * columns.  With exclude_part < 0 no part is excluded (the whole row block, remapped).  sync. */
+int gcnb_graph_block_gathered(const gcnb_graph* g, int transpose, int64_t r0, int64_t r1, int n_parts,
+                              const int64_t* h_bounds, int64_t pad_rows, int exclude_part, void* stream,
+                              gcnb_graph** out);
+
 /* Copy the device CSR (transpose = 0) or the CSR of A^T (transpose = 1) into caller
  * buffers: d_rowptr int32 [rows+1], d_col int32 [nnz], d_val fp32 [nnz]. */
 int gcnb_graph_export_csr(const gcnb_graph* g, int transpose, int32_t* d_rowptr, int32_t* d_col,
@@ -158,7 +167,8 @@ size_t gcnb_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k, int precision)
 
 /* d_out[0:f] = sum_rows g[r, 0:f]  (AddBackward0 of `output + self.bias`, layers.py:36).
  * If d_y != NULL the ReLU mask of the fused epilogue is applied first and the masked
- * gradient is written to d_gm (may alias d_g):  gm = g * [y > 0]. */
+ * gradient is written to d_gm (may alias d_g):  gm = g * [y > 0].  With d_y == NULL and
+ * d_gm != NULL, d_gm receives a copy of g (used to stage G into the padded all-gather panel). */
 int gcnb_colsum(int64_t n_rows, int64_t f, const float* d_g, int64_t ldg, const float* d_y,
                 int64_t ldy, float* d_gm, int64_t ldgm, float* d_out, void* d_ws, size_t ws_bytes,
                 void* stream);

@@ -53,6 +53,8 @@ SIGNATURES = {
     "gcnb_graph_free": (None, [c_vp]),
     "gcnb_graph_get_info": (c_int, [c_vp, ctypes.POINTER(GraphInfo)]),
     "gcnb_graph_block": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, ctypes.POINTER(c_vp)]),
+    "gcnb_graph_block_gathered": (c_int, [c_vp, c_int, c_i64, c_i64, c_int, ctypes.POINTER(c_i64), c_i64, c_int, c_vp,
+                                          ctypes.POINTER(c_vp)]),
     "gcnb_graph_export_coo": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "gcnb_graph_export_csr": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "gcnb_spmm": (c_int, [c_vp, c_int, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),

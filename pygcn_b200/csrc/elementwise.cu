@@ -27,10 +27,8 @@ colsum_partial_kernel(int64_t n_rows, int f, int cw, int64_t rows_per_block,
     if (j < f) {
       for (int64_t r = r0 + ty; r < r1; r += rl) {
         float v = g[r * ldg + j];
-        if (y != nullptr) {
-          v = (y[r * ldy + j] > 0.f) ? v : 0.f;
-          gm[r * ldgm + j] = v;
-        }
+        if (y != nullptr) v = (y[r * ldy + j] > 0.f) ? v : 0.f;
+        if (gm != nullptr) gm[r * ldgm + j] = v;  // masked gradient, or a plain copy when y == NULL
         acc += v;
       }
     }
@@ -100,7 +98,8 @@ int colsum_launch(int64_t n_rows, int64_t f, const float* g, int64_t ldg, const 
     return GCNB_OK;
   }
   GCNB_REQUIRE(g != nullptr && ldg >= f, "colsum: bad gradient operand");
-  GCNB_REQUIRE(y == nullptr || (gm != nullptr && ldy >= f && ldgm >= f), "colsum: bad mask operands");
+  GCNB_REQUIRE(y == nullptr || (gm != nullptr && ldy >= f), "colsum: bad mask operands");
+  GCNB_REQUIRE(gm == nullptr || ldgm >= f, "colsum: ldgm < width");
   const int nb = colsum_blocks(n_rows);
   const size_t need = colsum_workspace_bytes(n_rows, f);
   GCNB_REQUIRE(ws != nullptr && ws_bytes >= need, "colsum: workspace too small (%zu < %zu)", ws_bytes, need);

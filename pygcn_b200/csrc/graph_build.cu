@@ -208,6 +208,48 @@ __global__ void block_fill_kernel(int64_t r0, int64_t n_rows, int32_t c0, int32_
   }
 }
 
+// same as block_count/fill, but columns are remapped through the partition bounds (all-gather layout)
+__device__ __forceinline__ int part_of(const int64_t* __restrict__ bounds, int n_parts, int c) {
+  int lo = 0, hi = n_parts;  // largest q with bounds[q] <= c
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (bounds[mid] <= c) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void gathered_count_kernel(int64_t r0, int64_t n_rows, int n_parts,
+                                      const int64_t* __restrict__ bounds, int exclude,
+                                      const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                      int32_t* __restrict__ counts) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int cnt = 0;
+  for (int e = rowptr[r0 + r]; e < rowptr[r0 + r + 1]; ++e) cnt += (part_of(bounds, n_parts, col[e]) != exclude);
+  counts[r] = cnt;
+}
+
+__global__ void gathered_fill_kernel(int64_t r0, int64_t n_rows, int n_parts,
+                                     const int64_t* __restrict__ bounds, int exclude, int64_t pad_rows,
+                                     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                     const float* __restrict__ val, const int32_t* __restrict__ new_rowptr,
+                                     int32_t* __restrict__ new_col, float* __restrict__ new_val,
+                                     int32_t* __restrict__ new_rows) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int o = new_rowptr[r];
+  for (int e = rowptr[r0 + r]; e < rowptr[r0 + r + 1]; ++e) {
+    const int c = col[e];
+    const int q = part_of(bounds, n_parts, c);
+    if (q != exclude) {
+      new_col[o] = (int32_t)((int64_t)q * pad_rows + (c - bounds[q]));
+      new_val[o] = val[e];
+      new_rows[o] = (int32_t)r;
+      ++o;
+    }
+  }
+}
+
 __global__ void sum_i32_kernel(const int32_t* __restrict__ v, int64_t n, unsigned long long* out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && v[i] != 0) atomicAdd(out, (unsigned long long)v[i]);
@@ -853,6 +895,66 @@ extern "C" int gcnb_graph_block(const gcnb_graph* g, int transpose, int64_t r0, 
       block_fill_kernel<<<blocks_for(nr), kT, 0, st>>>(r0, nr, (int32_t)c0, (int32_t)c1, (int32_t)col_shift,
                                                        v.rowptr, v.col, v.val, b->rowptr, b->col, b->val,
                                                        rows32.as<int32_t>());
+      GCNB_LAUNCH_CHECK();
+    }
+    return finalize(b, rows32.as<int32_t>(), st, /*with_transpose=*/false);
+  };
+  const int s = impl();
+  GCNB_BUILD_EPILOGUE(s);
+}
+
+extern "C" int gcnb_graph_block_gathered(const gcnb_graph* g, int transpose, int64_t r0, int64_t r1, int n_parts,
+                                         const int64_t* h_bounds, int64_t pad_rows, int exclude_part, void* stream,
+                                         gcnb_graph** out) {
+  GCNB_REQUIRE(out != nullptr, "graph_block_gathered: out is null");
+  *out = nullptr;
+  GCNB_REQUIRE(g != nullptr && h_bounds != nullptr && n_parts >= 1, "graph_block_gathered: bad argument");
+  GCNB_REQUIRE(!transpose || g->has_transpose, "graph_block_gathered: handle has no transpose");
+  const CsrView& v = transpose ? g->bwd : g->fwd;
+  GCNB_REQUIRE(0 <= r0 && r0 <= r1 && r1 <= v.n_rows, "graph_block_gathered: bad row range");
+  GCNB_REQUIRE(h_bounds[0] == 0 && h_bounds[n_parts] == v.n_cols, "graph_block_gathered: bounds must cover the columns");
+  for (int q = 0; q < n_parts; ++q)
+    GCNB_REQUIRE(h_bounds[q] <= h_bounds[q + 1] && h_bounds[q + 1] - h_bounds[q] <= pad_rows,
+                 "graph_block_gathered: part %d larger than pad_rows", q);
+  const int64_t n_cols_out = (int64_t)n_parts * pad_rows;
+  GCNB_TRY(check_dims(r1 - r0, n_cols_out, 0));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nr = r1 - r0;
+  auto impl = [&]() -> int {
+    DevBuf counts, rowptr, temp, total, bounds;
+    GCNB_TRY(counts.alloc((size_t)(nr + 1) * 4));
+    GCNB_TRY(rowptr.alloc((size_t)(nr + 1) * 4));
+    GCNB_TRY(total.alloc(8));
+    GCNB_TRY(bounds.alloc((size_t)(n_parts + 1) * 8));
+    GCNB_CUDA(cudaMemcpyAsync(bounds.p, h_bounds, (size_t)(n_parts + 1) * 8, cudaMemcpyHostToDevice, st));
+    GCNB_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)(nr + 1) * 4, st));
+    GCNB_CUDA(cudaMemsetAsync(total.p, 0, 8, st));
+    if (nr > 0) {
+      gathered_count_kernel<<<blocks_for(nr), kT, 0, st>>>(r0, nr, n_parts, bounds.as<int64_t>(), exclude_part,
+                                                           v.rowptr, v.col, counts.as<int32_t>());
+      sum_i32_kernel<<<blocks_for(nr), kT, 0, st>>>(counts.as<int32_t>(), nr, total.as<unsigned long long>());
+      GCNB_LAUNCH_CHECK();
+    }
+    size_t tb = 0;
+    GCNB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.as<int32_t>(), rowptr.as<int32_t>(), (int)(nr + 1), st));
+    GCNB_TRY(temp.alloc(tb));
+    GCNB_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tb, counts.as<int32_t>(), rowptr.as<int32_t>(), (int)(nr + 1), st));
+    int64_t nnz = 0;
+    GCNB_CUDA(cudaMemcpyAsync(&nnz, total.p, 8, cudaMemcpyDeviceToHost, st));
+    GCNB_CUDA(cudaStreamSynchronize(st));
+    gcnb_graph* b = new_graph(nr, n_cols_out, nnz);
+    GCNB_REQUIRE(b != nullptr, "graph: host allocation failed");
+    *out = b;
+    DevBuf rows32;
+    GCNB_TRY(rows32.alloc((size_t)nnz * 4));
+    GCNB_TRY(graph_alloc(b, &b->rowptr, nr + 1));
+    GCNB_TRY(graph_alloc(b, &b->col, nnz));
+    GCNB_TRY(graph_alloc(b, &b->val, nnz));
+    GCNB_CUDA(cudaMemcpyAsync(b->rowptr, rowptr.p, (size_t)(nr + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    if (nr > 0 && nnz > 0) {
+      gathered_fill_kernel<<<blocks_for(nr), kT, 0, st>>>(r0, nr, n_parts, bounds.as<int64_t>(), exclude_part, pad_rows,
+                                                          v.rowptr, v.col, v.val, b->rowptr, b->col, b->val,
+                                                          rows32.as<int32_t>());
       GCNB_LAUNCH_CHECK();
     }
     return finalize(b, rows32.as<int32_t>(), st, /*with_transpose=*/false);

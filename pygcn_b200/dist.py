@@ -5,12 +5,13 @@ B200-native scaling of its hot path (pygcn/layers.py:32-38 + autograd):
 
   * rank p owns the contiguous row block p of A-hat (and the matching rows of X, out, G), block
     boundaries balance stored entries (nnz), W and b are replicated;
-  * the row block is cut into P column blocks A[p,q], one per source rank, with column ids local
-    to the source block, so the SpMM consumes the exchanged panel one source block at a time:
-        out_p = sum_q A[p,q] . S_q ,      S_q = X_q W  computed on rank q
-    the diagonal block runs first while the P-1 remote panels are in flight (NCCL send/recv over
-    NVLink on the communicator's stream); block q is accumulated as soon as its panel has landed;
-    bias/ReLU are applied by the last accumulation;
+  * the row block is cut into the diagonal block A[p,p] (columns this rank owns) and the remote
+    block A[p,~p] whose column ids address the all-gathered panel directly:
+        out_p = A[p,p] . S_p + A[p,~p] . allgather(S) ,      S_q = X_q W  computed on rank q
+    the diagonal block runs first while the NCCL all-gather of the panels is in flight over NVLink
+    (communicator stream); the remote block accumulates once it has landed and applies bias/ReLU.
+    (A finer per-source-rank column blocking was measured first and rejected: every extra pass over
+    the rows costs a read-modify-write of the output rows and shorter gather loops; profiles/.)
   * backward uses the same scheme on the row block of A-hat^T with G as the exchanged panel
     (atomic-free, deterministic), then dW/db are summed with one all-reduce.
 
@@ -51,26 +52,29 @@ def partition_rows_by_nnz(rowptr, world):
     return bounds
 
 
-def exchange_order(rank, world):
-    """Source blocks in the order rank `rank` consumes them: own block first, then the block of
-    rank+1, rank+2, ... (step k: receive from (rank+k) % world, send own panel to (rank-k) % world).
-    Every step is a perfect matching, so all NVLink ports are busy in every step."""
-    return [(rank + k) % world for k in range(world)]
-
-
 class DistGraph:
-    """Row block `rank` of A-hat and of A-hat^T, each cut into `world` column blocks."""
+    """Row block `rank` of A-hat and of A-hat^T, each split into the diagonal block (columns owned
+    by this rank, local ids) and the remote block (all other columns, ids remapped to the layout of
+    the all-gathered panel: source q occupies rows [q*pad_rows, q*pad_rows + n_q))."""
 
-    def __init__(self, rank, world, bounds, fwd_blocks, bwd_blocks, nnz_local, nnz_global):
+    def __init__(self, rank, world, bounds, pad_rows, fwd_diag, fwd_remote, bwd_diag, bwd_remote, nnz_local,
+                 nnz_global):
         self.rank, self.world = rank, world
         self.bounds = list(bounds)
-        self.fwd_blocks = fwd_blocks  # [q] -> block of shape [n_rank, n_q]
-        self.bwd_blocks = bwd_blocks
+        self.pad_rows = pad_rows
+        self.fwd_diag, self.fwd_remote = fwd_diag, fwd_remote
+        self.bwd_diag, self.bwd_remote = bwd_diag, bwd_remote
         self.nnz_local, self.nnz_global = nnz_local, nnz_global
 
     def n_rows(self, q=None):
         q = self.rank if q is None else q
         return self.bounds[q + 1] - self.bounds[q]
+
+    @staticmethod
+    def padded_rows(bounds):
+        """Rows per source slot of the all-gathered panel: the largest block, rounded up to 8."""
+        m = max(bounds[q + 1] - bounds[q] for q in range(len(bounds) - 1))
+        return max(8, (m + 7) // 8 * 8)
 
     @classmethod
     def from_graph(cls, graph, rank, world, bounds=None):
@@ -82,22 +86,29 @@ class DistGraph:
         if bounds is None:
             bounds = partition_rows_by_nnz(graph.csr()[0].cpu(), world)
         r0, r1 = bounds[rank], bounds[rank + 1]
+        pad = cls.padded_rows(bounds)
+        hb = (ctypes.c_int64 * (world + 1))(*bounds)
 
         def cut(transpose):
-            blocks = []
+            tag = "^T" if transpose else ""
             with torch.cuda.device(graph.device):
-                for q in range(world):
-                    c0, c1 = bounds[q], bounds[q + 1]
+                out = ctypes.c_void_p()
+                st = lib.gcnb_graph_block(graph._h, 1 if transpose else 0, r0, r1, r0, r1, 0, max(pad, 1),
+                                          _stream_ptr(graph.device), ctypes.byref(out))
+                _lib.check(st, "gcnb_graph_block")
+                diag = Graph(out.value, graph.device, "diag[%d]%s" % (rank, tag))
+                remote = None
+                if world > 1:
                     out = ctypes.c_void_p()
-                    st = lib.gcnb_graph_block(graph._h, 1 if transpose else 0, r0, r1, c0, c1, 0, max(c1 - c0, 0),
-                                              _stream_ptr(graph.device), ctypes.byref(out))
-                    _lib.check(st, "gcnb_graph_block")
-                    blocks.append(Graph(out.value, graph.device, "block[%d,%d]%s" % (rank, q, "^T" if transpose else "")))
-            return blocks
+                    st = lib.gcnb_graph_block_gathered(graph._h, 1 if transpose else 0, r0, r1, world, hb, pad, rank,
+                                                       _stream_ptr(graph.device), ctypes.byref(out))
+                    _lib.check(st, "gcnb_graph_block_gathered")
+                    remote = Graph(out.value, graph.device, "remote[%d]%s" % (rank, tag))
+            return diag, remote
 
-        fwd = cut(False)
-        bwd = cut(True)
-        return cls(rank, world, bounds, fwd, bwd, sum(b.nnz for b in fwd), graph.nnz)
+        fd, fr = cut(False)
+        bd, br = cut(True)
+        return cls(rank, world, bounds, pad, fd, fr, bd, br, fd.nnz + (fr.nnz if fr is not None else 0), graph.nnz)
 
 
 # ---------------------------------------------------------------------------- arithmetic backends
@@ -116,11 +127,12 @@ class CudaOps:
     def _sp(self, dev):
         return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
-    def gemm(self, a, b):
-        """a [m,k] @ b [k,n] (any strides)."""
+    def gemm(self, a, b, out=None):
+        """a [m,k] @ b [k,n] (any strides); written to the first m rows of `out` when given."""
         m, k = a.shape
         n = b.shape[1]
-        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+        if out is None:
+            out = torch.empty((m, n), dtype=torch.float32, device=a.device)
         with torch.cuda.device(a.device):
             ws = self.F._ws(self.lib.gcnb_gemm_workspace_bytes(m, n, k, self.precision), a.device)
             st = self.lib.gcnb_gemm(m, n, k, a.data_ptr(), a.stride(0), a.stride(1), b.data_ptr(), b.stride(0),
@@ -141,11 +153,13 @@ class CudaOps:
         self._lib.check(st, "gcnb_spmm")
         return out
 
-    def colsum(self, g, y=None):
-        """(column sums of g [masked by y > 0], masked g or g itself)."""
+    def colsum(self, g, y=None, gm=None):
+        """(column sums of g [masked by y > 0], the masked g).  When `gm` (>= n rows) is given the
+        masked gradient -- or a plain copy of g -- is staged into its first n rows."""
         n, f = g.shape
         out = torch.empty((f,), dtype=torch.float32, device=g.device)
-        gm = torch.empty_like(g) if y is not None else None
+        if gm is None and y is not None:
+            gm = torch.empty_like(g)
         with torch.cuda.device(g.device):
             ws = self.F._ws(self.lib.gcnb_colsum_workspace_bytes(n, f), g.device)
             st = self.lib.gcnb_colsum(n, f, g.data_ptr(), g.stride(0) if n > 1 else f,
@@ -160,55 +174,36 @@ class CudaOps:
 
 
 # ---------------------------------------------------------------------------- the exchange + layer
-def _exchange_panels(panel, dgraph, group, empty):
-    """Post the P-1 send/recv steps for `panel` (this rank's [n_p, F] block).  Returns
-    {source q: (buffer, work)}; wait on `work` before reading `buffer`."""
-    p, world = dgraph.rank, dgraph.world
-    f = panel.shape[1]
-    pending = {}
-    for k in range(1, world):
-        src = (p + k) % world
-        dst = (p - k) % world
-        buf = empty((dgraph.n_rows(src), f), panel)
-        works = dist.batch_isend_irecv([dist.P2POp(dist.isend, panel, dst, group),
-                                        dist.P2POp(dist.irecv, buf, src, group)])
-        pending[src] = (buf, works)
-    return pending
+def dist_spmm(ops, dgraph, diag, remote, panel, bias=None, relu=False, group=None):
+    """out_p = diag @ panel[:n_p] + remote @ allgather(panel) (+ bias) (relu).
 
-
-def _wait(works):
-    for w in works:
-        w.wait()
-
-
-def dist_spmm(ops, dgraph, blocks, panel, bias=None, relu=False, group=None):
-    """out_p = sum_q blocks[q] @ panel_q (+ bias) (relu), panels exchanged while the diagonal block runs."""
-    p, world = dgraph.rank, dgraph.world
+    `panel` is this rank's [pad_rows, F] slot (rows past n_p are padding nobody references).  The
+    all-gather of the slots (NCCL over NVLink, on the communicator's stream) runs while the
+    diagonal block is multiplied; the remote block is accumulated once the panel has landed."""
+    world = dgraph.world
     out = ops.empty((dgraph.n_rows(), panel.shape[1]), panel)
     if world == 1:
-        return ops.spmm_block(blocks[0], panel, out, False, bias, relu)
-    pending = _exchange_panels(panel, dgraph, group, ops.empty)
-    order = exchange_order(p, world)
-    ops.spmm_block(blocks[p], panel, out, False)
-    for i, q in enumerate(order[1:], start=1):
-        buf, works = pending[q]
-        _wait(works)
-        last = i == world - 1
-        ops.spmm_block(blocks[q], buf, out, True, bias if last else None, relu and last)
-    return out
+        return ops.spmm_block(diag, panel, out, False, bias, relu)
+    gathered = ops.empty((world * dgraph.pad_rows, panel.shape[1]), panel)
+    work = dist.all_gather_into_tensor(gathered, panel, group=group, async_op=True)
+    ops.spmm_block(diag, panel, out, False)
+    work.wait()
+    return ops.spmm_block(remote, gathered, out, True, bias, relu)
 
 
 def dist_layer_forward(ops, dgraph, x, w, b, relu=False, group=None):
     """Row block of  A (X W) + b  (pygcn/layers.py:33-36) for this rank."""
-    support = ops.gemm(x, w)
-    return dist_spmm(ops, dgraph, dgraph.fwd_blocks, support, b, relu, group)
+    support = ops.empty((dgraph.pad_rows, w.shape[1]), x)
+    ops.gemm(x, w, out=support)
+    return dist_spmm(ops, dgraph, dgraph.fwd_diag, dgraph.fwd_remote, support, b, relu, group)
 
 
 def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=True, group=None):
     """(dX rows of this rank or None, dW, db): dW/db are already summed over ranks."""
     fin, fout = w.shape
-    db, gm = ops.colsum(g, y)                        # local part of db (+ ReLU mask when y is given)
-    ds = dist_spmm(ops, dgraph, dgraph.bwd_blocks, gm, None, False, group)   # rows p of A^T G
+    gm = ops.empty((dgraph.pad_rows, fout), g)
+    db, _ = ops.colsum(g, y, gm)                     # local part of db; G (masked) staged into its slot
+    ds = dist_spmm(ops, dgraph, dgraph.bwd_diag, dgraph.bwd_remote, gm, None, False, group)  # rows p of A^T G
     dw = ops.gemm(x.t(), ds)                         # local part of X^T dS
     if dgraph.world > 1:
         flat = torch.cat([dw.reshape(-1), db.reshape(-1)])
@@ -321,6 +316,43 @@ def bench_main(args, wl):
         step()
     torch.cuda.synchronize()
     dist.barrier()
+
+    # capture the step (kernels + NCCL all-gathers / all-reduce) in a CUDA graph: removes the Python
+    # and launch gaps from the device time, like the single-GPU arm.  All ranks must agree.
+    cg = None
+    if not args.no_cuda_graph:
+        ok = torch.ones(1, device=dev)
+        try:
+            s_ = torch.cuda.Stream()
+            s_.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_):
+                for _ in range(2):
+                    step()
+            torch.cuda.current_stream().wait_stream(s_)
+            torch.cuda.synchronize()
+            layer.inner.weight.grad = None
+            layer.inner.bias.grad = None
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                out_static = layer(x, dgraph)
+                out_static.backward(g)
+            torch.cuda.synchronize()
+        except Exception as e:  # pragma: no cover
+            sys.stderr.write("rank %d: CUDA graph capture failed (%r); timing eager launches\n" % (rank, e))
+            cg = None
+            ok.zero_()
+            torch.cuda.synchronize()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            cg = None
+    eager_step = step
+    if cg is not None:
+        step = cg.replay
+        for _ in range(warm):
+            flush()
+            step()
+    torch.cuda.synchronize()
+    dist.barrier()
     torch.cuda.synchronize()
 
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -366,7 +398,7 @@ def bench_main(args, wl):
         sampler.stop()
 
     # dominant kernel on rank 0: the SpMM over its diagonal block, timed alone
-    blk = dgraph.fwd_blocks[rank]
+    blk = dgraph.fwd_diag
     ops = CudaOps()
     sup = torch.randn(n_local, fout, device=dev)
     outb = torch.empty(n_local, fout, device=dev)
@@ -392,13 +424,13 @@ def bench_main(args, wl):
             "config": {"workload": wl["name"] + " x %d GPUs (N=%d, row-partitioned by nnz)" % (world, n_global),
                        "nnz": nnz_global, "n": n_global, "in_features": fin, "out_features": fout,
                        "input_requires_grad": False, "l2": "flushed between timed steps (512 MiB write)",
-                       "cuda_graph": False, "graph_build_s": build_s, "bounds": dgraph.bounds,
-                       "exchange": "P-1 NCCL send/recv steps of the X.W / G panels overlapped with per-source-block SpMM; "
-                                   "all-reduce of dW,db"},
+                       "cuda_graph": cg is not None, "graph_build_s": build_s, "bounds": dgraph.bounds,
+                       "exchange": "NCCL all-gather of the X.W / G panels overlapped with the diagonal-block SpMM, then "
+                                   "the remote-block SpMM accumulates; all-reduce of dW,db"},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": (x_host.numel() + g_host.numel()) * 4,
                     "d2h_bytes_per_step": (fin * fout + fout) * 4, "ms_per_step": e2e_t.item() / args.steps * 1e3},
-            "gpu_launches": (3 + 2 * world + 4) * args.steps,
+            "gpu_launches": 10 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "spmm_rows_vec_kernel<8,1> on rank 0's diagonal block A[0,0]",
                          "algorithmic_bytes_per_launch": alg, "kernel_ms": spmm_ms, "peak_source": peak_src},

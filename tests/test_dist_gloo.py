@@ -1,6 +1,6 @@
 """World-size-2 (and 3) CPU tests of the multi-GPU host logic in pygcn_b200/dist.py over gloo:
-nnz-balanced row partition, per-source column blocks, the P-1 step panel exchange, accumulation
-order, dW/db all-reduce.  The arithmetic backend injected here is numpy (the oracle's formulas);
+nnz-balanced row partition, diagonal / remote column blocks in the all-gather layout, the padded
+panel all-gather, accumulation, dW/db all-reduce.  The arithmetic backend injected here is numpy (the oracle's formulas);
 the product backend (CudaOps) is exercised on GPUs by bench.py --gpus N and test_gpu_parity.py."""
 import os
 import socket
@@ -17,18 +17,30 @@ from pygcn_b200 import dist as D
 
 
 class HostBlock:
-    def __init__(self, idx, val, r0, r1, c0, c1):
-        m = (idx[0] >= r0) & (idx[0] < r1) & (idx[1] >= c0) & (idx[1] < c1)
+    """rows [r0, r1) of a COO matrix; columns either local to [c0, c1) (diagonal block) or remapped
+    to the padded all-gather layout with part `exclude` left out (remote block)."""
+
+    def __init__(self, idx, val, r0, r1, bounds=None, pad=None, exclude=None, c0=None, c1=None):
+        rows = (idx[0] >= r0) & (idx[0] < r1)
+        if bounds is None:
+            m = rows & (idx[1] >= c0) & (idx[1] < c1)
+            self.col = idx[1][m] - c0
+        else:
+            part = np.searchsorted(np.asarray(bounds), idx[1], side="right") - 1
+            m = rows & (part != exclude)
+            self.col = part[m] * pad + (idx[1][m] - np.asarray(bounds)[part[m]])
         self.row = idx[0][m] - r0
-        self.col = idx[1][m] - c0
         self.val = val[m]
-        self.shape = (r1 - r0, c1 - c0)
         self.nnz = int(m.sum())
 
 
 class NumpyOps:
-    def gemm(self, a, b):
-        return torch.from_numpy(a.numpy() @ b.numpy())
+    def gemm(self, a, b, out=None):
+        r = torch.from_numpy(a.numpy() @ b.numpy())
+        if out is None:
+            return r
+        out[: r.shape[0]] = r
+        return out
 
     def spmm_block(self, block, dense, out, accumulate, bias=None, relu=False):
         acc = out.numpy().copy() if accumulate else np.zeros(out.shape, np.float32)
@@ -40,12 +52,14 @@ class NumpyOps:
         out.copy_(torch.from_numpy(acc.astype(np.float32)))
         return out
 
-    def colsum(self, g, y=None):
-        gm = g if y is None else torch.where(y > 0, g, torch.zeros_like(g))
-        return gm.sum(0), gm
+    def colsum(self, g, y=None, gm=None):
+        m = g if y is None else torch.where(y > 0, g, torch.zeros_like(g))
+        if gm is not None:
+            gm[: m.shape[0]] = m
+        return m.sum(0), m
 
     def empty(self, shape, like):
-        return torch.empty(shape, dtype=torch.float32)
+        return torch.full(shape, float("nan"), dtype=torch.float32)  # padding must never be read
 
 
 def _problem(n=300, seed=3):
@@ -69,9 +83,12 @@ def _worker(rank, world, port, outdir, relu):
         bounds = D.partition_rows_by_nnz(O.coo_to_csr(idx, n), world)
         r0, r1 = bounds[rank], bounds[rank + 1]
         tidx = np.vstack([idx[1], idx[0]])
-        fwd = [HostBlock(idx, val, r0, r1, bounds[q], bounds[q + 1]) for q in range(world)]
-        bwd = [HostBlock(tidx, val, r0, r1, bounds[q], bounds[q + 1]) for q in range(world)]
-        dg = D.DistGraph(rank, world, bounds, fwd, bwd, sum(f.nnz for f in fwd), idx.shape[1])
+        pad = D.DistGraph.padded_rows(bounds)
+        blocks = []
+        for ii in (idx, tidx):
+            blocks.append(HostBlock(ii, val, r0, r1, c0=r0, c1=r1))
+            blocks.append(HostBlock(ii, val, r0, r1, bounds=bounds, pad=pad, exclude=rank))
+        dg = D.DistGraph(rank, world, bounds, pad, *blocks, blocks[0].nnz + blocks[1].nnz, idx.shape[1])
         ops = NumpyOps()
         xt, gt = torch.from_numpy(x[r0:r1].copy()), torch.from_numpy(g[r0:r1].copy())
         wt, bt = torch.from_numpy(w), torch.from_numpy(b)
@@ -121,8 +138,7 @@ def test_partition_balances_nnz_and_exchange_is_a_matching():
         assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(world))
         per = [rowptr[b[i + 1]] - rowptr[b[i]] for i in range(world)]
         assert max(per) - min(per) <= 2 * np.diff(rowptr).max()  # within one (long) row of perfect balance
-        for k in range(1, world):  # step k: sends and receives form a permutation
-            assert sorted((p - k) % world for p in range(world)) == list(range(world))
-            assert all(D.exchange_order(p, world)[k] == (p + k) % world for p in range(world))
+        pad = D.DistGraph.padded_rows(b)
+        assert pad % 8 == 0 and pad >= max(b[i + 1] - b[i] for i in range(world))
     # more ranks than rows: empty blocks allowed
     assert D.partition_rows_by_nnz(np.array([0, 2, 5]), 4)[-1] == 2

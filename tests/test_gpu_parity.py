@@ -433,28 +433,51 @@ def test_row_partition_blocks_emulated_on_one_gpu(P, world):
     w, b = layer.weight.detach(), layer.bias.detach()
     dgs = [D.DistGraph.from_graph(gr, p, world, bounds) for p in range(world)]
     assert sum(dg.nnz_local for dg in dgs) == gr.nnz
-    support = [ops.gemm(x[bounds[q]:bounds[q + 1]], w) for q in range(world)]
+    pad = dgs[0].pad_rows
+
+    def gathered(parts):  # what the all-gather of the padded slots delivers (padding poisoned with NaN)
+        buf = torch.full((world * pad, parts[0].shape[1]), float("nan"), device=dev())
+        for q, t in enumerate(parts):
+            buf[q * pad: q * pad + t.shape[0]] = t
+        return buf
+
+    s_all = gathered([ops.gemm(x[bounds[q]:bounds[q + 1]], w) for q in range(world)])
+    g_all = gathered([g[bounds[q]:bounds[q + 1]] for q in range(world)])
     dw_sum = torch.zeros_like(w)
     db_sum = torch.zeros_like(b)
     for p, dg in enumerate(dgs):
         r0, r1 = bounds[p], bounds[p + 1]
         out = torch.empty(r1 - r0, 12, device=dev())
-        order = D.exchange_order(p, world)
-        for i, q in enumerate(order):
-            last = i == world - 1
-            ops.spmm_block(dg.fwd_blocks[q], support[q], out, i > 0, b if last else None, False)
+        if world == 1:
+            ops.spmm_block(dg.fwd_diag, s_all[: r1 - r0], out, False, b, False)
+        else:
+            ops.spmm_block(dg.fwd_diag, s_all[p * pad: p * pad + pad], out, False)
+            ops.spmm_block(dg.fwd_remote, s_all, out, True, b, False)
         assert ((out - ref_out[r0:r1].detach()).abs().max() / ref_out.abs().max()).item() < TOL
         ds = torch.empty(r1 - r0, 12, device=dev())
-        for i, q in enumerate(order):
-            ops.spmm_block(dg.bwd_blocks[q], g[bounds[q]:bounds[q + 1]], ds, i > 0)
+        ops.spmm_block(dg.bwd_diag, g_all[p * pad: p * pad + pad], ds, False)
+        if world > 1:
+            ops.spmm_block(dg.bwd_remote, g_all, ds, True)
         dw_sum += ops.gemm(x[r0:r1].t(), ds)
-        db_sum += ops.colsum(g[r0:r1].contiguous())[0]
+        staged = torch.empty(pad, 12, device=dev())
+        db_p, _ = ops.colsum(g[r0:r1].contiguous(), None, staged)
+        assert torch.equal(staged[: r1 - r0], g[r0:r1])
+        db_sum += db_p
         dx = ops.gemm(ds, w.t())
         assert ((dx - xt.grad[r0:r1]).abs().max() / xt.grad.abs().max()).item() < TOL
     assert ((dw_sum - layer.weight.grad).abs().max() / layer.weight.grad.abs().max()).item() < TOL
     assert ((db_sum - layer.bias.grad).abs().max() / layer.bias.grad.abs().max()).item() < TOL
     with pytest.raises(RuntimeError):  # blocks carry no transpose
-        P.spmm(dgs[0].fwd_blocks[0], torch.zeros(bounds[1] - bounds[0], 4, device=dev(), requires_grad=True)).sum().backward()
+        P.spmm(dgs[0].fwd_diag, torch.zeros(dgs[0].fwd_diag.n_cols, 4, device=dev(), requires_grad=True)).sum().backward()
+    # single-process DistGraphConvolution (world 1) equals the plain layer
+    if world == 1:
+        dl = D.DistGraphConvolution(24, 12, precision="fp32").to(dev())
+        dl.inner.load_state_dict(layer.state_dict())
+        xt2 = x.clone().requires_grad_(True)
+        o2 = dl(xt2, dgs[0])
+        o2.backward(g)
+        assert torch.equal(o2, ref_out) and torch.allclose(xt2.grad, xt.grad, rtol=0, atol=0)
+        assert torch.equal(dl.inner.weight.grad, layer.weight.grad)
 
 
 # ------------------------------------------------------------------ error behaviour
