@@ -74,7 +74,7 @@ def _problem(n=300, seed=3):
     return n, idx, val, x, g, w, b
 
 
-def _worker(rank, world, port, outdir, relu):
+def _worker(rank, world, port, outdir, relu, split=True):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -86,9 +86,9 @@ def _worker(rank, world, port, outdir, relu):
         pad = D.DistGraph.padded_rows(bounds)
         blocks = []
         for ii in (idx, tidx):
-            blocks.append(HostBlock(ii, val, r0, r1, c0=r0, c1=r1))
-            blocks.append(HostBlock(ii, val, r0, r1, bounds=bounds, pad=pad, exclude=rank))
-        dg = D.DistGraph(rank, world, bounds, pad, *blocks, blocks[0].nnz + blocks[1].nnz, idx.shape[1])
+            blocks.append(HostBlock(ii, val, r0, r1, c0=r0, c1=r1) if split else None)
+            blocks.append(HostBlock(ii, val, r0, r1, bounds=bounds, pad=pad, exclude=rank if split else -1))
+        dg = D.DistGraph(rank, world, bounds, pad, *blocks, 0, idx.shape[1], split)
         ops = NumpyOps()
         xt, gt = torch.from_numpy(x[r0:r1].copy()), torch.from_numpy(g[r0:r1].copy())
         wt, bt = torch.from_numpy(w), torch.from_numpy(b)
@@ -108,10 +108,10 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,relu", [(2, False), (2, True), (3, False)])
-def test_row_partitioned_layer_matches_single_process_oracle(world, relu):
+@pytest.mark.parametrize("world,relu,split", [(2, False, True), (2, True, False), (3, False, True)])
+def test_row_partitioned_layer_matches_single_process_oracle(world, relu, split):
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_worker, args=(world, _free_port(), d, relu), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), d, relu, split), nprocs=world, join=True)
         parts = [np.load(os.path.join(d, "r%d.npz" % r)) for r in range(world)]
     n, idx, val, x, g, w, b = _problem()
     _, o_ref = O.c_layer_forward(x, w, b, idx, val, n)

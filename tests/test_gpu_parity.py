@@ -431,7 +431,7 @@ def test_row_partition_blocks_emulated_on_one_gpu(P, world):
     ref_out.backward(g)
     ops = D.CudaOps("fp32")
     w, b = layer.weight.detach(), layer.bias.detach()
-    dgs = [D.DistGraph.from_graph(gr, p, world, bounds) for p in range(world)]
+    dgs = [D.DistGraph.from_graph(gr, p, world, bounds, split=True) for p in range(world)]
     assert sum(dg.nnz_local for dg in dgs) == gr.nnz
     pad = dgs[0].pad_rows
 
@@ -467,6 +467,14 @@ def test_row_partition_blocks_emulated_on_one_gpu(P, world):
         assert ((dx - xt.grad[r0:r1]).abs().max() / xt.grad.abs().max()).item() < TOL
     assert ((dw_sum - layer.weight.grad).abs().max() / layer.weight.grad.abs().max()).item() < TOL
     assert ((db_sum - layer.bias.grad).abs().max() / layer.bias.grad.abs().max()).item() < TOL
+    if world > 1:  # unsplit variant: the whole row block over the all-gathered panel
+        dg = D.DistGraph.from_graph(gr, 1, world, bounds, split=False)
+        r0, r1 = bounds[1], bounds[2]
+        out = torch.empty(r1 - r0, 12, device=dev())
+        ops.spmm_block(dg.fwd_remote, s_all, out, False, b, False)
+        assert ((out - ref_out[r0:r1].detach()).abs().max() / ref_out.abs().max()).item() < TOL
+        assert dg.fwd_diag is None and dg.nnz_local == dgs[1].nnz_local
+        assert D.DistGraph.from_graph(gr, 1, world, bounds).split == (dgs[1].fwd_diag.nnz >= 0.5 * dgs[1].nnz_local)
     with pytest.raises(RuntimeError):  # blocks carry no transpose
         P.spmm(dgs[0].fwd_diag, torch.zeros(dgs[0].fwd_diag.n_cols, 4, device=dev(), requires_grad=True)).sum().backward()
     # single-process DistGraphConvolution (world 1) equals the plain layer
