@@ -61,7 +61,7 @@ class DistGraph:
     # shorter gather loops: measured +35 % SpMM time on the uniform CBG graph), and can hide at most
     # the diagonal block's share of the work behind the all-gather.  It pays only when the partition
     # has locality, i.e. most stored entries sit in the diagonal block.
-    SPLIT_MIN_DIAG_FRACTION = 0.5
+    SPLIT_MIN_DIAG_FRACTION = 0.6
 
     def __init__(self, rank, world, bounds, pad_rows, fwd_diag, fwd_remote, bwd_diag, bwd_remote, nnz_local,
                  nnz_global, split=True):
