@@ -25,12 +25,30 @@ colsum_partial_kernel(int64_t n_rows, int f, int cw, int64_t rows_per_block,
     const int j = j0 + tx;
     float acc = 0.f;
     if (j < f) {
-      for (int64_t r = r0 + ty; r < r1; r += rl) {
+      int64_t r = r0 + ty;
+      float a4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (; r + 3 * rl < r1; r += 4 * rl) {  // four rows in flight per thread
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = g[(r + u * rl) * ldg + j];
+        if (y != nullptr) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = (y[(r + u * rl) * ldy + j] > 0.f) ? v[u] : 0.f;
+        }
+        if (gm != nullptr) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) gm[(r + u * rl) * ldgm + j] = v[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a4[u] += v[u];
+      }
+      for (; r < r1; r += rl) {
         float v = g[r * ldg + j];
         if (y != nullptr) v = (y[r * ldy + j] > 0.f) ? v : 0.f;
         if (gm != nullptr) gm[r * ldgm + j] = v;  // masked gradient, or a plain copy when y == NULL
-        acc += v;
+        a4[0] += v;
       }
+      acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
     }
     red[threadIdx.x] = acc;
     __syncthreads();
@@ -52,8 +70,19 @@ reduce_partials_kernel(int64_t total, int64_t n, int n_parts, const float* __res
   const int ty = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * 32 + tx;
   float acc = 0.f;
-  if (i < total)
-    for (int s = ty; s < n_parts; s += 8) acc += partial[(int64_t)s * total + i];
+  if (i < total) {
+    // lane ty owns parts ty, ty+8, ...: four loads in flight, added in a fixed order
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int s = ty;
+    for (; s + 24 < n_parts; s += 32) {
+      a0 += partial[(int64_t)s * total + i];
+      a1 += partial[(int64_t)(s + 8) * total + i];
+      a2 += partial[(int64_t)(s + 16) * total + i];
+      a3 += partial[(int64_t)(s + 24) * total + i];
+    }
+    for (; s < n_parts; s += 8) a0 += partial[(int64_t)s * total + i];
+    acc = (a0 + a1) + (a2 + a3);
+  }
   red[ty][tx] = acc;
   __syncthreads();
   if (ty == 0 && i < total) {
@@ -76,7 +105,7 @@ __global__ void __launch_bounds__(kThreads) flush_kernel(float4* buf, size_t n4,
 }
 
 int colsum_blocks(int64_t n_rows) {
-  int64_t b = ceil_div(n_rows, 64);
+  int64_t b = ceil_div(n_rows, 128);
   if (b > kMaxBlocks) b = kMaxBlocks;
   return (int)(b < 1 ? 1 : b);
 }

@@ -267,24 +267,28 @@ gemm_tc_rows_kernel(int64_t M, int N, int K, const float* __restrict__ a, int64_
   uint32_t it = 0;              // K-block iteration counter across tiles (stage = it & 1)
   uint32_t acc_parity = 0;
 
+  // A tile loads: registers for the K block being split now (cur) and the one after it (nxt);
+  // the prefetch crosses tile boundaries, so the epilogue of a tile overlaps the next tile's loads.
+  auto load_a = [&](int64_t m0, int kb, float4 (&dst)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t r = m0 + row_in + 32 * j;
+      const int k = kb * BKF + chunk * 4;
+      dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < M && k < K) dst[j] = __ldg(reinterpret_cast<const float4*>(a + r * lda + k));
+    }
+  };
+  float4 cur[4];
+  if ((int64_t)blockIdx.x < m_tiles) load_a((int64_t)blockIdx.x * BM, 0, cur);
   for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
     const int64_t m0 = mt * BM;
-    float4 cur[4];
-    auto load_a = [&](int kb, float4 (&dst)[4]) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t r = m0 + row_in + 32 * j;
-        const int k = kb * BKF + chunk * 4;
-        dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < M && k < K) dst[j] = __ldg(reinterpret_cast<const float4*>(a + r * lda + k));
-      }
-    };
-    load_a(0, cur);
     for (int kb = 0; kb < nkb; ++kb, ++it) {
       const int s = it & 1;
       const uint32_t use = it >> 1;  // n-th use of stage s
       float4 nxt[4];
-      if (kb + 1 < nkb) load_a(kb + 1, nxt);  // prefetch next K block while this one is split/stored
+      const bool more_k = kb + 1 < nkb;
+      const bool more = more_k || (mt + gridDim.x < m_tiles);
+      if (more) load_a(more_k ? m0 : (mt + gridDim.x) * BM, more_k ? kb + 1 : 0, nxt);
       if (use > 0) mbar_wait(bar_mma[s], (use - 1) & 1);  // MMAs that read stage s have retired
       if (tid == 0) {
         mbar_expect_tx(bar_b[s], 2 * b_bytes);
@@ -312,7 +316,7 @@ gemm_tc_rows_kernel(int64_t M, int N, int K, const float* __restrict__ a, int64_
         umma_commit(bar_mma[s]);
         if (kb == nkb - 1 || kb % kChunkBlocks == kChunkBlocks - 1) umma_commit(bar_acc);
       }
-      if (kb + 1 < nkb) {
+      if (more) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
       }
