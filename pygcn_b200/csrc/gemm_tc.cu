@@ -224,7 +224,7 @@ pack_b_kernel(int64_t K, int64_t N, int npad, int n_tiles, int nkb, const float*
 }
 
 // ------------------------------------------------------------------ mode R kernel
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 gemm_tc_rows_kernel(int64_t M, int N, int K, const float* __restrict__ a, int64_t lda,
                     const float* __restrict__ img_hi, const float* __restrict__ img_lo, float* __restrict__ c,
                     int64_t ldc, int npad, int nkb, int tmem_cols, int vec_ok) {
@@ -267,9 +267,14 @@ gemm_tc_rows_kernel(int64_t M, int N, int K, const float* __restrict__ a, int64_
   uint32_t it = 0;              // K-block iteration counter across tiles (stage = it & 1)
   uint32_t acc_parity = 0;
 
-  // A tile loads: registers for the K block being split now (cur) and the one after it (nxt);
-  // the prefetch crosses tile boundaries, so the epilogue of a tile overlaps the next tile's loads.
-  auto load_a = [&](int64_t m0, int kb, float4 (&dst)[4]) {
+  // A tile loads run two K blocks ahead of the split (cur <- n1 <- n2) over the flattened
+  // (tile, K block) sequence of this CTA, so the prefetch crosses tile boundaries and the epilogue
+  // of a tile overlaps the next tile's loads: ~3 x 16 KB in flight per CTA, 2 CTAs per SM.
+  const int64_t my_tiles = (m_tiles > (int64_t)blockIdx.x) ? (m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t n_items = my_tiles * nkb;
+  auto load_item = [&](int64_t item, float4 (&dst)[4]) {
+    const int64_t m0 = ((int64_t)blockIdx.x + (item / nkb) * gridDim.x) * BM;
+    const int kb = (int)(item % nkb);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int64_t r = m0 + row_in + 32 * j;
@@ -278,17 +283,16 @@ gemm_tc_rows_kernel(int64_t M, int N, int K, const float* __restrict__ a, int64_
       if (r < M && k < K) dst[j] = __ldg(reinterpret_cast<const float4*>(a + r * lda + k));
     }
   };
-  float4 cur[4];
-  if ((int64_t)blockIdx.x < m_tiles) load_a((int64_t)blockIdx.x * BM, 0, cur);
+  float4 cur[4], n1[4], n2[4];
+  if (n_items > 0) load_item(0, cur);
+  if (n_items > 1) load_item(1, n1);
+  int64_t item = 0;
   for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
     const int64_t m0 = mt * BM;
-    for (int kb = 0; kb < nkb; ++kb, ++it) {
+    for (int kb = 0; kb < nkb; ++kb, ++it, ++item) {
       const int s = it & 1;
       const uint32_t use = it >> 1;  // n-th use of stage s
-      float4 nxt[4];
-      const bool more_k = kb + 1 < nkb;
-      const bool more = more_k || (mt + gridDim.x < m_tiles);
-      if (more) load_a(more_k ? m0 : (mt + gridDim.x) * BM, more_k ? kb + 1 : 0, nxt);
+      if (item + 2 < n_items) load_item(item + 2, n2);
       if (use > 0) mbar_wait(bar_mma[s], (use - 1) & 1);  // MMAs that read stage s have retired
       if (tid == 0) {
         mbar_expect_tx(bar_b[s], 2 * b_bytes);
@@ -316,9 +320,10 @@ gemm_tc_rows_kernel(int64_t M, int N, int K, const float* __restrict__ a, int64_
         umma_commit(bar_mma[s]);
         if (kb == nkb - 1 || kb % kChunkBlocks == kChunkBlocks - 1) umma_commit(bar_acc);
       }
-      if (more) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+      for (int j = 0; j < 4; ++j) {
+        cur[j] = n1[j];
+        n1[j] = n2[j];
       }
       if (kb == nkb - 1 || kb % kChunkBlocks == kChunkBlocks - 1) {
         // drain the accumulator every kChunkBlocks K blocks: the tensor core adds into TMEM with
@@ -409,13 +414,17 @@ gemm_tc_tn_kernel(int64_t R, int M, int N, const float* __restrict__ x, int64_t 
     }
   };
 
-  float4 av[4], bv[NBQ];
+  // loads run two K blocks ahead of the transposing stores when the registers allow it (NBQ <= 2)
+  constexpr bool kDeep = NBQ <= 2;
+  float4 av[4], bv[NBQ], a1[4], b1[NBQ], a2[kDeep ? 4 : 1], b2[kDeep ? NBQ : 1];
   if (nkb > 0) load_block(0, av, bv);
+  if (nkb > 1) load_block(1, a1, b1);
   for (int kb = 0; kb < nkb; ++kb) {
     const int s = kb & 1;
     const uint32_t use = (uint32_t)kb >> 1;
-    float4 an[4], bn[NBQ];
-    if (kb + 1 < nkb) load_block(kb + 1, an, bn);  // prefetch while this block is transposed
+    if constexpr (kDeep) {
+      if (kb + 2 < nkb) load_block(kb + 2, a2, b2);
+    }
     if (use > 0) mbar_wait(bar_mma[s], (use - 1) & 1);
 #pragma unroll
     for (int j = 0; j < 4; ++j) store_t(L.a_hi[s], L.a_lo[s], 4 * (warp + 8 * j), av[j]);
@@ -430,11 +439,17 @@ gemm_tc_tn_kernel(int64_t R, int M, int N, const float* __restrict__ x, int64_t 
       umma_commit(bar_mma[s]);
       if (kb == nkb - 1) umma_commit(bar_acc);
     }
-    if (kb + 1 < nkb) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) av[j] = an[j];
+    for (int j = 0; j < 4; ++j) av[j] = a1[j];
 #pragma unroll
-      for (int j = 0; j < NBQ; ++j) bv[j] = bn[j];
+    for (int j = 0; j < NBQ; ++j) bv[j] = b1[j];
+    if constexpr (kDeep) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a1[j] = a2[j];
+#pragma unroll
+      for (int j = 0; j < NBQ; ++j) b1[j] = b2[j];
+    } else {
+      if (kb + 2 < nkb) load_block(kb + 2, a1, b1);
     }
   }
   float* cdst = c + (int64_t)blockIdx.x * split_stride;
