@@ -18,6 +18,8 @@
 // 1024 B apart), accumulators live in TMEM (128 lanes x N columns fp32), tcgen05.mma is issued
 // by one thread, completion is tracked with tcgen05.commit -> mbarrier, the epilogue reads TMEM
 // with tcgen05.ld.  Two smem stages; 2 CTAs per SM give the inter-tile overlap.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gcnb {
@@ -119,9 +121,24 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, K-major both
-__host__ __device__ inline uint32_t make_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// MN-major descriptor for 32-bit operands: the only swizzled MN-major layout tf32 has is
+// SWIZZLE_128B_BASE32B (cute Layout_MN_SW128_32B_Atom): atoms of 4 K-rows x 128 B (32 contiguous
+// M/N elements), 32-byte chunk c of row r stored at chunk c ^ (r & 3).
+// LBO = byte stride between consecutive 32-element M/N groups, SBO = byte stride between 4-row K groups
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32;
+// mn_major sets a_major_/b_major_ (bits 15/16) for MN-major operands
+__host__ __device__ inline uint32_t make_idesc(int n, bool mn_major = false) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
 }
 
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
@@ -142,11 +159,14 @@ struct Smem {
   uint32_t bars;  // mma_done[2], b_full[2], accum_full  (5 x 8 bytes) then tmem slot
 };
 
-__host__ __device__ inline uint32_t smem_layout(int npad, Smem* s) {
+// b_slots: number of (hi, lo) B tile pairs kept in shared memory: 2 when B is streamed per K block,
+// nkb when the whole packed B fits and stays resident (slot kb at b_hi[0] + kb * 2 * npad * 128).
+__host__ __device__ inline uint32_t smem_layout(int npad, Smem* s, int b_slots = 2) {
   uint32_t off = 0;
   const uint32_t bt = (uint32_t)npad * 128;
   for (int i = 0; i < 2; ++i) { s->a_hi[i] = off; off += kTileBytes; s->a_lo[i] = off; off += kTileBytes; }
-  for (int i = 0; i < 2; ++i) { s->b_hi[i] = off; off += bt; s->b_lo[i] = off; off += bt; }
+  for (int i = 0; i < 2; ++i) { s->b_hi[i] = off + (uint32_t)i * 2 * bt; s->b_lo[i] = s->b_hi[i] + bt; }
+  off += (uint32_t)b_slots * 2 * bt;
   off = (off + 1023) & ~1023u;
   s->bars = off;
   off += 64;
@@ -163,6 +183,23 @@ __device__ __forceinline__ void issue_kblock(uint32_t tmem_d, uint32_t a_hi, uin
     umma_tf32(tmem_d, dal + adv, dbh + adv, idesc, (first && ks == 0) ? 0u : 1u);
     umma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
     umma_tf32(tmem_d, dah + adv, dbh + adv, idesc, 1u);
+  }
+}
+
+// MN-major variant: a_* tiles are 4 M-groups x 8 K-groups of 512-byte atoms (atom (mm,kg) at
+// (mm + 4*kg) * 512), b_* tiles are ng N-groups x 8 K-groups (atom (nn,kg) at (nn + ng*kg) * 512);
+// one UMMA K step (8 tf32) spans two K groups.
+__device__ __forceinline__ void issue_kblock_mn(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                                uint32_t b_lo, uint32_t idesc, int ng, bool first) {
+#pragma unroll
+  for (int ks = 0; ks < BKF / 8; ++ks) {
+    const uint32_t ao = (uint32_t)ks * 4096u, bo = (uint32_t)(ks * ng) * 1024u;
+    const uint64_t dah = make_desc_mn(a_hi + ao, 512u, 2048u), dal = make_desc_mn(a_lo + ao, 512u, 2048u);
+    const uint64_t dbh = make_desc_mn(b_hi + bo, 512u, (uint32_t)ng * 512u);
+    const uint64_t dbl = make_desc_mn(b_lo + bo, 512u, (uint32_t)ng * 512u);
+    umma_tf32(tmem_d, dal, dbh, idesc, (first && ks == 0) ? 0u : 1u);
+    umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+    umma_tf32(tmem_d, dah, dbh, idesc, 1u);
   }
 }
 
@@ -227,11 +264,11 @@ pack_b_kernel(int64_t K, int64_t N, int npad, int n_tiles, int nkb, const float*
 __global__ void __launch_bounds__(kThreads, 2)
 gemm_tc_rows_kernel(int64_t M, int N, int K, const float* __restrict__ a, int64_t lda,
                     const float* __restrict__ img_hi, const float* __restrict__ img_lo, float* __restrict__ c,
-                    int64_t ldc, int npad, int nkb, int tmem_cols, int vec_ok) {
+                    int64_t ldc, int npad, int nkb, int tmem_cols, int vec_ok, int b_resident) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   Smem L;
-  smem_layout(npad, &L);
+  smem_layout(npad, &L, b_resident ? nkb : 2);
   const uint32_t bar_mma[2] = {base + L.bars, base + L.bars + 8};
   const uint32_t bar_b[2] = {base + L.bars + 16, base + L.bars + 24};
   const uint32_t bar_acc = base + L.bars + 32;
@@ -257,6 +294,17 @@ gemm_tc_rows_kernel(int64_t M, int N, int K, const float* __restrict__ a, int64_
   const uint32_t b_bytes = (uint32_t)npad * 128;
 
   const int nt = blockIdx.y;           // N tile (npad columns)
+  if (b_resident && tid == 0) {
+    // the whole packed B (hi and lo images of every K block) is pulled once with TMA bulk copies
+    // and stays in shared memory: no per-K-block fetch on the MMA critical path
+    mbar_expect_tx(bar_b[0], 2 * b_bytes * (uint32_t)nkb);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int64_t blk = (int64_t)nt * nkb + kb;
+      bulk_g2s(base + L.b_hi[0] + (uint32_t)kb * 2 * b_bytes, img_hi + blk * ((int64_t)npad * BKF), b_bytes, bar_b[0]);
+      bulk_g2s(base + L.b_lo[0] + (uint32_t)kb * 2 * b_bytes, img_lo + blk * ((int64_t)npad * BKF), b_bytes, bar_b[0]);
+    }
+  }
+  bool b_ready = false;
   const int n0 = nt * npad;
   const int n_cols = min(npad, N - n0);
   const int64_t m_tiles = (M + BM - 1) / BM;
@@ -294,7 +342,7 @@ gemm_tc_rows_kernel(int64_t M, int N, int K, const float* __restrict__ a, int64_
       const uint32_t use = it >> 1;  // n-th use of stage s
       if (item + 2 < n_items) load_item(item + 2, n2);
       if (use > 0) mbar_wait(bar_mma[s], (use - 1) & 1);  // MMAs that read stage s have retired
-      if (tid == 0) {
+      if (tid == 0 && !b_resident) {
         mbar_expect_tx(bar_b[s], 2 * b_bytes);
         const int64_t blk = (int64_t)nt * nkb + kb;
         bulk_g2s(base + L.b_hi[s], img_hi + blk * ((int64_t)npad * BKF), b_bytes, bar_b[s]);
@@ -313,9 +361,16 @@ gemm_tc_rows_kernel(int64_t M, int N, int K, const float* __restrict__ a, int64_
       fence_proxy_async();
       __syncthreads();
       if (tid == 0) {
-        mbar_wait(bar_b[s], use & 1);
+        uint32_t bh = base + L.b_hi[s], bl = base + L.b_lo[s];
+        if (b_resident) {
+          if (!b_ready) { mbar_wait(bar_b[0], 0); b_ready = true; }
+          bh = base + L.b_hi[0] + (uint32_t)kb * 2 * b_bytes;
+          bl = base + L.b_lo[0] + (uint32_t)kb * 2 * b_bytes;
+        } else {
+          mbar_wait(bar_b[s], use & 1);
+        }
         tc_fence_after();
-        issue_kblock(tmem_d, base + L.a_hi[s], base + L.a_lo[s], base + L.b_hi[s], base + L.b_lo[s], idesc,
+        issue_kblock(tmem_d, base + L.a_hi[s], base + L.a_lo[s], bh, bl, idesc,
                      kb % kChunkBlocks == 0);
         umma_commit(bar_mma[s]);
         if (kb == nkb - 1 || kb % kChunkBlocks == kChunkBlocks - 1) umma_commit(bar_acc);
@@ -346,7 +401,10 @@ gemm_tc_rows_kernel(int64_t M, int N, int K, const float* __restrict__ a, int64_
 // ------------------------------------------------------------------ mode T kernel
 // C_partial[split][M tile rows][N] = sum over rows r in the split of X[r, m] * Y[r, n]
 // NBQ = float4 loads of Y per thread per K block (npad <= 32*NBQ).
-template <int NBQ>
+// MN = true keeps the operand tiles MN-major (rows of X / Y are stored as they arrive, 128-bit
+// shared-memory stores, UMMA descriptors with a_major = b_major = MN); MN = false transposes them
+// into K-major tiles with 32-bit stores.  npad must be a multiple of 32 when MN.
+template <int NBQ, bool MN>
 __global__ void __launch_bounds__(kThreads, (NBQ <= 2) ? 2 : 1)
 gemm_tc_tn_kernel(int64_t R, int M, int N, const float* __restrict__ x, int64_t ldx, const float* __restrict__ y,
                   int64_t ldy, float* __restrict__ c, int64_t ldc, int64_t split_stride, int64_t rows_per_split,
@@ -374,7 +432,8 @@ gemm_tc_tn_kernel(int64_t R, int M, int N, const float* __restrict__ x, int64_t 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *reinterpret_cast<volatile uint32_t*>(gen + L.bars + 40);
-  const uint32_t idesc = make_idesc(npad);
+  const uint32_t idesc = make_idesc(npad, MN);
+  const int ng = npad >> 5;
 
   const int m0 = blockIdx.y * BM;
   const int m_cols = min(BM, M - m0);          // valid rows of the C tile (= columns of X used)
@@ -402,6 +461,16 @@ gemm_tc_tn_kernel(int64_t R, int M, int N, const float* __restrict__ x, int64_t 
       if (r_ok && q < b_q) bv[j] = __ldg(reinterpret_cast<const float4*>(y + r * ldy + 4 * q));
     }
   };
+  // MN-major store: float4 q (elements 4q..4q+3) of reduction row `lane`, groups-per-K-group gpk
+  auto store_mn = [&](uint32_t tile_hi, uint32_t tile_lo, int q, int gpk, const float4& v) {
+    float4 hi, lo;
+    split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
+    split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+    const uint32_t off = (uint32_t)(((q >> 3) + gpk * (lane >> 2)) * 512 + (lane & 3) * 128 +
+                                    (((((q & 7) >> 1) ^ (lane & 3)) << 5) | ((q & 1) << 4)));
+    *reinterpret_cast<float4*>(gen + tile_hi + off) = hi;
+    *reinterpret_cast<float4*>(gen + tile_lo + off) = lo;
+  };
   auto store_t = [&](uint32_t tile_hi, uint32_t tile_lo, int row4, const float4& v) {
     const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -426,16 +495,28 @@ gemm_tc_tn_kernel(int64_t R, int M, int N, const float* __restrict__ x, int64_t 
       if (kb + 2 < nkb) load_block(kb + 2, a2, b2);
     }
     if (use > 0) mbar_wait(bar_mma[s], (use - 1) & 1);
+    if constexpr (MN) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) store_t(L.a_hi[s], L.a_lo[s], 4 * (warp + 8 * j), av[j]);
+      for (int j = 0; j < 4; ++j) store_mn(L.a_hi[s], L.a_lo[s], warp + 8 * j, 4, av[j]);
 #pragma unroll
-    for (int j = 0; j < NBQ; ++j)
-      if (4 * (warp + 8 * j) < npad) store_t(L.b_hi[s], L.b_lo[s], 4 * (warp + 8 * j), bv[j]);
+      for (int j = 0; j < NBQ; ++j)
+        if (4 * (warp + 8 * j) < npad) store_mn(L.b_hi[s], L.b_lo[s], warp + 8 * j, ng, bv[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) store_t(L.a_hi[s], L.a_lo[s], 4 * (warp + 8 * j), av[j]);
+#pragma unroll
+      for (int j = 0; j < NBQ; ++j)
+        if (4 * (warp + 8 * j) < npad) store_t(L.b_hi[s], L.b_lo[s], 4 * (warp + 8 * j), bv[j]);
+    }
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      issue_kblock(tmem_d, base + L.a_hi[s], base + L.a_lo[s], base + L.b_hi[s], base + L.b_lo[s], idesc, kb == 0);
+      if constexpr (MN)
+        issue_kblock_mn(tmem_d, base + L.a_hi[s], base + L.a_lo[s], base + L.b_hi[s], base + L.b_lo[s], idesc, ng,
+                        kb == 0);
+      else
+        issue_kblock(tmem_d, base + L.a_hi[s], base + L.a_lo[s], base + L.b_hi[s], base + L.b_lo[s], idesc, kb == 0);
       umma_commit(bar_mma[s]);
       if (kb == nkb - 1) umma_commit(bar_acc);
     }
@@ -486,10 +567,20 @@ RowsPlan rows_plan(int64_t n, int64_t k) {
   return p;
 }
 
+// GCNB_TN_LAYOUT=k selects the transposing K-major variant of the tn kernel (default: MN-major)
+bool tn_use_mn() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GCNB_TN_LAYOUT");
+    v = (e && (e[0] == 'k' || e[0] == 'K')) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 struct TnPlan { int npad, m_tiles; int64_t splits, rows_per_split; };
 TnPlan tn_plan(int64_t m, int64_t n, int64_t r) {
   TnPlan p;
-  p.npad = pad16(n);
+  p.npad = tn_use_mn() ? (int)(ceil_div(n, 32) * 32) : pad16(n);
   p.m_tiles = (int)ceil_div(m, BM);
   int64_t s = ceil_div(2 * kNumSMs, p.m_tiles);
   const int64_t max_s = ceil_div(r, 4 * BKF);  // at least 4 K blocks per split
@@ -531,7 +622,9 @@ int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t
   pack_b_kernel<<<pgrid, 256, 0, st>>>(k, n, p.npad, p.n_tiles, p.nkb, b, b_rs, b_cs, img_hi, img_lo);
   GCNB_LAUNCH_CHECK();
   Smem L;
-  const uint32_t smem = smem_layout(p.npad, &L) + 1024;
+  // keep the packed B resident when it costs no occupancy (<= 40 KB on top of the 64 KB of A stages)
+  const int b_resident = ((size_t)p.nkb * 2 * p.npad * 128 <= 40 * 1024) ? 1 : 0;
+  const uint32_t smem = smem_layout(p.npad, &L, b_resident ? p.nkb : 2) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     GCNB_CUDA(cudaFuncSetAttribute(gemm_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -545,7 +638,7 @@ int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t
   dim3 grid((unsigned)gx, (unsigned)p.n_tiles);
   const int vec_ok = (ldc % 4 == 0) && aligned16(c) && (p.npad % 4 == 0);
   gemm_tc_rows_kernel<<<grid, kThreads, smem, st>>>(m, (int)n, (int)k, a, lda, img_hi, img_lo, c, ldc, p.npad, p.nkb,
-                                                    tmem_cols_for(p.npad), vec_ok);
+                                                    tmem_cols_for(p.npad), vec_ok, b_resident);
   GCNB_LAUNCH_CHECK();
   return GCNB_OK;
 }
@@ -573,21 +666,29 @@ int gemm_tc_tn_launch(int64_t m, int64_t n, int64_t r, const float* x, int64_t l
   const int64_t stride = (p.splits > 1) ? m * n : 0;
   const int vec_ok = (dst_ld % 4 == 0) && aligned16(dst);
   dim3 grid((unsigned)p.splits, (unsigned)p.m_tiles);
-#define GCNB_TN_LAUNCH(NBQ_)                                                                                       \
+#define GCNB_TN_LAUNCH(NBQ_, MN_)                                                                                  \
   do {                                                                                                             \
     static bool attr_set = false;                                                                                  \
     if (!attr_set) {                                                                                               \
-      GCNB_CUDA(cudaFuncSetAttribute(gemm_tc_tn_kernel<NBQ_>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+      GCNB_CUDA(cudaFuncSetAttribute(gemm_tc_tn_kernel<NBQ_, MN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                      227 * 1024));                                                                 \
       attr_set = true;                                                                                             \
     }                                                                                                              \
-    gemm_tc_tn_kernel<NBQ_><<<grid, kThreads, smem, st>>>(r, (int)m, (int)n, x, ldx, y, ldy, dst, dst_ld, stride,  \
-                                                          p.rows_per_split, p.npad, tmem_cols_for(p.npad), vec_ok);\
+    gemm_tc_tn_kernel<NBQ_, MN_><<<grid, kThreads, smem, st>>>(r, (int)m, (int)n, x, ldx, y, ldy, dst, dst_ld,     \
+                                                               stride, p.rows_per_split, p.npad,                   \
+                                                               tmem_cols_for(p.npad), vec_ok);                     \
   } while (0)
-  if (p.npad <= 32) GCNB_TN_LAUNCH(1);
-  else if (p.npad <= 64) GCNB_TN_LAUNCH(2);
-  else if (p.npad <= 128) GCNB_TN_LAUNCH(4);
-  else GCNB_TN_LAUNCH(8);
+  if (tn_use_mn()) {
+    if (p.npad <= 32) GCNB_TN_LAUNCH(1, true);
+    else if (p.npad <= 64) GCNB_TN_LAUNCH(2, true);
+    else if (p.npad <= 128) GCNB_TN_LAUNCH(4, true);
+    else GCNB_TN_LAUNCH(8, true);
+  } else {
+    if (p.npad <= 32) GCNB_TN_LAUNCH(1, false);
+    else if (p.npad <= 64) GCNB_TN_LAUNCH(2, false);
+    else if (p.npad <= 128) GCNB_TN_LAUNCH(4, false);
+    else GCNB_TN_LAUNCH(8, false);
+  }
 #undef GCNB_TN_LAUNCH
   GCNB_LAUNCH_CHECK();
   if (p.splits > 1) GCNB_TRY(reduce_partials_launch(m, n, (int)p.splits, dst, c, ldc, st));
