@@ -96,7 +96,8 @@ typedef struct {
   int64_t max_degree, t_max_degree;
   int64_t n_long_chunks, t_n_long_chunks; /* work items the long-row bin was split into */
   int32_t pattern_symmetric;       /* 1: CSR^T shares rowptr/col with CSR (values differ) */
-  int32_t reserved;
+  int32_t dense_route;             /* 1: built from a dense matrix of density >= 10 %: products run as
+                                      tcgen05 GEMMs over zero-padded dense copies instead of the CSR */
   int64_t device_bytes;            /* HBM held by the handle                       */
   const int32_t* d_rowptr;         /* [n_rows+1]                                   */
   const int32_t* d_col;            /* [nnz]                                        */

@@ -34,7 +34,7 @@ class GraphInfo(ctypes.Structure):
         ("bin_rows", c_i64 * NUM_BINS), ("t_bin_rows", c_i64 * NUM_BINS),
         ("max_degree", c_i64), ("t_max_degree", c_i64),
         ("n_long_chunks", c_i64), ("t_n_long_chunks", c_i64),
-        ("pattern_symmetric", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("pattern_symmetric", ctypes.c_int32), ("dense_route", ctypes.c_int32),
         ("device_bytes", c_i64),
         ("d_rowptr", c_vp), ("d_col", c_vp), ("d_val", c_vp),
         ("d_t_rowptr", c_vp), ("d_t_col", c_vp), ("d_t_val", c_vp),

@@ -61,6 +61,42 @@ size_t gemm_ws(int64_t m, int64_t n, int64_t k, int precision) {
   return (w + 255) & ~(size_t)255;
 }
 
+// out = op(A) * B (+ bias) (relu) for a graph handle: CSR SpMM, or -- for handles on the dense route --
+// a tensor-core GEMM over the zero-padded dense copy:  C[M,F] = sum_r X[r,M]^T B[r,F]  with X = A^T
+// (forward) or A (transpose), i.e. the split-K "tn" kernel in both directions.
+size_t graph_matmul_ws(const gcnb_graph* g, bool transpose, int64_t f) {
+  const CsrView& v = transpose ? g->bwd : g->fwd;
+  size_t w = spmm_workspace_bytes(v, f);
+  if (g->dense_fwd) {
+    const int64_t m = transpose ? g->n_cols : g->n_rows, r = transpose ? g->n_rows : g->n_cols;
+    size_t a = gemm_fp32_workspace_bytes(m, f, r);
+    size_t b = (f <= 256) ? gemm_tc_tn_workspace_bytes(m, f, r) : 0;
+    if (a > w) w = a;
+    if (b > w) w = b;
+  }
+  return w;
+}
+
+int graph_matmul(const gcnb_graph* g, bool transpose, const float* b, int64_t ldb, int64_t f, const float* bias,
+                 bool relu, bool accumulate, float* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const CsrView& v = transpose ? g->bwd : g->fwd;
+  if (!g->dense_fwd || accumulate) {
+    return spmm_launch(v, b, ldb, f, bias, relu, out, ldo, ws, ws_bytes, st, accumulate);
+  }
+  GCNB_REQUIRE(f > 0 && ldb >= f && ldo >= f, "spmm(dense route): bad width / leading dimension");
+  const int64_t m = transpose ? g->n_cols : g->n_rows;   // output rows
+  const int64_t r = transpose ? g->n_rows : g->n_cols;   // reduction length
+  const float* x = transpose ? g->dense_fwd : g->dense_bwd;
+  const int64_t ldx = transpose ? g->ld_fwd : g->ld_bwd;
+  GCNB_REQUIRE(ws_bytes >= graph_matmul_ws(g, transpose, f), "spmm(dense route): workspace too small");
+  if (f <= 256 && gemm_tc_tn_eligible(m, f, r, x, ldx, b, ldb, /*padded=*/true)) {
+    GCNB_TRY(gemm_tc_tn_launch(m, f, r, x, ldx, b, ldb, out, ldo, ws, ws_bytes, st));
+  } else {
+    GCNB_TRY(gemm_fp32_launch(m, f, r, x, 1, ldx, b, ldb, 1, out, ldo, ws, ws_bytes, st));
+  }
+  return bias_act_launch(m, f, out, ldo, bias, relu, st);
+}
+
 }  // namespace
 }  // namespace gcnb
 
@@ -87,15 +123,13 @@ extern "C" int gcnb_spmm(const gcnb_graph* g, int flags, const float* d_b, int64
                          void* stream) {
   GCNB_REQUIRE(g != nullptr, "spmm: null graph");
   GCNB_REQUIRE(!(flags & GCNB_SPMM_TRANSPOSE) || g->has_transpose, "spmm: this handle is a block without a transpose");
-  const CsrView& v = (flags & GCNB_SPMM_TRANSPOSE) ? g->bwd : g->fwd;
-  return spmm_launch(v, d_b, ldb, f, d_bias, (flags & GCNB_SPMM_RELU) != 0, d_out, ldo, d_ws, ws_bytes,
-                     (cudaStream_t)stream, (flags & GCNB_SPMM_ACCUMULATE) != 0);
+  return graph_matmul(g, (flags & GCNB_SPMM_TRANSPOSE) != 0, d_b, ldb, f, d_bias, (flags & GCNB_SPMM_RELU) != 0,
+                      (flags & GCNB_SPMM_ACCUMULATE) != 0, d_out, ldo, d_ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" size_t gcnb_spmm_workspace_bytes(const gcnb_graph* g, int flags, int64_t f) {
   if (!g) return 0;
-  const CsrView& v = (flags & GCNB_SPMM_TRANSPOSE) ? g->bwd : g->fwd;
-  return spmm_workspace_bytes(v, f);
+  return graph_matmul_ws(g, (flags & GCNB_SPMM_TRANSPOSE) != 0, f);
 }
 
 extern "C" int gcnb_gemm(int64_t m, int64_t n, int64_t k, const float* d_a, int64_t a_rs, int64_t a_cs,
@@ -124,8 +158,8 @@ extern "C" size_t gcnb_colsum_workspace_bytes(int64_t n_rows, int64_t f) {
 
 extern "C" size_t gcnb_layer_workspace_bytes(const gcnb_graph* g, int64_t fin, int64_t fout, int precision) {
   if (!g) return 0;
-  size_t a = spmm_workspace_bytes(g->fwd, fout);
-  size_t b = spmm_workspace_bytes(g->bwd, fout);
+  size_t a = graph_matmul_ws(g, false, fout);
+  size_t b = graph_matmul_ws(g, true, fout);
   size_t s = a > b ? a : b;
   size_t c = colsum_workspace_bytes(g->n_rows, fout);
   size_t d0 = gemm_ws(g->n_cols, fout, fin, precision);  // X W
@@ -148,7 +182,7 @@ extern "C" int gcnb_layer_forward(const gcnb_graph* g, const float* d_x, int64_t
   GCNB_REQUIRE(ldx >= fin, "layer_forward: ldx < in_features");
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = reinterpret_cast<char*>(d_ws);
-  const size_t s_bytes = align256(spmm_workspace_bytes(g->fwd, fout));
+  const size_t s_bytes = align256(graph_matmul_ws(g, false, fout));
   const size_t d_bytes = gemm_ws(g->n_cols, fout, fin, precision);
   GCNB_REQUIRE(ws_bytes >= s_bytes + d_bytes && (s_bytes + d_bytes == 0 || ws != nullptr),
                "layer_forward: workspace too small");
@@ -157,8 +191,8 @@ extern "C" int gcnb_layer_forward(const gcnb_graph* g, const float* d_x, int64_t
   GCNB_TRY(gemm_dispatch(g->n_cols, fout, fin, d_x, ldx, 1, d_w, fout, 1, d_support, lds, precision,
                          ws + s_bytes, d_bytes, st));
   // out = A support (+ bias) (relu)                  (pygcn/layers.py:34-36, models.py:49)
-  return spmm_launch(g->fwd, d_support, lds, fout, d_bias, (flags & GCNB_LAYER_RELU) != 0, d_out, fout, ws,
-                     s_bytes, st);
+  return graph_matmul(g, false, d_support, lds, fout, d_bias, (flags & GCNB_LAYER_RELU) != 0, false, d_out, fout,
+                      ws, s_bytes, st);
 }
 
 extern "C" int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_t ldx, const float* d_w,
@@ -179,9 +213,9 @@ extern "C" int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_
   GCNB_REQUIRE(ws_bytes >= gcnb_layer_workspace_bytes(g, fin, fout, precision) && d_ws != nullptr,
                "layer_backward: workspace too small");
   char* ws = reinterpret_cast<char*>(d_ws);
-  const size_t s_bytes = align256(spmm_workspace_bytes(g->bwd, fout) > spmm_workspace_bytes(g->fwd, fout)
-                                      ? spmm_workspace_bytes(g->bwd, fout)
-                                      : spmm_workspace_bytes(g->fwd, fout));
+  const size_t s_bytes = align256(graph_matmul_ws(g, true, fout) > graph_matmul_ws(g, false, fout)
+                                      ? graph_matmul_ws(g, true, fout)
+                                      : graph_matmul_ws(g, false, fout));
   const size_t c_bytes = align256(colsum_workspace_bytes(g->n_rows, fout));
   void* ws_spmm = ws;
   void* ws_col = ws + s_bytes;
@@ -205,7 +239,7 @@ extern "C" int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_
   if (!need_dw && !need_dx) return GCNB_OK;
   // dS = A^T G                                      (MmBackward0 of torch.spmm)
   const int64_t lds = ceil_div(fout, 4) * 4;
-  GCNB_TRY(spmm_launch(g->bwd, gsrc, gld, fout, nullptr, false, d_ds, lds, ws_spmm, s_bytes, st));
+  GCNB_TRY(graph_matmul(g, true, gsrc, gld, fout, nullptr, false, false, d_ds, lds, ws_spmm, s_bytes, st));
   // dW = X^T dS                                     (MmBackward0 of torch.mm)
   if (need_dw) {
     GCNB_REQUIRE(d_dw != nullptr, "layer_backward: dW requested but null");

@@ -77,7 +77,7 @@ int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t
                         int64_t b_rs, int64_t b_cs, float* c, int64_t ldc, void* ws, size_t ws_bytes,
                         cudaStream_t stream);
 bool gemm_tc_tn_eligible(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y,
-                         int64_t ldy);
+                         int64_t ldy, bool padded = false);
 size_t gemm_tc_tn_workspace_bytes(int64_t m, int64_t n, int64_t r);
 int gemm_tc_tn_launch(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y,
                       int64_t ldy, float* c, int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t stream);
@@ -89,6 +89,10 @@ size_t colsum_workspace_bytes(int64_t n_rows, int64_t f);
 
 // out[(i / n) * ldo + i % n] = sum_{s < n_parts} partial[s * total + i], s ascending inside a fixed
 // 8-lane tree (deterministic).  total = m * n.
+// out[r, 0:f] = (accumulate ? out : 0) ... in place: out = act(out + bias)
+int bias_act_launch(int64_t n_rows, int64_t f, float* out, int64_t ldo, const float* bias, bool relu,
+                    cudaStream_t stream);
+
 int reduce_partials_launch(int64_t m, int64_t n, int n_parts, const float* partial, float* out,
                            int64_t ldo, cudaStream_t stream);
 
@@ -105,6 +109,11 @@ struct gcnb_graph {
   float* t_val = nullptr;
   bool pattern_symmetric = false;
   bool has_transpose = true;  // false for row/column blocks cut by gcnb_graph_block
+  // dense route (adjacency given as a dense matrix whose density makes the CSR gather the slower
+  // path): zero-padded copies of A [n_rows, ld_fwd] and A^T [n_cols, ld_bwd], ld = 4*ceil(./4)
+  float* dense_fwd = nullptr;
+  float* dense_bwd = nullptr;
+  int64_t ld_fwd = 0, ld_bwd = 0;
   int32_t* long_rows = nullptr;
   int32_t* long_chunk_ptr = nullptr;
   int32_t* t_long_rows = nullptr;

@@ -93,6 +93,19 @@ reduce_partials_kernel(int64_t total, int64_t n, int n_parts, const float* __res
   }
 }
 
+__global__ void __launch_bounds__(kThreads)
+bias_act_kernel(int64_t n_rows, int f, float* __restrict__ out, int64_t ldo, const float* __restrict__ bias, int relu) {
+  const int64_t total = n_rows * f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / f;
+    const int j = (int)(i % f);
+    float v = out[r * ldo + j];
+    if (bias) v += __ldg(bias + j);
+    if (relu) v = fmaxf(v, 0.f);
+    out[r * ldo + j] = v;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) zero_kernel(float* out, int f) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < f) out[j] = 0.f;
@@ -139,6 +152,16 @@ int colsum_launch(int64_t n_rows, int64_t f, const float* g, int64_t ldg, const 
                                                  ldgm, reinterpret_cast<float*>(ws));
   GCNB_LAUNCH_CHECK();
   return reduce_partials_launch(1, f, nb, reinterpret_cast<const float*>(ws), out, f, st);
+}
+
+int bias_act_launch(int64_t n_rows, int64_t f, float* out, int64_t ldo, const float* bias, bool relu,
+                    cudaStream_t st) {
+  if (n_rows == 0 || f == 0 || (bias == nullptr && !relu)) return GCNB_OK;
+  int64_t blocks = ceil_div(n_rows * f, kThreads);
+  if (blocks > kMaxBlocks) blocks = kMaxBlocks;
+  bias_act_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(n_rows, (int)f, out, ldo, bias, relu ? 1 : 0);
+  GCNB_LAUNCH_CHECK();
+  return GCNB_OK;
 }
 
 int reduce_partials_launch(int64_t m, int64_t n, int n_parts, const float* partial, float* out,

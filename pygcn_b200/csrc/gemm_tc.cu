@@ -644,9 +644,12 @@ int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t
 }
 
 // dW-shaped product: C[M,N] = sum_r X[r, 0:M]^T Y[r, 0:N]
-bool gemm_tc_tn_eligible(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y, int64_t ldy) {
-  return m > 0 && n > 0 && r > 0 && n <= 256 && (ldx % 4 == 0) && (ldy % 4 == 0) && (m % 4 == 0) && (n % 4 == 0) &&
-         aligned16(x) && aligned16(y);
+// padded = every row of x / y is readable (and finite) up to the next multiple of 4 columns
+bool gemm_tc_tn_eligible(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y, int64_t ldy,
+                         bool padded) {
+  const bool widths_ok = padded ? (ldx >= ceil_div(m, 4) * 4 && ldy >= ceil_div(n, 4) * 4) : (m % 4 == 0 && n % 4 == 0);
+  return m > 0 && n > 0 && r > 0 && n <= 256 && (ldx % 4 == 0) && (ldy % 4 == 0) && widths_ok && aligned16(x) &&
+         aligned16(y);
 }
 
 size_t gemm_tc_tn_workspace_bytes(int64_t m, int64_t n, int64_t r) {

@@ -47,6 +47,7 @@ class Graph:
         self.max_degree, self.t_max_degree = int(info.max_degree), int(info.t_max_degree)
         self.n_long_chunks, self.t_n_long_chunks = int(info.n_long_chunks), int(info.t_n_long_chunks)
         self.pattern_symmetric = bool(info.pattern_symmetric)
+        self.dense_route = bool(info.dense_route)
         self.device_bytes = int(info.device_bytes)
         self._finalizer = weakref.finalize(self, _lib.load().gcnb_graph_free, self._h)
 
@@ -151,9 +152,9 @@ class Graph:
         return (self.n_rows, self.n_cols)
 
     def __repr__(self):
-        return "Graph(%d x %d, nnz=%d, bins=%s, long_chunks=%d, sym_pattern=%s, %s, %.1f MB)" % (
+        return "Graph(%d x %d, nnz=%d, bins=%s, long_chunks=%d, sym_pattern=%s, %s%s, %.1f MB)" % (
             self.n_rows, self.n_cols, self.nnz, self.bin_rows, self.n_long_chunks, self.pattern_symmetric,
-            self.device, self.device_bytes / 1e6,
+            "dense route, " if self.dense_route else "", self.device, self.device_bytes / 1e6,
         )
 
 

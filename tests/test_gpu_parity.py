@@ -193,6 +193,39 @@ def test_layer_dense_adj_golden(P, golden):
     assert err(xt.grad, c["dense/dX"]) < TOL
 
 
+@pytest.mark.parametrize("n,fin,fout", [(2943, 8, 32), (300, 16, 7), (257, 33, 48)])
+def test_dense_route_fork_shape(P, n, fin, fout):
+    """The fork's live scripts pass a dense `torch.Tensor(adj)` (pygcn/utils.py:124-132, N = 2943 for
+    San Francisco): dense handles run as tensor-core GEMMs, results must match the reference's
+    `torch.spmm(dense, .)` == mm semantics (fp64 arbiter) for forward and all gradients."""
+    gen = torch.Generator(device=dev()).manual_seed(n)
+    v = torch.rand(40, n, generator=gen, device=dev())
+    adj = (v.t() @ v) / 40.0  # adj[i][j] = sum_p avg[p,i] * avg[p,j], fully dense, un-normalised
+    if n == 300:
+        adj = adj * (torch.rand(n, n, generator=gen, device=dev()) < 0.4)  # 40 % dense
+    gr = P.Graph.from_torch(adj)
+    assert gr.dense_route and gr.nnz == int((adj != 0).sum())
+    x = torch.randn(n, fin, generator=gen, device=dev())
+    g = torch.randn(n, fout, generator=gen, device=dev())
+    torch.manual_seed(42)
+    layer = P.GraphConvolution(fin, fout).to(dev())
+    xt = x.clone().requires_grad_(True)
+    out = layer(xt, adj)  # the tensor itself: converted once, cached
+    out.backward(g)
+    assert P.as_graph(adj) is P.as_graph(adj)
+    w64 = layer.weight.detach().double().requires_grad_(True)
+    b64 = layer.bias.detach().double().requires_grad_(True)
+    x64 = x.double().requires_grad_(True)
+    ref = adj.double() @ (x64 @ w64) + b64
+    ref.backward(g.double())
+    for mine, r in ((out, ref), (layer.weight.grad, w64.grad), (layer.bias.grad, b64.grad), (xt.grad, x64.grad)):
+        assert ((mine.double() - r).abs().max() / r.abs().max()).item() < TOL
+    # fused ReLU epilogue on the dense route
+    l2 = P.GraphConvolution(fin, fout, fuse_relu=True).to(dev())
+    l2.load_state_dict(layer.state_dict())
+    assert ((l2(x, adj) - torch.relu(ref.detach()).float()).abs().max() / ref.abs().max()).item() < TOL
+
+
 def test_layer_nobias_csr_golden(P, golden):
     c = golden("layer_cases.npz")
     n = int(c["ragged/n"])
