@@ -91,10 +91,12 @@ gemm_fp32_kernel(int m, int n, int64_t k, const float* __restrict__ a, int64_t a
 }
 
 int num_splits(int64_t m, int64_t n, int64_t k) {
-  // split only when the output is small and the reduction long (dW = X^T dS)
+  // split whenever the output tiles alone cannot fill the GPU and the reduction is long enough
+  // to share (dW = X^T dS: a handful of tiles, K = number of nodes)
   const int64_t tiles = ceil_div(m, 64) * ceil_div(n, 64);
-  if (k < 8 * kSplitChunk || tiles >= kNumSMs) return 1;
-  int64_t s = ceil_div(k, kSplitChunk);
+  if (k < 512 || tiles >= kNumSMs) return 1;
+  const int64_t chunk = (k >= 64 * kSplitChunk) ? kSplitChunk : 128;
+  int64_t s = ceil_div(k, chunk);
   const int64_t cap = ceil_div(4 * kNumSMs, tiles);
   if (s > cap) s = cap;
   return (int)(s < 1 ? 1 : s);

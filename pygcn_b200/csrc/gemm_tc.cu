@@ -443,31 +443,64 @@ gemm_tc_tn_kernel(int64_t R, int M, int N, const float* __restrict__ x, int64_t 
   const int a_q = (m_cols + 3) >> 2;  // float4 per X row inside this tile
   const int b_q = (N + 3) >> 2;       // float4 per Y row
 
-  // lane <-> reduction row k inside the block; warps stride over the float4 columns:
-  // the transposing STS.32 below are bank-conflict free with this mapping.
+  // Thread -> (reduction row k, float4 column q) of the K block.
+  //   MN-major tiles: lanes run along q, so a warp reads whole contiguous row segments (coalesced)
+  //     and each quarter-warp writes one full 128-byte shared-memory row (conflict free);
+  //   K-major tiles : lane <-> k, warps stride over q: the transposing STS.32 are conflict free.
+  int a_sh = 3, b_sh = 3;  // log2 of the float4 columns covered per row (power of two >= a_q / npad/4)
+  while ((1 << a_sh) < a_q) ++a_sh;
+  while ((1 << b_sh) < (npad >> 2)) ++b_sh;
+  auto item_a = [&](int j, int& k, int& q) -> bool {
+    if constexpr (MN) {
+      const int i = tid + kThreads * j;
+      k = i >> a_sh;
+      q = i & ((1 << a_sh) - 1);
+      return k < BKF;
+    } else {
+      k = lane;
+      q = warp + 8 * j;
+      return true;
+    }
+  };
+  auto item_b = [&](int j, int& k, int& q) -> bool {
+    if constexpr (MN) {
+      const int i = tid + kThreads * j;
+      k = i >> b_sh;
+      q = i & ((1 << b_sh) - 1);
+      return k < BKF;
+    } else {
+      k = lane;
+      q = warp + 8 * j;
+      return 4 * q < npad;
+    }
+  };
   auto load_block = [&](int kb, float4 (&av)[4], float4 (&bv)[NBQ]) {
-    const int64_t r = r_begin + (int64_t)kb * BKF + lane;
-    const bool r_ok = r < r_end;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int q = warp + 8 * j;
+      int k, q;
       av[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r_ok && q < a_q) av[j] = __ldg(reinterpret_cast<const float4*>(x + r * ldx + m0 + 4 * q));
+      if (item_a(j, k, q)) {
+        const int64_t r = r_begin + (int64_t)kb * BKF + k;
+        if (r < r_end && q < a_q) av[j] = __ldg(reinterpret_cast<const float4*>(x + r * ldx + m0 + 4 * q));
+      }
     }
 #pragma unroll
     for (int j = 0; j < NBQ; ++j) {
-      const int q = warp + 8 * j;
+      int k, q;
       bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r_ok && q < b_q) bv[j] = __ldg(reinterpret_cast<const float4*>(y + r * ldy + 4 * q));
+      if (item_b(j, k, q)) {
+        const int64_t r = r_begin + (int64_t)kb * BKF + k;
+        if (r < r_end && q < b_q) bv[j] = __ldg(reinterpret_cast<const float4*>(y + r * ldy + 4 * q));
+      }
     }
   };
-  // MN-major store: float4 q (elements 4q..4q+3) of reduction row `lane`, groups-per-K-group gpk
-  auto store_mn = [&](uint32_t tile_hi, uint32_t tile_lo, int q, int gpk, const float4& v) {
+  // MN-major store: float4 q (elements 4q..4q+3) of reduction row k, groups-per-K-group gpk
+  auto store_mn = [&](uint32_t tile_hi, uint32_t tile_lo, int k, int q, int gpk, const float4& v) {
     float4 hi, lo;
     split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
     split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-    const uint32_t off = (uint32_t)(((q >> 3) + gpk * (lane >> 2)) * 512 + (lane & 3) * 128 +
-                                    (((((q & 7) >> 1) ^ (lane & 3)) << 5) | ((q & 1) << 4)));
+    const uint32_t off = (uint32_t)(((q >> 3) + gpk * (k >> 2)) * 512 + (k & 3) * 128 +
+                                    (((((q & 7) >> 1) ^ (k & 3)) << 5) | ((q & 1) << 4)));
     *reinterpret_cast<float4*>(gen + tile_hi + off) = hi;
     *reinterpret_cast<float4*>(gen + tile_lo + off) = lo;
   };
@@ -497,10 +530,15 @@ gemm_tc_tn_kernel(int64_t R, int M, int N, const float* __restrict__ x, int64_t 
     if (use > 0) mbar_wait(bar_mma[s], (use - 1) & 1);
     if constexpr (MN) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) store_mn(L.a_hi[s], L.a_lo[s], warp + 8 * j, 4, av[j]);
+      for (int j = 0; j < 4; ++j) {
+        int k, q;
+        if (item_a(j, k, q)) store_mn(L.a_hi[s], L.a_lo[s], k, q, 4, av[j]);
+      }
 #pragma unroll
-      for (int j = 0; j < NBQ; ++j)
-        if (4 * (warp + 8 * j) < npad) store_mn(L.b_hi[s], L.b_lo[s], warp + 8 * j, ng, bv[j]);
+      for (int j = 0; j < NBQ; ++j) {
+        int k, q;
+        if (item_b(j, k, q)) store_mn(L.b_hi[s], L.b_lo[s], k, q, ng, bv[j]);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) store_t(L.a_hi[s], L.a_lo[s], 4 * (warp + 8 * j), av[j]);
