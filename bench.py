@@ -332,26 +332,77 @@ def run_ours(args, wl):
     achieved = alg_bytes / (spmm_ms * 1e-3) / 1e9
     traffic, xbar_bytes = ncu_traffic(args.workload)
 
-    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timing
-    e2e_s = 0.0
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timing.
+    # Inputs are double-buffered: step i+1's H2D copies run on a copy stream while step i computes,
+    # as a training loop with a pinned-memory loader does.  Every step still copies its own X and G
+    # in, and reads its dW/db back, inside the timed region.  No L2 flush here: one step touches
+    # ~200 MB (graph 120 MB + dense operands) > 126 MB L2.
     h2d = x_host.numel() * 4 + g_host.numel() * 4
     d2h = (fin * fout + fout) * 4
-    for i in range(2 + args.steps):
-        flush()
+    copy_stream = torch.cuda.Stream()
+    bufs = [(torch.empty_like(x), torch.empty_like(g)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        b = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[b])  # the step that last read this buffer pair has finished
+            bufs[b][0].copy_(x_host, non_blocking=True)
+            bufs[b][1].copy_(g_host, non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def e2e_loop(k):
+        for b in range(2):
+            done[b].record()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        xd = x_host.to(dev, non_blocking=True)
-        gd = g_host.to(dev, non_blocking=True)
-        layer.weight.grad = None
-        layer.bias.grad = None
-        o = layer(xd, graph)
-        o.backward(gd)
-        dw_h = layer.weight.grad.cpu()
-        db_h = layer.bias.grad.cpu()
+        prefetch(0)
+        for i in range(k):
+            if i + 1 < k:
+                prefetch(i + 1)
+            b = i % 2
+            torch.cuda.current_stream().wait_event(ready[b])
+            layer.weight.grad = None
+            layer.bias.grad = None
+            o = layer(bufs[b][0], graph)
+            o.backward(bufs[b][1])
+            done[b].record()
+            dw_h = layer.weight.grad.cpu()  # the step's result, read back every step (synchronises)
+            db_h = layer.bias.grad.cpu()
         torch.cuda.synchronize()
-        if i >= 2:
-            e2e_s += time.perf_counter() - t0
+        return time.perf_counter() - t0
+
+    e2e_loop(3)
+    e2e_s = e2e_loop(args.steps)
     e2e_value = nnz / (e2e_s / args.steps)
+
+    # ---- the reference's own three lines executed by PyTorch on this GPU (cuBLAS / cuSPARSE), the
+    # library kernels BASELINE.md asks to beat: adjacency as the COO tensor utils.py builds, and as CSR
+    torch_cuda = {}
+    try:
+        coo = graph.to_sparse_coo()
+        wref = layer.weight.detach().clone().requires_grad_(True)
+        bref = layer.bias.detach().clone().requires_grad_(True)
+        for form, adj_t in (("coo_as_built", coo), ("csr", coo.coalesce().to_sparse_csr())):
+            def ref_step():
+                wref.grad = None
+                bref.grad = None
+                o_ = torch.spmm(adj_t, torch.mm(x, wref)) + bref
+                o_.backward(g)
+            for _ in range(2):
+                ref_step()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = max(3, min(args.steps, 10))
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(reps):
+                ref_step()
+            b_.record()
+            torch.cuda.synchronize()
+            torch_cuda[form + "_ms_per_step"] = a.elapsed_time(b_) / reps
+    except Exception as e:  # pragma: no cover
+        torch_cuda["error"] = repr(e)
     sampler.stop()
 
     # ---- CPU baseline on the host cores (bounded sample), N=1 only
@@ -370,7 +421,10 @@ def run_ours(args, wl):
                    "bins": graph.bin_rows, "long_chunks": graph.n_long_chunks},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s / args.steps * 1e3},
+                "ms_per_step": e2e_s / args.steps * 1e3,
+                "how": "wall clock over K steps of layer(x_dev, graph); backward; grads.cpu(); inputs double-buffered "
+                       "from pinned host memory on a copy stream"},
+        "torch_cuda_reference": torch_cuda,
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "spmm_rows_vec_kernel<8,1> (CSR SpMM, fwd and A^T launches)",

@@ -35,7 +35,8 @@ struct DevBuf {
 
 template <typename T>
 int graph_alloc(gcnb_graph* g, T** out, int64_t count) {
-  size_t bytes = (size_t)(count > 0 ? count : 1) * sizeof(T);
+  // + 16 bytes: the TMA-staged SpMM widens its copy windows to 16-byte boundaries
+  size_t bytes = (size_t)(count > 0 ? count : 1) * sizeof(T) + 16;
   bytes = (bytes + 255) & ~(size_t)255;
   void* p = nullptr;
   GCNB_CUDA(cudaMalloc(&p, bytes));
@@ -528,8 +529,8 @@ int finalize(gcnb_graph* g, const int32_t* rows, cudaStream_t st, bool with_tran
     GCNB_CUDA(cudaStreamSynchronize(st));
     if (d == 0) {
       g->pattern_symmetric = true;
-      g->device_bytes -= (int64_t)((((size_t)(g->n_cols + 1) * 4 + 255) & ~(size_t)255) +
-                                   (((size_t)(nnz > 0 ? nnz : 1) * 4 + 255) & ~(size_t)255));
+      g->device_bytes -= (int64_t)((((size_t)(g->n_cols + 1) * 4 + 16 + 255) & ~(size_t)255) +
+                                   (((size_t)(nnz > 0 ? nnz : 1) * 4 + 16 + 255) & ~(size_t)255));
       cudaFree(g->t_rowptr);
       cudaFree(g->t_col);
       g->t_rowptr = g->rowptr;

@@ -12,7 +12,10 @@
 //     entries, one warp per chunk writes a partial row to scratch, a fix-up kernel adds the
 //     partials in chunk order (atomic-free, run-to-run deterministic);
 //   * bias add and ReLU are fused in the epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace gcnb {
 
@@ -179,6 +182,152 @@ spmm_rows_vec_kernel(int n_rows, const int32_t* __restrict__ rowptr, const int32
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-staged variant: the column-index and value streams of a row are pulled into shared memory
+// with cp.async.bulk (1-D TMA, mbarrier complete_tx) one chunk ahead of their use, instead of
+// being loaded into registers and broadcast with shuffles.  Each warp owns a two-slot ring
+// (2 x (132 int32 + 132 fp32)) and walks rows gw, gw + W, ...; the copy window is widened to
+// 16-byte boundaries (the CSR arrays are padded).  The gathers of feature rows are unchanged.
+constexpr int kTmaChunk = 128;           // stored entries per staged chunk
+constexpr int kTmaSlot = kTmaChunk + 4;  // + alignment slack; 528 bytes per array
+
+template <int LPR, int CH, int U>
+__device__ __forceinline__ void gather_batch_smem(float4 (&acc)[CH], const int32_t* __restrict__ cols,
+                                                  const float* __restrict__ vals, int s0, int cnt, int slot,
+                                                  const float* __restrict__ b, const int (&qoff)[CH], int64_t ldb) {
+  constexpr int G = 32 / LPR;
+  int cc[U];
+  float vv[U];
+  float4 x[U][CH];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int s = s0 + u * G + slot;  // entry index inside the current block of 32
+    const bool ok = s < cnt;
+    cc[u] = ok ? cols[s] : 0;
+    vv[u] = ok ? vals[s] : 0.f;
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const float* rowp = b + (int64_t)cc[u] * ldb;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) x[u][k] = ldg_f4(rowp + qoff[k]);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+#pragma unroll
+    for (int k = 0; k < CH; ++k) fma4(acc[k], vv[u], x[u][k]);
+}
+
+template <int LPR, int CH>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+spmm_rows_tma_kernel(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                     const float* __restrict__ val, const float* __restrict__ b, int64_t ldb, int f,
+                     const float* __restrict__ bias, int relu, float* __restrict__ out, int64_t ldo,
+                     int vec_out, int skip_long, int accumulate) {
+  constexpr int G = 32 / LPR;
+  constexpr int U = (LPR * CH >= 64) ? (8 / CH > 0 ? 8 / CH : 1) : (LPR < 8 ? LPR : 8);
+  __shared__ __align__(16) int32_t col_s[kWarpsPerCta][2][kTmaSlot];
+  __shared__ __align__(16) float val_s[kWarpsPerCta][2][kTmaSlot];
+  __shared__ __align__(8) unsigned long long bars[kWarpsPerCta][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = lane / LPR, sub = lane % LPR;
+  const uint32_t bar[2] = {smem_u32(&bars[warp][0]), smem_u32(&bars[warp][1])};
+  if (lane == 0) {
+    mbar_init(bar[0], 1);
+    mbar_init(bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int f4 = (f + 3) >> 2;
+  int qoff[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) qoff[k] = 4 * min(k * LPR + sub, f4 - 1);
+
+  const int W = gridDim.x * kWarpsPerCta;
+  // item = one chunk of one row: entries [e0, e1) of row `row` whose range ends at row_end
+  int row = blockIdx.x * kWarpsPerCta + warp - W, e0 = 0, e1 = 0, row_end = 0;
+  bool valid = true;
+  auto next_row = [&](int& r, int& a0, int& a1, int& rend) -> bool {
+    for (;;) {
+      r += W;
+      if (r >= n_rows) return false;
+      const int s_ = __ldg(rowptr + r), e_ = __ldg(rowptr + r + 1);
+      if (skip_long && e_ - s_ >= kLongRowThreshold) continue;
+      a0 = s_;
+      rend = e_;
+      a1 = min(s_ + kTmaChunk, e_);
+      return true;
+    }
+  };
+  auto issue = [&](int a0, int a1, int stage) {
+    if (a1 > a0 && lane == 0) {
+      const int w0 = a0 & ~3, w1 = (a1 + 3) & ~3;
+      const uint32_t bytes = (uint32_t)(w1 - w0) * 4u;
+      mbar_expect_tx(bar[stage], 2 * bytes);
+      bulk_g2s(smem_u32(&col_s[warp][stage][0]), col + w0, bytes, bar[stage]);
+      bulk_g2s(smem_u32(&val_s[warp][stage][0]), val + w0, bytes, bar[stage]);
+    }
+  };
+  valid = next_row(row, e0, e1, row_end);
+  int stage = 0;
+  uint32_t phase[2] = {0u, 0u};
+  if (valid) issue(e0, e1, 0);
+  float4 acc[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  while (valid) {
+    // the item after this one (next chunk of the row, or the first chunk of the warp's next row)
+    int nrow = row, ne0, ne1, nend = row_end;
+    bool nvalid = true;
+    if (e1 < row_end) {
+      ne0 = e1;
+      ne1 = min(e1 + kTmaChunk, row_end);
+    } else {
+      nvalid = next_row(nrow, ne0, ne1, nend);
+    }
+    if (nvalid) issue(ne0, ne1, stage ^ 1);
+    if (e1 > e0) {
+      mbar_wait(bar[stage], phase[stage]);
+      phase[stage] ^= 1u;
+      const int32_t* cols = &col_s[warp][stage][e0 & 3];
+      const float* vals = &val_s[warp][stage][e0 & 3];
+      const int n = e1 - e0;
+      for (int base = 0; base < n; base += 32) {
+        const int cnt = min(32, n - base);
+        const int jmax = (cnt + G - 1) / G;
+        int j = 0;
+        for (; j + U <= jmax; j += U)
+          gather_batch_smem<LPR, CH, U>(acc, cols + base, vals + base, j * G, cnt, slot, b, qoff, ldb);
+        if (U > 4 && j + 4 <= jmax) {
+          gather_batch_smem<LPR, CH, (U > 4 ? 4 : 1)>(acc, cols + base, vals + base, j * G, cnt, slot, b, qoff, ldb);
+          j += 4;
+        }
+        if (U > 2 && j + 2 <= jmax) {
+          gather_batch_smem<LPR, CH, (U > 2 ? 2 : 1)>(acc, cols + base, vals + base, j * G, cnt, slot, b, qoff, ldb);
+          j += 2;
+        }
+        if (U > 1 && j < jmax) gather_batch_smem<LPR, CH, 1>(acc, cols + base, vals + base, j * G, cnt, slot, b, qoff, ldb);
+      }
+    }
+    if (e1 == row_end) {  // row finished: combine the slots, epilogue, reset
+      reduce_slots<LPR, CH>(acc);
+      if (lane < LPR) {
+        float* out_row = out + (int64_t)row * ldo;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+          const int q = k * LPR + lane;
+          if (q < f4) store_row_chunk(out_row, q, f, vec_out, acc[k], bias, relu, accumulate);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();  // every lane is done with this slot before lane 0 lets TMA overwrite it
+    row = nrow; e0 = ne0; e1 = ne1; row_end = nend; valid = nvalid;
+    stage ^= 1;
+  }
+}
+
 // Long-row bin, phase 1: one warp per chunk of kLongChunk stored entries -> partial row.
 template <int LPR, int CH>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
@@ -280,13 +429,31 @@ spmm_rows_scalar_kernel(int n_rows, const int32_t* __restrict__ rowptr,
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// GCNB_SPMM_STAGING=tma | regs selects how the col/val streams reach the SM (default below)
+bool spmm_use_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GCNB_SPMM_STAGING");
+    v = (e && (e[0] == 't' || e[0] == 'T')) ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <int LPR, int CH>
 int launch_vec(const CsrView& a, const float* b, int64_t ldb, int f, const float* bias, bool relu,
                bool accumulate, float* out, int64_t ldo, bool vec_out, float* partial, int ldp,
                cudaStream_t st) {
   const bool has_long = a.n_long_rows > 0;
   const int grid = (int)ceil_div(a.n_rows, kWarpsPerCta);
-  if (grid > 0) {
+  if (grid > 0 && spmm_use_tma()) {
+    // persistent: 6 CTAs per SM walk the rows with a per-warp TMA ring for the index/value streams
+    int pgrid = 6 * kNumSMs;
+    if (pgrid > grid) pgrid = grid;
+    spmm_rows_tma_kernel<LPR, CH><<<pgrid, kWarpsPerCta * 32, 0, st>>>(
+        (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, f, bias, relu ? 1 : 0, out, ldo,
+        vec_out ? 1 : 0, has_long ? 1 : 0, accumulate ? 1 : 0);
+    GCNB_LAUNCH_CHECK();
+  } else if (grid > 0) {
     spmm_rows_vec_kernel<LPR, CH><<<grid, kWarpsPerCta * 32, 0, st>>>(
         (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, f, bias, relu ? 1 : 0, out, ldo,
         vec_out ? 1 : 0, has_long ? 1 : 0, accumulate ? 1 : 0);

@@ -47,7 +47,36 @@ def _ws(nbytes, device):
 
 
 def _ptr(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    # ctypes converts a plain int for c_void_p parameters; None is NULL
+    return t.data_ptr() if t is not None else None
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` only when dev is not already current (the common case costs nothing)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        self.ctx = None if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False
+
+
+def _layer_ws_bytes(lib, graph, fin, fout, precision):
+    """gcnb_layer_workspace_bytes, cached on the graph handle (constant per shape)."""
+    cache = graph.__dict__.setdefault("_ws_cache", {})
+    key = (fin, fout, precision)
+    v = cache.get(key)
+    if v is None:
+        v = cache[key] = int(lib.gcnb_layer_workspace_bytes(graph._h, fin, fout, precision))
+    return v
 
 
 class _GCNLayerFn(torch.autograd.Function):
@@ -61,14 +90,14 @@ class _GCNLayerFn(torch.autograd.Function):
         b = bias.contiguous() if bias is not None else None
         support = torch.empty((graph.n_cols, _ld4(fout)), dtype=torch.float32, device=dev)
         out = torch.empty((graph.n_rows, fout), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            nws = lib.gcnb_layer_workspace_bytes(graph._h, fin, fout, precision)
-            ws = _ws(nws, dev)
+        with _on_device(dev):
+            ws = _ws(_layer_ws_bytes(lib, graph, fin, fout, precision), dev)
             st = lib.gcnb_layer_forward(
                 graph._h, _ptr(xr), _ld(xr), _ptr(w), _ptr(b), fin, fout, _lib.LAYER_RELU if relu else 0, precision,
-                _ptr(support), _ptr(out), _ptr(ws), ws.numel(), _stream_ptr(dev),
+                _ptr(support), _ptr(out), _ptr(ws), ws.numel(), torch.cuda.current_stream(dev).cuda_stream,
             )
-        _lib.check(st, "gcnb_layer_forward")
+        if st:
+            _lib.check(st, "gcnb_layer_forward")
         ctx.graph = graph
         ctx.relu = relu
         ctx.precision = precision
@@ -95,14 +124,15 @@ class _GCNLayerFn(torch.autograd.Function):
         dw = torch.empty((fin, fout), dtype=torch.float32, device=dev) if need_dw else None
         db = torch.empty((fout,), dtype=torch.float32, device=dev) if need_db else None
         dx = torch.empty((graph.n_cols, fin), dtype=torch.float32, device=dev) if need_dx else None
-        with torch.cuda.device(dev):
-            nws = lib.gcnb_layer_workspace_bytes(graph._h, fin, fout, ctx.precision)
-            ws = _ws(nws, dev)
+        with _on_device(dev):
+            ws = _ws(_layer_ws_bytes(lib, graph, fin, fout, ctx.precision), dev)
             st = lib.gcnb_layer_backward(
                 graph._h, _ptr(xr), _ld(xr), _ptr(w), _ptr(gr), _ld(gr), _ptr(y), fin, fout, flags, ctx.precision,
-                _ptr(gm), _ptr(ds), _ptr(dw), _ptr(db), _ptr(dx), fin, _ptr(ws), ws.numel(), _stream_ptr(dev),
+                _ptr(gm), _ptr(ds), _ptr(dw), _ptr(db), _ptr(dx), fin, _ptr(ws), ws.numel(),
+                torch.cuda.current_stream(dev).cuda_stream,
             )
-        _lib.check(st, "gcnb_layer_backward")
+        if st:
+            _lib.check(st, "gcnb_layer_backward")
         return dx, dw, db, None, None, None
 
 
