@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GCNB_VERSION 100
+#define GCNB_VERSION 101
 
 #define GCNB_OK 0
 #define GCNB_E_INVALID 1  /* bad argument (shape, null pointer, alignment, overflow)  */
@@ -184,21 +184,27 @@ size_t gcnb_colsum_workspace_bytes(int64_t n_rows, int64_t f);
 #define GCNB_LAYER_NEED_DW 4
 #define GCNB_LAYER_NEED_DB 8
 
-/* forward of pygcn/layers.py:32-38:  support = X W ; out = A support (+ bias) (relu)
+/* forward of pygcn/layers.py:32-38:  support = X W ; out = A support (+ bias) (relu) (dropout)
  *   d_x [n_cols, fin] ld ldx ; d_w [fin, fout] contiguous ; d_bias [fout] or NULL
+ *   d_mask: NULL, or a keep-mask uint8 [n_rows, fout] applied last in the epilogue together with
+ *           mask_scale = 1/(1-p)  (upstream pygcn's F.dropout on the layer output; the fork has it
+ *           commented out, pygcn/models.py:50,54)
  *   d_support [n_cols, ld4(fout)] scratch, ld4(f) = 4*ceil(f/4) (rows stay 16-byte aligned)
  *   d_out [n_rows, fout] contiguous ; d_ws: gcnb_layer_workspace_bytes() bytes */
 int gcnb_layer_forward(const gcnb_graph* g, const float* d_x, int64_t ldx, const float* d_w,
                        const float* d_bias, int64_t fin, int64_t fout, int flags, int precision,
-                       float* d_support, float* d_out, void* d_ws, size_t ws_bytes, void* stream);
+                       const uint8_t* d_mask, float mask_scale, float* d_support, float* d_out, void* d_ws,
+                       size_t ws_bytes, void* stream);
 
 /* backward: db = colsum(G) ; dS = A^T G ; dW = X^T dS ; dX = dS W^T
  *   d_g [n_rows, fout] ld ldg ; d_y = forward output (only read with GCNB_LAYER_RELU)
- *   d_ds [n_cols, ld4(fout)] scratch ; d_gm [n_rows, fout] scratch (only with RELU)
+ *   d_ds [n_cols, ld4(fout)] scratch ; d_gm [n_rows, fout] scratch (only with RELU or a dropout mask)
+ *   d_mask / mask_scale: the same keep-mask the forward used (G is masked before anything else)
  *   d_dw [fin, fout], d_db [fout], d_dx [n_cols, fin] ld lddx: written when requested */
 int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_t ldx, const float* d_w,
                         const float* d_g, int64_t ldg, const float* d_y, int64_t fin, int64_t fout,
-                        int flags, int precision, float* d_gm, float* d_ds, float* d_dw,
+                        int flags, int precision, const uint8_t* d_mask, float mask_scale, float* d_gm,
+                        float* d_ds, float* d_dw,
                         float* d_db, float* d_dx, int64_t lddx, void* d_ws, size_t ws_bytes,
                         void* stream);
 size_t gcnb_layer_workspace_bytes(const gcnb_graph* g, int64_t fin, int64_t fout, int precision);

@@ -64,10 +64,10 @@ SIGNATURES = {
     "gcnb_gemm_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
     "gcnb_colsum": (c_int, [c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "gcnb_colsum_workspace_bytes": (c_sz, [c_i64, c_i64]),
-    "gcnb_layer_forward": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp,
-                                   c_vp, c_sz, c_vp]),
+    "gcnb_layer_forward": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, ctypes.c_float,
+                                   c_vp, c_vp, c_vp, c_sz, c_vp]),
     "gcnb_layer_backward": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int,
-                                    c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
+                                    c_vp, ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
     "gcnb_layer_workspace_bytes": (c_sz, [c_vp, c_i64, c_i64, c_int]),
     "gcnb_l2_flush": (c_int, [c_vp, c_sz, c_vp]),
 }

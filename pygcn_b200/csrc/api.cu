@@ -77,11 +77,12 @@ size_t graph_matmul_ws(const gcnb_graph* g, bool transpose, int64_t f) {
   return w;
 }
 
-int graph_matmul(const gcnb_graph* g, bool transpose, const float* b, int64_t ldb, int64_t f, const float* bias,
-                 bool relu, bool accumulate, float* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st) {
+int graph_matmul(const gcnb_graph* g, bool transpose, const float* b, int64_t ldb, int64_t f, const Epilogue& ep,
+                 float* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st) {
   const CsrView& v = transpose ? g->bwd : g->fwd;
-  if (!g->dense_fwd || accumulate) {
-    return spmm_launch(v, b, ldb, f, bias, relu, out, ldo, ws, ws_bytes, st, accumulate);
+  GCNB_REQUIRE(ep.mask == nullptr || ep.ld_mask >= f, "spmm: dropout mask leading dimension smaller than width");
+  if (!g->dense_fwd || ep.accumulate) {
+    return spmm_launch(v, b, ldb, f, ep, out, ldo, ws, ws_bytes, st);
   }
   GCNB_REQUIRE(f > 0 && ldb >= f && ldo >= f, "spmm(dense route): bad width / leading dimension");
   const int64_t m = transpose ? g->n_cols : g->n_rows;   // output rows
@@ -94,7 +95,18 @@ int graph_matmul(const gcnb_graph* g, bool transpose, const float* b, int64_t ld
   } else {
     GCNB_TRY(gemm_fp32_launch(m, f, r, x, 1, ldx, b, ldb, 1, out, ldo, ws, ws_bytes, st));
   }
-  return bias_act_launch(m, f, out, ldo, bias, relu, st);
+  return bias_act_launch(m, f, out, ldo, ep, st);
+}
+
+Epilogue make_epilogue(const float* bias, bool relu, bool accumulate, const uint8_t* mask, int64_t ld_mask, float scale) {
+  Epilogue ep;
+  ep.bias = bias;
+  ep.relu = relu ? 1 : 0;
+  ep.accumulate = accumulate ? 1 : 0;
+  ep.mask = mask;
+  ep.ld_mask = ld_mask;
+  ep.mask_scale = scale;
+  return ep;
 }
 
 }  // namespace
@@ -123,8 +135,10 @@ extern "C" int gcnb_spmm(const gcnb_graph* g, int flags, const float* d_b, int64
                          void* stream) {
   GCNB_REQUIRE(g != nullptr, "spmm: null graph");
   GCNB_REQUIRE(!(flags & GCNB_SPMM_TRANSPOSE) || g->has_transpose, "spmm: this handle is a block without a transpose");
-  return graph_matmul(g, (flags & GCNB_SPMM_TRANSPOSE) != 0, d_b, ldb, f, d_bias, (flags & GCNB_SPMM_RELU) != 0,
-                      (flags & GCNB_SPMM_ACCUMULATE) != 0, d_out, ldo, d_ws, ws_bytes, (cudaStream_t)stream);
+  return graph_matmul(g, (flags & GCNB_SPMM_TRANSPOSE) != 0, d_b, ldb, f,
+                      make_epilogue(d_bias, (flags & GCNB_SPMM_RELU) != 0, (flags & GCNB_SPMM_ACCUMULATE) != 0, nullptr, 0,
+                                    1.f),
+                      d_out, ldo, d_ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" size_t gcnb_spmm_workspace_bytes(const gcnb_graph* g, int flags, int64_t f) {
@@ -175,8 +189,8 @@ extern "C" size_t gcnb_layer_workspace_bytes(const gcnb_graph* g, int64_t fin, i
 
 extern "C" int gcnb_layer_forward(const gcnb_graph* g, const float* d_x, int64_t ldx, const float* d_w,
                                   const float* d_bias, int64_t fin, int64_t fout, int flags, int precision,
-                                  float* d_support, float* d_out, void* d_ws, size_t ws_bytes,
-                                  void* stream) {
+                                  const uint8_t* d_mask, float mask_scale, float* d_support, float* d_out,
+                                  void* d_ws, size_t ws_bytes, void* stream) {
   GCNB_REQUIRE(g != nullptr, "layer_forward: null graph");
   GCNB_REQUIRE(fin > 0 && fout > 0, "layer_forward: bad feature sizes %lld -> %lld", (long long)fin, (long long)fout);
   GCNB_REQUIRE(ldx >= fin, "layer_forward: ldx < in_features");
@@ -191,13 +205,15 @@ extern "C" int gcnb_layer_forward(const gcnb_graph* g, const float* d_x, int64_t
   GCNB_TRY(gemm_dispatch(g->n_cols, fout, fin, d_x, ldx, 1, d_w, fout, 1, d_support, lds, precision,
                          ws + s_bytes, d_bytes, st));
   // out = A support (+ bias) (relu)                  (pygcn/layers.py:34-36, models.py:49)
-  return graph_matmul(g, false, d_support, lds, fout, d_bias, (flags & GCNB_LAYER_RELU) != 0, false, d_out, fout,
-                      ws, s_bytes, st);
+  return graph_matmul(g, false, d_support, lds, fout,
+                      make_epilogue(d_bias, (flags & GCNB_LAYER_RELU) != 0, false, d_mask, fout, mask_scale), d_out,
+                      fout, ws, s_bytes, st);
 }
 
 extern "C" int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_t ldx, const float* d_w,
                                    const float* d_g, int64_t ldg, const float* d_y, int64_t fin,
-                                   int64_t fout, int flags, int precision, float* d_gm, float* d_ds,
+                                   int64_t fout, int flags, int precision, const uint8_t* d_mask,
+                                   float mask_scale, float* d_gm, float* d_ds,
                                    float* d_dw, float* d_db, float* d_dx, int64_t lddx, void* d_ws,
                                    size_t ws_bytes, void* stream) {
   GCNB_REQUIRE(g != nullptr, "layer_backward: null graph");
@@ -210,6 +226,7 @@ extern "C" int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_
   const bool need_dw = (flags & GCNB_LAYER_NEED_DW) != 0;
   const bool need_db = (flags & GCNB_LAYER_NEED_DB) != 0;
   GCNB_REQUIRE(!relu || (d_y != nullptr && d_gm != nullptr), "layer_backward: relu needs y and gm");
+  GCNB_REQUIRE(d_mask == nullptr || d_gm != nullptr, "layer_backward: dropout mask needs gm");
   GCNB_REQUIRE(ws_bytes >= gcnb_layer_workspace_bytes(g, fin, fout, precision) && d_ws != nullptr,
                "layer_backward: workspace too small");
   char* ws = reinterpret_cast<char*>(d_ws);
@@ -225,13 +242,16 @@ extern "C" int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_
   const float* gsrc = d_g;
   int64_t gld = ldg;
   // db = colsum(G) ; with the fused ReLU the mask is applied first: G <- G * [y > 0]
-  if (relu || need_db) {
+  const bool masked = relu || d_mask != nullptr;
+  if (masked || need_db) {
     float* db = d_db;
     GCNB_REQUIRE(db != nullptr || !need_db, "layer_backward: db requested but null");
     if (db == nullptr) db = reinterpret_cast<float*>(ws_gemm);  // discard
-    GCNB_TRY(colsum_launch(g->n_rows, fout, d_g, ldg, relu ? d_y : nullptr, fout, relu ? d_gm : nullptr,
-                           fout, db, ws_col, c_bytes, st));
-    if (relu) {
+    // with ReLU + dropout the forward output y is 0 wherever relu clipped or the mask dropped, and
+    // scale * relu(.) > 0 elsewhere, so [y > 0] is still the ReLU mask for the kept entries
+    GCNB_TRY(colsum_launch(g->n_rows, fout, d_g, ldg, relu ? d_y : nullptr, fout, masked ? d_gm : nullptr,
+                           fout, db, ws_col, c_bytes, st, d_mask, fout, mask_scale));
+    if (masked) {
       gsrc = d_gm;
       gld = fout;
     }
@@ -239,7 +259,7 @@ extern "C" int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_
   if (!need_dw && !need_dx) return GCNB_OK;
   // dS = A^T G                                      (MmBackward0 of torch.spmm)
   const int64_t lds = ceil_div(fout, 4) * 4;
-  GCNB_TRY(graph_matmul(g, true, gsrc, gld, fout, nullptr, false, false, d_ds, lds, ws_spmm, s_bytes, st));
+  GCNB_TRY(graph_matmul(g, true, gsrc, gld, fout, Epilogue(), d_ds, lds, ws_spmm, s_bytes, st));
   // dW = X^T dS                                     (MmBackward0 of torch.mm)
   if (need_dw) {
     GCNB_REQUIRE(d_dw != nullptr, "layer_backward: dW requested but null");

@@ -56,12 +56,22 @@ struct CsrView {
   int64_t bin_rows[GCNB_NUM_BINS] = {0, 0, 0, 0, 0};
 };
 
+// Fused SpMM epilogue:  out = dropout(relu(acc (+ out) (+ bias)))   -- pygcn/layers.py:36, the caller's
+// F.relu (models.py:49,53,56) and upstream pygcn's F.dropout on the layer output.
+struct Epilogue {
+  const float* bias = nullptr;    // [f] or null
+  int relu = 0;
+  int accumulate = 0;             // add the previous contents of out first
+  const uint8_t* mask = nullptr;  // [n_rows, ld_mask] keep-mask (0 / non-zero) or null
+  int64_t ld_mask = 0;
+  float mask_scale = 1.f;         // 1 / (1 - p)
+};
+
 constexpr int kLongRowThreshold = GCNB_BIN_EDGE_4;  // deg >= this -> split
 constexpr int kLongChunk = 1024;
 
-int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const float* bias,
-                bool relu, float* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t stream,
-                bool accumulate = false);
+int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const Epilogue& ep, float* out,
+                int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t spmm_workspace_bytes(const CsrView& a, int64_t f);
 
 int gemm_fp32_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs, int64_t a_cs,
@@ -84,14 +94,14 @@ int gemm_tc_tn_launch(int64_t m, int64_t n, int64_t r, const float* x, int64_t l
 
 int colsum_launch(int64_t n_rows, int64_t f, const float* g, int64_t ldg, const float* y,
                   int64_t ldy, float* gm, int64_t ldgm, float* out, void* ws, size_t ws_bytes,
-                  cudaStream_t stream);
+                  cudaStream_t stream, const uint8_t* mask = nullptr, int64_t ld_mask = 0,
+                  float mask_scale = 1.f);
 size_t colsum_workspace_bytes(int64_t n_rows, int64_t f);
 
 // out[(i / n) * ldo + i % n] = sum_{s < n_parts} partial[s * total + i], s ascending inside a fixed
 // 8-lane tree (deterministic).  total = m * n.
 // out[r, 0:f] = (accumulate ? out : 0) ... in place: out = act(out + bias)
-int bias_act_launch(int64_t n_rows, int64_t f, float* out, int64_t ldo, const float* bias, bool relu,
-                    cudaStream_t stream);
+int bias_act_launch(int64_t n_rows, int64_t f, float* out, int64_t ldo, const Epilogue& ep, cudaStream_t stream);
 
 int reduce_partials_launch(int64_t m, int64_t n, int n_parts, const float* partial, float* out,
                            int64_t ldo, cudaStream_t stream);

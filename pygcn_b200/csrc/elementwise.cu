@@ -14,7 +14,8 @@ __global__ void __launch_bounds__(kThreads)
 colsum_partial_kernel(int64_t n_rows, int f, int cw, int64_t rows_per_block,
                       const float* __restrict__ g, int64_t ldg, const float* __restrict__ y,
                       int64_t ldy, float* __restrict__ gm, int64_t ldgm,
-                      float* __restrict__ partial) {
+                      float* __restrict__ partial, const uint8_t* __restrict__ mask, int64_t ld_mask,
+                      float mask_scale) {
   __shared__ float red[kThreads];
   const int tx = threadIdx.x % cw;  // column lane
   const int ty = threadIdx.x / cw;  // row lane
@@ -31,6 +32,10 @@ colsum_partial_kernel(int64_t n_rows, int f, int cw, int64_t rows_per_block,
         float v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) v[u] = g[(r + u * rl) * ldg + j];
+        if (mask != nullptr) {  // backward of the dropout epilogue comes first (it was applied last)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = mask[(r + u * rl) * ld_mask + j] ? v[u] * mask_scale : 0.f;
+        }
         if (y != nullptr) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) v[u] = (y[(r + u * rl) * ldy + j] > 0.f) ? v[u] : 0.f;
@@ -44,6 +49,7 @@ colsum_partial_kernel(int64_t n_rows, int f, int cw, int64_t rows_per_block,
       }
       for (; r < r1; r += rl) {
         float v = g[r * ldg + j];
+        if (mask != nullptr) v = mask[r * ld_mask + j] ? v * mask_scale : 0.f;
         if (y != nullptr) v = (y[r * ldy + j] > 0.f) ? v : 0.f;
         if (gm != nullptr) gm[r * ldgm + j] = v;  // masked gradient, or a plain copy when y == NULL
         a4[0] += v;
@@ -94,14 +100,15 @@ reduce_partials_kernel(int64_t total, int64_t n, int n_parts, const float* __res
 }
 
 __global__ void __launch_bounds__(kThreads)
-bias_act_kernel(int64_t n_rows, int f, float* __restrict__ out, int64_t ldo, const float* __restrict__ bias, int relu) {
+bias_act_kernel(int64_t n_rows, int f, float* __restrict__ out, int64_t ldo, Epilogue ep) {
   const int64_t total = n_rows * f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / f;
     const int j = (int)(i % f);
     float v = out[r * ldo + j];
-    if (bias) v += __ldg(bias + j);
-    if (relu) v = fmaxf(v, 0.f);
+    if (ep.bias) v += __ldg(ep.bias + j);
+    if (ep.relu) v = fmaxf(v, 0.f);
+    if (ep.mask) v = __ldg(ep.mask + r * ep.ld_mask + j) ? v * ep.mask_scale : 0.f;
     out[r * ldo + j] = v;
   }
 }
@@ -131,7 +138,7 @@ size_t colsum_workspace_bytes(int64_t n_rows, int64_t f) {
 
 int colsum_launch(int64_t n_rows, int64_t f, const float* g, int64_t ldg, const float* y,
                   int64_t ldy, float* gm, int64_t ldgm, float* out, void* ws, size_t ws_bytes,
-                  cudaStream_t st) {
+                  cudaStream_t st, const uint8_t* mask, int64_t ld_mask, float mask_scale) {
   GCNB_REQUIRE(f > 0 && f < (1 << 24), "colsum: width out of range");
   GCNB_REQUIRE(out != nullptr, "colsum: null output");
   if (n_rows == 0) {
@@ -142,6 +149,7 @@ int colsum_launch(int64_t n_rows, int64_t f, const float* g, int64_t ldg, const 
   GCNB_REQUIRE(g != nullptr && ldg >= f, "colsum: bad gradient operand");
   GCNB_REQUIRE(y == nullptr || (gm != nullptr && ldy >= f), "colsum: bad mask operands");
   GCNB_REQUIRE(gm == nullptr || ldgm >= f, "colsum: ldgm < width");
+  GCNB_REQUIRE(mask == nullptr || (gm != nullptr && ld_mask >= f), "colsum: dropout mask needs gm and ld_mask >= width");
   const int nb = colsum_blocks(n_rows);
   const size_t need = colsum_workspace_bytes(n_rows, f);
   GCNB_REQUIRE(ws != nullptr && ws_bytes >= need, "colsum: workspace too small (%zu < %zu)", ws_bytes, need);
@@ -149,17 +157,16 @@ int colsum_launch(int64_t n_rows, int64_t f, const float* g, int64_t ldg, const 
   while (cw < f && cw < kThreads) cw <<= 1;
   const int64_t rows_per_block = ceil_div(n_rows, nb);
   colsum_partial_kernel<<<nb, kThreads, 0, st>>>(n_rows, (int)f, cw, rows_per_block, g, ldg, y, ldy, gm,
-                                                 ldgm, reinterpret_cast<float*>(ws));
+                                                 ldgm, reinterpret_cast<float*>(ws), mask, ld_mask, mask_scale);
   GCNB_LAUNCH_CHECK();
   return reduce_partials_launch(1, f, nb, reinterpret_cast<const float*>(ws), out, f, st);
 }
 
-int bias_act_launch(int64_t n_rows, int64_t f, float* out, int64_t ldo, const float* bias, bool relu,
-                    cudaStream_t st) {
-  if (n_rows == 0 || f == 0 || (bias == nullptr && !relu)) return GCNB_OK;
+int bias_act_launch(int64_t n_rows, int64_t f, float* out, int64_t ldo, const Epilogue& ep, cudaStream_t st) {
+  if (n_rows == 0 || f == 0 || (ep.bias == nullptr && !ep.relu && ep.mask == nullptr)) return GCNB_OK;
   int64_t blocks = ceil_div(n_rows * f, kThreads);
   if (blocks > kMaxBlocks) blocks = kMaxBlocks;
-  bias_act_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(n_rows, (int)f, out, ldo, bias, relu ? 1 : 0);
+  bias_act_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(n_rows, (int)f, out, ldo, ep);
   GCNB_LAUNCH_CHECK();
   return GCNB_OK;
 }

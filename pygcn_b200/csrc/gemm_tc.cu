@@ -357,6 +357,182 @@ gemm_tc_rows_kernel(int64_t M, int N, int K, const float* __restrict__ a, int64_
   }
 }
 
+// ------------------------------------------------------------------ mode R kernel, warp specialised
+// Same product and data path as gemm_tc_rows_kernel, restructured as the canonical Blackwell
+// pipeline: the three stages only meet through mbarriers, so loads, tensor-core work and the
+// TMEM drain of different tiles overlap inside one CTA (one CTA per SM, persistent over M tiles).
+//   warps 0-3  epilogue   : wait acc_full[a] -> tcgen05.ld lanes 32w..32w+31 -> global -> arrive acc_empty[a]
+//   warp  4    MMA issuer : TMEM alloc; resident B via TMA; wait full[s] -> 12 x tcgen05.mma ->
+//                           tcgen05.commit -> empty[s]; per K chunk commit -> acc_full[a]
+//   warps 5-8  producers  : HBM -> registers (one item ahead) -> (hi, lo) -> SW128 smem stage s ->
+//                           fence.proxy.async -> arrive full[s]
+// NS operand stages of 32 KB, two TMEM accumulators of npad columns.  Requires resident B.
+constexpr int kWsThreads = 288;
+
+__global__ void __launch_bounds__(kWsThreads, 1)
+gemm_tc_rows_ws_kernel(int64_t M, int N, int K, const float* __restrict__ a, int64_t lda,
+                       const float* __restrict__ img_hi, const float* __restrict__ img_lo, float* __restrict__ c,
+                       int64_t ldc, int npad, int nkb, int tmem_cols, int vec_ok, int ns) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  // layout: [ns x (a_hi 16K, a_lo 16K)] [nkb x (b_hi, b_lo)] [barriers]
+  const uint32_t b_bytes = (uint32_t)npad * 128;
+  const uint32_t off_b = (uint32_t)ns * 2 * kTileBytes;
+  const uint32_t off_bar = (off_b + (uint32_t)nkb * 2 * b_bytes + 1023u) & ~1023u;
+  auto bar_full = [&](int s_) { return base + off_bar + 8u * (uint32_t)s_; };
+  auto bar_empty = [&](int s_) { return base + off_bar + 64u + 8u * (uint32_t)s_; };
+  const uint32_t bar_b = base + off_bar + 128u;
+  auto bar_acc_full = [&](int a_) { return base + off_bar + 136u + 8u * (uint32_t)a_; };
+  auto bar_acc_empty = [&](int a_) { return base + off_bar + 152u + 8u * (uint32_t)a_; };
+  const uint32_t tmem_slot_off = off_bar + 168u;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < ns; ++i) { mbar_init(bar_full(i), 4); mbar_init(bar_empty(i), 1); }
+    mbar_init(bar_b, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full(i), 1); mbar_init(bar_acc_empty(i), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    __syncwarp();
+    tmem_alloc(base + tmem_slot_off, (uint32_t)tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + tmem_slot_off);
+
+  const int nt = blockIdx.y;
+  const int n0 = nt * npad;
+  const int n_cols = min(npad, N - n0);
+  const int64_t m_tiles = (M + BM - 1) / BM;
+  const int64_t my_tiles = (m_tiles > (int64_t)blockIdx.x) ? (m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t n_items = my_tiles * nkb;
+  const int chunks_per_tile = (nkb + kChunkBlocks - 1) / kChunkBlocks;
+
+  if (warp >= 5) {
+    // ===================== producers =====================
+    const int pt = tid - 160;
+    const int chunk = pt & 7;
+    const int row_in = pt >> 3;  // 0..15, +16*j
+    auto load_item = [&](int64_t item, float4 (&dst)[8]) {
+      const int64_t m0 = ((int64_t)blockIdx.x + (item / nkb) * gridDim.x) * BM;
+      const int k = (int)(item % nkb) * BKF + chunk * 4;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int64_t r = m0 + row_in + 16 * j;
+        dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < M && k < K) dst[j] = __ldg(reinterpret_cast<const float4*>(a + r * lda + k));
+      }
+    };
+    float4 cur[8], nxt[8];
+    if (n_items > 0) load_item(0, cur);
+    for (int64_t item = 0; item < n_items; ++item) {
+      const int s = (int)(item % ns);
+      const uint32_t use = (uint32_t)(item / ns);
+      if (item + 1 < n_items) load_item(item + 1, nxt);
+      if (use > 0) mbar_wait(bar_empty(s), (use - 1) & 1);
+      uint8_t* a_hi = gen + (uint32_t)s * 2 * kTileBytes;
+      uint8_t* a_lo = a_hi + kTileBytes;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = row_in + 16 * j;
+        float4 hi, lo;
+        split_tf32(cur[j].x, hi.x, lo.x); split_tf32(cur[j].y, hi.y, lo.y);
+        split_tf32(cur[j].z, hi.z, lo.z); split_tf32(cur[j].w, hi.w, lo.w);
+        const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
+        *reinterpret_cast<float4*>(a_hi + off) = hi;
+        *reinterpret_cast<float4*>(a_lo + off) = lo;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full(s));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(npad);
+      mbar_expect_tx(bar_b, 2 * b_bytes * (uint32_t)nkb);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int64_t blk = (int64_t)nt * nkb + kb;
+        bulk_g2s(base + off_b + (uint32_t)kb * 2 * b_bytes, img_hi + blk * ((int64_t)npad * BKF), b_bytes, bar_b);
+        bulk_g2s(base + off_b + (uint32_t)kb * 2 * b_bytes + b_bytes, img_lo + blk * ((int64_t)npad * BKF), b_bytes,
+                 bar_b);
+      }
+      mbar_wait(bar_b, 0);
+      int64_t item = 0;
+      uint32_t chunk_ctr = 0;
+      for (int64_t t = 0; t < my_tiles; ++t) {
+        for (int kb = 0; kb < nkb; ++kb, ++item) {
+          const int ab = (int)(chunk_ctr & 1u);
+          const uint32_t j_use = chunk_ctr >> 1;
+          if (kb % kChunkBlocks == 0 && j_use > 0) mbar_wait(bar_acc_empty(ab), (j_use - 1) & 1);
+          const int s = (int)(item % ns);
+          const uint32_t use = (uint32_t)(item / ns);
+          mbar_wait(bar_full(s), use & 1);
+          tc_fence_after();
+          const uint32_t a_hi = base + (uint32_t)s * 2 * kTileBytes;
+          const uint32_t bh = base + off_b + (uint32_t)kb * 2 * b_bytes;
+          issue_kblock(tmem_base + (uint32_t)ab * (uint32_t)npad, a_hi, a_hi + kTileBytes, bh, bh + b_bytes, idesc,
+                       kb % kChunkBlocks == 0);
+          umma_commit(bar_empty(s));
+          if (kb == nkb - 1 || kb % kChunkBlocks == kChunkBlocks - 1) {
+            umma_commit(bar_acc_full(ab));
+            ++chunk_ctr;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    uint32_t chunk_ctr = 0;
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      const int64_t m0 = ((int64_t)blockIdx.x + t * gridDim.x) * BM;
+      const int64_t row = m0 + warp * 32 + lane;
+      for (int ch = 0; ch < chunks_per_tile; ++ch, ++chunk_ctr) {
+        const int ab = (int)(chunk_ctr & 1u);
+        mbar_wait(bar_acc_full(ab), (chunk_ctr >> 1) & 1);
+        tc_fence_after();
+        const bool add = ch > 0;
+        for (int cb = 0; cb < npad; cb += 8) {
+          float v[8];
+          __syncwarp();
+          tmem_ld8(tmem_base + (uint32_t)ab * (uint32_t)npad + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, v);
+          if (row < M) {
+            float* dst = c + row * ldc + n0 + cb;
+            if (vec_ok && cb + 8 <= n_cols) {
+              if (add) {
+                const float4 p0 = *reinterpret_cast<const float4*>(dst);
+                const float4 p1 = *reinterpret_cast<const float4*>(dst + 4);
+                v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
+                v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+              }
+              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+#pragma unroll
+              for (int t2 = 0; t2 < 8; ++t2)
+                if (cb + t2 < n_cols) dst[t2] = add ? dst[t2] + v[t2] : v[t2];
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty(ab));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------ mode T kernel
 // C_partial[split][M tile rows][N] = sum over rows r in the split of X[r, m] * Y[r, n]
 // NBQ = float4 loads of Y per thread per K block (npad <= 32*NBQ).
@@ -564,6 +740,16 @@ RowsPlan rows_plan(int64_t n, int64_t k) {
   return p;
 }
 
+// GCNB_ROWS_KERNEL=sync selects the __syncthreads-pipelined rows kernel (default: warp specialised)
+bool rows_use_ws() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GCNB_ROWS_KERNEL");
+    v = (e && (e[0] == 's' || e[0] == 'S')) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // GCNB_TN_LAYOUT=k selects the transposing K-major variant of the tn kernel (default: MN-major)
 bool tn_use_mn() {
   static int v = -1;
@@ -628,6 +814,27 @@ int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t
     attr_set = true;
   }
   const int64_t m_tiles = ceil_div(m, BM);
+  const int vec_ok_ = (ldc % 4 == 0) && aligned16(c) && (p.npad % 4 == 0);
+  if (b_resident && rows_use_ws()) {
+    // warp-specialised pipeline: as many 32 KB operand stages as fit beside the resident B (<= 4)
+    const size_t b_total = (size_t)p.nkb * 2 * p.npad * 128;
+    int ns = (int)((200 * 1024 - b_total) / (2 * kTileBytes));
+    if (ns > 4) ns = 4;
+    const uint32_t smem_ws = (uint32_t)(ns * 2 * kTileBytes + ((b_total + 1023) & ~(size_t)1023) + 1024 + 1024);
+    static bool ws_attr = false;
+    if (!ws_attr) {
+      GCNB_CUDA(cudaFuncSetAttribute(gemm_tc_rows_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      ws_attr = true;
+    }
+    int64_t gxw = kNumSMs / p.n_tiles;
+    if (gxw < 1) gxw = 1;
+    if (gxw > m_tiles) gxw = m_tiles;
+    dim3 gridw((unsigned)gxw, (unsigned)p.n_tiles);
+    gemm_tc_rows_ws_kernel<<<gridw, kWsThreads, smem_ws, st>>>(m, (int)n, (int)k, a, lda, img_hi, img_lo, c, ldc, p.npad,
+                                                              p.nkb, tmem_cols_for(2 * p.npad), vec_ok_, ns);
+    GCNB_LAUNCH_CHECK();
+    return GCNB_OK;
+  }
   const int ctas_per_sm = (smem <= 110 * 1024) ? 2 : 1;
   int64_t gx = (int64_t)kNumSMs * ctas_per_sm / p.n_tiles;
   if (gx < 1) gx = 1;

@@ -122,11 +122,10 @@ __device__ __forceinline__ void reduce_slots(float4 (&acc)[CH]) {
   }
 }
 
-__device__ __forceinline__ void store_row_chunk(float* out_row, int q, int f, bool vec_out,
-                                                float4 a, const float* __restrict__ bias,
-                                                bool relu, bool accumulate) {
+__device__ __forceinline__ void store_row_chunk(float* out_row, int64_t row, int q, int f, bool vec_out,
+                                                float4 a, const Epilogue& ep) {
   float r[4] = {a.x, a.y, a.z, a.w};
-  if (accumulate) {  // out += A*B (column-blocked multi-GPU SpMM adds one source block at a time)
+  if (ep.accumulate) {  // out += A*B (column-blocked multi-GPU SpMM adds one source block at a time)
     if (vec_out) {
       const float4 o = *reinterpret_cast<const float4*>(out_row + 4 * q);
       r[0] += o.x; r[1] += o.y; r[2] += o.z; r[3] += o.w;
@@ -140,8 +139,9 @@ __device__ __forceinline__ void store_row_chunk(float* out_row, int q, int f, bo
   for (int t = 0; t < 4; ++t) {
     const int c = 4 * q + t;
     if (c < f) {
-      if (bias) r[t] += __ldg(bias + c);
-      if (relu) r[t] = fmaxf(r[t], 0.f);
+      if (ep.bias) r[t] += __ldg(ep.bias + c);
+      if (ep.relu) r[t] = fmaxf(r[t], 0.f);
+      if (ep.mask) r[t] = __ldg(ep.mask + row * ep.ld_mask + c) ? r[t] * ep.mask_scale : 0.f;
     }
   }
   if (vec_out) {
@@ -158,8 +158,7 @@ template <int LPR, int CH>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 spmm_rows_vec_kernel(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                      const float* __restrict__ val, const float* __restrict__ b, int64_t ldb, int f,
-                     const float* __restrict__ bias, int relu, float* __restrict__ out, int64_t ldo,
-                     int vec_out, int skip_long, int accumulate) {
+                     Epilogue ep, float* __restrict__ out, int64_t ldo, int vec_out, int skip_long) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (row >= n_rows) return;
@@ -177,7 +176,7 @@ spmm_rows_vec_kernel(int n_rows, const int32_t* __restrict__ rowptr, const int32
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
       const int q = k * LPR + lane;
-      if (q < f4) store_row_chunk(out_row, q, f, vec_out, acc[k], bias, relu, accumulate);
+      if (q < f4) store_row_chunk(out_row, row, q, f, vec_out, acc[k], ep);
     }
   }
 }
@@ -222,8 +221,7 @@ template <int LPR, int CH>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 spmm_rows_tma_kernel(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                      const float* __restrict__ val, const float* __restrict__ b, int64_t ldb, int f,
-                     const float* __restrict__ bias, int relu, float* __restrict__ out, int64_t ldo,
-                     int vec_out, int skip_long, int accumulate) {
+                     Epilogue ep, float* __restrict__ out, int64_t ldo, int vec_out, int skip_long) {
   constexpr int G = 32 / LPR;
   constexpr int U = (LPR * CH >= 64) ? (8 / CH > 0 ? 8 / CH : 1) : (LPR < 8 ? LPR : 8);
   __shared__ __align__(16) int32_t col_s[kWarpsPerCta][2][kTmaSlot];
@@ -316,7 +314,7 @@ spmm_rows_tma_kernel(int n_rows, const int32_t* __restrict__ rowptr, const int32
 #pragma unroll
         for (int k = 0; k < CH; ++k) {
           const int q = k * LPR + lane;
-          if (q < f4) store_row_chunk(out_row, q, f, vec_out, acc[k], bias, relu, accumulate);
+          if (q < f4) store_row_chunk(out_row, row, q, f, vec_out, acc[k], ep);
         }
       }
 #pragma unroll
@@ -370,8 +368,7 @@ spmm_long_partial_kernel(int n_long_rows, int n_chunks, const int32_t* __restric
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 spmm_long_fixup_kernel(int n_long_rows, const int32_t* __restrict__ long_rows,
                        const int32_t* __restrict__ long_chunk_ptr, const float* __restrict__ partial,
-                       int ldp, int f, const float* __restrict__ bias, int relu,
-                       float* __restrict__ out, int64_t ldo, int accumulate) {
+                       int ldp, int f, Epilogue ep, float* __restrict__ out, int64_t ldo) {
   const int lane = threadIdx.x & 31;
   const int li = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (li >= n_long_rows) return;
@@ -381,9 +378,10 @@ spmm_long_fixup_kernel(int n_long_rows, const int32_t* __restrict__ long_rows,
   for (int j = lane; j < f; j += 32) {
     float acc = 0.f;
     for (int c = c0; c < c1; ++c) acc += partial[(int64_t)c * ldp + j];
-    if (accumulate) acc += out[(int64_t)row * ldo + j];
-    if (bias) acc += __ldg(bias + j);
-    if (relu) acc = fmaxf(acc, 0.f);
+    if (ep.accumulate) acc += out[(int64_t)row * ldo + j];
+    if (ep.bias) acc += __ldg(ep.bias + j);
+    if (ep.relu) acc = fmaxf(acc, 0.f);
+    if (ep.mask) acc = __ldg(ep.mask + (int64_t)row * ep.ld_mask + j) ? acc * ep.mask_scale : 0.f;
     out[(int64_t)row * ldo + j] = acc;
   }
 }
@@ -393,8 +391,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 spmm_rows_scalar_kernel(int n_rows, const int32_t* __restrict__ rowptr,
                         const int32_t* __restrict__ col, const float* __restrict__ val,
                         const float* __restrict__ b, int64_t ldb, int f,
-                        const float* __restrict__ bias, int relu, float* __restrict__ out,
-                        int64_t ldo, int accumulate) {
+                        Epilogue ep, float* __restrict__ out, int64_t ldo) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (row >= n_rows) return;
@@ -419,9 +416,10 @@ spmm_rows_scalar_kernel(int n_rows, const int32_t* __restrict__ rowptr,
       }
     }
     if (j < f) {
-      if (accumulate) acc += out[(int64_t)row * ldo + j];
-      if (bias) acc += __ldg(bias + j);
-      if (relu) acc = fmaxf(acc, 0.f);
+      if (ep.accumulate) acc += out[(int64_t)row * ldo + j];
+      if (ep.bias) acc += __ldg(ep.bias + j);
+      if (ep.relu) acc = fmaxf(acc, 0.f);
+      if (ep.mask) acc = __ldg(ep.mask + (int64_t)row * ep.ld_mask + j) ? acc * ep.mask_scale : 0.f;
       out[(int64_t)row * ldo + j] = acc;
     }
   }
@@ -440,9 +438,8 @@ bool spmm_use_tma() {
 }
 
 template <int LPR, int CH>
-int launch_vec(const CsrView& a, const float* b, int64_t ldb, int f, const float* bias, bool relu,
-               bool accumulate, float* out, int64_t ldo, bool vec_out, float* partial, int ldp,
-               cudaStream_t st) {
+int launch_vec(const CsrView& a, const float* b, int64_t ldb, int f, const Epilogue& ep, float* out,
+               int64_t ldo, bool vec_out, float* partial, int ldp, cudaStream_t st) {
   const bool has_long = a.n_long_rows > 0;
   const int grid = (int)ceil_div(a.n_rows, kWarpsPerCta);
   if (grid > 0 && spmm_use_tma()) {
@@ -450,13 +447,11 @@ int launch_vec(const CsrView& a, const float* b, int64_t ldb, int f, const float
     int pgrid = 6 * kNumSMs;
     if (pgrid > grid) pgrid = grid;
     spmm_rows_tma_kernel<LPR, CH><<<pgrid, kWarpsPerCta * 32, 0, st>>>(
-        (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, f, bias, relu ? 1 : 0, out, ldo,
-        vec_out ? 1 : 0, has_long ? 1 : 0, accumulate ? 1 : 0);
+        (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, f, ep, out, ldo, vec_out ? 1 : 0, has_long ? 1 : 0);
     GCNB_LAUNCH_CHECK();
   } else if (grid > 0) {
     spmm_rows_vec_kernel<LPR, CH><<<grid, kWarpsPerCta * 32, 0, st>>>(
-        (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, f, bias, relu ? 1 : 0, out, ldo,
-        vec_out ? 1 : 0, has_long ? 1 : 0, accumulate ? 1 : 0);
+        (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, f, ep, out, ldo, vec_out ? 1 : 0, has_long ? 1 : 0);
     GCNB_LAUNCH_CHECK();
   }
   if (has_long) {
@@ -467,8 +462,7 @@ int launch_vec(const CsrView& a, const float* b, int64_t ldb, int f, const float
     GCNB_LAUNCH_CHECK();
     const int g2 = (int)ceil_div(a.n_long_rows, kWarpsPerCta);
     spmm_long_fixup_kernel<<<g2, kWarpsPerCta * 32, 0, st>>>(
-        (int)a.n_long_rows, a.long_rows, a.long_chunk_ptr, partial, ldp, f, bias, relu ? 1 : 0, out,
-        ldo, accumulate ? 1 : 0);
+        (int)a.n_long_rows, a.long_rows, a.long_chunk_ptr, partial, ldp, f, ep, out, ldo);
     GCNB_LAUNCH_CHECK();
   }
   return GCNB_OK;
@@ -483,9 +477,8 @@ size_t spmm_workspace_bytes(const CsrView& a, int64_t f) {
   return (size_t)a.n_long_chunks * (size_t)partial_ld(f) * sizeof(float);
 }
 
-int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const float* bias,
-                bool relu, float* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st,
-                bool accumulate) {
+int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const Epilogue& ep, float* out,
+                int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st) {
   GCNB_REQUIRE(f > 0 && f <= (1 << 20), "spmm: feature width %lld out of range", (long long)f);
   GCNB_REQUIRE(ldb >= f && ldo >= f, "spmm: leading dimension smaller than width");
   GCNB_REQUIRE(a.n_rows < (1ll << 31), "spmm: too many rows");
@@ -504,13 +497,12 @@ int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const 
     // generic path handles long rows too (a warp walks the whole row)
     const int grid = (int)ceil_div(a.n_rows, kWarpsPerCta);
     spmm_rows_scalar_kernel<<<grid, kWarpsPerCta * 32, 0, st>>>(
-        (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, (int)f, bias, relu ? 1 : 0, out, ldo,
-        accumulate ? 1 : 0);
+        (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, (int)f, ep, out, ldo);
     GCNB_LAUNCH_CHECK();
     return GCNB_OK;
   }
 #define GCNB_SPMM_CASE(LPR, CH) \
-  return launch_vec<LPR, CH>(a, b, ldb, (int)f, bias, relu, accumulate, out, ldo, vec_out, partial, ldp, st)
+  return launch_vec<LPR, CH>(a, b, ldb, (int)f, ep, out, ldo, vec_out, partial, ldp, st)
   if (f4 <= 1) GCNB_SPMM_CASE(1, 1);
   if (f4 <= 2) GCNB_SPMM_CASE(2, 1);
   if (f4 <= 4) GCNB_SPMM_CASE(4, 1);
@@ -523,8 +515,10 @@ int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const 
   // wider than 512 floats: column panels of 512
   for (int64_t f0 = 0; f0 < f; f0 += 512) {
     const int64_t fw = (f - f0 < 512) ? (f - f0) : 512;
-    GCNB_TRY(spmm_launch(a, b + f0, ldb, fw, bias ? bias + f0 : nullptr, relu, out + f0, ldo, ws,
-                         ws_bytes, st, accumulate));
+    Epilogue e2 = ep;
+    if (e2.bias) e2.bias += f0;
+    if (e2.mask) e2.mask += f0;
+    GCNB_TRY(spmm_launch(a, b + f0, ldb, fw, e2, out + f0, ldo, ws, ws_bytes, st));
   }
   return GCNB_OK;
 }

@@ -81,7 +81,7 @@ def _layer_ws_bytes(lib, graph, fin, fout, precision):
 
 class _GCNLayerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, graph, relu, precision):
+    def forward(ctx, x, weight, bias, graph, relu, precision, mask=None, mask_scale=1.0):
         lib = _lib.load()
         dev = x.device
         fin, fout = weight.shape
@@ -94,7 +94,8 @@ class _GCNLayerFn(torch.autograd.Function):
             ws = _ws(_layer_ws_bytes(lib, graph, fin, fout, precision), dev)
             st = lib.gcnb_layer_forward(
                 graph._h, _ptr(xr), _ld(xr), _ptr(w), _ptr(b), fin, fout, _lib.LAYER_RELU if relu else 0, precision,
-                _ptr(support), _ptr(out), _ptr(ws), ws.numel(), torch.cuda.current_stream(dev).cuda_stream,
+                _ptr(mask), mask_scale, _ptr(support), _ptr(out), _ptr(ws), ws.numel(),
+                torch.cuda.current_stream(dev).cuda_stream,
             )
         if st:
             _lib.check(st, "gcnb_layer_forward")
@@ -103,6 +104,8 @@ class _GCNLayerFn(torch.autograd.Function):
         ctx.precision = precision
         ctx.has_bias = bias is not None
         ctx.x_shape = tuple(x.shape)
+        ctx.mask = mask
+        ctx.mask_scale = mask_scale
         ctx.save_for_backward(xr, w, out if relu else None)
         return out
 
@@ -120,7 +123,8 @@ class _GCNLayerFn(torch.autograd.Function):
         flags = (_lib.LAYER_RELU if ctx.relu else 0) | (_lib.LAYER_NEED_DX if need_dx else 0) | (
             _lib.LAYER_NEED_DW if need_dw else 0) | (_lib.LAYER_NEED_DB if need_db else 0)
         ds = torch.empty((graph.n_cols, _ld4(fout)), dtype=torch.float32, device=dev)
-        gm = torch.empty((graph.n_rows, fout), dtype=torch.float32, device=dev) if ctx.relu else None
+        masked = ctx.relu or ctx.mask is not None
+        gm = torch.empty((graph.n_rows, fout), dtype=torch.float32, device=dev) if masked else None
         dw = torch.empty((fin, fout), dtype=torch.float32, device=dev) if need_dw else None
         db = torch.empty((fout,), dtype=torch.float32, device=dev) if need_db else None
         dx = torch.empty((graph.n_cols, fin), dtype=torch.float32, device=dev) if need_dx else None
@@ -128,12 +132,13 @@ class _GCNLayerFn(torch.autograd.Function):
             ws = _ws(_layer_ws_bytes(lib, graph, fin, fout, ctx.precision), dev)
             st = lib.gcnb_layer_backward(
                 graph._h, _ptr(xr), _ld(xr), _ptr(w), _ptr(gr), _ld(gr), _ptr(y), fin, fout, flags, ctx.precision,
-                _ptr(gm), _ptr(ds), _ptr(dw), _ptr(db), _ptr(dx), fin, _ptr(ws), ws.numel(),
+                _ptr(ctx.mask), ctx.mask_scale, _ptr(gm), _ptr(ds), _ptr(dw), _ptr(db), _ptr(dx), fin, _ptr(ws),
+                ws.numel(),
                 torch.cuda.current_stream(dev).cuda_stream,
             )
         if st:
             _lib.check(st, "gcnb_layer_backward")
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
 def _check_layer_args(x, graph, weight, bias):
@@ -159,17 +164,28 @@ def _check_layer_args(x, graph, weight, bias):
             raise RuntimeError("bias must be a float32 [%d] tensor on %s" % (weight.shape[1], graph.device))
 
 
-def gcn_layer(input, adj, weight, bias=None, relu=False, precision="auto"):
-    """`adj @ (input @ weight) + bias` (optionally followed by ReLU) -- pygcn/layers.py:32-38.
+def gcn_layer(input, adj, weight, bias=None, relu=False, precision="auto", dropout_mask=None, dropout_p=0.0):
+    """`adj @ (input @ weight) + bias` (optionally followed by ReLU, then dropout) -- pygcn/layers.py:32-38.
 
     adj: torch sparse COO / sparse CSR / dense tensor, or a `Graph`.
     relu=True fuses the `F.relu` the reference's models apply to every layer output
     (pygcn/models.py:49,53,56); applying F.relu again on the result is a no-op, so unchanged
     callers stay correct.
+    dropout_mask: optional keep-mask (bool/uint8 [n_rows, out_features]) fused into the same epilogue
+    with scale 1/(1-dropout_p) -- upstream pygcn's `F.dropout` on the layer output (commented out in
+    the fork, pygcn/models.py:50,54); the backward masks the incoming gradient the same way.
     """
     graph = as_graph(adj)
     _check_layer_args(input, graph, weight, bias)
-    return _GCNLayerFn.apply(input, weight, bias, graph, bool(relu), _PRECISIONS[precision])
+    mask, scale = None, 1.0
+    if dropout_mask is not None:
+        if not 0.0 <= dropout_p < 1.0:
+            raise ValueError("dropout probability has to be in [0, 1), got %r" % (dropout_p,))
+        if tuple(dropout_mask.shape) != (graph.n_rows, weight.shape[1]) or dropout_mask.device != graph.device:
+            raise RuntimeError("dropout_mask must be a [%d, %d] tensor on %s" % (graph.n_rows, weight.shape[1], graph.device))
+        mask = dropout_mask.to(torch.uint8).contiguous()
+        scale = 1.0 / (1.0 - dropout_p)
+    return _GCNLayerFn.apply(input, weight, bias, graph, bool(relu), _PRECISIONS[precision], mask, scale)
 
 
 class _SpmmFn(torch.autograd.Function):

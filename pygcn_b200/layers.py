@@ -21,15 +21,18 @@ class GraphConvolution(Module):
     Extra keyword-only options (defaults reproduce the reference exactly):
       fuse_relu  -- apply the ReLU every caller in pygcn/models.py applies, inside the SpMM
                     epilogue (a following F.relu is then a no-op, results are identical)
+      dropout    -- p of a dropout fused after the (optional) ReLU, active in training mode only
+                    (upstream pygcn applies F.dropout to the layer output; the fork commented it out)
       precision  -- "auto" (default: tcgen05 3xTF32 when the product is large enough, fp32 CUDA
                     cores otherwise), "tf32x3" or "fp32" for the dense products
     """
 
-    def __init__(self, in_features, out_features, bias=True, *, fuse_relu=False, precision="auto"):
+    def __init__(self, in_features, out_features, bias=True, *, fuse_relu=False, dropout=0.0, precision="auto"):
         super().__init__()
         self.in_features = in_features
         self.out_features = out_features
         self.fuse_relu = fuse_relu
+        self.dropout = dropout
         self.precision = precision
         self.weight = Parameter(torch.empty(in_features, out_features, dtype=torch.float32))
         if bias:
@@ -47,8 +50,13 @@ class GraphConvolution(Module):
             self.bias.data.uniform_(-bound, bound)
 
     def forward(self, input, adj):
-        return gcn_layer(input, adj, self.weight, self.bias,
-                         relu=getattr(self, "fuse_relu", False), precision=getattr(self, "precision", "auto"))
+        p = getattr(self, "dropout", 0.0)
+        mask = None
+        if p > 0.0 and self.training:
+            n_rows = adj.shape[0]
+            mask = torch.rand(n_rows, self.out_features, device=input.device) >= p
+        return gcn_layer(input, adj, self.weight, self.bias, relu=getattr(self, "fuse_relu", False),
+                         precision=getattr(self, "precision", "auto"), dropout_mask=mask, dropout_p=p)
 
     def __repr__(self):
         return "%s (%s -> %s)" % (self.__class__.__name__, self.in_features, self.out_features)

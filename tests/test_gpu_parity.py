@@ -226,6 +226,42 @@ def test_dense_route_fork_shape(P, n, fin, fout):
     assert ((l2(x, adj) - torch.relu(ref.detach()).float()).abs().max() / ref.abs().max()).item() < TOL
 
 
+def test_fused_dropout_relu_epilogue(P):
+    """bias + ReLU + dropout mask in the SpMM epilogue and the matching masked backward, against the
+    same ops composed in torch (F.relu then mask * 1/(1-p)), CSR and dense routes."""
+    n = 2000
+    src, dst = _powerlaw_graph(n, 30000, seed=9, hub_deg=1500)
+    gr = P.Graph.from_edges(cu(src), cu(dst), n)
+    dense = gr.to_sparse_coo().to_dense()
+    gen = torch.Generator(device=dev()).manual_seed(4)
+    x = torch.randn(n, 20, generator=gen, device=dev())
+    g = torch.randn(n, 12, generator=gen, device=dev())
+    mask = torch.rand(n, 12, generator=gen, device=dev()) >= 0.3
+    torch.manual_seed(42)
+    layer = P.GraphConvolution(20, 12).to(dev())
+    for adj in (gr, dense):
+        for relu in (False, True):
+            xt = x.clone().requires_grad_(True)
+            layer.zero_grad()
+            out = P.gcn_layer(xt, adj, layer.weight, layer.bias, relu=relu, dropout_mask=mask, dropout_p=0.3)
+            out.backward(g)
+            w = layer.weight.detach().double().requires_grad_(True)
+            b = layer.bias.detach().double().requires_grad_(True)
+            x64 = x.double().requires_grad_(True)
+            z = dense.double() @ (x64 @ w) + b
+            ref = (torch.relu(z) if relu else z) * mask.double() / 0.7
+            ref.backward(g.double())
+            for mine, r in ((out, ref), (layer.weight.grad, w.grad), (layer.bias.grad, b.grad), (xt.grad, x64.grad)):
+                assert ((mine.double() - r).abs().max() / r.abs().max()).item() < TOL
+    # module option: active in training mode only
+    drop = P.GraphConvolution(20, 12, dropout=0.5).to(dev())
+    drop.eval()
+    assert torch.equal(drop(x, gr), P.gcn_layer(x, gr, drop.weight, drop.bias))
+    drop.train()
+    frac = (drop(x, gr) == 0).float().mean().item()
+    assert 0.4 < frac < 0.6
+
+
 def test_layer_nobias_csr_golden(P, golden):
     c = golden("layer_cases.npz")
     n = int(c["ragged/n"])
