@@ -427,12 +427,14 @@ def run_ours(args, wl):
         "torch_cuda_reference": torch_cuda,
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "spmm_rows_vec_kernel<8,1> (CSR SpMM, fwd and A^T launches)",
+                     "traffic": traffic, "kernel": "spmm_group_kernel<8,4,6> (CSR SpMM, fwd and A^T launches)",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": spmm_ms, "peak_source": peak_src,
                      "frac_of_8TBs_nominal": achieved / 8000.0,
                      "l2_to_sm_gather_GBps": (xbar_bytes / (spmm_ms * 1e-3) / 1e9) if xbar_bytes else None,
-                     "note": "the gathered feature rows (nnz*F*4 B per launch) are L2 hits but L1 misses; the kernel "
-                             "runs at the L2->SM fabric limit (DESIGN.md section 3), DRAM traffic = algorithmic bytes",
+                     "note": "the gathered feature rows (nnz*F*4 B per launch) are L2 hits but L1 misses: the kernel is "
+                             "bound by the L1/TEX pipe and the L2 gather rate for random 128-byte rows (DESIGN.md "
+                             "section 3; tools/microbench/gather_bw.cu measures 16.5 TB/s for the bare gather), "
+                             "DRAM traffic = algorithmic bytes",
                      "how": "CUDA events around gcnb_spmm alone, L2 flushed before each launch, mean of %d launches" % len(sp_ms)},
         "wall_s_timed_region": wall,
     }

@@ -209,6 +209,14 @@ int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_t ldx, cons
                         void* stream);
 size_t gcnb_layer_workspace_bytes(const gcnb_graph* g, int64_t fin, int64_t fout, int precision);
 
+/* Tuning knobs (process-wide, not thread-safe against concurrent launches; for tests and benchmarks).
+ *   GCNB_TUNE_SPMM_KERNEL: 0 auto (default), 1 warp-per-row shuffle kernel, 2 group-per-row kernel,
+ *                          3 TMA-staged warp-per-row kernel
+ *   GCNB_TUNE_SPMM_GROUP_VARIANT: -1 auto, 0..4 = (gathers in flight, CTAs/SM) of the group kernel */
+#define GCNB_TUNE_SPMM_KERNEL 1
+#define GCNB_TUNE_SPMM_GROUP_VARIANT 2
+int gcnb_set_tuning(int key, int value);
+
 /* L2 flush helper for benchmarks: writes `bytes` of d_buf. */
 int gcnb_l2_flush(void* d_buf, size_t bytes, void* stream);
 

@@ -26,6 +26,7 @@ BUILD_SYMMETRIZE, BUILD_SELF_LOOPS, BUILD_ROW_NORMALIZE = 1, 2, 4
 SPMM_TRANSPOSE, SPMM_RELU, SPMM_ACCUMULATE = 1, 2, 4
 GEMM_FP32, GEMM_TF32X3, GEMM_AUTO = 0, 1, 2
 LAYER_RELU, LAYER_NEED_DX, LAYER_NEED_DW, LAYER_NEED_DB = 1, 2, 4, 8
+TUNE_SPMM_KERNEL, TUNE_SPMM_GROUP_VARIANT = 1, 2
 
 
 class GraphInfo(ctypes.Structure):
@@ -70,6 +71,7 @@ SIGNATURES = {
                                     c_vp, ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
     "gcnb_layer_workspace_bytes": (c_sz, [c_vp, c_i64, c_i64, c_int]),
     "gcnb_l2_flush": (c_int, [c_vp, c_sz, c_vp]),
+    "gcnb_set_tuning": (c_int, [c_int, c_int]),
 }
 
 _lock = threading.Lock()

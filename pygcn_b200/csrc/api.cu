@@ -130,6 +130,8 @@ extern "C" int gcnb_check_device(void) {
   return GCNB_OK;
 }
 
+extern "C" int gcnb_set_tuning(int key, int value) { return spmm_set_tuning(key, value); }
+
 extern "C" int gcnb_spmm(const gcnb_graph* g, int flags, const float* d_b, int64_t ldb, int64_t f,
                          const float* d_bias, float* d_out, int64_t ldo, void* d_ws, size_t ws_bytes,
                          void* stream) {

@@ -46,6 +46,9 @@ struct CsrView {
   const int32_t* rowptr = nullptr;
   const int32_t* col = nullptr;
   const float* val = nullptr;
+  // the same entries as (col, val bits) pairs, 16-byte aligned: what the group-per-row SpMM stages
+  // (one 16-byte cp.async moves two entries; with separate arrays it takes four 4-byte copies)
+  const uint2* pair = nullptr;
   // schedule: rows whose degree exceeds the long-row threshold are split into chunks of
   // kLongChunk stored entries; each chunk is one warp work item writing a partial row.
   int64_t n_long_rows = 0;
@@ -73,6 +76,7 @@ constexpr int kLongChunk = 1024;
 int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const Epilogue& ep, float* out,
                 int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t spmm_workspace_bytes(const CsrView& a, int64_t f);
+int spmm_set_tuning(int key, int value);
 
 int gemm_fp32_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs, int64_t a_cs,
                      const float* b, int64_t b_rs, int64_t b_cs, float* c, int64_t ldc, void* ws,
@@ -117,6 +121,8 @@ struct gcnb_graph {
   int32_t* t_rowptr = nullptr;  // may alias rowptr when the pattern is symmetric
   int32_t* t_col = nullptr;     // may alias col
   float* t_val = nullptr;
+  uint2* pair = nullptr;    // interleaved (col, val) of the CSR, [nnz]
+  uint2* t_pair = nullptr;  // interleaved (t_col, t_val) of the CSR of the transpose, [nnz]
   bool pattern_symmetric = false;
   bool has_transpose = true;  // false for row/column blocks cut by gcnb_graph_block
   // dense route (adjacency given as a dense matrix whose density makes the CSR gather the slower

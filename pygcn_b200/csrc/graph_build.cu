@@ -420,6 +420,23 @@ int bits_for(uint64_t max_value) {
   return b;
 }
 
+// pair[i] = (col[i], bits of val[i])
+__global__ void interleave_kernel(int64_t nnz, const int32_t* __restrict__ col, const float* __restrict__ val,
+                                  uint2* __restrict__ pair) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nnz) pair[i] = make_uint2((uint32_t)col[i], __float_as_uint(val[i]));
+}
+
+int build_pairs(gcnb_graph* g, const int32_t* col, const float* val, uint2** out, cudaStream_t st) {
+  GCNB_TRY(graph_alloc(g, out, g->nnz + 2));  // + slack: stages are copied two entries at a time
+  GCNB_CUDA(cudaMemsetAsync(*out, 0, (size_t)(g->nnz + 2) * sizeof(uint2), st));
+  if (g->nnz > 0) {
+    interleave_kernel<<<blocks_for(g->nnz), kT, 0, st>>>(g->nnz, col, val, *out);
+    GCNB_LAUNCH_CHECK();
+  }
+  return GCNB_OK;
+}
+
 // ---------------------------------------------------------------- schedule + transpose
 
 int build_schedule(gcnb_graph* g, const int32_t* rowptr, int64_t n, CsrView* view,
@@ -482,6 +499,8 @@ int finalize(gcnb_graph* g, const int32_t* rows, cudaStream_t st, bool with_tran
     g->pattern_symmetric = false;
     g->fwd.n_rows = g->n_rows; g->fwd.n_cols = g->n_cols; g->fwd.nnz = nnz;
     g->fwd.rowptr = g->rowptr; g->fwd.col = g->col; g->fwd.val = g->val;
+    GCNB_TRY(build_pairs(g, g->col, g->val, &g->pair, st));
+    g->fwd.pair = g->pair;
     g->bwd = CsrView();
     GCNB_TRY(build_schedule(g, g->rowptr, g->n_rows, &g->fwd, &g->long_rows, &g->long_chunk_ptr, st));
     GCNB_CUDA(cudaStreamSynchronize(st));
@@ -542,6 +561,10 @@ int finalize(gcnb_graph* g, const int32_t* rows, cudaStream_t st, bool with_tran
   g->fwd.rowptr = g->rowptr; g->fwd.col = g->col; g->fwd.val = g->val;
   g->bwd.n_rows = g->n_cols; g->bwd.n_cols = g->n_rows; g->bwd.nnz = nnz;
   g->bwd.rowptr = g->t_rowptr; g->bwd.col = g->t_col; g->bwd.val = g->t_val;
+  GCNB_TRY(build_pairs(g, g->col, g->val, &g->pair, st));
+  GCNB_TRY(build_pairs(g, g->t_col, g->t_val, &g->t_pair, st));
+  g->fwd.pair = g->pair;
+  g->bwd.pair = g->t_pair;
   GCNB_TRY(build_schedule(g, g->rowptr, g->n_rows, &g->fwd, &g->long_rows, &g->long_chunk_ptr, st));
   GCNB_TRY(build_schedule(g, g->t_rowptr, g->n_cols, &g->bwd, &g->t_long_rows, &g->t_long_chunk_ptr, st));
   GCNB_CUDA(cudaStreamSynchronize(st));
@@ -826,6 +849,8 @@ extern "C" void gcnb_graph_free(gcnb_graph* g) {
   cudaFree(g->col);
   cudaFree(g->val);
   cudaFree(g->t_val);
+  cudaFree(g->pair);
+  cudaFree(g->t_pair);
   cudaFree(g->long_rows);
   cudaFree(g->long_chunk_ptr);
   cudaFree(g->t_long_rows);

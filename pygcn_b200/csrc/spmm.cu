@@ -182,6 +182,159 @@ spmm_rows_vec_kernel(int n_rows, const int32_t* __restrict__ rowptr, const int32
 }
 
 // ---------------------------------------------------------------------------------------------
+// Group-per-row kernel (widths up to 64 floats): the G = 32/LPR lane groups of a warp each walk
+// their OWN row, so one LDG.128 instruction still moves G feature rows but there is no cross-slot
+// reduction, G rows' start-up latencies overlap, and short rows do not idle most of the warp.
+//
+// What bounds it (ncu, profiles/): the L1/TEX pipe -- every gathered 128-byte line is a wavefront
+// there, and so is every shared-memory access and every global load of the index/value stream.  So
+// the (col, val) pairs are staged with as few L1 operations as possible: the graph keeps them
+// interleaved (CsrView::pair), a stage of 32 pairs per group is copied global->shared with 16-byte
+// cp.async.cg (two pairs per copy, no registers held, L1 bypassed), and a batch of U entries is read
+// back with U/2 broadcast LDS.128.  Each gather is then one IMAD.WIDE.U32 (col * row bytes + lane
+// base) + one LDG.128 + 4 FFMA; the shuffle kernel above spends ~15 instructions per gather on 64-bit
+// index arithmetic and shuffles.  Per-row accumulation order is the stored order, run-to-run
+// deterministic.
+constexpr int kStageEntries = 32;
+
+// (OR of one word of every gathered row) & never, where `never` is a kernel argument that is always
+// 0 at run time (the compiler cannot know).  OR-ing it into the accumulators makes every FFMA of a
+// batch depend on ALL the batch's gathers, i.e. all U gathers are in flight together.  Left alone,
+// ptxas interleaves gathers and FFMAs assuming a short load latency and keeps 2-3 rows in flight per
+// lane; the L2 gather rate needs several hundred rows in flight per SM (tools/microbench/gather_bw.cu).
+template <int U>
+__device__ __forceinline__ uint32_t all_landed(const float4 (&x)[U], uint32_t never) {
+  uint32_t g = 0u;
+#pragma unroll
+  for (int u = 0; u < U; ++u) g |= __float_as_uint(x[u].w);
+  return g & never;
+}
+
+template <int LPR, int U, int MINB>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
+spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* __restrict__ pair,
+                  const float* __restrict__ b, uint32_t ldb_bytes, int f, Epilogue ep, float* __restrict__ out,
+                  int64_t ldo, int vec_out, int skip_long, uint32_t never) {
+  constexpr int G = 32 / LPR;
+  constexpr int E = (LPR >= 4) ? kStageEntries : kStageEntries / 2;  // static shared memory stays < 48 KB
+  constexpr int NC = E / (2 * LPR);  // 16-byte copies (two pairs) per lane and stage
+  static_assert(E % U == 0 && U % 2 == 0 && NC >= 1, "batches of U entries must divide the stage");
+  // +2 pairs of padding per buffer: buffers stay 16-byte aligned and consecutive groups start
+  // 2*(E+2)*2 = 136 words apart, i.e. 8 banks, so the G broadcast LDS.128 of one instruction hit
+  // disjoint banks
+  constexpr uint32_t kBufBytes = 8u * (E + 2);
+  __shared__ __align__(16) uint2 stage[kWarpsPerCta][G][2][E + 2];
+  // Register diet (the budget decides how many warps x gathers fly per SM): inside the loops only
+  // e (next entry to stage), left (entries not yet consumed, counted from the 2-aligned window start),
+  // the two buffer addresses, the lane's base pointer and the accumulators live; row / width data are
+  // rebuilt at the end.
+  const int sub = (threadIdx.x & 31) % LPR;
+  int e, left, lead;
+  {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * G + lane / LPR;
+    int start = 0, end = 0;
+    if (row < n_rows) {
+      start = __ldg(rowptr + row);
+      end = __ldg(rowptr + row + 1);
+      if (skip_long && end - start >= kLongRowThreshold) end = start;
+    }
+    lead = start & 1;  // the stage window starts at an even entry (16-byte aligned pair address)
+    e = start - lead + 2 * sub;
+    left = end - start + lead;
+    if (end == start) left = 0;
+  }
+  uint64_t bl;  // lane's base: column chunk `sub` of row 0 (lanes past the width read a clamped, valid chunk)
+  {
+    bl = reinterpret_cast<uint64_t>(b) + 16u * (uint32_t)min(sub, ((f + 3) >> 2) - 1);
+    asm volatile("" : "+l"(bl));  // keep it in a register pair (ptxas would rebuild it per gather)
+  }
+  uint32_t cur = smem_u32(&stage[threadIdx.x >> 5][((threadIdx.x & 31) / LPR)][0][0]);
+  uint32_t nxt = cur + kBufBytes;
+
+  // stage <- the next E pairs of this group's row, global -> shared; pairs past the row's end are
+  // zero-filled (col 0, val 0).  `ahead` = entries not yet staged, counted from this lane's first one.
+  auto fetch = [&](uint32_t dst_buf, int ahead) {
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int a = ahead - 2 * LPR * k;
+      const uint32_t bytes = a >= 2 ? 16u : (a == 1 ? 8u : 0u);
+      cp_async16_zfill(dst_buf + 16u * (uint32_t)(sub + LPR * k), pair + e + 2 * LPR * k, bytes);
+    }
+    cp_async_commit();
+    e += E;
+  };
+  auto pairs_at = [&](int j) {  // pairs j, j + 1 of the current stage: (col, val, col, val)
+    uint4 q;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(cur + 8u * (uint32_t)j));
+    return q;
+  };
+  auto gather = [&](uint32_t c) {  // one IMAD.WIDE.U32: c * row bytes + lane base
+    float4 x;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                 : "l"(bl + (uint64_t)c * ldb_bytes));
+    return x;
+  };
+  fetch(cur, left - 2 * sub);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool first = true;
+  while (!__all_sync(kFull, left <= 0)) {
+    fetch(nxt, left - E - 2 * sub);  // next stage flies while this one is consumed
+    cp_async_wait<1>();              // this lane's copies for the current stage have landed ...
+    __syncwarp();                    // ... and so have the other lanes'
+    if (first) {  // an odd row start: the window's first pair belongs to the previous row -> value 0
+      if (lead && sub == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(cur + 4u), "r"(0u) : "memory");
+      __syncwarp();
+      first = false;
+    }
+    const int cnt = min(max(left, 0), E);
+    const int cmax = __reduce_max_sync(kFull, cnt);
+    // (unroll 1: with the batches unrolled ptxas software-pipelines them with 2-3 gathers in flight)
+#pragma unroll 1
+    for (int j = 0; j < cmax; j += U) {
+      // groups whose row has ended sit the batch out (a divergent branch, reconverged below); inside a
+      // live batch the entries past the row's end are the zero-filled pairs: at most U-1 harmless
+      // gathers of row 0 per row instead of per-gather predicates
+      if (j < cnt) {
+        uint4 q[U / 2];
+        float4 x[U];
+#pragma unroll
+        for (int h = 0; h < U / 2; ++h) q[h] = pairs_at(j + 2 * h);  // j + u < E because U divides E
+#pragma unroll
+        for (int h = 0; h < U / 2; ++h) {
+          x[2 * h] = gather(q[h].x);
+          x[2 * h + 1] = gather(q[h].z);
+        }
+        const uint32_t zero = all_landed(x, never);
+        acc.x = __uint_as_float(__float_as_uint(acc.x) | zero);
+        acc.y = __uint_as_float(__float_as_uint(acc.y) | zero);
+        acc.z = __uint_as_float(__float_as_uint(acc.z) | zero);
+        acc.w = __uint_as_float(__float_as_uint(acc.w) | zero);
+#pragma unroll
+        for (int h = 0; h < U / 2; ++h) {
+          fma4(acc, __uint_as_float(q[h].y), x[2 * h]);
+          fma4(acc, __uint_as_float(q[h].w), x[2 * h + 1]);
+        }
+      }
+    }
+    __syncwarp();  // all lanes are done with `cur` before the next iteration's copies overwrite it
+    left -= E;
+    const uint32_t t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  cp_async_wait<0>();
+  {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * G + lane / LPR;
+    if (row >= n_rows || sub >= ((f + 3) >> 2)) return;
+    if (skip_long && __ldg(rowptr + row + 1) - __ldg(rowptr + row) >= kLongRowThreshold) return;
+    store_row_chunk(out + (int64_t)row * ldo, row, sub, f, vec_out, acc, ep);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // TMA-staged variant: the column-index and value streams of a row are pulled into shared memory
 // with cp.async.bulk (1-D TMA, mbarrier complete_tx) one chunk ahead of their use, instead of
 // being loaded into registers and broadcast with shuffles.  Each warp owns a two-slot ring
@@ -427,14 +580,43 @@ spmm_rows_scalar_kernel(int n_rows, const int32_t* __restrict__ rowptr,
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// GCNB_SPMM_STAGING=tma | regs selects how the col/val streams reach the SM (default below)
-bool spmm_use_tma() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("GCNB_SPMM_STAGING");
-    v = (e && (e[0] == 't' || e[0] == 'T')) ? 1 : 0;
+// Which kernel serves the short-row bins.  Default (auto): the group-per-row kernel when the shape
+// suits it, the warp-per-row shuffle kernel otherwise.  Environment GCNB_SPMM_KERNEL = rows | group |
+// tma and GCNB_SPMM_GROUP_VARIANT = 0..4 set the initial value; gcnb_set_tuning() changes it at run
+// time (tests force each kernel on small graphs).
+int g_spmm_kernel = -1;   // 0 auto, 1 rows, 2 group (forced), 3 tma
+int g_group_variant = -2;  // -1 auto
+
+void tuning_init() {
+  if (g_spmm_kernel < 0) {
+    const char* e = getenv("GCNB_SPMM_KERNEL");
+    g_spmm_kernel = !e ? 0 : (e[0] == 'r' ? 1 : (e[0] == 'g' ? 2 : (e[0] == 't' ? 3 : 0)));
+    const char* s = getenv("GCNB_SPMM_STAGING");  // older spelling of the tma switch
+    if (s && (s[0] == 't' || s[0] == 'T')) g_spmm_kernel = 3;
   }
-  return v == 1;
+  if (g_group_variant == -2) {
+    const char* e = getenv("GCNB_SPMM_GROUP_VARIANT");
+    g_group_variant = e ? atoi(e) : -1;
+  }
+}
+bool spmm_use_tma() { tuning_init(); return g_spmm_kernel == 3; }
+int spmm_group_variant() { tuning_init(); return g_group_variant; }
+
+// Long-row bin: chunk partials, then the ordered fix-up (both no-ops when the bin is empty).
+template <int LPR, int CH>
+int launch_long(const CsrView& a, const float* b, int64_t ldb, int f, const Epilogue& ep, float* out,
+                int64_t ldo, float* partial, int ldp, cudaStream_t st) {
+  if (a.n_long_rows == 0) return GCNB_OK;
+  const int g1 = (int)ceil_div(a.n_long_chunks, kWarpsPerCta);
+  spmm_long_partial_kernel<LPR, CH><<<g1, kWarpsPerCta * 32, 0, st>>>(
+      (int)a.n_long_rows, (int)a.n_long_chunks, a.long_rows, a.long_chunk_ptr, a.rowptr, a.col, a.val, b, ldb, f,
+      partial, ldp);
+  GCNB_LAUNCH_CHECK();
+  const int g2 = (int)ceil_div(a.n_long_rows, kWarpsPerCta);
+  spmm_long_fixup_kernel<<<g2, kWarpsPerCta * 32, 0, st>>>((int)a.n_long_rows, a.long_rows, a.long_chunk_ptr, partial,
+                                                          ldp, f, ep, out, ldo);
+  GCNB_LAUNCH_CHECK();
+  return GCNB_OK;
 }
 
 template <int LPR, int CH>
@@ -442,6 +624,36 @@ int launch_vec(const CsrView& a, const float* b, int64_t ldb, int f, const Epilo
                int64_t ldo, bool vec_out, float* partial, int ldp, cudaStream_t st) {
   const bool has_long = a.n_long_rows > 0;
   const int grid = (int)ceil_div(a.n_rows, kWarpsPerCta);
+  if constexpr (LPR >= 2 && LPR <= 16 && CH == 1) {
+    constexpr int G = 32 / LPR;
+    // one row per lane group needs enough rows to fill the machine with warps, and rows short enough
+    // that a group's serial walk is not the critical path (few long rows: warp-per-row splits them)
+    const bool shape_ok = a.n_rows >= (int64_t)kNumSMs * 16 * G && a.nnz <= a.n_rows * 384;
+    tuning_init();
+    const bool want_group = g_spmm_kernel == 2 || (g_spmm_kernel == 0 && (shape_ok || g_group_variant >= 0));
+    if (grid > 0 && a.pair != nullptr && want_group && ldb * 4 < (1ll << 32)) {
+      const int ggrid = (int)ceil_div(a.n_rows, (int64_t)kWarpsPerCta * G);
+#define GCNB_GROUP_LAUNCH(U_, MINB_)                                                                       \
+  spmm_group_kernel<LPR, U_, MINB_><<<ggrid, kWarpsPerCta * 32, 0, st>>>(                               \
+      (int)a.n_rows, a.rowptr, a.pair, b, (uint32_t)(ldb * 4), f, ep, out, ldo, vec_out ? 1 : 0, \
+      has_long ? 1 : 0, 0u)
+      // (gathers in flight per lane, CTAs per SM the register budget must allow).  Measured on B200
+      // (gpurun_out/probe_sweep8.log): 128/256-byte rows like many warps with 4 gathers each, narrower
+      // rows fewer warps with 8.  GCNB_SPMM_GROUP_VARIANT overrides (tuning knob).
+      int variant = spmm_group_variant();
+      if (variant < 0) variant = (LPR >= 8) ? 2 : 0;
+      switch (variant) {
+        case 1: GCNB_GROUP_LAUNCH(8, 3); break;
+        case 2: GCNB_GROUP_LAUNCH(4, 6); break;
+        case 3: GCNB_GROUP_LAUNCH(16, 2); break;
+        case 4: GCNB_GROUP_LAUNCH(4, 5); break;
+        default: GCNB_GROUP_LAUNCH(8, 4); break;
+      }
+#undef GCNB_GROUP_LAUNCH
+      GCNB_LAUNCH_CHECK();
+      return launch_long<LPR, CH>(a, b, ldb, f, ep, out, ldo, partial, ldp, st);
+    }
+  }
   if (grid > 0 && spmm_use_tma()) {
     // persistent: 6 CTAs per SM walk the rows with a per-warp TMA ring for the index/value streams
     int pgrid = 6 * kNumSMs;
@@ -454,23 +666,26 @@ int launch_vec(const CsrView& a, const float* b, int64_t ldb, int f, const Epilo
         (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, f, ep, out, ldo, vec_out ? 1 : 0, has_long ? 1 : 0);
     GCNB_LAUNCH_CHECK();
   }
-  if (has_long) {
-    const int g1 = (int)ceil_div(a.n_long_chunks, kWarpsPerCta);
-    spmm_long_partial_kernel<LPR, CH><<<g1, kWarpsPerCta * 32, 0, st>>>(
-        (int)a.n_long_rows, (int)a.n_long_chunks, a.long_rows, a.long_chunk_ptr, a.rowptr, a.col,
-        a.val, b, ldb, f, partial, ldp);
-    GCNB_LAUNCH_CHECK();
-    const int g2 = (int)ceil_div(a.n_long_rows, kWarpsPerCta);
-    spmm_long_fixup_kernel<<<g2, kWarpsPerCta * 32, 0, st>>>(
-        (int)a.n_long_rows, a.long_rows, a.long_chunk_ptr, partial, ldp, f, ep, out, ldo);
-    GCNB_LAUNCH_CHECK();
-  }
-  return GCNB_OK;
+  return launch_long<LPR, CH>(a, b, ldb, f, ep, out, ldo, partial, ldp, st);
 }
 
 inline int partial_ld(int64_t f) { return (int)(ceil_div(f, 4) * 4); }
 
 }  // namespace
+
+int spmm_set_tuning(int key, int value) {
+  tuning_init();
+  if (key == GCNB_TUNE_SPMM_KERNEL) {
+    GCNB_REQUIRE(value >= 0 && value <= 3, "set_tuning: spmm kernel must be 0..3");
+    g_spmm_kernel = value;
+  } else if (key == GCNB_TUNE_SPMM_GROUP_VARIANT) {
+    GCNB_REQUIRE(value >= -1 && value <= 4, "set_tuning: group variant must be -1..4");
+    g_group_variant = value;
+  } else {
+    GCNB_REQUIRE(false, "set_tuning: unknown key %d", key);
+  }
+  return GCNB_OK;
+}
 
 size_t spmm_workspace_bytes(const CsrView& a, int64_t f) {
   if (a.n_long_chunks == 0) return 0;

@@ -324,8 +324,27 @@ def _powerlaw_graph(n, n_edges, seed, hub_deg=0):
     return src.astype(np.int32), dst.astype(np.int32)
 
 
+_KERNELS = {"auto": 0, "rows": 1, "group": 2, "tma": 3}
+
+
+@pytest.fixture
+def spmm_kernel(P, request):
+    """Forces one of the SpMM kernels for the short-row bins (gcnb_set_tuning), restores auto after."""
+    from pygcn_b200 import _lib
+
+    lib = _lib.load()
+    name, variant = request.param if isinstance(request.param, tuple) else (request.param, -1)
+    _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_KERNEL, _KERNELS[name]), "set_tuning")
+    _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_GROUP_VARIANT, variant), "set_tuning")
+    yield name
+    lib.gcnb_set_tuning(_lib.TUNE_SPMM_KERNEL, 0)
+    lib.gcnb_set_tuning(_lib.TUNE_SPMM_GROUP_VARIANT, -1)
+
+
+@pytest.mark.parametrize("spmm_kernel", ["auto", "rows", "group", "tma", ("group", 0), ("group", 1), ("group", 3), ("group", 4)],
+                         indirect=True)
 @pytest.mark.parametrize("fin,fout", [(64, 32), (5, 1), (9, 3), (16, 7), (33, 47), (100, 256), (20, 600)])
-def test_layer_vs_oracle_widths_and_long_rows(P, fin, fout):
+def test_layer_vs_oracle_widths_and_long_rows(P, fin, fout, spmm_kernel):
     n = 6000
     src, dst = _powerlaw_graph(n, 60000, seed=fin * 1000 + fout, hub_deg=3000)
     idx, val = O.build_normalized_adjacency(src, dst, n)
