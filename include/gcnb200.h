@@ -130,6 +130,13 @@ int gcnb_graph_block_gathered(const gcnb_graph* g, int transpose, int64_t r0, in
                               const int64_t* h_bounds, int64_t pad_rows, int exclude_part, void* stream,
                               gcnb_graph** out);
 
+/* The same remap restricted to the source ranks whose bit is set in include_mask (n_parts <= 64): the
+ * column block "sources S" of the row block, for the pipelined peer-memory exchange (one SpMM per
+ * group of source ranks, started when their slots have landed).  sync. */
+int gcnb_graph_block_sources(const gcnb_graph* g, int transpose, int64_t r0, int64_t r1, int n_parts,
+                             const int64_t* h_bounds, int64_t pad_rows, unsigned long long include_mask, void* stream,
+                             gcnb_graph** out);
+
 /* Copy the device CSR (transpose = 0) or the CSR of A^T (transpose = 1) into caller
  * buffers: d_rowptr int32 [rows+1], d_col int32 [nnz], d_val fp32 [nnz]. */
 int gcnb_graph_export_csr(const gcnb_graph* g, int transpose, int32_t* d_rowptr, int32_t* d_col,
@@ -208,6 +215,36 @@ int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_t ldx, cons
                         float* d_db, float* d_dx, int64_t lddx, void* d_ws, size_t ws_bytes,
                         void* stream);
 size_t gcnb_layer_workspace_bytes(const gcnb_graph* g, int64_t fin, int64_t fout, int precision);
+
+/* ---- peer-memory exchange for the row-partitioned multi-GPU layer (one process per GPU) ------------
+ * The reference has no multi-GPU path; these entry points replace the NCCL all-gather
+ * of the X.W / G panels with our own push kernel over NVLink peer memory + per-source-rank flags, so
+ * the SpMM over the column block of source q can start when slot q has landed.
+ *   gcnb_symm_alloc : cudaMalloc + zero + CUDA IPC handle (GCNB_IPC_HANDLE_BYTES bytes, host memory)
+ *   gcnb_symm_open  : map a peer's allocation into this process (peer access enabled); close / free
+ *   gcnb_peer_epoch_bump : d_epoch[0] += 1, clears the n_peers arrival counters (1 tiny kernel)
+ *   gcnb_peer_push  : copies [d_src, d_src+bytes) into peer_dst[k] for k = 0..n_peers-1 in that order with
+ *                     P2P stores; per peer it first waits until *local_ack[k] >= epoch-1 (the peer has
+ *                     finished reading the previous exchange), and afterwards stores *peer_flag[k] = epoch
+ *                     with release semantics at system scope.  Pointer arrays are HOST arrays.
+ *   gcnb_peer_wait  : one-thread kernel spinning (bounded, traps on timeout) until *d_flag >= *d_epoch
+ *   gcnb_peer_ack   : *peer_ack = *d_epoch (release, system scope), after everything before it on the stream */
+#define GCNB_MAX_PEERS 15
+#define GCNB_IPC_HANDLE_BYTES 64
+int gcnb_symm_alloc(size_t bytes, void** d_ptr, void* handle_out);
+int gcnb_symm_open(const void* handle, void** d_ptr);
+int gcnb_symm_close(void* d_ptr);
+int gcnb_symm_free(void* d_ptr);
+int gcnb_peer_epoch_bump(uint32_t* d_epoch, uint32_t* d_counters, int n_peers, void* stream);
+int gcnb_peer_push(const void* d_src, size_t bytes, int n_peers, void* const* peer_dst, uint32_t* const* peer_flag,
+                   const uint32_t* const* local_ack, const uint32_t* d_epoch, uint32_t* d_counters, int n_ctas,
+                   void* stream);
+int gcnb_peer_wait(const uint32_t* d_flag, const uint32_t* d_epoch, void* stream);
+/* spins until *d_word >= *d_epoch - lag (lag = 1: the peer's ack of the previous exchange) */
+int gcnb_peer_wait_lag(const uint32_t* d_word, const uint32_t* d_epoch, uint32_t lag, void* stream);
+/* copy-engine transfer to / from mapped peer memory: cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) */
+int gcnb_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+int gcnb_peer_ack(uint32_t* peer_ack, const uint32_t* d_epoch, void* stream);
 
 /* Tuning knobs (process-wide, not thread-safe against concurrent launches; for tests and benchmarks).
  *   GCNB_TUNE_SPMM_KERNEL: 0 auto (default), 1 warp-per-row shuffle kernel, 2 group-per-row kernel,

@@ -72,6 +72,18 @@ SIGNATURES = {
     "gcnb_layer_workspace_bytes": (c_sz, [c_vp, c_i64, c_i64, c_int]),
     "gcnb_l2_flush": (c_int, [c_vp, c_sz, c_vp]),
     "gcnb_set_tuning": (c_int, [c_int, c_int]),
+    "gcnb_symm_alloc": (c_int, [c_sz, c_vp, c_vp]),
+    "gcnb_symm_open": (c_int, [c_vp, c_vp]),
+    "gcnb_symm_close": (c_int, [c_vp]),
+    "gcnb_symm_free": (c_int, [c_vp]),
+    "gcnb_peer_epoch_bump": (c_int, [c_vp, c_vp, c_int, c_vp]),
+    "gcnb_peer_push": (c_int, [c_vp, c_sz, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "gcnb_peer_wait": (c_int, [c_vp, c_vp, c_vp]),
+    "gcnb_peer_wait_lag": (c_int, [c_vp, c_vp, ctypes.c_uint32, c_vp]),
+    "gcnb_peer_copy": (c_int, [c_vp, c_vp, c_sz, c_vp]),
+    "gcnb_graph_block_sources": (c_int, [c_vp, c_int, c_i64, c_i64, c_int, ctypes.POINTER(c_i64), c_i64, ctypes.c_uint64,
+                                         c_vp, ctypes.POINTER(c_vp)]),
+    "gcnb_peer_ack": (c_int, [c_vp, c_vp, c_vp]),
 }
 
 _lock = threading.Lock()

@@ -221,18 +221,18 @@ __device__ __forceinline__ int part_of(const int64_t* __restrict__ bounds, int n
 }
 
 __global__ void gathered_count_kernel(int64_t r0, int64_t n_rows, int n_parts,
-                                      const int64_t* __restrict__ bounds, int exclude,
+                                      const int64_t* __restrict__ bounds, unsigned long long include,
                                       const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                       int32_t* __restrict__ counts) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   int cnt = 0;
-  for (int e = rowptr[r0 + r]; e < rowptr[r0 + r + 1]; ++e) cnt += (part_of(bounds, n_parts, col[e]) != exclude);
+  for (int e = rowptr[r0 + r]; e < rowptr[r0 + r + 1]; ++e) cnt += (int)((include >> part_of(bounds, n_parts, col[e])) & 1ull);
   counts[r] = cnt;
 }
 
 __global__ void gathered_fill_kernel(int64_t r0, int64_t n_rows, int n_parts,
-                                     const int64_t* __restrict__ bounds, int exclude, int64_t pad_rows,
+                                     const int64_t* __restrict__ bounds, unsigned long long include, int64_t pad_rows,
                                      const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                      const float* __restrict__ val, const int32_t* __restrict__ new_rowptr,
                                      int32_t* __restrict__ new_col, float* __restrict__ new_val,
@@ -243,7 +243,7 @@ __global__ void gathered_fill_kernel(int64_t r0, int64_t n_rows, int n_parts,
   for (int e = rowptr[r0 + r]; e < rowptr[r0 + r + 1]; ++e) {
     const int c = col[e];
     const int q = part_of(bounds, n_parts, c);
-    if (q != exclude) {
+    if ((include >> q) & 1ull) {
       new_col[o] = (int32_t)((int64_t)q * pad_rows + (c - bounds[q]));
       new_val[o] = val[e];
       new_rows[o] = (int32_t)r;
@@ -972,9 +972,18 @@ extern "C" int gcnb_graph_block(const gcnb_graph* g, int transpose, int64_t r0, 
 extern "C" int gcnb_graph_block_gathered(const gcnb_graph* g, int transpose, int64_t r0, int64_t r1, int n_parts,
                                          const int64_t* h_bounds, int64_t pad_rows, int exclude_part, void* stream,
                                          gcnb_graph** out) {
+  GCNB_REQUIRE(n_parts >= 1 && n_parts <= 64, "graph_block_gathered: 1..64 parts");
+  unsigned long long include = (n_parts == 64) ? ~0ull : ((1ull << n_parts) - 1ull);
+  if (exclude_part >= 0 && exclude_part < n_parts) include &= ~(1ull << exclude_part);
+  return gcnb_graph_block_sources(g, transpose, r0, r1, n_parts, h_bounds, pad_rows, include, stream, out);
+}
+
+extern "C" int gcnb_graph_block_sources(const gcnb_graph* g, int transpose, int64_t r0, int64_t r1, int n_parts,
+                                        const int64_t* h_bounds, int64_t pad_rows, unsigned long long include_mask,
+                                        void* stream, gcnb_graph** out) {
   GCNB_REQUIRE(out != nullptr, "graph_block_gathered: out is null");
   *out = nullptr;
-  GCNB_REQUIRE(g != nullptr && h_bounds != nullptr && n_parts >= 1, "graph_block_gathered: bad argument");
+  GCNB_REQUIRE(g != nullptr && h_bounds != nullptr && n_parts >= 1 && n_parts <= 64, "graph_block_gathered: bad argument");
   GCNB_REQUIRE(!transpose || g->has_transpose, "graph_block_gathered: handle has no transpose");
   const CsrView& v = transpose ? g->bwd : g->fwd;
   GCNB_REQUIRE(0 <= r0 && r0 <= r1 && r1 <= v.n_rows, "graph_block_gathered: bad row range");
@@ -996,7 +1005,7 @@ extern "C" int gcnb_graph_block_gathered(const gcnb_graph* g, int transpose, int
     GCNB_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)(nr + 1) * 4, st));
     GCNB_CUDA(cudaMemsetAsync(total.p, 0, 8, st));
     if (nr > 0) {
-      gathered_count_kernel<<<blocks_for(nr), kT, 0, st>>>(r0, nr, n_parts, bounds.as<int64_t>(), exclude_part,
+      gathered_count_kernel<<<blocks_for(nr), kT, 0, st>>>(r0, nr, n_parts, bounds.as<int64_t>(), include_mask,
                                                            v.rowptr, v.col, counts.as<int32_t>());
       sum_i32_kernel<<<blocks_for(nr), kT, 0, st>>>(counts.as<int32_t>(), nr, total.as<unsigned long long>());
       GCNB_LAUNCH_CHECK();
@@ -1018,7 +1027,7 @@ extern "C" int gcnb_graph_block_gathered(const gcnb_graph* g, int transpose, int
     GCNB_TRY(graph_alloc(b, &b->val, nnz));
     GCNB_CUDA(cudaMemcpyAsync(b->rowptr, rowptr.p, (size_t)(nr + 1) * 4, cudaMemcpyDeviceToDevice, st));
     if (nr > 0 && nnz > 0) {
-      gathered_fill_kernel<<<blocks_for(nr), kT, 0, st>>>(r0, nr, n_parts, bounds.as<int64_t>(), exclude_part, pad_rows,
+      gathered_fill_kernel<<<blocks_for(nr), kT, 0, st>>>(r0, nr, n_parts, bounds.as<int64_t>(), include_mask, pad_rows,
                                                           v.rowptr, v.col, v.val, b->rowptr, b->col, b->val,
                                                           rows32.as<int32_t>());
       GCNB_LAUNCH_CHECK();

@@ -15,6 +15,12 @@ B200-native scaling of its hot path (pygcn/layers.py:32-38 + autograd):
   * backward uses the same scheme on the row block of A-hat^T with G as the exchanged panel
     (atomic-free, deterministic), then dW/db are summed with one all-reduce.
 
+  * exchange "peer" (default on GPUs with peer access): the all-gather is replaced by our own push
+    kernel over NVLink peer memory (csrc/peer.cu) and the row block is cut into one column block per
+    source rank, consumed in the order p, p+1, ... as the slots land (flag per source), so the
+    transfer of slot q+1 overlaps the SpMM over block q.  `PeerExchange` below; the NCCL path stays as
+    exchange "nccl".
+
 One process per GPU (`torchrun`), `torch.distributed` for the plumbing.  The arithmetic is behind
 an `ops` object: `CudaOps` (libgcnb200.so) in production; the CPU tests of the host logic
 (tests/test_dist_gloo.py, gloo, world size 2) inject a numpy implementation.
@@ -52,6 +58,23 @@ def partition_rows_by_nnz(rowptr, world):
     return bounds
 
 
+def exchange_phases(rank, world):
+    """Consumption order of the source ranks for the pipelined exchange, grouped into phases:
+    [[p], [p+1, p+2], [p+3, p+4], ..., [last]] (mod world).  One SpMM per phase: this rank's own slot
+    first (nothing to wait for), pairs in the middle (a row restricted to ONE of 8 sources is ~12
+    stored entries -- too short to gather efficiently), and a single source at the end so that little
+    work is left once the last slot has landed."""
+    order = [(rank + k) % world for k in range(world)]
+    phases = [[order[0]]]
+    rest = order[1:]
+    while len(rest) > 1:
+        phases.append(rest[:2])
+        rest = rest[2:]
+    if rest:
+        phases.append(rest)
+    return phases
+
+
 class DistGraph:
     """Row block `rank` of A-hat and of A-hat^T, each split into the diagonal block (columns owned
     by this rank, local ids) and the remote block (all other columns, ids remapped to the layout of
@@ -74,6 +97,11 @@ class DistGraph:
         self.fwd_diag, self.fwd_remote = fwd_diag, fwd_remote
         self.bwd_diag, self.bwd_remote = bwd_diag, bwd_remote
         self.nnz_local, self.nnz_global = nnz_local, nnz_global
+        # exchange "peer": one column block per phase (group of source ranks, exchange_phases), columns in
+        # the gathered layout, for A and A^T
+        self.phases = None
+        self.fwd_blocks = None
+        self.bwd_blocks = None
 
     def n_rows(self, q=None):
         q = self.rank if q is None else q
@@ -86,9 +114,10 @@ class DistGraph:
         return max(8, (m + 7) // 8 * 8)
 
     @classmethod
-    def from_graph(cls, graph, rank, world, bounds=None, split=None):
+    def from_graph(cls, graph, rank, world, bounds=None, split=None, per_source=False):
         """Cut the row block of `rank` out of a full device `Graph` (CUDA).  split=None decides from
-        the share of stored entries in the diagonal block (SPLIT_MIN_DIAG_FRACTION)."""
+        the share of stored entries in the diagonal block (SPLIT_MIN_DIAG_FRACTION).
+        per_source=True additionally cuts one column block per source rank (exchange "peer")."""
         from . import _lib
         from .graph import Graph, _stream_ptr
 
@@ -116,6 +145,17 @@ class DistGraph:
                 return Graph(out.value, graph.device, "%s[%d]%s" % ("remote" if exclude >= 0 else "rows", rank,
                                                                     "^T" if transpose else ""))
 
+        def cut_sources(transpose, qs):
+            mask = 0
+            for q in qs:
+                mask |= 1 << q
+            with torch.cuda.device(graph.device):
+                out = ctypes.c_void_p()
+                st = lib.gcnb_graph_block_sources(graph._h, 1 if transpose else 0, r0, r1, world, hb, pad, mask,
+                                                  _stream_ptr(graph.device), ctypes.byref(out))
+                _lib.check(st, "gcnb_graph_block_sources")
+                return Graph(out.value, graph.device, "A[%d,%s]%s" % (rank, qs, "^T" if transpose else ""))
+
         fd = cut_diag(False)
         if world == 1:
             return cls(rank, world, bounds, pad, fd, None, cut_diag(True), None, fd.nnz, graph.nnz, True)
@@ -123,9 +163,15 @@ class DistGraph:
         if split is None:
             split = fd.nnz >= cls.SPLIT_MIN_DIAG_FRACTION * max(full.nnz, 1)
         if split:
-            return cls(rank, world, bounds, pad, fd, cut_gathered(False, rank), cut_diag(True),
-                       cut_gathered(True, rank), full.nnz, graph.nnz, True)
-        return cls(rank, world, bounds, pad, None, full, None, cut_gathered(True, -1), full.nnz, graph.nnz, False)
+            dg = cls(rank, world, bounds, pad, fd, cut_gathered(False, rank), cut_diag(True),
+                     cut_gathered(True, rank), full.nnz, graph.nnz, True)
+        else:
+            dg = cls(rank, world, bounds, pad, None, full, None, cut_gathered(True, -1), full.nnz, graph.nnz, False)
+        if per_source:
+            dg.phases = exchange_phases(rank, world)
+            dg.fwd_blocks = [cut_sources(False, qs) for qs in dg.phases]
+            dg.bwd_blocks = [cut_sources(True, qs) for qs in dg.phases]
+        return dg
 
 
 # ---------------------------------------------------------------------------- arithmetic backends
@@ -190,6 +236,167 @@ class CudaOps:
         return torch.empty(shape, dtype=torch.float32, device=like.device)
 
 
+# ---------------------------------------------------------------------------- peer-memory exchange
+class _DevMem:
+    """A raw device allocation seen as a tensor through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"data": (ptr, False), "shape": tuple(shape), "typestr": typestr, "version": 3,
+                                         "strides": None}
+
+
+class PeerExchange:
+    """One panel exchange buffer: gathered [world * pad_rows, f] fp32 on every rank, written by the
+    peers' push kernels over NVLink peer memory, plus flag / ack words per source rank (csrc/peer.cu).
+
+    Protocol per exchange (all on device, CUDA-graph replayable):
+      start(): epoch += 1 on the compute stream, then on the communication stream the push kernel
+               copies this rank's slot to ranks p-1, p-2, ... and publishes flag[p] = epoch there;
+      wait(q): the compute stream spins until slot q has landed;  done(q): acks it to rank q so q's next
+               push may overwrite it;  finish(): joins the communication stream."""
+
+    CTRL_BYTES = 1024
+    PUSH_CTAS = 32
+    # "ce": the slot is moved by the copy engines (cudaMemcpyAsync to the mapped peer pointer, 635 GB/s
+    # per peer pair measured, no SMs taken from the SpMM) between our wait-for-ack and publish-flag
+    # kernels; "sm": our push kernel stores it over NVLink itself (P2P stores, ~380-460 GB/s with 32-296
+    # CTAs, tools/peer_bw.py).  GCNB_PEER_PUSH overrides.
+    PUSH_MODE = os.environ.get("GCNB_PEER_PUSH", "ce")
+
+    def __init__(self, rank, world, pad_rows, f, device, group=None):
+        from . import _lib
+
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.rank, self.world, self.pad_rows, self.f = rank, world, pad_rows, f
+        self.device = device
+        if world - 1 > 15:
+            raise RuntimeError("peer exchange supports at most 16 ranks")
+        self.slot_bytes = pad_rows * f * 4
+        data = (world * self.slot_bytes + 255) // 256 * 256
+        self.off_flags, self.off_acks = data, data + 256
+        self.off_epoch, self.off_counters = data + 512, data + 768
+        self.bytes = data + self.CTRL_BYTES
+        with torch.cuda.device(device):
+            ptr = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(64)
+            _lib.check(self.lib.gcnb_symm_alloc(self.bytes, ctypes.byref(ptr), handle), "gcnb_symm_alloc")
+            self.ptr = ptr.value
+            handles = [None] * world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            self.peer_ptr = {}
+            for q in range(world):
+                if q == rank:
+                    continue
+                pp = ctypes.c_void_p()
+                _lib.check(self.lib.gcnb_symm_open(ctypes.create_string_buffer(handles[q], 64), ctypes.byref(pp)),
+                           "gcnb_symm_open")
+                self.peer_ptr[q] = pp.value
+        # push order: the rank that consumes our slot first (p-1) is served first
+        order = [(rank - k) % world for k in range(1, world)]
+        n = len(order)
+        self._n_peers = n
+        self._dst = (ctypes.c_void_p * max(n, 1))(*[self.peer_ptr[r] + rank * self.slot_bytes for r in order])
+        self._flag = (ctypes.c_void_p * max(n, 1))(*[self.peer_ptr[r] + self.off_flags + 4 * rank for r in order])
+        self._ack = (ctypes.c_void_p * max(n, 1))(*[self.ptr + self.off_acks + 4 * r for r in order])
+        self.gathered = torch.as_tensor(_DevMem(self.ptr, (world * pad_rows, f)), device=device)
+        self.my_slot = self.gathered[rank * pad_rows:(rank + 1) * pad_rows]
+        self.comm = torch.cuda.Stream(device=device, priority=-1)
+        self._ev = torch.cuda.Event()
+        dist.barrier(group=group)  # every rank has mapped every buffer before anyone pushes
+
+    def _sp(self, stream=None):
+        return ctypes.c_void_p((stream or torch.cuda.current_stream(self.device)).cuda_stream)
+
+    def start(self):
+        lib, ck = self.lib, self._lib.check
+        with torch.cuda.device(self.device):
+            ck(lib.gcnb_peer_epoch_bump(self.ptr + self.off_epoch, self.ptr + self.off_counters, self._n_peers, self._sp()),
+               "gcnb_peer_epoch_bump")
+            self._ev.record(torch.cuda.current_stream(self.device))
+            self.comm.wait_event(self._ev)
+            cs = self._sp(self.comm)
+            if self.PUSH_MODE == "sm":
+                ck(lib.gcnb_peer_push(self.ptr + self.rank * self.slot_bytes, self.slot_bytes, self._n_peers, self._dst,
+                                      self._flag, self._ack, self.ptr + self.off_epoch, self.ptr + self.off_counters,
+                                      self.PUSH_CTAS, cs), "gcnb_peer_push")
+            else:
+                ep = self.ptr + self.off_epoch
+                for k in range(self._n_peers):
+                    ck(lib.gcnb_peer_wait_lag(self._ack[k], ep, 1, cs), "gcnb_peer_wait_lag")  # peer done with the old slot
+                    ck(lib.gcnb_peer_copy(self._dst[k], self.ptr + self.rank * self.slot_bytes, self.slot_bytes, cs),
+                       "gcnb_peer_copy")
+                    ck(lib.gcnb_peer_ack(self._flag[k], ep, cs), "gcnb_peer_ack")               # publish flag = epoch
+
+    def wait(self, q):
+        if q != self.rank:
+            with torch.cuda.device(self.device):
+                self._lib.check(self.lib.gcnb_peer_wait(self.ptr + self.off_flags + 4 * q, self.ptr + self.off_epoch,
+                                                        self._sp()), "gcnb_peer_wait")
+
+    def done(self, q):
+        if q != self.rank:
+            with torch.cuda.device(self.device):
+                self._lib.check(self.lib.gcnb_peer_ack(self.peer_ptr[q] + self.off_acks + 4 * self.rank,
+                                                       self.ptr + self.off_epoch, self._sp()), "gcnb_peer_ack")
+
+    def finish(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.comm)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize(self.device)
+                for p in self.peer_ptr.values():
+                    self.lib.gcnb_symm_close(p)
+                self.lib.gcnb_symm_free(self.ptr)
+            self.ptr = None
+
+
+class CollectiveExchange:
+    """The same interface on top of one all-gather (gloo in the CPU tests of the host logic, or NCCL):
+    start() gathers every slot at once, wait / done are no-ops."""
+
+    def __init__(self, rank, world, pad_rows, f, like, group=None):
+        self.rank, self.world, self.pad_rows, self.f, self.group = rank, world, pad_rows, f, group
+        self.gathered = torch.zeros((world * pad_rows, f), dtype=torch.float32, device=like.device)
+        self.my_slot = self.gathered[rank * pad_rows:(rank + 1) * pad_rows]
+
+    def start(self):
+        dist.all_gather_into_tensor(self.gathered, self.my_slot.clone(), group=self.group)
+
+    def wait(self, q):
+        pass
+
+    def done(self, q):
+        pass
+
+    def finish(self):
+        pass
+
+    def close(self):
+        pass
+
+
+def dist_spmm_pipelined(ops, dgraph, blocks, exch, bias=None, relu=False):
+    """out_p = sum_i blocks[i] @ gathered (+ bias) (relu) over the phases of dgraph.phases (groups of
+    source ranks p, p+1, ...): this rank's slot is already in exch.my_slot; every other slot is consumed
+    as soon as it has landed (exch.wait) and released to its owner right after (exch.done).  The bias /
+    ReLU epilogue rides on the last block."""
+    out = ops.empty((dgraph.n_rows(), exch.f), exch.gathered)
+    exch.start()
+    n = len(dgraph.phases)
+    for i, qs in enumerate(dgraph.phases):
+        last = i == n - 1
+        for q in qs:
+            exch.wait(q)
+        ops.spmm_block(blocks[i], exch.gathered, out, i > 0, bias if last else None, relu and last)
+        for q in qs:
+            exch.done(q)
+    exch.finish()
+    return out
+
+
 # ---------------------------------------------------------------------------- the exchange + layer
 def dist_spmm(ops, dgraph, diag, remote, panel, bias=None, relu=False, group=None):
     """out_p = diag @ panel[:n_p] + remote @ allgather(panel) (+ bias) (relu).
@@ -211,19 +418,27 @@ def dist_spmm(ops, dgraph, diag, remote, panel, bias=None, relu=False, group=Non
     return ops.spmm_block(remote, gathered, out, True, bias, relu)
 
 
-def dist_layer_forward(ops, dgraph, x, w, b, relu=False, group=None):
-    """Row block of  A (X W) + b  (pygcn/layers.py:33-36) for this rank."""
+def dist_layer_forward(ops, dgraph, x, w, b, relu=False, group=None, exch=None):
+    """Row block of  A (X W) + b  (pygcn/layers.py:33-36) for this rank.  With `exch` (an exchange
+    object for [pad_rows, Fout] panels) the per-source-block pipelined scheme is used."""
+    if exch is not None and dgraph.world > 1:
+        ops.gemm(x, w, out=exch.my_slot)             # X_p W straight into this rank's slot
+        return dist_spmm_pipelined(ops, dgraph, dgraph.fwd_blocks, exch, b, relu)
     support = ops.empty((dgraph.pad_rows, w.shape[1]), x)
     ops.gemm(x, w, out=support)
     return dist_spmm(ops, dgraph, dgraph.fwd_diag, dgraph.fwd_remote, support, b, relu, group)
 
 
-def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=True, group=None):
+def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=True, group=None, exch=None):
     """(dX rows of this rank or None, dW, db): dW/db are already summed over ranks."""
     fin, fout = w.shape
-    gm = ops.empty((dgraph.pad_rows, fout), g)
-    db, _ = ops.colsum(g, y, gm)                     # local part of db; G (masked) staged into its slot
-    ds = dist_spmm(ops, dgraph, dgraph.bwd_diag, dgraph.bwd_remote, gm, None, False, group)  # rows p of A^T G
+    if exch is not None and dgraph.world > 1:
+        db, _ = ops.colsum(g, y, exch.my_slot)       # local part of db; G (masked) staged into this rank's slot
+        ds = dist_spmm_pipelined(ops, dgraph, dgraph.bwd_blocks, exch)  # rows p of A^T G
+    else:
+        gm = ops.empty((dgraph.pad_rows, fout), g)
+        db, _ = ops.colsum(g, y, gm)                 # local part of db; G (masked) staged into its slot
+        ds = dist_spmm(ops, dgraph, dgraph.bwd_diag, dgraph.bwd_remote, gm, None, False, group)  # rows p of A^T G
     dw = ops.gemm(x.t(), ds)                         # local part of X^T dS
     if dgraph.world > 1:
         flat = torch.cat([dw.reshape(-1), db.reshape(-1)])
@@ -236,9 +451,9 @@ def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=Tru
 
 class _DistGCNLayerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, dgraph, relu, ops, group):
-        out = dist_layer_forward(ops, dgraph, x, weight, bias, relu, group)
-        ctx.dgraph, ctx.relu, ctx.ops, ctx.group = dgraph, relu, ops, group
+    def forward(ctx, x, weight, bias, dgraph, relu, ops, group, exch_f=None, exch_b=None):
+        out = dist_layer_forward(ops, dgraph, x, weight, bias, relu, group, exch_f)
+        ctx.dgraph, ctx.relu, ctx.ops, ctx.group, ctx.exch_b = dgraph, relu, ops, group, exch_b
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, weight, out if relu else None)
         return out
@@ -248,8 +463,8 @@ class _DistGCNLayerFn(torch.autograd.Function):
     def backward(ctx, g):
         x, w, y = ctx.saved_tensors
         dx, dw, db = dist_layer_backward(ctx.ops, ctx.dgraph, x, w, g.contiguous(), y, ctx.needs_input_grad[0],
-                                         ctx.has_bias, ctx.group)
-        return dx, dw, db, None, None, None, None
+                                         ctx.has_bias, ctx.group, ctx.exch_b)
+        return dx, dw, db, None, None, None, None, None, None
 
 
 class DistGraphConvolution(torch.nn.Module):
@@ -257,13 +472,41 @@ class DistGraphConvolution(torch.nn.Module):
     Parameters are replicated (same seed on every rank = same init as the reference layer);
     `.grad` of weight/bias comes out already all-reduced."""
 
-    def __init__(self, in_features, out_features, bias=True, *, fuse_relu=False, precision="auto", group=None):
+    def __init__(self, in_features, out_features, bias=True, *, fuse_relu=False, precision="auto", group=None,
+                 exchange="auto"):
         super().__init__()
         from .layers import GraphConvolution
 
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
         self.inner = GraphConvolution(in_features, out_features, bias, fuse_relu=fuse_relu, precision=precision)
         self.group = group
+        self.exchange = exchange
         self._ops = None
+        self._exch = None  # (dgraph id, forward exchange, backward exchange): per layer, so that a slot is
+        #                    never overwritten by another layer's panel while a peer still reads it
+
+    @staticmethod
+    def resolve_exchange(exchange, world):
+        """'auto': measured on 8 x B200 (profiles/r01_dist_probe8.txt, r01_bench_n*_peer/nccl.json): the
+        pipelined peer-memory exchange wins at 2 GPUs (0.325 vs 0.380 ms/step); from 4 GPUs on its 2
+        small kernels per peer wait for SM slots behind the SpMM's CTAs and the phase-split SpMM costs
+        +38 %, so one NCCL all-gather + one SpMM is faster (0.704 vs 0.853 ms at 8)."""
+        if exchange == "auto":
+            return "peer" if world == 2 else "nccl"
+        return exchange
+
+    def _exchanges(self, dgraph, dev):
+        if dgraph.world == 1 or self.resolve_exchange(self.exchange, dgraph.world) == "nccl" or dgraph.fwd_blocks is None:
+            return None, None
+        if self._exch is None or self._exch[0] is not dgraph:
+            if self._exch is not None:
+                self._exch[1].close()
+                self._exch[2].close()
+            f = self.inner.out_features
+            self._exch = (dgraph, PeerExchange(dgraph.rank, dgraph.world, dgraph.pad_rows, f, dev, self.group),
+                          PeerExchange(dgraph.rank, dgraph.world, dgraph.pad_rows, f, dev, self.group))
+        return self._exch[1], self._exch[2]
 
     @property
     def weight(self):
@@ -278,8 +521,9 @@ class DistGraphConvolution(torch.nn.Module):
             self._ops = CudaOps(self.inner.precision)
         if not input.is_cuda:
             raise RuntimeError("DistGraphConvolution runs on CUDA devices only (no CPU fallback)")
+        ef, eb = self._exchanges(dgraph, input.device)
         return _DistGCNLayerFn.apply(input.contiguous(), self.inner.weight, self.inner.bias, dgraph,
-                                     self.inner.fuse_relu, self._ops, self.group)
+                                     self.inner.fuse_relu, self._ops, self.group, ef, eb)
 
 
 # ---------------------------------------------------------------------------- bench entry (N > 1)
@@ -301,8 +545,9 @@ def bench_main(args, wl):
     n_global = wl["n"] * world
     wlg = dict(wl, n=n_global)
     t0 = time.perf_counter()
+    exchange = DistGraphConvolution.resolve_exchange(os.environ.get("GCNB_DIST_EXCHANGE", "auto"), world)
     full = B.make_graph(P, torch, wlg, dev)          # same seed on every rank: identical global graph
-    dgraph = DistGraph.from_graph(full, rank, world)
+    dgraph = DistGraph.from_graph(full, rank, world, per_source=(exchange == "peer"))
     nnz_global = full.nnz
     del full
     torch.cuda.synchronize()
@@ -311,7 +556,7 @@ def bench_main(args, wl):
     fin, fout = wl["fin"], wl["fout"]
 
     torch.manual_seed(42)
-    layer = DistGraphConvolution(fin, fout).to(dev)
+    layer = DistGraphConvolution(fin, fout, exchange=exchange).to(dev)
     gen = torch.Generator(device="cpu")
     x_host = torch.randn(n_local, fin, generator=gen.manual_seed(1 + rank)).pin_memory()
     g_host = torch.randn(n_local, fout, generator=gen.manual_seed(100 + rank)).pin_memory()
@@ -446,8 +691,11 @@ def bench_main(args, wl):
                        "input_requires_grad": False, "l2": "flushed between timed steps (512 MiB write)",
                        "cuda_graph": cg is not None, "graph_build_s": build_s, "bounds": dgraph.bounds,
                        "row_block_split": dgraph.split,
-                       "exchange": "NCCL all-gather of the X.W / G panels overlapped with the diagonal-block SpMM, then "
-                                   "the remote-block SpMM accumulates; all-reduce of dW,db"},
+                       "exchange": ("peer: own push kernel over NVLink peer memory (P2P stores + release flags), one "
+                                    "column block per source rank consumed as its slot lands; NCCL all-reduce of dW,db"
+                                    if exchange == "peer" else
+                                    "nccl: all-gather of the X.W / G panels, then the SpMM over the row block; "
+                                    "all-reduce of dW,db")},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": (x_host.numel() + g_host.numel()) * 4,
                     "d2h_bytes_per_step": (fin * fout + fout) * 4, "ms_per_step": e2e_t.item() / args.steps * 1e3},

@@ -20,14 +20,14 @@ class HostBlock:
     """rows [r0, r1) of a COO matrix; columns either local to [c0, c1) (diagonal block) or remapped
     to the padded all-gather layout with part `exclude` left out (remote block)."""
 
-    def __init__(self, idx, val, r0, r1, bounds=None, pad=None, exclude=None, c0=None, c1=None):
+    def __init__(self, idx, val, r0, r1, bounds=None, pad=None, exclude=None, c0=None, c1=None, only=None):
         rows = (idx[0] >= r0) & (idx[0] < r1)
         if bounds is None:
             m = rows & (idx[1] >= c0) & (idx[1] < c1)
             self.col = idx[1][m] - c0
         else:
             part = np.searchsorted(np.asarray(bounds), idx[1], side="right") - 1
-            m = rows & (part != exclude)
+            m = rows & ((part != exclude) if only is None else np.isin(part, list(only)))
             self.col = part[m] * pad + (idx[1][m] - np.asarray(bounds)[part[m]])
         self.row = idx[0][m] - r0
         self.val = val[m]
@@ -74,7 +74,7 @@ def _problem(n=300, seed=3):
     return n, idx, val, x, g, w, b
 
 
-def _worker(rank, world, port, outdir, relu, split=True):
+def _worker(rank, world, port, outdir, relu, split=True, pipelined=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -92,8 +92,15 @@ def _worker(rank, world, port, outdir, relu, split=True):
         ops = NumpyOps()
         xt, gt = torch.from_numpy(x[r0:r1].copy()), torch.from_numpy(g[r0:r1].copy())
         wt, bt = torch.from_numpy(w), torch.from_numpy(b)
-        out = D.dist_layer_forward(ops, dg, xt, wt, bt, relu=relu)
-        dx, dw, db = D.dist_layer_backward(ops, dg, xt, wt, gt, out if relu else None, True, True)
+        ef = eb = None
+        if pipelined:  # one column block per source rank, consumed in the order p, p+1, ... (exchange "peer")
+            dg.phases = D.exchange_phases(rank, world)
+            dg.fwd_blocks = [HostBlock(idx, val, r0, r1, bounds=bounds, pad=pad, only=qs) for qs in dg.phases]
+            dg.bwd_blocks = [HostBlock(tidx, val, r0, r1, bounds=bounds, pad=pad, only=qs) for qs in dg.phases]
+            ef = D.CollectiveExchange(rank, world, pad, w.shape[1], xt)
+            eb = D.CollectiveExchange(rank, world, pad, w.shape[1], xt)
+        out = D.dist_layer_forward(ops, dg, xt, wt, bt, relu=relu, exch=ef)
+        dx, dw, db = D.dist_layer_backward(ops, dg, xt, wt, gt, out if relu else None, True, True, exch=eb)
         np.savez(os.path.join(outdir, "r%d.npz" % rank), out=out.numpy(), dx=dx.numpy(), dw=dw.numpy(), db=db.numpy(),
                  bounds=np.array(bounds))
     finally:
@@ -108,10 +115,12 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,relu,split", [(2, False, True), (2, True, False), (3, False, True)])
-def test_row_partitioned_layer_matches_single_process_oracle(world, relu, split):
+@pytest.mark.parametrize("world,relu,split,pipelined", [(2, False, True, False), (2, True, False, False),
+                                                        (3, False, True, False), (2, True, False, True),
+                                                        (3, False, False, True), (4, True, False, True)])
+def test_row_partitioned_layer_matches_single_process_oracle(world, relu, split, pipelined):
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_worker, args=(world, _free_port(), d, relu, split), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), d, relu, split, pipelined), nprocs=world, join=True)
         parts = [np.load(os.path.join(d, "r%d.npz" % r)) for r in range(world)]
     n, idx, val, x, g, w, b = _problem()
     _, o_ref = O.c_layer_forward(x, w, b, idx, val, n)
@@ -128,6 +137,16 @@ def test_row_partitioned_layer_matches_single_process_oracle(world, relu, split)
     for p in parts:  # all-reduced: every rank holds the full gradient
         assert O.normwise_err(p["dw"], dw) < 1e-5 and O.normwise_err(p["db"], db) < 1e-5
     assert list(parts[0]["bounds"]) == list(parts[-1]["bounds"])
+
+
+def test_exchange_phases_cover_every_source_once_own_slot_first():
+    for world in (1, 2, 3, 4, 5, 8, 16):
+        for rank in range(world):
+            ph = D.exchange_phases(rank, world)
+            flat = [q for qs in ph for q in qs]
+            assert ph[0] == [rank] and sorted(flat) == list(range(world))
+            assert flat == [(rank + k) % world for k in range(world)]  # arrival order of the rotated pushes
+            assert all(1 <= len(qs) <= 2 for qs in ph) and (world < 3 or len(ph[-1]) == 1 or world % 2 == 1)
 
 
 def test_partition_balances_nnz_and_exchange_is_a_matching():
