@@ -69,8 +69,9 @@ size_t graph_matmul_ws(const gcnb_graph* g, bool transpose, int64_t f) {
   size_t w = spmm_workspace_bytes(v, f);
   if (g->dense_fwd) {
     const int64_t m = transpose ? g->n_cols : g->n_rows, r = transpose ? g->n_rows : g->n_cols;
-    size_t a = gemm_fp32_workspace_bytes(m, f, r);
-    size_t b = (f <= 256) ? gemm_tc_tn_workspace_bytes(m, f, r) : 0;
+    const int64_t fw = f < 256 ? f : 256;
+    size_t a = gemm_fp32_workspace_bytes(m, fw, r);
+    size_t b = gemm_tc_tn_workspace_bytes(m, fw, r);
     if (a > w) w = a;
     if (b > w) w = b;
   }
@@ -90,10 +91,14 @@ int graph_matmul(const gcnb_graph* g, bool transpose, const float* b, int64_t ld
   const float* x = transpose ? g->dense_fwd : g->dense_bwd;
   const int64_t ldx = transpose ? g->ld_fwd : g->ld_bwd;
   GCNB_REQUIRE(ws_bytes >= graph_matmul_ws(g, transpose, f), "spmm(dense route): workspace too small");
-  if (f <= 256 && gemm_tc_tn_eligible(m, f, r, x, ldx, b, ldb, /*padded=*/true)) {
-    GCNB_TRY(gemm_tc_tn_launch(m, f, r, x, ldx, b, ldb, out, ldo, ws, ws_bytes, st));
-  } else {
-    GCNB_TRY(gemm_fp32_launch(m, f, r, x, 1, ldx, b, ldb, 1, out, ldo, ws, ws_bytes, st));
+  // the tn kernel takes up to 256 output columns: wider operands (batched layers) go in column panels
+  for (int64_t f0 = 0; f0 < f; f0 += 256) {
+    const int64_t fw = (f - f0 < 256) ? (f - f0) : 256;
+    if (gemm_tc_tn_eligible(m, fw, r, x, ldx, b + f0, ldb, /*padded=*/true) && (f0 % 4 == 0)) {
+      GCNB_TRY(gemm_tc_tn_launch(m, fw, r, x, ldx, b + f0, ldb, out + f0, ldo, ws, ws_bytes, st));
+    } else {
+      GCNB_TRY(gemm_fp32_launch(m, fw, r, x, 1, ldx, b + f0, ldb, 1, out + f0, ldo, ws, ws_bytes, st));
+    }
   }
   return bias_act_launch(m, f, out, ldo, ep, st);
 }

@@ -67,6 +67,95 @@ colsum_partial_kernel(int64_t n_rows, int f, int cw, int64_t rows_per_block,
   }
 }
 
+// Vectorised single-launch variant (f % 4 == 0, 16-byte aligned operands): every thread owns one float4
+// column chunk and walks rows with four 16-byte loads in flight; the CTA's partial sums go to scratch and
+// the LAST CTA to arrive (atomic ticket) adds all partials in block order -- one launch instead of two,
+// still run-to-run deterministic (the order of the final additions is fixed, only who does them varies).
+__global__ void __launch_bounds__(kThreads)
+colsum_vec_kernel(int64_t n_rows, int f4, int cw, int64_t rows_per_block, const float4* __restrict__ g, int64_t ldg4,
+                  const float4* __restrict__ y, int64_t ldy4, float4* __restrict__ gm, int64_t ldgm4,
+                  float4* __restrict__ partial, unsigned int* __restrict__ ticket, float* __restrict__ out,
+                  const uchar4* __restrict__ mask, int64_t ld_mask4, float mask_scale) {
+  __shared__ float4 red[kThreads];
+  __shared__ bool is_last;
+  const int tx = threadIdx.x % cw;  // float4 column chunk
+  const int ty = threadIdx.x / cw;  // row lane
+  const int rl = kThreads / cw;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = (r0 + rows_per_block < n_rows) ? (r0 + rows_per_block) : n_rows;
+  auto load = [&](int64_t r) {
+    float4 v = g[r * ldg4 + tx];
+    if (mask != nullptr) {  // backward of the dropout epilogue comes first (it was applied last)
+      const uchar4 m = mask[r * ld_mask4 + tx];
+      v.x = m.x ? v.x * mask_scale : 0.f; v.y = m.y ? v.y * mask_scale : 0.f;
+      v.z = m.z ? v.z * mask_scale : 0.f; v.w = m.w ? v.w * mask_scale : 0.f;
+    }
+    if (y != nullptr) {
+      const float4 o = y[r * ldy4 + tx];
+      v.x = o.x > 0.f ? v.x : 0.f; v.y = o.y > 0.f ? v.y : 0.f;
+      v.z = o.z > 0.f ? v.z : 0.f; v.w = o.w > 0.f ? v.w : 0.f;
+    }
+    if (gm != nullptr) gm[r * ldgm4 + tx] = v;  // masked gradient, or a plain copy when y == NULL
+    return v;
+  };
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tx < f4) {
+    float4 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t r = r0 + ty;
+    for (; r + 3 * rl < r1; r += 4 * rl) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = load(r + u * rl);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a[u].x += v[u].x; a[u].y += v[u].y; a[u].z += v[u].z; a[u].w += v[u].w; }
+    }
+    for (; r < r1; r += rl) {
+      const float4 v = load(r);
+      a[0].x += v.x; a[0].y += v.y; a[0].z += v.z; a[0].w += v.w;
+    }
+    acc.x = (a[0].x + a[1].x) + (a[2].x + a[3].x);
+    acc.y = (a[0].y + a[1].y) + (a[2].y + a[3].y);
+    acc.z = (a[0].z + a[1].z) + (a[2].z + a[3].z);
+    acc.w = (a[0].w + a[1].w) + (a[2].w + a[3].w);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (ty == 0 && tx < f4) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < rl; ++t) {
+      const float4 v = red[t * cw + tx];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    partial[(int64_t)blockIdx.x * f4 + tx] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // final pass: row lane ty adds the partials of blocks ty, ty + rl, ... ; then the lanes in order
+  acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tx < f4) {
+    for (int b = ty; b < (int)gridDim.x; b += rl) {
+      const float4 v = partial[(int64_t)b * f4 + tx];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (ty == 0 && tx < f4) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < rl; ++t) {
+      const float4 v = red[t * cw + tx];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[tx] = s;
+  }
+}
+
 // out[i] = sum over parts of partial[s][i]: 32 outputs x 8 part-lanes per CTA, fixed-order tree.
 __global__ void __launch_bounds__(kThreads)
 reduce_partials_kernel(int64_t total, int64_t n, int n_parts, const float* __restrict__ partial,
@@ -133,7 +222,8 @@ int colsum_blocks(int64_t n_rows) {
 }  // namespace
 
 size_t colsum_workspace_bytes(int64_t n_rows, int64_t f) {
-  return (size_t)colsum_blocks(n_rows) * (size_t)f * sizeof(float);
+  // partials [blocks][f] (16-byte aligned rows) + the arrival ticket of the single-launch variant
+  return (size_t)colsum_blocks(n_rows) * (size_t)(ceil_div(f, 4) * 4) * sizeof(float) + 256;
 }
 
 int colsum_launch(int64_t n_rows, int64_t f, const float* g, int64_t ldg, const float* y,
@@ -153,9 +243,26 @@ int colsum_launch(int64_t n_rows, int64_t f, const float* g, int64_t ldg, const 
   const int nb = colsum_blocks(n_rows);
   const size_t need = colsum_workspace_bytes(n_rows, f);
   GCNB_REQUIRE(ws != nullptr && ws_bytes >= need, "colsum: workspace too small (%zu < %zu)", ws_bytes, need);
+  const int64_t rows_per_block = ceil_div(n_rows, nb);
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const bool vec = f % 4 == 0 && f <= 4 * kThreads && al16(g) && ldg % 4 == 0 && al16(out) && al16(ws) &&
+                   (y == nullptr || (al16(y) && ldy % 4 == 0)) && (gm == nullptr || (al16(gm) && ldgm % 4 == 0)) &&
+                   (mask == nullptr || ((reinterpret_cast<uintptr_t>(mask) & 3u) == 0 && ld_mask % 4 == 0));
+  if (vec) {
+    const int f4 = (int)(f / 4);
+    int cw4 = 1;
+    while (cw4 < f4) cw4 <<= 1;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + (need - 256));
+    GCNB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st));
+    colsum_vec_kernel<<<nb, kThreads, 0, st>>>(
+        n_rows, f4, cw4, rows_per_block, reinterpret_cast<const float4*>(g), ldg / 4, reinterpret_cast<const float4*>(y),
+        ldy / 4, reinterpret_cast<float4*>(gm), ldgm / 4, reinterpret_cast<float4*>(ws), ticket, out,
+        reinterpret_cast<const uchar4*>(mask), ld_mask / 4, mask_scale);
+    GCNB_LAUNCH_CHECK();
+    return GCNB_OK;
+  }
   int cw = 32;
   while (cw < f && cw < kThreads) cw <<= 1;
-  const int64_t rows_per_block = ceil_div(n_rows, nb);
   colsum_partial_kernel<<<nb, kThreads, 0, st>>>(n_rows, (int)f, cw, rows_per_block, g, ldg, y, ldy, gm,
                                                  ldgm, reinterpret_cast<float*>(ws), mask, ld_mask, mask_scale);
   GCNB_LAUNCH_CHECK();

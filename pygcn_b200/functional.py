@@ -141,6 +141,96 @@ class _GCNLayerFn(torch.autograd.Function):
         return dx, dw, db, None, None, None, None, None
 
 
+class _GCNLayerBatchedFn(torch.autograd.Function):
+    """The layer over a batch of feature matrices that share one adjacency: x [B, N, Fin] -> [B, N, Fout].
+
+    The fork's real training step calls the 3-layer GCN once per sample with the same `adj`
+    (GCN_OVER_MLP.forward, pygcn/models.py:343-349: 20 samples -> 60 layer calls per step).  Here the
+    batch is laid out node-major, Xn [(N*B), Fin], so that X.W is ONE GEMM whose result, seen as
+    [N, B*Fout], is the dense operand of ONE SpMM: the index/value stream of the adjacency is read
+    once per layer instead of B times, and B*Fout-wide rows gather at the wide-row rate."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, graph, relu, precision):
+        lib = _lib.load()
+        dev = x.device
+        bsz, n, fin = x.shape
+        fout = weight.shape[1]
+        wide = bsz * fout
+        xn = x.permute(1, 0, 2).contiguous().view(n * bsz, fin)   # node-major rows (n, b); free if already so
+        w = weight.contiguous()
+        s2 = torch.empty((n * bsz, fout), dtype=torch.float32, device=dev)
+        out2 = torch.empty((graph.n_rows, wide), dtype=torch.float32, device=dev)
+        brep = bias.detach().repeat(bsz).contiguous() if bias is not None else None
+        with _on_device(dev):
+            sp = _stream_ptr(dev)
+            ws = _ws(lib.gcnb_gemm_workspace_bytes(n * bsz, fout, fin, precision), dev)
+            st = lib.gcnb_gemm(n * bsz, fout, fin, _ptr(xn), fin, 1, _ptr(w), fout, 1, _ptr(s2), fout, precision,
+                               _ptr(ws), ws.numel(), sp)
+            _lib.check(st, "gcnb_gemm")
+            ws2 = _ws(lib.gcnb_spmm_workspace_bytes(graph._h, 0, wide), dev)
+            st = lib.gcnb_spmm(graph._h, _lib.SPMM_RELU if relu else 0, _ptr(s2), wide, wide, _ptr(brep), _ptr(out2),
+                               wide, _ptr(ws2), ws2.numel(), sp)
+            _lib.check(st, "gcnb_spmm")
+        ctx.graph, ctx.relu, ctx.precision = graph, relu, precision
+        ctx.has_bias = bias is not None
+        ctx.dims = (bsz, n, fin, fout)
+        ctx.save_for_backward(xn, w, out2 if relu else None)
+        return out2.view(graph.n_rows, bsz, fout).permute(1, 0, 2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        lib = _lib.load()
+        xn, w, y2 = ctx.saved_tensors
+        graph, precision = ctx.graph, ctx.precision
+        bsz, n, fin, fout = ctx.dims
+        wide = bsz * fout
+        dev = g.device
+        need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        g2 = g.permute(1, 0, 2).contiguous().view(graph.n_rows, wide)
+        dx = dw = db = None
+        with _on_device(dev):
+            sp = _stream_ptr(dev)
+            gm2 = g2
+            if ctx.relu or need_db:
+                gm2 = torch.empty_like(g2) if ctx.relu else None
+                dbrep = torch.empty((wide,), dtype=torch.float32, device=dev)
+                ws = _ws(lib.gcnb_colsum_workspace_bytes(graph.n_rows, wide), dev)
+                st = lib.gcnb_colsum(graph.n_rows, wide, _ptr(g2), wide, _ptr(y2) if ctx.relu else None, wide,
+                                     _ptr(gm2), wide, _ptr(dbrep), _ptr(ws), ws.numel(), sp)
+                _lib.check(st, "gcnb_colsum")
+                if gm2 is None:
+                    gm2 = g2
+                if need_db:  # db = sum over the batch of the per-sample column sums
+                    db = torch.empty((fout,), dtype=torch.float32, device=dev)
+                    ws = _ws(lib.gcnb_colsum_workspace_bytes(bsz, fout), dev)
+                    st = lib.gcnb_colsum(bsz, fout, _ptr(dbrep), fout, None, fout, None, fout, _ptr(db), _ptr(ws),
+                                         ws.numel(), sp)
+                    _lib.check(st, "gcnb_colsum")
+            if need_dw or need_dx:
+                ds2 = torch.empty((graph.n_cols, wide), dtype=torch.float32, device=dev)
+                ws = _ws(lib.gcnb_spmm_workspace_bytes(graph._h, _lib.SPMM_TRANSPOSE, wide), dev)
+                st = lib.gcnb_spmm(graph._h, _lib.SPMM_TRANSPOSE, _ptr(gm2), wide, wide, None, _ptr(ds2), wide, _ptr(ws),
+                                   ws.numel(), sp)
+                _lib.check(st, "gcnb_spmm(transpose)")
+                rows = n * bsz
+                if need_dw:  # dW = Xn^T dS over the (n, b) rows: one split-K product
+                    dw = torch.empty((fin, fout), dtype=torch.float32, device=dev)
+                    ws = _ws(lib.gcnb_gemm_workspace_bytes(fin, fout, rows, precision), dev)
+                    st = lib.gcnb_gemm(fin, fout, rows, _ptr(xn), 1, fin, _ptr(ds2), fout, 1, _ptr(dw), fout, precision,
+                                       _ptr(ws), ws.numel(), sp)
+                    _lib.check(st, "gcnb_gemm(dW)")
+                if need_dx:
+                    dxn = torch.empty((rows, fin), dtype=torch.float32, device=dev)
+                    ws = _ws(lib.gcnb_gemm_workspace_bytes(rows, fin, fout, precision), dev)
+                    st = lib.gcnb_gemm(rows, fin, fout, _ptr(ds2), fout, 1, _ptr(w), 1, fout, _ptr(dxn), fin, precision,
+                                       _ptr(ws), ws.numel(), sp)
+                    _lib.check(st, "gcnb_gemm(dX)")
+                    dx = dxn.view(n, bsz, fin).permute(1, 0, 2)
+        return dx, dw, db, None, None, None
+
+
 def _check_layer_args(x, graph, weight, bias):
     _require_cuda(x, "input")
     _require_cuda(weight, "weight")
@@ -176,6 +266,13 @@ def gcn_layer(input, adj, weight, bias=None, relu=False, precision="auto", dropo
     the fork, pygcn/models.py:50,54); the backward masks the incoming gradient the same way.
     """
     graph = as_graph(adj)
+    if input.dim() == 3:  # [B, N, Fin]: the batch shares the adjacency (pygcn/models.py:343-349)
+        if dropout_mask is not None:
+            raise NotImplementedError("the fused dropout mask is not available for batched input")
+        _check_layer_args(input[0], graph, weight, bias)
+        if input.shape[0] == 0:
+            return input.new_empty((0, graph.n_rows, weight.shape[1]))
+        return _GCNLayerBatchedFn.apply(input, weight, bias, graph, bool(relu), _PRECISIONS[precision])
     _check_layer_args(input, graph, weight, bias)
     mask, scale = None, 1.0
     if dropout_mask is not None:

@@ -50,9 +50,12 @@ class GraphConvolution(Module):
             self.bias.data.uniform_(-bound, bound)
 
     def forward(self, input, adj):
+        """input [N, in_features] (the reference's call), or [B, N, in_features]: B feature matrices
+        over the same adjacency in one pass (what GCN_OVER_MLP's per-sample loop computes,
+        pygcn/models.py:343-349) -> [B, N, out_features]."""
         p = getattr(self, "dropout", 0.0)
         mask = None
-        if p > 0.0 and self.training:
+        if p > 0.0 and self.training and input.dim() == 2:
             n_rows = adj.shape[0]
             mask = torch.rand(n_rows, self.out_features, device=input.device) >= p
         return gcn_layer(input, adj, self.weight, self.bias, relu=getattr(self, "fuse_relu", False),

@@ -262,6 +262,39 @@ def test_fused_dropout_relu_epilogue(P):
     assert 0.4 < frac < 0.6
 
 
+@pytest.mark.parametrize("kind", ["csr", "dense"])
+@pytest.mark.parametrize("relu", [False, True])
+def test_batched_samples_match_per_sample_loop(P, kind, relu):
+    """x [B, N, Fin] in one pass (one GEMM + one SpMM of width B*Fout) == the reference's per-sample loop
+    (GCN_OVER_MLP.forward, pygcn/models.py:343-349) over the unbatched layer, forward and all gradients."""
+    n, bsz, fin, fout = 1500, 5, 8, 32
+    src, dst = _powerlaw_graph(n, 20000, seed=21, hub_deg=1200)
+    gr = P.Graph.from_edges(cu(src), cu(dst), n)
+    adj = gr if kind == "csr" else gr.to_sparse_coo().to_dense()
+    gen = torch.Generator(device=dev()).manual_seed(8)
+    x = torch.randn(bsz, n, fin + 3, generator=gen, device=dev())[:, :, :fin]  # column-slice view (models.py:345)
+    g = torch.randn(bsz, n, fout, generator=gen, device=dev())
+    torch.manual_seed(42)
+    layer = P.GraphConvolution(fin, fout, fuse_relu=relu).to(dev())
+    xb = x.clone().requires_grad_(True)
+    out = layer(xb, adj)
+    assert out.shape == (bsz, n, fout)
+    out.backward(g)
+    gw, gb = layer.weight.grad.clone(), layer.bias.grad.clone()
+    layer.zero_grad()
+    xs = x.clone().requires_grad_(True)
+    outs = torch.stack([layer(xs[i], adj) for i in range(bsz)])
+    outs.backward(g)
+    for mine, ref in ((out, outs), (xb.grad, xs.grad), (gw, layer.weight.grad), (gb, layer.bias.grad)):
+        assert ((mine - ref).abs().max() / ref.abs().max()).item() < TOL
+    # fp64 arbiter for the batched path itself
+    a64 = gr.to_sparse_coo().to_dense().double()
+    ref64 = a64 @ (x.double() @ layer.weight.detach().double()) + layer.bias.detach().double()
+    if relu:
+        ref64 = torch.relu(ref64)
+    assert ((out.double() - ref64).abs().max() / ref64.abs().max()).item() < TOL
+
+
 def test_layer_nobias_csr_golden(P, golden):
     c = golden("layer_cases.npz")
     n = int(c["ragged/n"])

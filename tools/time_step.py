@@ -84,8 +84,38 @@ def run(name, adj_graph, adj_torch, n, fin, fout, need_dx=False):
     print("%-60s ours %8.1f us   torch-on-CUDA reference lines %8.1f us   x%.2f" % (name, t_ours, t_ref, t_ref / t_ours))
 
 
+def run_batched(name, adj, n, bsz, fin, fout):
+    """fork's evaluator step shape: the same layer on B samples -- one batched call vs the per-sample loop."""
+    x = torch.randn(bsz, n, fin, device=dev, requires_grad=True)
+    g = torch.randn(bsz, n, fout, device=dev)
+    layer = P.GraphConvolution(fin, fout, fuse_relu=True).to(dev)
+
+    def batched():
+        layer.weight.grad = None
+        layer.bias.grad = None
+        layer(x, adj).backward(g)
+
+    def loop():
+        layer.weight.grad = None
+        layer.bias.grad = None
+        torch.stack([layer(x[i], adj) for i in range(bsz)]).backward(g)
+
+    tb, tl = graph_time(batched), graph_time(loop)
+    print("%-60s batched %8.1f us   per-sample loop %8.1f us   x%.2f" % (name, tb, tl, tl / tb))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["fork", "cbg"]
+    if "batched" in which:
+        n = 2943
+        v = torch.rand(40, n, device=dev)
+        adj = P.Graph.from_torch((v.t() @ v) / 40)
+        run_batched("fork evaluator: dense adj N=2943, B=20, 8->32 (+relu)", adj, n, 20, 8, 32)
+        run_batched("fork evaluator: dense adj N=2943, B=20, 32->32 (+relu)", adj, n, 20, 32, 32)
+        n = 100_000
+        src = torch.randint(0, n, (n * 50,), device=dev, dtype=torch.int32)
+        dst = torch.randint(0, n, (n * 50,), device=dev, dtype=torch.int32)
+        run_batched("CBG graph N=100000, B=8, 64->32 (+relu)", P.Graph.from_edges(src, dst, n), n, 8, 64, 32)
     if "fork" in which:
         n = 2943
         v = torch.rand(40, n, device=dev)
