@@ -539,6 +539,8 @@ gemm_tc_rows_ws_kernel(int64_t M, int N, int K, const float* __restrict__ a, int
 // MN = true keeps the operand tiles MN-major (rows of X / Y are stored as they arrive, 128-bit
 // shared-memory stores, UMMA descriptors with a_major = b_major = MN); MN = false transposes them
 // into K-major tiles with 32-bit stores.  npad must be a multiple of 32 when MN.
+constexpr int kTnDrainBlocks = 16;  // K blocks (of 32 rows) accumulated in TMEM between drains
+
 template <int NBQ, bool MN>
 __global__ void __launch_bounds__(kThreads, (NBQ <= 2) ? 2 : 1)
 gemm_tc_tn_kernel(int64_t R, int M, int N, const float* __restrict__ x, int64_t ldx, const float* __restrict__ y,
@@ -653,6 +655,8 @@ gemm_tc_tn_kernel(int64_t R, int M, int N, const float* __restrict__ x, int64_t 
 
   // loads run two K blocks ahead of the transposing stores when the registers allow it (NBQ <= 2)
   constexpr bool kDeep = NBQ <= 2;
+  float* cdst = c + (int64_t)blockIdx.x * split_stride;
+  uint32_t acc_parity = 0;
   float4 av[4], bv[NBQ], a1[4], b1[NBQ], a2[kDeep ? 4 : 1], b2[kDeep ? NBQ : 1];
   if (nkb > 0) load_block(0, av, bv);
   if (nkb > 1) load_block(1, a1, b1);
@@ -683,15 +687,29 @@ gemm_tc_tn_kernel(int64_t R, int M, int N, const float* __restrict__ x, int64_t 
     }
     fence_proxy_async();
     __syncthreads();
+    // The tensor core adds into TMEM with truncation: after kTnDrainBlocks K blocks the accumulator is
+    // moved out (fp32 round-to-nearest adds into the partial tile in global memory, L2 resident) and
+    // restarted, like the rows kernel does, so that long reductions (2.4 M rows for the products-shaped
+    // dW) stay inside the fp32 tier's 1e-5.
+    const bool chunk_first = (kb % kTnDrainBlocks) == 0;
+    const bool chunk_last = (kb % kTnDrainBlocks) == kTnDrainBlocks - 1 || kb == nkb - 1;
     if (tid == 0) {
       tc_fence_after();
       if constexpr (MN)
         issue_kblock_mn(tmem_d, base + L.a_hi[s], base + L.a_lo[s], base + L.b_hi[s], base + L.b_lo[s], idesc, ng,
-                        kb == 0);
+                        chunk_first);
       else
-        issue_kblock(tmem_d, base + L.a_hi[s], base + L.a_lo[s], base + L.b_hi[s], base + L.b_lo[s], idesc, kb == 0);
+        issue_kblock(tmem_d, base + L.a_hi[s], base + L.a_lo[s], base + L.b_hi[s], base + L.b_lo[s], idesc, chunk_first);
       umma_commit(bar_mma[s]);
-      if (kb == nkb - 1) umma_commit(bar_acc);
+      if (chunk_last) umma_commit(bar_acc);
+    }
+    if (chunk_last) {
+      mbar_wait(bar_acc, acc_parity);
+      acc_parity ^= 1u;
+      tc_fence_after();
+      epilogue_store(tmem_d, npad, cdst, ldc, m0, M, 0, N, vec_ok != 0, kb >= kTnDrainBlocks);
+      tc_fence_before();
+      __syncthreads();  // every warp has read its TMEM lanes before the next chunk overwrites them
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) av[j] = a1[j];
@@ -706,13 +724,7 @@ gemm_tc_tn_kernel(int64_t R, int M, int N, const float* __restrict__ x, int64_t 
       if (kb + 2 < nkb) load_block(kb + 2, a1, b1);
     }
   }
-  float* cdst = c + (int64_t)blockIdx.x * split_stride;
-  if (nkb > 0) {
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    epilogue_store(tmem_d, npad, cdst, ldc, m0, M, 0, N, vec_ok != 0);
-    tc_fence_before();
-  } else {
+  if (nkb == 0) {
     for (int i = tid; i < m_cols * N; i += kThreads) cdst[(int64_t)(m0 + i / N) * ldc + (i % N)] = 0.f;
   }
   __syncthreads();

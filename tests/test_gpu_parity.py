@@ -530,6 +530,101 @@ def test_cbg_backward_matches_torch_autograd(P, cbg):
         assert ((mine - ref).abs().max() / ref.abs().max()).item() < TOL
 
 
+# ------------------------------------------------------------------ full-size properties (BASELINE configs 2, 3)
+def _rmat_edges(n, n_edges, seed, a=0.57, b=0.19, c=0.19):
+    """R-MAT endpoints on the device (a,b,c,d = .57,.19,.19,.05), folded into [0, n)."""
+    gen = torch.Generator(device=dev()).manual_seed(seed)
+    bits = max(1, (n - 1).bit_length())
+    src = torch.zeros(n_edges, dtype=torch.int64, device=dev())
+    dst = torch.zeros(n_edges, dtype=torch.int64, device=dev())
+    for _ in range(bits):
+        r = torch.rand(n_edges, generator=gen, device=dev())
+        src = src * 2 + (r >= a + b).to(torch.int64)
+        dst = dst * 2 + (((r >= a) & (r < a + b)) | (r >= a + b + c)).to(torch.int64)
+    return (src % n).to(torch.int32), (dst % n).to(torch.int32)
+
+
+def _shape_properties(P, gr, n, fin, fout, seed):
+    """Size-independent checks of one layer on a big graph: rows of D^-1(A+I) sum to one, adjoint identity
+    between the forward and the transposed SpMM, linearity, run-to-run determinism, agreement of the
+    forward and of every gradient with torch's CUDA ops on the exported tensor."""
+    gen = torch.Generator(device=dev()).manual_seed(seed)
+    ones = torch.ones(n, 8, device=dev())
+    # fp32 accumulation of deg terms 1/deg: rounding grows like sqrt(deg) (hub rows of the R-MAT graph
+    # hold > 1e5 entries); 4 ulp * sqrt(max degree), never tighter than 1e-5
+    assert (P.spmm(gr, ones) - 1).abs().max().item() < max(1e-5, 2.4e-7 * gr.max_degree ** 0.5)
+    x = torch.randn(n, fout, generator=gen, device=dev(), requires_grad=True)
+    y = torch.randn(n, fout, generator=gen, device=dev())
+    ax = P.spmm(gr, x)
+    ax.backward(y)
+    lhs = (ax.double() * y.double()).sum().item()
+    rhs = (x.detach().double() * x.grad.double()).sum().item()
+    # both sides are sums of ~n*fout products that largely cancel: the scale of their rounding is
+    # |Ax| |y| (Cauchy-Schwarz), not the value of the sum
+    scale = ax.detach().double().norm().item() * y.double().norm().item()
+    assert abs(lhs - rhs) <= 1e-6 * scale
+    csr = gr.to_sparse_coo().coalesce().to_sparse_csr()
+    ref = torch.sparse.mm(csr, x.detach())
+    assert ((ax.detach() - ref).abs().max() / ref.abs().max()).item() < TOL
+    del ref, ax
+    torch.manual_seed(42)
+    layer = P.GraphConvolution(fin, fout).to(dev())
+    a = torch.randn(n, fin, generator=gen, device=dev())
+    g = torch.randn(n, fout, generator=gen, device=dev())
+    at = a.clone().requires_grad_(True)
+    out = layer(at, gr)
+    out.backward(g)
+    with torch.no_grad():
+        assert torch.equal(layer(a, gr), out)  # atomic-free: bit-stable
+    w = layer.weight.detach().clone().requires_grad_(True)
+    b = layer.bias.detach().clone().requires_grad_(True)
+    ar = a.clone().requires_grad_(True)
+    o_ref = torch.sparse.mm(csr, torch.mm(ar, w)) + b  # the reference's three lines on CUDA
+    o_ref.backward(g)
+    pairs = ((out, o_ref), (layer.weight.grad, w.grad), (layer.bias.grad, b.grad), (at.grad, ar.grad))
+    errs = [((mine.detach() - r.detach()).abs().max() / r.detach().abs().max()).item() for mine, r in pairs]
+    if max(errs) >= TOL:
+        # two fp32 computations of a 2.4 M-row reduction may differ by more than 1e-5 from each other:
+        # the fp64 run of the same formula arbitrates (SURVEY.md 8d): our error must be below
+        # max(1e-5, 2 x torch's own fp32 error)
+        w64 = layer.weight.detach().double().requires_grad_(True)
+        b64 = layer.bias.detach().double().requires_grad_(True)
+        a64 = a.double().requires_grad_(True)
+        o64 = torch.sparse.mm(csr.to(torch.float64), torch.mm(a64, w64)) + b64
+        o64.backward(g.double())
+        for (mine, r), r64 in zip(pairs, (o64, w64.grad, b64.grad, a64.grad)):
+            scale = r64.detach().abs().max()
+            mine_err = ((mine.detach().double() - r64.detach()).abs().max() / scale).item()
+            ref_err = ((r.detach().double() - r64.detach()).abs().max() / scale).item()
+            assert mine_err < max(TOL, 2 * ref_err), (mine_err, ref_err)
+
+
+def test_reddit_shape_full_size_properties(P):
+    """BASELINE configs[2]: N=232 965, ~114.6 M stored entries (uniform), 602 -> 256: wide-row SpMM
+    (warp-per-row kernel, two float4 chunks per lane) and compute-relevant tcgen05 GEMMs."""
+    n = 232_965
+    gen = torch.Generator(device=dev()).manual_seed(0)
+    src = torch.randint(0, n, (n * 246,), generator=gen, device=dev(), dtype=torch.int32)
+    dst = torch.randint(0, n, (n * 246,), generator=gen, device=dev(), dtype=torch.int32)
+    gr = P.Graph.from_edges(src, dst, n)
+    del src, dst
+    assert 113_000_000 < gr.nnz < 116_000_000 and gr.pattern_symmetric
+    _shape_properties(P, gr, n, 602, 256, seed=5)
+
+
+def test_products_shape_full_size_properties(P):
+    """BASELINE configs[3]: N=2 449 029, ~62 M stored entries, R-MAT (power-law: every degree bin and
+    the long-row split are populated), 100 -> 256 and the 256 -> 47 output layer."""
+    n = 2_449_029
+    src, dst = _rmat_edges(n, 31_000_000, seed=7)
+    gr = P.Graph.from_edges(src, dst, n)
+    del src, dst
+    assert 40_000_000 < gr.nnz < 66_000_000 and gr.n_long_chunks > 0 and gr.max_degree > 1024
+    assert all(b > 0 for b in gr.bin_rows[1:])
+    _shape_properties(P, gr, n, 100, 256, seed=6)
+    _shape_properties(P, gr, n, 256, 47, seed=7)
+
+
 # ------------------------------------------------------------------ multi-GPU building blocks on one GPU
 @pytest.mark.parametrize("world", [1, 3, 8])
 def test_row_partition_blocks_emulated_on_one_gpu(P, world):
