@@ -31,6 +31,34 @@ int gemm_route(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs, in
   return 0;
 }
 
+// Widths that are not a multiple of 4 floats (Reddit's 602 features) break the 16-byte loads of the
+// tensor-core kernels.  For products big enough to matter the operand is copied once into scratch with
+// rows zero-padded to the next multiple of 4 (one extra read + write of it: 0.17 ms for Reddit's X,
+// against 4.4 ms for the CUDA-core kernel) and the tensor-core kernel runs on the copy.
+constexpr double kPadMinWork = 1.0e8;
+inline int64_t pad4(int64_t v) { return ceil_div(v, 4) * 4; }
+// 1: A [m,k] row-major with k % 4 != 0 -> rows kernel on a padded copy; 2: A = X^T with X [k rows, m cols],
+// m % 4 != 0 -> tn kernel on a padded copy of X; 0: no
+int gemm_pad_route(int64_t m, int64_t n, int64_t k, int64_t a_rs, int64_t a_cs, const float* b, int64_t b_rs,
+                   int64_t b_cs, int precision) {
+  if (precision == GCNB_GEMM_FP32 || (double)m * (double)n * (double)k < kPadMinWork) return 0;
+  if (a_cs == 1 && k % 4 != 0 && k <= (1 << 20) && n <= (1 << 20)) return 1;
+  if (a_rs == 1 && b_cs == 1 && m % 4 != 0 && n <= 256 && b_rs % 4 == 0 && b_rs >= pad4(n) &&
+      (reinterpret_cast<uintptr_t>(b) & 15u) == 0)
+    return 2;
+  return 0;
+}
+size_t gemm_pad_bytes(int64_t m, int64_t n, int64_t k, int precision) {
+  if (precision == GCNB_GEMM_FP32 || (double)m * (double)n * (double)k < kPadMinWork) return 0;
+  size_t r = 0;
+  if (k % 4 != 0) r = (size_t)m * (size_t)pad4(k) * sizeof(float);
+  if (m % 4 != 0) {
+    const size_t t = (size_t)k * (size_t)pad4(m) * sizeof(float);
+    if (t > r) r = t;
+  }
+  return r ? align256(r) : 0;
+}
+
 int gemm_dispatch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs, int64_t a_cs,
                   const float* b, int64_t b_rs, int64_t b_cs, float* c, int64_t ldc, int precision,
                   void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -45,8 +73,28 @@ int gemm_dispatch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs,
     case 2:
       return gemm_tc_tn_launch(m, n, k, a, a_cs, b, b_rs, c, ldc, ws, ws_bytes, st);
     default:
-      return gemm_fp32_launch(m, n, k, a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, ws, ws_bytes, st);
+      break;
   }
+  const int pr = gemm_pad_route(m, n, k, a_rs, a_cs, b, b_rs, b_cs, precision);
+  const size_t pad_bytes = gemm_pad_bytes(m, n, k, precision);
+  if (pr != 0 && pad_bytes != 0 && ws != nullptr && ws_bytes > pad_bytes) {
+    float* pad = reinterpret_cast<float*>(ws);
+    char* rest = reinterpret_cast<char*>(ws) + pad_bytes;
+    const size_t rest_bytes = ws_bytes - pad_bytes;
+    if (pr == 1) {
+      const int64_t k4 = pad4(k);
+      GCNB_TRY(pad_copy_launch(m, k, a, a_rs, pad, k4, st));
+      if (gemm_tc_rows_eligible(m, n, k4, pad, k4, 1, c, ldc) && rest_bytes >= gemm_tc_rows_workspace_bytes(m, n, k))
+        return gemm_tc_rows_launch(m, n, k, pad, k4, b, b_rs, b_cs, c, ldc, rest, rest_bytes, st);
+    } else {
+      const int64_t m4 = pad4(m);
+      GCNB_TRY(pad_copy_launch(k, m, a, a_cs, pad, m4, st));  // X [k rows, m cols], row stride a_cs
+      if (gemm_tc_tn_eligible(m, n, k, pad, m4, b, b_rs, /*padded=*/true) &&
+          rest_bytes >= gemm_tc_tn_workspace_bytes(m, n, k))
+        return gemm_tc_tn_launch(m, n, k, pad, m4, b, b_rs, c, ldc, rest, rest_bytes, st);
+    }
+  }
+  return gemm_fp32_launch(m, n, k, a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, ws, ws_bytes, st);
 }
 
 // conservative: large enough for whichever kernel the route picks at call time
@@ -57,6 +105,7 @@ size_t gemm_ws(int64_t m, int64_t n, int64_t k, int precision) {
     const size_t t = (n <= 256) ? gemm_tc_tn_workspace_bytes(m, n, k) : 0;
     if (r > w) w = r;
     if (t > w) w = t;
+    w = align256(w) + gemm_pad_bytes(m, n, k, precision);
   }
   return (w + 255) & ~(size_t)255;
 }

@@ -105,6 +105,10 @@ size_t colsum_workspace_bytes(int64_t n_rows, int64_t f);
 // out[(i / n) * ldo + i % n] = sum_{s < n_parts} partial[s * total + i], s ascending inside a fixed
 // 8-lane tree (deterministic).  total = m * n.
 // out[r, 0:f] = (accumulate ? out : 0) ... in place: out = act(out + bias)
+// dst[r, 0:w4] = (src[r, 0:w], 0 ...) for r < n_rows, w4 = 4*ceil(w/4): zero-padded, 16-byte aligned rows
+int pad_copy_launch(int64_t n_rows, int64_t w, const float* src, int64_t ld_src, float* dst, int64_t ld_dst,
+                    cudaStream_t stream);
+
 int bias_act_launch(int64_t n_rows, int64_t f, float* out, int64_t ldo, const Epilogue& ep, cudaStream_t stream);
 
 int reduce_partials_launch(int64_t m, int64_t n, int n_parts, const float* partial, float* out,

@@ -202,6 +202,17 @@ bias_act_kernel(int64_t n_rows, int f, float* __restrict__ out, int64_t ldo, Epi
   }
 }
 
+__global__ void __launch_bounds__(kThreads)
+pad_copy_kernel(int64_t n_rows, int w, int w4, const float* __restrict__ src, int64_t ld_src, float* __restrict__ dst,
+                int64_t ld_dst) {
+  const int64_t total = n_rows * w4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / w4;
+    const int j = (int)(i % w4);
+    dst[r * ld_dst + j] = (j < w) ? __ldg(src + r * ld_src + j) : 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) zero_kernel(float* out, int f) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < f) out[j] = 0.f;
@@ -267,6 +278,19 @@ int colsum_launch(int64_t n_rows, int64_t f, const float* g, int64_t ldg, const 
                                                  ldgm, reinterpret_cast<float*>(ws), mask, ld_mask, mask_scale);
   GCNB_LAUNCH_CHECK();
   return reduce_partials_launch(1, f, nb, reinterpret_cast<const float*>(ws), out, f, st);
+}
+
+int pad_copy_launch(int64_t n_rows, int64_t w, const float* src, int64_t ld_src, float* dst, int64_t ld_dst,
+                    cudaStream_t st) {
+  if (n_rows == 0 || w == 0) return GCNB_OK;
+  const int64_t w4 = ceil_div(w, 4) * 4;
+  GCNB_REQUIRE(ld_dst >= w4 && ld_src >= w, "pad_copy: bad leading dimension");
+  int64_t blocks = ceil_div(n_rows * w4, kThreads * 4);
+  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  if (blocks < 1) blocks = 1;
+  pad_copy_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(n_rows, (int)w, (int)w4, src, ld_src, dst, ld_dst);
+  GCNB_LAUNCH_CHECK();
+  return GCNB_OK;
 }
 
 int bias_act_launch(int64_t n_rows, int64_t f, float* out, int64_t ldo, const Epilogue& ep, cudaStream_t st) {
