@@ -116,6 +116,20 @@ def build_normalized_adjacency(src, dst, n):
     return to_torch_coo_layout(r, c, v)
 
 
+def cbg_adjacency(hourly_visits):
+    """pygcn/utils.py:108-129 (`load_adj`): average the hourly POI x CBG visit matrices
+    (`avg_array += poi_cbg_visits_list[i]; avg_array /= num_hours`, :117-120), then
+    `adj[i][j] = np.sum(avg_array[:, i] * avg_array[:, j])` (:124-128) in float64, returned as
+    `torch.FloatTensor(adj)` (:131), i.e. float32.  hourly_visits: [hours, n_poi, n_cbg]."""
+    hv = np.asarray(hourly_visits, dtype=np.float64)
+    avg = np.zeros(hv.shape[1:], dtype=np.float64)
+    for h in range(hv.shape[0]):
+        avg += hv[h]
+    avg /= hv.shape[0]
+    adj = avg.T @ avg  # the reference's double loop, one dot product per (i, j)
+    return avg, adj.astype(np.float32)
+
+
 def coo_to_csr(idx, n_rows):
     """Row pointer of a row-sorted COO (what the device build must reproduce)."""
     counts = np.bincount(idx[0], minlength=n_rows)

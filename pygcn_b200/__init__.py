@@ -6,15 +6,16 @@ Public surface (mirrors the reference's for this path):
     gcn_layer             functional form of the layer
     Graph                 device-resident adjacency (replaces utils.normalize /
                           utils.sparse_mx_to_torch_sparse_tensor, built on the GPU)
+    load_adj              the CBG adjacency avg^T avg of utils.load_adj, on the device
     install_as_pygcn      make `import layers` / `import pygcn.layers` resolve to this package
 """
 import sys as _sys
 
-from .functional import gcn_layer, mm, spmm
+from .functional import gcn_layer, load_adj, mm, spmm
 from .graph import Graph, as_graph, clear_cache
 from .layers import GraphConvolution
 
-__all__ = ["GraphConvolution", "Graph", "as_graph", "clear_cache", "gcn_layer", "spmm", "mm", "install_as_pygcn"]
+__all__ = ["GraphConvolution", "Graph", "as_graph", "clear_cache", "gcn_layer", "spmm", "mm", "load_adj", "install_as_pygcn"]
 
 
 def install_as_pygcn():

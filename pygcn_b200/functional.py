@@ -342,6 +342,33 @@ def spmm(adj, dense):
     return _SpmmFn.apply(dense, graph)
 
 
+def load_adj(avg_visits, precision="auto"):
+    """The CBG adjacency of `utils.load_adj` (pygcn/utils.py:122-131) on the device:
+    adj[i][j] = sum_p avg[p, i] * avg[p, j]  for the averaged POI x CBG visit matrix `avg` [n_poi, n_cbg]
+    (the reference's O(N^2 M) Python double loop, cached as adj_<msa>.npy), returned as the dense fp32
+    [n_cbg, n_cbg] tensor the scripts pass as `adj`.  One split-K tensor-core product per 256-column panel
+    (gcnb_gemm, tcgen05 3xTF32 "tn" kernel) on a copy of `avg` whose rows are zero-padded to a multiple of 4."""
+    lib = _lib.load()
+    _require_cuda(avg_visits, "avg_visits")
+    if avg_visits.dim() != 2:
+        raise RuntimeError("avg_visits must be a [n_poi, n_cbg] matrix")
+    a = avg_visits.to(torch.float32)
+    p_, n = a.shape
+    n4 = _ld4(n)
+    a4 = torch.zeros((p_, n4), dtype=torch.float32, device=a.device)
+    a4[:, :n] = a
+    out = torch.empty((n4, n4), dtype=torch.float32, device=a.device)
+    prec = _PRECISIONS[precision]
+    with torch.cuda.device(a.device):
+        for f0 in range(0, n4, 256):
+            fw = min(256, n4 - f0)
+            ws = _ws(lib.gcnb_gemm_workspace_bytes(n4, fw, p_, prec), a.device)
+            st = lib.gcnb_gemm(n4, fw, p_, _ptr(a4), 1, n4, a4.data_ptr() + 4 * f0, n4, 1, out.data_ptr() + 4 * f0, n4,
+                               prec, _ptr(ws), ws.numel(), _stream_ptr(a.device))
+            _lib.check(st, "gcnb_gemm")
+    return out[:n, :n].contiguous()
+
+
 def mm(a, b, precision="auto"):
     """`torch.mm(a, b)` through gcnb_gemm (no autograd); used by tests and the benchmark."""
     lib = _lib.load()

@@ -221,6 +221,35 @@ def main():
     put("stack3", d6)
 
     np.savez_compressed(os.path.join(OUT, "layer_cases.npz"), **cases)
+
+    # ---------------------------------------------------------------- load_adj (utils.py:93-132): CBG adjacency
+    # The reference's own function, fed a synthetic hourly POI x CBG visit list through the file layout it
+    # expects (<mob_data_root>/<msa>/<full name>_2020-03-01_to_2020-05-02.pkl): adj = avg^T avg, dense fp32.
+    import pickle
+    import tempfile
+
+    constants = sys.modules.get("constants") or __import__("constants")
+    rs = np.random.default_rng(61)
+    n_poi, n_cbg, n_hours = 53, 31, 6
+    hours = []
+    for _ in range(n_hours):
+        dense = rs.poisson(0.4, size=(n_poi, n_cbg)).astype(np.float64) * rs.random((n_poi, n_cbg))
+        hours.append(sp.csr_matrix(dense))
+    with tempfile.TemporaryDirectory() as root, tempfile.TemporaryDirectory() as outdir:
+        msa = "SanFrancisco"
+        os.makedirs(os.path.join(root, msa))
+        with open(os.path.join(root, msa, "%s_2020-03-01_to_2020-05-02.pkl" % constants.MSA_NAME_FULL_DICT[msa]), "wb") as f:
+            pickle.dump(hours, f)
+        # First call: `np.zeros(..) += <scipy sparse>` turns avg_array into an np.matrix, and the matrix product
+        # in the double loop (utils.py:128) raises -- after avg_array_<msa>.npy has been saved.  A second call
+        # loads that file as a plain ndarray and completes: that is how the function runs at all upstream.
+        try:
+            adj_ref, num_cbgs = utils.load_adj(msa, root, outdir)
+        except ValueError:
+            adj_ref, num_cbgs = utils.load_adj(msa, root, outdir)
+    assert num_cbgs == n_cbg and adj_ref.dtype == torch.float32
+    np.savez_compressed(os.path.join(OUT, "load_adj.npz"), hours=np.stack([h.toarray() for h in hours]),
+                        adj=adj_ref.numpy().copy())
     print("wrote", sorted(os.listdir(OUT)))
     for f in os.listdir(OUT):
         if f.endswith(".npz"):

@@ -295,6 +295,24 @@ def test_batched_samples_match_per_sample_loop(P, kind, relu):
     assert ((out.double() - ref64).abs().max() / ref64.abs().max()).item() < TOL
 
 
+def test_load_adj_matches_reference_golden_and_oracle(P, golden):
+    """the CBG adjacency avg^T avg of utils.load_adj on the device, against the
+    reference-generated fixture and, at a fork-like size (2943 CBGs), against the oracle."""
+    c = golden("load_adj.npz")
+    avg, adj_o = O.cbg_adjacency(c["hours"])
+    adj = P.load_adj(cu(avg.astype(np.float32)))
+    assert adj.shape == c["adj"].shape and adj.dtype == torch.float32
+    assert err(adj, c["adj"]) < TOL and err(adj, adj_o) < TOL
+    rs = np.random.default_rng(5)
+    hours = rs.poisson(0.05, size=(3, 4000, 2943)) * rs.random((3, 4000, 2943))
+    avg, adj_o = O.cbg_adjacency(hours)
+    adj = P.load_adj(cu(avg.astype(np.float32)))
+    assert err(adj, adj_o) < TOL
+    # and it feeds the layer like the scripts' dense `adj` does (policy-generator.py:339)
+    gr = P.Graph.from_torch(adj)
+    assert gr.n_rows == 2943
+
+
 def test_layer_nobias_csr_golden(P, golden):
     c = golden("layer_cases.npz")
     n = int(c["ragged/n"])

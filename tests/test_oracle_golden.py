@@ -166,3 +166,13 @@ def test_ref_port_matches_golden(golden):
         torch.from_numpy(rng_inputs(3, (n, 16))), torch.from_numpy(c["cora_l2/weight"]),
         torch.from_numpy(c["cora_l2/bias"]), csr, torch.from_numpy(rng_inputs(4, (n, 7))))
     assert O.normwise_err(out2.numpy(), c["cora_l2/out"]) < TOL
+
+
+def test_cbg_adjacency_oracle_matches_reference_load_adj(golden):
+    """oracle.cbg_adjacency == the reference's own utils.load_adj (pygcn/utils.py:93-132) on the
+    reference-generated fixture: same float32 matrix bit for bit (both accumulate in float64)."""
+    c = golden("load_adj.npz")
+    avg, adj = O.cbg_adjacency(c["hours"])
+    assert adj.dtype == np.float32 and adj.shape == c["adj"].shape
+    assert O.normwise_err(adj, c["adj"]) < 1e-7
+    assert np.array_equal(adj, adj.T)
