@@ -67,6 +67,15 @@ int gemm_dispatch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs,
   GCNB_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm: negative dimension");
   GCNB_REQUIRE(ldc >= n, "gemm: ldc < n");
   if (m == 0 || n == 0) return GCNB_OK;
+  // narrow products over many rows (CBG 64->32, the fork's 8->32): HBM-bound streams, exact fp32 on CUDA
+  // cores beats the tensor-core pipeline's fixed costs; "tf32x3" still forces the tcgen05 kernels
+  if (precision != GCNB_GEMM_TF32X3) {
+    if (gemm_skinny_rows_eligible(m, n, k, a, a_rs, a_cs))
+      return gemm_skinny_rows_launch(m, n, k, a, a_rs, b, b_rs, b_cs, c, ldc, st);
+    if (a_rs == 1 && b_cs == 1 && gemm_skinny_tn_eligible(m, n, k, a, a_cs, b, b_rs) && ws != nullptr &&
+        ws_bytes >= gemm_skinny_tn_workspace_bytes(m, n, k))
+      return gemm_skinny_tn_launch(m, n, k, a, a_cs, b, b_rs, c, ldc, ws, ws_bytes, st);
+  }
   switch (gemm_route(m, n, k, a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, precision)) {
     case 1:
       return gemm_tc_rows_launch(m, n, k, a, a_rs, b, b_rs, b_cs, c, ldc, ws, ws_bytes, st);
@@ -100,6 +109,10 @@ int gemm_dispatch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs,
 // conservative: large enough for whichever kernel the route picks at call time
 size_t gemm_ws(int64_t m, int64_t n, int64_t k, int precision) {
   size_t w = gemm_fp32_workspace_bytes(m, n, k);
+  if (m <= 64 && n <= 32 && k >= 4096) {
+    const size_t sk = gemm_skinny_tn_workspace_bytes(m, n, k);
+    if (sk > w) w = sk;
+  }
   if (precision != GCNB_GEMM_FP32 && m > 0 && n > 0 && k > 0) {
     const size_t r = gemm_tc_rows_workspace_bytes(m, n, k);
     const size_t t = (n <= 256) ? gemm_tc_tn_workspace_bytes(m, n, k) : 0;

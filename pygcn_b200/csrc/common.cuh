@@ -96,6 +96,15 @@ size_t gemm_tc_tn_workspace_bytes(int64_t m, int64_t n, int64_t r);
 int gemm_tc_tn_launch(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y,
                       int64_t ldy, float* c, int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t stream);
 
+// CUDA-core kernels for narrow products over many rows (gemm_skinny.cu): K (resp. M) <= 64, N <= 64
+bool gemm_skinny_rows_eligible(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs, int64_t a_cs);
+int gemm_skinny_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t b_rs,
+                            int64_t b_cs, float* c, int64_t ldc, cudaStream_t stream);
+bool gemm_skinny_tn_eligible(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y, int64_t ldy);
+size_t gemm_skinny_tn_workspace_bytes(int64_t m, int64_t n, int64_t r);
+int gemm_skinny_tn_launch(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y, int64_t ldy,
+                          float* c, int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t stream);
+
 int colsum_launch(int64_t n_rows, int64_t f, const float* g, int64_t ldg, const float* y,
                   int64_t ldy, float* gm, int64_t ldgm, float* out, void* ws, size_t ws_bytes,
                   cudaStream_t stream, const uint8_t* mask = nullptr, int64_t ld_mask = 0,
