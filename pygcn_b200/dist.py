@@ -245,6 +245,11 @@ class _DevMem:
                                          "strides": None}
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """CUDA IPC / peer access is not available between the ranks (raised on EVERY rank, after a collective
+    agreement, so that all of them fall back to the NCCL exchange together)."""
+
+
 class PeerExchange:
     """One panel exchange buffer: gathered [world * pad_rows, f] fp32 on every rank, written by the
     peers' push kernels over NVLink peer memory, plus flag / ack words per source rank (csrc/peer.cu).
@@ -277,21 +282,36 @@ class PeerExchange:
         self.off_flags, self.off_acks = data, data + 256
         self.off_epoch, self.off_counters = data + 512, data + 768
         self.bytes = data + self.CTRL_BYTES
+        ok, why = 1, ""
+        self.ptr, self.peer_ptr = None, {}
         with torch.cuda.device(device):
             ptr = ctypes.c_void_p()
             handle = ctypes.create_string_buffer(64)
-            _lib.check(self.lib.gcnb_symm_alloc(self.bytes, ctypes.byref(ptr), handle), "gcnb_symm_alloc")
-            self.ptr = ptr.value
+            try:
+                _lib.check(self.lib.gcnb_symm_alloc(self.bytes, ctypes.byref(ptr), handle), "gcnb_symm_alloc")
+                self.ptr = ptr.value
+            except Exception as e:  # no IPC in this environment: every rank must learn it (collectives below)
+                ok, why = 0, repr(e)
             handles = [None] * world
-            dist.all_gather_object(handles, handle.raw, group=group)
-            self.peer_ptr = {}
-            for q in range(world):
-                if q == rank:
-                    continue
-                pp = ctypes.c_void_p()
-                _lib.check(self.lib.gcnb_symm_open(ctypes.create_string_buffer(handles[q], 64), ctypes.byref(pp)),
-                           "gcnb_symm_open")
-                self.peer_ptr[q] = pp.value
+            dist.all_gather_object(handles, handle.raw if ok else None, group=group)
+            if ok and all(h is not None for h in handles):
+                try:
+                    for q in range(world):
+                        if q == rank:
+                            continue
+                        pp = ctypes.c_void_p()
+                        _lib.check(self.lib.gcnb_symm_open(ctypes.create_string_buffer(handles[q], 64), ctypes.byref(pp)),
+                                   "gcnb_symm_open")
+                        self.peer_ptr[q] = pp.value
+                except Exception as e:
+                    ok, why = 0, repr(e)
+            else:
+                ok = 0
+            flag = torch.tensor([float(ok)], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # also: every rank has mapped every buffer
+            if flag.item() < 1:
+                self.close()
+                raise PeerExchangeUnavailable("peer-memory exchange unavailable on at least one rank (%s)" % (why or "peer"))
         # push order: the rank that consumes our slot first (p-1) is served first
         order = [(rank - k) % world for k in range(1, world)]
         n = len(order)
@@ -303,7 +323,6 @@ class PeerExchange:
         self.my_slot = self.gathered[rank * pad_rows:(rank + 1) * pad_rows]
         self.comm = torch.cuda.Stream(device=device, priority=-1)
         self._ev = torch.cuda.Event()
-        dist.barrier(group=group)  # every rank has mapped every buffer before anyone pushes
 
     def _sp(self, stream=None):
         return ctypes.c_void_p((stream or torch.cuda.current_stream(self.device)).cuda_stream)
@@ -344,11 +363,12 @@ class PeerExchange:
         torch.cuda.current_stream(self.device).wait_stream(self.comm)
 
     def close(self):
-        if getattr(self, "ptr", None):
-            with torch.cuda.device(self.device):
-                torch.cuda.synchronize(self.device)
-                for p in self.peer_ptr.values():
-                    self.lib.gcnb_symm_close(p)
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for p in getattr(self, "peer_ptr", {}).values():
+                self.lib.gcnb_symm_close(p)
+            self.peer_ptr = {}
+            if getattr(self, "ptr", None):
                 self.lib.gcnb_symm_free(self.ptr)
             self.ptr = None
 
@@ -503,9 +523,20 @@ class DistGraphConvolution(torch.nn.Module):
             if self._exch is not None:
                 self._exch[1].close()
                 self._exch[2].close()
+                self._exch = None
             f = self.inner.out_features
-            self._exch = (dgraph, PeerExchange(dgraph.rank, dgraph.world, dgraph.pad_rows, f, dev, self.group),
-                          PeerExchange(dgraph.rank, dgraph.world, dgraph.pad_rows, f, dev, self.group))
+            try:
+                ef = PeerExchange(dgraph.rank, dgraph.world, dgraph.pad_rows, f, dev, self.group)
+                try:
+                    eb = PeerExchange(dgraph.rank, dgraph.world, dgraph.pad_rows, f, dev, self.group)
+                except PeerExchangeUnavailable:
+                    ef.close()
+                    raise
+            except PeerExchangeUnavailable as e:  # agreed on by all ranks: use the NCCL exchange from now on
+                sys.stderr.write("pygcn_b200.dist: %s; falling back to exchange='nccl'\n" % e)
+                self.exchange = "nccl"
+                return None, None
+            self._exch = (dgraph, ef, eb)
         return self._exch[1], self._exch[2]
 
     @property
@@ -581,6 +612,8 @@ def bench_main(args, wl):
         step()
     torch.cuda.synchronize()
     dist.barrier()
+    if layer._exch is None:
+        exchange = "nccl"  # requested peer exchange was not available (agreed on by all ranks)
 
     # capture the step (kernels + NCCL all-gathers / all-reduce) in a CUDA graph: removes the Python
     # and launch gaps from the device time, like the single-GPU arm.  All ranks must agree.
