@@ -212,7 +212,7 @@ __device__ __forceinline__ uint32_t all_landed(const float4 (&x)[U], uint32_t ne
 
 template <int LPR, int U, int MINB>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
-spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* __restrict__ pair,
+spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* __restrict__ pair, int last_pair,
                   const float* __restrict__ b, uint32_t ldb_bytes, int f, Epilogue ep, float* __restrict__ out,
                   int64_t ldo, int vec_out, int skip_long, uint32_t never) {
   constexpr int G = 32 / LPR;
@@ -259,7 +259,8 @@ spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* _
     for (int k = 0; k < NC; ++k) {
       const int a = ahead - 2 * LPR * k;
       const uint32_t bytes = a >= 2 ? 16u : (a == 1 ? 8u : 0u);
-      cp_async16_zfill(dst_buf + 16u * (uint32_t)(sub + LPR * k), pair + e + 2 * LPR * k, bytes);
+      // (zero-byte copies past the row's end still carry an address: keep it inside the array)
+      cp_async16_zfill(dst_buf + 16u * (uint32_t)(sub + LPR * k), pair + min(e + 2 * LPR * k, last_pair), bytes);
     }
     cp_async_commit();
     e += E;
@@ -635,8 +636,8 @@ int launch_vec(const CsrView& a, const float* b, int64_t ldb, int f, const Epilo
       const int ggrid = (int)ceil_div(a.n_rows, (int64_t)kWarpsPerCta * G);
 #define GCNB_GROUP_LAUNCH(U_, MINB_)                                                                       \
   spmm_group_kernel<LPR, U_, MINB_><<<ggrid, kWarpsPerCta * 32, 0, st>>>(                               \
-      (int)a.n_rows, a.rowptr, a.pair, b, (uint32_t)(ldb * 4), f, ep, out, ldo, vec_out ? 1 : 0, \
-      has_long ? 1 : 0, 0u)
+      (int)a.n_rows, a.rowptr, a.pair, (int)(a.nnz & ~1ll), b, (uint32_t)(ldb * 4), f, ep, out, ldo,  \
+      vec_out ? 1 : 0, has_long ? 1 : 0, 0u)
       // (gathers in flight per lane, CTAs per SM the register budget must allow).  Measured on B200
       // (gpurun_out/probe_sweep8.log): 128/256-byte rows like many warps with 4 gathers each, narrower
       // rows fewer warps with 8.  GCNB_SPMM_GROUP_VARIANT overrides (tuning knob).
