@@ -313,6 +313,51 @@ def test_load_adj_matches_reference_golden_and_oracle(P, golden):
     assert gr.n_rows == 2943
 
 
+def test_cora_two_layer_training_follows_torch_reference(P, golden):
+    """the upstream 2-layer GCN training loop (dropout after layer 1, log_softmax +
+    NLL, Adam -- the semantics of the commented-out Cora loader, pygcn/utils.py:348-382 / upstream train.py)
+    on the real cora.cites graph with synthetic features and planted labels.  Our layers (fused ReLU +
+    fused dropout mask) and the reference's three lines on torch CUDA ops start from the same weights
+    and see the same dropout masks: the loss curves must agree step by step, and training must work."""
+    c = golden("cora_pipeline.npz")
+    n = int(c["n"])
+    e = c["edges"]
+    gr = P.Graph.from_edges(cu(e[:, 0]), cu(e[:, 1]), n)
+    coo = gr.to_sparse_coo().coalesce()
+    rs = np.random.default_rng(77)
+    labels = torch.from_numpy(rs.integers(0, 7, n)).to(dev())
+    feats = torch.from_numpy((rs.standard_normal((n, 64)) + 2.0 * np.eye(7)[labels.cpu().numpy()].repeat(10, 1)[:, :64]
+                              ).astype(np.float32)).to(dev())
+    idx_train = torch.arange(0, 140, device=dev())
+    torch.manual_seed(42)
+    g1, g2 = P.GraphConvolution(64, 16, fuse_relu=True).to(dev()), P.GraphConvolution(16, 7).to(dev())
+    w1, b1 = (t.detach().clone().requires_grad_(True) for t in (g1.weight, g1.bias))
+    w2, b2 = (t.detach().clone().requires_grad_(True) for t in (g2.weight, g2.bias))
+    opt_a = torch.optim.Adam(list(g1.parameters()) + list(g2.parameters()), lr=0.01, weight_decay=5e-4)
+    opt_b = torch.optim.Adam([w1, b1, w2, b2], lr=0.01, weight_decay=5e-4)
+    gen = torch.Generator(device=dev()).manual_seed(3)
+    la, lb = [], []
+    for step in range(30):
+        mask = torch.rand(n, 16, generator=gen, device=dev()) >= 0.5
+        opt_a.zero_grad()
+        h = P.gcn_layer(feats, gr, g1.weight, g1.bias, relu=True, dropout_mask=mask, dropout_p=0.5)
+        out = F.log_softmax(g2(h, gr), dim=1)
+        loss = F.nll_loss(out[idx_train], labels[idx_train])
+        loss.backward()
+        opt_a.step()
+        opt_b.zero_grad()
+        hr = torch.relu(torch.spmm(coo, torch.mm(feats, w1)) + b1) * mask / 0.5
+        outr = F.log_softmax(torch.spmm(coo, torch.mm(hr, w2)) + b2, dim=1)
+        lossr = F.nll_loss(outr[idx_train], labels[idx_train])
+        lossr.backward()
+        opt_b.step()
+        la.append(loss.item())
+        lb.append(lossr.item())
+    assert la[-1] < 0.5 * la[0]                                  # it trains
+    assert max(abs(a - b) for a, b in zip(la, lb)) < 2e-4 * max(la)  # and follows the reference trajectory
+    assert ((g1.weight - w1).abs().max() / w1.abs().max()).item() < 1e-3
+
+
 def test_layer_nobias_csr_golden(P, golden):
     c = golden("layer_cases.npz")
     n = int(c["ragged/n"])
