@@ -688,6 +688,36 @@ def test_products_shape_full_size_properties(P):
     _shape_properties(P, gr, n, 256, 47, seed=7)
 
 
+@pytest.mark.parametrize("world", [1, 3, 4])
+def test_partitioned_graph_build_is_bit_identical_to_cutting_the_full_graph(P, world):
+    """dist.build_partitioned (no rank ever holds the whole adjacency) == row blocks cut out of the
+    single-GPU Graph.from_edges result: same rowptr / columns / fp32 values bit for bit, for A and A^T.
+    Ranks are emulated one after the other on this GPU; the all-gather of the row sums is a concatenation."""
+    from pygcn_b200 import dist as D
+
+    n = 4000
+    src, dst = _powerlaw_graph(n, 30000, seed=30 + world, hub_deg=1500)
+    src = np.concatenate([src, src[:500]])  # duplicate edges: counts > 1
+    dst = np.concatenate([dst, dst[:500]])
+    s, d = cu(src), cu(dst)
+    full = P.Graph.from_edges(s, d, n)
+    bounds = D.partition_rows_by_nnz(full.csr()[0].cpu(), world)
+    pad = D.DistGraph.padded_rows(bounds)
+    stage1 = [D._partition_counts(s, d, n, bounds[r], bounds[r + 1]) for r in range(world)]
+    rowsum_global = torch.cat([t[4] for t in stage1])
+    for r in range(world):
+        ref = D.DistGraph.from_graph(full, r, world, bounds, split=False)
+        lrp, lcol, a, rows, _ = stage1[r]
+        mine = D._partition_blocks(r, world, bounds, pad, lrp, lcol, a, rows, rowsum_global.clone(), full.nnz)
+        for got, want in ((mine.fwd_remote, ref.fwd_remote or ref.fwd_diag), (mine.bwd_remote, ref.bwd_remote or ref.bwd_diag)):
+            assert got.shape == want.shape and got.nnz == want.nnz
+            for x, y in zip(got.csr(), want.csr()):
+                assert torch.equal(x, y)
+    # and the single-rank entry point end to end
+    dg = D.build_partitioned(s, d, n, 0, 1)
+    assert dg.fwd_remote.nnz == full.nnz and torch.equal(dg.fwd_remote.csr()[2], full.csr()[2])
+
+
 # ------------------------------------------------------------------ multi-GPU building blocks on one GPU
 @pytest.mark.parametrize("world", [1, 3, 8])
 def test_row_partition_blocks_emulated_on_one_gpu(P, world):

@@ -38,6 +38,14 @@ def main():
     dgraph = D.DistGraph.from_graph(full, rank, world, per_source=True)
     r0, r1 = dgraph.bounds[rank], dgraph.bounds[rank + 1]
     ok = True
+    # the partitioned build (no rank holds the whole graph) under the real all-gather: bit-identical blocks
+    dg2 = D.build_partitioned(src, dst, n, rank, world, bounds=dgraph.bounds)
+    same = dgraph.split or all(torch.equal(a_, b_) for got, want in ((dg2.fwd_remote, dgraph.fwd_remote),
+                                                                       (dg2.bwd_remote, dgraph.bwd_remote))
+                               for a_, b_ in zip(got.csr(), want.csr()))
+    ok = ok and same and dg2.nnz_global == full.nnz
+    if rank == 0:
+        print("partitioned build == cut of the full graph: %s (nnz_global %d)" % (same, dg2.nnz_global), flush=True)
     for exchange in ("peer", "nccl"):
         torch.manual_seed(42)
         layer = D.DistGraphConvolution(fin, fout, fuse_relu=True, exchange=exchange).to(dev)
