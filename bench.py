@@ -380,10 +380,23 @@ def run_ours(args, wl):
     # ---- the reference's own three lines executed by PyTorch on this GPU (cuBLAS / cuSPARSE), the
     # library kernels BASELINE.md asks to beat: adjacency as the COO tensor utils.py builds, and as CSR
     torch_cuda = {}
+    parity = None
     try:
         coo = graph.to_sparse_coo()
         wref = layer.weight.detach().clone().requires_grad_(True)
         bref = layer.bias.detach().clone().requires_grad_(True)
+        # parity gate printed with the timing: our step vs the reference's three lines run by
+        # torch on this GPU on the same tensors, norm-wise max|a-b| / max|b|
+        o_ours = step_eager()
+        o_ref = torch.spmm(coo, torch.mm(x, wref)) + bref
+        o_ref.backward(g)
+
+        def nerr(a, b):
+            return ((a.detach() - b.detach()).abs().max() / b.detach().abs().max()).item()
+        parity = {"out": nerr(o_ours, o_ref), "dW": nerr(layer.weight.grad, wref.grad), "db": nerr(layer.bias.grad, bref.grad),
+                  "tolerance": 1e-5, "against": "torch.mm / torch.spmm (cuBLAS / cuSPARSE) + autograd on the exported COO tensor"}
+        parity["ok"] = all(parity[k] <= 1e-5 for k in ("out", "dW", "db"))
+        del o_ours, o_ref
         for form, adj_t in (("coo_as_built", coo), ("csr", coo.coalesce().to_sparse_csr())):
             def ref_step():
                 wref.grad = None
@@ -425,6 +438,7 @@ def run_ours(args, wl):
                 "how": "wall clock over K steps of layer(x_dev, graph); backward; grads.cpu(); inputs double-buffered "
                        "from pinned host memory on a copy stream"},
         "torch_cuda_reference": torch_cuda,
+        "parity": parity,
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "spmm_group_kernel<8,4,6> (CSR SpMM, fwd and A^T launches)",
