@@ -70,7 +70,9 @@ int gemm_dispatch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs,
   // narrow products over many rows (CBG 64->32, the fork's 8->32): HBM-bound streams, exact fp32 on CUDA
   // cores beats the tensor-core pipeline's fixed costs; "tf32x3" still forces the tcgen05 kernels
   if (precision != GCNB_GEMM_TF32X3) {
-    if (gemm_skinny_rows_eligible(m, n, k, a, a_rs, a_cs))
+    if (gemm_skinny_rows_eligible(m, n, k, a, a_rs, a_cs) &&
+        !(precision == GCNB_GEMM_AUTO && (double)m * (double)n * (double)k >= kTcMinWork && gemm_tc_rows_beats_skinny(k) &&
+          gemm_tc_rows_eligible(m, n, k, a, a_rs, a_cs, c, ldc)))
       return gemm_skinny_rows_launch(m, n, k, a, a_rs, b, b_rs, b_cs, c, ldc, st);
     if (a_rs == 1 && b_cs == 1 && gemm_skinny_tn_eligible(m, n, k, a, a_cs, b, b_rs) && ws != nullptr &&
         ws_bytes >= gemm_skinny_tn_workspace_bytes(m, n, k))

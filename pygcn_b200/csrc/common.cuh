@@ -90,6 +90,7 @@ size_t gemm_tc_rows_workspace_bytes(int64_t m, int64_t n, int64_t k);
 int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b,
                         int64_t b_rs, int64_t b_cs, float* c, int64_t ldc, void* ws, size_t ws_bytes,
                         cudaStream_t stream);
+bool gemm_tc_rows_beats_skinny(int64_t k);
 bool gemm_tc_tn_eligible(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y,
                          int64_t ldy, bool padded = false);
 size_t gemm_tc_tn_workspace_bytes(int64_t m, int64_t n, int64_t r);

@@ -18,7 +18,9 @@
 // 1024 B apart), accumulators live in TMEM (128 lanes x N columns fp32), tcgen05.mma is issued
 // by one thread, completion is tracked with tcgen05.commit -> mbarrier, the epilogue reads TMEM
 // with tcgen05.ld.  Two smem stages; 2 CTAs per SM give the inter-tile overlap.
+#include <cuda.h>  // CUtensorMap types only: the encoder is fetched with cudaGetDriverEntryPoint (no libcuda link)
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -31,6 +33,7 @@ constexpr int BM = 128;        // UMMA M
 constexpr int BKF = 32;        // floats per K block (one 128-byte swizzle row)
 constexpr int kTileBytes = BM * 128;  // one 128-row operand tile (hi or lo)
 constexpr int kChunkBlocks = 8;  // K blocks (of 32) accumulated inside TMEM before a drain
+constexpr int kTnDrainBlocks = 16;  // K blocks (of 32 rows) accumulated in TMEM between drains
 
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -533,13 +536,428 @@ gemm_tc_rows_ws_kernel(int64_t M, int N, int K, const float* __restrict__ a, int
   }
 }
 
+// ------------------------------------------------------------------ mode R kernel, TMA-fed
+// The two kernels above move A through registers: HBM -> LDG -> split -> STS.  A thread can keep only one or
+// two 16 KB K blocks ahead that way (16-48 KB in flight per SM), and measured 1.7 TB/s on the shapes that
+// are pure streams (papers100M-shaped 13.8 M x 128 -> 128: 8.2 ms for 14.1 GB).  Here the copy engine does
+// the streaming and the SM only does arithmetic:
+//   warp  5    TMA producer: one thread issues cp.async.bulk.tensor.2d per (M tile, K block): a 128 x 32 fp32
+//              box of A, SWIZZLE_128B, lands in stage s as the K-major UMMA tile; rows / columns past the
+//              matrix are zero-filled by the tensor map.  With ns stages, (ns-1) x 16 KB stay in flight.
+//              When the packed B does not fit in shared memory, its (hi, lo) K block rides in the same stage.
+//   warps 6-9  splitters: wait raw_full[s]; a_lo = a - tf32(a) written to the stage's second tile at the SAME
+//              byte offsets (the swizzle is a property of the address, so no index arithmetic); the raw tile
+//              itself is the hi operand -- kind::tf32 reads the upper 19 bits of each word, i.e. truncates, and
+//              a - trunc(a) is exact in fp32 (hi_rna = 1 instead overwrites the raw tile with cvt.rna values).
+//   warp  4    MMA issuer (one thread): 12 tcgen05.mma per K block into one of two TMEM accumulators,
+//              tcgen05.commit -> empty[s] / acc_full[a].
+//   warps 0-3  epilogue: tcgen05.ld 32 columns -> registers -> per-warp shared staging (row stride 36 floats,
+//              conflict free) -> global stores in which 8 lanes write one full 128-byte line of a C row
+//              (the lane-per-row stores of the kernels above touch 32 lines per instruction).
+constexpr int kTmaThreads = 320;
+constexpr int kEpiLd = 36;
+constexpr int kTmaMaxStages = 8;
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct alignas(64) TmaDesc { uint8_t bytes[128]; };  // CUtensorMap (opaque, 128 bytes, 64-byte aligned)
+
+__global__ void __launch_bounds__(kTmaThreads, 1)
+gemm_tc_rows_tma_kernel(const __grid_constant__ TmaDesc tmap_a, int64_t M, int N, int K,
+                        const float* __restrict__ img_hi, const float* __restrict__ img_lo, float* __restrict__ c,
+                        int64_t ldc, int npad, int nkb, int tmem_cols, int vec_ok, int ns, int b_resident, int hi_rna) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  // layout: [ns x (a_raw 16K, a_lo 16K, (b_hi, b_lo when streamed))] [resident B: nkb x (b_hi, b_lo)]
+  //         [epilogue staging 4 x 32 x 36 floats] [barriers]
+  const uint32_t b_bytes = (uint32_t)npad * 128;
+  const uint32_t stage_bytes = 2u * kTileBytes + (b_resident ? 0u : 2u * b_bytes);
+  const uint32_t off_b = (uint32_t)ns * stage_bytes;
+  const uint32_t off_epi = off_b + (b_resident ? (uint32_t)nkb * 2u * b_bytes : 0u);
+  const uint32_t off_bar = (off_epi + 4u * 32u * kEpiLd * 4u + 1023u) & ~1023u;
+  auto bar_raw = [&](int s_) { return base + off_bar + 8u * (uint32_t)s_; };
+  auto bar_split = [&](int s_) { return base + off_bar + 64u + 8u * (uint32_t)s_; };
+  auto bar_empty = [&](int s_) { return base + off_bar + 128u + 8u * (uint32_t)s_; };
+  const uint32_t bar_b = base + off_bar + 192u;
+  auto bar_acc_full = [&](int a_) { return base + off_bar + 200u + 8u * (uint32_t)a_; };
+  auto bar_acc_empty = [&](int a_) { return base + off_bar + 216u + 8u * (uint32_t)a_; };
+  const uint32_t tmem_slot_off = off_bar + 232u;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < ns; ++i) { mbar_init(bar_raw(i), 1); mbar_init(bar_split(i), 4); mbar_init(bar_empty(i), 1); }
+    mbar_init(bar_b, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full(i), 1); mbar_init(bar_acc_empty(i), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    __syncwarp();
+    tmem_alloc(base + tmem_slot_off, (uint32_t)tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + tmem_slot_off);
+
+  const int nt = blockIdx.y;
+  const int n0 = nt * npad;
+  const int n_cols = min(npad, N - n0);
+  const int64_t m_tiles = (M + BM - 1) / BM;
+  const int64_t my_tiles = (m_tiles > (int64_t)blockIdx.x) ? (m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t n_items = my_tiles * nkb;
+  const int chunks_per_tile = (nkb + kChunkBlocks - 1) / kChunkBlocks;
+
+  if (warp == 5) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      if (b_resident) {
+        mbar_expect_tx(bar_b, 2 * b_bytes * (uint32_t)nkb);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int64_t blk = (int64_t)nt * nkb + kb;
+          bulk_g2s(base + off_b + (uint32_t)kb * 2 * b_bytes, img_hi + blk * ((int64_t)npad * BKF), b_bytes, bar_b);
+          bulk_g2s(base + off_b + (uint32_t)kb * 2 * b_bytes + b_bytes, img_lo + blk * ((int64_t)npad * BKF), b_bytes, bar_b);
+        }
+      }
+      int64_t item = 0;
+      for (int64_t t = 0; t < my_tiles; ++t) {
+        const int64_t m0 = ((int64_t)blockIdx.x + t * gridDim.x) * BM;
+        for (int kb = 0; kb < nkb; ++kb, ++item) {
+          const int s = (int)(item % ns);
+          const uint32_t use = (uint32_t)(item / ns);
+          if (use > 0) mbar_wait(bar_empty(s), (use - 1) & 1);
+          const uint32_t st_base = base + (uint32_t)s * stage_bytes;
+          mbar_expect_tx(bar_raw(s), (uint32_t)kTileBytes + (b_resident ? 0u : 2u * b_bytes));
+          tma_load_2d(st_base, &tmap_a, kb * BKF, (int)m0, bar_raw(s));
+          if (!b_resident) {
+            const int64_t blk = (int64_t)nt * nkb + kb;
+            bulk_g2s(st_base + 2u * kTileBytes, img_hi + blk * ((int64_t)npad * BKF), b_bytes, bar_raw(s));
+            bulk_g2s(st_base + 2u * kTileBytes + b_bytes, img_lo + blk * ((int64_t)npad * BKF), b_bytes, bar_raw(s));
+          }
+        }
+      }
+    }
+  } else if (warp >= 6) {
+    // ===================== splitters =====================
+    const int pt = tid - 192;  // 0..127
+    for (int64_t item = 0; item < n_items; ++item) {
+      const int s = (int)(item % ns);
+      const uint32_t use = (uint32_t)(item / ns);
+      mbar_wait(bar_raw(s), use & 1);
+      uint8_t* raw = gen + (uint32_t)s * stage_bytes;
+      uint8_t* lo_t = raw + kTileBytes;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t off = 16u * (uint32_t)(pt + 128 * j);
+        const float4 v = *reinterpret_cast<const float4*>(raw + off);
+        float4 hi, lo;
+        if (hi_rna) {
+          split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
+          split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+          *reinterpret_cast<float4*>(raw + off) = hi;
+        } else {
+          lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        }
+        *reinterpret_cast<float4*>(lo_t + off) = lo;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_split(s));
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(npad);
+      if (b_resident) mbar_wait(bar_b, 0);
+      int64_t item = 0;
+      uint32_t chunk_ctr = 0;
+      for (int64_t t = 0; t < my_tiles; ++t) {
+        for (int kb = 0; kb < nkb; ++kb, ++item) {
+          const int ab = (int)(chunk_ctr & 1u);
+          const uint32_t j_use = chunk_ctr >> 1;
+          if (kb % kChunkBlocks == 0 && j_use > 0) mbar_wait(bar_acc_empty(ab), (j_use - 1) & 1);
+          const int s = (int)(item % ns);
+          const uint32_t use = (uint32_t)(item / ns);
+          mbar_wait(bar_split(s), use & 1);
+          tc_fence_after();
+          const uint32_t a_hi = base + (uint32_t)s * stage_bytes;
+          const uint32_t bh = b_resident ? base + off_b + (uint32_t)kb * 2 * b_bytes : a_hi + 2u * kTileBytes;
+          issue_kblock(tmem_base + (uint32_t)ab * (uint32_t)npad, a_hi, a_hi + kTileBytes, bh, bh + b_bytes, idesc,
+                       kb % kChunkBlocks == 0);
+          umma_commit(bar_empty(s));
+          if (kb == nkb - 1 || kb % kChunkBlocks == kChunkBlocks - 1) {
+            umma_commit(bar_acc_full(ab));
+            ++chunk_ctr;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    float* stg = reinterpret_cast<float*>(gen + off_epi) + warp * 32 * kEpiLd;
+    uint32_t chunk_ctr = 0;
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      const int64_t m0 = ((int64_t)blockIdx.x + t * gridDim.x) * BM + warp * 32;
+      for (int ch = 0; ch < chunks_per_tile; ++ch, ++chunk_ctr) {
+        const int ab = (int)(chunk_ctr & 1u);
+        mbar_wait(bar_acc_full(ab), (chunk_ctr >> 1) & 1);
+        tc_fence_after();
+        const bool add = ch > 0;
+        for (int cb = 0; cb < n_cols; cb += 32) {
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld32(tmem_base + (uint32_t)ab * (uint32_t)npad + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, r);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(stg + lane * kEpiLd + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+          __syncwarp();
+          const int q = lane & 7;
+          const int col = cb + 4 * q;  // column inside this N tile
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3);
+            float4 v = *reinterpret_cast<const float4*>(stg + rr * kEpiLd + 4 * q);
+            const int64_t row = m0 + rr;
+            if (row < M && col < n_cols) {
+              float* dst = c + row * ldc + n0 + col;
+              if (vec_ok && col + 4 <= n_cols) {
+                if (add) {
+                  const float4 p = *reinterpret_cast<const float4*>(dst);
+                  v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+                }
+                *reinterpret_cast<float4*>(dst) = v;
+              } else {
+                const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int t2 = 0; t2 < 4; ++t2)
+                  if (col + t2 < n_cols) dst[t2] = add ? dst[t2] + e[t2] : e[t2];
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty(ab));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------ mode T kernel, TMA-fed
+// C_partial[split][128-row M tile][npad] = sum over the split's rows r of X[r, m0:m0+128]^T Y[r, 0:npad]
+// with the same division of labour as gemm_tc_rows_tma_kernel.  Both operands are MN-major (a reduction row
+// holds contiguous M resp. N elements), so the UMMA tiles are SWIZZLE_128B_BASE32B atoms of 4 reduction rows x
+// 32 elements -- exactly what a tensor map with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes for a box of 32
+// floats x 32 rows.  One K block (32 reduction rows) = 4 boxes of X (M groups, 4 KB apart) + npad/32 boxes of
+// Y; columns past the matrices' widths and rows past R arrive as zeros.  K step ks of a block starts 1 KB
+// into every box (two 4-row K groups of 512 B), LBO = 4096 (next M/N group), SBO = 512 (next K group).
+__global__ void __launch_bounds__(kTmaThreads, 1)
+gemm_tc_tn_tma_kernel(const __grid_constant__ TmaDesc tmap_x, const __grid_constant__ TmaDesc tmap_y, int64_t R, int M,
+                      int N, float* __restrict__ c, int64_t ldc, int64_t split_stride, int64_t rows_per_split, int npad,
+                      int tmem_cols, int vec_ok, int ns) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  // stage: [x_raw 16K][y_raw npad*128][x_lo 16K][y_lo npad*128]  (raw | lo halves have the same internal offsets)
+  const uint32_t y_bytes = (uint32_t)npad * 128;
+  const uint32_t half = (uint32_t)kTileBytes + y_bytes;
+  const uint32_t stage_bytes = 2u * half;
+  const uint32_t off_epi = (uint32_t)ns * stage_bytes;
+  const uint32_t off_bar = (off_epi + 4u * 32u * kEpiLd * 4u + 1023u) & ~1023u;
+  auto bar_raw = [&](int s_) { return base + off_bar + 8u * (uint32_t)s_; };
+  auto bar_split = [&](int s_) { return base + off_bar + 64u + 8u * (uint32_t)s_; };
+  auto bar_empty = [&](int s_) { return base + off_bar + 128u + 8u * (uint32_t)s_; };
+  auto bar_acc_full = [&](int a_) { return base + off_bar + 200u + 8u * (uint32_t)a_; };
+  auto bar_acc_empty = [&](int a_) { return base + off_bar + 216u + 8u * (uint32_t)a_; };
+  const uint32_t tmem_slot_off = off_bar + 232u;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < ns; ++i) { mbar_init(bar_raw(i), 1); mbar_init(bar_split(i), 4); mbar_init(bar_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_acc_full(i), 1); mbar_init(bar_acc_empty(i), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    __syncwarp();
+    tmem_alloc(base + tmem_slot_off, (uint32_t)tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + tmem_slot_off);
+
+  const int m0 = blockIdx.y * BM;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_split;
+  const int64_t r_end = min(R, r_begin + rows_per_split);
+  const int nkb = (r_end > r_begin) ? (int)((r_end - r_begin + BKF - 1) / BKF) : 0;
+  const int n_chunks = (nkb + kTnDrainBlocks - 1) / kTnDrainBlocks;
+  const int ng = npad >> 5;
+  float* cdst = c + (int64_t)blockIdx.x * split_stride;
+
+  if (warp == 5) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % ns;
+        const uint32_t use = (uint32_t)(kb / ns);
+        if (use > 0) mbar_wait(bar_empty(s), (use - 1) & 1);
+        const uint32_t st_base = base + (uint32_t)s * stage_bytes;
+        const int r0 = (int)(r_begin + (int64_t)kb * BKF);
+        mbar_expect_tx(bar_raw(s), half);
+#pragma unroll
+        for (int mg = 0; mg < 4; ++mg) tma_load_2d(st_base + (uint32_t)mg * 4096u, &tmap_x, m0 + 32 * mg, r0, bar_raw(s));
+        for (int g = 0; g < ng; ++g)
+          tma_load_2d(st_base + (uint32_t)kTileBytes + (uint32_t)g * 4096u, &tmap_y, 32 * g, r0, bar_raw(s));
+      }
+    }
+  } else if (warp >= 6) {
+    // ===================== splitters =====================
+    const int pt = tid - 192;  // 0..127
+    const int n16 = (int)(half >> 4);  // 16-byte chunks of the raw half (multiple of 128)
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % ns;
+      const uint32_t use = (uint32_t)(kb / ns);
+      mbar_wait(bar_raw(s), use & 1);
+      uint8_t* raw = gen + (uint32_t)s * stage_bytes;
+      uint8_t* lo_t = raw + half;
+#pragma unroll 4
+      for (int i = pt; i < n16; i += 128) {
+        const uint32_t off = 16u * (uint32_t)i;
+        const float4 v = *reinterpret_cast<const float4*>(raw + off);
+        float4 lo;
+        lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+        lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+        lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        *reinterpret_cast<float4*>(lo_t + off) = lo;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_split(s));
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(npad, true);
+      uint32_t chunk_ctr = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int ab = (int)(chunk_ctr & 1u);
+        const uint32_t j_use = chunk_ctr >> 1;
+        const bool first = (kb % kTnDrainBlocks) == 0;
+        if (first && j_use > 0) mbar_wait(bar_acc_empty(ab), (j_use - 1) & 1);
+        const int s = kb % ns;
+        const uint32_t use = (uint32_t)(kb / ns);
+        mbar_wait(bar_split(s), use & 1);
+        tc_fence_after();
+        const uint32_t xh = base + (uint32_t)s * stage_bytes, yh = xh + (uint32_t)kTileBytes;
+        const uint32_t xl = xh + half, yl = yh + half;
+        const uint32_t d = tmem_base + (uint32_t)ab * (uint32_t)npad;
+#pragma unroll
+        for (int ks = 0; ks < BKF / 8; ++ks) {
+          const uint32_t o = (uint32_t)ks * 1024u;
+          const uint64_t dxh = make_desc_mn(xh + o, 4096u, 512u), dxl = make_desc_mn(xl + o, 4096u, 512u);
+          const uint64_t dyh = make_desc_mn(yh + o, 4096u, 512u), dyl = make_desc_mn(yl + o, 4096u, 512u);
+          umma_tf32(d, dxl, dyh, idesc, (first && ks == 0) ? 0u : 1u);
+          umma_tf32(d, dxh, dyl, idesc, 1u);
+          umma_tf32(d, dxh, dyh, idesc, 1u);
+        }
+        umma_commit(bar_empty(s));
+        if (kb == nkb - 1 || (kb % kTnDrainBlocks) == kTnDrainBlocks - 1) {
+          umma_commit(bar_acc_full(ab));
+          ++chunk_ctr;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: partial tile rows m0 + 32*warp .. (TMEM lane = m) =====================
+    float* stg = reinterpret_cast<float*>(gen + off_epi) + warp * 32 * kEpiLd;
+    const int q = lane & 7;
+    if (nkb == 0) {  // an empty split still owns its partial tile
+      for (int i = lane; i < 32 * N; i += 32) {
+        const int row = m0 + warp * 32 + i / N;
+        if (row < M) cdst[(int64_t)row * ldc + (i % N)] = 0.f;
+      }
+    }
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int ab = ch & 1;
+      mbar_wait(bar_acc_full(ab), (uint32_t)(ch >> 1) & 1u);
+      tc_fence_after();
+      const bool add = ch > 0;
+      for (int cb = 0; cb < N; cb += 32) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + (uint32_t)ab * (uint32_t)npad + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, r);
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq)
+          *reinterpret_cast<uint4*>(stg + lane * kEpiLd + 4 * qq) = make_uint4(r[4 * qq], r[4 * qq + 1], r[4 * qq + 2], r[4 * qq + 3]);
+        __syncwarp();
+        const int col = cb + 4 * q;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3);
+          float4 v = *reinterpret_cast<const float4*>(stg + rr * kEpiLd + 4 * q);
+          const int row = m0 + warp * 32 + rr;
+          if (row < M && col < N) {
+            float* dst = cdst + (int64_t)row * ldc + col;
+            if (vec_ok && col + 4 <= N) {
+              if (add) {
+                const float4 p = *reinterpret_cast<const float4*>(dst);
+                v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+              }
+              *reinterpret_cast<float4*>(dst) = v;
+            } else {
+              const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int t2 = 0; t2 < 4; ++t2)
+                if (col + t2 < N) dst[t2] = add ? dst[t2] + e[t2] : e[t2];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty(ab));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------ mode T kernel
 // C_partial[split][M tile rows][N] = sum over rows r in the split of X[r, m] * Y[r, n]
 // NBQ = float4 loads of Y per thread per K block (npad <= 32*NBQ).
 // MN = true keeps the operand tiles MN-major (rows of X / Y are stored as they arrive, 128-bit
 // shared-memory stores, UMMA descriptors with a_major = b_major = MN); MN = false transposes them
 // into K-major tiles with 32-bit stores.  npad must be a multiple of 32 when MN.
-constexpr int kTnDrainBlocks = 16;  // K blocks (of 32 rows) accumulated in TMEM between drains
 
 template <int NBQ, bool MN>
 __global__ void __launch_bounds__(kThreads, (NBQ <= 2) ? 2 : 1)
@@ -752,14 +1170,125 @@ RowsPlan rows_plan(int64_t n, int64_t k) {
   return p;
 }
 
-// GCNB_ROWS_KERNEL=sync selects the __syncthreads-pipelined rows kernel (default: warp specialised)
-bool rows_use_ws() {
+// GCNB_ROWS_KERNEL=tma (default) | ws | sync; GCNB_TC_HI=rna makes the TMA kernel's splitters overwrite the raw
+// tile with cvt.rna values instead of letting the tensor core truncate the raw words
+int rows_kernel_choice() {  // 2 tma, 1 ws, 0 sync
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("GCNB_ROWS_KERNEL");
-    v = (e && (e[0] == 's' || e[0] == 'S')) ? 0 : 1;
+    v = !e ? 2 : ((e[0] == 's' || e[0] == 'S') ? 0 : ((e[0] == 'w' || e[0] == 'W') ? 1 : 2));
   }
-  return v == 1;
+  return v;
+}
+int tma_hi_rna() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GCNB_TC_HI");
+    v = (e && (e[0] == 'r' || e[0] == 'R')) ? 1 : 0;
+  }
+  return v;
+}
+
+struct TmaPlan { int npad, n_tiles, nkb, ns, b_resident; size_t img_floats; uint32_t smem; };
+TmaPlan tma_plan(int64_t n, int64_t k) {
+  TmaPlan p;
+  p.npad = n >= 256 ? 256 : (int)(ceil_div(n, 32) * 32);
+  p.n_tiles = (int)ceil_div(n, p.npad);
+  p.nkb = (int)ceil_div(k, BKF);
+  p.img_floats = (size_t)p.n_tiles * p.nkb * p.npad * BKF;
+  const size_t b_total = (size_t)p.nkb * 2 * p.npad * 128;
+  const size_t epi = 4 * 32 * kEpiLd * sizeof(float);
+  const size_t budget = 227 * 1024 - epi - 1024 /*barriers*/ - 2048 /*alignment*/;
+  size_t stage = 2 * kTileBytes;
+  if (b_total + 3 * stage <= budget) {
+    p.b_resident = 1;
+    p.ns = (int)((budget - b_total) / stage);
+  } else {
+    p.b_resident = 0;
+    stage += 2 * (size_t)p.npad * 128;
+    p.ns = (int)(budget / stage);
+  }
+  if (p.ns > kTmaMaxStages) p.ns = kTmaMaxStages;
+  const size_t off_epi = (size_t)p.ns * stage + (p.b_resident ? b_total : 0);
+  const size_t off_bar = (off_epi + epi + 1023) & ~(size_t)1023;
+  p.smem = (uint32_t)(off_bar + 256 + 1024);
+  return p;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point table
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+// A [M, K] fp32 row-major (lda floats) as boxes of 128 rows x 32 floats, SWIZZLE_128B, zero fill outside
+bool make_tmap_a(TmaDesc* out, const float* a, int64_t m, int64_t k, int64_t lda) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || m >= (1ll << 31)) return false;
+  CUtensorMap tm;
+  const cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)m};
+  const cuuint64_t gstride[1] = {(cuuint64_t)lda * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)BKF, (cuuint32_t)BM};
+  const cuuint32_t estr[2] = {1, 1};
+  if (fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a), gdim, gstride, box, estr,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "CUtensorMap is 128 bytes");
+  memcpy(out, &tm, sizeof(tm));
+  return true;
+}
+
+// X [R, W] fp32 row-major (ld floats) as boxes of 32 floats x 32 rows, SWIZZLE_128B_ATOM_32B (the MN-major UMMA atom)
+bool make_tmap_mn(TmaDesc* out, const float* x, int64_t rows, int64_t width, int64_t ld) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || rows >= (1ll << 31) || width >= (1ll << 31)) return false;
+  CUtensorMap tm;
+  const cuuint64_t gdim[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)BKF};
+  const cuuint32_t estr[2] = {1, 1};
+  if (fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstride, box, estr,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  memcpy(out, &tm, sizeof(tm));
+  return true;
+}
+
+struct TnTmaPlan { int npad, m_tiles, ns; int64_t splits, rows_per_split; uint32_t smem; };
+TnTmaPlan tn_tma_plan(int64_t m, int64_t n, int64_t r) {
+  TnTmaPlan p;
+  p.npad = (int)(ceil_div(n, 32) * 32);
+  p.m_tiles = (int)ceil_div(m, BM);
+  int64_t s = kNumSMs / p.m_tiles;  // one CTA per SM
+  const int64_t max_s = ceil_div(r, 4 * BKF);
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  p.rows_per_split = ceil_div(ceil_div(r, s), BKF) * BKF;
+  p.splits = ceil_div(r, p.rows_per_split);
+  if (p.splits < 1) p.splits = 1;
+  const size_t epi = 4 * 32 * kEpiLd * sizeof(float);
+  const size_t budget = 227 * 1024 - epi - 1024 - 2048;
+  const size_t stage = 2 * ((size_t)kTileBytes + (size_t)p.npad * 128);
+  p.ns = (int)(budget / stage);
+  if (p.ns > kTmaMaxStages) p.ns = kTmaMaxStages;
+  const size_t off_bar = ((size_t)p.ns * stage + epi + 1023) & ~(size_t)1023;
+  p.smem = (uint32_t)(off_bar + 256 + 1024);
+  return p;
 }
 
 // GCNB_TN_LAYOUT=k selects the transposing K-major variant of the tn kernel (default: MN-major)
@@ -800,14 +1329,43 @@ bool gemm_tc_rows_eligible(int64_t m, int64_t n, int64_t k, const float* a, int6
 size_t gemm_tc_rows_workspace_bytes(int64_t m, int64_t n, int64_t k) {
   (void)m;
   const RowsPlan p = rows_plan(n, k);
-  return 2 * p.img_floats * sizeof(float) + 256;
+  const TmaPlan t = tma_plan(n, k);  // (pads N to 32: the larger image)
+  const size_t f = p.img_floats > t.img_floats ? p.img_floats : t.img_floats;
+  return 2 * f * sizeof(float) + 256;
 }
 
 int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t b_rs,
                         int64_t b_cs, float* c, int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t st) {
-  const RowsPlan p = rows_plan(n, k);
   GCNB_REQUIRE(ws != nullptr && ws_bytes >= gemm_tc_rows_workspace_bytes(m, n, k) && aligned16(ws),
                "gemm(tc rows): workspace too small or unaligned");
+  if (rows_kernel_choice() == 2) {
+    const TmaPlan t = tma_plan(n, k);
+    TmaDesc tmap;
+    if (t.ns >= 2 && make_tmap_a(&tmap, a, m, k, lda)) {
+      float* hi = reinterpret_cast<float*>(ws);
+      float* lo = hi + ((t.img_floats + 31) & ~(size_t)31);
+      int pg = (int)ceil_div((int64_t)t.img_floats, 256);
+      if (pg > 4 * kNumSMs) pg = 4 * kNumSMs;
+      pack_b_kernel<<<pg, 256, 0, st>>>(k, n, t.npad, t.n_tiles, t.nkb, b, b_rs, b_cs, hi, lo);
+      GCNB_LAUNCH_CHECK();
+      static bool tma_attr = false;
+      if (!tma_attr) {
+        GCNB_CUDA(cudaFuncSetAttribute(gemm_tc_rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        tma_attr = true;
+      }
+      const int64_t mt = ceil_div(m, BM);
+      int64_t gx = kNumSMs / t.n_tiles;
+      if (gx < 1) gx = 1;
+      if (gx > mt) gx = mt;
+      const int vec = (ldc % 4 == 0) && aligned16(c);
+      gemm_tc_rows_tma_kernel<<<dim3((unsigned)gx, (unsigned)t.n_tiles), kTmaThreads, t.smem, st>>>(
+          tmap, m, (int)n, (int)k, hi, lo, c, ldc, t.npad, t.nkb, tmem_cols_for(2 * t.npad), vec, t.ns, t.b_resident,
+          tma_hi_rna());
+      GCNB_LAUNCH_CHECK();
+      return GCNB_OK;
+    }
+  }
+  const RowsPlan p = rows_plan(n, k);
   float* img_hi = reinterpret_cast<float*>(ws);
   float* img_lo = img_hi + ((p.img_floats + 31) & ~(size_t)31);
   GCNB_REQUIRE((size_t)((char*)(img_lo + p.img_floats) - (char*)ws) <= ws_bytes, "gemm(tc rows): workspace layout");
@@ -827,7 +1385,7 @@ int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t
   }
   const int64_t m_tiles = ceil_div(m, BM);
   const int vec_ok_ = (ldc % 4 == 0) && aligned16(c) && (p.npad % 4 == 0);
-  if (b_resident && rows_use_ws()) {
+  if (b_resident && rows_kernel_choice() >= 1) {
     // warp-specialised pipeline: as many 32 KB operand stages as fit beside the resident B (<= 4)
     const size_t b_total = (size_t)p.nkb * 2 * p.npad * 128;
     int ns = (int)((200 * 1024 - b_total) / (2 * kTileBytes));
@@ -859,11 +1417,18 @@ int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t
   return GCNB_OK;
 }
 
+// narrow "rows" products with K >= 32 measure faster on the TMA-fed tensor-core kernel than on the CUDA-core
+// skinny kernel (CBG 64->32 X W: 23.1 vs 26.6 us in the step's graph; 8->32: 16.6 vs 12.3)
+bool gemm_tc_rows_beats_skinny(int64_t k) { return rows_kernel_choice() == 2 && k >= 32 && encode_tiled_fn() != nullptr; }
+
 // dW-shaped product: C[M,N] = sum_r X[r, 0:M]^T Y[r, 0:N]
 // padded = every row of x / y is readable (and finite) up to the next multiple of 4 columns
 bool gemm_tc_tn_eligible(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y, int64_t ldy,
                          bool padded) {
-  const bool widths_ok = padded ? (ldx >= ceil_div(m, 4) * 4 && ldy >= ceil_div(n, 4) * 4) : (m % 4 == 0 && n % 4 == 0);
+  // the TMA-fed kernel zero-fills past the widths itself; the register-fed one reads whole float4s
+  const bool tma = rows_kernel_choice() == 2 && tn_use_mn() && encode_tiled_fn() != nullptr;
+  const bool widths_ok = tma ? true
+                             : (padded ? (ldx >= ceil_div(m, 4) * 4 && ldy >= ceil_div(n, 4) * 4) : (m % 4 == 0 && n % 4 == 0));
   return m > 0 && n > 0 && r > 0 && n <= 256 && (ldx % 4 == 0) && (ldy % 4 == 0) && widths_ok && aligned16(x) &&
          aligned16(y);
 }
@@ -878,6 +1443,29 @@ int gemm_tc_tn_launch(int64_t m, int64_t n, int64_t r, const float* x, int64_t l
   const TnPlan p = tn_plan(m, n, r);
   const size_t need = gemm_tc_tn_workspace_bytes(m, n, r);
   GCNB_REQUIRE(need == 0 || (ws != nullptr && ws_bytes >= need && aligned16(ws)), "gemm(tc tn): workspace too small");
+  if (rows_kernel_choice() == 2 && tn_use_mn() && n <= 256) {
+    const TnTmaPlan t = tn_tma_plan(m, n, r);
+    TmaDesc tx, ty;
+    const size_t need_t = t.splits > 1 ? (size_t)t.splits * (size_t)m * (size_t)n * sizeof(float) : 0;
+    if (t.ns >= 2 && need_t <= ws_bytes && make_tmap_mn(&tx, x, r, m, ldx) && make_tmap_mn(&ty, y, r, n, ldy)) {
+      float* dst_t = (t.splits > 1) ? reinterpret_cast<float*>(ws) : c;
+      const int64_t ld_t = (t.splits > 1) ? n : ldc;
+      const int64_t stride_t = (t.splits > 1) ? m * n : 0;
+      const int vec = (ld_t % 4 == 0) && aligned16(dst_t);
+      static bool tn_attr = false;
+      if (!tn_attr) {
+        GCNB_CUDA(cudaFuncSetAttribute(gemm_tc_tn_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        tn_attr = true;
+      }
+      gemm_tc_tn_tma_kernel<<<dim3((unsigned)t.splits, (unsigned)t.m_tiles), kTmaThreads, t.smem, st>>>(
+          tx, ty, r, (int)m, (int)n, dst_t, ld_t, stride_t, t.rows_per_split, t.npad, tmem_cols_for(2 * t.npad), vec, t.ns);
+      GCNB_LAUNCH_CHECK();
+      if (t.splits > 1) GCNB_TRY(reduce_partials_launch(m, n, (int)t.splits, dst_t, c, ldc, st));
+      return GCNB_OK;
+    }
+  }
+  GCNB_REQUIRE(ldx >= ceil_div(m, 4) * 4 && ldy >= ceil_div(n, 4) * 4,
+               "gemm(tc tn): rows must be readable up to the next multiple of 4 columns without the TMA kernel");
   Smem L;
   const uint32_t smem = smem_layout(p.npad, &L) + 1024;
   float* dst = (p.splits > 1) ? reinterpret_cast<float*>(ws) : c;
