@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GCNB_VERSION 101
+#define GCNB_VERSION 102
 
 #define GCNB_OK 0
 #define GCNB_E_INVALID 1  /* bad argument (shape, null pointer, alignment, overflow)  */
@@ -158,6 +158,16 @@ int gcnb_spmm(const gcnb_graph* g, int flags, const float* d_b, int64_t ldb, int
               void* stream);
 /* scratch for the partial rows of the split long-row bin (0 when the graph has none) */
 size_t gcnb_spmm_workspace_bytes(const gcnb_graph* g, int flags, int64_t f);
+
+/* Reduced-precision tier of the same product (BASELINE north_star: "2e-2 when bf16 features are used"): the
+ * dense operand is bf16, so a gathered row is half the bytes the kernel is bound by; accumulation, bias, ReLU
+ * and the output stay fp32.  d_b is [n_cols, ldb] bf16 with ldb a multiple of 8 and >= 8*ceil(f/8), rows
+ * 16-byte aligned (gcnb_to_bf16 produces exactly that).  Not available for handles on the dense route. */
+int gcnb_spmm_bf16(const gcnb_graph* g, int flags, const uint16_t* d_b, int64_t ldb, int64_t f,
+                   const float* d_bias, float* d_out, int64_t ldo, void* d_ws, size_t ws_bytes, void* stream);
+/* d_dst[r, 0:ld_dst] = bf16(d_src[r, 0:f]) round-to-nearest-even, zeros past f (the panel gcnb_spmm_bf16 gathers) */
+int gcnb_to_bf16(int64_t n_rows, int64_t f, const float* d_src, int64_t ld_src, uint16_t* d_dst, int64_t ld_dst,
+                 void* stream);
 
 #define GCNB_GEMM_FP32 0    /* CUDA-core fp32 FMA (bit-faithful fp32 accumulate)          */
 #define GCNB_GEMM_TF32X3 1  /* tcgen05 kind::tf32, 3-term split: fp32-level accuracy      */

@@ -59,6 +59,8 @@ SIGNATURES = {
     "gcnb_graph_export_coo": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "gcnb_graph_export_csr": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "gcnb_spmm": (c_int, [c_vp, c_int, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "gcnb_spmm_bf16": (c_int, [c_vp, c_int, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "gcnb_to_bf16": (c_int, [c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "gcnb_spmm_workspace_bytes": (c_sz, [c_vp, c_int, c_i64]),
     "gcnb_gemm": (c_int, [c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_int,
                           c_vp, c_sz, c_vp]),

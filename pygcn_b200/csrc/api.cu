@@ -212,6 +212,24 @@ extern "C" int gcnb_spmm(const gcnb_graph* g, int flags, const float* d_b, int64
                       d_out, ldo, d_ws, ws_bytes, (cudaStream_t)stream);
 }
 
+extern "C" int gcnb_spmm_bf16(const gcnb_graph* g, int flags, const uint16_t* d_b, int64_t ldb, int64_t f,
+                              const float* d_bias, float* d_out, int64_t ldo, void* d_ws, size_t ws_bytes,
+                              void* stream) {
+  GCNB_REQUIRE(g != nullptr, "spmm_bf16: null graph");
+  const bool transpose = (flags & GCNB_SPMM_TRANSPOSE) != 0;
+  GCNB_REQUIRE(!transpose || g->has_transpose, "spmm_bf16: this handle is a block without a transpose");
+  GCNB_REQUIRE(g->dense_fwd == nullptr, "spmm_bf16: handles on the dense route have no bf16 panel path (use gcnb_spmm)");
+  return spmm_bf16_launch(transpose ? g->bwd : g->fwd, d_b, ldb, f,
+                          make_epilogue(d_bias, (flags & GCNB_SPMM_RELU) != 0, (flags & GCNB_SPMM_ACCUMULATE) != 0,
+                                        nullptr, 0, 1.f),
+                          d_out, ldo, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int gcnb_to_bf16(int64_t n_rows, int64_t f, const float* d_src, int64_t ld_src, uint16_t* d_dst,
+                            int64_t ld_dst, void* stream) {
+  return to_bf16_launch(n_rows, f, d_src, ld_src, d_dst, ld_dst, (cudaStream_t)stream);
+}
+
 extern "C" size_t gcnb_spmm_workspace_bytes(const gcnb_graph* g, int flags, int64_t f) {
   if (!g) return 0;
   return graph_matmul_ws(g, (flags & GCNB_SPMM_TRANSPOSE) != 0, f);

@@ -75,6 +75,11 @@ constexpr int kLongChunk = 1024;
 
 int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const Epilogue& ep, float* out,
                 int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t stream);
+// the same product with a bf16 panel (the <= 2e-2 tier): b is [n_cols, ldb] bf16, ldb % 8 == 0, 16-byte aligned
+int spmm_bf16_launch(const CsrView& a, const uint16_t* b, int64_t ldb, int64_t f, const Epilogue& ep, float* out,
+                     int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t stream);
+int to_bf16_launch(int64_t n_rows, int64_t f, const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst,
+                   cudaStream_t stream);
 size_t spmm_workspace_bytes(const CsrView& a, int64_t f);
 int spmm_set_tuning(int key, int value);
 

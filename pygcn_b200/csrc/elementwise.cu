@@ -293,6 +293,48 @@ int pad_copy_launch(int64_t n_rows, int64_t w, const float* src, int64_t ld_src,
   return GCNB_OK;
 }
 
+// dst[r, 0:ld8] = bf16(src[r, 0:f]) (round to nearest even), zero past f: one thread per 8 output elements
+// (16-byte store); rows of dst are 16-byte aligned (ld_dst % 8 == 0).  src rows may be unaligned / strided.
+__global__ void __launch_bounds__(kThreads)
+to_bf16_kernel(int64_t n_rows, int f, int c8, const float* __restrict__ src, int64_t ld_src, uint16_t* __restrict__ dst,
+               int64_t ld_dst, int vec_in) {
+  const int64_t total = n_rows * c8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c8;
+    const int q = (int)(i % c8);
+    const float* p = src + r * ld_src + 8 * q;
+    float v[8];
+    if (vec_in && 8 * q + 8 <= f) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[t] = (8 * q + t < f) ? __ldg(p + t) : 0.f;
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)  // cvt.rn.bf16x2.f32 d, hi, lo: element 2t in the low half
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[t]) : "f"(v[2 * t + 1]), "f"(v[2 * t]));
+    *reinterpret_cast<uint4*>(dst + r * ld_dst + 8 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+int to_bf16_launch(int64_t n_rows, int64_t f, const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst,
+                   cudaStream_t st) {
+  if (n_rows == 0 || f == 0) return GCNB_OK;
+  const int64_t c8 = ceil_div(f, 8);
+  GCNB_REQUIRE(src != nullptr && dst != nullptr, "to_bf16: null operand");
+  GCNB_REQUIRE(ld_src >= f && ld_dst >= 8 * c8 && ld_dst % 8 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0,
+               "to_bf16: destination rows must be 16-byte aligned with ld a multiple of 8 and >= 8*ceil(f/8)");
+  const int vec_in = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && (ld_src % 4 == 0);
+  int64_t blocks = ceil_div(n_rows * c8, kThreads);
+  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  to_bf16_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(n_rows, (int)f, (int)c8, src, ld_src, dst, ld_dst, vec_in);
+  GCNB_LAUNCH_CHECK();
+  return GCNB_OK;
+}
+
 int bias_act_launch(int64_t n_rows, int64_t f, float* out, int64_t ldo, const Epilogue& ep, cudaStream_t st) {
   if (n_rows == 0 || f == 0 || (ep.bias == nullptr && !ep.relu && ep.mask == nullptr)) return GCNB_OK;
   int64_t blocks = ceil_div(n_rows * f, kThreads);

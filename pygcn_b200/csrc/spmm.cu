@@ -14,6 +14,8 @@
 //   * bias add and ReLU are fused in the epilogue.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -24,9 +26,23 @@ namespace {
 constexpr int kWarpsPerCta = 8;
 constexpr unsigned kFull = 0xffffffffu;
 
-__device__ __forceinline__ float4 ldg_f4(const float* p) {
-  return __ldg(reinterpret_cast<const float4*>(p));
-}
+// The dense operand ("panel") is fp32, or -- the reduced-precision tier (<= 2e-2, BASELINE north_star) -- bf16:
+// a gathered row is then half the bytes, which is what the kernel is bound by (L2 -> SM gather traffic for
+// narrow rows, HBM for panels that do not fit L2).  Accumulation and output stay fp32.  Every 16-byte load
+// carries kElems elements and feeds kAcc float4 accumulators.
+template <bool BF16>
+struct Panel {
+  static constexpr int kElems = BF16 ? 8 : 4;
+  static constexpr int kAcc = BF16 ? 2 : 1;
+  static constexpr int kElemBytes = BF16 ? 2 : 4;
+  using elem_t = typename std::conditional<BF16, uint16_t, float>::type;
+  using vec_t = typename std::conditional<BF16, uint4, float4>::type;  // one 16-byte load
+  static __host__ __device__ __forceinline__ int chunks(int f) { return (f + kElems - 1) / kElems; }
+  static __device__ __forceinline__ vec_t ldg(const elem_t* p) { return __ldg(reinterpret_cast<const vec_t*>(p)); }
+};
+
+__device__ __forceinline__ uint4 ldg_u4(const char* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 __device__ __forceinline__ void fma4(float4& acc, float v, const float4& x) {
   acc.x = fmaf(v, x.x, acc.x);
@@ -34,18 +50,38 @@ __device__ __forceinline__ void fma4(float4& acc, float v, const float4& x) {
   acc.z = fmaf(v, x.z, acc.z);
   acc.w = fmaf(v, x.w, acc.w);
 }
+// acc[0..kAcc) += v * (the elements of one 16-byte chunk); bf16 -> fp32 is a shift / a mask
+__device__ __forceinline__ void fma_vec(float4* acc, float v, const float4& x) { fma4(acc[0], v, x); }
+__device__ __forceinline__ void fma_vec(float4* acc, float v, const uint4& x) {
+  fma4(acc[0], v, make_float4(__uint_as_float(x.x << 16), __uint_as_float(x.x & 0xffff0000u),
+                              __uint_as_float(x.y << 16), __uint_as_float(x.y & 0xffff0000u)));
+  fma4(acc[1], v, make_float4(__uint_as_float(x.z << 16), __uint_as_float(x.z & 0xffff0000u),
+                              __uint_as_float(x.w << 16), __uint_as_float(x.w & 0xffff0000u)));
+}
+template <bool BF16>
+__device__ __forceinline__ void fma_chunk(float4* acc, float v, const uint4& x) {
+  if constexpr (!BF16) {
+    fma4(acc[0], v, make_float4(__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w)));
+  } else {
+    fma4(acc[0], v, make_float4(__uint_as_float(x.x << 16), __uint_as_float(x.x & 0xffff0000u),
+                                __uint_as_float(x.y << 16), __uint_as_float(x.y & 0xffff0000u)));
+    fma4(acc[1], v, make_float4(__uint_as_float(x.z << 16), __uint_as_float(x.z & 0xffff0000u),
+                                __uint_as_float(x.w << 16), __uint_as_float(x.w & 0xffff0000u)));
+  }
+}
 
 // U gathered rows per lane in flight: all loads are issued before the first FMA (memory-level
 // parallelism is what this kernel lives on).  Entry s = (j + u) * G + slot of the current block
 // of 32; lanes past the end of the row carry v = 0 / c = 0 and are never asked for here.
-template <int LPR, int CH, int U>
-__device__ __forceinline__ void gather_batch(float4 (&acc)[CH], int c, float v, int j, int slot,
-                                             const float* __restrict__ b, const int (&qoff)[CH],
-                                             int64_t ldb) {
+template <int LPR, int CH, int U, bool BF16>
+__device__ __forceinline__ void gather_batch(float4 (&acc)[CH * Panel<BF16>::kAcc], int c, float v, int j, int slot,
+                                             const typename Panel<BF16>::elem_t* __restrict__ b,
+                                             const int (&qoff)[CH], int64_t ldb) {
   constexpr int G = 32 / LPR;
+  constexpr int A = Panel<BF16>::kAcc;
   int cc[U];
   float vv[U];
-  float4 x[U][CH];
+  typename Panel<BF16>::vec_t x[U][CH];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int s = (j + u) * G + slot;
@@ -54,26 +90,27 @@ __device__ __forceinline__ void gather_batch(float4 (&acc)[CH], int c, float v, 
   }
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    const float* rowp = b + (int64_t)cc[u] * ldb;
+    const typename Panel<BF16>::elem_t* rowp = b + (int64_t)cc[u] * ldb;
 #pragma unroll
-    for (int k = 0; k < CH; ++k) x[u][k] = ldg_f4(rowp + qoff[k]);
+    for (int k = 0; k < CH; ++k) x[u][k] = Panel<BF16>::ldg(rowp + qoff[k]);
   }
 #pragma unroll
   for (int u = 0; u < U; ++u)
 #pragma unroll
-    for (int k = 0; k < CH; ++k) fma4(acc[k], vv[u], x[u][k]);
+    for (int k = 0; k < CH; ++k) fma_vec(&acc[k * A], vv[u], x[u][k]);
 }
 
 // Accumulate stored entries [start, end) of one row into acc (per-lane partial sums).
 // LPR lanes cover one gathered row; CH float4 chunks per lane (CH > 1 only when LPR == 32).
 // Lanes whose float4 index is past the row width read a clamped (valid) address and build a
 // value that is never stored.
-template <int LPR, int CH>
-__device__ __forceinline__ void accumulate_range(float4 (&acc)[CH], int start, int end,
+// b / ldb in elements of the panel type; nch = 16-byte chunks per panel row.
+template <int LPR, int CH, bool BF16>
+__device__ __forceinline__ void accumulate_range(float4 (&acc)[CH * Panel<BF16>::kAcc], int start, int end,
                                                  const int32_t* __restrict__ col,
                                                  const float* __restrict__ val,
-                                                 const float* __restrict__ b, int64_t ldb, int f4,
-                                                 int lane) {
+                                                 const typename Panel<BF16>::elem_t* __restrict__ b, int64_t ldb,
+                                                 int nch, int lane) {
   constexpr int G = 32 / LPR;
   constexpr int U = (LPR * CH >= 64) ? (8 / CH > 0 ? 8 / CH : 1) : (LPR < 8 ? LPR : 8);
   const int slot = lane / LPR;
@@ -81,7 +118,7 @@ __device__ __forceinline__ void accumulate_range(float4 (&acc)[CH], int start, i
   // chunk k of this lane is float4 index k*LPR + sub; clamp so that every chunk is readable
   int qoff[CH];
 #pragma unroll
-  for (int k = 0; k < CH; ++k) qoff[k] = 4 * min(k * LPR + sub, f4 - 1);
+  for (int k = 0; k < CH; ++k) qoff[k] = Panel<BF16>::kElems * min(k * LPR + sub, nch - 1);
   int c = 0;
   float v = 0.f;
   if (start + lane < end) {
@@ -99,16 +136,16 @@ __device__ __forceinline__ void accumulate_range(float4 (&acc)[CH], int start, i
     const int cnt = min(32, end - base);
     const int jmax = (cnt + G - 1) / G;  // entries past cnt have v = 0, c = 0: harmless
     int j = 0;
-    for (; j + U <= jmax; j += U) gather_batch<LPR, CH, U>(acc, c, v, j, slot, b, qoff, ldb);
-    if (U > 4 && j + 4 <= jmax) { gather_batch<LPR, CH, (U > 4 ? 4 : 1)>(acc, c, v, j, slot, b, qoff, ldb); j += 4; }
-    if (U > 2 && j + 2 <= jmax) { gather_batch<LPR, CH, (U > 2 ? 2 : 1)>(acc, c, v, j, slot, b, qoff, ldb); j += 2; }
-    if (U > 1 && j < jmax) { gather_batch<LPR, CH, 1>(acc, c, v, j, slot, b, qoff, ldb); j += 1; }
+    for (; j + U <= jmax; j += U) gather_batch<LPR, CH, U, BF16>(acc, c, v, j, slot, b, qoff, ldb);
+    if (U > 4 && j + 4 <= jmax) { gather_batch<LPR, CH, (U > 4 ? 4 : 1), BF16>(acc, c, v, j, slot, b, qoff, ldb); j += 4; }
+    if (U > 2 && j + 2 <= jmax) { gather_batch<LPR, CH, (U > 2 ? 2 : 1), BF16>(acc, c, v, j, slot, b, qoff, ldb); j += 2; }
+    if (U > 1 && j < jmax) { gather_batch<LPR, CH, 1, BF16>(acc, c, v, j, slot, b, qoff, ldb); j += 1; }
     c = cn;
     v = vn;
   }
 }
 
-template <int LPR, int CH>
+template <int LPR, int CH>  // CH = number of float4 accumulators per lane here
 __device__ __forceinline__ void reduce_slots(float4 (&acc)[CH]) {
 #pragma unroll
   for (int off = LPR; off < 32; off <<= 1) {
@@ -153,30 +190,42 @@ __device__ __forceinline__ void store_row_chunk(float* out_row, int64_t row, int
   }
 }
 
-// One warp per row.  Rows of the long bin are skipped when skip_long is set.
-template <int LPR, int CH>
+// the kAcc float4 results of 16-byte panel chunk q -> output columns [q * kElems, (q + 1) * kElems)
+template <bool BF16>
+__device__ __forceinline__ void store_panel_chunk(float* out_row, int64_t row, int q, int f, bool vec_out,
+                                                  const float4* acc, const Epilogue& ep) {
+  constexpr int A = Panel<BF16>::kAcc;
+#pragma unroll
+  for (int t = 0; t < A; ++t)
+    if (4 * (q * A + t) < f) store_row_chunk(out_row, row, q * A + t, f, vec_out, acc[t], ep);
+}
+
+// One warp per row.  Rows of the long bin are skipped when skip_long is set.  b / ldb in elements of the panel type.
+template <int LPR, int CH, bool BF16>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 spmm_rows_vec_kernel(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                     const float* __restrict__ val, const float* __restrict__ b, int64_t ldb, int f,
+                     const float* __restrict__ val, const void* __restrict__ b, int64_t ldb, int f,
                      Epilogue ep, float* __restrict__ out, int64_t ldo, int vec_out, int skip_long) {
+  constexpr int A = Panel<BF16>::kAcc;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (row >= n_rows) return;
   const int start = __ldg(rowptr + row);
   const int end = __ldg(rowptr + row + 1);
   if (skip_long && end - start >= kLongRowThreshold) return;
-  const int f4 = (f + 3) >> 2;
-  float4 acc[CH];
+  const int nch = Panel<BF16>::chunks(f);
+  float4 acc[CH * A];
 #pragma unroll
-  for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  accumulate_range<LPR, CH>(acc, start, end, col, val, b, ldb, f4, lane);
-  reduce_slots<LPR, CH>(acc);
+  for (int k = 0; k < CH * A; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  accumulate_range<LPR, CH, BF16>(acc, start, end, col, val, reinterpret_cast<const typename Panel<BF16>::elem_t*>(b), ldb,
+                                  nch, lane);
+  reduce_slots<LPR, CH * A>(acc);
   if (lane < LPR) {
     float* out_row = out + (int64_t)row * ldo;
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
       const int q = k * LPR + lane;
-      if (q < f4) store_row_chunk(out_row, row, q, f, vec_out, acc[k], ep);
+      if (q < nch) store_panel_chunk<BF16>(out_row, row, q, f, vec_out, &acc[k * A], ep);
     }
   }
 }
@@ -203,19 +252,20 @@ constexpr int kStageEntries = 32;
 // ptxas interleaves gathers and FFMAs assuming a short load latency and keeps 2-3 rows in flight per
 // lane; the L2 gather rate needs several hundred rows in flight per SM (tools/microbench/gather_bw.cu).
 template <int U>
-__device__ __forceinline__ uint32_t all_landed(const float4 (&x)[U], uint32_t never) {
+__device__ __forceinline__ uint32_t all_landed(const uint4 (&x)[U], uint32_t never) {
   uint32_t g = 0u;
 #pragma unroll
-  for (int u = 0; u < U; ++u) g |= __float_as_uint(x[u].w);
+  for (int u = 0; u < U; ++u) g |= x[u].w;
   return g & never;
 }
 
-template <int LPR, int U, int MINB>
+template <int LPR, int U, int MINB, bool BF16>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
 spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* __restrict__ pair, int last_pair,
-                  const float* __restrict__ b, uint32_t ldb_bytes, int f, Epilogue ep, float* __restrict__ out,
+                  const void* __restrict__ b, uint32_t ldb_bytes, int f, Epilogue ep, float* __restrict__ out,
                   int64_t ldo, int vec_out, int skip_long, uint32_t never) {
   constexpr int G = 32 / LPR;
+  constexpr int A = Panel<BF16>::kAcc;
   constexpr int E = (LPR >= 4) ? kStageEntries : kStageEntries / 2;  // static shared memory stays < 48 KB
   constexpr int NC = E / (2 * LPR);  // 16-byte copies (two pairs) per lane and stage
   static_assert(E % U == 0 && U % 2 == 0 && NC >= 1, "batches of U entries must divide the stage");
@@ -246,7 +296,7 @@ spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* _
   }
   uint64_t bl;  // lane's base: column chunk `sub` of row 0 (lanes past the width read a clamped, valid chunk)
   {
-    bl = reinterpret_cast<uint64_t>(b) + 16u * (uint32_t)min(sub, ((f + 3) >> 2) - 1);
+    bl = reinterpret_cast<uint64_t>(b) + 16u * (uint32_t)min(sub, Panel<BF16>::chunks(f) - 1);
     asm volatile("" : "+l"(bl));  // keep it in a register pair (ptxas would rebuild it per gather)
   }
   uint32_t cur = smem_u32(&stage[threadIdx.x >> 5][((threadIdx.x & 31) / LPR)][0][0]);
@@ -271,14 +321,16 @@ spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* _
     return q;
   };
   auto gather = [&](uint32_t c) {  // one IMAD.WIDE.U32: c * row bytes + lane base
-    float4 x;
-    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+    uint4 x;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
                  : "l"(bl + (uint64_t)c * ldb_bytes));
     return x;
   };
   fetch(cur, left - 2 * sub);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc[A];
+#pragma unroll
+  for (int t = 0; t < A; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
   bool first = true;
   while (!__all_sync(kFull, left <= 0)) {
     fetch(nxt, left - E - 2 * sub);  // next stage flies while this one is consumed
@@ -299,7 +351,7 @@ spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* _
       // gathers of row 0 per row instead of per-gather predicates
       if (j < cnt) {
         uint4 q[U / 2];
-        float4 x[U];
+        uint4 x[U];
 #pragma unroll
         for (int h = 0; h < U / 2; ++h) q[h] = pairs_at(j + 2 * h);  // j + u < E because U divides E
 #pragma unroll
@@ -308,14 +360,17 @@ spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* _
           x[2 * h + 1] = gather(q[h].z);
         }
         const uint32_t zero = all_landed(x, never);
-        acc.x = __uint_as_float(__float_as_uint(acc.x) | zero);
-        acc.y = __uint_as_float(__float_as_uint(acc.y) | zero);
-        acc.z = __uint_as_float(__float_as_uint(acc.z) | zero);
-        acc.w = __uint_as_float(__float_as_uint(acc.w) | zero);
+#pragma unroll
+        for (int t = 0; t < A; ++t) {
+          acc[t].x = __uint_as_float(__float_as_uint(acc[t].x) | zero);
+          acc[t].y = __uint_as_float(__float_as_uint(acc[t].y) | zero);
+          acc[t].z = __uint_as_float(__float_as_uint(acc[t].z) | zero);
+          acc[t].w = __uint_as_float(__float_as_uint(acc[t].w) | zero);
+        }
 #pragma unroll
         for (int h = 0; h < U / 2; ++h) {
-          fma4(acc, __uint_as_float(q[h].y), x[2 * h]);
-          fma4(acc, __uint_as_float(q[h].w), x[2 * h + 1]);
+          fma_chunk<BF16>(acc, __uint_as_float(q[h].y), x[2 * h]);
+          fma_chunk<BF16>(acc, __uint_as_float(q[h].w), x[2 * h + 1]);
         }
       }
     }
@@ -329,9 +384,9 @@ spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* _
   {
     const int lane = threadIdx.x & 31;
     const int row = (blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * G + lane / LPR;
-    if (row >= n_rows || sub >= ((f + 3) >> 2)) return;
+    if (row >= n_rows || sub >= Panel<BF16>::chunks(f)) return;
     if (skip_long && __ldg(rowptr + row + 1) - __ldg(rowptr + row) >= kLongRowThreshold) return;
-    store_row_chunk(out + (int64_t)row * ldo, row, sub, f, vec_out, acc, ep);
+    store_panel_chunk<BF16>(out + (int64_t)row * ldo, row, sub, f, vec_out, acc, ep);
   }
 }
 
@@ -481,13 +536,14 @@ spmm_rows_tma_kernel(int n_rows, const int32_t* __restrict__ rowptr, const int32
 }
 
 // Long-row bin, phase 1: one warp per chunk of kLongChunk stored entries -> partial row.
-template <int LPR, int CH>
+template <int LPR, int CH, bool BF16>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 spmm_long_partial_kernel(int n_long_rows, int n_chunks, const int32_t* __restrict__ long_rows,
                          const int32_t* __restrict__ long_chunk_ptr,
                          const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                         const float* __restrict__ val, const float* __restrict__ b, int64_t ldb,
+                         const float* __restrict__ val, const void* __restrict__ b, int64_t ldb,
                          int f, float* __restrict__ partial, int ldp) {
+  constexpr int A = Panel<BF16>::kAcc;
   const int lane = threadIdx.x & 31;
   const int ch = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (ch >= n_chunks) return;
@@ -502,18 +558,22 @@ spmm_long_partial_kernel(int n_long_rows, int n_chunks, const int32_t* __restric
   const int row_end = __ldg(rowptr + row + 1);
   const int start = row_start + local * kLongChunk;
   const int end = min(start + kLongChunk, row_end);
+  const int nch = Panel<BF16>::chunks(f);
   const int f4 = (f + 3) >> 2;
-  float4 acc[CH];
+  float4 acc[CH * A];
 #pragma unroll
-  for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  accumulate_range<LPR, CH>(acc, start, end, col, val, b, ldb, f4, lane);
-  reduce_slots<LPR, CH>(acc);
+  for (int k = 0; k < CH * A; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  accumulate_range<LPR, CH, BF16>(acc, start, end, col, val, reinterpret_cast<const typename Panel<BF16>::elem_t*>(b), ldb,
+                                  nch, lane);
+  reduce_slots<LPR, CH * A>(acc);
   if (lane < LPR) {
     float* prow = partial + (int64_t)ch * ldp;
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
       const int q = k * LPR + lane;
-      if (q < f4) *reinterpret_cast<float4*>(prow + 4 * q) = acc[k];
+#pragma unroll
+      for (int t = 0; t < A; ++t)
+        if (q * A + t < f4) *reinterpret_cast<float4*>(prow + 4 * (q * A + t)) = acc[k * A + t];
     }
   }
 }
@@ -604,12 +664,12 @@ bool spmm_use_tma() { tuning_init(); return g_spmm_kernel == 3; }
 int spmm_group_variant() { tuning_init(); return g_group_variant; }
 
 // Long-row bin: chunk partials, then the ordered fix-up (both no-ops when the bin is empty).
-template <int LPR, int CH>
-int launch_long(const CsrView& a, const float* b, int64_t ldb, int f, const Epilogue& ep, float* out,
+template <int LPR, int CH, bool BF16>
+int launch_long(const CsrView& a, const void* b, int64_t ldb, int f, const Epilogue& ep, float* out,
                 int64_t ldo, float* partial, int ldp, cudaStream_t st) {
   if (a.n_long_rows == 0) return GCNB_OK;
   const int g1 = (int)ceil_div(a.n_long_chunks, kWarpsPerCta);
-  spmm_long_partial_kernel<LPR, CH><<<g1, kWarpsPerCta * 32, 0, st>>>(
+  spmm_long_partial_kernel<LPR, CH, BF16><<<g1, kWarpsPerCta * 32, 0, st>>>(
       (int)a.n_long_rows, (int)a.n_long_chunks, a.long_rows, a.long_chunk_ptr, a.rowptr, a.col, a.val, b, ldb, f,
       partial, ldp);
   GCNB_LAUNCH_CHECK();
@@ -620,9 +680,10 @@ int launch_long(const CsrView& a, const float* b, int64_t ldb, int f, const Epil
   return GCNB_OK;
 }
 
-template <int LPR, int CH>
-int launch_vec(const CsrView& a, const float* b, int64_t ldb, int f, const Epilogue& ep, float* out,
+template <int LPR, int CH, bool BF16>
+int launch_vec(const CsrView& a, const void* b, int64_t ldb, int f, const Epilogue& ep, float* out,
                int64_t ldo, bool vec_out, float* partial, int ldp, cudaStream_t st) {
+  constexpr int kEB = Panel<BF16>::kElemBytes;
   const bool has_long = a.n_long_rows > 0;
   const int grid = (int)ceil_div(a.n_rows, kWarpsPerCta);
   if constexpr (LPR >= 2 && LPR <= 16 && CH == 1) {
@@ -632,11 +693,11 @@ int launch_vec(const CsrView& a, const float* b, int64_t ldb, int f, const Epilo
     const bool shape_ok = a.n_rows >= (int64_t)kNumSMs * 16 * G && a.nnz <= a.n_rows * 384;
     tuning_init();
     const bool want_group = g_spmm_kernel == 2 || (g_spmm_kernel == 0 && (shape_ok || g_group_variant >= 0));
-    if (grid > 0 && a.pair != nullptr && want_group && ldb * 4 < (1ll << 32)) {
+    if (grid > 0 && a.pair != nullptr && want_group && ldb * kEB < (1ll << 32)) {
       const int ggrid = (int)ceil_div(a.n_rows, (int64_t)kWarpsPerCta * G);
 #define GCNB_GROUP_LAUNCH(U_, MINB_)                                                                       \
-  spmm_group_kernel<LPR, U_, MINB_><<<ggrid, kWarpsPerCta * 32, 0, st>>>(                               \
-      (int)a.n_rows, a.rowptr, a.pair, (int)(a.nnz & ~1ll), b, (uint32_t)(ldb * 4), f, ep, out, ldo,  \
+  spmm_group_kernel<LPR, U_, MINB_, BF16><<<ggrid, kWarpsPerCta * 32, 0, st>>>(                         \
+      (int)a.n_rows, a.rowptr, a.pair, (int)(a.nnz & ~1ll), b, (uint32_t)(ldb * kEB), f, ep, out, ldo, \
       vec_out ? 1 : 0, has_long ? 1 : 0, 0u)
       // (gathers in flight per lane, CTAs per SM the register budget must allow).  Measured on B200
       // (gpurun_out/probe_sweep8.log): 128/256-byte rows like many warps with 4 gathers each, narrower
@@ -652,22 +713,23 @@ int launch_vec(const CsrView& a, const float* b, int64_t ldb, int f, const Epilo
       }
 #undef GCNB_GROUP_LAUNCH
       GCNB_LAUNCH_CHECK();
-      return launch_long<LPR, CH>(a, b, ldb, f, ep, out, ldo, partial, ldp, st);
+      return launch_long<LPR, CH, BF16>(a, b, ldb, f, ep, out, ldo, partial, ldp, st);
     }
   }
-  if (grid > 0 && spmm_use_tma()) {
+  if (grid > 0 && !BF16 && spmm_use_tma()) {
     // persistent: 6 CTAs per SM walk the rows with a per-warp TMA ring for the index/value streams
     int pgrid = 6 * kNumSMs;
     if (pgrid > grid) pgrid = grid;
     spmm_rows_tma_kernel<LPR, CH><<<pgrid, kWarpsPerCta * 32, 0, st>>>(
-        (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, f, ep, out, ldo, vec_out ? 1 : 0, has_long ? 1 : 0);
+        (int)a.n_rows, a.rowptr, a.col, a.val, reinterpret_cast<const float*>(b), ldb, f, ep, out, ldo, vec_out ? 1 : 0,
+        has_long ? 1 : 0);
     GCNB_LAUNCH_CHECK();
   } else if (grid > 0) {
-    spmm_rows_vec_kernel<LPR, CH><<<grid, kWarpsPerCta * 32, 0, st>>>(
+    spmm_rows_vec_kernel<LPR, CH, BF16><<<grid, kWarpsPerCta * 32, 0, st>>>(
         (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, f, ep, out, ldo, vec_out ? 1 : 0, has_long ? 1 : 0);
     GCNB_LAUNCH_CHECK();
   }
-  return launch_long<LPR, CH>(a, b, ldb, f, ep, out, ldo, partial, ldp, st);
+  return launch_long<LPR, CH, BF16>(a, b, ldb, f, ep, out, ldo, partial, ldp, st);
 }
 
 inline int partial_ld(int64_t f) { return (int)(ceil_div(f, 4) * 4); }
@@ -693,8 +755,13 @@ size_t spmm_workspace_bytes(const CsrView& a, int64_t f) {
   return (size_t)a.n_long_chunks * (size_t)partial_ld(f) * sizeof(float);
 }
 
-int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const Epilogue& ep, float* out,
-                int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st) {
+namespace {
+template <bool BF16>
+int spmm_launch_t(const CsrView& a, const void* bv, int64_t ldb, int64_t f, const Epilogue& ep, float* out,
+                  int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using elem_t = typename std::conditional<BF16, uint16_t, float>::type;
+  constexpr int kE = Panel<BF16>::kElems;
+  const elem_t* b = reinterpret_cast<const elem_t*>(bv);
   GCNB_REQUIRE(f > 0 && f <= (1 << 20), "spmm: feature width %lld out of range", (long long)f);
   GCNB_REQUIRE(ldb >= f && ldo >= f, "spmm: leading dimension smaller than width");
   GCNB_REQUIRE(a.n_rows < (1ll << 31), "spmm: too many rows");
@@ -705,38 +772,54 @@ int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const 
                "spmm: workspace too small (%zu < %zu) or unaligned", ws_bytes, need);
   float* partial = reinterpret_cast<float*>(ws);
   const int ldp = partial_ld(f);
-  const int f4 = (int)ceil_div(f, 4);
-  // vector gathers need 16-byte aligned rows of b that are readable up to f4*4 floats
-  const bool vec_in = aligned16(b) && (ldb % 4 == 0) && (ldb >= (int64_t)f4 * 4);
+  const int nch = (int)ceil_div(f, kE);  // 16-byte chunks per panel row
+  // vector gathers need 16-byte aligned rows of b that are readable up to nch whole chunks
+  const bool vec_in = aligned16(b) && (ldb % kE == 0) && (ldb >= (int64_t)nch * kE);
   const bool vec_out = aligned16(out) && (ldo % 4 == 0) && (f % 4 == 0);
   if (!vec_in) {
-    // generic path handles long rows too (a warp walks the whole row)
-    const int grid = (int)ceil_div(a.n_rows, kWarpsPerCta);
-    spmm_rows_scalar_kernel<<<grid, kWarpsPerCta * 32, 0, st>>>(
-        (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, (int)f, ep, out, ldo);
-    GCNB_LAUNCH_CHECK();
-    return GCNB_OK;
+    if constexpr (BF16) {
+      GCNB_REQUIRE(false, "spmm(bf16 panel): rows must be 16-byte aligned with ld a multiple of 8 and >= 8*ceil(f/8)");
+    } else {
+      // generic path handles long rows too (a warp walks the whole row)
+      const int grid = (int)ceil_div(a.n_rows, kWarpsPerCta);
+      spmm_rows_scalar_kernel<<<grid, kWarpsPerCta * 32, 0, st>>>(
+          (int)a.n_rows, a.rowptr, a.col, a.val, b, ldb, (int)f, ep, out, ldo);
+      GCNB_LAUNCH_CHECK();
+      return GCNB_OK;
+    }
   }
 #define GCNB_SPMM_CASE(LPR, CH) \
-  return launch_vec<LPR, CH>(a, b, ldb, (int)f, ep, out, ldo, vec_out, partial, ldp, st)
-  if (f4 <= 1) GCNB_SPMM_CASE(1, 1);
-  if (f4 <= 2) GCNB_SPMM_CASE(2, 1);
-  if (f4 <= 4) GCNB_SPMM_CASE(4, 1);
-  if (f4 <= 8) GCNB_SPMM_CASE(8, 1);
-  if (f4 <= 16) GCNB_SPMM_CASE(16, 1);
-  if (f4 <= 32) GCNB_SPMM_CASE(32, 1);
-  if (f4 <= 64) GCNB_SPMM_CASE(32, 2);
-  if (f4 <= 128) GCNB_SPMM_CASE(32, 4);
+  return launch_vec<LPR, CH, BF16>(a, b, ldb, (int)f, ep, out, ldo, vec_out, partial, ldp, st)
+  if (nch <= 1) GCNB_SPMM_CASE(1, 1);
+  if (nch <= 2) GCNB_SPMM_CASE(2, 1);
+  if (nch <= 4) GCNB_SPMM_CASE(4, 1);
+  if (nch <= 8) GCNB_SPMM_CASE(8, 1);
+  if (nch <= 16) GCNB_SPMM_CASE(16, 1);
+  if (nch <= 32) GCNB_SPMM_CASE(32, 1);
+  if (nch <= 64) GCNB_SPMM_CASE(32, 2);
+  if (nch <= 128) GCNB_SPMM_CASE(32, 4);
 #undef GCNB_SPMM_CASE
-  // wider than 512 floats: column panels of 512
-  for (int64_t f0 = 0; f0 < f; f0 += 512) {
-    const int64_t fw = (f - f0 < 512) ? (f - f0) : 512;
+  // wider than 128 chunks: column panels of 128 chunks (512 floats / 1024 bf16)
+  const int64_t pw = 128 * kE;
+  for (int64_t f0 = 0; f0 < f; f0 += pw) {
+    const int64_t fw = (f - f0 < pw) ? (f - f0) : pw;
     Epilogue e2 = ep;
     if (e2.bias) e2.bias += f0;
     if (e2.mask) e2.mask += f0;
-    GCNB_TRY(spmm_launch(a, b + f0, ldb, fw, e2, out + f0, ldo, ws, ws_bytes, st));
+    GCNB_TRY(spmm_launch_t<BF16>(a, b + f0, ldb, fw, e2, out + f0, ldo, ws, ws_bytes, st));
   }
   return GCNB_OK;
+}
+}  // namespace
+
+int spmm_launch(const CsrView& a, const float* b, int64_t ldb, int64_t f, const Epilogue& ep, float* out,
+                int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st) {
+  return spmm_launch_t<false>(a, b, ldb, f, ep, out, ldo, ws, ws_bytes, st);
+}
+
+int spmm_bf16_launch(const CsrView& a, const uint16_t* b, int64_t ldb, int64_t f, const Epilogue& ep, float* out,
+                     int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st) {
+  return spmm_launch_t<true>(a, b, ldb, f, ep, out, ldo, ws, ws_bytes, st);
 }
 
 }  // namespace gcnb

@@ -17,7 +17,9 @@ from torch.autograd.function import once_differentiable
 from . import _lib
 from .graph import Graph, _require_cuda, _stream_ptr, as_graph
 
-_PRECISIONS = {"fp32": _lib.GEMM_FP32, "tf32x3": _lib.GEMM_TF32X3, "auto": _lib.GEMM_AUTO}
+# "bf16": bf16 panels for the SpMM (the 2e-2 tier); its dense products, and the layer on a dense-route or
+# batched input, use the "auto" kernels
+_PRECISIONS = {"fp32": _lib.GEMM_FP32, "tf32x3": _lib.GEMM_TF32X3, "auto": _lib.GEMM_AUTO, "bf16": _lib.GEMM_AUTO}
 
 
 def _ld4(f):
@@ -139,6 +141,90 @@ class _GCNLayerFn(torch.autograd.Function):
         if st:
             _lib.check(st, "gcnb_layer_backward")
         return dx, dw, db, None, None, None, None, None
+
+
+def _ld8(f):
+    return (f + 7) // 8 * 8
+
+
+class _GCNLayerBf16Fn(torch.autograd.Function):
+    """The layer with bf16 PANELS (precision="bf16", the <= 2e-2 tier of BASELINE's north_star): the operand the
+    SpMM gathers -- support = X W forward, the (masked) upstream gradient backward -- is rounded to bf16 once
+    (gcnb_to_bf16) and gathered at half the bytes per row (gcnb_spmm_bf16); X, W, the dense products, the
+    accumulation of the SpMM, bias, ReLU and every output stay fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, graph, relu):
+        lib = _lib.load()
+        dev = x.device
+        fin, fout = weight.shape
+        xr = _rowmajor(x)
+        w = weight.contiguous()
+        b = bias.contiguous() if bias is not None else None
+        n = graph.n_cols
+        support = torch.empty((n, _ld4(fout)), dtype=torch.float32, device=dev)
+        panel = torch.empty((n, _ld8(fout)), dtype=torch.bfloat16, device=dev)
+        out = torch.empty((graph.n_rows, fout), dtype=torch.float32, device=dev)
+        auto = _lib.GEMM_AUTO
+        with _on_device(dev):
+            sp = _stream_ptr(dev)
+            ws = _ws(lib.gcnb_gemm_workspace_bytes(n, fout, fin, auto), dev)
+            _lib.check(lib.gcnb_gemm(n, fout, fin, _ptr(xr), _ld(xr), 1, _ptr(w), fout, 1, _ptr(support), _ld4(fout), auto,
+                                     _ptr(ws), ws.numel(), sp), "gcnb_gemm")
+            _lib.check(lib.gcnb_to_bf16(n, fout, _ptr(support), _ld4(fout), _ptr(panel), _ld8(fout), sp), "gcnb_to_bf16")
+            ws2 = _ws(lib.gcnb_spmm_workspace_bytes(graph._h, 0, fout), dev)
+            _lib.check(lib.gcnb_spmm_bf16(graph._h, _lib.SPMM_RELU if relu else 0, _ptr(panel), _ld8(fout), fout, _ptr(b),
+                                          _ptr(out), fout, _ptr(ws2), ws2.numel(), sp), "gcnb_spmm_bf16")
+        ctx.graph, ctx.relu, ctx.has_bias = graph, relu, bias is not None
+        ctx.save_for_backward(xr, w, out if relu else None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        lib = _lib.load()
+        xr, w, y = ctx.saved_tensors
+        graph = ctx.graph
+        dev = g.device
+        fin, fout = w.shape
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_db = ctx.has_bias and ctx.needs_input_grad[2]
+        gr = _rowmajor(g)
+        auto = _lib.GEMM_AUTO
+        dx = dw = db = None
+        with _on_device(dev):
+            sp = _stream_ptr(dev)
+            gsrc = gr
+            if ctx.relu or need_db:
+                gm = torch.empty((graph.n_rows, fout), dtype=torch.float32, device=dev) if ctx.relu else None
+                db = torch.empty((fout,), dtype=torch.float32, device=dev)
+                ws = _ws(lib.gcnb_colsum_workspace_bytes(graph.n_rows, fout), dev)
+                _lib.check(lib.gcnb_colsum(graph.n_rows, fout, _ptr(gr), _ld(gr), _ptr(y) if ctx.relu else None, fout,
+                                           _ptr(gm), fout, _ptr(db), _ptr(ws), ws.numel(), sp), "gcnb_colsum")
+                if gm is not None:
+                    gsrc = gm
+                if not need_db:
+                    db = None
+            if need_dw or need_dx:
+                panel = torch.empty((graph.n_rows, _ld8(fout)), dtype=torch.bfloat16, device=dev)
+                _lib.check(lib.gcnb_to_bf16(graph.n_rows, fout, _ptr(gsrc), _ld(gsrc), _ptr(panel), _ld8(fout), sp),
+                           "gcnb_to_bf16")
+                ds = torch.empty((graph.n_cols, _ld4(fout)), dtype=torch.float32, device=dev)
+                ws = _ws(lib.gcnb_spmm_workspace_bytes(graph._h, _lib.SPMM_TRANSPOSE, fout), dev)
+                _lib.check(lib.gcnb_spmm_bf16(graph._h, _lib.SPMM_TRANSPOSE, _ptr(panel), _ld8(fout), fout, None, _ptr(ds),
+                                              _ld4(fout), _ptr(ws), ws.numel(), sp), "gcnb_spmm_bf16(transpose)")
+                n = graph.n_cols
+                if need_dw:
+                    dw = torch.empty((fin, fout), dtype=torch.float32, device=dev)
+                    ws = _ws(lib.gcnb_gemm_workspace_bytes(fin, fout, n, auto), dev)
+                    _lib.check(lib.gcnb_gemm(fin, fout, n, _ptr(xr), 1, _ld(xr), _ptr(ds), _ld4(fout), 1, _ptr(dw), fout,
+                                             auto, _ptr(ws), ws.numel(), sp), "gcnb_gemm(dW)")
+                if need_dx:
+                    dx = torch.empty((n, fin), dtype=torch.float32, device=dev)
+                    ws = _ws(lib.gcnb_gemm_workspace_bytes(n, fin, fout, auto), dev)
+                    _lib.check(lib.gcnb_gemm(n, fin, fout, _ptr(ds), _ld4(fout), 1, _ptr(w), 1, fout, _ptr(dx), fin, auto,
+                                             _ptr(ws), ws.numel(), sp), "gcnb_gemm(dX)")
+        return dx, dw, db, None, None
 
 
 class _GCNLayerBatchedFn(torch.autograd.Function):
@@ -274,6 +360,10 @@ def gcn_layer(input, adj, weight, bias=None, relu=False, precision="auto", dropo
             return input.new_empty((0, graph.n_rows, weight.shape[1]))
         return _GCNLayerBatchedFn.apply(input, weight, bias, graph, bool(relu), _PRECISIONS[precision])
     _check_layer_args(input, graph, weight, bias)
+    if precision == "bf16" and not graph.dense_route:
+        if dropout_mask is not None:
+            raise NotImplementedError("the fused dropout mask is not available in the bf16 panel tier")
+        return _GCNLayerBf16Fn.apply(input, weight, bias, graph, bool(relu))
     mask, scale = None, 1.0
     if dropout_mask is not None:
         if not 0.0 <= dropout_p < 1.0:

@@ -24,7 +24,8 @@ class GraphConvolution(Module):
       dropout    -- p of a dropout fused after the (optional) ReLU, active in training mode only
                     (upstream pygcn applies F.dropout to the layer output; the fork commented it out)
       precision  -- "auto" (default: tcgen05 3xTF32 when the product is large enough, fp32 CUDA
-                    cores otherwise), "tf32x3" or "fp32" for the dense products
+                    cores otherwise), "tf32x3" or "fp32" for the dense products; "bf16" = the reduced
+                    tier (<= 2e-2): the panels the SpMM gathers are rounded to bf16, everything else fp32
     """
 
     def __init__(self, in_features, out_features, bias=True, *, fuse_relu=False, dropout=0.0, precision="auto"):

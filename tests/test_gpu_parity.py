@@ -479,6 +479,138 @@ def test_layer_vs_oracle_widths_and_long_rows(P, fin, fout, spmm_kernel):
     assert err(layer2.weight.grad, dw2) < TOL and err(layer2.bias.grad, db2) < TOL and err(xt2.grad, dx2) < TOL
 
 
+# ------------------------------------------------------------------ bf16 panel tier (north_star: 2e-2)
+TOL_BF16 = 2e-2
+
+
+def _to_bf16(P, src, ld_dst=None):
+    import ctypes
+
+    from pygcn_b200 import _lib
+
+    lib = _lib.load()
+    n, f = src.shape
+    ld = ld_dst or (f + 7) // 8 * 8
+    dst = torch.full((n, ld), float("nan"), dtype=torch.bfloat16, device=src.device)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.gcnb_to_bf16(n, f, src.data_ptr(), src.stride(0), dst.data_ptr(), ld, st), "gcnb_to_bf16")
+    return dst
+
+
+def _spmm_raw(P, gr, dense, f, bf16, flags=0, bias=None):
+    import ctypes
+
+    from pygcn_b200 import _lib
+
+    lib = _lib.load()
+    rows = gr.n_cols if flags & _lib.SPMM_TRANSPOSE else gr.n_rows
+    out = torch.empty(rows, f, device=dense.device)
+    ws = torch.empty(max(int(lib.gcnb_spmm_workspace_bytes(gr._h, flags, f)), 256), dtype=torch.uint8, device=dense.device)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    fn = lib.gcnb_spmm_bf16 if bf16 else lib.gcnb_spmm
+    _lib.check(fn(gr._h, flags, dense.data_ptr(), dense.stride(0), f, bias.data_ptr() if bias is not None else None,
+                  out.data_ptr(), f, ws.data_ptr(), ws.numel(), st), "spmm")
+    return out
+
+
+@pytest.mark.parametrize("f", [1, 3, 7, 8, 9, 32, 47, 100, 256])
+def test_to_bf16_is_round_to_nearest_even_with_zero_padding(P, f):
+    gen = torch.Generator(device=dev()).manual_seed(f)
+    wide = torch.randn(777, f + 5, generator=gen, device=dev()) * 100
+    wide[5, 0] = float("inf")
+    wide[6, 0] = 1.00390625  # exactly between two bf16 values: ties to even
+    src = wide[:, :f]  # row stride > width
+    got = _to_bf16(P, src)
+    assert torch.equal(got[:, :f].view(torch.int16), src.to(torch.bfloat16).view(torch.int16))
+    assert (got[:, f:].float() == 0).all()
+
+
+@pytest.mark.parametrize("spmm_kernel", ["auto", "rows", "group", ("group", 0), ("group", 1), ("group", 3)], indirect=True)
+@pytest.mark.parametrize("f", [1, 3, 7, 8, 24, 32, 47, 64, 100, 256, 600, 1100])
+def test_spmm_bf16_panel_equals_fp32_kernel_on_the_rounded_panel(P, f, spmm_kernel):
+    """gcnb_spmm_bf16 gathers bf16 rows and accumulates in fp32: on a panel that is already bf16-representable
+    it must agree with the fp32 kernel (1e-5: the two may pick different kernels, hence summation orders, for
+    a width), forward, transposed, with bias + ReLU, on a power-law graph with split long rows."""
+    from pygcn_b200 import _lib
+
+    n = 5000
+    src, dst = _powerlaw_graph(n, 50000, seed=f, hub_deg=2500)
+    gr = P.Graph.from_edges(cu(src), cu(dst), n)
+    assert gr.n_long_chunks > 0
+    gen = torch.Generator(device=dev()).manual_seed(f)
+    dense = torch.randn(n, f, generator=gen, device=dev())
+    bias = torch.randn(f, generator=gen, device=dev())
+    panel = _to_bf16(P, dense)
+    rounded = panel[:, :f].float().contiguous()
+    for flags, b in ((0, None), (_lib.SPMM_TRANSPOSE, None), (_lib.SPMM_RELU, bias)):
+        got = _spmm_raw(P, gr, panel, f, True, flags, b)
+        want = _spmm_raw(P, gr, rounded, f, False, flags, b)
+        assert err(got, want.cpu().numpy()) < TOL, (f, flags)
+        full = _spmm_raw(P, gr, dense, f, False, flags, b)  # the fp32 panel: the tier's bound
+        assert err(got, full.cpu().numpy()) < TOL_BF16
+
+
+def test_spmm_bf16_rejects_unaligned_panels_and_dense_route(P):
+    from pygcn_b200 import _lib
+
+    n = 300
+    src, dst = _powerlaw_graph(n, 3000, seed=1)
+    gr = P.Graph.from_edges(cu(src), cu(dst), n)
+    panel = torch.zeros(n, 40, dtype=torch.bfloat16, device=dev())
+    with pytest.raises(_lib.GcnbError):
+        _spmm_raw(P, gr, panel[:, 1:34], 33, True)  # rows not 16-byte aligned
+    dense_adj = torch.rand(64, 64, device=dev())
+    gd = P.Graph.from_torch(dense_adj)
+    assert gd.dense_route
+    with pytest.raises(_lib.GcnbError):
+        _spmm_raw(P, gd, torch.zeros(64, 8, dtype=torch.bfloat16, device=dev()), 8, True)
+    # the layer falls back to the fp32-tier kernels there instead of failing
+    layer = P.GraphConvolution(8, 8, precision="bf16").to(dev())
+    x = torch.randn(64, 8, device=dev())
+    ref = dense_adj @ (x @ layer.weight) + layer.bias
+    assert err(layer(x, gd), ref.detach().cpu().numpy()) < TOL
+
+
+@pytest.mark.parametrize("fin,fout,relu", [(64, 32, False), (64, 32, True), (16, 7, True), (100, 256, False), (33, 47, True)])
+def test_layer_bf16_tier_within_2e_2_of_the_reference_lines(P, fin, fout, relu):
+    """precision="bf16": output and every gradient within 2e-2 (norm-wise) of the reference's three lines in
+    fp32 (pygcn/layers.py:33-36 + autograd), measured ~2e-3; dX only when asked."""
+    n = 6000
+    src, dst = _powerlaw_graph(n, 60000, seed=fin + fout, hub_deg=3000)
+    gr = P.Graph.from_edges(cu(src), cu(dst), n)
+    coo = gr.to_sparse_coo()
+    torch.manual_seed(42)
+    layer = P.GraphConvolution(fin, fout, fuse_relu=relu, precision="bf16").to(dev())
+    x = cu(rng_inputs(1, (n, fin))).requires_grad_(True)
+    g = cu(rng_inputs(2, (n, fout)))
+    out = layer(x, gr)
+    out.backward(g)
+    w = layer.weight.detach().clone().requires_grad_(True)
+    b = layer.bias.detach().clone().requires_grad_(True)
+    x2 = x.detach().clone().requires_grad_(True)
+    o_pre = torch.spmm(coo, torch.mm(x2, w)) + b
+    o_ref = F.relu(o_pre) if relu else o_pre
+    gm = g
+    if relu:
+        # the ReLU mask comes from OUR forward output: entries within the tier's error of zero may sit on the
+        # other side of it than the fp32 run's (a max-norm comparison of gradients under two different masks
+        # measures the mask, not the arithmetic); everywhere else the masks must agree
+        flips = (out.detach() > 0) != (o_pre.detach() > 0)
+        assert flips.float().mean().item() < 0.01
+        assert (not flips.any()) or o_pre.detach()[flips].abs().max().item() < TOL_BF16 * o_pre.detach().abs().max().item()
+        gm = g * (out.detach() > 0)
+    o_pre.backward(gm)
+    errs = {"out": err(out, o_ref.detach().cpu().numpy()), "dW": err(layer.weight.grad, w.grad.cpu().numpy()),
+            "db": err(layer.bias.grad, b.grad.cpu().numpy()), "dX": err(x.grad, x2.grad.cpu().numpy())}
+    assert all(v < TOL_BF16 for v in errs.values()), errs
+    assert errs["out"] > 1e-6  # the panel really is bf16 (an fp32 run would sit at ~1e-7)
+    # without input grad no dX is produced
+    x3 = x.detach().clone()
+    layer.zero_grad()
+    layer(x3, gr).backward(g)
+    assert x3.grad is None and layer.weight.grad is not None
+
+
 def test_gemm_generic_strides(P):
     rs = np.random.default_rng(7)
     for (m, n, k) in [(1, 1, 1), (130, 33, 70), (64, 32, 20000), (257, 100, 16), (1000, 7, 1433)]:

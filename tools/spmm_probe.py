@@ -51,6 +51,35 @@ def main():
         assert err < 1e-5
         del csr, ref
     alg = B.algorithmic_bytes_spmm(graph.nnz, n, f)
+    if "--bf16" in sys.argv:  # the bf16 panel tier: same product, panel rounded to bf16 once
+        ld8 = (f + 7) // 8 * 8
+        panel = torch.empty(n, ld8, dtype=torch.bfloat16, device=dev)
+        _lib.check(lib.gcnb_to_bf16(n, f, ctypes.c_void_p(s.data_ptr()), f, ctypes.c_void_p(panel.data_ptr()), ld8, st), "to_bf16")
+        assert torch.equal(panel[:, :f], s.to(torch.bfloat16)), "gcnb_to_bf16 != torch's round-to-nearest-even"
+        spmm(0)
+        ref32 = out.clone()
+
+        def spmm(tflag):  # noqa: F811
+            wsb = lib.gcnb_spmm_workspace_bytes(graph._h, tflag, f)
+            ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=dev)
+            _lib.check(lib.gcnb_spmm_bf16(graph._h, tflag, ctypes.c_void_p(panel.data_ptr()), ld8, f, None,
+                                          ctypes.c_void_p(out.data_ptr()), f, ctypes.c_void_p(ws.data_ptr()), ws.numel(), st),
+                       "spmm_bf16")
+        spmm(0)
+        e = ((out - ref32).abs().max() / ref32.abs().max()).item()
+        # against the fp32 kernel on the SAME rounded panel the two must agree to fp32 rounding
+        s_keep = s
+        s = panel[:, :f].float().contiguous()
+        out2 = out.clone()
+        wsb = lib.gcnb_spmm_workspace_bytes(graph._h, 0, f)
+        ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=dev)
+        _lib.check(lib.gcnb_spmm(graph._h, 0, ctypes.c_void_p(s.data_ptr()), f, f, None, ctypes.c_void_p(out.data_ptr()), f,
+                                 ctypes.c_void_p(ws.data_ptr()), ws.numel(), st), "spmm")
+        e2 = ((out - out2).abs().max() / out.abs().max()).item()
+        print("bf16 panel: vs fp32 panel %.2e (tier bound 2e-2), vs fp32 kernel on the rounded panel %.2e" % (e, e2))
+        assert e < 2e-2 and e2 < 1e-5
+        s = s_keep
+        alg = graph.nnz * 8 + (n + 1) * 4 + n * f * 2 + n * f * 4
     for tflag, name in ((0, "fwd"), (_lib.SPMM_TRANSPOSE, "A^T")):
         ts = []
         for it in range(2 + reps):
@@ -64,7 +93,7 @@ def main():
                 ts.append(a.elapsed_time(b))
         ms = sum(ts) / len(ts)
         print("%s n=%d nnz=%d f=%d %s: %.3f ms  alg %.1f GB/s  gather %.2f TB/s  %.2f Gedges/s" % (
-            args[0] if args else "cbg", n, graph.nnz, f, name, ms, alg / ms / 1e6, graph.nnz * f * 4 / ms / 1e9,
+            args[0] if args else "cbg", n, graph.nnz, f, name, ms, alg / ms / 1e6, graph.nnz * f * (2 if "--bf16" in sys.argv else 4) / ms / 1e9,
             graph.nnz / ms / 1e6))
 
 
