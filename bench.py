@@ -416,6 +416,54 @@ def run_ours(args, wl):
             torch_cuda[form + "_ms_per_step"] = a.elapsed_time(b_) / reps
     except Exception as e:  # pragma: no cover
         torch_cuda["error"] = repr(e)
+
+    # ---- the reduced-precision tier beside the headline (north_star: 2e-2 with bf16 features): the same step with
+    # bf16 SpMM panels, timed the same way (CUDA-graph replay, L2 flushed).  Reported, never the headline value.
+    bf16_tier = None
+    try:
+        layer16 = P.GraphConvolution(fin, fout, precision="bf16").to(dev)
+        layer16.load_state_dict(layer.state_dict())
+
+        def step16():
+            layer16.weight.grad = None
+            layer16.bias.grad = None
+            o_ = layer16(x, graph)
+            o_.backward(g)
+            return o_
+        o32 = step_eager()
+        o16 = step16()
+        e16 = {"out": ((o16 - o32).abs().max() / o32.abs().max()).item(),
+               "dW": ((layer16.weight.grad - layer.weight.grad).abs().max() / layer.weight.grad.abs().max()).item(),
+               "db": ((layer16.bias.grad - layer.bias.grad).abs().max() / layer.bias.grad.abs().max()).item()}
+        del o32, o16
+        s16 = torch.cuda.Stream()
+        s16.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s16):
+            for _ in range(2):
+                step16()
+        torch.cuda.current_stream().wait_stream(s16)
+        layer16.weight.grad = None
+        layer16.bias.grad = None
+        cg16 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg16):
+            step16()
+        ev16 = []
+        for it in range(3 + args.steps):
+            flush()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            cg16.replay()
+            b_.record()
+            if it >= 3:
+                ev16.append((a, b_))
+        torch.cuda.synchronize()
+        ms16 = sum(a.elapsed_time(b_) for a, b_ in ev16) / len(ev16)
+        bf16_tier = {"ms_per_step": ms16, "value": nnz / (ms16 * 1e-3), "unit": "edges/s", "errors_vs_fp32_step": e16,
+                     "tolerance": 2e-2, "ok": all(v <= 2e-2 for v in e16.values()),
+                     "what": "GraphConvolution(precision='bf16'): the panels the two SpMMs gather are bf16 "
+                             "(gcnb_to_bf16 + gcnb_spmm_bf16), everything else fp32"}
+    except Exception as e:  # pragma: no cover
+        bf16_tier = {"error": repr(e)}
     sampler.stop()
 
     # ---- CPU baseline on the host cores (bounded sample), N=1 only
@@ -439,9 +487,13 @@ def run_ours(args, wl):
                        "from pinned host memory on a copy stream"},
         "torch_cuda_reference": torch_cuda,
         "parity": parity,
+        "bf16_tier": bf16_tier,
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "spmm_group_kernel<8,4,6> (CSR SpMM, fwd and A^T launches)",
+                     "traffic": traffic,
+                     "kernel": ("spmm_group_kernel<%d,%s> (CSR SpMM, fwd and A^T launches)" % (
+                         max(1, 1 << max(0, ((fout + 3) // 4 - 1).bit_length())), "4,6" if fout > 16 else "8,4")
+                         if fout <= 64 else "spmm_rows_vec_kernel<32,%d> (CSR SpMM, fwd and A^T launches)" % ((fout + 127) // 128)),
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": spmm_ms, "peak_source": peak_src,
                      "frac_of_8TBs_nominal": achieved / 8000.0,
                      "l2_to_sm_gather_GBps": (xbar_bytes / (spmm_ms * 1e-3) / 1e9) if xbar_bytes else None,
