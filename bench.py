@@ -183,6 +183,9 @@ def run_reference(args, wl):
     csr = R.make_reference_adj(torch.from_numpy(idx), torch.from_numpy(val), (n, n), "csr")
     sec_csr = R.time_reference(x, w, b, csr, g, max(2, min(args.steps, 5)), 1)
     sample = "%d steps of the full %s workload (nnz=%d) after %d warm-up" % (args.steps, args.workload, nnz, args.warmup)
+    if args.gpus > 1:  # our arm's N-GPU workload is N x this graph (weak scaling): the CPU arm times one N-th of it
+        sample = ("%d steps on a 1/%d sample of the %d-GPU workload = the per-GPU graph (nnz=%d; edges/s does not depend "
+                  "on the graph size on the CPU path) after %d warm-up" % (args.steps, args.gpus, args.gpus, nnz, args.warmup))
     line = {
         "impl": "reference", "metric": "gcn_layer_fwd_bwd_edges_per_sec", "value": value, "unit": "edges/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,

@@ -1189,6 +1189,18 @@ int tma_hi_rna() {
   return v;
 }
 
+// the 227 KB dynamic shared memory opt-in is a per-device attribute of the function: once per (kernel, device)
+int allow_big_smem(const void* kernel, int slot) {
+  static bool done[2][64] = {};
+  int dev = 0;
+  GCNB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !done[slot][dev]) {
+    GCNB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (dev >= 0 && dev < 64) done[slot][dev] = true;
+  }
+  return GCNB_OK;
+}
+
 struct TmaPlan { int npad, n_tiles, nkb, ns, b_resident; size_t img_floats; uint32_t smem; };
 TmaPlan tma_plan(int64_t n, int64_t k) {
   TmaPlan p;
@@ -1348,11 +1360,7 @@ int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t
       if (pg > 4 * kNumSMs) pg = 4 * kNumSMs;
       pack_b_kernel<<<pg, 256, 0, st>>>(k, n, t.npad, t.n_tiles, t.nkb, b, b_rs, b_cs, hi, lo);
       GCNB_LAUNCH_CHECK();
-      static bool tma_attr = false;
-      if (!tma_attr) {
-        GCNB_CUDA(cudaFuncSetAttribute(gemm_tc_rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        tma_attr = true;
-      }
+      GCNB_TRY(allow_big_smem(reinterpret_cast<const void*>(gemm_tc_rows_tma_kernel), 0));
       const int64_t mt = ceil_div(m, BM);
       int64_t gx = kNumSMs / t.n_tiles;
       if (gx < 1) gx = 1;
@@ -1452,11 +1460,7 @@ int gemm_tc_tn_launch(int64_t m, int64_t n, int64_t r, const float* x, int64_t l
       const int64_t ld_t = (t.splits > 1) ? n : ldc;
       const int64_t stride_t = (t.splits > 1) ? m * n : 0;
       const int vec = (ld_t % 4 == 0) && aligned16(dst_t);
-      static bool tn_attr = false;
-      if (!tn_attr) {
-        GCNB_CUDA(cudaFuncSetAttribute(gemm_tc_tn_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        tn_attr = true;
-      }
+      GCNB_TRY(allow_big_smem(reinterpret_cast<const void*>(gemm_tc_tn_tma_kernel), 1));
       gemm_tc_tn_tma_kernel<<<dim3((unsigned)t.splits, (unsigned)t.m_tiles), kTmaThreads, t.smem, st>>>(
           tx, ty, r, (int)m, (int)n, dst_t, ld_t, stride_t, t.rows_per_split, t.npad, tmem_cols_for(2 * t.npad), vec, t.ns);
       GCNB_LAUNCH_CHECK();
