@@ -474,7 +474,9 @@ def run_ours(args, wl):
     if not args.no_cpu_baseline:
         cpu = cpu_baseline(torch, graph, layer, x_host, g_host, wl)
 
-    launches_per_step = 7  # gemm XW, spmm | colsum x2, spmm^T, gemm dW partial + split-K reduce
+    # pack W + X.W (TMA-fed tcgen05), SpMM | SpMM^T, dW with the fused colsum(G) + split-K reduce
+    # (profiles/r01_launches_v10_summary.txt); wide layers add nothing, masked backwards add one colsum
+    launches_per_step = 6
     line = {
         "metric": "gcn_layer_fwd_bwd_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -332,7 +332,14 @@ extern "C" int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_
   int64_t gld = ldg;
   // db = colsum(G) ; with the fused ReLU the mask is applied first: G <- G * [y > 0]
   const bool masked = relu || d_mask != nullptr;
-  if (masked || need_db) {
+  // Without a mask, db = colsum(G) rides in the narrow dW kernel (third operand, gemm_skinny.cu): G and dS have the
+  // same number of rows when the adjacency is square, so the pass over (X, dS) adds G's column sums for free.
+  const int64_t lds_ = ceil_div(fout, 4) * 4;
+  const bool fuse_db = !masked && need_db && need_dw && precision != GCNB_GEMM_TF32X3 && g->n_rows == g->n_cols &&
+                       d_db != nullptr && ldg % 4 == 0 && (reinterpret_cast<uintptr_t>(d_g) & 15u) == 0 &&
+                       gemm_skinny_tn_eligible(fin, fout, g->n_cols, d_x, ldx, d_ds, lds_) &&
+                       g_bytes >= gemm_skinny_tn_workspace_bytes(fin, fout, g->n_cols);
+  if (!fuse_db && (masked || need_db)) {
     float* db = d_db;
     GCNB_REQUIRE(db != nullptr || !need_db, "layer_backward: db requested but null");
     if (db == nullptr) db = reinterpret_cast<float*>(ws_gemm);  // discard
@@ -352,8 +359,13 @@ extern "C" int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_
   // dW = X^T dS                                     (MmBackward0 of torch.mm)
   if (need_dw) {
     GCNB_REQUIRE(d_dw != nullptr, "layer_backward: dW requested but null");
-    GCNB_TRY(gemm_dispatch(fin, fout, g->n_cols, d_x, 1, ldx, d_ds, lds, 1, d_dw, fout, precision, ws_gemm,
-                           g_bytes, st));
+    if (fuse_db) {
+      GCNB_TRY(gemm_skinny_tn_launch(fin, fout, g->n_cols, d_x, ldx, d_ds, lds, d_dw, fout, ws_gemm, g_bytes, st, d_g, ldg,
+                                     d_db));
+    } else {
+      GCNB_TRY(gemm_dispatch(fin, fout, g->n_cols, d_x, 1, ldx, d_ds, lds, 1, d_dw, fout, precision, ws_gemm,
+                             g_bytes, st));
+    }
   }
   // dX = dS W^T
   if (need_dx) {

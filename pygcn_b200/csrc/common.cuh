@@ -108,8 +108,10 @@ int gemm_skinny_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int
                             int64_t b_cs, float* c, int64_t ldc, cudaStream_t stream);
 bool gemm_skinny_tn_eligible(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y, int64_t ldy);
 size_t gemm_skinny_tn_workspace_bytes(int64_t m, int64_t n, int64_t r);
+// gx / db: optional third operand G [r, n] whose column sums are produced in the same pass (db = colsum(G))
 int gemm_skinny_tn_launch(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y, int64_t ldy,
-                          float* c, int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t stream);
+                          float* c, int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t stream,
+                          const float* gx = nullptr, int64_t ldg = 0, float* db = nullptr);
 
 int colsum_launch(int64_t n_rows, int64_t f, const float* g, int64_t ldg, const float* y,
                   int64_t ldy, float* gm, int64_t ldgm, float* out, void* ws, size_t ws_bytes,
@@ -126,8 +128,9 @@ int pad_copy_launch(int64_t n_rows, int64_t w, const float* src, int64_t ld_src,
 
 int bias_act_launch(int64_t n_rows, int64_t f, float* out, int64_t ldo, const Epilogue& ep, cudaStream_t stream);
 
+// extra_row != nullptr: every part holds m + 1 rows and the sum of row m goes to extra_row[0:n]
 int reduce_partials_launch(int64_t m, int64_t n, int n_parts, const float* partial, float* out,
-                           int64_t ldo, cudaStream_t stream);
+                           int64_t ldo, cudaStream_t stream, float* extra_row = nullptr);
 
 }  // namespace gcnb
 

@@ -159,7 +159,7 @@ colsum_vec_kernel(int64_t n_rows, int f4, int cw, int64_t rows_per_block, const 
 // out[i] = sum over parts of partial[s][i]: 32 outputs x 8 part-lanes per CTA, fixed-order tree.
 __global__ void __launch_bounds__(kThreads)
 reduce_partials_kernel(int64_t total, int64_t n, int n_parts, const float* __restrict__ partial,
-                       float* __restrict__ out, int64_t ldo) {
+                       float* __restrict__ out, int64_t ldo, int64_t m, float* __restrict__ extra_row) {
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31;
   const int ty = threadIdx.x >> 5;
@@ -184,7 +184,8 @@ reduce_partials_kernel(int64_t total, int64_t n, int n_parts, const float* __res
     float v = 0.f;
 #pragma unroll
     for (int t = 0; t < 8; ++t) v += red[t][tx];
-    out[(i / n) * ldo + (i % n)] = v;
+    if (i / n < m) out[(i / n) * ldo + (i % n)] = v;
+    else extra_row[i % n] = v;  // row m of every part: the fused column sum
   }
 }
 
@@ -193,7 +194,7 @@ reduce_partials_kernel(int64_t total, int64_t n, int n_parts, const float* __res
 // CBG dW: 8.7 us for 2.4 MB).  Lane p adds parts p, p+32, ... in order, then lanes are added in order: fixed.
 __global__ void __launch_bounds__(kThreads)
 reduce_partials_vec_kernel(int64_t total4, int64_t n4, int n_parts, const float4* __restrict__ partial,
-                           float* __restrict__ out, int64_t ldo) {
+                           float* __restrict__ out, int64_t ldo, int64_t m, float* __restrict__ extra_row) {
   __shared__ float4 red[32][8];
   const int tx = threadIdx.x & 7;
   const int ty = threadIdx.x >> 3;
@@ -225,7 +226,8 @@ reduce_partials_vec_kernel(int64_t total4, int64_t n4, int n_parts, const float4
       const float4 r = red[t][tx];
       v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
     }
-    *reinterpret_cast<float4*>(out + (i / n4) * ldo + 4 * (i % n4)) = v;
+    float* dst = (i / n4 < m) ? out + (i / n4) * ldo + 4 * (i % n4) : extra_row + 4 * (i % n4);
+    *reinterpret_cast<float4*>(dst) = v;
   }
 }
 
@@ -386,18 +388,18 @@ int bias_act_launch(int64_t n_rows, int64_t f, float* out, int64_t ldo, const Ep
 }
 
 int reduce_partials_launch(int64_t m, int64_t n, int n_parts, const float* partial, float* out,
-                           int64_t ldo, cudaStream_t st) {
-  const int64_t total = m * n;
+                           int64_t ldo, cudaStream_t st, float* extra_row) {
+  const int64_t total = (m + (extra_row ? 1 : 0)) * n;
   if (total == 0) return GCNB_OK;
   if (n_parts >= 16 && n % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(partial) & 15u) == 0 &&
-      (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+      (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && (reinterpret_cast<uintptr_t>(extra_row) & 15u) == 0) {
     reduce_partials_vec_kernel<<<(unsigned)ceil_div(total / 4, 8), kThreads, 0, st>>>(
-        total / 4, n / 4, n_parts, reinterpret_cast<const float4*>(partial), out, ldo);
+        total / 4, n / 4, n_parts, reinterpret_cast<const float4*>(partial), out, ldo, m, extra_row);
     GCNB_LAUNCH_CHECK();
     return GCNB_OK;
   }
   reduce_partials_kernel<<<(unsigned)ceil_div(total, 32), kThreads, 0, st>>>(total, n, n_parts, partial,
-                                                                            out, ldo);
+                                                                            out, ldo, m, extra_row);
   GCNB_LAUNCH_CHECK();
   return GCNB_OK;
 }

@@ -109,14 +109,21 @@ skinny_rows_kernel(int64_t M, int N, int K, const float* __restrict__ a, int64_t
 
 // ---------------------------------------------------------------------------------------------- tn
 // C_partial[cta][Mo][N] = sum over this CTA's rows of X[r, 0:Mo]^T Y[r, 0:N];  MMAX = padded Mo, N <= 32.
-template <int MMAX>
+// GSUM: a third operand G [R, N] rides along and its column sums (db = colsum(G), the AddBackward0 of
+// pygcn/layers.py:36) land in row Mo of the partial tile -- the layer's backward then needs no colsum kernel when
+// no mask has to be applied to G first (one launch and one 12.8 MB pass less on the CBG shape).
+template <int MMAX, bool GSUM>
 __global__ void __launch_bounds__(kThreads)
 skinny_tn_kernel(int64_t R, int Mo, int N, const float* __restrict__ x, int64_t ldx, const float* __restrict__ y,
-                 int64_t ldy, float* __restrict__ partial) {
+                 int64_t ldy, const float* __restrict__ gx, int64_t ldg, float* __restrict__ partial) {
   constexpr int M4 = MMAX / 4;
-  __shared__ __align__(16) float xs[kWarps][2][kStageRows][MMAX];
-  __shared__ __align__(16) float ys[kWarps][2][kStageRows][32];
+  extern __shared__ __align__(16) float skinny_smem[];
+  float (*xs)[2][kStageRows][MMAX] = reinterpret_cast<float (*)[2][kStageRows][MMAX]>(skinny_smem);
+  float (*ys)[2][kStageRows][32] = reinterpret_cast<float (*)[2][kStageRows][32]>(skinny_smem + kWarps * 2 * kStageRows * MMAX);
+  float (*gs)[2][kStageRows][32] = reinterpret_cast<float (*)[2][kStageRows][32]>(
+      skinny_smem + kWarps * 2 * kStageRows * (MMAX + 32));  // only touched when GSUM
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float gacc = 0.f;
   float acc[MMAX];
 #pragma unroll
   for (int k = 0; k < MMAX; ++k) acc[k] = 0.f;
@@ -146,6 +153,8 @@ skinny_tn_kernel(int64_t R, int Mo, int N, const float* __restrict__ x, int64_t 
         const int left = N - 4 * q;
         const uint32_t bytes = (row < R && q < n4 && left > 0) ? (uint32_t)(left >= 4 ? 16 : 4 * left) : 0u;
         cp_async16_zfill(smem_u32(&ys[warp][buf][r][4 * q]), y + (row < R ? row : 0) * ldy + 4 * q, bytes);
+        if constexpr (GSUM)
+          cp_async16_zfill(smem_u32(&gs[warp][buf][r][4 * q]), gx + (row < R ? row : 0) * ldg + 4 * q, bytes);
       }
     }
     cp_async_commit();
@@ -159,6 +168,7 @@ skinny_tn_kernel(int64_t R, int Mo, int N, const float* __restrict__ x, int64_t 
 #pragma unroll 2
     for (int r = 0; r < kStageRows; ++r) {
       const float yv = ys[warp][buf][r][lane];  // zero-filled past N and past R
+      if constexpr (GSUM) gacc += gs[warp][buf][r][lane];
 #pragma unroll
       for (int q = 0; q < M4; ++q) {
         const float4 xv = *reinterpret_cast<const float4*>(&xs[warp][buf][r][4 * q]);  // broadcast
@@ -174,7 +184,7 @@ skinny_tn_kernel(int64_t R, int Mo, int N, const float* __restrict__ x, int64_t 
   cp_async_wait<0>();
   __syncthreads();
   // CTA reduction in a fixed order: warp w adds into the shared tile in turn (w = 0 initialises)
-  float* tile = &xs[0][0][0][0];  // MMAX * 32 floats <= the xs array (kWarps*2*8*MMAX floats)
+  float* tile = &xs[0][0][0][0];  // (MMAX + 1) * 32 floats <= the xs array (kWarps*2*8*MMAX floats)
   for (int wv = 0; wv < kWarps; ++wv) {
     if (warp == wv) {
 #pragma unroll
@@ -182,11 +192,16 @@ skinny_tn_kernel(int64_t R, int Mo, int N, const float* __restrict__ x, int64_t 
         const float prev = (wv == 0) ? 0.f : tile[k * 32 + lane];
         tile[k * 32 + lane] = prev + acc[k];
       }
+      if constexpr (GSUM) tile[MMAX * 32 + lane] = ((wv == 0) ? 0.f : tile[MMAX * 32 + lane]) + gacc;
     }
     __syncthreads();
   }
-  float* dst = partial + (int64_t)blockIdx.x * Mo * N;
-  for (int i = threadIdx.x; i < Mo * N; i += kThreads) dst[i] = tile[(i / N) * 32 + (i % N)];
+  const int rows_out = GSUM ? Mo + 1 : Mo;  // row Mo of the partial tile = column sums of G
+  float* dst = partial + (int64_t)blockIdx.x * rows_out * N;
+  for (int i = threadIdx.x; i < rows_out * N; i += kThreads) {
+    const int k = i / N;
+    dst[i] = tile[((GSUM && k == Mo) ? MMAX : k) * 32 + (i % N)];
+  }
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -238,23 +253,47 @@ static int skinny_tn_ctas(int64_t r) {
 }
 
 size_t gemm_skinny_tn_workspace_bytes(int64_t m, int64_t n, int64_t r) {
-  return (size_t)skinny_tn_ctas(r) * (size_t)m * (size_t)n * sizeof(float);
+  return (size_t)skinny_tn_ctas(r) * (size_t)(m + 1) * (size_t)n * sizeof(float);  // (+1: the colsum row)
 }
 
+template <int MMAX, bool GSUM>
+static int skinny_tn_launch_t(int ctas, int64_t r, int m, int n, const float* x, int64_t ldx, const float* y, int64_t ldy,
+                              const float* gx, int64_t ldg, float* partial, cudaStream_t st) {
+  const size_t smem = (size_t)kWarps * 2 * kStageRows * (MMAX + 32 + (GSUM ? 32 : 0)) * sizeof(float);
+  if (smem > 48 * 1024) {  // per-device opt-in above the static limit (MMAX = 64 with the third operand: 64 KB)
+    static bool done[64] = {};
+    int dev = 0;
+    GCNB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+      GCNB_CUDA(cudaFuncSetAttribute(skinny_tn_kernel<MMAX, GSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+  }
+  skinny_tn_kernel<MMAX, GSUM><<<ctas, kThreads, smem, st>>>(r, m, n, x, ldx, y, ldy, gx, ldg, partial);
+  GCNB_LAUNCH_CHECK();
+  return GCNB_OK;
+}
+
+// gx != nullptr: also db[0:n] = column sums of G [r, n] (row stride ldg), fused into the same pass
 int gemm_skinny_tn_launch(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y, int64_t ldy,
-                          float* c, int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t st) {
+                          float* c, int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t st, const float* gx, int64_t ldg,
+                          float* db) {
   const int ctas = skinny_tn_ctas(r);
   GCNB_REQUIRE(ws != nullptr && ws_bytes >= gemm_skinny_tn_workspace_bytes(m, n, r), "gemm(skinny tn): workspace too small");
+  GCNB_REQUIRE(gx == nullptr || (db != nullptr && ldg % 4 == 0 && ldg >= n && al16(gx)),
+               "gemm(skinny tn): the fused column sum needs 16-byte aligned rows of G and an output");
   float* partial = reinterpret_cast<float*>(ws);
-#define GCNB_SKINNY_TN(MMAX_) \
-  skinny_tn_kernel<MMAX_><<<ctas, kThreads, 0, st>>>(r, (int)m, (int)n, x, ldx, y, ldy, partial)
+  int status;
+#define GCNB_SKINNY_TN(MMAX_)                                                                                              \
+  status = gx ? (skinny_tn_launch_t<MMAX_, true>(ctas, r, (int)m, (int)n, x, ldx, y, ldy, gx, ldg, partial, st))           \
+              : (skinny_tn_launch_t<MMAX_, false>(ctas, r, (int)m, (int)n, x, ldx, y, ldy, nullptr, 0, partial, st))
   if (m <= 8) GCNB_SKINNY_TN(8);
   else if (m <= 16) GCNB_SKINNY_TN(16);
   else if (m <= 32) GCNB_SKINNY_TN(32);
   else GCNB_SKINNY_TN(64);
 #undef GCNB_SKINNY_TN
-  GCNB_LAUNCH_CHECK();
-  return reduce_partials_launch(m, n, ctas, partial, c, ldc, st);
+  GCNB_TRY(status);
+  return reduce_partials_launch(m, n, ctas, partial, c, ldc, st, gx ? db : nullptr);
 }
 
 }  // namespace gcnb
