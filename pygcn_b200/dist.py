@@ -500,13 +500,49 @@ def dist_spmm_pipelined(ops, dgraph, blocks, exch, bias=None, relu=False):
 
 
 # ---------------------------------------------------------------------------- the exchange + layer
-def dist_spmm(ops, dgraph, diag, remote, panel, bias=None, relu=False, group=None):
+def chunk_columns(f, chunks):
+    """Column ranges [(c0, c1), ...] that cut a width-f panel into at most `chunks` pieces whose
+    boundaries are multiples of 4 floats (gathered rows stay 16-byte aligned); fewer pieces when f
+    is too narrow to give every piece at least 8 columns."""
+    chunks = max(1, min(int(chunks), f // 8 if f >= 8 else 1))
+    quads = (f + 3) // 4
+    cuts = [min(f, 4 * ((quads * k + chunks - 1) // chunks)) for k in range(chunks + 1)]
+    cuts[-1] = f
+    return [(cuts[k], cuts[k + 1]) for k in range(chunks) if cuts[k + 1] > cuts[k]]
+
+
+def dist_spmm_chunked(ops, dgraph, block, panel, chunks, bias=None, relu=False, group=None):
+    """The unsplit row block against the all-gathered panel, pipelined over COLUMN chunks of the panel:
+    every chunk's all-gather is issued at once (they queue on the communicator's stream), and the SpMM
+    over chunk k (width f/chunks, its own slice of the output, bias slice and ReLU fused) starts when
+    that chunk has landed -- while chunk k+1 is still on the wire.  No extra kernels, no protocol state:
+    the exchange stays NCCL's, only its granularity changes.  The price is the adjacency's index stream,
+    read once per chunk instead of once, and narrower gathered rows."""
+    world = dgraph.world
+    f = panel.shape[1]
+    out = ops.empty((dgraph.n_rows(), f), panel)
+    pending = []
+    for c0, c1 in chunk_columns(f, chunks):
+        send = panel[:, c0:c1].contiguous()
+        gathered = ops.empty((world * dgraph.pad_rows, c1 - c0), panel)
+        work = dist.all_gather_into_tensor(gathered, send, group=group, async_op=True)
+        pending.append((c0, c1, gathered, work, send))
+    for c0, c1, gathered, work, _send in pending:
+        work.wait()
+        ops.spmm_block(block, gathered, out[:, c0:c1], False, bias[c0:c1] if bias is not None else None, relu)
+    return out
+
+
+def dist_spmm(ops, dgraph, diag, remote, panel, bias=None, relu=False, group=None, chunks=1):
     """out_p = diag @ panel[:n_p] + remote @ allgather(panel) (+ bias) (relu).
 
     `panel` is this rank's [pad_rows, F] slot (rows past n_p are padding nobody references).  The
     all-gather of the slots (NCCL over NVLink, on the communicator's stream) runs while the
-    diagonal block is multiplied; the remote block is accumulated once the panel has landed."""
+    diagonal block is multiplied; the remote block is accumulated once the panel has landed.
+    chunks > 1 (unsplit row blocks only): dist_spmm_chunked."""
     world = dgraph.world
+    if world > 1 and not dgraph.split and chunks > 1 and len(chunk_columns(panel.shape[1], chunks)) > 1:
+        return dist_spmm_chunked(ops, dgraph, remote, panel, chunks, bias, relu, group)
     out = ops.empty((dgraph.n_rows(), panel.shape[1]), panel)
     if world == 1:
         return ops.spmm_block(diag, panel, out, False, bias, relu)
@@ -520,18 +556,19 @@ def dist_spmm(ops, dgraph, diag, remote, panel, bias=None, relu=False, group=Non
     return ops.spmm_block(remote, gathered, out, True, bias, relu)
 
 
-def dist_layer_forward(ops, dgraph, x, w, b, relu=False, group=None, exch=None):
+def dist_layer_forward(ops, dgraph, x, w, b, relu=False, group=None, exch=None, chunks=1):
     """Row block of  A (X W) + b  (pygcn/layers.py:33-36) for this rank.  With `exch` (an exchange
-    object for [pad_rows, Fout] panels) the per-source-block pipelined scheme is used."""
+    object for [pad_rows, Fout] panels) the per-source-block pipelined scheme is used; `chunks` > 1
+    pipelines the NCCL exchange over column chunks of the panel instead (dist_spmm_chunked)."""
     if exch is not None and dgraph.world > 1:
         ops.gemm(x, w, out=exch.my_slot)             # X_p W straight into this rank's slot
         return dist_spmm_pipelined(ops, dgraph, dgraph.fwd_blocks, exch, b, relu)
     support = ops.empty((dgraph.pad_rows, w.shape[1]), x)
     ops.gemm(x, w, out=support)
-    return dist_spmm(ops, dgraph, dgraph.fwd_diag, dgraph.fwd_remote, support, b, relu, group)
+    return dist_spmm(ops, dgraph, dgraph.fwd_diag, dgraph.fwd_remote, support, b, relu, group, chunks)
 
 
-def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=True, group=None, exch=None):
+def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=True, group=None, exch=None, chunks=1):
     """(dX rows of this rank or None, dW, db): dW/db are already summed over ranks."""
     fin, fout = w.shape
     if exch is not None and dgraph.world > 1:
@@ -540,7 +577,7 @@ def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=Tru
     else:
         gm = ops.empty((dgraph.pad_rows, fout), g)
         db, _ = ops.colsum(g, y, gm)                 # local part of db; G (masked) staged into its slot
-        ds = dist_spmm(ops, dgraph, dgraph.bwd_diag, dgraph.bwd_remote, gm, None, False, group)  # rows p of A^T G
+        ds = dist_spmm(ops, dgraph, dgraph.bwd_diag, dgraph.bwd_remote, gm, None, False, group, chunks)  # rows p of A^T G
     dw = ops.gemm(x.t(), ds)                         # local part of X^T dS
     if dgraph.world > 1:
         flat = torch.cat([dw.reshape(-1), db.reshape(-1)])
@@ -553,9 +590,9 @@ def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=Tru
 
 class _DistGCNLayerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, dgraph, relu, ops, group, exch_f=None, exch_b=None):
-        out = dist_layer_forward(ops, dgraph, x, weight, bias, relu, group, exch_f)
-        ctx.dgraph, ctx.relu, ctx.ops, ctx.group, ctx.exch_b = dgraph, relu, ops, group, exch_b
+    def forward(ctx, x, weight, bias, dgraph, relu, ops, group, exch_f=None, exch_b=None, chunks=1):
+        out = dist_layer_forward(ops, dgraph, x, weight, bias, relu, group, exch_f, chunks)
+        ctx.dgraph, ctx.relu, ctx.ops, ctx.group, ctx.exch_b, ctx.chunks = dgraph, relu, ops, group, exch_b, chunks
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, weight, out if relu else None)
         return out
@@ -565,8 +602,8 @@ class _DistGCNLayerFn(torch.autograd.Function):
     def backward(ctx, g):
         x, w, y = ctx.saved_tensors
         dx, dw, db = dist_layer_backward(ctx.ops, ctx.dgraph, x, w, g.contiguous(), y, ctx.needs_input_grad[0],
-                                         ctx.has_bias, ctx.group, ctx.exch_b)
-        return dx, dw, db, None, None, None, None, None, None
+                                         ctx.has_bias, ctx.group, ctx.exch_b, ctx.chunks)
+        return dx, dw, db, None, None, None, None, None, None, None
 
 
 class DistGraphConvolution(torch.nn.Module):
@@ -575,7 +612,7 @@ class DistGraphConvolution(torch.nn.Module):
     `.grad` of weight/bias comes out already all-reduced."""
 
     def __init__(self, in_features, out_features, bias=True, *, fuse_relu=False, precision="auto", group=None,
-                 exchange="auto"):
+                 exchange="auto", nccl_chunks=None):
         super().__init__()
         from .layers import GraphConvolution
 
@@ -584,6 +621,11 @@ class DistGraphConvolution(torch.nn.Module):
         self.inner = GraphConvolution(in_features, out_features, bias, fuse_relu=fuse_relu, precision=precision)
         self.group = group
         self.exchange = exchange
+        # exchange "nccl" on an unsplit row block: number of column chunks the panel all-gather is pipelined
+        # over (dist_spmm_chunked); 1 = one all-gather, then one SpMM (the measured default)
+        self.nccl_chunks = int(os.environ.get("GCNB_DIST_NCCL_CHUNKS", "1")) if nccl_chunks is None else int(nccl_chunks)
+        if self.nccl_chunks < 1:
+            raise ValueError("nccl_chunks must be >= 1")
         self._ops = None
         self._exch = None  # (dgraph id, forward exchange, backward exchange): per layer, so that a slot is
         #                    never overwritten by another layer's panel while a peer still reads it
@@ -636,7 +678,7 @@ class DistGraphConvolution(torch.nn.Module):
             raise RuntimeError("DistGraphConvolution runs on CUDA devices only (no CPU fallback)")
         ef, eb = self._exchanges(dgraph, input.device)
         return _DistGCNLayerFn.apply(input.contiguous(), self.inner.weight, self.inner.bias, dgraph,
-                                     self.inner.fuse_relu, self._ops, self.group, ef, eb)
+                                     self.inner.fuse_relu, self._ops, self.group, ef, eb, self.nccl_chunks)
 
 
 # ---------------------------------------------------------------------------- bench entry (N > 1)
@@ -810,7 +852,8 @@ def bench_main(args, wl):
                                     "column block per source rank consumed as its slot lands; NCCL all-reduce of dW,db"
                                     if exchange == "peer" else
                                     "nccl: all-gather of the X.W / G panels, then the SpMM over the row block; "
-                                    "all-reduce of dW,db")},
+                                    "all-reduce of dW,db"),
+                       "nccl_chunks": layer.nccl_chunks},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": (x_host.numel() + g_host.numel()) * 4,
                     "d2h_bytes_per_step": (fin * fout + fout) * 4, "ms_per_step": e2e_t.item() / args.steps * 1e3},

@@ -62,24 +62,24 @@ class NumpyOps:
         return torch.full(shape, float("nan"), dtype=torch.float32)  # padding must never be read
 
 
-def _problem(n=300, seed=3):
+def _problem(n=300, seed=3, fout=5):
     rs = np.random.default_rng(seed)
     src = (n * rs.random(4000) ** 2).astype(np.int64)  # skewed degrees: nnz balance != row balance
     dst = rs.integers(0, n, 4000)
     idx, val = O.build_normalized_adjacency(src, dst, n)
     x = rs.standard_normal((n, 12)).astype(np.float32)
-    g = rs.standard_normal((n, 5)).astype(np.float32)
-    w = rs.standard_normal((12, 5)).astype(np.float32)
-    b = rs.standard_normal(5).astype(np.float32)
+    g = rs.standard_normal((n, fout)).astype(np.float32)
+    w = rs.standard_normal((12, fout)).astype(np.float32)
+    b = rs.standard_normal(fout).astype(np.float32)
     return n, idx, val, x, g, w, b
 
 
-def _worker(rank, world, port, outdir, relu, split=True, pipelined=False):
+def _worker(rank, world, port, outdir, relu, split=True, pipelined=False, chunks=1):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        n, idx, val, x, g, w, b = _problem()
+        n, idx, val, x, g, w, b = _problem(fout=_fout(chunks))
         bounds = D.partition_rows_by_nnz(O.coo_to_csr(idx, n), world)
         r0, r1 = bounds[rank], bounds[rank + 1]
         tidx = np.vstack([idx[1], idx[0]])
@@ -99,12 +99,18 @@ def _worker(rank, world, port, outdir, relu, split=True, pipelined=False):
             dg.bwd_blocks = [HostBlock(tidx, val, r0, r1, bounds=bounds, pad=pad, only=qs) for qs in dg.phases]
             ef = D.CollectiveExchange(rank, world, pad, w.shape[1], xt)
             eb = D.CollectiveExchange(rank, world, pad, w.shape[1], xt)
-        out = D.dist_layer_forward(ops, dg, xt, wt, bt, relu=relu, exch=ef)
-        dx, dw, db = D.dist_layer_backward(ops, dg, xt, wt, gt, out if relu else None, True, True, exch=eb)
+        out = D.dist_layer_forward(ops, dg, xt, wt, bt, relu=relu, exch=ef, chunks=chunks)
+        dx, dw, db = D.dist_layer_backward(ops, dg, xt, wt, gt, out if relu else None, True, True, exch=eb, chunks=chunks)
         np.savez(os.path.join(outdir, "r%d.npz" % rank), out=out.numpy(), dx=dx.numpy(), dw=dw.numpy(), db=db.numpy(),
                  bounds=np.array(bounds))
     finally:
         dist.destroy_process_group()
+
+
+def _fout(chunks):
+    """Panel width of the test problem: 5 columns normally, 37 (uneven 16-byte-aligned pieces) when the
+    exchange is cut into column chunks."""
+    return 5 if chunks == 1 else 37
 
 
 def _free_port():
@@ -115,14 +121,16 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,relu,split,pipelined", [(2, False, True, False), (2, True, False, False),
-                                                        (3, False, True, False), (2, True, False, True),
-                                                        (3, False, False, True), (4, True, False, True)])
-def test_row_partitioned_layer_matches_single_process_oracle(world, relu, split, pipelined):
+@pytest.mark.parametrize("world,relu,split,pipelined,chunks", [
+    (2, False, True, False, 1), (2, True, False, False, 1), (3, False, True, False, 1), (2, True, False, True, 1),
+    (3, False, False, True, 1), (4, True, False, True, 1),
+    # the all-gather exchange pipelined over column chunks of the panel (dist_spmm_chunked), 37-column panels
+    (2, True, False, False, 2), (3, False, False, False, 4)])
+def test_row_partitioned_layer_matches_single_process_oracle(world, relu, split, pipelined, chunks):
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_worker, args=(world, _free_port(), d, relu, split, pipelined), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), d, relu, split, pipelined, chunks), nprocs=world, join=True)
         parts = [np.load(os.path.join(d, "r%d.npz" % r)) for r in range(world)]
-    n, idx, val, x, g, w, b = _problem()
+    n, idx, val, x, g, w, b = _problem(fout=_fout(chunks))
     _, o_ref = O.c_layer_forward(x, w, b, idx, val, n)
     gm = g
     if relu:
@@ -137,6 +145,19 @@ def test_row_partitioned_layer_matches_single_process_oracle(world, relu, split,
     for p in parts:  # all-reduced: every rank holds the full gradient
         assert O.normwise_err(p["dw"], dw) < 1e-5 and O.normwise_err(p["db"], db) < 1e-5
     assert list(parts[0]["bounds"]) == list(parts[-1]["bounds"])
+
+
+def test_chunk_columns_are_aligned_and_cover_the_panel():
+    for f in (1, 5, 7, 8, 16, 20, 32, 37, 47, 64, 256, 600):
+        for chunks in (1, 2, 3, 4, 8):
+            cc = D.chunk_columns(f, chunks)
+            assert cc[0][0] == 0 and cc[-1][1] == f and 1 <= len(cc) <= chunks
+            assert all(a[1] == b[0] for a, b in zip(cc, cc[1:]))          # contiguous, in order
+            assert all(c0 % 4 == 0 and c1 > c0 for c0, c1 in cc)          # 16-byte aligned starts, no empty piece
+            assert len(cc) == 1 or min(c1 - c0 for c0, c1 in cc[:-1]) >= 8  # no sliver pieces
+    assert D.chunk_columns(32, 2) == [(0, 16), (16, 32)]
+    assert D.chunk_columns(37, 4) == [(0, 12), (12, 20), (20, 32), (32, 37)]
+    assert D.chunk_columns(5, 4) == [(0, 5)]
 
 
 def test_exchange_phases_cover_every_source_once_own_slot_first():
