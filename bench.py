@@ -334,6 +334,8 @@ def run_ours(args, wl):
     alg_bytes = algorithmic_bytes_spmm(nnz, n, fout)
     achieved = alg_bytes / (spmm_ms * 1e-3) / 1e9
     traffic, xbar_bytes = ncu_traffic(args.workload)
+    gemm_bytes = (n * fin + fin * fout + n * fout) * 4  # X.W reads X, W, writes S; dW reads X, dS, writes dW
+    layer_bytes = 2 * alg_bytes + 2 * gemm_bytes
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timing.
     # Inputs are double-buffered: step i+1's H2D copies run on a copy stream while step i computes,
@@ -475,7 +477,7 @@ def run_ours(args, wl):
         cpu = cpu_baseline(torch, graph, layer, x_host, g_host, wl)
 
     # pack W + X.W (TMA-fed tcgen05), SpMM | SpMM^T, dW with the fused colsum(G) + split-K reduce
-    # (profiles/r01_launches_v10_summary.txt); wide layers add nothing, masked backwards add one colsum
+    # (profiles/r01_launches_v10_summary.txt: skinny_tn_kernel<64,1>); wide layers add nothing, masked backwards add one colsum
     launches_per_step = 6
     line = {
         "metric": "gcn_layer_fwd_bwd_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": 1,
@@ -506,7 +508,11 @@ def run_ours(args, wl):
                              "bound by the L1/TEX pipe and the L2 gather rate for random 128-byte rows (DESIGN.md "
                              "section 3; tools/microbench/gather_bw.cu measures 16.5 TB/s for the bare gather), "
                              "DRAM traffic = algorithmic bytes",
-                     "how": "CUDA events around gcnb_spmm alone, L2 flushed before each launch, mean of %d launches" % len(sp_ms)},
+                     "how": "CUDA events around gcnb_spmm alone, L2 flushed before each launch, mean of %d launches" % len(sp_ms),
+                     # the whole step against the same peak (2 B_spmm + 2 B_gemm; the epilogues and db add 0)
+                     "layer_step": {"algorithmic_bytes": layer_bytes, "achieved": layer_bytes / (ms_per_step * 1e-3) / 1e9,
+                                    "unit": "GB/s", "frac": layer_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                                    "spmm_share_of_step": 2 * spmm_ms / ms_per_step}},
         "wall_s_timed_region": wall,
     }
     if cpu is not None:
