@@ -498,8 +498,9 @@ def run_ours(args, wl):
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic,
-                     "kernel": ("spmm_group_kernel<%d,%s> (CSR SpMM, fwd and A^T launches)" % (
-                         max(1, 1 << max(0, ((fout + 3) // 4 - 1).bit_length())), "4,6" if fout > 16 else "8,4")
+                     "kernel": ("spmm_group_kernel<LPR=%d,%s> (CSR SpMM, fwd and A^T launches)" % (
+                         max(1, 1 << max(0, ((fout + 3) // 4 - 1).bit_length())),
+                         "U=4,24 CTAs/SM,W=2,SE=16" if fout > 16 else ("U=8,16 CTAs/SM,W=2,SE=16" if fout > 8 else "U=8,4 CTAs/SM"))
                          if fout <= 64 else "spmm_rows_vec_kernel<32,%d> (CSR SpMM, fwd and A^T launches)" % ((fout + 127) // 128)),
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": spmm_ms, "peak_source": peak_src,
                      "frac_of_8TBs_nominal": achieved / 8000.0,

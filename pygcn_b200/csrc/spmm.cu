@@ -245,6 +245,12 @@ spmm_rows_vec_kernel(int n_rows, const int32_t* __restrict__ rowptr, const int32
 // index arithmetic and shuffles.  Per-row accumulation order is the stored order, run-to-run
 // deterministic.
 constexpr int kStageEntries = 32;
+// the largest power of two <= `want` for which `groups` double-buffered stages of (E + 2) pairs fit 48 KB
+constexpr int stage_entries(int want, int groups) {
+  int e = want;
+  while (e > 2 && groups * 2 * (e + 2) * 8 > 48 * 1024) e /= 2;
+  return e;
+}
 
 // (OR of one word of every gathered row) & never, where `never` is a kernel argument that is always
 // 0 at run time (the compiler cannot know).  OR-ing it into the accumulators makes every FFMA of a
@@ -259,21 +265,23 @@ __device__ __forceinline__ uint32_t all_landed(const uint4 (&x)[U], uint32_t nev
   return g & never;
 }
 
-template <int LPR, int U, int MINB, bool BF16>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
+// W = warps per CTA, SE = entries per stage (tuning variants: smaller CTAs free their slots in finer steps at the
+// tail of the grid; longer stages halve the per-stage bookkeeping of a ~100-entry row)
+template <int LPR, int U, int MINB, bool BF16, int W = kWarpsPerCta, int SE = kStageEntries>
+__global__ void __launch_bounds__(W * 32, MINB)
 spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* __restrict__ pair, int last_pair,
                   const void* __restrict__ b, uint32_t ldb_bytes, int f, Epilogue ep, float* __restrict__ out,
                   int64_t ldo, int vec_out, int skip_long, uint32_t never) {
   constexpr int G = 32 / LPR;
   constexpr int A = Panel<BF16>::kAcc;
-  constexpr int E = (LPR >= 4) ? kStageEntries : kStageEntries / 2;  // static shared memory stays < 48 KB
+  constexpr int E = stage_entries(SE, W * G) < 2 * LPR ? 2 * LPR : stage_entries(SE, W * G);  // static shared memory stays < 48 KB (32 entries for LPR >= 4, else 16)
   constexpr int NC = E / (2 * LPR);  // 16-byte copies (two pairs) per lane and stage
   static_assert(E % U == 0 && U % 2 == 0 && NC >= 1, "batches of U entries must divide the stage");
   // +2 pairs of padding per buffer: buffers stay 16-byte aligned and consecutive groups start
   // 2*(E+2)*2 = 136 words apart, i.e. 8 banks, so the G broadcast LDS.128 of one instruction hit
   // disjoint banks
   constexpr uint32_t kBufBytes = 8u * (E + 2);
-  __shared__ __align__(16) uint2 stage[kWarpsPerCta][G][2][E + 2];
+  __shared__ __align__(16) uint2 stage[W][G][2][E + 2];
   // Register diet (the budget decides how many warps x gathers fly per SM): inside the loops only
   // e (next entry to stage), left (entries not yet consumed, counted from the 2-aligned window start),
   // the two buffer addresses, the lane's base pointer and the accumulators live; row / width data are
@@ -282,7 +290,7 @@ spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* _
   int e, left, lead;
   {
     const int lane = threadIdx.x & 31;
-    const int row = (blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * G + lane / LPR;
+    const int row = (blockIdx.x * W + (threadIdx.x >> 5)) * G + lane / LPR;
     int start = 0, end = 0;
     if (row < n_rows) {
       start = __ldg(rowptr + row);
@@ -383,7 +391,7 @@ spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* _
   cp_async_wait<0>();
   {
     const int lane = threadIdx.x & 31;
-    const int row = (blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * G + lane / LPR;
+    const int row = (blockIdx.x * W + (threadIdx.x >> 5)) * G + lane / LPR;
     if (row >= n_rows || sub >= Panel<BF16>::chunks(f)) return;
     if (skip_long && __ldg(rowptr + row + 1) - __ldg(rowptr + row) >= kLongRowThreshold) return;
     store_panel_chunk<BF16>(out + (int64_t)row * ldo, row, sub, f, vec_out, acc, ep);
@@ -694,24 +702,40 @@ int launch_vec(const CsrView& a, const void* b, int64_t ldb, int f, const Epilog
     tuning_init();
     const bool want_group = g_spmm_kernel == 2 || (g_spmm_kernel == 0 && (shape_ok || g_group_variant >= 0));
     if (grid > 0 && a.pair != nullptr && want_group && ldb * kEB < (1ll << 32)) {
-      const int ggrid = (int)ceil_div(a.n_rows, (int64_t)kWarpsPerCta * G);
-#define GCNB_GROUP_LAUNCH(U_, MINB_)                                                                       \
-  spmm_group_kernel<LPR, U_, MINB_, BF16><<<ggrid, kWarpsPerCta * 32, 0, st>>>(                         \
-      (int)a.n_rows, a.rowptr, a.pair, (int)(a.nnz & ~1ll), b, (uint32_t)(ldb * kEB), f, ep, out, ldo, \
+#define GCNB_GROUP_LAUNCH_W(U_, MINB_, W_, SE_)                                                                      \
+  spmm_group_kernel<LPR, U_, MINB_, BF16, W_, SE_><<<(int)ceil_div(a.n_rows, (int64_t)(W_) * G), (W_) * 32, 0, st>>>( \
+      (int)a.n_rows, a.rowptr, a.pair, (int)(a.nnz & ~1ll), b, (uint32_t)(ldb * kEB), f, ep, out, ldo,               \
       vec_out ? 1 : 0, has_long ? 1 : 0, 0u)
+#define GCNB_GROUP_LAUNCH(U_, MINB_) GCNB_GROUP_LAUNCH_W(U_, MINB_, kWarpsPerCta, kStageEntries)
       // (gathers in flight per lane, CTAs per SM the register budget must allow).  Measured on B200
       // (gpurun_out/probe_sweep8.log): 128/256-byte rows like many warps with 4 gathers each, narrower
       // rows fewer warps with 8.  GCNB_SPMM_GROUP_VARIANT overrides (tuning knob).
       int variant = spmm_group_variant();
-      if (variant < 0) variant = (LPR >= 8) ? 2 : 0;
+      // auto (profiles/r01_spmm_variant_sweep_w_se_*.txt): 2-warp CTAs and 16-entry stages -- slots are handed to the
+      // next rows in finer steps, the first stage of a row is half as long, and 24 x 2.3 KB of staging leave more
+      // of the SM's L1 to the gathers: 4-6 % over the 8-warp / 32-entry shapes (variants 2 and 0) on every
+      // measured graph
+      if (variant < 0) variant = (LPR >= 8) ? 13 : (LPR == 4 ? 14 : 0);
       switch (variant) {
         case 1: GCNB_GROUP_LAUNCH(8, 3); break;
         case 2: GCNB_GROUP_LAUNCH(4, 6); break;
         case 3: GCNB_GROUP_LAUNCH(16, 2); break;
         case 4: GCNB_GROUP_LAUNCH(4, 5); break;
+        case 5: GCNB_GROUP_LAUNCH(4, 7); break;                       // 56 warps per SM (a few spilled registers)
+        case 6: GCNB_GROUP_LAUNCH_W(4, 12, 4, kStageEntries); break;  // 4-warp CTAs, same 48 warps per SM
+        case 7: GCNB_GROUP_LAUNCH_W(4, 6, kWarpsPerCta, 64); break;   // 64-entry stages
+        case 8: GCNB_GROUP_LAUNCH_W(4, 12, 4, 64); break;             // both
+        case 9: GCNB_GROUP_LAUNCH_W(8, 8, 4, kStageEntries); break;   // variant 0 with 4-warp CTAs
+        case 10: GCNB_GROUP_LAUNCH_W(4, 24, 2, kStageEntries); break; // 2-warp CTAs
+        case 11: GCNB_GROUP_LAUNCH_W(8, 16, 2, kStageEntries); break;
+        case 12: GCNB_GROUP_LAUNCH_W(4, 12, 4, 16); break;            // 16-entry stages
+        case 13: GCNB_GROUP_LAUNCH_W(4, 24, 2, 16); break;
+        case 14: GCNB_GROUP_LAUNCH_W(8, 16, 2, 16); break;
+        case 15: GCNB_GROUP_LAUNCH_W(8, 8, 4, 16); break;
         default: GCNB_GROUP_LAUNCH(8, 4); break;
       }
 #undef GCNB_GROUP_LAUNCH
+#undef GCNB_GROUP_LAUNCH_W
       GCNB_LAUNCH_CHECK();
       return launch_long<LPR, CH, BF16>(a, b, ldb, f, ep, out, ldo, partial, ldp, st);
     }
@@ -742,7 +766,7 @@ int spmm_set_tuning(int key, int value) {
     GCNB_REQUIRE(value >= 0 && value <= 3, "set_tuning: spmm kernel must be 0..3");
     g_spmm_kernel = value;
   } else if (key == GCNB_TUNE_SPMM_GROUP_VARIANT) {
-    GCNB_REQUIRE(value >= -1 && value <= 4, "set_tuning: group variant must be -1..4");
+    GCNB_REQUIRE(value >= -1 && value <= 15, "set_tuning: group variant must be -1..15");
     g_group_variant = value;
   } else {
     GCNB_REQUIRE(false, "set_tuning: unknown key %d", key);

@@ -859,7 +859,7 @@ def bench_main(args, wl):
                     "d2h_bytes_per_step": (fin * fout + fout) * 4, "ms_per_step": e2e_t.item() / args.steps * 1e3},
             "gpu_launches": 10 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "spmm_group_kernel<8,4,6> on rank 0's %s" % ("diagonal block" if dgraph.split else "row block (all-gathered panel)"),
+                         "traffic": None, "kernel": "spmm_group_kernel<LPR=8,U=4,24 CTAs/SM,W=2,SE=16> on rank 0's %s" % ("diagonal block" if dgraph.split else "row block (all-gathered panel)"),
                          "algorithmic_bytes_per_launch": alg, "kernel_ms": spmm_ms, "peak_source": peak_src},
         }
         print(json.dumps(line), flush=True)

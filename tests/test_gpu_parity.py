@@ -437,8 +437,8 @@ def spmm_kernel(P, request):
     lib.gcnb_set_tuning(_lib.TUNE_SPMM_GROUP_VARIANT, -1)
 
 
-@pytest.mark.parametrize("spmm_kernel", ["auto", "rows", "group", "tma", ("group", 0), ("group", 1), ("group", 3), ("group", 4)],
-                         indirect=True)
+@pytest.mark.parametrize("spmm_kernel", ["auto", "rows", "group", "tma", ("group", 0), ("group", 1), ("group", 2), ("group", 3),
+                                         ("group", 4), ("group", 7), ("group", 13), ("group", 14)], indirect=True)
 @pytest.mark.parametrize("fin,fout", [(64, 32), (5, 1), (9, 3), (16, 7), (33, 47), (100, 256), (20, 600)])
 def test_layer_vs_oracle_widths_and_long_rows(P, fin, fout, spmm_kernel):
     n = 6000
@@ -525,7 +525,8 @@ def test_to_bf16_is_round_to_nearest_even_with_zero_padding(P, f):
     assert (got[:, f:].float() == 0).all()
 
 
-@pytest.mark.parametrize("spmm_kernel", ["auto", "rows", "group", ("group", 0), ("group", 1), ("group", 3)], indirect=True)
+@pytest.mark.parametrize("spmm_kernel", ["auto", "rows", "group", ("group", 0), ("group", 1), ("group", 3), ("group", 13),
+                                         ("group", 14)], indirect=True)
 @pytest.mark.parametrize("f", [1, 3, 7, 8, 24, 32, 47, 64, 100, 256, 600, 1100])
 def test_spmm_bf16_panel_equals_fp32_kernel_on_the_rounded_panel(P, f, spmm_kernel):
     """gcnb_spmm_bf16 gathers bf16 rows and accumulates in fp32: on a panel that is already bf16-representable
