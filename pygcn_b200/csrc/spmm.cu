@@ -715,7 +715,9 @@ int launch_vec(const CsrView& a, const void* b, int64_t ldb, int f, const Epilog
       // next rows in finer steps, the first stage of a row is half as long, and 24 x 2.3 KB of staging leave more
       // of the SM's L1 to the gathers: 4-6 % over the 8-warp / 32-entry shapes (variants 2 and 0) on every
       // measured graph
-      if (variant < 0) variant = (LPR >= 8) ? 13 : (LPR == 4 ? 14 : 0);
+      // (bf16 panels with 64-byte rows stay on variant 0: 75.3 us per CBG launch there, 77.3 us with variant 14,
+      // profiles/r01_launches_v10_summary.txt vs _v12_)
+      if (variant < 0) variant = (LPR >= 8) ? 13 : ((LPR == 4 && !BF16) ? 14 : 0);
       switch (variant) {
         case 1: GCNB_GROUP_LAUNCH(8, 3); break;
         case 2: GCNB_GROUP_LAUNCH(4, 6); break;
