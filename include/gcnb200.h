@@ -263,6 +263,9 @@ int gcnb_peer_ack(uint32_t* peer_ack, const uint32_t* d_epoch, void* stream);
  *   the group kernel (spmm.cu) */
 #define GCNB_TUNE_SPMM_KERNEL 1
 #define GCNB_TUNE_SPMM_GROUP_VARIANT 2
+/*   GCNB_TUNE_PDL: 0 (default) plain stream order; 1 = the layer's kernels are launched with programmatic
+ *   stream serialization (each starts while its predecessor drains and waits on-device before touching its output) */
+#define GCNB_TUNE_PDL 3
 int gcnb_set_tuning(int key, int value);
 
 /* L2 flush helper for benchmarks: writes `bytes` of d_buf. */

@@ -26,7 +26,7 @@ BUILD_SYMMETRIZE, BUILD_SELF_LOOPS, BUILD_ROW_NORMALIZE = 1, 2, 4
 SPMM_TRANSPOSE, SPMM_RELU, SPMM_ACCUMULATE = 1, 2, 4
 GEMM_FP32, GEMM_TF32X3, GEMM_AUTO = 0, 1, 2
 LAYER_RELU, LAYER_NEED_DX, LAYER_NEED_DW, LAYER_NEED_DB = 1, 2, 4, 8
-TUNE_SPMM_KERNEL, TUNE_SPMM_GROUP_VARIANT = 1, 2
+TUNE_SPMM_KERNEL, TUNE_SPMM_GROUP_VARIANT, TUNE_PDL = 1, 2, 3
 
 
 class GraphInfo(ctypes.Structure):

@@ -38,6 +38,30 @@ void set_error(const char* fmt, ...);
 
 constexpr int kNumSMs = 148;  // B200
 
+// Programmatic dependent launch of the layer's kernel chain (pack W, X.W, SpMM | SpMM^T, dW, split-K reduce):
+// OFF by default; GCNB_PDL=1 or gcnb_set_tuning(GCNB_TUNE_PDL, 1) turns it on.  Each kernel of the chain then runs
+// its PDL instantiation: `griddepcontrol.launch_dependents` first, so that the next kernel's CTAs take the SM slots
+// this grid frees in its last wave, and `griddepcontrol.wait` before the first access to anything an earlier kernel
+// of the stream may have written.  Only data that is constant for the life of the graph handle (rowptr, the
+// (col,val) pairs) is touched before the wait.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // One CSR (either the adjacency or its transpose) plus its row-length-binned schedule.

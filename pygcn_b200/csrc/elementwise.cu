@@ -2,6 +2,7 @@
 // the ReLU mask of the fused epilogue applied on the fly when requested, plus the L2 flush
 // helper the benchmark uses.  Two-phase deterministic reduction (no atomics).
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace gcnb {
 namespace {
@@ -192,10 +193,15 @@ reduce_partials_kernel(int64_t total, int64_t n, int n_parts, const float* __res
 // The same sum for many parts (split-K over 148-296 CTAs): 32 part-lanes per output float4, so a lane adds ~10
 // parts whose loads are all in flight together (the kernel above walks 37 dependent rounds of L2 latency for the
 // CBG dW: 8.7 us for 2.4 MB).  Lane p adds parts p, p+32, ... in order, then lanes are added in order: fixed.
+template <bool PDL>  // (the programmatic-dependent-launch instantiation, common.cuh)
 __global__ void __launch_bounds__(kThreads)
 reduce_partials_vec_kernel(int64_t total4, int64_t n4, int n_parts, const float4* __restrict__ partial,
                            float* __restrict__ out, int64_t ldo, int64_t m, float* __restrict__ extra_row) {
   __shared__ float4 red[32][8];
+  if constexpr (PDL) {
+    pdl_launch_dependents();
+    pdl_wait();  // the partial tiles are the previous kernel's output
+  }
   const int tx = threadIdx.x & 7;
   const int ty = threadIdx.x >> 3;
   const int64_t i = (int64_t)blockIdx.x * 8 + tx;
@@ -393,7 +399,12 @@ int reduce_partials_launch(int64_t m, int64_t n, int n_parts, const float* parti
   if (total == 0) return GCNB_OK;
   if (n_parts >= 16 && n % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(partial) & 15u) == 0 &&
       (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && (reinterpret_cast<uintptr_t>(extra_row) & 15u) == 0) {
-    reduce_partials_vec_kernel<<<(unsigned)ceil_div(total / 4, 8), kThreads, 0, st>>>(
+    if (pdl_enabled()) {  // opt-in (common.cuh)
+      GCNB_CUDA(launch_pdl(reduce_partials_vec_kernel<true>, dim3((unsigned)ceil_div(total / 4, 8)), dim3(kThreads), 0, st,
+                           total / 4, n / 4, n_parts, reinterpret_cast<const float4*>(partial), out, ldo, m, extra_row));
+      return GCNB_OK;
+    }
+    reduce_partials_vec_kernel<false><<<(unsigned)ceil_div(total / 4, 8), kThreads, 0, st>>>(
         total / 4, n / 4, n_parts, reinterpret_cast<const float4*>(partial), out, ldo, m, extra_row);
     GCNB_LAUNCH_CHECK();
     return GCNB_OK;

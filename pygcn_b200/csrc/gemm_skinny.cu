@@ -112,10 +112,16 @@ skinny_rows_kernel(int64_t M, int N, int K, const float* __restrict__ a, int64_t
 // GSUM: a third operand G [R, N] rides along and its column sums (db = colsum(G), the AddBackward0 of
 // pygcn/layers.py:36) land in row Mo of the partial tile -- the layer's backward then needs no colsum kernel when
 // no mask has to be applied to G first (one launch and one 12.8 MB pass less on the CBG shape).
-template <int MMAX, bool GSUM>
+// PDL: the programmatic-dependent-launch instantiation (common.cuh); y is the previous kernel's output, so the wait
+// comes first and only the launch latency and the CTA scheduling overlap.
+template <int MMAX, bool GSUM, bool PDL = false>
 __global__ void __launch_bounds__(kThreads)
 skinny_tn_kernel(int64_t R, int Mo, int N, const float* __restrict__ x, int64_t ldx, const float* __restrict__ y,
                  int64_t ldy, const float* __restrict__ gx, int64_t ldg, float* __restrict__ partial) {
+  if constexpr (PDL) {
+    pdl_launch_dependents();
+    pdl_wait();
+  }
   constexpr int M4 = MMAX / 4;
   extern __shared__ __align__(16) float skinny_smem[];
   float (*xs)[2][kStageRows][MMAX] = reinterpret_cast<float (*)[2][kStageRows][MMAX]>(skinny_smem);
@@ -256,19 +262,31 @@ size_t gemm_skinny_tn_workspace_bytes(int64_t m, int64_t n, int64_t r) {
   return (size_t)skinny_tn_ctas(r) * (size_t)(m + 1) * (size_t)n * sizeof(float);  // (+1: the colsum row)
 }
 
+// per-device opt-in above the static 48 KB limit (MMAX = 64 with the third operand: 64 KB)
+template <int MMAX, bool GSUM, bool PDL>
+static int skinny_tn_allow_smem(size_t smem) {
+  if (smem <= 48 * 1024) return GCNB_OK;
+  static bool done[64] = {};
+  int dev = 0;
+  GCNB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !done[dev]) {
+    GCNB_CUDA(cudaFuncSetAttribute(skinny_tn_kernel<MMAX, GSUM, PDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+  }
+  return GCNB_OK;
+}
+
 template <int MMAX, bool GSUM>
 static int skinny_tn_launch_t(int ctas, int64_t r, int m, int n, const float* x, int64_t ldx, const float* y, int64_t ldy,
                               const float* gx, int64_t ldg, float* partial, cudaStream_t st) {
   const size_t smem = (size_t)kWarps * 2 * kStageRows * (MMAX + 32 + (GSUM ? 32 : 0)) * sizeof(float);
-  if (smem > 48 * 1024) {  // per-device opt-in above the static limit (MMAX = 64 with the third operand: 64 KB)
-    static bool done[64] = {};
-    int dev = 0;
-    GCNB_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !done[dev]) {
-      GCNB_CUDA(cudaFuncSetAttribute(skinny_tn_kernel<MMAX, GSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      if (dev >= 0 && dev < 64) done[dev] = true;
-    }
+  if (pdl_enabled()) {  // opt-in (common.cuh)
+    GCNB_TRY((skinny_tn_allow_smem<MMAX, GSUM, true>(smem)));
+    GCNB_CUDA(launch_pdl(skinny_tn_kernel<MMAX, GSUM, true>, dim3((unsigned)ctas), dim3(kThreads), smem, st, r, m, n, x, ldx,
+                         y, ldy, gx, ldg, partial));
+    return GCNB_OK;
   }
+  GCNB_TRY((skinny_tn_allow_smem<MMAX, GSUM, false>(smem)));
   skinny_tn_kernel<MMAX, GSUM><<<ctas, kThreads, smem, st>>>(r, m, n, x, ldx, y, ldy, gx, ldg, partial);
   GCNB_LAUNCH_CHECK();
   return GCNB_OK;

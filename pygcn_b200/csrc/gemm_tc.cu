@@ -200,9 +200,15 @@ __device__ __forceinline__ void epilogue_store(uint32_t tmem_d, int npad, float*
 
 // ------------------------------------------------------------------ B packing (mode R)
 // image[(nt * nkb + kb)][n][32 floats, swizzled]; zero padded in n and k.
+// (PDL: the programmatic-dependent-launch instantiation, common.cuh)
+template <bool PDL>
 __global__ void __launch_bounds__(256)
 pack_b_kernel(int64_t K, int64_t N, int npad, int n_tiles, int nkb, const float* __restrict__ b, int64_t b_rs,
               int64_t b_cs, float* __restrict__ img_hi, float* __restrict__ img_lo) {
+  if constexpr (PDL) {
+    pdl_launch_dependents();
+    pdl_wait();  // B (the weights) may have been written by the previous kernel of the stream
+  }
   const int64_t total = (int64_t)n_tiles * nkb * npad * BKF;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int kk = (int)(i % BKF);
@@ -578,6 +584,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 struct alignas(64) TmaDesc { uint8_t bytes[128]; };  // CUtensorMap (opaque, 128 bytes, 64-byte aligned)
 
+template <bool PDL>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 gemm_tc_rows_tma_kernel(const __grid_constant__ TmaDesc tmap_a, int64_t M, int N, int K,
                         const float* __restrict__ img_hi, const float* __restrict__ img_lo, float* __restrict__ c,
@@ -611,10 +618,14 @@ gemm_tc_rows_tma_kernel(const __grid_constant__ TmaDesc tmap_a, int64_t M, int N
     __syncwarp();
     tmem_alloc(base + tmem_slot_off, (uint32_t)tmem_cols);
   }
+  if constexpr (PDL) pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + tmem_slot_off);
+  // barriers initialised and TMEM allocated while the previous kernel (the pack of B) drains; A, the packed B and C
+  // are touched only from here on
+  if constexpr (PDL) pdl_wait();
 
   const int nt = blockIdx.y;
   const int n0 = nt * npad;
@@ -1191,7 +1202,7 @@ int tma_hi_rna() {
 
 // the 227 KB dynamic shared memory opt-in is a per-device attribute of the function: once per (kernel, device)
 int allow_big_smem(const void* kernel, int slot) {
-  static bool done[2][64] = {};
+  static bool done[3][64] = {};
   int dev = 0;
   GCNB_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !done[slot][dev]) {
@@ -1358,15 +1369,24 @@ int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t
       float* lo = hi + ((t.img_floats + 31) & ~(size_t)31);
       int pg = (int)ceil_div((int64_t)t.img_floats, 256);
       if (pg > 4 * kNumSMs) pg = 4 * kNumSMs;
-      pack_b_kernel<<<pg, 256, 0, st>>>(k, n, t.npad, t.n_tiles, t.nkb, b, b_rs, b_cs, hi, lo);
-      GCNB_LAUNCH_CHECK();
-      GCNB_TRY(allow_big_smem(reinterpret_cast<const void*>(gemm_tc_rows_tma_kernel), 0));
       const int64_t mt = ceil_div(m, BM);
       int64_t gx = kNumSMs / t.n_tiles;
       if (gx < 1) gx = 1;
       if (gx > mt) gx = mt;
       const int vec = (ldc % 4 == 0) && aligned16(c);
-      gemm_tc_rows_tma_kernel<<<dim3((unsigned)gx, (unsigned)t.n_tiles), kTmaThreads, t.smem, st>>>(
+      if (pdl_enabled()) {  // opt-in: both kernels start while their predecessor drains (common.cuh)
+        GCNB_CUDA(launch_pdl(pack_b_kernel<true>, dim3((unsigned)pg), dim3(256), 0, st, k, n, t.npad, t.n_tiles, t.nkb, b,
+                             b_rs, b_cs, hi, lo));
+        GCNB_TRY(allow_big_smem(reinterpret_cast<const void*>(gemm_tc_rows_tma_kernel<true>), 2));
+        GCNB_CUDA(launch_pdl(gemm_tc_rows_tma_kernel<true>, dim3((unsigned)gx, (unsigned)t.n_tiles), dim3(kTmaThreads),
+                             t.smem, st, tmap, m, (int)n, (int)k, (const float*)hi, (const float*)lo, c, ldc, t.npad, t.nkb,
+                             (int)tmem_cols_for(2 * t.npad), vec, t.ns, t.b_resident, (int)tma_hi_rna()));
+        return GCNB_OK;
+      }
+      pack_b_kernel<false><<<pg, 256, 0, st>>>(k, n, t.npad, t.n_tiles, t.nkb, b, b_rs, b_cs, hi, lo);
+      GCNB_LAUNCH_CHECK();
+      GCNB_TRY(allow_big_smem(reinterpret_cast<const void*>(gemm_tc_rows_tma_kernel<false>), 0));
+      gemm_tc_rows_tma_kernel<false><<<dim3((unsigned)gx, (unsigned)t.n_tiles), kTmaThreads, t.smem, st>>>(
           tmap, m, (int)n, (int)k, hi, lo, c, ldc, t.npad, t.nkb, tmem_cols_for(2 * t.npad), vec, t.ns, t.b_resident,
           tma_hi_rna());
       GCNB_LAUNCH_CHECK();
@@ -1380,7 +1400,7 @@ int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t
   const int64_t total = (int64_t)p.img_floats;
   int pgrid = (int)ceil_div(total, 256);
   if (pgrid > 4 * kNumSMs) pgrid = 4 * kNumSMs;
-  pack_b_kernel<<<pgrid, 256, 0, st>>>(k, n, p.npad, p.n_tiles, p.nkb, b, b_rs, b_cs, img_hi, img_lo);
+  pack_b_kernel<false><<<pgrid, 256, 0, st>>>(k, n, p.npad, p.n_tiles, p.nkb, b, b_rs, b_cs, img_hi, img_lo);
   GCNB_LAUNCH_CHECK();
   Smem L;
   // keep the packed B resident when it costs no occupancy (<= 40 KB on top of the 64 KB of A stages)

@@ -63,4 +63,10 @@ __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// Programmatic dependent launch (opt-in, common.cuh launch_pdl): `launch_dependents` lets the next kernel in the
+// stream become resident while this grid drains; `wait` blocks until every prerequisite grid has completed and its
+// writes are visible.  Both are no-ops in a kernel that was launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace gcnb

@@ -267,7 +267,10 @@ __device__ __forceinline__ uint32_t all_landed(const uint4 (&x)[U], uint32_t nev
 
 // W = warps per CTA, SE = entries per stage (tuning variants: smaller CTAs free their slots in finer steps at the
 // tail of the grid; longer stages halve the per-stage bookkeeping of a ~100-entry row)
-template <int LPR, int U, int MINB, bool BF16, int W = kWarpsPerCta, int SE = kStageEntries>
+// PDL: the programmatic-dependent-launch instantiation (common.cuh): the row pointers and the first stage of (col,val)
+// pairs -- constant for the life of the graph handle -- are fetched while the previous kernel of the stream drains;
+// the wait sits in front of the first gather of the dense operand.
+template <int LPR, int U, int MINB, bool BF16, int W = kWarpsPerCta, int SE = kStageEntries, bool PDL = false>
 __global__ void __launch_bounds__(W * 32, MINB)
 spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* __restrict__ pair, int last_pair,
                   const void* __restrict__ b, uint32_t ldb_bytes, int f, Epilogue ep, float* __restrict__ out,
@@ -282,6 +285,7 @@ spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* _
   // disjoint banks
   constexpr uint32_t kBufBytes = 8u * (E + 2);
   __shared__ __align__(16) uint2 stage[W][G][2][E + 2];
+  if constexpr (PDL) pdl_launch_dependents();
   // Register diet (the budget decides how many warps x gathers fly per SM): inside the loops only
   // e (next entry to stage), left (entries not yet consumed, counted from the 2-aligned window start),
   // the two buffer addresses, the lane's base pointer and the accumulators live; row / width data are
@@ -336,6 +340,7 @@ spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* _
     return x;
   };
   fetch(cur, left - 2 * sub);
+  if constexpr (PDL) pdl_wait();  // the dense operand (and, for the accumulate epilogue, out) may come from the previous kernel
   float4 acc[A];
 #pragma unroll
   for (int t = 0; t < A; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -655,6 +660,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // time (tests force each kernel on small graphs).
 int g_spmm_kernel = -1;   // 0 auto, 1 rows, 2 group (forced), 3 tma
 int g_group_variant = -2;  // -1 auto
+int g_pdl = -1;            // programmatic dependent launch of the layer's kernel chain: 0 off (default), 1 on
 
 void tuning_init() {
   if (g_spmm_kernel < 0) {
@@ -666,6 +672,10 @@ void tuning_init() {
   if (g_group_variant == -2) {
     const char* e = getenv("GCNB_SPMM_GROUP_VARIANT");
     g_group_variant = e ? atoi(e) : -1;
+  }
+  if (g_pdl < 0) {
+    const char* e = getenv("GCNB_PDL");
+    g_pdl = (e && atoi(e) > 0) ? 1 : 0;
   }
 }
 bool spmm_use_tma() { tuning_init(); return g_spmm_kernel == 3; }
@@ -702,10 +712,16 @@ int launch_vec(const CsrView& a, const void* b, int64_t ldb, int f, const Epilog
     tuning_init();
     const bool want_group = g_spmm_kernel == 2 || (g_spmm_kernel == 0 && (shape_ok || g_group_variant >= 0));
     if (grid > 0 && a.pair != nullptr && want_group && ldb * kEB < (1ll << 32)) {
+#define GCNB_GROUP_ARGS                                                                                 \
+  (int)a.n_rows, a.rowptr, a.pair, (int)(a.nnz & ~1ll), b, (uint32_t)(ldb * kEB), f, ep, out, ldo, \
+      vec_out ? 1 : 0, has_long ? 1 : 0, 0u
 #define GCNB_GROUP_LAUNCH_W(U_, MINB_, W_, SE_)                                                                      \
   spmm_group_kernel<LPR, U_, MINB_, BF16, W_, SE_><<<(int)ceil_div(a.n_rows, (int64_t)(W_) * G), (W_) * 32, 0, st>>>( \
-      (int)a.n_rows, a.rowptr, a.pair, (int)(a.nnz & ~1ll), b, (uint32_t)(ldb * kEB), f, ep, out, ldo,               \
-      vec_out ? 1 : 0, has_long ? 1 : 0, 0u)
+      GCNB_GROUP_ARGS)
+// the PDL instantiation exists for the auto variants only
+#define GCNB_GROUP_LAUNCH_PDL(U_, MINB_, W_, SE_)                                                                 \
+  GCNB_CUDA(launch_pdl(spmm_group_kernel<LPR, U_, MINB_, BF16, W_, SE_, true>,                                    \
+                       dim3((unsigned)ceil_div(a.n_rows, (int64_t)(W_) * G)), dim3((W_) * 32), 0, st, GCNB_GROUP_ARGS))
 #define GCNB_GROUP_LAUNCH(U_, MINB_) GCNB_GROUP_LAUNCH_W(U_, MINB_, kWarpsPerCta, kStageEntries)
       // (gathers in flight per lane, CTAs per SM the register budget must allow).  Measured on B200
       // (gpurun_out/probe_sweep8.log): 128/256-byte rows like many warps with 4 gathers each, narrower
@@ -718,6 +734,12 @@ int launch_vec(const CsrView& a, const void* b, int64_t ldb, int f, const Epilog
       // (bf16 panels with 64-byte rows stay on variant 0: 75.3 us per CBG launch there, 77.3 us with variant 14,
       // profiles/r01_launches_v10_summary.txt vs _v12_)
       if (variant < 0) variant = (LPR >= 8) ? 13 : ((LPR == 4 && !BF16) ? 14 : 0);
+      const bool pdl = pdl_enabled() && spmm_group_variant() < 0;
+      if (pdl) {
+        if (variant == 13) GCNB_GROUP_LAUNCH_PDL(4, 24, 2, 16);
+        else if (variant == 14) GCNB_GROUP_LAUNCH_PDL(8, 16, 2, 16);
+        else GCNB_GROUP_LAUNCH_PDL(8, 4, kWarpsPerCta, kStageEntries);
+      } else
       switch (variant) {
         case 1: GCNB_GROUP_LAUNCH(8, 3); break;
         case 2: GCNB_GROUP_LAUNCH(4, 6); break;
@@ -738,6 +760,8 @@ int launch_vec(const CsrView& a, const void* b, int64_t ldb, int f, const Epilog
       }
 #undef GCNB_GROUP_LAUNCH
 #undef GCNB_GROUP_LAUNCH_W
+#undef GCNB_GROUP_LAUNCH_PDL
+#undef GCNB_GROUP_ARGS
       GCNB_LAUNCH_CHECK();
       return launch_long<LPR, CH, BF16>(a, b, ldb, f, ep, out, ldo, partial, ldp, st);
     }
@@ -762,6 +786,11 @@ inline int partial_ld(int64_t f) { return (int)(ceil_div(f, 4) * 4); }
 
 }  // namespace
 
+bool pdl_enabled() {
+  tuning_init();
+  return g_pdl > 0;
+}
+
 int spmm_set_tuning(int key, int value) {
   tuning_init();
   if (key == GCNB_TUNE_SPMM_KERNEL) {
@@ -770,6 +799,9 @@ int spmm_set_tuning(int key, int value) {
   } else if (key == GCNB_TUNE_SPMM_GROUP_VARIANT) {
     GCNB_REQUIRE(value >= -1 && value <= 15, "set_tuning: group variant must be -1..15");
     g_group_variant = value;
+  } else if (key == GCNB_TUNE_PDL) {
+    GCNB_REQUIRE(value == 0 || value == 1, "set_tuning: PDL must be 0 or 1");
+    g_pdl = value;
   } else {
     GCNB_REQUIRE(false, "set_tuning: unknown key %d", key);
   }

@@ -59,6 +59,30 @@ def test_header_constants_match_binding():
     assert inspect.signature(O.degree_bins).parameters["edges"].default == _lib.BIN_EDGES
 
 
+def test_tuning_knobs_validate_their_values(lib):
+    """gcnb_set_tuning touches host state only: valid values are accepted, anything else is refused with a message
+    (the defaults -- auto kernel, auto variant, plain stream order -- are restored)."""
+    from pygcn_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "gcnb200.h")).read()
+    consts = dict(re.findall(r"#define (GCNB_TUNE_[A-Z0-9_]+) (\d+)", header))
+    assert (int(consts["GCNB_TUNE_SPMM_KERNEL"]), int(consts["GCNB_TUNE_SPMM_GROUP_VARIANT"]), int(consts["GCNB_TUNE_PDL"])) == (
+        _lib.TUNE_SPMM_KERNEL, _lib.TUNE_SPMM_GROUP_VARIANT, _lib.TUNE_PDL)
+    try:
+        for key, good, bad in ((_lib.TUNE_SPMM_KERNEL, (0, 1, 2, 3), (-1, 4)),
+                               (_lib.TUNE_SPMM_GROUP_VARIANT, tuple(range(-1, 16)), (-2, 16)),
+                               (_lib.TUNE_PDL, (0, 1), (-1, 2))):
+            for v in good:
+                assert lib.gcnb_set_tuning(key, v) == 0, (key, v, _lib.last_error())
+            for v in bad:
+                assert lib.gcnb_set_tuning(key, v) != 0 and "set_tuning" in _lib.last_error()
+        assert lib.gcnb_set_tuning(99, 0) != 0 and "unknown key" in _lib.last_error()
+    finally:
+        lib.gcnb_set_tuning(_lib.TUNE_SPMM_KERNEL, 0)
+        lib.gcnb_set_tuning(_lib.TUNE_SPMM_GROUP_VARIANT, -1)
+        lib.gcnb_set_tuning(_lib.TUNE_PDL, 0)
+
+
 def test_init_draws_match_reference(golden):
     import pygcn_b200 as P
 
