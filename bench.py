@@ -543,7 +543,15 @@ def cpu_baseline(torch, graph, layer, x_host, g_host, wl):
     sec = R.time_reference(x, w, b, adj, g, steps, 0)
     csr = R.make_reference_adj(idx, val, (n, n), "csr")
     sec_csr = R.time_reference(x, w, b, csr, g, 3, 1)
+    # the same as-written path on one thread (its per-entry COO loop barely scales with threads)
+    sec_1t = None
+    try:
+        torch.set_num_threads(1)
+        sec_1t = R.time_reference(x, w, b, adj, g, 1, 1)
+    finally:
+        torch.set_num_threads(cores)
     return {"value": graph.nnz / sec, "unit": "edges/s", "cores": cores, "kind": "port",
+            "alt_1thread_edges_per_s": (graph.nnz / sec_1t) if sec_1t else None,
             "sample": "%d fwd+bwd steps of the full workload (nnz=%d) after 2 warm-up, torch CPU %d threads, "
                       "adj = uncoalesced COO as utils.py:407-414 builds it" % (steps, graph.nnz, torch.get_num_threads()),
             "ms_per_step": sec * 1e3, "alt_csr_edges_per_s": graph.nnz / sec_csr}
