@@ -1,0 +1,29 @@
+#!/bin/bash
+# The measurements prepared at the end of round 1 (GPU budget spent), in the order they should be run.
+# Each block is one gpurun call; copy what matters from gpurun_out/ into profiles/.
+#
+# 1 GPU (about a minute of box time):
+#   gpurun --timeout 200 -- 'bash tools/next_gpu_calls.sh one'
+# 8 GPUs (charged 8x; about a minute):
+#   gpurun --gpus 8 --timeout 300 -- 'bash tools/next_gpu_calls.sh eight'
+set -x
+mkdir -p gpurun_out
+case "$1" in
+one)
+  # programmatic dependent launch of the step's kernel chain: bit-identity + graph-replay time, off / on
+  timeout 60 python tools/pdl_probe.py cbg 40 > gpurun_out/pdl_probe_cbg.txt 2>&1
+  # the bf16 panel kernels were not in the CTA-shape sweeps: 64-byte rows stay on variant 0 until this says otherwise
+  timeout 60 python tools/variant_sweep.py 0,2,13,14 20 --bf16 > gpurun_out/variant_sweep_bf16.txt 2>&1
+  # with PDL on, the whole bench line
+  GCNB_PDL=1 timeout 100 python bench.py --no-cpu-baseline > gpurun_out/bench_pdl.json 2> gpurun_out/bench_pdl.err
+  ;;
+eight)
+  for chunks in 1 2; do
+    GCNB_DIST_NCCL_CHUNKS=$chunks timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
+      --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 5 \
+      > gpurun_out/bench_n8_chunks$chunks.json 2> gpurun_out/bench_n8_chunks$chunks.err
+  done
+  ;;
+*)
+  echo "usage: $0 one|eight"; exit 2;;
+esac

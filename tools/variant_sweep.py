@@ -1,7 +1,10 @@
 """All group-per-row SpMM variants (gcnb_set_tuning) on the same graphs in ONE process: parity with torch's
 CUDA CSR spmm, then forward / transposed launch times with the L2 flushed.
 
-    python tools/variant_sweep.py [variants=0,1,2,...] [reps=20]
+    python tools/variant_sweep.py [variants=0,1,2,...] [reps=20] [--bf16]
+
+--bf16: the same sweep through gcnb_spmm_bf16 (panel rounded once with gcnb_to_bf16; parity bound 2e-2 against the
+fp32 product).
 """
 import ctypes
 import os
@@ -16,8 +19,10 @@ from pygcn_b200 import _lib
 
 
 def main():
-    variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "2,4,5,6,7,8").split(",")]
-    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+    bf16 = "--bf16" in sys.argv
+    variants = [int(v) for v in (argv[0] if len(argv) > 0 else "0,2,13,14").split(",")]
+    reps = int(argv[1]) if len(argv) > 1 else 20
     dev = torch.device("cuda:0")
     lib = _lib.load()
     flush_buf = torch.empty(B.L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
@@ -41,7 +46,18 @@ def main():
             ref = torch.sparse.mm(csr, s)
             ws = torch.empty(max(lib.gcnb_spmm_workspace_bytes(graph._h, 0, f), 256), dtype=torch.uint8, device=dev)
 
+            if bf16:
+                ld8 = (f + 7) // 8 * 8
+                panel = torch.empty(n, ld8, dtype=torch.bfloat16, device=dev)
+                _lib.check(lib.gcnb_to_bf16(n, f, ctypes.c_void_p(s.data_ptr()), f, ctypes.c_void_p(panel.data_ptr()), ld8, st),
+                           "to_bf16")
+
             def spmm(tflag):
+                if bf16:
+                    _lib.check(lib.gcnb_spmm_bf16(graph._h, tflag, ctypes.c_void_p(panel.data_ptr()), ld8, f, None,
+                                                  ctypes.c_void_p(out.data_ptr()), f, ctypes.c_void_p(ws.data_ptr()),
+                                                  ws.numel(), st), "spmm_bf16")
+                    return
                 _lib.check(lib.gcnb_spmm(graph._h, tflag, ctypes.c_void_p(s.data_ptr()), f, f, None,
                                          ctypes.c_void_p(out.data_ptr()), f, ctypes.c_void_p(ws.data_ptr()), ws.numel(), st),
                            "spmm")
@@ -65,7 +81,7 @@ def main():
                         torch.cuda.synchronize()
                         ts[tflag] = 1e3 * sum(a.elapsed_time(b) for a, b in evs) / len(evs)
                     print("%-10s f=%-3d variant %d round %d: fwd %6.1f us  A^T %6.1f us  err %.1e%s" % (
-                        name, f, v, rnd, ts[0], ts[_lib.SPMM_TRANSPOSE], err, "" if err < 1e-5 else "  PARITY FAIL"), flush=True)
+                        name, f, v, rnd, ts[0], ts[_lib.SPMM_TRANSPOSE], err, "" if err < (2e-2 if bf16 else 1e-5) else "  PARITY FAIL"), flush=True)
             _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_GROUP_VARIANT, -1), "set_tuning")
         del graph, csr
 
