@@ -31,6 +31,10 @@ WORKLOADS = {
     # configs[3]: ogbn-products-shaped, hidden layer
     "products": dict(n=2_449_029, avg_deg=25, fin=100, fout=256,
                      name="synthetic ogbn-products shape: N=2449029, nnz~62M, 100->256"),
+    # configs[4]: ogbn-papers100M-shaped, multi-GPU only: 1.6 G stored entries exceed one int32 graph handle, every
+    # rank builds its own row block from the replicated edge list (dist.build_partitioned); fixed total size
+    "papers": dict(n=111_059_956, n_raw=752_000_000, avg_deg=14, fin=128, fout=128, partitioned=True,
+                   name="synthetic ogbn-papers100M shape: N=111059956, 752M raw edges (~1.6G stored entries), 128->128"),
 }
 L2_FLUSH_BYTES = 512 << 20  # > 126 MB L2
 
@@ -165,6 +169,10 @@ def run_reference(args, wl):
     t0 = time.perf_counter()
     rs = np.random.default_rng(0)
     n_raw = n * wl["avg_deg"] // 2
+    shrink = 1
+    if wl.get("partitioned"):  # the full graph does not fit a host run of minutes: same degree, 1/512 of the nodes
+        shrink = 512
+        n, n_raw = n // shrink, wl["n_raw"] // shrink
     src = rs.integers(0, n, n_raw)
     dst = rs.integers(0, n, n_raw)
     idx, val = O.build_normalized_adjacency(src, dst, n)  # host pipeline (oracle restatement)
@@ -183,13 +191,17 @@ def run_reference(args, wl):
     csr = R.make_reference_adj(torch.from_numpy(idx), torch.from_numpy(val), (n, n), "csr")
     sec_csr = R.time_reference(x, w, b, csr, g, max(2, min(args.steps, 5)), 1)
     sample = "%d steps of the full %s workload (nnz=%d) after %d warm-up" % (args.steps, args.workload, nnz, args.warmup)
-    if args.gpus > 1:  # our arm's N-GPU workload is N x this graph (weak scaling): the CPU arm times one N-th of it
+    if shrink > 1:
+        sample = ("%d steps on a graph of the same average degree with 1/%d of the nodes (n=%d, nnz=%d; edges/s does not "
+                  "depend on the graph size on the CPU path) after %d warm-up" % (args.steps, shrink, n, nnz, args.warmup))
+    elif args.gpus > 1:  # our arm's N-GPU workload is N x this graph (weak scaling): the CPU arm times one N-th of it
         sample = ("%d steps on a 1/%d sample of the %d-GPU workload = the per-GPU graph (nnz=%d; edges/s does not depend "
                   "on the graph size on the CPU path) after %d warm-up" % (args.steps, args.gpus, args.gpus, nnz, args.warmup))
     line = {
         "impl": "reference", "metric": "gcn_layer_fwd_bwd_edges_per_sec", "value": value, "unit": "edges/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if wl.get("partitioned") else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "nnz": nnz, "in_features": fin, "out_features": fout,
                    "adj_form": "uncoalesced fp32 COO, int64 indices (utils.py:407-414), torch CPU",
                    "input_requires_grad": False},
@@ -217,6 +229,9 @@ def run_ours(args, wl):
         from pygcn_b200 import dist as D
 
         return D.bench_main(args, wl)
+    if wl.get("partitioned"):
+        raise SystemExit("--workload %s holds more stored entries than one graph handle (2^31): run it row-partitioned, "
+                         "torchrun ... bench.py --gpus 8 --workload %s" % (args.workload, args.workload))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     lib = _lib.load()

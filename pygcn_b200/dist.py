@@ -697,14 +697,29 @@ def bench_main(args, wl):
     _lib.check(lib.gcnb_check_device(), "gcnb_check_device")
     sampler = B.ClockSampler(local_rank) if rank == 0 else None
 
-    n_global = wl["n"] * world
-    wlg = dict(wl, n=n_global)
+    partitioned = bool(wl.get("partitioned"))
     t0 = time.perf_counter()
-    exchange = DistGraphConvolution.resolve_exchange(os.environ.get("GCNB_DIST_EXCHANGE", "auto"), world)
-    full = B.make_graph(P, torch, wlg, dev)          # same seed on every rank: identical global graph
-    dgraph = DistGraph.from_graph(full, rank, world, per_source=(exchange == "peer"))
-    nnz_global = full.nnz
-    del full
+    if partitioned:
+        # fixed total size (BASELINE configs[4]): the whole adjacency never exists on one GPU, every rank builds its
+        # row block of A and A^T from the replicated edge list; the exchange is the NCCL all-gather
+        n_global = wl["n"]
+        exchange = "nccl"
+        gen = torch.Generator(device=dev).manual_seed(0)
+        src = torch.randint(0, n_global, (wl["n_raw"],), generator=gen, device=dev, dtype=torch.int32)
+        dst = torch.randint(0, n_global, (wl["n_raw"],), generator=gen, device=dev, dtype=torch.int32)
+        dgraph = build_partitioned(src, dst, n_global, rank, world)
+        nnz_global = dgraph.nnz_global
+        del src, dst
+        torch.cuda.empty_cache()
+        args.no_cuda_graph = True  # a captured step would pin a second 58 GB gathered panel in the graph's pool
+    else:
+        n_global = wl["n"] * world
+        wlg = dict(wl, n=n_global)
+        exchange = DistGraphConvolution.resolve_exchange(os.environ.get("GCNB_DIST_EXCHANGE", "auto"), world)
+        full = B.make_graph(P, torch, wlg, dev)          # same seed on every rank: identical global graph
+        dgraph = DistGraph.from_graph(full, rank, world, per_source=(exchange == "peer"))
+        nnz_global = full.nnz
+        del full
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
     n_local = dgraph.n_rows()
@@ -842,8 +857,10 @@ def bench_main(args, wl):
         line = {
             "metric": "gcn_layer_fwd_bwd_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"] + " x %d GPUs (N=%d, row-partitioned by nnz)" % (world, n_global),
+            "scaling": "strong" if partitioned else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"] + ((" over %d GPUs (row-partitioned by nnz, partitioned build)" % world)
+                                                  if partitioned else
+                                                  " x %d GPUs (N=%d, row-partitioned by nnz)" % (world, n_global)),
                        "nnz": nnz_global, "n": n_global, "in_features": fin, "out_features": fout,
                        "input_requires_grad": False, "l2": "flushed between timed steps (512 MiB write)",
                        "cuda_graph": cg is not None, "graph_build_s": build_s, "bounds": dgraph.bounds,

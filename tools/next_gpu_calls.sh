@@ -24,6 +24,13 @@ eight)
       > gpurun_out/bench_n8_chunks$chunks.json 2> gpurun_out/bench_n8_chunks$chunks.err
   done
   ;;
+papers) ;;  # below
 *)
-  echo "usage: $0 one|eight"; exit 2;;
+  echo "usage: $0 one|eight|papers"; exit 2;;
 esac
+# BASELINE configs[4], never run end to end in round 1 (one rank's share was, tools/papers_block.py):
+#   gpurun --gpus 8 --timeout 600 -- 'bash tools/next_gpu_calls.sh papers'
+if [ "$1" = papers ]; then
+  timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 \
+    bench.py --gpus 8 --workload papers --steps 5 --warmup 3 > gpurun_out/bench_n8_papers.json 2> gpurun_out/bench_n8_papers.err
+fi
