@@ -810,24 +810,82 @@ def bench_main(args, wl):
     ms_per_step = total_ms.item() / args.steps
     value = nnz_global / (ms_per_step * 1e-3)
 
-    # end to end from pinned host buffers, per rank; max over ranks
-    e2e_s = 0.0
-    for i in range(2 + args.steps):
-        flush()
-        torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
-        xd = x_host.to(dev, non_blocking=True)
-        gd = g_host.to(dev, non_blocking=True)
-        layer.inner.weight.grad = None
-        layer.inner.bias.grad = None
-        o = layer(xd, dgraph)
-        o.backward(gd)
-        layer.inner.weight.grad.cpu()
-        layer.inner.bias.grad.cpu()
-        torch.cuda.synchronize()
-        if i >= 2:
-            e2e_s += time.perf_counter() - t0
+    # end to end from pinned host buffers, per rank; max over ranks.  As in the single-GPU arm the inputs are
+    # double-buffered: step i+1's H2D copies run on a copy stream while step i computes; every step still copies
+    # its own X and G in and reads dW / db back inside the timed region.  No L2 flush here: one step touches the
+    # row block's index stream and the gathered panel, more than the L2 holds.
+    def e2e_sequential():
+        total = 0.0
+        for i in range(2 + args.steps):
+            flush()
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            xd = x_host.to(dev, non_blocking=True)
+            gd = g_host.to(dev, non_blocking=True)
+            layer.inner.weight.grad = None
+            layer.inner.bias.grad = None
+            o = layer(xd, dgraph)
+            o.backward(gd)
+            layer.inner.weight.grad.cpu()
+            layer.inner.bias.grad.cpu()
+            torch.cuda.synchronize()
+            if i >= 2:
+                total += time.perf_counter() - t0
+        return total
+
+    def e2e_pipelined():
+        copy_stream = torch.cuda.Stream()
+        bufs = [(torch.empty_like(x), torch.empty_like(g)) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(i):
+            b = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[b])  # the step that last read this buffer pair has finished
+                bufs[b][0].copy_(x_host, non_blocking=True)
+                bufs[b][1].copy_(g_host, non_blocking=True)
+                ready[b].record(copy_stream)
+
+        def loop(k):
+            for b in range(2):
+                done[b].record()
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            prefetch(0)
+            for i in range(k):
+                if i + 1 < k:
+                    prefetch(i + 1)
+                b = i % 2
+                torch.cuda.current_stream().wait_event(ready[b])
+                layer.inner.weight.grad = None
+                layer.inner.bias.grad = None
+                o = layer(bufs[b][0], dgraph)
+                o.backward(bufs[b][1])
+                done[b].record()
+                layer.inner.weight.grad.cpu()  # the step's result, read back every step (synchronises)
+                layer.inner.bias.grad.cpu()
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0
+
+        loop(3)
+        return loop(args.steps)
+
+    e2e_how = "wall clock over K eager steps of layer(x_dev, dist_graph); backward; grads.cpu(); max over ranks; "
+    if partitioned or os.environ.get("GCNB_BENCH_E2E", "pipelined") == "sequential":
+        e2e_s = e2e_sequential()  # (a second pair of 7 GB input buffers is not worth it at the papers size)
+        e2e_how += "inputs copied from pinned host memory at the start of every step"
+    else:
+        try:
+            e2e_s = e2e_pipelined()
+            e2e_how += "inputs double-buffered from pinned host memory on a copy stream"
+        except Exception as e:  # pragma: no cover  (same code and shapes on every rank: all ranks take this path together)
+            sys.stderr.write("rank %d: pipelined e2e loop failed (%r); timing the sequential loop\n" % (rank, e))
+            torch.cuda.synchronize()
+            e2e_s = e2e_sequential()
+            e2e_how += "inputs copied from pinned host memory at the start of every step"
     e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = nnz_global / (e2e_t.item() / args.steps)
@@ -873,7 +931,8 @@ def bench_main(args, wl):
                        "nccl_chunks": layer.nccl_chunks},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": (x_host.numel() + g_host.numel()) * 4,
-                    "d2h_bytes_per_step": (fin * fout + fout) * 4, "ms_per_step": e2e_t.item() / args.steps * 1e3},
+                    "d2h_bytes_per_step": (fin * fout + fout) * 4, "ms_per_step": e2e_t.item() / args.steps * 1e3,
+                    "how": e2e_how},
             "gpu_launches": 10 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "spmm_group_kernel<LPR=8,U=4,24 CTAs/SM,W=2,SE=16> on rank 0's %s" % ("diagonal block" if dgraph.split else "row block (all-gathered panel)"),
