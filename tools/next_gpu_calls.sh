@@ -18,6 +18,10 @@ one)
   GCNB_PDL=1 timeout 100 python bench.py --no-cpu-baseline > gpurun_out/bench_pdl.json 2> gpurun_out/bench_pdl.err
   ;;
 eight)
+  # the double-buffered end-to-end loop of the multi-GPU arm (opt-in until this has run)
+  GCNB_BENCH_E2E=pipelined timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
+    --master-addr 127.0.0.1 --master-port 29510 bench.py --gpus 8 --steps 20 --warmup 5 \
+    > gpurun_out/bench_n8_e2e_pipelined.json 2> gpurun_out/bench_n8_e2e_pipelined.err
   for chunks in 1 2; do
     GCNB_DIST_NCCL_CHUNKS=$chunks timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
       --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 5 \
