@@ -254,6 +254,11 @@ int gcnb_peer_wait(const uint32_t* d_flag, const uint32_t* d_epoch, void* stream
 int gcnb_peer_wait_lag(const uint32_t* d_word, const uint32_t* d_epoch, uint32_t lag, void* stream);
 /* copy-engine transfer to / from mapped peer memory: cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) */
 int gcnb_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+/* NVLS multicast push (exchange "nvls", pygcn_b200/dist.py::MulticastExchange): `bytes` of src (local) stored to the
+ * multicast address mc_dst with multimem.st -- the NVSwitch replicates every store into the same offset of every
+ * rank's symmetric buffer.  The caller brackets it with device barriers over all ranks (slots free / slots landed).
+ * Nothing in the reference (single-GPU). */
+int gcnb_multimem_push(void* mc_dst, const void* src, size_t bytes, int ctas, void* stream);
 int gcnb_peer_ack(uint32_t* peer_ack, const uint32_t* d_epoch, void* stream);
 
 /* Tuning knobs (process-wide, not thread-safe against concurrent launches; for tests and benchmarks).

@@ -190,6 +190,34 @@ extern "C" int gcnb_peer_copy(void* dst, const void* src, size_t bytes, void* st
   return GCNB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- NVLS multicast push
+// One store per 16 bytes to a MULTICAST address (an NVSwitch multicast object bound to the same offset of every
+// rank's symmetric buffer): the switch replicates it into all peers' memory, so an all-gather costs each GPU one
+// slot of egress instead of world - 1.  Written in round 1 after the multi-GPU minutes were spent: not yet run.
+__global__ void __launch_bounds__(512)
+multimem_push_kernel(float4* __restrict__ mc_dst, const float4* __restrict__ src, size_t n16) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const float4 v = src[i];
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_dst + i), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+  }
+}
+
+extern "C" int gcnb_multimem_push(void* mc_dst, const void* src, size_t bytes, int ctas, void* stream) {
+  GCNB_REQUIRE(mc_dst && src, "multimem_push: null argument");
+  GCNB_REQUIRE(bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(mc_dst) & 15u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0,
+               "multimem_push: 16-byte aligned addresses and size required");
+  if (bytes == 0) return GCNB_OK;
+  if (ctas < 1) ctas = 1;
+  if (ctas > 8 * kNumSMs) ctas = 8 * kNumSMs;
+  multimem_push_kernel<<<ctas, 512, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(mc_dst),
+                                                               reinterpret_cast<const float4*>(src), bytes / 16);
+  GCNB_LAUNCH_CHECK();
+  return GCNB_OK;
+}
+
 extern "C" int gcnb_peer_ack(uint32_t* peer_ack, const uint32_t* d_epoch, void* stream) {
   GCNB_REQUIRE(peer_ack && d_epoch, "peer_ack: null argument");
   ack_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(peer_ack, d_epoch);

@@ -480,6 +480,69 @@ class CollectiveExchange:
         pass
 
 
+class MulticastExchange:
+    """Exchange "nvls" (opt-in; written after round 1's multi-GPU minutes were spent -- NOT yet run on hardware):
+    gathered [world * pad_rows, f] lives in torch's symmetric memory (torch.distributed._symmetric_memory: a cuMem
+    allocation every peer maps, bound to an NVLS multicast object -- plumbing), and the all-gather is OUR kernel:
+    every rank stores its slot once to the multicast address (gcnb_multimem_push, multimem.st) and the NVSwitch
+    replicates it into all ranks' buffers, so a GPU sends one slot instead of world - 1 and the exchange is bounded
+    by its ingress alone.  allgather() = barrier (every rank is done reading the previous contents) -> push ->
+    barrier (every slot has landed); both barriers are the symmetric-memory handle's device barriers on the current
+    stream, the whole sequence is stream-ordered and capturable."""
+
+    PUSH_CTAS = int(os.environ.get("GCNB_NVLS_PUSH_CTAS", "64"))
+
+    def __init__(self, rank, world, pad_rows, f, device, group=None):
+        from . import _lib
+
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.rank, self.world, self.pad_rows, self.f, self.device = rank, world, pad_rows, f, device
+        self.slot_bytes = pad_rows * f * 4
+        ok, why = 1, ""
+        self.hdl = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            pg = group if group is not None else dist.group.WORLD
+            with torch.cuda.device(device):
+                self.gathered = symm.empty((world * pad_rows, f), dtype=torch.float32, device=device)
+                self.hdl = symm.rendezvous(self.gathered, pg)
+            if not int(self.hdl.multicast_ptr):  # 0 when the group has no NVLS multicast object
+                ok, why = 0, "no NVLS multicast support for this group"
+        except Exception as e:  # every rank must learn it (collective below)
+            ok, why = 0, repr(e)
+        flag = torch.tensor([float(ok)], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if flag.item() < 1:
+            raise PeerExchangeUnavailable("multicast exchange unavailable on at least one rank (%s)" % (why or "peer"))
+        self.mc_slot = int(self.hdl.multicast_ptr) + rank * self.slot_bytes
+        self.my_slot = self.gathered[rank * pad_rows:(rank + 1) * pad_rows]
+
+    def allgather(self):
+        """Every rank's my_slot -> every rank's gathered, in stream order on the current stream."""
+        with torch.cuda.device(self.device):
+            self.hdl.barrier(channel=0)  # nobody still reads the slots of the previous exchange
+            self._lib.check(self.lib.gcnb_multimem_push(self.mc_slot, self.my_slot.data_ptr(), self.slot_bytes, self.PUSH_CTAS,
+                                                        ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                            "gcnb_multimem_push")
+            self.hdl.barrier(channel=1)  # every slot has landed everywhere
+
+    def close(self):
+        self.hdl = None
+        self.gathered = self.my_slot = None
+
+
+def dist_spmm_gathered(ops, dgraph, diag, remote, exch, bias=None, relu=False):
+    """out_p over an exchange object that gathers in place (MulticastExchange): this rank's slot is already in
+    exch.my_slot; the diagonal block (if the row block is split) runs before the exchange."""
+    out = ops.empty((dgraph.n_rows(), exch.f), exch.gathered)
+    if dgraph.split:
+        ops.spmm_block(diag, exch.my_slot, out, False)
+    exch.allgather()
+    return ops.spmm_block(remote, exch.gathered, out, dgraph.split, bias, relu)
+
+
 def dist_spmm_pipelined(ops, dgraph, blocks, exch, bias=None, relu=False):
     """out_p = sum_i blocks[i] @ gathered (+ bias) (relu) over the phases of dgraph.phases (groups of
     source ranks p, p+1, ...): this rank's slot is already in exch.my_slot; every other slot is consumed
@@ -562,6 +625,8 @@ def dist_layer_forward(ops, dgraph, x, w, b, relu=False, group=None, exch=None, 
     pipelines the NCCL exchange over column chunks of the panel instead (dist_spmm_chunked)."""
     if exch is not None and dgraph.world > 1:
         ops.gemm(x, w, out=exch.my_slot)             # X_p W straight into this rank's slot
+        if hasattr(exch, "allgather"):  # gathers in place (MulticastExchange)
+            return dist_spmm_gathered(ops, dgraph, dgraph.fwd_diag, dgraph.fwd_remote, exch, b, relu)
         return dist_spmm_pipelined(ops, dgraph, dgraph.fwd_blocks, exch, b, relu)
     support = ops.empty((dgraph.pad_rows, w.shape[1]), x)
     ops.gemm(x, w, out=support)
@@ -573,7 +638,10 @@ def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=Tru
     fin, fout = w.shape
     if exch is not None and dgraph.world > 1:
         db, _ = ops.colsum(g, y, exch.my_slot)       # local part of db; G (masked) staged into this rank's slot
-        ds = dist_spmm_pipelined(ops, dgraph, dgraph.bwd_blocks, exch)  # rows p of A^T G
+        if hasattr(exch, "allgather"):  # gathers in place (MulticastExchange)
+            ds = dist_spmm_gathered(ops, dgraph, dgraph.bwd_diag, dgraph.bwd_remote, exch)
+        else:
+            ds = dist_spmm_pipelined(ops, dgraph, dgraph.bwd_blocks, exch)  # rows p of A^T G
     else:
         gm = ops.empty((dgraph.pad_rows, fout), g)
         db, _ = ops.colsum(g, y, gm)                 # local part of db; G (masked) staged into its slot
@@ -616,8 +684,8 @@ class DistGraphConvolution(torch.nn.Module):
         super().__init__()
         from .layers import GraphConvolution
 
-        if exchange not in ("auto", "peer", "nccl"):
-            raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+        if exchange not in ("auto", "peer", "nccl", "nvls"):
+            raise ValueError("exchange must be 'auto', 'peer', 'nccl' or 'nvls'")
         self.inner = GraphConvolution(in_features, out_features, bias, fuse_relu=fuse_relu, precision=precision)
         self.group = group
         self.exchange = exchange
@@ -641,8 +709,10 @@ class DistGraphConvolution(torch.nn.Module):
         return exchange
 
     def _exchanges(self, dgraph, dev):
-        if dgraph.world == 1 or self.resolve_exchange(self.exchange, dgraph.world) == "nccl" or dgraph.fwd_blocks is None:
+        kind = self.resolve_exchange(self.exchange, dgraph.world)
+        if dgraph.world == 1 or kind == "nccl" or (kind == "peer" and dgraph.fwd_blocks is None):
             return None, None
+        cls = MulticastExchange if kind == "nvls" else PeerExchange
         if self._exch is None or self._exch[0] is not dgraph:
             if self._exch is not None:
                 self._exch[1].close()
@@ -650,9 +720,9 @@ class DistGraphConvolution(torch.nn.Module):
                 self._exch = None
             f = self.inner.out_features
             try:
-                ef = PeerExchange(dgraph.rank, dgraph.world, dgraph.pad_rows, f, dev, self.group)
+                ef = cls(dgraph.rank, dgraph.world, dgraph.pad_rows, f, dev, self.group)
                 try:
-                    eb = PeerExchange(dgraph.rank, dgraph.world, dgraph.pad_rows, f, dev, self.group)
+                    eb = cls(dgraph.rank, dgraph.world, dgraph.pad_rows, f, dev, self.group)
                 except PeerExchangeUnavailable:
                     ef.close()
                     raise
@@ -927,6 +997,9 @@ def bench_main(args, wl):
                        "exchange": ("peer: own push kernel over NVLink peer memory (P2P stores + release flags), one "
                                     "column block per source rank consumed as its slot lands; NCCL all-reduce of dW,db"
                                     if exchange == "peer" else
+                                    "nvls: own multimem.st push of each rank's slot to the NVLS multicast address of a "
+                                    "symmetric buffer, device barriers, then the SpMM over the row block; NCCL "
+                                    "all-reduce of dW,db" if exchange == "nvls" else
                                     "nccl: all-gather of the X.W / G panels, then the SpMM over the row block; "
                                     "all-reduce of dW,db"),
                        "nccl_chunks": layer.nccl_chunks},

@@ -62,6 +62,20 @@ class NumpyOps:
         return torch.full(shape, float("nan"), dtype=torch.float32)  # padding must never be read
 
 
+class InPlaceGather:
+    """Stand-in for dist.MulticastExchange on CPU: same interface (gathered, my_slot, f, allgather()), the all-gather
+    itself done by gloo."""
+
+    def __init__(self, rank, world, pad_rows, f):
+        self.f = f
+        self.gathered = torch.full((world * pad_rows, f), float("nan"), dtype=torch.float32)
+        self.my_slot = self.gathered[rank * pad_rows:(rank + 1) * pad_rows]
+        self.my_slot.zero_()
+
+    def allgather(self):
+        dist.all_gather_into_tensor(self.gathered, self.my_slot.clone())
+
+
 def _problem(n=300, seed=3, fout=5):
     rs = np.random.default_rng(seed)
     src = (n * rs.random(4000) ** 2).astype(np.int64)  # skewed degrees: nnz balance != row balance
@@ -93,12 +107,15 @@ def _worker(rank, world, port, outdir, relu, split=True, pipelined=False, chunks
         xt, gt = torch.from_numpy(x[r0:r1].copy()), torch.from_numpy(g[r0:r1].copy())
         wt, bt = torch.from_numpy(w), torch.from_numpy(b)
         ef = eb = None
-        if pipelined:  # one column block per source rank, consumed in the order p, p+1, ... (exchange "peer")
+        if pipelined is True:  # one column block per source rank, consumed in the order p, p+1, ... (exchange "peer")
             dg.phases = D.exchange_phases(rank, world)
             dg.fwd_blocks = [HostBlock(idx, val, r0, r1, bounds=bounds, pad=pad, only=qs) for qs in dg.phases]
             dg.bwd_blocks = [HostBlock(tidx, val, r0, r1, bounds=bounds, pad=pad, only=qs) for qs in dg.phases]
             ef = D.CollectiveExchange(rank, world, pad, w.shape[1], xt)
             eb = D.CollectiveExchange(rank, world, pad, w.shape[1], xt)
+        if pipelined == "gathered":  # the in-place all-gather route of exchange "nvls" (dist_spmm_gathered)
+            ef = InPlaceGather(rank, world, pad, w.shape[1])
+            eb = InPlaceGather(rank, world, pad, w.shape[1])
         out = D.dist_layer_forward(ops, dg, xt, wt, bt, relu=relu, exch=ef, chunks=chunks)
         dx, dw, db = D.dist_layer_backward(ops, dg, xt, wt, gt, out if relu else None, True, True, exch=eb, chunks=chunks)
         np.savez(os.path.join(outdir, "r%d.npz" % rank), out=out.numpy(), dx=dx.numpy(), dw=dw.numpy(), db=db.numpy(),
@@ -125,7 +142,9 @@ def _free_port():
     (2, False, True, False, 1), (2, True, False, False, 1), (3, False, True, False, 1), (2, True, False, True, 1),
     (3, False, False, True, 1), (4, True, False, True, 1),
     # the all-gather exchange pipelined over column chunks of the panel (dist_spmm_chunked), 37-column panels
-    (2, True, False, False, 2), (3, False, False, False, 4)])
+    (2, True, False, False, 2), (3, False, False, False, 4),
+    # the in-place gathered route (exchange "nvls"), unsplit and split row blocks
+    (2, True, False, "gathered", 1), (3, False, True, "gathered", 1)])
 def test_row_partitioned_layer_matches_single_process_oracle(world, relu, split, pipelined, chunks):
     with tempfile.TemporaryDirectory() as d:
         mp.spawn(_worker, args=(world, _free_port(), d, relu, split, pipelined, chunks), nprocs=world, join=True)

@@ -46,7 +46,8 @@ def main():
     ok = ok and same and dg2.nnz_global == full.nnz
     if rank == 0:
         print("partitioned build == cut of the full graph: %s (nnz_global %d)" % (same, dg2.nnz_global), flush=True)
-    for exchange in ("peer", "nccl"):
+    # GCNB_DIST_CHECK_EXCHANGES=peer,nccl,nvls adds the NVLS multicast exchange (written at the end of round 1, not yet run)
+    for exchange in os.environ.get("GCNB_DIST_CHECK_EXCHANGES", "peer,nccl").split(","):
         torch.manual_seed(42)
         layer = D.DistGraphConvolution(fin, fout, fuse_relu=True, exchange=exchange).to(dev)
         xl = x[r0:r1].clone().requires_grad_(True)

@@ -4,6 +4,8 @@
 #
 # 1 GPU (about a minute of box time):
 #   gpurun --timeout 200 -- 'bash tools/next_gpu_calls.sh one'
+# 2 GPUs (charged 2x):
+#   gpurun --gpus 2 --timeout 300 -- 'bash tools/next_gpu_calls.sh two'
 # 8 GPUs (charged 8x; about a minute):
 #   gpurun --gpus 8 --timeout 300 -- 'bash tools/next_gpu_calls.sh eight'
 set -x
@@ -17,7 +19,16 @@ one)
   # with PDL on, the whole bench line
   GCNB_PDL=1 timeout 100 python bench.py --no-cpu-baseline > gpurun_out/bench_pdl.json 2> gpurun_out/bench_pdl.err
   ;;
+two)
+  # parity of every exchange with the single-GPU layer at 2 GPUs, eager and graph replay; "nvls" = the multicast
+  # exchange (own multimem.st push into torch symmetric memory), written but never run in round 1
+  GCNB_DIST_CHECK_EXCHANGES=peer,nccl,nvls timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
+    --master-addr 127.0.0.1 --master-port 29513 tools/dist_check.py > gpurun_out/dist_check_2gpu_nvls.txt 2>&1
+  ;;
 eight)
+  GCNB_DIST_EXCHANGE=nvls timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
+    --master-addr 127.0.0.1 --master-port 29509 bench.py --gpus 8 --steps 20 --warmup 5 \
+    > gpurun_out/bench_n8_nvls.json 2> gpurun_out/bench_n8_nvls.err
   # the double-buffered end-to-end loop of the multi-GPU arm (opt-in until this has run)
   GCNB_BENCH_E2E=pipelined timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
     --master-addr 127.0.0.1 --master-port 29510 bench.py --gpus 8 --steps 20 --warmup 5 \
@@ -30,7 +41,7 @@ eight)
   ;;
 papers) ;;  # below
 *)
-  echo "usage: $0 one|eight|papers"; exit 2;;
+  echo "usage: $0 one|two|eight|papers"; exit 2;;
 esac
 # BASELINE configs[4], never run end to end in round 1 (one rank's share was, tools/papers_block.py):
 #   gpurun --gpus 8 --timeout 600 -- 'bash tools/next_gpu_calls.sh papers'
