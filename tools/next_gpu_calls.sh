@@ -12,6 +12,8 @@ set -x
 mkdir -p gpurun_out
 case "$1" in
 one)
+  # the opt-in paths' own parity tests (skipped by default because they had never run on hardware)
+  GCNB_TEST_UNVERIFIED=1 timeout 120 python -m pytest tests/test_gpu_optin.py -m gpu -x -q > gpurun_out/pytest_optin.log 2>&1
   # programmatic dependent launch of the step's kernel chain: bit-identity + graph-replay time, off / on
   timeout 60 python tools/pdl_probe.py cbg 40 > gpurun_out/pdl_probe_cbg.txt 2>&1
   # the bf16 panel kernels were not in the CTA-shape sweeps: 64-byte rows stay on variant 0 until this says otherwise
