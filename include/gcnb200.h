@@ -264,7 +264,7 @@ int gcnb_peer_ack(uint32_t* peer_ack, const uint32_t* d_epoch, void* stream);
 /* Tuning knobs (process-wide, not thread-safe against concurrent launches; for tests and benchmarks).
  *   GCNB_TUNE_SPMM_KERNEL: 0 auto (default), 1 warp-per-row shuffle kernel, 2 group-per-row kernel,
  *                          3 TMA-staged warp-per-row kernel
- *   GCNB_TUNE_SPMM_GROUP_VARIANT: -1 auto, 0..15 = (gathers in flight, CTAs/SM, warps per CTA, stage entries) of
+ *   GCNB_TUNE_SPMM_GROUP_VARIANT: -1 auto, 0..17 = (gathers in flight, CTAs/SM, warps per CTA, stage entries) of
  *   the group kernel (spmm.cu) */
 #define GCNB_TUNE_SPMM_KERNEL 1
 #define GCNB_TUNE_SPMM_GROUP_VARIANT 2

@@ -70,7 +70,7 @@ def test_tuning_knobs_validate_their_values(lib):
         _lib.TUNE_SPMM_KERNEL, _lib.TUNE_SPMM_GROUP_VARIANT, _lib.TUNE_PDL)
     try:
         for key, good, bad in ((_lib.TUNE_SPMM_KERNEL, (0, 1, 2, 3), (-1, 4)),
-                               (_lib.TUNE_SPMM_GROUP_VARIANT, tuple(range(-1, 16)), (-2, 16)),
+                               (_lib.TUNE_SPMM_GROUP_VARIANT, tuple(range(-1, 18)), (-2, 18)),
                                (_lib.TUNE_PDL, (0, 1), (-1, 2))):
             for v in good:
                 assert lib.gcnb_set_tuning(key, v) == 0, (key, v, _lib.last_error())

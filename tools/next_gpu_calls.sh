@@ -16,6 +16,8 @@ one)
   GCNB_TEST_UNVERIFIED=1 timeout 120 python -m pytest tests/test_gpu_optin.py -m gpu -x -q > gpurun_out/pytest_optin.log 2>&1
   # programmatic dependent launch of the step's kernel chain: bit-identity + graph-replay time, off / on
   timeout 60 python tools/pdl_probe.py cbg 40 > gpurun_out/pdl_probe_cbg.txt 2>&1
+  # the persistent group kernel with the next row set prefetched (variants 16 / 17) against the defaults (13 / 14)
+  timeout 60 python tools/variant_sweep.py 13,16,14,17 20 > gpurun_out/variant_sweep_persistent.txt 2>&1
   # the bf16 panel kernels were not in the CTA-shape sweeps: 64-byte rows stay on variant 0 until this says otherwise
   timeout 60 python tools/variant_sweep.py 0,2,13,14 20 --bf16 > gpurun_out/variant_sweep_bf16.txt 2>&1
   # with PDL on, the whole bench line
