@@ -505,6 +505,7 @@ class MulticastExchange:
             import torch.distributed._symmetric_memory as symm
 
             pg = group if group is not None else dist.group.WORLD
+            self._group_name = pg.group_name
             with torch.cuda.device(device):
                 self.gathered = symm.empty((world * pad_rows, f), dtype=torch.float32, device=device)
                 self.hdl = symm.rendezvous(self.gathered, pg)
@@ -521,6 +522,12 @@ class MulticastExchange:
 
     def allgather(self):
         """Every rank's my_slot -> every rank's gathered, in stream order on the current stream."""
+        if os.environ.get("GCNB_NVLS_LIBRARY_PUSH") == "1":
+            # debugging aid for the first hardware run: torch's own multimem all-gather over the same symmetric
+            # buffer (barrier, multimem.st, barrier in one library kernel) -- tells a bug in our push from an
+            # environment without NVLS.  Never the product path.
+            torch.ops.symm_mem.multimem_all_gather_out(self.my_slot.clone(), self._group_name, self.gathered)
+            return
         with torch.cuda.device(self.device):
             self.hdl.barrier(channel=0)  # nobody still reads the slots of the previous exchange
             self._lib.check(self.lib.gcnb_multimem_push(self.mc_slot, self.my_slot.data_ptr(), self.slot_bytes, self.PUSH_CTAS,
