@@ -39,19 +39,26 @@ from torch.autograd.function import once_differentiable
 
 
 # ---------------------------------------------------------------------------- host logic
-def partition_rows_by_nnz(rowptr, world):
-    """Row-block boundaries [b_0=0, ..., b_world=N] with ~equal stored entries per block.
+def partition_rows_by_nnz(rowptr, world, row_weight=0.0):
+    """Row-block boundaries [b_0=0, ..., b_world=N] with ~equal cost per block, cost = stored entries +
+    row_weight * rows.
 
     rowptr: 1-D integer tensor/array of length N+1 (host).  Boundaries are non-decreasing; a block
     may be empty when there are fewer rows than ranks.
+    row_weight = 0 (default) balances stored entries alone: right for the SpMM, and on graphs with even
+    degrees the blocks then hold equal row counts too.  On power-law graphs they do not (products-shaped R-MAT,
+    8 ranks: 21 K ... 909 K rows, tools/halo_fraction.py), and the all-gather ships world * max(rows) padded
+    panel rows; row_weight = the average degree weighs both equally and bounds that padding.
     """
     rp = torch.as_tensor(rowptr, dtype=torch.int64).cpu()
     n = rp.numel() - 1
-    nnz = int(rp[-1])
+    if row_weight:
+        rp = rp.to(torch.float64) + float(row_weight) * torch.arange(n + 1, dtype=torch.float64)
+    total = rp[-1].item()
     bounds = [0]
     for k in range(1, world):
-        target = (nnz * k) // world
-        r = int(torch.searchsorted(rp, torch.tensor([target], dtype=torch.int64), right=False)[0])
+        target = (total * k) // world if not row_weight else total * k / world
+        r = int(torch.searchsorted(rp, torch.tensor([target], dtype=rp.dtype), right=False)[0])
         r = min(max(r, bounds[-1]), n)
         bounds.append(r)
     bounds.append(n)
@@ -114,7 +121,7 @@ class DistGraph:
         return max(8, (m + 7) // 8 * 8)
 
     @classmethod
-    def from_graph(cls, graph, rank, world, bounds=None, split=None, per_source=False):
+    def from_graph(cls, graph, rank, world, bounds=None, split=None, per_source=False, row_weight=0.0):
         """Cut the row block of `rank` out of a full device `Graph` (CUDA).  split=None decides from
         the share of stored entries in the diagonal block (SPLIT_MIN_DIAG_FRACTION).
         per_source=True additionally cuts one column block per source rank (exchange "peer")."""
@@ -123,7 +130,7 @@ class DistGraph:
 
         lib = _lib.load()
         if bounds is None:
-            bounds = partition_rows_by_nnz(graph.csr()[0].cpu(), world)
+            bounds = partition_rows_by_nnz(graph.csr()[0].cpu(), world, row_weight)
         r0, r1 = bounds[rank], bounds[rank + 1]
         pad = cls.padded_rows(bounds)
         hb = (ctypes.c_int64 * (world + 1))(*bounds)
@@ -230,7 +237,7 @@ def _partition_blocks(rank, world, bounds, pad, lrp, lcol, a, rows, rowsum_globa
     return DistGraph(rank, world, bounds, pad, None, fwd, None, bwd, fwd.nnz, n_global_nnz, False)
 
 
-def build_partitioned(src, dst, n, rank, world, bounds=None, group=None):
+def build_partitioned(src, dst, n, rank, world, bounds=None, group=None, row_weight=0.0):
     """This rank's DistGraph from a (replicated) edge list WITHOUT building the whole adjacency on any GPU:
     what a papers100M-sized graph needs (3.2 G stored entries exceed one int32 handle).
     Bit-identical to cutting the block out of the single-GPU `Graph.from_edges` result.  Collective:
@@ -239,7 +246,7 @@ def build_partitioned(src, dst, n, rank, world, bounds=None, group=None):
     if bounds is None:  # balance stored entries with the incident-edge count as the estimate
         deg = torch.bincount(src.long(), minlength=n) + torch.bincount(dst.long(), minlength=n) + 1
         rp = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), deg.cumsum(0)])
-        bounds = partition_rows_by_nnz(rp, world)
+        bounds = partition_rows_by_nnz(rp, world, row_weight)
     pad = DistGraph.padded_rows(bounds)
     lrp, lcol, a, rows, rowsum = _partition_counts(src, dst, n, bounds[rank], bounds[rank + 1])
     slot = torch.ones(pad, dtype=torch.float64, device=dev)

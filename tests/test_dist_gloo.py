@@ -199,5 +199,16 @@ def test_partition_balances_nnz_and_exchange_is_a_matching():
         assert max(per) - min(per) <= 2 * np.diff(rowptr).max()  # within one (long) row of perfect balance
         pad = D.DistGraph.padded_rows(b)
         assert pad % 8 == 0 and pad >= max(b[i + 1] - b[i] for i in range(world))
+    # row_weight: cost = stored entries + weight * rows.  Degrees sorted descending (hubs first, like the low ids of an
+    # R-MAT graph): entries alone give the first block few rows and the last one most of them; weighing rows by the
+    # average degree bounds the largest block (= the padded all-gather slot) at the price of some nnz imbalance
+    deg = np.sort((3000 * np.random.default_rng(5).random(4000) ** 8).astype(np.int64) + 1)[::-1]
+    rp = np.concatenate([[0], np.cumsum(deg)])
+    plain = D.partition_rows_by_nnz(rp, 8)
+    mixed = D.partition_rows_by_nnz(rp, 8, row_weight=float(deg.mean()))
+    rows = lambda b: [b[i + 1] - b[i] for i in range(8)]
+    assert mixed[0] == 0 and mixed[-1] == 4000 and all(mixed[i] <= mixed[i + 1] for i in range(8))
+    assert max(rows(mixed)) < 0.5 * max(rows(plain))
+    assert max(rows(mixed)) <= 2 * 4000 // 8 + 1   # at most twice the even share when both terms weigh the same
     # more ranks than rows: empty blocks allowed
     assert D.partition_rows_by_nnz(np.array([0, 2, 5]), 4)[-1] == 2

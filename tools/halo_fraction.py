@@ -27,7 +27,17 @@ def analyse(name, src, dst, n, world):
     rows, cols = keys // n, keys % n
     nnz = keys.size
     rowptr = np.searchsorted(rows, np.arange(n + 1))
-    bounds = [0] + [int(np.searchsorted(rowptr, nnz * k // world)) for k in range(1, world)] + [n]
+    report(name, rows, cols, n, nnz, rowptr, world,
+           [0] + [int(np.searchsorted(rowptr, nnz * k // world)) for k in range(1, world)] + [n], "entries only")
+    # cost = entries + (average degree) * rows: what dist.partition_rows_by_nnz(row_weight=avg degree) cuts
+    w = nnz / n
+    cost = rowptr + w * np.arange(n + 1)
+    report(name, rows, cols, n, nnz, rowptr, world,
+           [0] + [int(np.searchsorted(cost, cost[-1] * k / world)) for k in range(1, world)] + [n],
+           "entries + avg degree x rows")
+
+
+def report(name, rows, cols, n, nnz, rowptr, world, bounds, how):
     total_needed = total_full = 0
     worst = 0.0
     for p in range(world):
@@ -38,7 +48,11 @@ def analyse(name, src, dst, n, world):
         total_needed += remote.size
         total_full += full
         worst = max(worst, remote.size / max(full, 1))
-    print("%-8s n=%d nnz=%d world=%d: rows per rank %s" % (name, n, nnz, world, [bounds[i + 1] - bounds[i] for i in range(world)]))
+    per = [bounds[i + 1] - bounds[i] for i in range(world)]
+    ent = [int(rowptr[bounds[i + 1]] - rowptr[bounds[i]]) for i in range(world)]
+    print("%-8s n=%d nnz=%d world=%d, balanced by %s: rows per rank %s" % (name, n, nnz, world, how, per))
+    print("         padded all-gather rows / real rows: %.2f; largest block's entries / mean: %.2f" % (
+        world * max(per) / n, max(ent) / (nnz / world)))
     print("         remote panel rows a rank reads: %.1f %% of what the all-gather delivers (worst rank %.1f %%)" % (
         100.0 * total_needed / total_full, 100.0 * worst))
 
