@@ -109,6 +109,8 @@ class DistGraph:
         self.phases = None
         self.fwd_blocks = None
         self.bwd_blocks = None
+        # exchange "nccl": ship only the rows each block really holds (allgather_slots); off = padded all-gather
+        self.exact_slots = os.environ.get("GCNB_DIST_EXACT_SLOTS", "0") == "1"
 
     def n_rows(self, q=None):
         q = self.rank if q is None else q
@@ -577,6 +579,47 @@ def dist_spmm_pipelined(ops, dgraph, blocks, exch, bias=None, relu=False):
 
 
 # ---------------------------------------------------------------------------- the exchange + layer
+class _Works:
+    """wait() on a list of request objects (batch_isend_irecv) like on one collective's work handle."""
+
+    def __init__(self, reqs):
+        self.reqs = reqs
+
+    def wait(self):
+        for r in self.reqs:
+            r.wait()
+
+
+def allgather_slots(gathered, panel, dgraph, group=None, async_op=False):
+    """Every rank's slot `panel` [pad_rows, w] -> gathered [world * pad_rows, w] on every rank.
+
+    Default: one all_gather_into_tensor of the padded slots.  With dgraph.exact_slots (opt-in: DistGraph.exact_slots =
+    True or GCNB_DIST_EXACT_SLOTS=1) only the rows a block really holds travel: one grouped batch of point-to-point
+    sends / receives (the same slot to every peer, every peer's n_q rows into its place), which is what skewed
+    partitions need -- on a products-shaped R-MAT graph the padded slots are 3x the real rows (tools/halo_fraction.py).
+    The layout of `gathered` (source q at row q * pad_rows) is the same either way, so the blocks do not change."""
+    if not getattr(dgraph, "exact_slots", False):
+        return dist.all_gather_into_tensor(gathered, panel, group=group, async_op=async_op)
+    world, p, pad = dgraph.world, dgraph.rank, dgraph.pad_rows
+    n_p = dgraph.n_rows()
+    if n_p:
+        gathered[p * pad: p * pad + n_p].copy_(panel[:n_p])
+    ops_ = []
+    for k in range(1, world):
+        dst, src = (p + k) % world, (p - k) % world
+        if n_p:
+            ops_.append(dist.P2POp(dist.isend, panel[:n_p], dst if group is None else dist.get_global_rank(group, dst), group))
+        n_s = dgraph.n_rows(src)
+        if n_s:
+            ops_.append(dist.P2POp(dist.irecv, gathered[src * pad: src * pad + n_s],
+                                   src if group is None else dist.get_global_rank(group, src), group))
+    works = _Works(dist.batch_isend_irecv(ops_) if ops_ else [])
+    if async_op:
+        return works
+    works.wait()
+    return None
+
+
 def chunk_columns(f, chunks):
     """Column ranges [(c0, c1), ...] that cut a width-f panel into at most `chunks` pieces whose
     boundaries are multiples of 4 floats (gathered rows stay 16-byte aligned); fewer pieces when f
@@ -602,7 +645,7 @@ def dist_spmm_chunked(ops, dgraph, block, panel, chunks, bias=None, relu=False, 
     for c0, c1 in chunk_columns(f, chunks):
         send = panel[:, c0:c1].contiguous()
         gathered = ops.empty((world * dgraph.pad_rows, c1 - c0), panel)
-        work = dist.all_gather_into_tensor(gathered, send, group=group, async_op=True)
+        work = allgather_slots(gathered, send, dgraph, group, async_op=True)
         pending.append((c0, c1, gathered, work, send))
     for c0, c1, gathered, work, _send in pending:
         work.wait()
@@ -625,9 +668,9 @@ def dist_spmm(ops, dgraph, diag, remote, panel, bias=None, relu=False, group=Non
         return ops.spmm_block(diag, panel, out, False, bias, relu)
     gathered = ops.empty((world * dgraph.pad_rows, panel.shape[1]), panel)
     if not dgraph.split:  # no locality to exploit: one pass over the whole row block
-        dist.all_gather_into_tensor(gathered, panel, group=group)
+        allgather_slots(gathered, panel, dgraph, group)
         return ops.spmm_block(remote, gathered, out, False, bias, relu)
-    work = dist.all_gather_into_tensor(gathered, panel, group=group, async_op=True)
+    work = allgather_slots(gathered, panel, dgraph, group, async_op=True)
     ops.spmm_block(diag, panel, out, False)
     work.wait()
     return ops.spmm_block(remote, gathered, out, True, bias, relu)

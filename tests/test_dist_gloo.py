@@ -88,7 +88,7 @@ def _problem(n=300, seed=3, fout=5):
     return n, idx, val, x, g, w, b
 
 
-def _worker(rank, world, port, outdir, relu, split=True, pipelined=False, chunks=1):
+def _worker(rank, world, port, outdir, relu, split=True, pipelined=False, chunks=1, exact=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -103,6 +103,7 @@ def _worker(rank, world, port, outdir, relu, split=True, pipelined=False, chunks
             blocks.append(HostBlock(ii, val, r0, r1, c0=r0, c1=r1) if split else None)
             blocks.append(HostBlock(ii, val, r0, r1, bounds=bounds, pad=pad, exclude=rank if split else -1))
         dg = D.DistGraph(rank, world, bounds, pad, *blocks, 0, idx.shape[1], split)
+        dg.exact_slots = exact  # only the rows a block holds travel (allgather_slots), padding stays NaN
         ops = NumpyOps()
         xt, gt = torch.from_numpy(x[r0:r1].copy()), torch.from_numpy(g[r0:r1].copy())
         wt, bt = torch.from_numpy(w), torch.from_numpy(b)
@@ -138,6 +139,14 @@ def _free_port():
     return p
 
 
+@pytest.mark.parametrize("world,relu,split,chunks", [(2, True, False, 1), (3, False, True, 1), (4, True, False, 2)])
+def test_exact_size_slot_exchange_matches_single_process_oracle(world, relu, split, chunks):
+    """The grouped point-to-point exchange that ships every block's real rows only (dist.allgather_slots with
+    exact_slots) under the unsplit, split and column-chunked schemes; the nnz-balanced blocks of the skewed test graph
+    hold different row counts, and the padding rows of the gathered buffers stay NaN."""
+    test_row_partitioned_layer_matches_single_process_oracle(world, relu, split, False, chunks, exact=True)
+
+
 @pytest.mark.parametrize("world,relu,split,pipelined,chunks", [
     (2, False, True, False, 1), (2, True, False, False, 1), (3, False, True, False, 1), (2, True, False, True, 1),
     (3, False, False, True, 1), (4, True, False, True, 1),
@@ -145,9 +154,9 @@ def _free_port():
     (2, True, False, False, 2), (3, False, False, False, 4),
     # the in-place gathered route (exchange "nvls"), unsplit and split row blocks
     (2, True, False, "gathered", 1), (3, False, True, "gathered", 1)])
-def test_row_partitioned_layer_matches_single_process_oracle(world, relu, split, pipelined, chunks):
+def test_row_partitioned_layer_matches_single_process_oracle(world, relu, split, pipelined, chunks, exact=False):
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_worker, args=(world, _free_port(), d, relu, split, pipelined, chunks), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), d, relu, split, pipelined, chunks, exact), nprocs=world, join=True)
         parts = [np.load(os.path.join(d, "r%d.npz" % r)) for r in range(world)]
     n, idx, val, x, g, w, b = _problem(fout=_fout(chunks))
     _, o_ref = O.c_layer_forward(x, w, b, idx, val, n)
