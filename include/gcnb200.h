@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GCNB_VERSION 102
+#define GCNB_VERSION 103
 
 #define GCNB_OK 0
 #define GCNB_E_INVALID 1  /* bad argument (shape, null pointer, alignment, overflow)  */
