@@ -326,6 +326,23 @@ class CudaOps:
     def empty(self, shape, like):
         return torch.empty(shape, dtype=torch.float32, device=like.device)
 
+    # -- build-time helpers of the halo exchange (HaloPlan): blocks as CSR tensors and back
+    def block_csr(self, block):
+        rowptr, col, val = block.csr()
+        return rowptr.long(), col.long(), val
+
+    def block_from_csr(self, rowptr, col, val, n_rows, n_cols):
+        from .graph import Graph
+
+        adj = torch.sparse_csr_tensor(rowptr, col, val, size=(n_rows, n_cols), check_invariants=False)
+        return Graph.from_torch(adj)
+
+    def selection_block(self, ids, n_cols):
+        """[len(ids), n_cols] with a single 1.0 per row: block @ dense packs the rows `ids` of dense (exact copies)."""
+        k = ids.numel()
+        rowptr = torch.arange(k + 1, dtype=torch.int64, device=ids.device)
+        return self.block_from_csr(rowptr, ids.long(), torch.ones(k, dtype=torch.float32, device=ids.device), k, n_cols)
+
 
 # ---------------------------------------------------------------------------- peer-memory exchange
 class _DevMem:
@@ -579,6 +596,80 @@ def dist_spmm_pipelined(ops, dgraph, blocks, exch, bias=None, relu=False):
 
 
 # ---------------------------------------------------------------------------- the exchange + layer
+class HaloPlan:
+    """Needed-rows-only ("halo") exchange for one direction of one DistGraph (opt-in, exchange "halo"; host logic
+    covered by the gloo tests, composed of kernels that are measured -- the packing is an SpMM with a selection
+    block -- but NOT yet run on GPUs as a whole).
+
+    The all-gather ships every row of every slot; a rank only reads the rows that appear as a column in its block:
+    95.6 % of them on a uniform graph, 35 % on a products-shaped R-MAT graph (tools/halo_fraction.py).  Built once
+    (collective: the lists of needed rows are exchanged): need[q] = sorted local ids of source q's rows this rank
+    reads; give[r] = ids of this rank's rows that rank r reads; pack[r] = selection block so that pack[r] @ panel is
+    the send buffer for r; block = the rank's (remote or whole) row block with its columns renumbered to the compact
+    panel [own slot (unsplit blocks only) | halo of source 0 | halo of source 1 | ...]."""
+
+    def __init__(self, ops, dgraph, block, group=None):
+        p, world, pad = dgraph.rank, dgraph.world, dgraph.pad_rows
+        rowptr, col, val = ops.block_csr(block)
+        src = torch.div(col, pad, rounding_mode="floor")
+        loc = col - src * pad
+        self.own = 0 if dgraph.split else pad  # a split row block keeps its own columns in the diagonal block
+        self.need, self.offset = {}, {}
+        new_col = torch.empty_like(col)
+        mine = src == p
+        new_col[mine] = loc[mine]
+        off = self.own
+        for q in range(world):
+            if q == p:
+                continue
+            m = src == q
+            ids = torch.unique(loc[m])  # sorted
+            self.need[q], self.offset[q] = ids, off
+            if ids.numel():
+                new_col[m] = off + torch.searchsorted(ids, loc[m])
+            off += ids.numel()
+        self.n_compact = max(off, 1)
+        lists = [None] * world
+        dist.all_gather_object(lists, {q: v.cpu() for q, v in self.need.items()}, group=group)
+        self.give = {r: lists[r][p].to(col.device) for r in range(world) if r != p}
+        n_p = dgraph.n_rows()
+        self.pack = {r: ops.selection_block(ids, max(pad, 1)) for r, ids in self.give.items() if ids.numel()}
+        self.block = ops.block_from_csr(rowptr, new_col, val, n_p, self.n_compact)
+        self.rows_received = off - self.own
+        self.rows_all_gather = (world - 1) * pad
+
+
+def dist_spmm_halo(ops, dgraph, plan, diag, panel, bias=None, relu=False, group=None):
+    """out_p with the needed-rows-only exchange: every peer r gets pack[r] @ panel (the rows of this rank it reads),
+    this rank receives need[q] rows from every source q into the compact panel, then one SpMM over the renumbered
+    block (after the diagonal block when the row block is split)."""
+    f = panel.shape[1]
+    p, world = dgraph.rank, dgraph.world
+    out = ops.empty((dgraph.n_rows(), f), panel)
+    compact = ops.empty((plan.n_compact, f), panel)
+    sends, p2p = [], []
+    for k in range(1, world):
+        r = (p + k) % world
+        if r in plan.pack:
+            buf = ops.empty((plan.give[r].numel(), f), panel)
+            ops.spmm_block(plan.pack[r], panel, buf, False)
+            sends.append(buf)
+            p2p.append(dist.P2POp(dist.isend, buf, r if group is None else dist.get_global_rank(group, r), group))
+        q = (p - k) % world
+        n_q = plan.need[q].numel()
+        if n_q:
+            p2p.append(dist.P2POp(dist.irecv, compact[plan.offset[q]: plan.offset[q] + n_q],
+                                  q if group is None else dist.get_global_rank(group, q), group))
+    reqs = dist.batch_isend_irecv(p2p) if p2p else []
+    if dgraph.split:
+        ops.spmm_block(diag, panel, out, False)           # runs while the halo rows are on the wire
+    else:
+        compact[: panel.shape[0]].copy_(panel)            # own slot at the front of the compact panel
+    for rq in reqs:
+        rq.wait()
+    return ops.spmm_block(plan.block, compact, out, dgraph.split, bias, relu)
+
+
 class _Works:
     """wait() on a list of request objects (batch_isend_irecv) like on one collective's work handle."""
 
@@ -676,24 +767,35 @@ def dist_spmm(ops, dgraph, diag, remote, panel, bias=None, relu=False, group=Non
     return ops.spmm_block(remote, gathered, out, True, bias, relu)
 
 
+def halo_plans(ops, dgraph, group=None):
+    """(forward, backward) HaloPlan of a DistGraph, built on first use (collective) and kept on the graph."""
+    plans = getattr(dgraph, "_halo_plans", None)
+    if plans is None:
+        plans = (HaloPlan(ops, dgraph, dgraph.fwd_remote, group), HaloPlan(ops, dgraph, dgraph.bwd_remote, group))
+        dgraph._halo_plans = plans
+    return plans
+
+
 def dist_layer_forward(ops, dgraph, x, w, b, relu=False, group=None, exch=None, chunks=1):
     """Row block of  A (X W) + b  (pygcn/layers.py:33-36) for this rank.  With `exch` (an exchange
     object for [pad_rows, Fout] panels) the per-source-block pipelined scheme is used; `chunks` > 1
     pipelines the NCCL exchange over column chunks of the panel instead (dist_spmm_chunked)."""
-    if exch is not None and dgraph.world > 1:
+    if exch is not None and exch != "halo" and dgraph.world > 1:
         ops.gemm(x, w, out=exch.my_slot)             # X_p W straight into this rank's slot
         if hasattr(exch, "allgather"):  # gathers in place (MulticastExchange)
             return dist_spmm_gathered(ops, dgraph, dgraph.fwd_diag, dgraph.fwd_remote, exch, b, relu)
         return dist_spmm_pipelined(ops, dgraph, dgraph.fwd_blocks, exch, b, relu)
     support = ops.empty((dgraph.pad_rows, w.shape[1]), x)
     ops.gemm(x, w, out=support)
+    if exch == "halo" and dgraph.world > 1:
+        return dist_spmm_halo(ops, dgraph, halo_plans(ops, dgraph, group)[0], dgraph.fwd_diag, support, b, relu, group)
     return dist_spmm(ops, dgraph, dgraph.fwd_diag, dgraph.fwd_remote, support, b, relu, group, chunks)
 
 
 def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=True, group=None, exch=None, chunks=1):
     """(dX rows of this rank or None, dW, db): dW/db are already summed over ranks."""
     fin, fout = w.shape
-    if exch is not None and dgraph.world > 1:
+    if exch is not None and exch != "halo" and dgraph.world > 1:
         db, _ = ops.colsum(g, y, exch.my_slot)       # local part of db; G (masked) staged into this rank's slot
         if hasattr(exch, "allgather"):  # gathers in place (MulticastExchange)
             ds = dist_spmm_gathered(ops, dgraph, dgraph.bwd_diag, dgraph.bwd_remote, exch)
@@ -702,7 +804,10 @@ def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=Tru
     else:
         gm = ops.empty((dgraph.pad_rows, fout), g)
         db, _ = ops.colsum(g, y, gm)                 # local part of db; G (masked) staged into its slot
-        ds = dist_spmm(ops, dgraph, dgraph.bwd_diag, dgraph.bwd_remote, gm, None, False, group, chunks)  # rows p of A^T G
+        if exch == "halo" and dgraph.world > 1:
+            ds = dist_spmm_halo(ops, dgraph, halo_plans(ops, dgraph, group)[1], dgraph.bwd_diag, gm, None, False, group)
+        else:
+            ds = dist_spmm(ops, dgraph, dgraph.bwd_diag, dgraph.bwd_remote, gm, None, False, group, chunks)  # rows p of A^T G
     dw = ops.gemm(x.t(), ds)                         # local part of X^T dS
     if dgraph.world > 1:
         flat = torch.cat([dw.reshape(-1), db.reshape(-1)])
@@ -741,8 +846,8 @@ class DistGraphConvolution(torch.nn.Module):
         super().__init__()
         from .layers import GraphConvolution
 
-        if exchange not in ("auto", "peer", "nccl", "nvls"):
-            raise ValueError("exchange must be 'auto', 'peer', 'nccl' or 'nvls'")
+        if exchange not in ("auto", "peer", "nccl", "nvls", "halo"):
+            raise ValueError("exchange must be 'auto', 'peer', 'nccl', 'nvls' or 'halo'")
         self.inner = GraphConvolution(in_features, out_features, bias, fuse_relu=fuse_relu, precision=precision)
         self.group = group
         self.exchange = exchange
@@ -767,6 +872,8 @@ class DistGraphConvolution(torch.nn.Module):
 
     def _exchanges(self, dgraph, dev):
         kind = self.resolve_exchange(self.exchange, dgraph.world)
+        if kind == "halo" and dgraph.world > 1:
+            return "halo", "halo"  # needed-rows-only exchange: the plans live on the DistGraph (halo_plans)
         if dgraph.world == 1 or kind == "nccl" or (kind == "peer" and dgraph.fwd_blocks is None):
             return None, None
         cls = MulticastExchange if kind == "nvls" else PeerExchange
@@ -878,8 +985,8 @@ def bench_main(args, wl):
         step()
     torch.cuda.synchronize()
     dist.barrier()
-    if layer._exch is None:
-        exchange = "nccl"  # requested peer exchange was not available (agreed on by all ranks)
+    if layer._exch is None and exchange in ("peer", "nvls"):
+        exchange = "nccl"  # requested peer / multicast exchange was not available (agreed on by all ranks)
 
     # capture the step (kernels + NCCL all-gathers / all-reduce) in a CUDA graph: removes the Python
     # and launch gaps from the device time, like the single-GPU arm.  All ranks must agree.
@@ -1057,6 +1164,9 @@ def bench_main(args, wl):
                                     "nvls: own multimem.st push of each rank's slot to the NVLS multicast address of a "
                                     "symmetric buffer, device barriers, then the SpMM over the row block; NCCL "
                                     "all-reduce of dW,db" if exchange == "nvls" else
+                                    "halo: needed-rows-only exchange (selection SpMM packs the rows each peer reads, grouped "
+                                    "send / recv into a compact panel), then the SpMM over the renumbered row block; NCCL "
+                                    "all-reduce of dW,db" if exchange == "halo" else
                                     "nccl: all-gather of the X.W / G panels, then the SpMM over the row block; "
                                     "all-reduce of dW,db"),
                        "nccl_chunks": layer.nccl_chunks},

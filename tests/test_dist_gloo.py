@@ -32,6 +32,7 @@ class HostBlock:
         self.row = idx[0][m] - r0
         self.val = val[m]
         self.nnz = int(m.sum())
+        self.n_rows = r1 - r0
 
 
 class NumpyOps:
@@ -60,6 +61,27 @@ class NumpyOps:
 
     def empty(self, shape, like):
         return torch.full(shape, float("nan"), dtype=torch.float32)  # padding must never be read
+
+    # build-time helpers of the halo exchange (dist.HaloPlan)
+    def block_csr(self, block):
+        order = np.argsort(block.row, kind="stable")
+        n_rows = block.n_rows
+        rowptr = np.zeros(n_rows + 1, np.int64)
+        np.add.at(rowptr, block.row + 1, 1)
+        return (torch.from_numpy(np.cumsum(rowptr)), torch.from_numpy(block.col[order].astype(np.int64)),
+                torch.from_numpy(block.val[order].astype(np.float32)))
+
+    def block_from_csr(self, rowptr, col, val, n_rows, n_cols):
+        b = HostBlock.__new__(HostBlock)
+        counts = np.diff(rowptr.numpy())
+        b.row = np.repeat(np.arange(n_rows), counts)
+        b.col, b.val, b.nnz, b.n_rows = col.numpy(), val.numpy(), int(col.numel()), n_rows
+        assert b.col.size == 0 or (b.col.min() >= 0 and b.col.max() < n_cols)
+        return b
+
+    def selection_block(self, ids, n_cols):
+        k = ids.numel()
+        return self.block_from_csr(torch.arange(k + 1), ids.long(), torch.ones(k), k, n_cols)
 
 
 class InPlaceGather:
@@ -114,6 +136,8 @@ def _worker(rank, world, port, outdir, relu, split=True, pipelined=False, chunks
             dg.bwd_blocks = [HostBlock(tidx, val, r0, r1, bounds=bounds, pad=pad, only=qs) for qs in dg.phases]
             ef = D.CollectiveExchange(rank, world, pad, w.shape[1], xt)
             eb = D.CollectiveExchange(rank, world, pad, w.shape[1], xt)
+        if pipelined == "halo":  # needed-rows-only exchange (dist.HaloPlan / dist_spmm_halo)
+            ef = eb = "halo"
         if pipelined == "gathered":  # the in-place all-gather route of exchange "nvls" (dist_spmm_gathered)
             ef = InPlaceGather(rank, world, pad, w.shape[1])
             eb = InPlaceGather(rank, world, pad, w.shape[1])
@@ -153,7 +177,9 @@ def test_exact_size_slot_exchange_matches_single_process_oracle(world, relu, spl
     # the all-gather exchange pipelined over column chunks of the panel (dist_spmm_chunked), 37-column panels
     (2, True, False, False, 2), (3, False, False, False, 4),
     # the in-place gathered route (exchange "nvls"), unsplit and split row blocks
-    (2, True, False, "gathered", 1), (3, False, True, "gathered", 1)])
+    (2, True, False, "gathered", 1), (3, False, True, "gathered", 1),
+    # the needed-rows-only exchange: unsplit (own slot at the front of the compact panel) and split row blocks
+    (2, True, False, "halo", 1), (3, False, True, "halo", 1), (4, True, False, "halo", 1)])
 def test_row_partitioned_layer_matches_single_process_oracle(world, relu, split, pipelined, chunks, exact=False):
     with tempfile.TemporaryDirectory() as d:
         mp.spawn(_worker, args=(world, _free_port(), d, relu, split, pipelined, chunks, exact), nprocs=world, join=True)

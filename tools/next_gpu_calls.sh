@@ -26,7 +26,7 @@ one)
 two)
   # parity of every exchange with the single-GPU layer at 2 GPUs, eager and graph replay; "nvls" = the multicast
   # exchange (own multimem.st push into torch symmetric memory), written but never run in round 1
-  GCNB_DIST_CHECK_EXCHANGES=peer,nccl,nvls timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
+  GCNB_DIST_CHECK_EXCHANGES=peer,nccl,nvls,halo timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
     --master-addr 127.0.0.1 --master-port 29513 tools/dist_check.py > gpurun_out/dist_check_2gpu_nvls.txt 2>&1
   # the exact-size slot exchange (grouped send / recv instead of the padded all-gather) and the column-chunked one
   GCNB_DIST_EXACT_SLOTS=1 GCNB_DIST_CHECK_EXCHANGES=nccl timeout 120 python -m torch.distributed.run --nnodes=1 \
