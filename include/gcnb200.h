@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GCNB_VERSION 103
+#define GCNB_VERSION 104
 
 #define GCNB_OK 0
 #define GCNB_E_INVALID 1  /* bad argument (shape, null pointer, alignment, overflow)  */
@@ -225,6 +225,25 @@ int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_t ldx, cons
                         float* d_db, float* d_dx, int64_t lddx, void* d_ws, size_t ws_bytes,
                         void* stream);
 size_t gcnb_layer_workspace_bytes(const gcnb_graph* g, int64_t fin, int64_t fout, int precision);
+
+/* ---- (ReLU ->) fresh training-mode BatchNorm1d over the layer output ------------------------
+ * Replaces pygcn/models.py:41-45 `GCN.apply_bn` (a NEW nn.BatchNorm1d(F) per call: affine weight 1 / bias 0, batch
+ * statistics even under model.eval()) as the models apply it, `apply_bn(F.relu(gc(x, adj)))` (models.py:49,53), and
+ * its autograd backward.  relu != 0 folds the caller's F.relu and its backward mask into the same two passes.
+ *   forward : a = relu ? max(y, 0) : y;  mean_c, rstd_c = 1 / sqrt(biased var_c + eps) over the n_rows rows;
+ *             out = (a - mean) * rstd;  d_mean / d_rstd [f] are kept by the caller for backward.
+ *   backward: dy = [relu: y > 0] * rstd * (g - mean_rows(g) - xh * mean_rows(g * xh)), xh recomputed from y;
+ *             d_gstat [2 * f] receives the two row means (scratch the caller owns).
+ * One statistics pass (fp64 accumulation, per-CTA partials added in fixed order: deterministic) and one apply pass
+ * each way.  d_ws: gcnb_fresh_bn_workspace_bytes(n_rows, f) bytes, 8-byte aligned.  Operands fp32 row-major with
+ * leading dimensions; float4 path when f, the leading dimensions and the addresses allow it.
+ * Written at the end of round 1: compiled, NOT yet run on hardware; not called by any other entry point. */
+size_t gcnb_fresh_bn_workspace_bytes(int64_t n_rows, int64_t f);
+int gcnb_fresh_bn_forward(int64_t n_rows, int64_t f, const float* d_y, int64_t ldy, int relu, float eps, float* d_out,
+                          int64_t ldo, float* d_mean, float* d_rstd, void* d_ws, size_t ws_bytes, void* stream);
+int gcnb_fresh_bn_backward(int64_t n_rows, int64_t f, const float* d_y, int64_t ldy, int relu, const float* d_g,
+                           int64_t ldg, const float* d_mean, const float* d_rstd, float* d_dy, int64_t lddy,
+                           float* d_gstat, void* d_ws, size_t ws_bytes, void* stream);
 
 /* ---- peer-memory exchange for the row-partitioned multi-GPU layer (one process per GPU) ------------
  * The reference has no multi-GPU path; these entry points replace the NCCL all-gather

@@ -15,6 +15,7 @@ file next to it), the algorithm the reference executes on this path:
   * layer forward        pygcn/layers.py:32-38  (mm, spmm, + bias)
   * layer backward       autograd of the above
   * parameter init       pygcn/layers.py:23-29
+  * ReLU -> fresh BatchNorm  pygcn/models.py:41-45, 49, 53 (``GCN.apply_bn``)
 
 The arithmetic of the reference lives in third-party libraries that are not
 vendored under /root/reference: PyTorch (``torch.mm`` / ``torch.spmm``; unpinned
@@ -211,6 +212,30 @@ def layer_backward(x, w, has_bias, idx, val, n_cols, g, dtype=np.float32):
 def relu_backward(g, out):
     """threshold_backward of the caller's F.relu (models.py:49,53,56)."""
     return np.where(out > 0, g, np.zeros_like(g))
+
+
+def fresh_batchnorm_forward(y, relu=True, eps=1e-5, dtype=np.float64):
+    """`GCN.apply_bn` as the models call it (pygcn/models.py:41-45, 49, 53): a NEW nn.BatchNorm1d(F) per call --
+    affine weight 1 / bias 0, training mode, so batch statistics with the BIASED variance -- on F.relu(y):
+    a = relu(y); out = (a - mean_rows(a)) / sqrt(var_rows(a) + eps).  Returns (out, mean, rstd)."""
+    a = np.asarray(y, dtype=dtype)
+    if relu:
+        a = np.maximum(a, 0)
+    mean = a.mean(axis=0)
+    var = ((a - mean) ** 2).mean(axis=0)
+    rstd = 1.0 / np.sqrt(var + dtype(eps))
+    return (a - mean) * rstd, mean, rstd
+
+
+def fresh_batchnorm_backward(y, g, relu=True, eps=1e-5, dtype=np.float64):
+    """Autograd of the above: with xh = out, da = rstd * (g - mean_rows(g) - xh * mean_rows(g * xh)) (the batch
+    statistics depend on the input), then threshold_backward of the F.relu: dy = da * [y > 0]."""
+    xh, _mean, rstd = fresh_batchnorm_forward(y, relu, eps, dtype)
+    g = np.asarray(g, dtype=dtype)
+    da = rstd * (g - g.mean(axis=0) - xh * (g * xh).mean(axis=0))
+    if relu:
+        da = np.where(np.asarray(y) > 0, da, np.zeros_like(da))
+    return da
 
 
 def normwise_err(a, b):

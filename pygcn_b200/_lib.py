@@ -84,6 +84,11 @@ SIGNATURES = {
     "gcnb_peer_wait_lag": (c_int, [c_vp, c_vp, ctypes.c_uint32, c_vp]),
     "gcnb_peer_copy": (c_int, [c_vp, c_vp, c_sz, c_vp]),
     "gcnb_multimem_push": (c_int, [c_vp, c_vp, c_sz, c_int, c_vp]),
+    "gcnb_fresh_bn_workspace_bytes": (c_sz, [c_i64, c_i64]),
+    "gcnb_fresh_bn_forward": (c_int, [c_i64, c_i64, c_vp, c_i64, c_int, ctypes.c_float, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz,
+                                      c_vp]),
+    "gcnb_fresh_bn_backward": (c_int, [c_i64, c_i64, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp,
+                                       c_sz, c_vp]),
     "gcnb_graph_block_sources": (c_int, [c_vp, c_int, c_i64, c_i64, c_int, ctypes.POINTER(c_i64), c_i64, ctypes.c_uint64,
                                          c_vp, ctypes.POINTER(c_vp)]),
     "gcnb_peer_ack": (c_int, [c_vp, c_vp, c_vp]),

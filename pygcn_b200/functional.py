@@ -476,3 +476,63 @@ def mm(a, b, precision="auto"):
                            max(n, 1), prec, _ptr(ws), ws.numel(), _stream_ptr(a.device))
     _lib.check(st, "gcnb_gemm")
     return out
+
+
+# ---------------------------------------------------------------------------- (ReLU ->) fresh BatchNorm
+class _FreshBatchNormFn(torch.autograd.Function):
+    """gcnb_fresh_bn_forward / _backward: `GCN.apply_bn(F.relu(y))` (pygcn/models.py:41-45, 49, 53) in one statistics
+    pass and one apply pass each way."""
+
+    @staticmethod
+    def forward(ctx, y, relu, eps):
+        lib = _lib.load()
+        dev = y.device
+        yr = _rowmajor(y)
+        n, f = yr.shape
+        out = torch.empty((n, f), dtype=torch.float32, device=dev)
+        stat = torch.empty((2, _ld4(f)), dtype=torch.float32, device=dev)  # mean | rstd, rows 16-byte aligned
+        with torch.cuda.device(dev):
+            ws = _ws(lib.gcnb_fresh_bn_workspace_bytes(n, f), dev)
+            st = lib.gcnb_fresh_bn_forward(n, f, _ptr(yr), _ld(yr), 1 if relu else 0, float(eps), _ptr(out), max(f, 1),
+                                           stat[0].data_ptr(), stat[1].data_ptr(), _ptr(ws), ws.numel(), _stream_ptr(dev))
+        _lib.check(st, "gcnb_fresh_bn_forward")
+        ctx.relu = bool(relu)
+        ctx.save_for_backward(yr, stat)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        lib = _lib.load()
+        yr, stat = ctx.saved_tensors
+        dev = yr.device
+        gr = _rowmajor(g)
+        n, f = yr.shape
+        dy = torch.empty((n, f), dtype=torch.float32, device=dev)
+        gstat = torch.empty((2 * f,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _ws(lib.gcnb_fresh_bn_workspace_bytes(n, f), dev)
+            st = lib.gcnb_fresh_bn_backward(n, f, _ptr(yr), _ld(yr), 1 if ctx.relu else 0, _ptr(gr), _ld(gr),
+                                            stat[0].data_ptr(), stat[1].data_ptr(), _ptr(dy), max(f, 1), _ptr(gstat),
+                                            _ptr(ws), ws.numel(), _stream_ptr(dev))
+        _lib.check(st, "gcnb_fresh_bn_backward")
+        return dy, None, None
+
+
+def apply_bn(x, relu=False, eps=1e-5):
+    """Drop-in for `GCN.apply_bn` (pygcn/models.py:41-45): batch-normalise the [N, F] layer output with a FRESH
+    BatchNorm1d -- affine weight 1 / bias 0, batch statistics (biased variance, eps 1e-5) whatever the model's
+    train / eval mode.  relu=True folds the `F.relu` the models apply first (`apply_bn(F.relu(gc(x, adj)))`,
+    models.py:49,53) and its backward mask into the same two passes:  apply_bn(y, relu=True) == apply_bn(F.relu(y)).
+    Differentiable w.r.t. x.  Errors mirror torch's: fewer than 2 rows raise ValueError, CPU tensors raise (no
+    fallback).  Opt-in: written at the end of round 1, not yet run on hardware (tests/test_gpu_optin.py)."""
+    _require_cuda(x, "x")
+    if x.dim() != 2:
+        raise ValueError("expected 2D input (got %dD input)" % x.dim())  # the reference passes [N, F] (models.py:44)
+    if x.dtype != torch.float32:
+        raise RuntimeError("expected float32, got %s" % x.dtype)
+    if x.shape[0] < 2:
+        raise ValueError("Expected more than 1 value per channel when training, got input size %s" % (tuple(x.shape),))
+    if x.shape[1] == 0:
+        return torch.empty_like(x)
+    return _FreshBatchNormFn.apply(x, bool(relu), float(eps))

@@ -86,9 +86,49 @@ def run_layer(layers, fin, fout, bias, x, adj, g, seed=42, x_requires_grad=True)
     return res
 
 
+def make_apply_bn(models):
+    """apply_bn.npz: the reference's own `GCN.apply_bn` (pygcn/models.py:41-45) as the models call it,
+    `apply_bn(F.relu(y))` (models.py:49,53), forward and autograd backward, on CPU.  The method moves its fresh
+    BatchNorm1d to the GPU with `.cuda()`; there is none here, so `nn.Module.cuda` is a no-op while it runs (a shim in
+    this harness, the reference's lines execute unchanged)."""
+    import torch.nn.functional as F
+
+    cases = {}
+    real_cuda = torch.nn.Module.cuda
+    torch.nn.Module.cuda = lambda self, device=None: self
+    try:
+        for name, (n, f, seed, relu, offset) in {
+            "cbg32": (1100, 32, 71, True, 0.0),        # hidden width of the CBG models, float4 path
+            "odd7": (257, 7, 72, True, 0.0),           # 7 classes: scalar path, ragged row count
+            "plain16": (400, 16, 73, False, 2.5),      # apply_bn alone on a shifted input (mean >> 0)
+            "deadcol": (300, 8, 74, True, 0.0),        # a column that ReLU zeroes entirely (var = 0 -> rstd = eps^-1/2)
+            "two_rows": (2, 4, 75, False, 0.0),        # the smallest batch torch accepts
+        }.items():
+            y = rng_inputs(seed, (n, f)) + np.float32(offset)
+            if name == "deadcol":
+                y[:, 3] = -np.abs(y[:, 3]) - 1.0
+            g = rng_inputs(seed + 100, (n, f))
+            yt = torch.from_numpy(y.copy()).requires_grad_(True)
+            out = models.GCN.apply_bn(None, F.relu(yt) if relu else yt)
+            out.backward(torch.from_numpy(g))
+            cases[name + "/y"] = y
+            cases[name + "/g"] = g
+            cases[name + "/relu"] = np.int64(relu)
+            cases[name + "/out"] = out.detach().numpy().copy()
+            cases[name + "/dy"] = yt.grad.numpy().copy()
+    finally:
+        torch.nn.Module.cuda = real_cuda
+    np.savez_compressed(os.path.join(OUT, "apply_bn.npz"), **cases)
+
+
 def main():
     torch.set_num_threads(1)
     layers, utils, models = _load_reference()
+    if sys.argv[1:] == ["apply_bn"]:  # only this fixture (the others are unchanged)
+        make_apply_bn(models)
+        print("wrote apply_bn.npz", os.path.getsize(os.path.join(OUT, "apply_bn.npz")) // 1024, "KiB")
+        return
+    make_apply_bn(models)
 
     # ---------------------------------------------------------------- Cora graph pipeline
     raw = np.loadtxt(os.path.join(REF, "data", "cora", "cora.cites"), dtype=np.int64)

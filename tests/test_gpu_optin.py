@@ -87,3 +87,92 @@ def test_pdl_chain_is_bit_identical_to_plain_launches(pdl, n, fin, fout, relu):
     torch.cuda.synchronize()
     assert torch.equal(o_static.detach(), want[0])
     assert torch.equal(layer.weight.grad, want[2]) and torch.equal(layer.bias.grad, want[3])
+
+
+# ---------------------------------------------------------------- (ReLU ->) fresh BatchNorm
+def _torch_apply_bn(y, relu):
+    """The reference's lines (pygcn/models.py:41-45, 49): a fresh nn.BatchNorm1d on F.relu(y)."""
+    a = torch.relu(y) if relu else y
+    return torch.nn.BatchNorm1d(y.shape[1]).to(y.device)(a)
+
+
+def _normwise(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("name", ["cbg32", "odd7", "plain16", "deadcol", "two_rows"])
+def test_apply_bn_matches_reference_fixture(golden, name):
+    """apply_bn through the C ABI against the reference's own apply_bn(F.relu(y)) outputs and gradients
+    (tests/golden/apply_bn.npz): <= 1e-5 norm-wise (the 2-row batch's gradient is a cancellation: 1e-4)."""
+    import pygcn_b200 as P
+
+    c = golden("apply_bn.npz")
+    relu = bool(c[name + "/relu"])
+    y = torch.from_numpy(c[name + "/y"]).to(dev()).requires_grad_(True)
+    out = P.apply_bn(y, relu=relu)
+    out.backward(torch.from_numpy(c[name + "/g"]).to(dev()))
+    assert _normwise(out.detach().cpu(), torch.from_numpy(c[name + "/out"])) < 1e-5
+    assert _normwise(y.grad.cpu(), torch.from_numpy(c[name + "/dy"])) < (1e-4 if name == "two_rows" else 1e-5)
+
+
+@pytest.mark.parametrize("n,f,relu", [(100000, 32, True), (100000, 32, False), (50001, 47, True), (232965, 256, True),
+                                      (3, 1, True), (70000, 1040, False)])
+def test_apply_bn_matches_torch_batchnorm(n, f, relu):
+    """Against torch's own CUDA BatchNorm1d + ReLU + autograd on the same input (what the reference executes on a GPU),
+    an fp64 evaluation arbitrating; float4 and scalar paths, a panel wider than one column tile, bit-identical reruns."""
+    import pygcn_b200 as P
+
+    gen = torch.Generator(device=dev()).manual_seed(n + f)
+    y = (torch.randn(n, f, generator=gen, device=dev()) + 0.25).requires_grad_(True)
+    g = torch.randn(n, f, generator=gen, device=dev())
+    out = P.apply_bn(y, relu=relu)
+    out.backward(g)
+    dy = y.grad.clone()
+    y.grad = None
+    ref = _torch_apply_bn(y, relu)
+    ref.backward(g)
+    y64 = y.detach().double().requires_grad_(True)
+    a64 = torch.relu(y64) if relu else y64
+    ex = (a64 - a64.mean(0)) / torch.sqrt(a64.var(0, unbiased=False) + 1e-5)
+    ex.backward(g.double())
+    for ours, theirs, exact in ((out.detach(), ref.detach(), ex.detach()), (dy, y.grad, y64.grad)):
+        assert _normwise(ours, exact) <= max(1e-5, 2 * _normwise(theirs, exact))
+    y.grad = None
+    out2 = P.apply_bn(y, relu=relu)
+    out2.backward(g)
+    assert torch.equal(out2, out) and torch.equal(y.grad, dy)
+
+
+def test_apply_bn_after_the_fused_relu_layer_and_on_views():
+    """As the models use it: apply_bn(F.relu(gc(x, adj))) == apply_bn(gc_fused_relu(x, adj)) == apply_bn(gc(x, adj),
+    relu=True), gradients reaching the layer's weights; a column-slice view as input; torch's error for a 1-row batch."""
+    import pygcn_b200 as P
+
+    n, fin, fout = 20000, 64, 32
+    gr = _graph(P, n, 20 * n, seed=3)
+    gen = torch.Generator(device=dev()).manual_seed(9)
+    x = torch.randn(n, fin, generator=gen, device=dev())
+    g = torch.randn(n, fout, generator=gen, device=dev())
+    torch.manual_seed(42)
+    layer = P.GraphConvolution(fin, fout).to(dev())
+    fused = P.GraphConvolution(fin, fout, fuse_relu=True).to(dev())
+    fused.load_state_dict(layer.state_dict())
+    res = []
+    for fn in (lambda: _torch_apply_bn(torch.relu(layer(x, gr)), False), lambda: P.apply_bn(layer(x, gr), relu=True),
+               lambda: P.apply_bn(fused(x, gr))):
+        for m in (layer, fused):
+            m.zero_grad()
+        o = fn()
+        o.backward(g)
+        used = fused if fused.weight.grad is not None else layer
+        res.append((o.detach(), used.weight.grad.clone(), used.bias.grad.clone()))
+    for o, dw, db in res[1:]:
+        assert _normwise(o, res[0][0]) < 1e-5 and _normwise(dw, res[0][1]) < 1e-5
+        assert float((db - res[0][2]).abs().max()) < 1e-5 * float(res[0][1].abs().max())  # (db of a layer under BN is ~0)
+    wide = torch.randn(5000, 40, generator=gen, device=dev())
+    view = wide[:, 3:35]  # row stride 40 > width 32, start not 16-byte aligned: scalar path
+    assert _normwise(P.apply_bn(view, relu=True), _torch_apply_bn(view, True)) < 1e-5
+    with pytest.raises(ValueError):
+        P.apply_bn(torch.zeros(1, 8, device=dev()))
+    with pytest.raises(RuntimeError):
+        P.apply_bn(torch.zeros(4, 8))

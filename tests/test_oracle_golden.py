@@ -176,3 +176,24 @@ def test_cbg_adjacency_oracle_matches_reference_load_adj(golden):
     assert adj.dtype == np.float32 and adj.shape == c["adj"].shape
     assert O.normwise_err(adj, c["adj"]) < 1e-7
     assert np.array_equal(adj, adj.T)
+
+
+BN_CASES = ["cbg32", "odd7", "plain16", "deadcol", "two_rows"]
+
+
+@pytest.mark.parametrize("name", BN_CASES)
+def test_fresh_batchnorm_oracle_matches_reference_apply_bn(golden, name):
+    """oracle.fresh_batchnorm_* == the reference's own GCN.apply_bn(F.relu(y)) (pygcn/models.py:41-45, 49, 53) and its
+    autograd backward on the reference-generated fixture (apply_bn.npz): <= 1e-5 norm-wise, fp32 and fp64 restatement
+    (torch's own fp32 result sits 3e-6 from exact arithmetic on these cases; the 2-row batch differentiates through a
+    catastrophic cancellation -- var ~ the squared half-difference -- where torch's fp32 gradient is 4e-5 off)."""
+    c = golden("apply_bn.npz")
+    y, g, relu = c[name + "/y"], c[name + "/g"], bool(c[name + "/relu"])
+    for dtype, tol in ((np.float32, TOL), (np.float64, 1e-4 if name == "two_rows" else TOL)):
+        out, mean, rstd = O.fresh_batchnorm_forward(y, relu, 1e-5, dtype)
+        assert out.shape == y.shape and mean.shape == (y.shape[1],) and rstd.shape == (y.shape[1],)
+        assert O.normwise_err(out, c[name + "/out"]) < tol
+        assert O.normwise_err(O.fresh_batchnorm_backward(y, g, relu, 1e-5, dtype), c[name + "/dy"]) < tol
+    if name == "deadcol":  # ReLU zeroes column 3 entirely: var = 0, the output and the gradient of that column are 0
+        assert not c[name + "/out"][:, 3].any() and not c[name + "/dy"][:, 3].any()
+        assert not O.fresh_batchnorm_forward(y, relu)[0][:, 3].any()

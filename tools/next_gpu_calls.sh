@@ -3,7 +3,7 @@
 # Each block is one gpurun call; copy what matters from gpurun_out/ into profiles/.
 #
 # 1 GPU (about a minute of box time):
-#   gpurun --timeout 200 -- 'bash tools/next_gpu_calls.sh one'
+#   gpurun --timeout 420 -- 'bash tools/next_gpu_calls.sh one'
 # 2 GPUs (charged 2x):
 #   gpurun --gpus 2 --timeout 300 -- 'bash tools/next_gpu_calls.sh two'
 # 8 GPUs (charged 8x; about a minute):
@@ -13,13 +13,15 @@ mkdir -p gpurun_out
 case "$1" in
 one)
   # the opt-in paths' own parity tests (skipped by default because they had never run on hardware)
-  GCNB_TEST_UNVERIFIED=1 timeout 120 python -m pytest tests/test_gpu_optin.py -m gpu -x -q > gpurun_out/pytest_optin.log 2>&1
+  GCNB_TEST_UNVERIFIED=1 timeout 240 python -m pytest tests/test_gpu_optin.py -m gpu -x -q > gpurun_out/pytest_optin.log 2>&1
   # programmatic dependent launch of the step's kernel chain: bit-identity + graph-replay time, off / on
   timeout 60 python tools/pdl_probe.py cbg 40 > gpurun_out/pdl_probe_cbg.txt 2>&1
   # the persistent group kernel with the next row set prefetched (variants 16 / 17) against the defaults (13 / 14)
   timeout 60 python tools/variant_sweep.py 13,16,14,17 20 > gpurun_out/variant_sweep_persistent.txt 2>&1
   # the bf16 panel kernels were not in the CTA-shape sweeps: 64-byte rows stay on variant 0 until this says otherwise
   timeout 60 python tools/variant_sweep.py 0,2,13,14 20 --bf16 > gpurun_out/variant_sweep_bf16.txt 2>&1
+  # (ReLU ->) fresh BatchNorm: parity and time against torch's relu + batch_norm
+  timeout 90 python tools/bn_probe.py 20 > gpurun_out/bn_probe.txt 2>&1
   # with PDL on, the whole bench line
   GCNB_PDL=1 timeout 100 python bench.py --no-cpu-baseline > gpurun_out/bench_pdl.json 2> gpurun_out/bench_pdl.err
   ;;
