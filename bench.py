@@ -148,6 +148,18 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def cpu_model():
+    """CPU model string of the host (SURVEY.md 8d asks for it beside the core count); None if unreadable."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return None
+
+
 # --------------------------------------------------------------------------- reference arm
 def run_reference(args, wl):
     """`--impl reference`: the reference layer's own CPU path (torch.mm + torch.spmm on the COO
@@ -206,7 +218,7 @@ def run_reference(args, wl):
                    "adj_form": "uncoalesced fp32 COO, int64 indices (utils.py:407-414), torch CPU",
                    "input_requires_grad": False},
         "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample,
-                         "torch_threads": torch.get_num_threads(),
+                         "torch_threads": torch.get_num_threads(), "cpu_model": cpu_model(),
                          "alt_csr_edges_per_s": nnz / sec_csr, "host_graph_build_s": build_s},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -569,7 +581,7 @@ def cpu_baseline(torch, graph, layer, x_host, g_host, wl):
             "alt_1thread_edges_per_s": (graph.nnz / sec_1t) if sec_1t else None,
             "sample": "%d fwd+bwd steps of the full workload (nnz=%d) after 2 warm-up, torch CPU %d threads, "
                       "adj = uncoalesced COO as utils.py:407-414 builds it" % (steps, graph.nnz, torch.get_num_threads()),
-            "ms_per_step": sec * 1e3, "alt_csr_edges_per_s": graph.nnz / sec_csr}
+            "ms_per_step": sec * 1e3, "alt_csr_edges_per_s": graph.nnz / sec_csr, "cpu_model": cpu_model()}
 
 
 def main():
