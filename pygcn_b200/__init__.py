@@ -8,15 +8,18 @@ Public surface (mirrors the reference's for this path):
                           utils.sparse_mx_to_torch_sparse_tensor, built on the GPU)
     load_adj              the CBG adjacency avg^T avg of utils.load_adj, on the device
     apply_bn              (ReLU ->) fresh BatchNorm1d of models.GCN.apply_bn (opt-in, not yet run on hardware)
+    io                    the on-disk formats either side of the layer: `.cites` edge lists, the npy / pickle levels
+                          of utils.load_adj (host-side parsing in front of the device paths)
     install_as_pygcn      make `import layers` / `import pygcn.layers` resolve to this package
 """
 import sys as _sys
 
 from .functional import apply_bn, gcn_layer, load_adj, mm, spmm
+from . import io
 from .graph import Graph, as_graph, clear_cache
 from .layers import GraphConvolution
 
-__all__ = ["GraphConvolution", "Graph", "as_graph", "clear_cache", "gcn_layer", "spmm", "mm", "load_adj", "apply_bn", "install_as_pygcn"]
+__all__ = ["GraphConvolution", "Graph", "as_graph", "clear_cache", "gcn_layer", "spmm", "mm", "load_adj", "apply_bn", "io", "install_as_pygcn"]
 
 
 def install_as_pygcn():

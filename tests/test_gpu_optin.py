@@ -176,3 +176,37 @@ def test_apply_bn_after_the_fused_relu_layer_and_on_views():
         P.apply_bn(torch.zeros(1, 8, device=dev()))
     with pytest.raises(RuntimeError):
         P.apply_bn(torch.zeros(4, 8))
+
+
+# ---------------------------------------------------------------- on-disk formats (pygcn_b200/io.py)
+def test_graph_from_cites_and_load_adj_files_on_the_device(tmp_path, golden):
+    """The file loaders composed with the measured device paths: a `.cites` file written from the golden Cora edges ->
+    the golden adjacency bit for bit; the three file levels of utils.load_adj with the tcgen05 product -> the
+    reference's adjacency (<= 1e-5), cached like the reference caches it."""
+    import pickle
+
+    import scipy.sparse as sp
+
+    from pygcn_b200 import io as IO
+
+    g = golden("cora_pipeline.npz")
+    ids = np.arange(1000, 1000 + int(g["n"]), dtype=np.int64) * 7            # any increasing paper ids
+    p = tmp_path / "cora.cites"
+    np.savetxt(p, ids[g["edges"]], fmt="%d", delimiter="\t")
+    gr, ids_back = IO.graph_from_cites(str(p), dev())
+    coo = gr.to_sparse_coo()
+    assert np.array_equal(ids_back, ids)
+    assert np.array_equal(coo._indices().cpu().numpy(), g["indices"])
+    assert np.array_equal(coo._values().cpu().numpy(), g["values"])
+
+    c = golden("load_adj.npz")
+    root, out = tmp_path / "mob", tmp_path / "out"
+    (root / "SanFrancisco").mkdir(parents=True)
+    out.mkdir()
+    with open(root / "SanFrancisco" / ("X" + IO.CBG_PICKLE_SUFFIX), "wb") as f:
+        pickle.dump([sp.csr_matrix(h) for h in c["hours"]], f)
+    adj, n = IO.load_adj_files("SanFrancisco", str(root), str(out), dev(), msa_name_full="X")
+    assert n == c["adj"].shape[0] and adj.is_cuda and adj.dtype == torch.float32
+    assert _normwise(adj.cpu(), torch.from_numpy(c["adj"])) < 1e-5
+    adj1, _ = IO.load_adj_files("SanFrancisco", "/nonexistent", str(out), dev())
+    assert torch.equal(adj1, adj)
