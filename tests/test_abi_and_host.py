@@ -112,6 +112,10 @@ def test_cpu_tensors_raise_not_fallback():
         P.spmm(torch.eye(5).to_sparse(), torch.zeros(5, 2))
     with pytest.raises(TypeError):
         P.spmm([[1.0]], torch.zeros(1, 1))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.apply_bn(torch.zeros(5, 4), relu=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.load_adj(torch.zeros(5, 4))
 
 
 def test_whole_model_pickle_under_reference_module_path():
