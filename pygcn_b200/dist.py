@@ -1146,6 +1146,15 @@ def bench_main(args, wl):
     alg = B.algorithmic_bytes_spmm(blk.nnz, n_local, fout)
     peak, peak_src = B.peaks()
     achieved = alg / (spmm_ms * 1e-3) / 1e9
+    # our kernels per step (the claim behind "gpu_launches"; NCCL's and torch's own kernels are not counted): pack W,
+    # X.W, colsum(G), dW, split-K reduce = 5, plus per SpMM (forward, transposed) the products over the row block --
+    # one, two for a split block, one per phase of the peer exchange -- and the peer protocol's epoch bump, push and a
+    # wait + ack per remote source
+    if exchange == "peer" and dgraph.phases is not None:
+        per_spmm = len(dgraph.phases) + 2 + 2 * (world - 1)
+    else:
+        per_spmm = 2 if dgraph.split else 1
+    launches_per_step = 5 + 2 * per_spmm
     if rank == 0:
         line = {
             "metric": "gcn_layer_fwd_bwd_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world,
@@ -1174,7 +1183,7 @@ def bench_main(args, wl):
             "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": (x_host.numel() + g_host.numel()) * 4,
                     "d2h_bytes_per_step": (fin * fout + fout) * 4, "ms_per_step": e2e_t.item() / args.steps * 1e3,
                     "how": e2e_how},
-            "gpu_launches": 10 * args.steps,
+            "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "spmm_group_kernel<LPR=8,U=4,24 CTAs/SM,W=2,SE=16> on rank 0's %s" % ("diagonal block" if dgraph.split else "row block (all-gathered panel)"),
                          "algorithmic_bytes_per_launch": alg, "kernel_ms": spmm_ms, "peak_source": peak_src},
