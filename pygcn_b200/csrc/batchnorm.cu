@@ -7,8 +7,8 @@
 // and its autograd backward (xh = out):
 //     da = rstd_c * (g - mean_rows(g) - xh * mean_rows(g * xh));  dy = da * [y > 0].
 // With torch that is ReLU (read + write), BatchNorm (statistics pass + normalise pass), and in backward a reduce pass,
-// an apply pass and the ReLU mask pass.  Here: one statistics pass + one apply pass each way, the ReLU and its mask
-// folded into both.  The layer output was just written by the SpMM, so on B200 the statistics pass reads it out of the
+// an apply pass and the ReLU mask pass: 13 panel reads / writes.  Here: one statistics pass + one apply pass each way,
+// the ReLU and its mask folded into both: 8.  The layer output was just written by the SpMM, so on B200 the statistics pass reads it out of the
 // 126 MB L2, not HBM, for every BASELINE shape up to 30 M elements.
 //
 // Deterministic: per-thread fp64 accumulation, per-CTA partials combined in CTA order by a warp per column, no atomics.
