@@ -89,3 +89,27 @@ def test_load_adj_files_walks_the_three_levels_of_utils_load_adj(tmp_path, golde
     assert np.array_equal(IO.average_visits(hours), avg_o)
     with pytest.raises(ValueError):
         IO.average_visits([])
+
+
+def test_read_cites_random_files_against_the_loader_lines(tmp_path):
+    """Seeded sweep: random paper ids, link lists and `.content` orders through read_cites == the loader's own
+    statements (pygcn/utils.py:354-359) executed on the same file."""
+    rs = np.random.default_rng(11)
+    for case in range(25):
+        n = int(rs.integers(1, 40))
+        ids = rs.choice(np.arange(1, 10 ** 6), size=n, replace=False)
+        e = int(rs.integers(1, 120))
+        raw = ids[rs.integers(0, n, size=(e, 2))]
+        p = tmp_path / ("c%d.cites" % case)
+        np.savetxt(p, raw, fmt="%d", delimiter="\t" if case % 2 else " ")
+        order = rs.permutation(ids)
+        if case % 3 == 0:  # nodes that appear in no link
+            order = np.concatenate([order, np.arange(10 ** 6 + 1, 10 ** 6 + 4)])
+        idx_map = {j: i for i, j in enumerate(order.tolist())}
+        edges_unordered = np.genfromtxt(str(p), dtype=np.int32).reshape(-1, 2)
+        want = np.array(list(map(idx_map.get, edges_unordered.flatten())), dtype=np.int32).reshape(edges_unordered.shape)
+        got, back = IO.read_cites(str(p), order)
+        assert np.array_equal(got, want) and np.array_equal(back, order)
+        got_default, ids_default = IO.read_cites(str(p))
+        assert np.array_equal(ids_default[got_default], raw)  # the default order is the sorted ids that occur
+        assert np.array_equal(ids_default, np.unique(raw))
