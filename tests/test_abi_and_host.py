@@ -83,6 +83,40 @@ def test_tuning_knobs_validate_their_values(lib):
         lib.gcnb_set_tuning(_lib.TUNE_PDL, 0)
 
 
+def test_fresh_bn_entry_points_validate_before_launching(lib):
+    """gcnb_fresh_bn_*: every argument check runs on the host before any kernel is launched, so refusals can be
+    exercised without a GPU -- shapes, null operands, leading dimensions, workspace size and alignment; an empty batch
+    is a no-op; the workspace size is the per-CTA fp64 partials [blocks][2][f]."""
+    import ctypes
+
+    from pygcn_b200 import _lib
+
+    blocks = lambda n: max(1, min(-(-n // 128), 4 * 148))
+    for n, f in ((1, 1), (100000, 32), (257, 7), (10 ** 7, 256)):
+        assert lib.gcnb_fresh_bn_workspace_bytes(n, f) == blocks(n) * 2 * f * 8 + 16
+    assert lib.gcnb_fresh_bn_workspace_bytes(0, 32) == 16
+    buf = (ctypes.c_float * 4096)()
+    a = ctypes.addressof(buf)
+    fwd = lambda n, f, y, ldy, out, ldo, mean, rstd, ws, wsb, eps=1e-5: lib.gcnb_fresh_bn_forward(
+        n, f, y, ldy, 1, eps, out, ldo, mean, rstd, ws, wsb, None)
+    bwd = lambda n, f, y, ldy, g, ldg, mean, rstd, dy, lddy, gstat, ws, wsb: lib.gcnb_fresh_bn_backward(
+        n, f, y, ldy, 1, g, ldg, mean, rstd, dy, lddy, gstat, ws, wsb, None)
+    assert fwd(0, 8, None, 8, None, 8, None, None, None, 0) == 0             # empty batch: nothing to do
+    assert bwd(0, 8, None, 8, None, 8, None, None, None, 8, None, None, 0) == 0
+    for call, msg in ((lambda: fwd(4, 0, a, 8, a, 8, a, a, a, 4096), "shape out of range"),
+                    (lambda: fwd(-1, 8, a, 8, a, 8, a, a, a, 4096), "shape out of range"),
+                    (lambda: fwd(4, 8, a, 8, a, 8, a, a, a, 4096, eps=-1.0), "eps"),
+                    (lambda: fwd(4, 8, None, 8, a, 8, a, a, a, 4096), "null operand"),
+                    (lambda: fwd(4, 8, a, 7, a, 8, a, a, a, 4096), "leading dimension"),
+                    (lambda: fwd(4, 8, a, 8, a, 8, a, a, a, 8), "workspace too small"),
+                    (lambda: fwd(4, 8, a, 8, a, 8, a, a, a + 4, 4096), "misaligned"),
+                    (lambda: bwd(4, 8, a, 8, None, 8, a, a, a, 8, a, a, 4096), "null operand"),
+                    (lambda: bwd(4, 8, a, 8, a, 8, a, a, a, 7, a, a, 4096), "leading dimension"),
+                    (lambda: bwd(4, 8, a, 8, a, 8, a, a, a, 8, a, a, 8), "workspace too small")):
+        st = call()
+        assert st == 1 and msg in _lib.last_error(), (st, msg, _lib.last_error())
+
+
 def test_init_draws_match_reference(golden):
     import pygcn_b200 as P
 
