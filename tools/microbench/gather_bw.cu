@@ -138,6 +138,58 @@ __global__ void __launch_bounds__(256, 2) k_bulk(const int* __restrict__ idx, in
   if (acc.x + acc.y + acc.z + acc.w == 12345.678f) out[0] = acc.x;
 }
 
+// G: the gathers themselves as 16-byte cp.async (LDGSTS) into a per-warp shared-memory ring, read back with LDS.128.
+// No destination registers are held while a gather is in flight, so the number of lines in flight is bounded by shared
+// memory (STAGES - 1 stages of 32 rows x 128 B per warp), not by the register file -- the question for the SpMM, where
+// 64 % of the stall samples wait on the join of four register-held gathers (profiles/r01_spmm_group_v3_source_stalls.txt).
+// Price: every gathered line crosses the L1/TEX pipe twice (fill + LDS).  Written at the end of round 1, not yet run.
+template <int STAGES>
+__global__ void __launch_bounds__(256) k_cpasync(const int* __restrict__ idx, int64_t m, const float* __restrict__ t, float* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, sub = lane & 7, slot = lane >> 3;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  uint8_t* my = smem + (size_t)w * (STAGES * 4096);
+  const char* base = reinterpret_cast<const char*>(t) + sub * 16;
+  auto issue = [&](int64_t b0, int s) {  // rows slot, slot + 4, ... of the stage; lane moves chunk `sub` of each
+    const int mine = __ldg(idx + b0 + lane);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = __shfl_sync(0xffffffffu, mine, slot + 4 * k);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my + s * 4096 + (slot + 4 * k) * 128 + sub * 16)),
+                   "l"(base + (uint64_t)(uint32_t)c * 128u) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float4 acc = make_float4(0, 0, 0, 0);
+  const int64_t stride = nwarps * 32;
+  int64_t b_issue = warp * 32;
+  int n_issued = 0;
+  for (; n_issued < STAGES - 1; ++n_issued, b_issue += stride) {
+    if (b_issue + 32 <= m) issue(b_issue, n_issued);
+    else asm volatile("cp.async.commit_group;" ::: "memory");  // keep the group count uniform
+  }
+  int cons = 0;
+  for (int64_t b0 = warp * 32; b0 + 32 <= m; b0 += stride) {
+    if (b_issue + 32 <= m) issue(b_issue, n_issued % STAGES);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    ++n_issued;
+    b_issue += stride;
+    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+    __syncwarp();
+    const float4* st = reinterpret_cast<const float4*>(my + (cons % STAGES) * 4096);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 x = st[(slot + 4 * k) * 8 + sub];
+      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+    __syncwarp();
+    ++cons;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (acc.x + acc.y + acc.z + acc.w == 12345.678f) out[0] = acc.x;
+}
+
 template <typename F>
 float time_ms(F f, void* flush, size_t flush_bytes, int reps = 5) {
   cudaEvent_t a, b;
@@ -198,6 +250,22 @@ int main(int argc, char** argv) {
     report(nm, time_ms([&] { k_bulk<4><<<sms * ctas, 256, 8 * (4 * 4096 + 64)>>>(idx, m, t, out); }, flush, flush_bytes));
     snprintf(nm, 128, "F TMA bulk 128B x32/stage, 2 stages, grid=%dx148", ctas);
     report(nm, time_ms([&] { k_bulk<2><<<sms * ctas, 256, 8 * (2 * 4096 + 64)>>>(idx, m, t, out); }, flush, flush_bytes));
+  }
+  // G: cp.async gathers into shared memory (lines in flight bounded by shared memory, not registers)
+  {
+    auto run_g = [&](auto kern, int stages, int ctas) {
+      const int smem_bytes = 8 * stages * 4096;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      char nm[128];
+      snprintf(nm, 128, "G cp.async 16B -> smem, %d stages, grid=%dx148 (%d lines in flight / SM)", stages, ctas,
+               ctas * 8 * (stages - 1) * 32);
+      report(nm, time_ms([&] { kern<<<sms * ctas, 256, smem_bytes>>>(idx, m, t, out); }, flush, flush_bytes));
+    };
+    run_g(k_cpasync<2>, 2, 3);
+    run_g(k_cpasync<2>, 2, 2);
+    run_g(k_cpasync<3>, 3, 2);
+    run_g(k_cpasync<4>, 4, 1);
+    run_g(k_cpasync<6>, 6, 1);
   }
   // table warm in L2 (no flush between), pattern A
   {

@@ -20,6 +20,10 @@ one)
   timeout 60 python tools/variant_sweep.py 13,16,14,17 20 > gpurun_out/variant_sweep_persistent.txt 2>&1
   # the bf16 panel kernels were not in the CTA-shape sweeps: 64-byte rows stay on variant 0 until this says otherwise
   timeout 60 python tools/variant_sweep.py 0,2,13,14 20 --bf16 > gpurun_out/variant_sweep_bf16.txt 2>&1
+  # bare-gather floor again, now with mode G: the gathers as 16-byte cp.async into shared memory (lines in flight bounded
+  # by shared memory instead of registers) -- decides whether a cp.async-gather SpMM variant is worth writing
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/microbench/gather_bw tools/microbench/gather_bw.cu \
+    && timeout 90 tools/microbench/gather_bw > gpurun_out/gather_bw_cpasync.txt 2>&1
   # (ReLU ->) fresh BatchNorm: parity and time against torch's relu + batch_norm
   timeout 90 python tools/bn_probe.py 20 > gpurun_out/bn_probe.txt 2>&1
   # with PDL on, the whole bench line
