@@ -524,11 +524,29 @@ def apply_bn(x, relu=False, eps=1e-5):
     BatchNorm1d -- affine weight 1 / bias 0, batch statistics (biased variance, eps 1e-5) whatever the model's
     train / eval mode.  relu=True folds the `F.relu` the models apply first (`apply_bn(F.relu(gc(x, adj)))`,
     models.py:49,53) and its backward mask into the same two passes:  apply_bn(y, relu=True) == apply_bn(F.relu(y)).
+    x may also be this package's batched samples [B, N, F]: normalised per sample, as the per-sample loop does.
     Differentiable w.r.t. x.  Errors mirror torch's: fewer than 2 rows raise ValueError, CPU tensors raise (no
     fallback).  Opt-in: written at the end of round 1, not yet run on hardware (tests/test_gpu_optin.py)."""
     _require_cuda(x, "x")
+    if x.dim() == 3:
+        # this package's batched-samples layout x[B, N, F] (GraphConvolution.forward(x[B, N, Fin], adj), DESIGN 3.5): the
+        # per-sample loop of GCN_OVER_MLP (pygcn/models.py:343-349) applies a fresh BatchNorm to every sample's [N, F]
+        # output, i.e. statistics per (sample, feature) over the N nodes -- one pass over the node-major [N, B*F] panel,
+        # which is how the batched layer stores its output (a free view).  NOT torch's [B, C, L] convention.
+        if x.dtype != torch.float32:
+            raise RuntimeError("expected float32, got %s" % x.dtype)
+        b, n, f = x.shape
+        if n < 2:
+            raise ValueError("Expected more than 1 value per channel when training, got input size %s" % (tuple(x.shape),))
+        if b == 0 or f == 0:
+            return torch.empty_like(x)
+        xn = x.permute(1, 0, 2)
+        if not xn.is_contiguous():
+            xn = xn.contiguous()
+        out = _FreshBatchNormFn.apply(xn.reshape(n, b * f), bool(relu), float(eps))
+        return out.view(n, b, f).permute(1, 0, 2)
     if x.dim() != 2:
-        raise ValueError("expected 2D input (got %dD input)" % x.dim())  # the reference passes [N, F] (models.py:44)
+        raise ValueError("expected 2D input [N, F] or batched samples [B, N, F] (got %dD input)" % x.dim())  # models.py:44
     if x.dtype != torch.float32:
         raise RuntimeError("expected float32, got %s" % x.dtype)
     if x.shape[0] < 2:

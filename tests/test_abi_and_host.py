@@ -178,3 +178,43 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.GcnbError, match="no CPU/PyTorch fallback"):
         _lib.load(build_if_missing=False)
+
+
+def test_apply_bn_batched_layout_plumbing(monkeypatch):
+    """apply_bn(x[B, N, F]): the host-side plumbing (node-major view, one 2-D call on [N, B*F], the permuted view back,
+    autograd through the views) with a torch stand-in for the CUDA op -- the result is the per-sample loop of
+    GCN_OVER_MLP.forward (pygcn/models.py:343-349), for batch-major storage and for the batched layer's own layout."""
+    import pygcn_b200.functional as Fn
+
+    calls = []
+
+    class StandIn:
+        @staticmethod
+        def apply(x2, relu, eps):
+            calls.append(tuple(x2.shape))
+            assert x2.dim() == 2 and x2.is_contiguous()
+            a = torch.relu(x2) if relu else x2
+            return (a - a.mean(0)) / torch.sqrt(a.var(0, unbiased=False) + eps)
+
+    monkeypatch.setattr(Fn, "_require_cuda", lambda t, what: None)
+    monkeypatch.setattr(Fn, "_FreshBatchNormFn", StandIn)
+    gen = torch.Generator().manual_seed(3)
+    b, n, f = 4, 50, 6
+    x = torch.randn(b, n, f, generator=gen, requires_grad=True)
+    g = torch.randn(b, n, f, generator=gen)
+    out = Fn.apply_bn(x, relu=True)
+    out.backward(g)
+    got_grad = x.grad.clone()
+    x.grad = None
+    want = torch.stack([torch.nn.BatchNorm1d(f)(torch.relu(x[i])) for i in range(b)])
+    want.backward(g)
+    assert out.shape == (b, n, f) and calls == [(n, b * f)]
+    assert torch.allclose(out, want, atol=1e-5) and torch.allclose(got_grad, x.grad, atol=1e-5)
+    node_major = torch.randn(n, b, f, generator=gen).permute(1, 0, 2)  # what the batched layer returns: a free view
+    assert torch.allclose(Fn.apply_bn(node_major), torch.stack([torch.nn.BatchNorm1d(f)(node_major[i]) for i in range(b)]),
+                          atol=1e-5)
+    with pytest.raises(ValueError):
+        Fn.apply_bn(torch.zeros(2, 1, 3))       # one node per sample: torch's training-mode error
+    with pytest.raises(ValueError):
+        Fn.apply_bn(torch.zeros(2, 2, 3, 4))
+    assert Fn.apply_bn(torch.zeros(0, 5, 3)).shape == (0, 5, 3)

@@ -145,3 +145,19 @@ def test_real_kernel_source_matches_the_reference_fixture(sim, golden, name):
     assert O.normwise_err(dy, c[name + "/dy"]) < (1e-4 if name == "two_rows" else 1e-5)
     if name == "deadcol":
         assert not out[:, 3].any() and not dy[:, 3].any()
+
+
+def test_batched_samples_are_columns_of_the_node_major_panel(sim):
+    """apply_bn(x[B, N, F]) runs the 2-D op on the node-major [N, B*F] panel: per-(sample, feature) statistics, i.e.
+    exactly the per-sample loop of GCN_OVER_MLP.forward (pygcn/models.py:343-349) -- here through the real kernels."""
+    rs = np.random.default_rng(3)
+    b, n, f = 3, 150, 4
+    x = rs.standard_normal((b, n, f), dtype=np.float32) + np.float32(0.2)
+    g = rs.standard_normal((b, n, f), dtype=np.float32)
+    panel = np.ascontiguousarray(x.transpose(1, 0, 2)).reshape(n, b * f)
+    out, dy, _, _ = run(sim, panel, np.ascontiguousarray(g.transpose(1, 0, 2)).reshape(n, b * f), True)
+    out = out.reshape(n, b, f).transpose(1, 0, 2)
+    dy = dy.reshape(n, b, f).transpose(1, 0, 2)
+    for i in range(b):
+        assert O.normwise_err(out[i], O.fresh_batchnorm_forward(x[i], True)[0]) < 1e-5
+        assert O.normwise_err(dy[i], O.fresh_batchnorm_backward(x[i], g[i], True)) < 1e-5

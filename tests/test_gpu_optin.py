@@ -210,3 +210,29 @@ def test_graph_from_cites_and_load_adj_files_on_the_device(tmp_path, golden):
     assert _normwise(adj.cpu(), torch.from_numpy(c["adj"])) < 1e-5
     adj1, _ = IO.load_adj_files("SanFrancisco", "/nonexistent", str(out), dev())
     assert torch.equal(adj1, adj)
+
+
+def test_apply_bn_on_batched_samples_equals_the_per_sample_loop():
+    """x[B, N, F] (the batched layer's output layout): one pass over the node-major [N, B*F] panel == apply_bn on every
+    sample, the loop of GCN_OVER_MLP.forward (pygcn/models.py:343-349); gradients too; composed with the batched layer."""
+    import pygcn_b200 as P
+
+    b, n, fin, f = 5, 20000, 8, 32
+    gr = _graph(P, n, 10 * n, seed=4)
+    gen = torch.Generator(device=dev()).manual_seed(12)
+    x = torch.randn(b, n, fin, generator=gen, device=dev())
+    g = torch.randn(b, n, f, generator=gen, device=dev())
+    torch.manual_seed(42)
+    layer = P.GraphConvolution(fin, f).to(dev())
+    layer.zero_grad()
+    out = P.apply_bn(layer(x, gr), relu=True)
+    out.backward(g)
+    dw = layer.weight.grad.clone()
+    layer.zero_grad()
+    outs = torch.stack([_torch_apply_bn(layer(x[i], gr), True) for i in range(b)])
+    outs.backward(g)
+    assert out.shape == (b, n, f)
+    assert _normwise(out.detach(), outs.detach()) < 1e-5 and _normwise(dw, layer.weight.grad) < 1e-5
+    plain = torch.randn(3, 1000, 12, generator=gen, device=dev())  # batch-major storage: one copy into the node-major layout
+    want = torch.stack([_torch_apply_bn(plain[i], False) for i in range(3)])
+    assert _normwise(P.apply_bn(plain), want) < 1e-5
