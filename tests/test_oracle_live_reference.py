@@ -28,7 +28,8 @@ def ref():
     saved = {k: sys.modules.get(k) for k in ("layers", "utils", "models")}
     saved_path = list(sys.path)
     spec.loader.exec_module(mg)
-    layers, utils, _models = mg._load_reference()
+    layers, utils, models = mg._load_reference()
+    mg.models = models
     yield mg, layers, utils
     sys.path[:] = saved_path    # (the loader puts the reference's directories in front)
     for k, v in saved.items():  # do not leave the reference's modules registered for the other tests
@@ -89,3 +90,22 @@ def test_layer_forward_backward_matches_the_reference(ref, seed):
     assert O.normwise_err(dx, xt.grad.numpy()) < 1e-5
     if bias:
         assert O.normwise_err(db, gc.bias.grad.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fresh_batchnorm_matches_the_reference_apply_bn(ref, seed, monkeypatch):
+    """The reference's own `GCN.apply_bn(F.relu(y))` (pygcn/models.py:41-45, 49, 53; its `.cuda()` a no-op here) and its
+    autograd backward against the oracle's restatement on fresh random panels: <= 1e-5 norm-wise (well-conditioned
+    batches: >= 16 rows)."""
+    mg, _layers, _utils = ref
+    monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, device=None: self)
+    rs = np.random.default_rng(3000 + seed)
+    n, f = int(rs.integers(16, 500)), int(rs.integers(1, 48))
+    relu = bool(seed % 2)
+    y = (rs.standard_normal((n, f)) * rs.uniform(0.1, 4.0) + rs.uniform(-1.0, 1.0)).astype(np.float32)
+    g = rs.standard_normal((n, f)).astype(np.float32)
+    yt = torch.from_numpy(y).clone().requires_grad_(True)
+    out = mg.models.GCN.apply_bn(None, torch.relu(yt) if relu else yt)
+    out.backward(torch.from_numpy(g))
+    assert O.normwise_err(O.fresh_batchnorm_forward(y, relu)[0], out.detach().numpy()) < 1e-5
+    assert O.normwise_err(O.fresh_batchnorm_backward(y, g, relu), yt.grad.numpy()) < 1e-5
