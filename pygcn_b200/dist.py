@@ -326,6 +326,34 @@ class CudaOps:
     def empty(self, shape, like):
         return torch.empty(shape, dtype=torch.float32, device=like.device)
 
+    # -- the bf16 panel tier (precision="bf16", <= 2e-2): the exchanged panel is rounded once and gathered at half the bytes
+    def to_bf16(self, panel):
+        """[rows, f] fp32 -> [rows, 8 * ceil(f / 8)] bf16 (round to nearest even, zero padded): gcnb_to_bf16."""
+        rows, f = panel.shape
+        ld8 = (f + 7) // 8 * 8
+        out = torch.empty((rows, ld8), dtype=torch.bfloat16, device=panel.device)
+        with torch.cuda.device(panel.device):
+            st = self.lib.gcnb_to_bf16(rows, f, panel.data_ptr(), panel.stride(0) if rows > 1 else f, out.data_ptr(), ld8,
+                                       self._sp(panel.device))
+        self._lib.check(st, "gcnb_to_bf16")
+        return out
+
+    def empty_bf16(self, shape, like):
+        return torch.empty(shape, dtype=torch.bfloat16, device=like.device)
+
+    def spmm_block_bf16(self, block, dense, f, out, accumulate, bias=None, relu=False):
+        """out (+)= block @ dense[:, :f] (+ bias) (relu) with a bf16 panel `dense` [n_cols, ld8]: gcnb_spmm_bf16
+        (fp32 accumulation and output)."""
+        flags = (self._lib.SPMM_ACCUMULATE if accumulate else 0) | (self._lib.SPMM_RELU if relu else 0)
+        with torch.cuda.device(dense.device):
+            ws = self.F._ws(self.lib.gcnb_spmm_workspace_bytes(block._h, 0, f), dense.device)
+            st = self.lib.gcnb_spmm_bf16(block._h, flags, dense.data_ptr(), dense.stride(0) if dense.shape[0] > 1 else
+                                         dense.shape[1], f, bias.data_ptr() if bias is not None else None, out.data_ptr(),
+                                         out.stride(0) if out.shape[0] > 1 else f, ws.data_ptr(), ws.numel(),
+                                         self._sp(dense.device))
+        self._lib.check(st, "gcnb_spmm_bf16")
+        return out
+
     # -- build-time helpers of the halo exchange (HaloPlan): blocks as CSR tensors and back
     def block_csr(self, block):
         rowptr, col, val = block.csr()
@@ -767,6 +795,28 @@ def dist_spmm(ops, dgraph, diag, remote, panel, bias=None, relu=False, group=Non
     return ops.spmm_block(remote, gathered, out, True, bias, relu)
 
 
+def dist_spmm_bf16(ops, dgraph, diag, remote, panel, bias=None, relu=False, group=None):
+    """dist_spmm with the exchanged panel in bf16 (DistGraphConvolution(precision="bf16"), the <= 2e-2 tier; opt-in, a
+    composition of measured kernels -- gcnb_to_bf16, gcnb_spmm_bf16 -- not yet run over NCCL): this rank's slot is rounded
+    to bf16 once, the all-gather moves HALF the bytes (the exchange is what bounds the multi-GPU step),
+    and the SpMM gathers half the bytes per row; accumulation, bias, ReLU and the output stay fp32.  Every rank rounds
+    the same values the single-GPU bf16 tier rounds, so the result equals that tier's to summation order."""
+    world = dgraph.world
+    f = panel.shape[1]
+    out = ops.empty((dgraph.n_rows(), f), panel)
+    send = ops.to_bf16(panel)
+    if world == 1:
+        return ops.spmm_block_bf16(diag, send, f, out, False, bias, relu)
+    gathered = ops.empty_bf16((world * dgraph.pad_rows, send.shape[1]), panel)
+    if not dgraph.split:
+        allgather_slots(gathered, send, dgraph, group)
+        return ops.spmm_block_bf16(remote, gathered, f, out, False, bias, relu)
+    work = allgather_slots(gathered, send, dgraph, group, async_op=True)
+    ops.spmm_block_bf16(diag, send, f, out, False)
+    work.wait()
+    return ops.spmm_block_bf16(remote, gathered, f, out, True, bias, relu)
+
+
 def halo_plans(ops, dgraph, group=None):
     """(forward, backward) HaloPlan of a DistGraph, built on first use (collective) and kept on the graph."""
     plans = getattr(dgraph, "_halo_plans", None)
@@ -776,7 +826,7 @@ def halo_plans(ops, dgraph, group=None):
     return plans
 
 
-def dist_layer_forward(ops, dgraph, x, w, b, relu=False, group=None, exch=None, chunks=1):
+def dist_layer_forward(ops, dgraph, x, w, b, relu=False, group=None, exch=None, chunks=1, bf16=False):
     """Row block of  A (X W) + b  (pygcn/layers.py:33-36) for this rank.  With `exch` (an exchange
     object for [pad_rows, Fout] panels) the per-source-block pipelined scheme is used; `chunks` > 1
     pipelines the NCCL exchange over column chunks of the panel instead (dist_spmm_chunked)."""
@@ -789,10 +839,13 @@ def dist_layer_forward(ops, dgraph, x, w, b, relu=False, group=None, exch=None, 
     ops.gemm(x, w, out=support)
     if exch == "halo" and dgraph.world > 1:
         return dist_spmm_halo(ops, dgraph, halo_plans(ops, dgraph, group)[0], dgraph.fwd_diag, support, b, relu, group)
+    if bf16:
+        return dist_spmm_bf16(ops, dgraph, dgraph.fwd_diag, dgraph.fwd_remote, support, b, relu, group)
     return dist_spmm(ops, dgraph, dgraph.fwd_diag, dgraph.fwd_remote, support, b, relu, group, chunks)
 
 
-def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=True, group=None, exch=None, chunks=1):
+def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=True, group=None, exch=None, chunks=1,
+                        bf16=False):
     """(dX rows of this rank or None, dW, db): dW/db are already summed over ranks."""
     fin, fout = w.shape
     if exch is not None and exch != "halo" and dgraph.world > 1:
@@ -806,6 +859,8 @@ def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=Tru
         db, _ = ops.colsum(g, y, gm)                 # local part of db; G (masked) staged into its slot
         if exch == "halo" and dgraph.world > 1:
             ds = dist_spmm_halo(ops, dgraph, halo_plans(ops, dgraph, group)[1], dgraph.bwd_diag, gm, None, False, group)
+        elif bf16:
+            ds = dist_spmm_bf16(ops, dgraph, dgraph.bwd_diag, dgraph.bwd_remote, gm, None, False, group)
         else:
             ds = dist_spmm(ops, dgraph, dgraph.bwd_diag, dgraph.bwd_remote, gm, None, False, group, chunks)  # rows p of A^T G
     dw = ops.gemm(x.t(), ds)                         # local part of X^T dS
@@ -820,9 +875,10 @@ def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=Tru
 
 class _DistGCNLayerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, dgraph, relu, ops, group, exch_f=None, exch_b=None, chunks=1):
-        out = dist_layer_forward(ops, dgraph, x, weight, bias, relu, group, exch_f, chunks)
+    def forward(ctx, x, weight, bias, dgraph, relu, ops, group, exch_f=None, exch_b=None, chunks=1, bf16=False):
+        out = dist_layer_forward(ops, dgraph, x, weight, bias, relu, group, exch_f, chunks, bf16)
         ctx.dgraph, ctx.relu, ctx.ops, ctx.group, ctx.exch_b, ctx.chunks = dgraph, relu, ops, group, exch_b, chunks
+        ctx.bf16 = bf16
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, weight, out if relu else None)
         return out
@@ -832,8 +888,8 @@ class _DistGCNLayerFn(torch.autograd.Function):
     def backward(ctx, g):
         x, w, y = ctx.saved_tensors
         dx, dw, db = dist_layer_backward(ctx.ops, ctx.dgraph, x, w, g.contiguous(), y, ctx.needs_input_grad[0],
-                                         ctx.has_bias, ctx.group, ctx.exch_b, ctx.chunks)
-        return dx, dw, db, None, None, None, None, None, None, None
+                                         ctx.has_bias, ctx.group, ctx.exch_b, ctx.chunks, ctx.bf16)
+        return dx, dw, db, None, None, None, None, None, None, None, None
 
 
 class DistGraphConvolution(torch.nn.Module):
@@ -872,6 +928,10 @@ class DistGraphConvolution(torch.nn.Module):
 
     def _exchanges(self, dgraph, dev):
         kind = self.resolve_exchange(self.exchange, dgraph.world)
+        if self.inner.precision == "bf16":  # bf16 panels travel through the all-gather exchange only (dist_spmm_bf16)
+            if self.exchange not in ("auto", "nccl") or self.nccl_chunks != 1:
+                raise ValueError("precision='bf16' of the row-partitioned layer needs exchange 'auto' / 'nccl' and nccl_chunks=1")
+            return None, None
         if kind == "halo" and dgraph.world > 1:
             return "halo", "halo"  # needed-rows-only exchange: the plans live on the DistGraph (halo_plans)
         if dgraph.world == 1 or kind == "nccl" or (kind == "peer" and dgraph.fwd_blocks is None):
@@ -912,7 +972,8 @@ class DistGraphConvolution(torch.nn.Module):
             raise RuntimeError("DistGraphConvolution runs on CUDA devices only (no CPU fallback)")
         ef, eb = self._exchanges(dgraph, input.device)
         return _DistGCNLayerFn.apply(input.contiguous(), self.inner.weight, self.inner.bias, dgraph,
-                                     self.inner.fuse_relu, self._ops, self.group, ef, eb, self.nccl_chunks)
+                                     self.inner.fuse_relu, self._ops, self.group, ef, eb, self.nccl_chunks,
+                                     self.inner.precision == "bf16")
 
 
 # ---------------------------------------------------------------------------- bench entry (N > 1)
@@ -1127,6 +1188,50 @@ def bench_main(args, wl):
     if sampler:
         sampler.stop()
 
+    # opt-in side measurement (GCNB_BENCH_DIST_BF16=1; written after the round's multi-GPU minutes were spent): the same
+    # step with bf16 panels -- half the all-gather bytes, half the gathered bytes -- as eager launches, max over ranks
+    bf16_tier = None
+    if os.environ.get("GCNB_BENCH_DIST_BF16") == "1" and not partitioned:
+        try:
+            layer16 = DistGraphConvolution(fin, fout, exchange="nccl", precision="bf16").to(dev)
+            layer16.inner.load_state_dict(layer.inner.state_dict())
+
+            def step16():
+                layer16.inner.weight.grad = None
+                layer16.inner.bias.grad = None
+                layer16(x, dgraph).backward(g)
+
+            for _ in range(warm):
+                flush()
+                step16()
+            torch.cuda.synchronize()
+            dist.barrier()
+            ev16 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for a_, b_ in ev16:
+                flush()
+                a_.record()
+                step16()
+                b_.record()
+            torch.cuda.synchronize()
+            t16 = torch.tensor([sum(a_.elapsed_time(b_) for a_, b_ in ev16)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t16, op=dist.ReduceOp.MAX)
+            eager_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for a_, b_ in eager_ev:  # the fp32 step as eager launches too, for a like-for-like ratio
+                flush()
+                a_.record()
+                eager_step()
+                b_.record()
+            torch.cuda.synchronize()
+            t32 = torch.tensor([sum(a_.elapsed_time(b_) for a_, b_ in eager_ev)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t32, op=dist.ReduceOp.MAX)
+            bf16_tier = {"ms_per_step_eager": t16.item() / args.steps, "fp32_ms_per_step_eager": t32.item() / args.steps,
+                         "value": nnz_global / (t16.item() / args.steps * 1e-3), "unit": "edges/s", "tolerance": 0.02,
+                         "what": "DistGraphConvolution(precision='bf16'): bf16 slots all-gathered (half the bytes), "
+                                 "gcnb_spmm_bf16 over the gathered panel, everything else fp32"}
+        except Exception as e:  # pragma: no cover  (same code on every rank)
+            sys.stderr.write("rank %d: bf16 side tier failed (%r)\n" % (rank, e))
+            torch.cuda.synchronize()
+
     # dominant kernel on rank 0: the SpMM over its diagonal block, timed alone
     blk = dgraph.fwd_diag if dgraph.split else dgraph.fwd_remote
     ops = CudaOps()
@@ -1188,6 +1293,8 @@ def bench_main(args, wl):
                          "traffic": None, "kernel": "spmm_group_kernel<LPR=8,U=4,24 CTAs/SM,W=2,SE=16> on rank 0's %s" % ("diagonal block" if dgraph.split else "row block (all-gathered panel)"),
                          "algorithmic_bytes_per_launch": alg, "kernel_ms": spmm_ms, "peak_source": peak_src},
         }
+        if bf16_tier is not None:
+            line["bf16_tier"] = bf16_tier
         print(json.dumps(line), flush=True)
     # a captured graph that holds NCCL kernels must go before the communicator does
     del step, cg

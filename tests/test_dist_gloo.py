@@ -62,6 +62,20 @@ class NumpyOps:
     def empty(self, shape, like):
         return torch.full(shape, float("nan"), dtype=torch.float32)  # padding must never be read
 
+    # the bf16 panel tier (dist_spmm_bf16): torch's cast is the same round-to-nearest-even as gcnb_to_bf16
+    def to_bf16(self, panel):
+        rows, f = panel.shape
+        out = torch.zeros((rows, (f + 7) // 8 * 8), dtype=torch.bfloat16)
+        out[:, :f] = panel.to(torch.bfloat16)
+        return out
+
+    def empty_bf16(self, shape, like):
+        return torch.full(shape, float("nan"), dtype=torch.bfloat16)
+
+    def spmm_block_bf16(self, block, dense, f, out, accumulate, bias=None, relu=False):
+        assert dense.dtype == torch.bfloat16
+        return self.spmm_block(block, dense[:, :f].to(torch.float32), out, accumulate, bias, relu)
+
     # build-time helpers of the halo exchange (dist.HaloPlan)
     def block_csr(self, block):
         order = np.argsort(block.row, kind="stable")
@@ -110,7 +124,7 @@ def _problem(n=300, seed=3, fout=5):
     return n, idx, val, x, g, w, b
 
 
-def _worker(rank, world, port, outdir, relu, split=True, pipelined=False, chunks=1, exact=False):
+def _worker(rank, world, port, outdir, relu, split=True, pipelined=False, chunks=1, exact=False, bf16=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -141,8 +155,9 @@ def _worker(rank, world, port, outdir, relu, split=True, pipelined=False, chunks
         if pipelined == "gathered":  # the in-place all-gather route of exchange "nvls" (dist_spmm_gathered)
             ef = InPlaceGather(rank, world, pad, w.shape[1])
             eb = InPlaceGather(rank, world, pad, w.shape[1])
-        out = D.dist_layer_forward(ops, dg, xt, wt, bt, relu=relu, exch=ef, chunks=chunks)
-        dx, dw, db = D.dist_layer_backward(ops, dg, xt, wt, gt, out if relu else None, True, True, exch=eb, chunks=chunks)
+        out = D.dist_layer_forward(ops, dg, xt, wt, bt, relu=relu, exch=ef, chunks=chunks, bf16=bf16)
+        dx, dw, db = D.dist_layer_backward(ops, dg, xt, wt, gt, out if relu else None, True, True, exch=eb, chunks=chunks,
+                                           bf16=bf16)
         np.savez(os.path.join(outdir, "r%d.npz" % rank), out=out.numpy(), dx=dx.numpy(), dw=dw.numpy(), db=db.numpy(),
                  bounds=np.array(bounds))
     finally:
@@ -247,3 +262,35 @@ def test_partition_balances_nnz_and_exchange_is_a_matching():
     assert max(rows(mixed)) <= 2 * 4000 // 8 + 1   # at most twice the even share when both terms weigh the same
     # more ranks than rows: empty blocks allowed
     assert D.partition_rows_by_nnz(np.array([0, 2, 5]), 4)[-1] == 2
+
+
+@pytest.mark.parametrize("world,relu,split,exact", [(2, True, False, False), (3, False, True, False), (4, True, False, True)])
+def test_bf16_panel_tier_of_the_row_partitioned_layer(world, relu, split, exact):
+    """dist_spmm_bf16 (DistGraphConvolution(precision="bf16")): each rank rounds its slot to bf16 once, the all-gather
+    moves the bf16 slots (half the bytes), the SpMM accumulates in fp32.  Equal (<= 1e-5) to the single-process layer
+    with the same two panels rounded -- support forward, the masked gradient backward -- and within 2e-2 of the fp32
+    layer (north_star's bf16 tolerance); unsplit, split and exact-size-slot exchanges."""
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(world, _free_port(), d, relu, split, False, 1, exact, True), nprocs=world, join=True)
+        parts = [np.load(os.path.join(d, "r%d.npz" % r)) for r in range(world)]
+    n, idx, val, x, g, w, b = _problem()
+    rnd = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).to(torch.float32).numpy()
+    a = np.zeros((n, n), np.float64)
+    np.add.at(a, (idx[0], idx[1]), val.astype(np.float64))
+    o_t = a @ rnd(x @ w).astype(np.float64) + b            # the tier: bf16(support) gathered, fp32 everything else
+    gm = g
+    if relu:
+        gm = np.where(o_t > 0, g, 0).astype(np.float32)
+        o_t = np.maximum(o_t, 0)
+    ds_t = a.T @ rnd(gm).astype(np.float64)
+    dw_t, db_t, dx_t = x.T.astype(np.float64) @ ds_t, gm.sum(0), ds_t @ w.T.astype(np.float64)
+    out = np.concatenate([p["out"] for p in parts])
+    dxs = np.concatenate([p["dx"] for p in parts])
+    assert O.normwise_err(out, o_t) < 1e-5 and O.normwise_err(dxs, dx_t) < 1e-5
+    for p in parts:
+        assert O.normwise_err(p["dw"], dw_t) < 1e-5 and O.normwise_err(p["db"], db_t) < 1e-5
+    _, o_ref = O.c_layer_forward(x, w, b, idx, val, n)      # and the fp32 layer within the tier's tolerance
+    g32 = O.relu_backward(g, o_ref) if relu else g
+    dw, db, dx, _ = O.c_layer_backward(x, w, True, idx, val, n, g32)
+    assert O.normwise_err(out, np.maximum(o_ref, 0) if relu else o_ref) < 2e-2
+    assert O.normwise_err(dxs, dx) < 2e-2 and O.normwise_err(parts[0]["dw"], dw) < 2e-2

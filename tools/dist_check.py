@@ -47,9 +47,22 @@ def main():
     if rank == 0:
         print("partitioned build == cut of the full graph: %s (nnz_global %d)" % (same, dg2.nnz_global), flush=True)
     # GCNB_DIST_CHECK_EXCHANGES=peer,nccl,nvls adds the NVLS multicast exchange (written at the end of round 1, not yet run)
+    # "nccl-bf16": the bf16 panel tier of the row-partitioned layer (dist_spmm_bf16), checked against the single-GPU layer
+    # of the same tier (same two panels rounded: equal to summation order)
+    fp32_ref = (o_ref, xr.grad, ref.weight.grad, ref.bias.grad)
     for exchange in os.environ.get("GCNB_DIST_CHECK_EXCHANGES", "peer,nccl").split(","):
+        precision = "auto"
+        o_ref, dx_ref, dw_ref, db_ref = fp32_ref
+        if exchange.endswith("-bf16"):
+            exchange, precision = exchange[:-5], "bf16"
+            torch.manual_seed(42)
+            ref16 = P.GraphConvolution(fin, fout, fuse_relu=True, precision="bf16").to(dev)
+            x16 = x.clone().requires_grad_(True)
+            o_ref = ref16(x16, full)
+            o_ref.backward(g)
+            o_ref, dx_ref, dw_ref, db_ref = o_ref.detach(), x16.grad, ref16.weight.grad, ref16.bias.grad
         torch.manual_seed(42)
-        layer = D.DistGraphConvolution(fin, fout, fuse_relu=True, exchange=exchange).to(dev)
+        layer = D.DistGraphConvolution(fin, fout, fuse_relu=True, exchange=exchange, precision=precision).to(dev)
         xl = x[r0:r1].clone().requires_grad_(True)
         gl = g[r0:r1].contiguous()
         for step in range(4):
@@ -61,9 +74,9 @@ def main():
         torch.cuda.synchronize()
         errs = {
             "out": ((out - o_ref[r0:r1]).abs().max() / o_ref.abs().max()).item(),
-            "dX": ((xl.grad - xr.grad[r0:r1]).abs().max() / xr.grad.abs().max()).item(),
-            "dW": ((layer.inner.weight.grad - ref.weight.grad).abs().max() / ref.weight.grad.abs().max()).item(),
-            "db": ((layer.inner.bias.grad - ref.bias.grad).abs().max() / ref.bias.grad.abs().max()).item(),
+            "dX": ((xl.grad - dx_ref[r0:r1]).abs().max() / dx_ref.abs().max()).item(),
+            "dW": ((layer.inner.weight.grad - dw_ref).abs().max() / dw_ref.abs().max()).item(),
+            "db": ((layer.inner.bias.grad - db_ref).abs().max() / db_ref.abs().max()).item(),
         }
         good = all(v < 1e-5 for v in errs.values())
         ok = ok and good
@@ -71,7 +84,7 @@ def main():
         # (fresh leaf: an AccumulateGrad node born on the default stream would pull the legacy stream into
         # the capture)
         torch.manual_seed(42)
-        layer = D.DistGraphConvolution(fin, fout, fuse_relu=True, exchange=exchange).to(dev)
+        layer = D.DistGraphConvolution(fin, fout, fuse_relu=True, exchange=exchange, precision=precision).to(dev)
         s_ = torch.cuda.Stream()
         s_.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s_):
@@ -106,8 +119,8 @@ def main():
         e_graph = ((o_static - o_ref[r0:r1]).abs().max() / o_ref.abs().max()).item()
         ok = ok and e_graph < 1e-5
         if rank == 0:
-            print("exchange=%s world=%d n=%d nnz=%d: errs %s graph-replay out err %.2e  step %.3f ms (max over ranks, no L2 flush) %s" % (
-                exchange, world, n, full.nnz, {k: "%.1e" % v for k, v in errs.items()}, e_graph, ms.item(),
+            print("exchange=%s precision=%s world=%d n=%d nnz=%d: errs %s graph-replay out err %.2e  step %.3f ms (max over ranks, no L2 flush) %s" % (
+                exchange, precision, world, n, full.nnz, {k: "%.1e" % v for k, v in errs.items()}, e_graph, ms.item(),
                 "OK" if good else "FAIL"), flush=True)
         del cg, layer
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)

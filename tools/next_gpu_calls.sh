@@ -32,7 +32,7 @@ one)
 two)
   # parity of every exchange with the single-GPU layer at 2 GPUs, eager and graph replay; "nvls" = the multicast
   # exchange (own multimem.st push into torch symmetric memory), written but never run in round 1
-  GCNB_DIST_CHECK_EXCHANGES=peer,nccl,nvls,halo timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
+  GCNB_DIST_CHECK_EXCHANGES=peer,nccl,nccl-bf16,nvls,halo timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
     --master-addr 127.0.0.1 --master-port 29513 tools/dist_check.py > gpurun_out/dist_check_2gpu_nvls.txt 2>&1
   # the exact-size slot exchange (grouped send / recv instead of the padded all-gather) and the column-chunked one
   GCNB_DIST_EXACT_SLOTS=1 GCNB_DIST_CHECK_EXCHANGES=nccl timeout 120 python -m torch.distributed.run --nnodes=1 \
@@ -48,6 +48,10 @@ eight)
   GCNB_BENCH_E2E=pipelined timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
     --master-addr 127.0.0.1 --master-port 29510 bench.py --gpus 8 --steps 20 --warmup 5 \
     > gpurun_out/bench_n8_e2e_pipelined.json 2> gpurun_out/bench_n8_e2e_pipelined.err
+  # the bf16 panel tier of the row-partitioned layer beside the fp32 step (half the exchange bytes)
+  GCNB_BENCH_DIST_BF16=1 timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
+    --master-addr 127.0.0.1 --master-port 29516 bench.py --gpus 8 --steps 20 --warmup 5 \
+    > gpurun_out/bench_n8_bf16_tier.json 2> gpurun_out/bench_n8_bf16_tier.err
   for chunks in 1 2; do
     GCNB_DIST_NCCL_CHUNKS=$chunks timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
       --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 5 \
