@@ -294,3 +294,31 @@ def test_bf16_panel_tier_of_the_row_partitioned_layer(world, relu, split, exact)
     dw, db, dx, _ = O.c_layer_backward(x, w, True, idx, val, n, g32)
     assert O.normwise_err(out, np.maximum(o_ref, 0) if relu else o_ref) < 2e-2
     assert O.normwise_err(dxs, dx) < 2e-2 and O.normwise_err(parts[0]["dw"], dw) < 2e-2
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_autograd_function_of_the_partitioned_layer_at_world_1(bf16):
+    """_DistGCNLayerFn (what DistGraphConvolution.forward calls) end to end through torch autograd with the numpy
+    backend at world size 1 -- no process group needed: argument / gradient arity, ctx plumbing, needs_input_grad,
+    the fused-ReLU mask, both precision tiers."""
+    n, idx, val, x, g, w, b = _problem()
+    tidx = np.vstack([idx[1], idx[0]])
+    bounds = [0, n]
+    pad = D.DistGraph.padded_rows(bounds)
+    dg = D.DistGraph(0, 1, bounds, pad, HostBlock(idx, val, 0, n, c0=0, c1=n), None, HostBlock(tidx, val, 0, n, c0=0, c1=n),
+                     None, idx.shape[1], idx.shape[1], True)
+    xt = torch.from_numpy(x.copy()).requires_grad_(True)
+    wt = torch.from_numpy(w.copy()).requires_grad_(True)
+    bt = torch.from_numpy(b.copy()).requires_grad_(True)
+    out = D._DistGCNLayerFn.apply(xt, wt, bt, dg, True, NumpyOps(), None, None, None, 1, bf16)
+    out.backward(torch.from_numpy(g))
+    _, o_ref = O.c_layer_forward(x, w, b, idx, val, n)
+    dw, db, dx, _ = O.c_layer_backward(x, w, True, idx, val, n, O.relu_backward(g, o_ref))
+    tol = 2e-2 if bf16 else 1e-5
+    assert O.normwise_err(out.detach().numpy(), np.maximum(o_ref, 0)) < tol
+    assert O.normwise_err(wt.grad.numpy(), dw) < tol and O.normwise_err(xt.grad.numpy(), dx) < tol
+    assert O.normwise_err(bt.grad.numpy(), db) < tol
+    x2 = torch.from_numpy(x.copy())  # input without grad: no dX is computed
+    out2 = D._DistGCNLayerFn.apply(x2, wt, None, dg, False, NumpyOps(), None, None, None, 1, bf16)
+    out2.sum().backward()
+    assert x2.grad is None and out2.shape == (n, w.shape[1])
