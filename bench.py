@@ -29,8 +29,8 @@ WORKLOADS = {
     "reddit": dict(n=232_965, avg_deg=492, fin=602, fout=256,
                    name="synthetic Reddit shape: N=232965, nnz~114.6M, 602->256"),
     # configs[3]: ogbn-products-shaped, hidden layer
-    "products": dict(n=2_449_029, avg_deg=25, fin=100, fout=256,
-                     name="synthetic ogbn-products shape: N=2449029, nnz~62M, 100->256"),
+    "products": dict(n=2_449_029, avg_deg=25, n_raw=31_000_000, family="rmat", fin=100, fout=256,
+                     name="synthetic ogbn-products shape: N=2449029, R-MAT(.57,.19,.19,.05) 31M raw edges, nnz~62.8M, 100->256"),
     # configs[4]: ogbn-papers100M-shaped, multi-GPU only: 1.6 G stored entries exceed one int32 graph handle, every
     # rank builds its own row block from the replicated edge list (dist.build_partitioned); fixed total size
     "papers": dict(n=111_059_956, n_raw=752_000_000, avg_deg=14, fin=128, fout=128, partitioned=True,
@@ -117,13 +117,37 @@ def algorithmic_bytes_spmm(nnz, n, f):
     return nnz * 8 + (n + 1) * 4 + n * f * 4 + n * f * 4
 
 
-def make_graph(P, torch, wl, dev, seed=0):
-    n = wl["n"]
-    n_raw = n * wl["avg_deg"] // 2
-    gen = torch.Generator(device=dev).manual_seed(seed)
-    src = torch.randint(0, n, (n_raw,), generator=gen, device=dev, dtype=torch.int32)
-    dst = torch.randint(0, n, (n_raw,), generator=gen, device=dev, dtype=torch.int32)
-    g = P.Graph.from_edges(src, dst, n)  # sym (max) + I + D^-1: the reference's pipeline, on device
+def rmat_edges(torch, n, n_edges, gen, device, a=0.57, b=0.19, c=0.19):
+    """R-MAT endpoints (BASELINE.md 3.3 / SURVEY.md 8d: a, b, c, d = .57, .19, .19, .05), one quadrant choice per
+    address bit, folded into [0, n).  Power-law degrees: hubs, every row-length bin, the long-row split."""
+    bits = max(1, (n - 1).bit_length())
+    src = torch.zeros(n_edges, dtype=torch.int64, device=device)
+    dst = torch.zeros(n_edges, dtype=torch.int64, device=device)
+    for _ in range(bits):
+        r = torch.rand(n_edges, generator=gen, device=device)
+        src = src * 2 + (r >= a + b).to(torch.int64)
+        dst = dst * 2 + (((r >= a) & (r < a + b)) | (r >= a + b + c)).to(torch.int64)
+    return (src % n).to(torch.int32), (dst % n).to(torch.int32)
+
+
+def make_edges(torch, wl, seed=0, device="cpu", shrink=1):
+    """The workload's seeded raw edge list.  Drawn with a CPU torch.Generator by default so that both arms of the
+    benchmark (ours and --impl reference) see the SAME edges; shrink > 1 draws the same family at 1/shrink of the
+    nodes and edges (the CPU arms' bounded sample)."""
+    n = wl["n"] // shrink
+    n_raw = wl.get("n_raw", wl["n"] * wl["avg_deg"] // 2) // shrink
+    gen = torch.Generator(device=device).manual_seed(seed)
+    if wl.get("family", "uniform") == "rmat":
+        src, dst = rmat_edges(torch, n, n_raw, gen, device)
+    else:
+        src = torch.randint(0, n, (n_raw,), generator=gen, device=device, dtype=torch.int32)
+        dst = torch.randint(0, n, (n_raw,), generator=gen, device=device, dtype=torch.int32)
+    return src, dst, n
+
+
+def make_graph(P, torch, wl, dev, seed=0, edges_on="cpu"):
+    src, dst, n = make_edges(torch, wl, seed, device=edges_on)
+    g = P.Graph.from_edges(src.to(dev), dst.to(dev), n)  # sym (max) + I + D^-1: the reference's pipeline, on device
     del src, dst
     return g
 

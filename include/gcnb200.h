@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GCNB_VERSION 104
+#define GCNB_VERSION 200
 
 #define GCNB_OK 0
 #define GCNB_E_INVALID 1  /* bad argument (shape, null pointer, alignment, overflow)  */
@@ -283,13 +283,26 @@ int gcnb_peer_ack(uint32_t* peer_ack, const uint32_t* d_epoch, void* stream);
 /* Tuning knobs (process-wide, not thread-safe against concurrent launches; for tests and benchmarks).
  *   GCNB_TUNE_SPMM_KERNEL: 0 auto (default), 1 warp-per-row shuffle kernel, 2 group-per-row kernel,
  *                          3 TMA-staged warp-per-row kernel
- *   GCNB_TUNE_SPMM_GROUP_VARIANT: -1 auto, 0..17 = (gathers in flight, CTAs/SM, warps per CTA, stage entries) of
+ *   GCNB_TUNE_SPMM_GROUP_VARIANT: -1 auto, 0..15 = (gathers in flight, CTAs/SM, warps per CTA, stage entries) of
  *   the group kernel (spmm.cu) */
 #define GCNB_TUNE_SPMM_KERNEL 1
 #define GCNB_TUNE_SPMM_GROUP_VARIANT 2
 /*   GCNB_TUNE_PDL: 0 (default) plain stream order; 1 = the layer's kernels are launched with programmatic
  *   stream serialization (each starts while its predecessor drains and waits on-device before touching its output) */
 #define GCNB_TUNE_PDL 3
+/*   The streaming SpMM (spmm_stream.cu: entry-balanced items, one TMA copy per gathered panel row, L2 eviction hints):
+ *   GCNB_TUNE_SPMM_STREAM: 0 off, 1 auto (default: panel rows of >= MIN_ROW_BYTES on graphs without empty rows),
+ *                          2 wherever the view is eligible;
+ *   GCNB_TUNE_STREAM_HOT_MB: L2 budget (MB, default 48) for the rows of the most referenced columns (evict_last);
+ *   GCNB_TUNE_STREAM_HINT: 0 no eviction hints, 1 hot rows evict_last, 2 (default) + the other rows evict_first;
+ *   GCNB_TUNE_STREAM_MIN_ROW_BYTES: auto threshold (default 256);  GCNB_TUNE_STREAM_BATCH: 0 auto, 8 / 16 / 32 rows
+ *   per TMA batch.  Environment: GCNB_SPMM_STREAM, GCNB_L2_HOT_MB, GCNB_STREAM_HINT, GCNB_STREAM_MIN_ROW_BYTES,
+ *   GCNB_STREAM_BATCH. */
+#define GCNB_TUNE_SPMM_STREAM 4
+#define GCNB_TUNE_STREAM_HOT_MB 5
+#define GCNB_TUNE_STREAM_HINT 6
+#define GCNB_TUNE_STREAM_MIN_ROW_BYTES 7
+#define GCNB_TUNE_STREAM_BATCH 8
 int gcnb_set_tuning(int key, int value);
 
 /* L2 flush helper for benchmarks: writes `bytes` of d_buf. */

@@ -27,6 +27,7 @@ SPMM_TRANSPOSE, SPMM_RELU, SPMM_ACCUMULATE = 1, 2, 4
 GEMM_FP32, GEMM_TF32X3, GEMM_AUTO = 0, 1, 2
 LAYER_RELU, LAYER_NEED_DX, LAYER_NEED_DW, LAYER_NEED_DB = 1, 2, 4, 8
 TUNE_SPMM_KERNEL, TUNE_SPMM_GROUP_VARIANT, TUNE_PDL = 1, 2, 3
+TUNE_SPMM_STREAM, TUNE_STREAM_HOT_MB, TUNE_STREAM_HINT, TUNE_STREAM_MIN_ROW_BYTES, TUNE_STREAM_BATCH = 4, 5, 6, 7, 8
 
 
 class GraphInfo(ctypes.Structure):
@@ -110,10 +111,22 @@ def load(build_if_missing=True):
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH) and build_if_missing:
-            from . import build as _build
+        from . import build as _build
 
-            _build.build()
+        # a library older than csrc/ or include/gcnb200.h would be called with the NEW signatures below: rebuild it
+        # when nvcc is here, refuse to load it otherwise (GCNB_SKIP_STALE_CHECK=1 for a tree shipped without sources)
+        stale = os.path.exists(LIB_PATH) and os.environ.get("GCNB_SKIP_STALE_CHECK") != "1" and _build.needs_build()
+        if (stale or not os.path.exists(LIB_PATH)) and build_if_missing:
+            try:
+                _build.build()
+                stale = False
+            except RuntimeError:
+                if not os.path.exists(LIB_PATH):
+                    raise
+        if stale:
+            raise GcnbError(
+                "libgcnb200.so at %s is older than its sources (pygcn_b200/csrc, include/gcnb200.h): rebuild it with "
+                "`python -m pygcn_b200.build`" % LIB_PATH)
         if not os.path.exists(LIB_PATH):
             raise GcnbError(
                 "libgcnb200.so not found at %s: build it with `python -m pygcn_b200.build` "

@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libgcnb200.so")
 
-SOURCES = ["api.cu", "spmm.cu", "gemm_simt.cu", "gemm_skinny.cu", "gemm_tc.cu", "elementwise.cu", "graph_build.cu", "peer.cu", "batchnorm.cu"]
+SOURCES = ["api.cu", "spmm.cu", "spmm_stream.cu", "gemm_simt.cu", "gemm_skinny.cu", "gemm_tc.cu", "elementwise.cu", "graph_build.cu", "peer.cu", "batchnorm.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -43,7 +43,7 @@ def _digest(paths):
     h = hashlib.sha256()
     for p in sorted(paths):
         with open(p, "rb") as f:
-            h.update(p.encode())
+            h.update(os.path.relpath(p, ROOT).encode())  # relative: the digest must not depend on where the tree lives
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()

@@ -81,7 +81,28 @@ struct CsrView {
   const int32_t* long_chunk_ptr = nullptr;  // [n_long_rows+1] prefix of chunks per long row
   int64_t max_degree = 0;
   int64_t bin_rows[GCNB_NUM_BINS] = {0, 0, 0, 0, 0};
+  // Entry-balanced ("merge-style") schedule of the streaming SpMM (spmm_stream.cu): item i = stored entries
+  // [i * kStreamItem, (i + 1) * kStreamItem); stream_items[i] = the row holding the item's first entry, bit 31 set
+  // when that row began in an earlier item.  pair_tagged: the pair stream carries, in the upper bits of the column
+  // word, the heat class of the column (bits 27..30, kPairClassShift) and an end-of-row flag (bit 31).
+  int64_t n_stream_items = 0;
+  const uint32_t* stream_items = nullptr;
+  bool pair_tagged = false;
 };
+
+// Tags in the column word of a (col, val) pair (graphs with n_cols <= 2^27; wider ones keep plain columns):
+//   bits 0..26  column
+//   bits 27..30 heat class c of the column: it is among the 1024 * 2^c most referenced columns of the view
+//               (kPairColdClass = not among the 16 M most referenced); the streaming SpMM asks L2 to keep the rows
+//               of the hottest classes (evict_last) -- on a power-law graph a few % of the panel rows take most of
+//               the gathers
+//   bit  31     the entry is the last one of its row
+constexpr int kPairColBits = 27;
+constexpr uint32_t kPairColMask = (1u << kPairColBits) - 1u;
+constexpr int kPairClassShift = kPairColBits;
+constexpr uint32_t kPairColdClass = 15u;
+constexpr uint32_t kPairRowEnd = 0x80000000u;
+constexpr int kStreamItem = 1024;  // stored entries per work item of the streaming SpMM
 
 // Fused SpMM epilogue:  out = dropout(relu(acc (+ out) (+ bias)))   -- pygcn/layers.py:36, the caller's
 // F.relu (models.py:49,53,56) and upstream pygcn's F.dropout on the layer output.
@@ -106,6 +127,14 @@ int to_bf16_launch(int64_t n_rows, int64_t f, const float* src, int64_t ld_src, 
                    cudaStream_t stream);
 size_t spmm_workspace_bytes(const CsrView& a, int64_t f);
 int spmm_set_tuning(int key, int value);
+
+// streaming SpMM (spmm_stream.cu): TMA row gathers over the entry-balanced items of the view
+bool spmm_stream_eligible(const CsrView& a, int64_t row_bytes, int nch);
+size_t spmm_stream_workspace_bytes(const CsrView& a, int64_t f);
+int spmm_stream_launch(const CsrView& a, const void* b, int64_t ldb_bytes, int f, bool bf16, const Epilogue& ep,
+                       float* out, int64_t ldo, bool vec_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+int spmm_stream_mode();         // 0 off, 1 auto (default), 2 forced wherever eligible
+void spmm_stream_set(int key, int value);
 
 int gemm_fp32_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs, int64_t a_cs,
                      const float* b, int64_t b_rs, int64_t b_cs, float* c, int64_t ldc, void* ws,
@@ -180,6 +209,8 @@ struct gcnb_graph {
   int32_t* long_chunk_ptr = nullptr;
   int32_t* t_long_rows = nullptr;
   int32_t* t_long_chunk_ptr = nullptr;
+  uint32_t* stream_items = nullptr;
+  uint32_t* t_stream_items = nullptr;
   gcnb::CsrView fwd, bwd;
   int64_t device_bytes = 0;
 };

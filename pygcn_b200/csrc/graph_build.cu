@@ -427,6 +427,51 @@ __global__ void interleave_kernel(int64_t nnz, const int32_t* __restrict__ col, 
   if (i < nnz) pair[i] = make_uint2((uint32_t)col[i], __float_as_uint(val[i]));
 }
 
+// ---- tags of the pair stream (common.cuh: heat class of the column, end-of-row flag) and the entry-balanced
+// ---- items of the streaming SpMM
+__global__ void col_count_kernel(int64_t nnz, const int32_t* __restrict__ col, int32_t* __restrict__ cnt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nnz) atomicAdd(cnt + col[i], 1);  // integer counts: order-independent
+}
+
+struct HeatThresholds { int32_t t[15]; };  // class c <=> count > t[c] (t non-increasing in c)
+
+// pair[i].x |= class(col) << 27
+__global__ void tag_class_kernel(int64_t nnz, const int32_t* __restrict__ cnt, HeatThresholds th,
+                                 uint2* __restrict__ pair) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  const uint32_t c = pair[i].x;
+  const int32_t k = cnt[c];
+  uint32_t cls = kPairColdClass;
+#pragma unroll
+  for (int j = 14; j >= 0; --j)
+    if (k > th.t[j]) cls = (uint32_t)j;
+  pair[i].x = c | (cls << kPairClassShift);
+}
+
+// the last stored entry of every non-empty row carries kPairRowEnd
+__global__ void tag_row_end_kernel(int64_t n, const int32_t* __restrict__ rowptr, uint2* __restrict__ pair) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int s = rowptr[r], e = rowptr[r + 1];
+  if (e > s) pair[e - 1].x |= kPairRowEnd;
+}
+
+// items[i] = row holding stored entry i * kStreamItem | (that row began before the item ? 1 << 31 : 0)
+__global__ void stream_items_kernel(int64_t n_items, int64_t n, const int32_t* __restrict__ rowptr,
+                                    uint32_t* __restrict__ items) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  const int e = (int)(i * kStreamItem);
+  int64_t lo = 0, hi = n;  // last r in [0, n) with rowptr[r] <= e  (rowptr[0] = 0 <= e); empty rows share a value
+  while (hi - lo > 1) {    // with their successor, so the last such r is the row that holds entry e
+    const int64_t mid = (lo + hi) >> 1;
+    if (rowptr[mid] <= e) lo = mid; else hi = mid;
+  }
+  items[i] = (uint32_t)lo | (rowptr[lo] < e ? 0x80000000u : 0u);
+}
+
 int build_pairs(gcnb_graph* g, const int32_t* col, const float* val, uint2** out, cudaStream_t st) {
   GCNB_TRY(graph_alloc(g, out, g->nnz + 2));  // + slack: stages are copied two entries at a time
   GCNB_CUDA(cudaMemsetAsync(*out, 0, (size_t)(g->nnz + 2) * sizeof(uint2), st));
@@ -434,6 +479,52 @@ int build_pairs(gcnb_graph* g, const int32_t* col, const float* val, uint2** out
     interleave_kernel<<<blocks_for(g->nnz), kT, 0, st>>>(g->nnz, col, val, *out);
     GCNB_LAUNCH_CHECK();
   }
+  return GCNB_OK;
+}
+
+// Tags `pair` (n_rows x n_cols view, CSR rowptr / col) and builds the view's stream items.
+int build_stream_schedule(gcnb_graph* g, const int32_t* rowptr, const int32_t* col, int64_t n_rows, int64_t n_cols,
+                          uint2* pair, CsrView* view, uint32_t** items_out, cudaStream_t st) {
+  const int64_t nnz = g->nnz;
+  view->pair_tagged = false;
+  view->n_stream_items = 0;
+  view->stream_items = nullptr;
+  *items_out = nullptr;
+  if (nnz == 0 || n_cols > (1ll << kPairColBits) || n_rows == 0) return GCNB_OK;
+  // heat classes: class c = among the 1024 * 2^c most referenced columns (strictly more references than the
+  // column at that rank)
+  DevBuf cnt, sorted, temp;
+  GCNB_TRY(cnt.alloc((size_t)n_cols * 4));
+  GCNB_TRY(sorted.alloc((size_t)n_cols * 4));
+  GCNB_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)n_cols * 4, st));
+  col_count_kernel<<<blocks_for(nnz), kT, 0, st>>>(nnz, col, cnt.as<int32_t>());
+  GCNB_LAUNCH_CHECK();
+  size_t tb = 0;
+  GCNB_CUDA(cub::DeviceRadixSort::SortKeysDescending(nullptr, tb, cnt.as<int32_t>(), sorted.as<int32_t>(), (int)n_cols, 0, 32, st));
+  GCNB_TRY(temp.alloc(tb));
+  GCNB_CUDA(cub::DeviceRadixSort::SortKeysDescending(temp.p, tb, cnt.as<int32_t>(), sorted.as<int32_t>(), (int)n_cols, 0, 32, st));
+  HeatThresholds th;
+  for (int c = 0; c < 15; ++c) {
+    const int64_t rank = 1024ll << c;
+    th.t[c] = 0x7fffffff;  // nothing qualifies ...
+    if (rank < n_cols) {
+      GCNB_CUDA(cudaMemcpyAsync(&th.t[c], sorted.as<int32_t>() + rank, 4, cudaMemcpyDeviceToHost, st));
+    } else {
+      th.t[c] = -1;        // ... or, when the class holds every column, everything does
+    }
+  }
+  GCNB_CUDA(cudaStreamSynchronize(st));
+  tag_class_kernel<<<blocks_for(nnz), kT, 0, st>>>(nnz, cnt.as<int32_t>(), th, pair);
+  GCNB_LAUNCH_CHECK();
+  tag_row_end_kernel<<<blocks_for(n_rows), kT, 0, st>>>(n_rows, rowptr, pair);
+  GCNB_LAUNCH_CHECK();
+  view->pair_tagged = true;
+  const int64_t n_items = ceil_div(nnz, kStreamItem);
+  GCNB_TRY(graph_alloc(g, items_out, n_items));
+  stream_items_kernel<<<blocks_for(n_items), kT, 0, st>>>(n_items, n_rows, rowptr, *items_out);
+  GCNB_LAUNCH_CHECK();
+  view->n_stream_items = n_items;
+  view->stream_items = *items_out;
   return GCNB_OK;
 }
 
@@ -503,6 +594,7 @@ int finalize(gcnb_graph* g, const int32_t* rows, cudaStream_t st, bool with_tran
     g->fwd.pair = g->pair;
     g->bwd = CsrView();
     GCNB_TRY(build_schedule(g, g->rowptr, g->n_rows, &g->fwd, &g->long_rows, &g->long_chunk_ptr, st));
+    GCNB_TRY(build_stream_schedule(g, g->rowptr, g->col, g->n_rows, g->n_cols, g->pair, &g->fwd, &g->stream_items, st));
     GCNB_CUDA(cudaStreamSynchronize(st));
     return GCNB_OK;
   }
@@ -567,6 +659,8 @@ int finalize(gcnb_graph* g, const int32_t* rows, cudaStream_t st, bool with_tran
   g->bwd.pair = g->t_pair;
   GCNB_TRY(build_schedule(g, g->rowptr, g->n_rows, &g->fwd, &g->long_rows, &g->long_chunk_ptr, st));
   GCNB_TRY(build_schedule(g, g->t_rowptr, g->n_cols, &g->bwd, &g->t_long_rows, &g->t_long_chunk_ptr, st));
+  GCNB_TRY(build_stream_schedule(g, g->rowptr, g->col, g->n_rows, g->n_cols, g->pair, &g->fwd, &g->stream_items, st));
+  GCNB_TRY(build_stream_schedule(g, g->t_rowptr, g->t_col, g->n_cols, g->n_rows, g->t_pair, &g->bwd, &g->t_stream_items, st));
   GCNB_CUDA(cudaStreamSynchronize(st));
   return GCNB_OK;
 }
@@ -855,6 +949,8 @@ extern "C" void gcnb_graph_free(gcnb_graph* g) {
   cudaFree(g->long_chunk_ptr);
   cudaFree(g->t_long_rows);
   cudaFree(g->t_long_chunk_ptr);
+  cudaFree(g->stream_items);
+  cudaFree(g->t_stream_items);
   cudaFree(g->dense_fwd);
   cudaFree(g->dense_bwd);
   if (cur != g->device) cudaSetDevice(cur);

@@ -275,7 +275,7 @@ template <int LPR, int U, int MINB, bool BF16, int W = kWarpsPerCta, int SE = kS
 __global__ void __launch_bounds__(W * 32, MINB)
 spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* __restrict__ pair, int last_pair,
                   const void* __restrict__ b, uint32_t ldb_bytes, int f, Epilogue ep, float* __restrict__ out,
-                  int64_t ldo, int vec_out, int skip_long, uint32_t never) {
+                  int64_t ldo, int vec_out, int skip_long, uint32_t never, uint32_t col_mask) {
   constexpr int G = 32 / LPR;
   constexpr int A = Panel<BF16>::kAcc;
   constexpr int E = stage_entries(SE, W * G) < 2 * LPR ? 2 * LPR : stage_entries(SE, W * G);  // static shared memory stays < 48 KB (32 entries for LPR >= 4, else 16)
@@ -370,8 +370,8 @@ spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* _
         for (int h = 0; h < U / 2; ++h) q[h] = pairs_at(j + 2 * h);  // j + u < E because U divides E
 #pragma unroll
         for (int h = 0; h < U / 2; ++h) {
-          x[2 * h] = gather(q[h].x);
-          x[2 * h + 1] = gather(q[h].z);
+          x[2 * h] = gather(q[h].x & col_mask);  // the column word may carry tags (common.cuh kPairColMask)
+          x[2 * h + 1] = gather(q[h].z & col_mask);
         }
         const uint32_t zero = all_landed(x, never);
 #pragma unroll
@@ -402,165 +402,6 @@ spmm_group_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* _
     if (skip_long && __ldg(rowptr + row + 1) - __ldg(rowptr + row) >= kLongRowThreshold) return;
     store_panel_chunk<BF16>(out + (int64_t)row * ldo, row, sub, f, vec_out, acc, ep);
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Persistent form of the group-per-row kernel (tuning variants 16 / 17; written after round 1's GPU minutes were
-// spent -- NOT yet run on hardware, never chosen automatically).  The grid is one resident wave; every warp walks
-// row sets  blockIdx.x, blockIdx.x + gridDim.x, ...  and hides the start-up chain of the NEXT set (rowptr -> first
-// stage of pairs -> first gathers, ~2-3 us of a ~26 us row) behind the current one: the next set's row pointers are
-// loaded when the current set starts, and in the last stage iteration of the current set -- where the plain kernel
-// issues an empty fetch -- the next set's first stage is copied into the free buffer.  Everything else (staging,
-// batches of U gathers, all_landed, per-row order) is the kernel above.
-template <int LPR, int U, int MINB, bool BF16, int W, int SE>
-__global__ void __launch_bounds__(W * 32, MINB)
-spmm_group_persistent_kernel(int n_rows, const int32_t* __restrict__ rowptr, const uint2* __restrict__ pair, int last_pair,
-                             const void* __restrict__ b, uint32_t ldb_bytes, int f, Epilogue ep, float* __restrict__ out,
-                             int64_t ldo, int vec_out, int skip_long, uint32_t never) {
-  constexpr int G = 32 / LPR;
-  constexpr int A = Panel<BF16>::kAcc;
-  constexpr int E = stage_entries(SE, W * G) < 2 * LPR ? 2 * LPR : stage_entries(SE, W * G);
-  constexpr int NC = E / (2 * LPR);
-  static_assert(E % U == 0 && U % 2 == 0 && NC >= 1, "batches of U entries must divide the stage");
-  constexpr uint32_t kBufBytes = 8u * (E + 2);
-  __shared__ __align__(16) uint2 stage[W][G][2][E + 2];
-  const int sub = (threadIdx.x & 31) % LPR;
-  const int n_sets = (n_rows + W * G - 1) / (W * G);
-  // rows of set s handled by this lane's group: (s * W + warp) * G + group
-  auto row_of = [&](int s_) { return (s_ * W + (int)(threadIdx.x >> 5)) * G + (int)(threadIdx.x & 31) / LPR; };
-  auto load_row = [&](int s_, int& start, int& end) {
-    start = 0;
-    end = 0;
-    if (s_ < n_sets) {
-      const int row = row_of(s_);
-      if (row < n_rows) {
-        start = __ldg(rowptr + row);
-        end = __ldg(rowptr + row + 1);
-        if (skip_long && end - start >= kLongRowThreshold) end = start;
-      }
-    }
-  };
-  uint64_t bl;
-  {
-    bl = reinterpret_cast<uint64_t>(b) + 16u * (uint32_t)min(sub, Panel<BF16>::chunks(f) - 1);
-    asm volatile("" : "+l"(bl));
-  }
-  uint32_t cur = smem_u32(&stage[threadIdx.x >> 5][((threadIdx.x & 31) / LPR)][0][0]);
-  uint32_t nxt = cur + kBufBytes;
-  // stage <- E pairs starting at entry `from` (this lane's first one), zero-filled past `ahead` entries
-  auto fetch_at = [&](uint32_t dst_buf, int from, int ahead) {
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      const int a = ahead - 2 * LPR * k;
-      const uint32_t bytes = a >= 2 ? 16u : (a == 1 ? 8u : 0u);
-      cp_async16_zfill(dst_buf + 16u * (uint32_t)(sub + LPR * k), pair + min(max(from + 2 * LPR * k, 0), last_pair), bytes);
-    }
-    cp_async_commit();
-  };
-  auto pairs_at = [&](int j) {
-    uint4 q;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(cur + 8u * (uint32_t)j));
-    return q;
-  };
-  auto gather = [&](uint32_t c) {
-    uint4 x;
-    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
-                 : "l"(bl + (uint64_t)c * ldb_bytes));
-    return x;
-  };
-
-  int set = blockIdx.x;
-  int e, left, lead;
-  {
-    int start, end;
-    load_row(set, start, end);
-    lead = start & 1;
-    e = start - lead + 2 * sub;
-    left = (end == start) ? 0 : end - start + lead;
-  }
-  fetch_at(cur, e, left - 2 * sub);  // first stage of the first set
-  e += E;
-  int nstart, nend;
-  load_row(set + (int)gridDim.x, nstart, nend);  // the next set's row pointers fly while this set is processed
-  while (true) {
-    float4 acc[A];
-#pragma unroll
-    for (int t = 0; t < A; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    bool first = true;
-    bool prefetched = false;
-    while (!__all_sync(kFull, left <= 0)) {
-      if (!__all_sync(kFull, left - E <= 0)) {
-        fetch_at(nxt, e, left - E - 2 * sub);  // next stage of this set flies while this one is consumed
-        e += E;
-      } else {
-        // last stage of this set for every group of the warp: the free buffer takes the NEXT set's first stage
-        const int nlead = nstart & 1;
-        const int nleft = (nend == nstart) ? 0 : nend - nstart + nlead;
-        fetch_at(nxt, nstart - nlead + 2 * sub, nleft - 2 * sub);
-        prefetched = true;
-      }
-      cp_async_wait<1>();
-      __syncwarp();
-      if (first) {
-        if (lead && sub == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(cur + 4u), "r"(0u) : "memory");
-        __syncwarp();
-        first = false;
-      }
-      const int cnt = min(max(left, 0), E);
-      const int cmax = __reduce_max_sync(kFull, cnt);
-#pragma unroll 1
-      for (int j = 0; j < cmax; j += U) {
-        if (j < cnt) {
-          uint4 q[U / 2];
-          uint4 x[U];
-#pragma unroll
-          for (int h = 0; h < U / 2; ++h) q[h] = pairs_at(j + 2 * h);
-#pragma unroll
-          for (int h = 0; h < U / 2; ++h) {
-            x[2 * h] = gather(q[h].x);
-            x[2 * h + 1] = gather(q[h].z);
-          }
-          const uint32_t zero = all_landed(x, never);
-#pragma unroll
-          for (int t = 0; t < A; ++t) {
-            acc[t].x = __uint_as_float(__float_as_uint(acc[t].x) | zero);
-            acc[t].y = __uint_as_float(__float_as_uint(acc[t].y) | zero);
-            acc[t].z = __uint_as_float(__float_as_uint(acc[t].z) | zero);
-            acc[t].w = __uint_as_float(__float_as_uint(acc[t].w) | zero);
-          }
-#pragma unroll
-          for (int h = 0; h < U / 2; ++h) {
-            fma_chunk<BF16>(acc, __uint_as_float(q[h].y), x[2 * h]);
-            fma_chunk<BF16>(acc, __uint_as_float(q[h].w), x[2 * h + 1]);
-          }
-        }
-      }
-      __syncwarp();
-      left -= E;
-      const uint32_t t = cur;
-      cur = nxt;
-      nxt = t;
-    }
-    {
-      const int row = row_of(set);
-      bool store = row < n_rows && sub < Panel<BF16>::chunks(f);
-      if (store && skip_long && __ldg(rowptr + row + 1) - __ldg(rowptr + row) >= kLongRowThreshold) store = false;
-      if (store) store_panel_chunk<BF16>(out + (int64_t)row * ldo, row, sub, f, vec_out, acc, ep);
-    }
-    set += (int)gridDim.x;
-    if (set >= n_sets) break;  // (CTA-uniform)
-    lead = nstart & 1;
-    e = nstart - lead + 2 * sub;
-    left = (nend == nstart) ? 0 : nend - nstart + lead;
-    if (!prefetched) {  // the stage loop did not run (every row of the set was empty or long)
-      cp_async_wait<0>();  // the skipped set's (zero-byte) first-stage copies target the same buffer: let them land first
-      fetch_at(cur, e, left - 2 * sub);
-    }
-    e += E;
-    load_row(set + (int)gridDim.x, nstart, nend);
-  }
-  cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -874,7 +715,7 @@ int launch_vec(const CsrView& a, const void* b, int64_t ldb, int f, const Epilog
     if (grid > 0 && a.pair != nullptr && want_group && ldb * kEB < (1ll << 32)) {
 #define GCNB_GROUP_ARGS                                                                                 \
   (int)a.n_rows, a.rowptr, a.pair, (int)(a.nnz & ~1ll), b, (uint32_t)(ldb * kEB), f, ep, out, ldo, \
-      vec_out ? 1 : 0, has_long ? 1 : 0, 0u
+      vec_out ? 1 : 0, has_long ? 1 : 0, 0u, a.pair_tagged ? kPairColMask : 0xffffffffu
 #define GCNB_GROUP_LAUNCH_W(U_, MINB_, W_, SE_)                                                                      \
   spmm_group_kernel<LPR, U_, MINB_, BF16, W_, SE_><<<(int)ceil_div(a.n_rows, (int64_t)(W_) * G), (W_) * 32, 0, st>>>( \
       GCNB_GROUP_ARGS)
@@ -883,10 +724,6 @@ int launch_vec(const CsrView& a, const void* b, int64_t ldb, int f, const Epilog
   GCNB_CUDA(launch_pdl(spmm_group_kernel<LPR, U_, MINB_, BF16, W_, SE_, true>,                                    \
                        dim3((unsigned)ceil_div(a.n_rows, (int64_t)(W_) * G)), dim3((W_) * 32), 0, st, GCNB_GROUP_ARGS))
 #define GCNB_GROUP_LAUNCH(U_, MINB_) GCNB_GROUP_LAUNCH_W(U_, MINB_, kWarpsPerCta, kStageEntries)
-#define GCNB_GROUP_LAUNCH_PERSISTENT(U_, MINB_, W_, SE_)                                                       \
-  spmm_group_persistent_kernel<LPR, U_, MINB_, BF16, W_, SE_>                                                  \
-      <<<(int)std::min<int64_t>(ceil_div(a.n_rows, (int64_t)(W_) * G), (int64_t)kNumSMs * (MINB_)), (W_) * 32, 0, st>>>( \
-          GCNB_GROUP_ARGS)
       // (gathers in flight per lane, CTAs per SM the register budget must allow).  Measured on B200
       // (gpurun_out/probe_sweep8.log): 128/256-byte rows like many warps with 4 gathers each, narrower
       // rows fewer warps with 8.  GCNB_SPMM_GROUP_VARIANT overrides (tuning knob).
@@ -920,14 +757,11 @@ int launch_vec(const CsrView& a, const void* b, int64_t ldb, int f, const Epilog
         case 13: GCNB_GROUP_LAUNCH_W(4, 24, 2, 16); break;
         case 14: GCNB_GROUP_LAUNCH_W(8, 16, 2, 16); break;
         case 15: GCNB_GROUP_LAUNCH_W(8, 8, 4, 16); break;
-        case 16: GCNB_GROUP_LAUNCH_PERSISTENT(4, 24, 2, 16); break;   // persistent, next set prefetched (unmeasured)
-        case 17: GCNB_GROUP_LAUNCH_PERSISTENT(8, 16, 2, 16); break;
         default: GCNB_GROUP_LAUNCH(8, 4); break;
       }
 #undef GCNB_GROUP_LAUNCH
 #undef GCNB_GROUP_LAUNCH_W
 #undef GCNB_GROUP_LAUNCH_PDL
-#undef GCNB_GROUP_LAUNCH_PERSISTENT
 #undef GCNB_GROUP_ARGS
       GCNB_LAUNCH_CHECK();
       return launch_long<LPR, CH, BF16>(a, b, ldb, f, ep, out, ldo, partial, ldp, st);
@@ -964,11 +798,26 @@ int spmm_set_tuning(int key, int value) {
     GCNB_REQUIRE(value >= 0 && value <= 3, "set_tuning: spmm kernel must be 0..3");
     g_spmm_kernel = value;
   } else if (key == GCNB_TUNE_SPMM_GROUP_VARIANT) {
-    GCNB_REQUIRE(value >= -1 && value <= 17, "set_tuning: group variant must be -1..17");
+    GCNB_REQUIRE(value >= -1 && value <= 15, "set_tuning: group variant must be -1..15");
     g_group_variant = value;
   } else if (key == GCNB_TUNE_PDL) {
     GCNB_REQUIRE(value == 0 || value == 1, "set_tuning: PDL must be 0 or 1");
     g_pdl = value;
+  } else if (key == GCNB_TUNE_SPMM_STREAM) {
+    GCNB_REQUIRE(value >= 0 && value <= 2, "set_tuning: stream mode must be 0..2");
+    spmm_stream_set(key, value);
+  } else if (key == GCNB_TUNE_STREAM_HOT_MB) {
+    GCNB_REQUIRE(value >= 0 && value <= 126, "set_tuning: hot-row L2 budget must be 0..126 MB");
+    spmm_stream_set(key, value);
+  } else if (key == GCNB_TUNE_STREAM_HINT) {
+    GCNB_REQUIRE(value >= 0 && value <= 2, "set_tuning: stream hint mode must be 0..2");
+    spmm_stream_set(key, value);
+  } else if (key == GCNB_TUNE_STREAM_MIN_ROW_BYTES) {
+    GCNB_REQUIRE(value >= 16 && value <= 1024, "set_tuning: stream row threshold must be 16..1024 bytes");
+    spmm_stream_set(key, value);
+  } else if (key == GCNB_TUNE_STREAM_BATCH) {
+    GCNB_REQUIRE(value == 0 || value == 8 || value == 16 || value == 32, "set_tuning: stream batch must be 0, 8, 16 or 32");
+    spmm_stream_set(key, value);
   } else {
     GCNB_REQUIRE(false, "set_tuning: unknown key %d", key);
   }
@@ -976,8 +825,10 @@ int spmm_set_tuning(int key, int value) {
 }
 
 size_t spmm_workspace_bytes(const CsrView& a, int64_t f) {
-  if (a.n_long_chunks == 0) return 0;
-  return (size_t)a.n_long_chunks * (size_t)partial_ld(f) * sizeof(float);
+  // (the streaming kernel works on column panels of at most 256 floats / 512 bf16: spmm_launch_t)
+  const size_t stream = spmm_stream_mode() != 0 ? spmm_stream_workspace_bytes(a, f < 512 ? f : 512) : 0;
+  const size_t lng = a.n_long_chunks == 0 ? 0 : (size_t)a.n_long_chunks * (size_t)partial_ld(f) * sizeof(float);
+  return stream > lng ? stream : lng;
 }
 
 namespace {
@@ -1012,6 +863,21 @@ int spmm_launch_t(const CsrView& a, const void* bv, int64_t ldb, int64_t f, cons
       GCNB_LAUNCH_CHECK();
       return GCNB_OK;
     }
+  }
+  // wide panel rows on graphs whose every row is non-empty: the streaming kernel (spmm_stream.cu), at most 64
+  // 16-byte chunks per pass
+  tuning_init();
+  if (g_spmm_kernel == 0 && spmm_stream_eligible(a, 16 * (int64_t)(nch < 64 ? nch : 64), nch < 64 ? nch : 64)) {
+    const int64_t pw = 64 * kE;
+    for (int64_t f0 = 0; f0 < f; f0 += pw) {
+      const int64_t fw = (f - f0 < pw) ? (f - f0) : pw;
+      Epilogue e2 = ep;
+      if (e2.bias) e2.bias += f0;
+      if (e2.mask) e2.mask += f0;
+      GCNB_TRY(spmm_stream_launch(a, b + f0, ldb * (int64_t)sizeof(elem_t), (int)fw, BF16, e2, out + f0, ldo, vec_out,
+                                  ws, ws_bytes, st));
+    }
+    return GCNB_OK;
   }
 #define GCNB_SPMM_CASE(LPR, CH) \
   return launch_vec<LPR, CH, BF16>(a, b, ldb, (int)f, ep, out, ldo, vec_out, partial, ldp, st)

@@ -70,8 +70,13 @@ def test_tuning_knobs_validate_their_values(lib):
         _lib.TUNE_SPMM_KERNEL, _lib.TUNE_SPMM_GROUP_VARIANT, _lib.TUNE_PDL)
     try:
         for key, good, bad in ((_lib.TUNE_SPMM_KERNEL, (0, 1, 2, 3), (-1, 4)),
-                               (_lib.TUNE_SPMM_GROUP_VARIANT, tuple(range(-1, 18)), (-2, 18)),
-                               (_lib.TUNE_PDL, (0, 1), (-1, 2))):
+                               (_lib.TUNE_SPMM_GROUP_VARIANT, tuple(range(-1, 16)), (-2, 16)),
+                               (_lib.TUNE_PDL, (0, 1), (-1, 2)),
+                               (_lib.TUNE_SPMM_STREAM, (0, 1, 2), (-1, 3)),
+                               (_lib.TUNE_STREAM_HOT_MB, (0, 48, 126), (-1, 127)),
+                               (_lib.TUNE_STREAM_HINT, (0, 1, 2), (-1, 3)),
+                               (_lib.TUNE_STREAM_MIN_ROW_BYTES, (16, 256, 1024), (8, 2048)),
+                               (_lib.TUNE_STREAM_BATCH, (0, 8, 16, 32), (4, 64))):
             for v in good:
                 assert lib.gcnb_set_tuning(key, v) == 0, (key, v, _lib.last_error())
             for v in bad:
@@ -81,6 +86,11 @@ def test_tuning_knobs_validate_their_values(lib):
         lib.gcnb_set_tuning(_lib.TUNE_SPMM_KERNEL, 0)
         lib.gcnb_set_tuning(_lib.TUNE_SPMM_GROUP_VARIANT, -1)
         lib.gcnb_set_tuning(_lib.TUNE_PDL, 0)
+        lib.gcnb_set_tuning(_lib.TUNE_SPMM_STREAM, 1)
+        lib.gcnb_set_tuning(_lib.TUNE_STREAM_HOT_MB, 48)
+        lib.gcnb_set_tuning(_lib.TUNE_STREAM_HINT, 2)
+        lib.gcnb_set_tuning(_lib.TUNE_STREAM_MIN_ROW_BYTES, 256)
+        lib.gcnb_set_tuning(_lib.TUNE_STREAM_BATCH, 0)
 
 
 def test_fresh_bn_entry_points_validate_before_launching(lib):

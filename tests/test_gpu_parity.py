@@ -430,15 +430,24 @@ def spmm_kernel(P, request):
 
     lib = _lib.load()
     name, variant = request.param if isinstance(request.param, tuple) else (request.param, -1)
-    _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_KERNEL, _KERNELS[name]), "set_tuning")
-    _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_GROUP_VARIANT, variant), "set_tuning")
+    if name == "stream":  # the streaming kernel wherever the view is eligible (auto keeps it for big graphs); variant = batch
+        _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_KERNEL, 0), "set_tuning")
+        _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_STREAM, 2), "set_tuning")
+        _lib.check(lib.gcnb_set_tuning(_lib.TUNE_STREAM_BATCH, max(variant, 0)), "set_tuning")
+    else:
+        _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_STREAM, 0 if name != "auto" else 1), "set_tuning")
+        _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_KERNEL, _KERNELS[name]), "set_tuning")
+        _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_GROUP_VARIANT, variant), "set_tuning")
     yield name
     lib.gcnb_set_tuning(_lib.TUNE_SPMM_KERNEL, 0)
     lib.gcnb_set_tuning(_lib.TUNE_SPMM_GROUP_VARIANT, -1)
+    lib.gcnb_set_tuning(_lib.TUNE_SPMM_STREAM, 1)
+    lib.gcnb_set_tuning(_lib.TUNE_STREAM_BATCH, 0)
 
 
 @pytest.mark.parametrize("spmm_kernel", ["auto", "rows", "group", "tma", ("group", 0), ("group", 1), ("group", 2), ("group", 3),
-                                         ("group", 4), ("group", 7), ("group", 13), ("group", 14)], indirect=True)
+                                         ("group", 4), ("group", 7), ("group", 13), ("group", 14), "stream", ("stream", 8),
+                                         ("stream", 32)], indirect=True)
 @pytest.mark.parametrize("fin,fout", [(64, 32), (5, 1), (9, 3), (16, 7), (33, 47), (100, 256), (20, 600)])
 def test_layer_vs_oracle_widths_and_long_rows(P, fin, fout, spmm_kernel):
     n = 6000
@@ -526,7 +535,7 @@ def test_to_bf16_is_round_to_nearest_even_with_zero_padding(P, f):
 
 
 @pytest.mark.parametrize("spmm_kernel", ["auto", "rows", "group", ("group", 0), ("group", 1), ("group", 3), ("group", 13),
-                                         ("group", 14)], indirect=True)
+                                         ("group", 14), "stream", ("stream", 16)], indirect=True)
 @pytest.mark.parametrize("f", [1, 3, 7, 8, 24, 32, 47, 64, 100, 256, 600, 1100])
 def test_spmm_bf16_panel_equals_fp32_kernel_on_the_rounded_panel(P, f, spmm_kernel):
     """gcnb_spmm_bf16 gathers bf16 rows and accumulates in fp32: on a panel that is already bf16-representable
@@ -549,6 +558,80 @@ def test_spmm_bf16_panel_equals_fp32_kernel_on_the_rounded_panel(P, f, spmm_kern
         assert err(got, want.cpu().numpy()) < TOL, (f, flags)
         full = _spmm_raw(P, gr, dense, f, False, flags, b)  # the fp32 panel: the tier's bound
         assert err(got, full.cpu().numpy()) < TOL_BF16
+
+
+@pytest.mark.parametrize("spmm_kernel", ["stream", ("stream", 8), ("stream", 16), ("stream", 32)], indirect=True)
+@pytest.mark.parametrize("f", [4, 48, 100, 256, 300])
+def test_stream_spmm_item_boundaries_and_epilogues(P, f, spmm_kernel):
+    """The streaming SpMM (spmm_stream.cu) on a CSR whose rows start and end exactly on the 1024-entry item
+    boundaries, span whole items, or hold one entry; every epilogue (bias, ReLU, dropout mask, accumulate), a strided
+    output, fp32 and bf16 panels, forward and transposed -- against torch's CUDA CSR product; twice, bit-identical."""
+    import ctypes
+
+    from pygcn_b200 import _lib
+
+    lib = _lib.load()
+    rs = np.random.default_rng(f)
+    lengths = np.concatenate([[1024, 1024, 512, 512, 2048, 1, 1023, 3072, 5, 4096 + 7], rs.integers(1, 40, 3000),
+                              np.ones(700, np.int64), [9000], rs.integers(1, 6, 2000)])
+    n = len(lengths)
+    crow = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+    col = rs.integers(0, n, crow[-1])
+    val = rs.standard_normal(crow[-1]).astype(np.float32)
+    csr = torch.sparse_csr_tensor(cu(crow), cu(col), cu(val), (n, n))
+    gr = P.Graph.from_torch(csr)
+    assert gr.nnz == crow[-1]
+    dense = torch.randn(n, f, generator=torch.Generator(device=dev()).manual_seed(1), device=dev())
+    ref = torch.sparse.mm(csr, dense)
+    ref_t = torch.sparse.mm(csr.to_sparse_coo().t().coalesce().to_sparse_csr(), dense)
+    got = _spmm_raw(P, gr, dense, f, False)
+    assert err(got, ref.cpu().numpy()) < TOL
+    assert torch.equal(got, _spmm_raw(P, gr, dense, f, False))
+    assert err(_spmm_raw(P, gr, dense, f, False, _lib.SPMM_TRANSPOSE), ref_t.cpu().numpy()) < TOL
+    bias = torch.randn(f, device=dev())
+    assert err(_spmm_raw(P, gr, dense, f, False, _lib.SPMM_RELU, bias), torch.relu(ref + bias).cpu().numpy()) < TOL
+    # accumulate into a strided output: out[:, 3:3+f] of a wider buffer += A dense
+    wide = torch.randn(n, f + 9, device=dev())
+    keep = wide.clone()
+    view = wide[:, 4:4 + f]
+    ws = torch.empty(max(int(lib.gcnb_spmm_workspace_bytes(gr._h, 0, f)), 256), dtype=torch.uint8, device=dev())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.gcnb_spmm(gr._h, _lib.SPMM_ACCUMULATE, dense.data_ptr(), f, f, None, view.data_ptr(), wide.stride(0),
+                             ws.data_ptr(), ws.numel(), st), "spmm")
+    assert err(view, (keep[:, 4:4 + f] + ref).cpu().numpy()) < TOL
+    assert torch.equal(wide[:, :4], keep[:, :4]) and torch.equal(wide[:, 4 + f:], keep[:, 4 + f:])
+    # bf16 panel
+    panel = _to_bf16(P, dense)
+    want = torch.sparse.mm(csr, panel[:, :f].float())
+    assert err(_spmm_raw(P, gr, panel, f, True), want.cpu().numpy()) < TOL
+    # fused dropout mask + ReLU through the layer API (mask epilogue of the streaming kernel)
+    keepmask = torch.rand(n, f, device=dev()) > 0.3
+    w = torch.eye(f, device=dev())
+    out = P.gcn_layer(dense, gr, w, bias, relu=True, dropout_mask=keepmask, dropout_p=0.3)
+    want = torch.relu(ref + bias) * keepmask / 0.7
+    assert err(out, want.cpu().numpy()) < TOL
+
+
+def test_stream_spmm_falls_back_when_a_row_is_empty(P):
+    """A view with an empty row has no entry to carry the end-of-row tag: it takes the row kernels."""
+    from pygcn_b200 import _lib
+
+    lib = _lib.load()
+    _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_STREAM, 2), "set_tuning")
+    try:
+        n = 300
+        rs = np.random.default_rng(0)
+        lengths = rs.integers(0, 30, n)
+        lengths[7] = 0
+        crow = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+        col = rs.integers(0, n, crow[-1])
+        val = rs.standard_normal(crow[-1]).astype(np.float32)
+        csr = torch.sparse_csr_tensor(cu(crow), cu(col), cu(val), (n, n))
+        gr = P.Graph.from_torch(csr)
+        dense = torch.randn(n, 64, device=dev())
+        assert err(_spmm_raw(P, gr, dense, 64, False), torch.sparse.mm(csr, dense).cpu().numpy()) < TOL
+    finally:
+        lib.gcnb_set_tuning(_lib.TUNE_SPMM_STREAM, 1)
 
 
 def test_spmm_bf16_rejects_unaligned_panels_and_dense_route(P):
