@@ -1,10 +1,14 @@
 #!/usr/bin/env python
-"""Benchmark of the GCN-layer hot path (BASELINE.json metric: layer fwd+bwd edges/sec).
+"""Benchmark of the GCN-layer hot path (BASELINE.json metric: GCN layer fwd+bwd edges/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cbg]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload products|reddit|cbg|papers]
 
-One "step" = one GraphConvolution forward + backward (pygcn/layers.py:32-38 + autograd) over
-the whole synthetic graph.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
+Default workload = BASELINE.json configs[3], the largest single-GPU configuration: the ogbn-products-shaped R-MAT
+graph (N = 2 449 029, 62.8 M stored entries) under the named 3-layer model 100 -> 256 -> 256 -> 47, written as the
+reference writes its 3-layer GCN (`x = F.relu(self.gcK(x, adj))` three times, pygcn/models.py:102-111).
+One "step" = forward + backward of every layer of the workload's model (pygcn/layers.py:32-38 + autograd) over the
+whole graph; `value` = layers x stored entries / step time (layer fwd+bwd edges per second).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
 """
 from __future__ import annotations
 
@@ -21,22 +25,29 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# dims: the widths of the workload's stack of GraphConvolution layers; relu: every layer is followed by F.relu (the
+# reference's GeneratorGCN form); ref_shrink: the CPU arms time the same family at 1/ref_shrink of the nodes and edges
 WORKLOADS = {
-    # BASELINE.json configs[1]: ~100K nodes, ~10M edges, 64 feats; hidden 32
-    "cbg": dict(n=100_000, avg_deg=100, fin=64, fout=32,
-                name="synthetic CBG mobility-graph shape: N=100000 uniform graph, nnz~10.1M (sym+I, row-normalised), 64->32"),
-    # configs[2]: Reddit-shaped
-    "reddit": dict(n=232_965, avg_deg=492, fin=602, fout=256,
-                   name="synthetic Reddit shape: N=232965, nnz~114.6M, 602->256"),
-    # configs[3]: ogbn-products-shaped, hidden layer
-    "products": dict(n=2_449_029, avg_deg=25, n_raw=31_000_000, family="rmat", fin=100, fout=256,
-                     name="synthetic ogbn-products shape: N=2449029, R-MAT(.57,.19,.19,.05) 31M raw edges, nnz~62.8M, 100->256"),
+    # BASELINE.json configs[3]: ogbn-products-shaped, the named 3-layer model (hidden 256, 47 classes)
+    "products": dict(n=2_449_029, avg_deg=25, n_raw=31_000_000, family="rmat", dims=[100, 256, 256, 47], relu=True,
+                     ref_shrink=32,
+                     name="synthetic ogbn-products shape: N=2449029, R-MAT(.57,.19,.19,.05) 31M raw edges, nnz~62.8M "
+                          "(sym+I, row-normalised), 3-layer GCN 100->256->256->47 with ReLU (pygcn/models.py:102-111)"),
+    # configs[2]: Reddit-shaped, one layer
+    "reddit": dict(n=232_965, avg_deg=492, dims=[602, 256], relu=False, ref_shrink=16,
+                   name="synthetic Reddit shape: N=232965 uniform graph, nnz~114.7M, one layer 602->256"),
+    # configs[1]: ~100K nodes, ~10M edges, 64 feats; hidden 32
+    "cbg": dict(n=100_000, avg_deg=100, dims=[64, 32], relu=False, ref_shrink=1,
+                name="synthetic CBG mobility-graph shape: N=100000 uniform graph, nnz~10.1M (sym+I, row-normalised), one layer 64->32"),
     # configs[4]: ogbn-papers100M-shaped, multi-GPU only: 1.6 G stored entries exceed one int32 graph handle, every
     # rank builds its own row block from the replicated edge list (dist.build_partitioned); fixed total size
-    "papers": dict(n=111_059_956, n_raw=752_000_000, avg_deg=14, fin=128, fout=128, partitioned=True,
-                   name="synthetic ogbn-papers100M shape: N=111059956, 752M raw edges (~1.6G stored entries), 128->128"),
+    "papers": dict(n=111_059_956, n_raw=752_000_000, avg_deg=14, dims=[128, 128], relu=False, partitioned=True, ref_shrink=512,
+                   name="synthetic ogbn-papers100M shape: N=111059956, 752M raw edges (~1.6G stored entries), one layer 128->128"),
 }
+for _w in WORKLOADS.values():  # (tools/ read the first layer's widths)
+    _w["fin"], _w["fout"] = _w["dims"][0], _w["dims"][1]
 L2_FLUSH_BYTES = 512 << 20  # > 126 MB L2
+METRIC = "gcn_layer_fwd_bwd_edges_per_sec"
 
 
 # --------------------------------------------------------------------------- clocks
@@ -111,10 +122,10 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- helpers
-def algorithmic_bytes_spmm(nnz, n, f):
-    """int32 col + fp32 val per stored entry, rowptr, read the dense operand once,
-    write the output once (fp32)."""
-    return nnz * 8 + (n + 1) * 4 + n * f * 4 + n * f * 4
+def algorithmic_bytes_spmm(nnz, n, f, elem=4):
+    """int32 col + fp32 val per stored entry, rowptr, read the dense operand once (elem bytes per
+    element), write the output once (fp32)."""
+    return nnz * 8 + (n + 1) * 4 + n * f * elem + n * f * 4
 
 
 def rmat_edges(torch, n, n_edges, gen, device, a=0.57, b=0.19, c=0.19):
@@ -152,15 +163,41 @@ def make_graph(P, torch, wl, dev, seed=0, edges_on="cpu"):
     return g
 
 
-def ncu_traffic(wl_key):
-    """dram__bytes_read.sum + dram__bytes_write.sum per SpMM launch from the committed ncu capture
-    (profiles/, CBG workload only); None when no capture matches the workload."""
-    p = os.path.join(ROOT, "profiles", "spmm_ncu_latest.json")
-    if wl_key != "cbg" or not os.path.exists(p):
-        return None, None
-    with open(p) as f:
-        d = json.load(f)
-    return d.get("dram_bytes_per_launch"), d.get("xbar2l1_read_bytes_per_launch")
+def host_pattern_nnz(torch, src, dst, n):
+    """Stored entries of max(C, C^T) + I for an edge list, on the host (the count the device build must reproduce)."""
+    s, d = src.long(), dst.long()
+    return int(torch.unique(torch.cat([s * n + d, d * n + s, torch.arange(n, dtype=torch.int64) * (n + 1)])).numel())
+
+
+def host_adjacency(torch, src, dst, n):
+    """The reference's pipeline (pygcn/utils.py:360-368, 390-397, 407-414) on the host through the oracle:
+    (indices int64 [2, nnz], values fp32 [nnz])."""
+    from oracle import gcn_oracle as O
+
+    idx, val = O.build_normalized_adjacency(src.numpy(), dst.numpy(), n)
+    return torch.from_numpy(idx), torch.from_numpy(val)
+
+
+def init_params(torch, dims, seed=42):
+    """The parameters both arms start from: the reference's own initialisation calls in the reference's order
+    (pygcn/layers.py:23-29: kaiming_uniform_ on weight [in, out], then bias.uniform_), one layer after the other."""
+    import math
+
+    torch.manual_seed(seed)
+    params = []
+    for fin, fout in zip(dims[:-1], dims[1:]):
+        w = torch.empty(fin, fout)
+        torch.nn.init.kaiming_uniform_(w)
+        b = torch.empty(fout).uniform_(-1.0 / math.sqrt(fout), 1.0 / math.sqrt(fout))
+        params.append((w, b))
+    return params
+
+
+def config_of(wl, nnz, n):
+    """The `config` both arms print (identical by construction: same seeded edge list, same model)."""
+    return {"workload": wl["name"], "n": n, "nnz": nnz, "layers": wl["dims"], "relu_after_every_layer": bool(wl["relu"]),
+            "edges_per_step": (nnz * (len(wl["dims"]) - 1)) if nnz else None, "input_requires_grad": False,
+            "graph_seed": 0, "edge_generator": "torch CPU Generator (same edge list in both arms)"}
 
 
 def peaks():
@@ -184,74 +221,285 @@ def cpu_model():
     return None
 
 
-# --------------------------------------------------------------------------- reference arm
-def run_reference(args, wl):
-    """`--impl reference`: the reference layer's own CPU path (torch.mm + torch.spmm on the COO
-    tensor utils.py builds + bias, autograd backward), restated in oracle/ref_layer_torch.py
-    because /root/reference is not on the GPU box.  Host cores only."""
-    import torch
+def ncu_traffic(wl_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant SpMM from the committed `ncu --set
+    full` capture of this workload (profiles/spmm_ncu_latest.json, written by tools/ncu_summary.py; its `source`
+    field says which build and command it came from); None when the capture is of another workload."""
+    p = os.path.join(ROOT, "profiles", "spmm_ncu_latest.json")
+    if not os.path.exists(p):
+        return None, None, None
+    with open(p) as f:
+        d = json.load(f)
+    if d.get("workload", "cbg") != wl_key:
+        return None, None, None
+    return d.get("dram_bytes_per_launch"), d.get("xbar2l1_read_bytes_per_launch"), d.get("source")
 
-    from oracle import gcn_oracle as O
+
+# --------------------------------------------------------------------------- CPU arms (reference layer on host cores)
+def cpu_reference_run(torch, wl, steps, warmup, shrink, extras=True):
+    """The reference's own layer class (oracle/_ref/layers.py when oracle/make_ref.py put it there, else the port in
+    oracle/ref_layer_torch.py) on the host cores, on the workload's family at 1/shrink scale: adjacency = the
+    uncoalesced fp32 COO tensor utils.py:407-414 builds.  Returns a dict (seconds per step, edges/s, ...)."""
     from oracle import ref_layer_torch as R
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dims, relu = wl["dims"], wl["relu"]
+    t0 = time.perf_counter()
+    src, dst, n = make_edges(torch, wl, 0, shrink=shrink)
+    idx, val = host_adjacency(torch, src, dst, n)
+    build_s = time.perf_counter() - t0
+    nnz = int(val.shape[0])
+    adj = R.make_reference_adj(idx, val, (n, n), "coo_as_written")
+    params = init_params(torch, dims)
+    gen = torch.Generator(device="cpu")
+    x = torch.randn(n, dims[0], generator=gen.manual_seed(1))
+    g = torch.randn(n, dims[-1], generator=gen.manual_seed(2))
+    sec, kind = R.time_reference_stack(dims, params, relu, x, adj, g, steps, warmup)
+    layers = len(dims) - 1
+    res = {"sec_per_step": sec, "value": layers * nnz / sec, "kind": kind, "cores": cores, "n": n, "nnz": nnz,
+           "host_graph_build_s": build_s, "torch_threads": torch.get_num_threads(), "cpu_model": cpu_model()}
+    if extras:
+        # torch's best CPU path on the same matrix (BASELINE.md row B) and the as-written path on one thread (row C)
+        csr = R.make_reference_adj(idx, val, (n, n), "csr")
+        sec_csr, _ = R.time_reference_stack(dims, params, relu, x, csr, g, max(1, min(steps, 3)), 1)
+        res["alt_csr_edges_per_s"] = layers * nnz / sec_csr
+        try:
+            torch.set_num_threads(1)
+            sec_1t, _ = R.time_reference_stack(dims, params, relu, x, adj, g, 1, 0)
+            res["alt_1thread_edges_per_s"] = layers * nnz / sec_1t
+        finally:
+            torch.set_num_threads(cores)
+    return res
+
+
+def sample_text(wl, shrink, r, steps, warmup):
+    what = "the full workload" if shrink == 1 else (
+        "the same graph family and model at 1/%d of the nodes and raw edges (a bounded sample: the CPU path's edges/s "
+        "does not grow with the graph)" % shrink)
+    return ("%d fwd+bwd steps after %d warm-up on %s: n=%d, nnz=%d, layers %s; torch CPU %d threads; adj = uncoalesced "
+            "COO as utils.py:407-414 builds it; %s" % (steps, warmup, what, r["n"], r["nnz"], wl["dims"], r["torch_threads"],
+                                                       "the reference's own GraphConvolution class (oracle/_ref/layers.py)"
+                                                       if r["kind"] == "reference" else "port of the reference layer (oracle/ref_layer_torch.py)"))
+
+
+def run_reference(args, wl):
+    """`--impl reference`: the reference layer's own CPU path on the box's host cores, all threads, on our arm's
+    config / metric / unit; each step a bounded sample of the workload (WORKLOADS[...]["ref_shrink"])."""
+    import torch
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    import numpy as np
-
-    n, fin, fout = wl["n"], wl["fin"], wl["fout"]
-    t0 = time.perf_counter()
-    rs = np.random.default_rng(0)
-    n_raw = n * wl["avg_deg"] // 2
-    shrink = 1
-    if wl.get("partitioned"):  # the full graph does not fit a host run of minutes: same degree, 1/512 of the nodes
-        shrink = 512
-        n, n_raw = n // shrink, wl["n_raw"] // shrink
-    src = rs.integers(0, n, n_raw)
-    dst = rs.integers(0, n, n_raw)
-    idx, val = O.build_normalized_adjacency(src, dst, n)  # host pipeline (oracle restatement)
-    build_s = time.perf_counter() - t0
-    nnz = int(val.shape[0])
-    adj = R.make_reference_adj(torch.from_numpy(idx), torch.from_numpy(val), (n, n), "coo_as_written")
-    torch.manual_seed(42)
-    w = torch.empty(fin, fout)
-    torch.nn.init.kaiming_uniform_(w)
-    b = torch.empty(fout).uniform_(-1.0 / fout ** 0.5, 1.0 / fout ** 0.5)
-    x = torch.from_numpy(np.random.default_rng(1).standard_normal((n, fin), dtype=np.float32))
-    g = torch.from_numpy(np.random.default_rng(2).standard_normal((n, fout), dtype=np.float32))
-    sec = R.time_reference(x, w, b, adj, g, args.steps, args.warmup)
-    value = nnz / sec
-    # torch's best CPU path on the same matrix (BASELINE.md row B), a few steps, reported beside
-    csr = R.make_reference_adj(torch.from_numpy(idx), torch.from_numpy(val), (n, n), "csr")
-    sec_csr = R.time_reference(x, w, b, csr, g, max(2, min(args.steps, 5)), 1)
-    sample = "%d steps of the full %s workload (nnz=%d) after %d warm-up" % (args.steps, args.workload, nnz, args.warmup)
-    if shrink > 1:
-        sample = ("%d steps on a graph of the same average degree with 1/%d of the nodes (n=%d, nnz=%d; edges/s does not "
-                  "depend on the graph size on the CPU path) after %d warm-up" % (args.steps, shrink, n, nnz, args.warmup))
-    elif args.gpus > 1:  # our arm's N-GPU workload is N x this graph (weak scaling): the CPU arm times one N-th of it
-        sample = ("%d steps on a 1/%d sample of the %d-GPU workload = the per-GPU graph (nnz=%d; edges/s does not depend "
-                  "on the graph size on the CPU path) after %d warm-up" % (args.steps, args.gpus, args.gpus, nnz, args.warmup))
+    shrink = wl["ref_shrink"]
+    n_full = wl["n"]
+    if wl.get("partitioned"):
+        nnz_full = None  # 1.6 G stored entries: not countable on the host in minutes
+    else:
+        src, dst, _ = make_edges(torch, wl, 0)
+        nnz_full = host_pattern_nnz(torch, src, dst, n_full)
+        del src, dst
+    r = cpu_reference_run(torch, wl, args.steps, args.warmup, shrink)
+    sample = sample_text(wl, shrink, r, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": "gcn_layer_fwd_bwd_edges_per_sec", "value": value, "unit": "edges/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "strong" if wl.get("partitioned") else "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "nnz": nnz, "in_features": fin, "out_features": fout,
-                   "adj_form": "uncoalesced fp32 COO, int64 indices (utils.py:407-414), torch CPU",
-                   "input_requires_grad": False},
-        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample,
-                         "torch_threads": torch.get_num_threads(), "cpu_model": cpu_model(),
-                         "alt_csr_edges_per_s": nnz / sec_csr, "host_graph_build_s": build_s},
-        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "edges/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_of(wl, nnz_full, n_full),
+        "cpu_baseline": {"value": r["value"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"], "sample": sample,
+                         "torch_threads": r["torch_threads"], "cpu_model": r["cpu_model"],
+                         "alt_csr_edges_per_s": r.get("alt_csr_edges_per_s"),
+                         "alt_1thread_edges_per_s": r.get("alt_1thread_edges_per_s"),
+                         "host_graph_build_s": r["host_graph_build_s"]},
+        "e2e": {"value": r["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
 
 
-# --------------------------------------------------------------------------- our arm
+# --------------------------------------------------------------------------- our arm, one GPU
+class Timer:
+    def __init__(self, torch, lib, _lib, dev):
+        self.torch, self.lib, self._lib = torch, lib, _lib
+        self.flush_buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def flush(self):
+        t = self.torch
+        self._lib.check(self.lib.gcnb_l2_flush(ctypes.c_void_p(self.flush_buf.data_ptr()), self.flush_buf.numel(),
+                                               ctypes.c_void_p(t.cuda.current_stream().cuda_stream)), "l2_flush")
+
+    def time(self, fn, reps, warm=3):
+        """Mean ms of fn() over reps launches, L2 flushed before each, CUDA events on the current stream."""
+        t = self.torch
+        evs = []
+        for it in range(warm + reps):
+            self.flush()
+            a, b = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            if it >= warm:
+                evs.append((a, b))
+        t.cuda.synchronize()
+        ms = [a.elapsed_time(b) for a, b in evs]
+        return sum(ms) / len(ms), ms
+
+
+def build_stack(P, torch, dims, relu, params, dev, precision="auto"):
+    layers = torch.nn.ModuleList([P.GraphConvolution(a, b, fuse_relu=relu, precision=precision)
+                                  for a, b in zip(dims[:-1], dims[1:])])
+    with torch.no_grad():
+        for l, (w, b) in zip(layers, params):
+            l.weight.copy_(w)
+            l.bias.copy_(b)
+    return layers.to(dev)
+
+
+def stack_step(layers, x, graph, g):
+    for l in layers:
+        l.weight.grad = None
+        l.bias.grad = None
+    h = x
+    for l in layers:
+        h = l(h, graph)
+    h.backward(g)
+    return h
+
+
+def capture(torch, fn):
+    """fn() captured in a CUDA graph after two eager runs on a side stream; None if capture fails."""
+    try:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                fn()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg):
+            fn()
+        torch.cuda.synchronize()
+        return cg
+    except Exception as e:  # pragma: no cover
+        sys.stderr.write("CUDA graph capture failed (%r); timing eager launches\n" % (e,))
+        torch.cuda.synchronize()
+        return None
+
+
+def spmm_plan(dims):
+    """The SpMMs of one step, as (layer, width, launches, order): the association order each layer takes
+    (functional._aggregate_first: the first layer's input needs no gradient, the others' does)."""
+    plan = []
+    for i, (fin, fout) in enumerate(zip(dims[:-1], dims[1:])):
+        need_dx = i > 0
+        cost_ref, cost_agg = 2 * fout, fin * (2 if need_dx else 1)
+        if fin % 4 == 0 and cost_agg < cost_ref:
+            plan.append((i, fin, 2 if need_dx else 1, "(A X) W"))
+        else:
+            plan.append((i, fout, 2, "A (X W)"))
+    return plan
+
+
+def measure_single(torch, P, _lib, lib, wl, dev, steps, warm, timer, full=True, use_graph=True):
+    """One workload on one GPU: graph build, the model's step (CUDA-graph replay, L2 flushed), the SpMM alone at every
+    width the step uses.  Returns (result dict, objects kept for the other sections of the line)."""
+    dims, relu = wl["dims"], wl["relu"]
+    n = wl["n"]
+    t0 = time.perf_counter()
+    src, dst, _ = make_edges(torch, wl, 0)
+    edges_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    graph = P.Graph.from_edges(src.to(dev), dst.to(dev), n)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    del src, dst
+    nnz = graph.nnz
+    layers_n = len(dims) - 1
+    params = init_params(torch, dims)
+    layers = build_stack(P, torch, dims, relu, params, dev)
+    gen = torch.Generator(device="cpu")
+    x_host = torch.randn(n, dims[0], generator=gen.manual_seed(1)).pin_memory()
+    g_host = torch.randn(n, dims[-1], generator=gen.manual_seed(2)).pin_memory()
+    x, g = x_host.to(dev), g_host.to(dev)
+
+    def step_eager():
+        return stack_step(layers, x, graph, g)
+
+    for _ in range(max(warm, 3)):
+        step_eager()
+    torch.cuda.synchronize()
+    c0 = lib.gcnb_launch_count()
+    step_eager()
+    launches_per_step = int(lib.gcnb_launch_count() - c0)
+    cg = capture(torch, step_eager) if use_graph else None
+    step = cg.replay if cg is not None else step_eager
+    ms_per_step, _ = timer.time(step, steps, warm=max(warm, 3))
+    res = {"ms_per_step": ms_per_step, "value": layers_n * nnz / (ms_per_step * 1e-3), "nnz": nnz, "n": n,
+           "cuda_graph": cg is not None, "graph_build_s": build_s, "host_edge_generation_s": edges_s,
+           "launches_per_step": launches_per_step, "bins": graph.bin_rows, "long_chunks": graph.n_long_chunks,
+           "max_degree": graph.max_degree}
+
+    # ---- the SpMM alone (forward and A^T launches) at every width the step runs it at
+    peak, peak_src = peaks()
+    spmm = []
+    for (li, f, count, order) in spmm_plan(dims):
+        f4 = (f + 3) // 4 * 4
+        panel = torch.randn(n, f4, device=dev)
+        outbuf = torch.empty(n, f4, device=dev)
+        per = []
+        for tflag in ((0, _lib.SPMM_TRANSPOSE) if count > 1 else (0,)):
+            ws = torch.empty(max(lib.gcnb_spmm_workspace_bytes(graph._h, tflag, f), 256), dtype=torch.uint8, device=dev)
+
+            def one(tflag=tflag, ws=ws):
+                _lib.check(lib.gcnb_spmm(graph._h, tflag, ctypes.c_void_p(panel.data_ptr()), f4, f, None,
+                                         ctypes.c_void_p(outbuf.data_ptr()), f4, ctypes.c_void_p(ws.data_ptr()),
+                                         ws.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "spmm")
+            per.append(timer.time(one, max(3, min(steps, 10)))[0])
+        ms = sum(per) / len(per)
+        alg = algorithmic_bytes_spmm(nnz, n, f)
+        spmm.append({"layer": li + 1, "order": order, "width": f, "launches_per_step": count, "kernel_ms": ms,
+                     "algorithmic_bytes_per_launch": alg, "achieved_GBps": alg / ms / 1e6, "frac": alg / ms / 1e6 / peak,
+                     "gathered_GBps": nnz * f * 4 / ms / 1e6})
+        del panel, outbuf
+    res["spmm"] = spmm
+    res["peak"], res["peak_source"] = peak, peak_src
+    if not full:
+        del layers, x, g
+        return res, None
+    return res, dict(graph=graph, layers=layers, params=params, x=x, g=g, x_host=x_host, g_host=g_host, step_eager=step_eager)
+
+
+def torch_reference_lines(torch, graph, params, relu, x, g, adj_form, reps):
+    """The reference's own lines executed by PyTorch on this GPU (cuBLAS / cuSPARSE): returns (out, grads, ms/step)."""
+    coo = graph.to_sparse_coo()
+    adj = coo if adj_form == "coo_as_built" else coo.coalesce().to_sparse_csr()
+    ws = [(w.detach().clone().to(x.device).requires_grad_(True), b.detach().clone().to(x.device).requires_grad_(True))
+          for w, b in params]
+
+    def ref_step():
+        for w, b in ws:
+            w.grad = None
+            b.grad = None
+        h = x
+        for w, b in ws:
+            h = torch.spmm(adj, torch.mm(h, w)) + b
+            if relu:
+                h = torch.nn.functional.relu(h)
+        h.backward(g)
+        return h
+    out = ref_step()
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        out = ref_step()
+    b_.record()
+    torch.cuda.synchronize()
+    return out.detach(), [(w.grad.clone(), b.grad.clone()) for w, b in ws], a.elapsed_time(b_) / reps
+
+
 def run_ours(args, wl):
     import torch
 
@@ -259,7 +507,6 @@ def run_ours(args, wl):
     from pygcn_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         from pygcn_b200 import dist as D
@@ -274,127 +521,48 @@ def run_ours(args, wl):
     _lib.check(lib.gcnb_check_device(), "gcnb_check_device")
     sampler = ClockSampler(torch.cuda.current_device() if os.environ.get("CUDA_VISIBLE_DEVICES") is None
                            else int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
-
-    n, fin, fout = wl["n"], wl["fin"], wl["fout"]
-    t0 = time.perf_counter()
-    graph = make_graph(P, torch, wl, dev)
-    torch.cuda.synchronize()
-    build_s = time.perf_counter() - t0
-    nnz = graph.nnz
-
-    torch.manual_seed(42)
-    layer = P.GraphConvolution(fin, fout).to(dev)
-    gen = torch.Generator(device="cpu")
-    x_host = torch.randn(n, fin, generator=gen.manual_seed(1)).pin_memory()
-    g_host = torch.randn(n, fout, generator=gen.manual_seed(2)).pin_memory()
-    x = x_host.to(dev)
-    g = g_host.to(dev)
-    flush_buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
-
-    def flush():
-        _lib.check(lib.gcnb_l2_flush(ctypes.c_void_p(flush_buf.data_ptr()), flush_buf.numel(),
-                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "l2_flush")
-
-    def step_eager():
-        layer.weight.grad = None
-        layer.bias.grad = None
-        out = layer(x, graph)
-        out.backward(g)
-        return out
+    timer = Timer(torch, lib, _lib, dev)
+    dims, relu = wl["dims"], wl["relu"]
+    layers_n = len(dims) - 1
+    warm = max(args.warmup, 3)
 
     sampler.start()
-    # ---- warm-up (eager, public API)
-    for _ in range(max(args.warmup, 3)):
-        step_eager()
-    torch.cuda.synchronize()
-
-    # ---- capture the step in a CUDA graph (removes Python/launch gaps from the device time)
-    use_graph = not args.no_cuda_graph
-    cg = None
-    if use_graph:
-        try:
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                for _ in range(2):
-                    step_eager()
-            torch.cuda.current_stream().wait_stream(s)
-            layer.weight.grad = None
-            layer.bias.grad = None
-            cg = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(cg):
-                out_static = layer(x, graph)
-                out_static.backward(g)
-            torch.cuda.synchronize()
-        except Exception as e:  # pragma: no cover
-            sys.stderr.write("CUDA graph capture failed (%r); timing eager launches\n" % (e,))
-            cg = None
-            torch.cuda.synchronize()
-
-    def step():
-        if cg is not None:
-            cg.replay()
-        else:
-            step_eager()
-
-    for _ in range(max(args.warmup, 3)):
-        flush()
-        step()
-    torch.cuda.synchronize()
-
-    # ---- timed region: K steps, L2 flushed between steps, CUDA events on the launching stream
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    torch.cuda.synchronize()
-    sampler.in_region = True
+    sampler.in_region = True  # (the clock samples that count are those taken while the step is being timed)
     wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush()
-        ev[i][0].record()
-        step()
-        ev[i][1].record()
-    torch.cuda.synchronize()
+    res, keep = measure_single(torch, P, _lib, lib, wl, dev, args.steps, warm, timer, full=True,
+                               use_graph=not args.no_cuda_graph)
     wall = time.perf_counter() - wall0
     sampler.in_region = False
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = sum(step_ms)
-    ms_per_step = total_ms / args.steps
-    value = nnz / (ms_per_step * 1e-3)
+    graph, layers, params = keep["graph"], keep["layers"], keep["params"]
+    x, g, x_host, g_host = keep["x"], keep["g"], keep["x_host"], keep["g_host"]
+    n, nnz = res["n"], res["nnz"]
+    ms_per_step, value = res["ms_per_step"], res["value"]
 
-    # ---- dominant kernel (CSR SpMM, forward and transposed launch) timed alone, same inputs
-    support = torch.randn(n, fout, device=dev)
-    outbuf = torch.empty(n, fout, device=dev)
-    sp_ms = []
-    for tflag in (0, _lib.SPMM_TRANSPOSE):
-        wsb = lib.gcnb_spmm_workspace_bytes(graph._h, tflag, fout)
-        ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=dev)
-        for it in range(3 + args.steps):
-            flush()
-            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            _lib.check(lib.gcnb_spmm(graph._h, tflag, ctypes.c_void_p(support.data_ptr()), fout, fout, None,
-                                     ctypes.c_void_p(outbuf.data_ptr()), fout, ctypes.c_void_p(ws.data_ptr()),
-                                     ws.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "spmm")
-            b_.record()
-            if it >= 3:
-                sp_ms.append((a, b_))
-    torch.cuda.synchronize()
-    sp_ms = [a.elapsed_time(b_) for a, b_ in sp_ms]
-    spmm_ms = sum(sp_ms) / len(sp_ms)
-    peak, peak_src = peaks()
-    alg_bytes = algorithmic_bytes_spmm(nnz, n, fout)
-    achieved = alg_bytes / (spmm_ms * 1e-3) / 1e9
-    traffic, xbar_bytes = ncu_traffic(args.workload)
-    gemm_bytes = (n * fin + fin * fout + n * fout) * 4  # X.W reads X, W, writes S; dW reads X, dS, writes dW
-    layer_bytes = 2 * alg_bytes + 2 * gemm_bytes
+    # ---- every layer of the model alone (input gradient as inside the stack: none for the first layer)
+    per_layer = []
+    if layers_n > 1:
+        gen = torch.Generator(device=dev).manual_seed(5)
+        for i, l in enumerate(layers):
+            xi = torch.randn(n, dims[i], generator=gen, device=dev).requires_grad_(i > 0)
+            gi = torch.randn(n, dims[i + 1], generator=gen, device=dev)
 
-    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timing.
-    # Inputs are double-buffered: step i+1's H2D copies run on a copy stream while step i computes,
-    # as a training loop with a pinned-memory loader does.  Every step still copies its own X and G
-    # in, and reads its dW/db back, inside the timed region.  No L2 flush here: one step touches
-    # ~200 MB (graph 120 MB + dense operands) > 126 MB L2.
+            def one(l=l, xi=xi, gi=gi):
+                l.weight.grad = None
+                l.bias.grad = None
+                xi.grad = None
+                l(xi, graph).backward(gi)
+            cgl = capture(torch, one) if not args.no_cuda_graph else None
+            ms = timer.time(cgl.replay if cgl is not None else one, max(3, min(args.steps, 10)))[0]
+            per_layer.append({"layer": "%d->%d" % (dims[i], dims[i + 1]), "input_requires_grad": i > 0, "ms": ms,
+                              "edges_per_s": nnz / (ms * 1e-3)})
+            del xi, gi, cgl
+        torch.cuda.empty_cache()
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timing.  Inputs are
+    # double-buffered: step i+1's H2D copies run on a copy stream while step i computes, as a training loop with a
+    # pinned-memory loader does.  Every step copies its own X and G in and reads every dW / db back.
     h2d = x_host.numel() * 4 + g_host.numel() * 4
-    d2h = (fin * fout + fout) * 4
+    d2h = sum(w.numel() + b.numel() for w, b in params) * 4
     copy_stream = torch.cuda.Stream()
     bufs = [(torch.empty_like(x), torch.empty_like(g)) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
@@ -419,193 +587,149 @@ def run_ours(args, wl):
                 prefetch(i + 1)
             b = i % 2
             torch.cuda.current_stream().wait_event(ready[b])
-            layer.weight.grad = None
-            layer.bias.grad = None
-            o = layer(bufs[b][0], graph)
-            o.backward(bufs[b][1])
+            stack_step(layers, bufs[b][0], graph, bufs[b][1])
             done[b].record()
-            dw_h = layer.weight.grad.cpu()  # the step's result, read back every step (synchronises)
-            db_h = layer.bias.grad.cpu()
+            [(l.weight.grad.cpu(), l.bias.grad.cpu()) for l in layers]  # read back every step (synchronises)
         torch.cuda.synchronize()
         return time.perf_counter() - t0
 
-    e2e_loop(3)
+    e2e_loop(2)
     e2e_s = e2e_loop(args.steps)
-    e2e_value = nnz / (e2e_s / args.steps)
+    e2e_value = layers_n * nnz / (e2e_s / args.steps)
+    del bufs
 
-    # ---- the reference's own three lines executed by PyTorch on this GPU (cuBLAS / cuSPARSE), the
-    # library kernels BASELINE.md asks to beat: adjacency as the COO tensor utils.py builds, and as CSR
-    torch_cuda = {}
-    parity = None
+    # ---- parity gate + the library kernels BASELINE.md asks to beat: the reference's lines run by torch on this GPU
+    torch_cuda, parity = {}, None
     try:
-        coo = graph.to_sparse_coo()
-        wref = layer.weight.detach().clone().requires_grad_(True)
-        bref = layer.bias.detach().clone().requires_grad_(True)
-        # parity gate printed with the timing: our step vs the reference's three lines run by
-        # torch on this GPU on the same tensors, norm-wise max|a-b| / max|b|
-        o_ours = step_eager()
-        o_ref = torch.spmm(coo, torch.mm(x, wref)) + bref
-        o_ref.backward(g)
+        o_ours = keep["step_eager"]().detach().clone()
+        ours_grads = [(l.weight.grad.clone(), l.bias.grad.clone()) for l in layers]
 
         def nerr(a, b):
-            return ((a.detach() - b.detach()).abs().max() / b.detach().abs().max()).item()
-        parity = {"out": nerr(o_ours, o_ref), "dW": nerr(layer.weight.grad, wref.grad), "db": nerr(layer.bias.grad, bref.grad),
-                  "tolerance": 1e-5, "against": "torch.mm / torch.spmm (cuBLAS / cuSPARSE) + autograd on the exported COO tensor"}
-        parity["ok"] = all(parity[k] <= 1e-5 for k in ("out", "dW", "db"))
-        del o_ours, o_ref
-        for form, adj_t in (("coo_as_built", coo), ("csr", coo.coalesce().to_sparse_csr())):
-            def ref_step():
-                wref.grad = None
-                bref.grad = None
-                o_ = torch.spmm(adj_t, torch.mm(x, wref)) + bref
-                o_.backward(g)
-            for _ in range(2):
-                ref_step()
-            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = max(3, min(args.steps, 10))
-            torch.cuda.synchronize()
-            a.record()
-            for _ in range(reps):
-                ref_step()
-            b_.record()
-            torch.cuda.synchronize()
-            torch_cuda[form + "_ms_per_step"] = a.elapsed_time(b_) / reps
+            return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+        for form in ("csr", "coo_as_built"):
+            o_ref, ref_grads, ms = torch_reference_lines(torch, graph, params, relu, x, g, form, 2)
+            torch_cuda[form + "_ms_per_step"] = ms
+            if form == "coo_as_built":
+                parity = {"out": nerr(o_ours, o_ref), "tolerance": 1e-5,
+                          "against": "torch.mm / torch.spmm (cuBLAS / cuSPARSE) + F.relu + autograd on the exported COO "
+                                     "tensor, same tensors, norm-wise max|a-b| / max|b|"}
+                for i, ((dw, db), (rw, rb)) in enumerate(zip(ours_grads, ref_grads), 1):
+                    parity["dW%d" % i], parity["db%d" % i] = nerr(dw, rw), nerr(db, rb)
+                parity["ok"] = all(v <= 1e-5 for k_, v in parity.items() if k_ not in ("tolerance", "against"))
+            del o_ref, ref_grads
+            torch.cuda.empty_cache()
+        del o_ours, ours_grads
     except Exception as e:  # pragma: no cover
         torch_cuda["error"] = repr(e)
+    torch.cuda.empty_cache()
 
     # ---- the reduced-precision tier beside the headline (north_star: 2e-2 with bf16 features): the same step with
-    # bf16 SpMM panels, timed the same way (CUDA-graph replay, L2 flushed).  Reported, never the headline value.
+    # bf16 SpMM panels, timed the same way.  Reported, never the headline value.
     bf16_tier = None
     try:
-        layer16 = P.GraphConvolution(fin, fout, precision="bf16").to(dev)
-        layer16.load_state_dict(layer.state_dict())
+        layers16 = build_stack(P, torch, dims, relu, params, dev, precision="bf16")
+        o32 = keep["step_eager"]().detach().clone()
+        g32 = [(l.weight.grad.clone(), l.bias.grad.clone()) for l in layers]
+        o16 = stack_step(layers16, x, graph, g).detach()
+        e16 = {"out": ((o16 - o32).abs().max() / o32.abs().max()).item()}
+        for i, (l16, (dw, db)) in enumerate(zip(layers16, g32), 1):
+            e16["dW%d" % i] = ((l16.weight.grad - dw).abs().max() / dw.abs().max()).item()
+            e16["db%d" % i] = ((l16.bias.grad - db).abs().max() / db.abs().max()).item()
+        del o32, o16, g32
 
         def step16():
-            layer16.weight.grad = None
-            layer16.bias.grad = None
-            o_ = layer16(x, graph)
-            o_.backward(g)
-            return o_
-        o32 = step_eager()
-        o16 = step16()
-        e16 = {"out": ((o16 - o32).abs().max() / o32.abs().max()).item(),
-               "dW": ((layer16.weight.grad - layer.weight.grad).abs().max() / layer.weight.grad.abs().max()).item(),
-               "db": ((layer16.bias.grad - layer.bias.grad).abs().max() / layer.bias.grad.abs().max()).item()}
-        del o32, o16
-        s16 = torch.cuda.Stream()
-        s16.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s16):
-            for _ in range(2):
-                step16()
-        torch.cuda.current_stream().wait_stream(s16)
-        layer16.weight.grad = None
-        layer16.bias.grad = None
-        cg16 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(cg16):
-            step16()
-        ev16 = []
-        for it in range(3 + args.steps):
-            flush()
-            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            cg16.replay()
-            b_.record()
-            if it >= 3:
-                ev16.append((a, b_))
-        torch.cuda.synchronize()
-        ms16 = sum(a.elapsed_time(b_) for a, b_ in ev16) / len(ev16)
-        bf16_tier = {"ms_per_step": ms16, "value": nnz / (ms16 * 1e-3), "unit": "edges/s", "errors_vs_fp32_step": e16,
-                     "tolerance": 2e-2, "ok": all(v <= 2e-2 for v in e16.values()),
-                     "what": "GraphConvolution(precision='bf16'): the panels the two SpMMs gather are bf16 "
-                             "(gcnb_to_bf16 + gcnb_spmm_bf16), everything else fp32"}
+            return stack_step(layers16, x, graph, g)
+        cg16 = capture(torch, step16) if not args.no_cuda_graph else None
+        ms16 = timer.time(cg16.replay if cg16 is not None else step16, max(3, min(args.steps, 10)))[0]
+        bf16_tier = {"ms_per_step": ms16, "value": layers_n * nnz / (ms16 * 1e-3), "unit": "edges/s",
+                     "errors_vs_fp32_step": e16, "tolerance": 2e-2, "ok": all(v <= 2e-2 for v in e16.values()),
+                     "what": "GraphConvolution(precision='bf16'): the panels the SpMMs gather are bf16, everything else fp32"}
+        del layers16, cg16
     except Exception as e:  # pragma: no cover
         bf16_tier = {"error": repr(e)}
     sampler.stop()
+    clocks = sampler.summary()
+
+    # ---- roofline of the dominant kernel: the SpMM at the width that takes most of the step
+    dom = max(res["spmm"], key=lambda s: s["kernel_ms"] * s["launches_per_step"])
+    traffic, xbar_bytes, traffic_src = ncu_traffic(args.workload)
+    gemm_bytes = sum((n * a + a * b + n * b) * 4 for a, b in zip(dims[:-1], dims[1:]))
+    layer_bytes = sum(s["algorithmic_bytes_per_launch"] * s["launches_per_step"] for s in res["spmm"]) + 2 * gemm_bytes
+    spmm_ms_in_step = sum(s["kernel_ms"] * s["launches_per_step"] for s in res["spmm"])
+    roofline = {"bound": "hbm", "achieved": dom["achieved_GBps"], "peak": res["peak"], "unit": "GB/s", "frac": dom["frac"],
+                "traffic": traffic, "traffic_source": traffic_src,
+                "frac_of_dram_traffic": (traffic / (dom["kernel_ms"] * 1e-3) / 1e9 / res["peak"]) if traffic else None,
+                "kernel": "CSR SpMM, width %d (layer %d, %s; %d launches per step)" % (dom["width"], dom["layer"], dom["order"],
+                                                                                     dom["launches_per_step"]),
+                "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "kernel_ms": dom["kernel_ms"],
+                "peak_source": res["peak_source"], "frac_of_8TBs_nominal": dom["achieved_GBps"] / 8000.0,
+                "gathered_GBps_through_l2": dom["gathered_GBps"],
+                "l2_to_sm_GBps_from_ncu": (xbar_bytes / (dom["kernel_ms"] * 1e-3) / 1e9) if xbar_bytes else None,
+                "how": "CUDA events around gcnb_spmm alone (forward and A^T launches), L2 flushed before each launch",
+                "spmm_by_width": res["spmm"],
+                "layer_step": {"algorithmic_bytes": layer_bytes, "achieved": layer_bytes / (ms_per_step * 1e-3) / 1e9,
+                               "unit": "GB/s", "frac": layer_bytes / (ms_per_step * 1e-3) / 1e9 / res["peak"],
+                               "spmm_share_of_step": spmm_ms_in_step / ms_per_step}}
+
+    # ---- the other single-GPU BASELINE configs, briefly, under their own key (the headline stays the workload above)
+    others = {}
+    if args.workload == "products" and not args.no_extras:
+        del graph, layers, x, g, keep
+        torch.cuda.empty_cache()
+        for key in ("cbg", "reddit"):
+            try:
+                r2, _ = measure_single(torch, P, _lib, lib, WORKLOADS[key], dev, min(args.steps, 10), 3, timer, full=False,
+                                       use_graph=not args.no_cuda_graph)
+                others[key] = {"workload": WORKLOADS[key]["name"], "ms_per_step": r2["ms_per_step"], "value": r2["value"],
+                               "unit": "edges/s", "nnz": r2["nnz"], "launches_per_step": r2["launches_per_step"],
+                               "spmm": r2["spmm"]}
+            except Exception as e:  # pragma: no cover
+                others[key] = {"error": repr(e)}
+            torch.cuda.empty_cache()
 
     # ---- CPU baseline on the host cores (bounded sample), N=1 only
     cpu = None
     if not args.no_cpu_baseline:
-        cpu = cpu_baseline(torch, graph, layer, x_host, g_host, wl)
+        shrink = wl["ref_shrink"]
+        r = cpu_reference_run(torch, wl, 1, 1, shrink, extras=False)
+        k = max(2, min(5, int(12.0 / max(r["sec_per_step"], 1e-3))))
+        r = cpu_reference_run(torch, wl, k, 0, shrink)
+        cpu = {"value": r["value"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"],
+               "sample": sample_text(wl, shrink, r, k, 1), "ms_per_step": r["sec_per_step"] * 1e3,
+               "alt_csr_edges_per_s": r.get("alt_csr_edges_per_s"), "alt_1thread_edges_per_s": r.get("alt_1thread_edges_per_s"),
+               "cpu_model": r["cpu_model"]}
 
-    # pack W + X.W (TMA-fed tcgen05), SpMM | SpMM^T, dW with the fused colsum(G) + split-K reduce
-    # (profiles/r01_launches_v10_summary.txt: skinny_tn_kernel<64,1>); wide layers add nothing, masked backwards add one colsum
-    launches_per_step = 6
+    cfg = config_of(wl, nnz, n)
+    cfg.update({"l2": "flushed between timed steps (512 MiB write); one step touches > 10x the L2",
+                "cuda_graph": res["cuda_graph"], "graph_build_s": res["graph_build_s"],
+                "host_edge_generation_s": res["host_edge_generation_s"], "bins": res["bins"],
+                "long_chunks": res["long_chunks"], "max_degree": res["max_degree"],
+                "association": [s["order"] for s in res["spmm"]]})
     line = {
-        "metric": "gcn_layer_fwd_bwd_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": 1,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "nnz": nnz, "n": n, "in_features": fin, "out_features": fout,
-                   "input_requires_grad": False, "l2": "flushed between timed steps (512 MiB write)",
-                   "cuda_graph": cg is not None, "graph_build_s": build_s,
-                   "bins": graph.bin_rows, "long_chunks": graph.n_long_chunks},
-        "clocks": sampler.summary(),
+        "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": cfg,
+        "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3,
-                "how": "wall clock over K steps of layer(x_dev, graph); backward; grads.cpu(); inputs double-buffered "
-                       "from pinned host memory on a copy stream"},
+                "how": "wall clock over K steps of the model through the public API (GraphConvolution.forward / backward); "
+                       "every step's X and G copied from pinned host memory (double-buffered on a copy stream), every "
+                       "dW / db read back with .cpu()"},
+        "per_layer": per_layer,
         "torch_cuda_reference": torch_cuda,
         "parity": parity,
         "bf16_tier": bf16_tier,
-        "gpu_launches": launches_per_step * args.steps,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic,
-                     "kernel": ("spmm_group_kernel<LPR=%d,%s> (CSR SpMM, fwd and A^T launches)" % (
-                         max(1, 1 << max(0, ((fout + 3) // 4 - 1).bit_length())),
-                         "U=4,24 CTAs/SM,W=2,SE=16" if fout > 16 else ("U=8,16 CTAs/SM,W=2,SE=16" if fout > 8 else "U=8,4 CTAs/SM"))
-                         if fout <= 64 else "spmm_rows_vec_kernel<32,%d> (CSR SpMM, fwd and A^T launches)" % ((fout + 127) // 128)),
-                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": spmm_ms, "peak_source": peak_src,
-                     "frac_of_8TBs_nominal": achieved / 8000.0,
-                     "l2_to_sm_gather_GBps": (xbar_bytes / (spmm_ms * 1e-3) / 1e9) if xbar_bytes else None,
-                     "note": "the gathered feature rows (nnz*F*4 B per launch) are L2 hits but L1 misses: the kernel is "
-                             "bound by the L1/TEX pipe and the L2 gather rate for random 128-byte rows (DESIGN.md "
-                             "section 3; tools/microbench/gather_bw.cu measures 16.5 TB/s for the bare gather), "
-                             "DRAM traffic = algorithmic bytes",
-                     "how": "CUDA events around gcnb_spmm alone, L2 flushed before each launch, mean of %d launches" % len(sp_ms),
-                     # the whole step against the same peak (2 B_spmm + 2 B_gemm; the epilogues and db add 0)
-                     "layer_step": {"algorithmic_bytes": layer_bytes, "achieved": layer_bytes / (ms_per_step * 1e-3) / 1e9,
-                                    "unit": "GB/s", "frac": layer_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
-                                    "spmm_share_of_step": 2 * spmm_ms / ms_per_step}},
-        "wall_s_timed_region": wall,
+        "gpu_launches": res["launches_per_step"] * args.steps,
+        "gpu_launches_per_step": res["launches_per_step"],
+        "roofline": roofline,
+        "other_configs": others,
+        "wall_s_measure_section": wall,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))
     return 0
-
-
-def cpu_baseline(torch, graph, layer, x_host, g_host, wl):
-    """The reference layer's CPU path (oracle/ref_layer_torch.py) on this box's host cores."""
-    from oracle import ref_layer_torch as R
-
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    coo = graph.to_sparse_coo()
-    idx = coo._indices().cpu()
-    val = coo._values().cpu()
-    n = graph.n_rows
-    adj = R.make_reference_adj(idx, val, (n, n), "coo_as_written")
-    w = layer.weight.detach().cpu()
-    b = layer.bias.detach().cpu()
-    x = x_host.clone()
-    g = g_host.clone()
-    # bounded sample: aim at ~15 s of CPU work
-    t1 = R.time_reference(x, w, b, adj, g, 1, 1)
-    steps = max(2, min(10, int(15.0 / max(t1, 1e-3))))
-    sec = R.time_reference(x, w, b, adj, g, steps, 0)
-    csr = R.make_reference_adj(idx, val, (n, n), "csr")
-    sec_csr = R.time_reference(x, w, b, csr, g, 3, 1)
-    # SURVEY.md 8d: the same as-written path on one thread (its per-entry COO loop barely scales with threads)
-    sec_1t = None
-    try:
-        torch.set_num_threads(1)
-        sec_1t = R.time_reference(x, w, b, adj, g, 1, 1)
-    finally:
-        torch.set_num_threads(cores)
-    return {"value": graph.nnz / sec, "unit": "edges/s", "cores": cores, "kind": "port",
-            "alt_1thread_edges_per_s": (graph.nnz / sec_1t) if sec_1t else None,
-            "sample": "%d fwd+bwd steps of the full workload (nnz=%d) after 2 warm-up, torch CPU %d threads, "
-                      "adj = uncoalesced COO as utils.py:407-414 builds it" % (steps, graph.nnz, torch.get_num_threads()),
-            "ms_per_step": sec * 1e3, "alt_csr_edges_per_s": graph.nnz / sec_csr, "cpu_model": cpu_model()}
 
 
 def main():
@@ -614,9 +738,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cbg", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="products", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the brief runs of the other single-GPU configs")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -42,6 +42,9 @@ typedef struct gcnb_graph gcnb_graph; /* opaque: CSR + CSR^T + row-length-binned
 
 int gcnb_version(void);
 const char* gcnb_last_error(void);
+/* Number of kernels this library has launched in the process so far (every launch site counts itself): the
+ * difference across one captured step is the step's launch count (bench.py "gpu_launches"). */
+long long gcnb_launch_count(void);
 /* 0 when the current device is compute capability 10.x (the only target of this build). */
 int gcnb_check_device(void);
 
@@ -200,6 +203,13 @@ size_t gcnb_colsum_workspace_bytes(int64_t n_rows, int64_t f);
 #define GCNB_LAYER_NEED_DX 2  /* compute dX (ctx.needs_input_grad[0])   */
 #define GCNB_LAYER_NEED_DW 4
 #define GCNB_LAYER_NEED_DB 8
+/* Association order.  The reference computes A (X W) (pygcn/layers.py:33-34).  With this flag the layer computes
+ * (A X) W + bias instead -- the same function and gradients to fp32 rounding (tests: <= 1e-5), chosen by the host
+ * when in_features < out_features: the SpMM then gathers rows of X (fin wide) instead of rows of X W (fout wide), and
+ * backward needs no SpMM for dW = (A X)^T G  (dX = A^T (G W^T), width fin, only when the input requires grad).
+ * forward : d_support receives A X [n_rows, ld4(fin)] (keep it for backward); d_x must have 16-byte aligned rows.
+ * backward: pass that A X as d_x (ldx = ld4(fin)); d_ds is scratch [n_rows, ld4(fin)] for G W^T (dX only). */
+#define GCNB_LAYER_AGG_FIRST 16
 
 /* forward of pygcn/layers.py:32-38:  support = X W ; out = A support (+ bias) (relu) (dropout)
  *   d_x [n_cols, fin] ld ldx ; d_w [fin, fout] contiguous ; d_bias [fout] or NULL
@@ -290,13 +300,13 @@ int gcnb_peer_ack(uint32_t* peer_ack, const uint32_t* d_epoch, void* stream);
 /*   GCNB_TUNE_PDL: 0 (default) plain stream order; 1 = the layer's kernels are launched with programmatic
  *   stream serialization (each starts while its predecessor drains and waits on-device before touching its output) */
 #define GCNB_TUNE_PDL 3
-/*   The streaming SpMM (spmm_stream.cu: entry-balanced items, one TMA copy per gathered panel row, L2 eviction hints):
+/*   The streaming SpMM (spmm_stream.cu: entry-balanced items, one warp per 1024 stored entries, L2 eviction hints):
  *   GCNB_TUNE_SPMM_STREAM: 0 off, 1 auto (default: panel rows of >= MIN_ROW_BYTES on graphs without empty rows),
  *                          2 wherever the view is eligible;
  *   GCNB_TUNE_STREAM_HOT_MB: L2 budget (MB, default 48) for the rows of the most referenced columns (evict_last);
- *   GCNB_TUNE_STREAM_HINT: 0 no eviction hints, 1 hot rows evict_last, 2 (default) + the other rows evict_first;
- *   GCNB_TUNE_STREAM_MIN_ROW_BYTES: auto threshold (default 256);  GCNB_TUNE_STREAM_BATCH: 0 auto, 8 / 16 / 32 rows
- *   per TMA batch.  Environment: GCNB_SPMM_STREAM, GCNB_L2_HOT_MB, GCNB_STREAM_HINT, GCNB_STREAM_MIN_ROW_BYTES,
+ *   GCNB_TUNE_STREAM_HINT: 0 (default) no eviction hints, 1 hot rows evict_last, 2 + the other rows evict_first;
+ *   GCNB_TUNE_STREAM_MIN_ROW_BYTES: auto threshold (default 256);  GCNB_TUNE_STREAM_BATCH: 0 auto, 2 / 4 / 8 gathered rows
+ *   in flight per lane.  Environment: GCNB_SPMM_STREAM, GCNB_L2_HOT_MB, GCNB_STREAM_HINT, GCNB_STREAM_MIN_ROW_BYTES,
  *   GCNB_STREAM_BATCH. */
 #define GCNB_TUNE_SPMM_STREAM 4
 #define GCNB_TUNE_STREAM_HOT_MB 5

@@ -25,7 +25,7 @@ BIN_EDGES = (0, 1, 9, 33, 1025)
 BUILD_SYMMETRIZE, BUILD_SELF_LOOPS, BUILD_ROW_NORMALIZE = 1, 2, 4
 SPMM_TRANSPOSE, SPMM_RELU, SPMM_ACCUMULATE = 1, 2, 4
 GEMM_FP32, GEMM_TF32X3, GEMM_AUTO = 0, 1, 2
-LAYER_RELU, LAYER_NEED_DX, LAYER_NEED_DW, LAYER_NEED_DB = 1, 2, 4, 8
+LAYER_RELU, LAYER_NEED_DX, LAYER_NEED_DW, LAYER_NEED_DB, LAYER_AGG_FIRST = 1, 2, 4, 8, 16
 TUNE_SPMM_KERNEL, TUNE_SPMM_GROUP_VARIANT, TUNE_PDL = 1, 2, 3
 TUNE_SPMM_STREAM, TUNE_STREAM_HOT_MB, TUNE_STREAM_HINT, TUNE_STREAM_MIN_ROW_BYTES, TUNE_STREAM_BATCH = 4, 5, 6, 7, 8
 
@@ -93,6 +93,7 @@ SIGNATURES = {
     "gcnb_graph_block_sources": (c_int, [c_vp, c_int, c_i64, c_i64, c_int, ctypes.POINTER(c_i64), c_i64, ctypes.c_uint64,
                                          c_vp, ctypes.POINTER(c_vp)]),
     "gcnb_peer_ack": (c_int, [c_vp, c_vp, c_vp]),
+    "gcnb_launch_count": (ctypes.c_longlong, []),
 }
 
 _lock = threading.Lock()

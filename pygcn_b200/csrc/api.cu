@@ -8,6 +8,9 @@ namespace gcnb {
 
 static thread_local char g_error[1024] = "";
 
+static long long g_launch_count = 0;
+void count_launch() { __atomic_add_fetch(&g_launch_count, 1, __ATOMIC_RELAXED); }
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -59,9 +62,13 @@ size_t gemm_pad_bytes(int64_t m, int64_t n, int64_t k, int precision) {
   return r ? align256(r) : 0;
 }
 
+// fuse: optional (bias, ReLU) the TMA-fed tensor-core rows kernel applies in its epilogue; *fused says whether it did
 int gemm_dispatch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs, int64_t a_cs,
                   const float* b, int64_t b_rs, int64_t b_cs, float* c, int64_t ldc, int precision,
-                  void* ws, size_t ws_bytes, cudaStream_t st) {
+                  void* ws, size_t ws_bytes, cudaStream_t st, const Epilogue* fuse = nullptr, bool* fused = nullptr) {
+  const float* fb = fuse ? fuse->bias : nullptr;
+  const int fr = fuse ? fuse->relu : 0;
+  if (fused) *fused = false;
   GCNB_REQUIRE(precision == GCNB_GEMM_FP32 || precision == GCNB_GEMM_TF32X3 || precision == GCNB_GEMM_AUTO,
                "gemm: unknown precision %d", precision);
   GCNB_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm: negative dimension");
@@ -80,7 +87,7 @@ int gemm_dispatch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs,
   }
   switch (gemm_route(m, n, k, a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, precision)) {
     case 1:
-      return gemm_tc_rows_launch(m, n, k, a, a_rs, b, b_rs, b_cs, c, ldc, ws, ws_bytes, st);
+      return gemm_tc_rows_launch(m, n, k, a, a_rs, b, b_rs, b_cs, c, ldc, ws, ws_bytes, st, fb, fr, fused);
     case 2:
       return gemm_tc_tn_launch(m, n, k, a, a_cs, b, b_rs, c, ldc, ws, ws_bytes, st);
     default:
@@ -96,7 +103,7 @@ int gemm_dispatch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs,
       const int64_t k4 = pad4(k);
       GCNB_TRY(pad_copy_launch(m, k, a, a_rs, pad, k4, st));
       if (gemm_tc_rows_eligible(m, n, k4, pad, k4, 1, c, ldc) && rest_bytes >= gemm_tc_rows_workspace_bytes(m, n, k))
-        return gemm_tc_rows_launch(m, n, k, pad, k4, b, b_rs, b_cs, c, ldc, rest, rest_bytes, st);
+        return gemm_tc_rows_launch(m, n, k, pad, k4, b, b_rs, b_cs, c, ldc, rest, rest_bytes, st, fb, fr, fused);
     } else {
       const int64_t m4 = pad4(m);
       GCNB_TRY(pad_copy_launch(k, m, a, a_cs, pad, m4, st));  // X [k rows, m cols], row stride a_cs
@@ -106,6 +113,21 @@ int gemm_dispatch(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs,
     }
   }
   return gemm_fp32_launch(m, n, k, a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, ws, ws_bytes, st);
+}
+
+// C = dropout(relu(A B + bias)): the epilogue rides in the GEMM when the kernel that runs can take it, and is one
+// in-place pass over C otherwise (small / unaligned shapes); a dropout mask is always that pass
+int gemm_dispatch_ep(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs, int64_t a_cs, const float* b,
+                     int64_t b_rs, int64_t b_cs, float* c, int64_t ldc, int precision, void* ws, size_t ws_bytes,
+                     cudaStream_t st, const Epilogue& ep) {
+  bool fused = false;
+  GCNB_TRY(gemm_dispatch(m, n, k, a, a_rs, a_cs, b, b_rs, b_cs, c, ldc, precision, ws, ws_bytes, st, &ep, &fused));
+  Epilogue rest = ep;
+  if (fused) {
+    rest.bias = nullptr;
+    rest.relu = 0;
+  }
+  return bias_act_launch(m, n, c, ldc, rest, st);
 }
 
 // conservative: large enough for whichever kernel the route picks at call time
@@ -187,6 +209,8 @@ extern "C" int gcnb_version(void) { return GCNB_VERSION; }
 
 extern "C" const char* gcnb_last_error(void) { return g_error; }
 
+extern "C" long long gcnb_launch_count(void) { return __atomic_load_n(&g_launch_count, __ATOMIC_RELAXED); }
+
 extern "C" int gcnb_check_device(void) {
   int dev = 0;
   GCNB_CUDA(cudaGetDevice(&dev));
@@ -261,15 +285,24 @@ extern "C" size_t gcnb_colsum_workspace_bytes(int64_t n_rows, int64_t f) {
 
 extern "C" size_t gcnb_layer_workspace_bytes(const gcnb_graph* g, int64_t fin, int64_t fout, int precision) {
   if (!g) return 0;
-  size_t a = graph_matmul_ws(g, false, fout);
-  size_t b = graph_matmul_ws(g, true, fout);
-  size_t s = a > b ? a : b;
+  size_t s = 0;
+  for (int64_t w : {fout, fin})  // (the aggregate-first order runs its SpMMs at width fin)
+    for (bool t : {false, true}) {
+      const size_t v = graph_matmul_ws(g, t, w);
+      if (v > s) s = v;
+    }
   size_t c = colsum_workspace_bytes(g->n_rows, fout);
   size_t d0 = gemm_ws(g->n_cols, fout, fin, precision);  // X W
   size_t d1 = gemm_ws(fin, fout, g->n_cols, precision);  // X^T dS
   size_t d2 = gemm_ws(g->n_cols, fin, fout, precision);  // dS W^T
+  size_t d3 = gemm_ws(g->n_rows, fout, fin, precision);  // (A X) W and, transposed roles, G W^T
+  size_t d4 = gemm_ws(g->n_rows, fin, fout, precision);
+  size_t d5 = gemm_ws(fin, fout, g->n_rows, precision);  // (A X)^T G
   size_t d = d0 > d1 ? d0 : d1;
   d = d > d2 ? d : d2;
+  d = d > d3 ? d : d3;
+  d = d > d4 ? d : d4;
+  d = d > d5 ? d : d5;
   // regions are used by different kernels of one call that run back to back on one stream,
   // but colsum / spmm / gemm scratch never overlap in time with themselves only -- keep them
   // disjoint to stay safe under future multi-stream use.
@@ -285,6 +318,19 @@ extern "C" int gcnb_layer_forward(const gcnb_graph* g, const float* d_x, int64_t
   GCNB_REQUIRE(ldx >= fin, "layer_forward: ldx < in_features");
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = reinterpret_cast<char*>(d_ws);
+  if (flags & GCNB_LAYER_AGG_FIRST) {
+    // out = (A X) W + bias: the SpMM gathers rows of X (width fin) instead of rows of X W (width fout) -- the order
+    // that moves fewer bytes when fin < fout.  d_support receives A X [n_rows, 4*ceil(fin/4)], kept for backward.
+    GCNB_REQUIRE(!g->dense_fwd, "layer_forward: the aggregate-first order is for CSR handles");
+    const size_t s_bytes = align256(graph_matmul_ws(g, false, fin));
+    const size_t d_bytes = gemm_ws(g->n_rows, fout, fin, precision);
+    GCNB_REQUIRE(ws_bytes >= s_bytes + d_bytes && (s_bytes + d_bytes == 0 || ws != nullptr),
+                 "layer_forward: workspace too small");
+    const int64_t ldax = ceil_div(fin, 4) * 4;
+    GCNB_TRY(graph_matmul(g, false, d_x, ldx, fin, Epilogue(), d_support, ldax, ws, s_bytes, st));
+    return gemm_dispatch_ep(g->n_rows, fout, fin, d_support, ldax, 1, d_w, fout, 1, d_out, fout, precision, ws + s_bytes,
+                            d_bytes, st, make_epilogue(d_bias, (flags & GCNB_LAYER_RELU) != 0, false, d_mask, fout, mask_scale));
+  }
   const size_t s_bytes = align256(graph_matmul_ws(g, false, fout));
   const size_t d_bytes = gemm_ws(g->n_cols, fout, fin, precision);
   GCNB_REQUIRE(ws_bytes >= s_bytes + d_bytes && (s_bytes + d_bytes == 0 || ws != nullptr),
@@ -319,9 +365,11 @@ extern "C" int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_
   GCNB_REQUIRE(ws_bytes >= gcnb_layer_workspace_bytes(g, fin, fout, precision) && d_ws != nullptr,
                "layer_backward: workspace too small");
   char* ws = reinterpret_cast<char*>(d_ws);
-  const size_t s_bytes = align256(graph_matmul_ws(g, true, fout) > graph_matmul_ws(g, false, fout)
-                                      ? graph_matmul_ws(g, true, fout)
-                                      : graph_matmul_ws(g, false, fout));
+  const bool agg_first = (flags & GCNB_LAYER_AGG_FIRST) != 0;
+  const int64_t sw = agg_first ? fin : fout;  // width of this order's SpMMs
+  const size_t s_bytes = align256(graph_matmul_ws(g, true, sw) > graph_matmul_ws(g, false, sw)
+                                      ? graph_matmul_ws(g, true, sw)
+                                      : graph_matmul_ws(g, false, sw));
   const size_t c_bytes = align256(colsum_workspace_bytes(g->n_rows, fout));
   void* ws_spmm = ws;
   void* ws_col = ws + s_bytes;
@@ -335,7 +383,7 @@ extern "C" int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_
   // Without a mask, db = colsum(G) rides in the narrow dW kernel (third operand, gemm_skinny.cu): G and dS have the
   // same number of rows when the adjacency is square, so the pass over (X, dS) adds G's column sums for free.
   const int64_t lds_ = ceil_div(fout, 4) * 4;
-  const bool fuse_db = !masked && need_db && need_dw && precision != GCNB_GEMM_TF32X3 && g->n_rows == g->n_cols &&
+  const bool fuse_db = !agg_first && !masked && need_db && need_dw && precision != GCNB_GEMM_TF32X3 && g->n_rows == g->n_cols &&
                        d_db != nullptr && ldg % 4 == 0 && (reinterpret_cast<uintptr_t>(d_g) & 15u) == 0 &&
                        gemm_skinny_tn_eligible(fin, fout, g->n_cols, d_x, ldx, d_ds, lds_) &&
                        g_bytes >= gemm_skinny_tn_workspace_bytes(fin, fout, g->n_cols);
@@ -353,6 +401,22 @@ extern "C" int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_
     }
   }
   if (!need_dw && !need_dx) return GCNB_OK;
+  if (agg_first) {
+    // forward was out = (A X) W + b with d_x = A X [n_rows, 4*ceil(fin/4)] kept from it:
+    //   dW = (A X)^T G   -- no SpMM at all;   dX = A^T (G W^T)  -- one SpMM of width fin, only when asked for
+    const int64_t ldax = ceil_div(fin, 4) * 4;
+    GCNB_REQUIRE(ldx >= fin, "layer_backward: ld of the saved A X < in_features");
+    if (need_dw) {
+      GCNB_REQUIRE(d_dw != nullptr, "layer_backward: dW requested but null");
+      GCNB_TRY(gemm_dispatch(fin, fout, g->n_rows, d_x, 1, ldx, gsrc, gld, 1, d_dw, fout, precision, ws_gemm, g_bytes, st));
+    }
+    if (need_dx) {
+      GCNB_REQUIRE(d_dx != nullptr && lddx >= fin && d_ds != nullptr, "layer_backward: dX requested but null / lddx < in_features");
+      GCNB_TRY(gemm_dispatch(g->n_rows, fin, fout, gsrc, gld, 1, d_w, 1, fout, d_ds, ldax, precision, ws_gemm, g_bytes, st));
+      GCNB_TRY(graph_matmul(g, true, d_ds, ldax, fin, Epilogue(), d_dx, lddx, ws_spmm, s_bytes, st));
+    }
+    return GCNB_OK;
+  }
   // dS = A^T G                                      (MmBackward0 of torch.spmm)
   const int64_t lds = ceil_div(fout, 4) * 4;
   GCNB_TRY(graph_matmul(g, true, gsrc, gld, fout, Epilogue(), d_ds, lds, ws_spmm, s_bytes, st));

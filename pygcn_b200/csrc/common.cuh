@@ -34,7 +34,14 @@ void set_error(const char* fmt, ...);
     if (_s != GCNB_OK) return _s;   \
   } while (0)
 
-#define GCNB_LAUNCH_CHECK() GCNB_CUDA(cudaGetLastError())
+// every kernel launch of the library passes through here (or launch_pdl): gcnb_launch_count() reports the total, which
+// is how bench.py counts the launches of one step instead of claiming a number
+void count_launch();
+#define GCNB_LAUNCH_CHECK()          \
+  do {                               \
+    ::gcnb::count_launch();          \
+    GCNB_CUDA(cudaGetLastError());   \
+  } while (0)
 
 constexpr int kNumSMs = 148;  // B200
 
@@ -59,6 +66,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  count_launch();
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -129,7 +137,7 @@ size_t spmm_workspace_bytes(const CsrView& a, int64_t f);
 int spmm_set_tuning(int key, int value);
 
 // streaming SpMM (spmm_stream.cu): TMA row gathers over the entry-balanced items of the view
-bool spmm_stream_eligible(const CsrView& a, int64_t row_bytes, int nch);
+bool spmm_stream_eligible(const CsrView& a, int64_t row_bytes, int nch, bool bf16);
 size_t spmm_stream_workspace_bytes(const CsrView& a, int64_t f);
 int spmm_stream_launch(const CsrView& a, const void* b, int64_t ldb_bytes, int f, bool bf16, const Epilogue& ep,
                        float* out, int64_t ldo, bool vec_out, void* ws, size_t ws_bytes, cudaStream_t stream);
@@ -145,9 +153,11 @@ size_t gemm_fp32_workspace_bytes(int64_t m, int64_t n, int64_t k);
 bool gemm_tc_rows_eligible(int64_t m, int64_t n, int64_t k, const float* a, int64_t a_rs, int64_t a_cs,
                            const float* c, int64_t ldc);
 size_t gemm_tc_rows_workspace_bytes(int64_t m, int64_t n, int64_t k);
+// ep_bias / ep_relu: C = act(A B + bias) when the kernel that runs can fuse it (*ep_done = true); otherwise the
+// caller applies bias_act_launch afterwards
 int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b,
                         int64_t b_rs, int64_t b_cs, float* c, int64_t ldc, void* ws, size_t ws_bytes,
-                        cudaStream_t stream);
+                        cudaStream_t stream, const float* ep_bias = nullptr, int ep_relu = 0, bool* ep_done = nullptr);
 bool gemm_tc_rows_beats_skinny(int64_t k);
 bool gemm_tc_tn_eligible(int64_t m, int64_t n, int64_t r, const float* x, int64_t ldx, const float* y,
                          int64_t ldy, bool padded = false);

@@ -588,7 +588,8 @@ template <bool PDL>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 gemm_tc_rows_tma_kernel(const __grid_constant__ TmaDesc tmap_a, int64_t M, int N, int K,
                         const float* __restrict__ img_hi, const float* __restrict__ img_lo, float* __restrict__ c,
-                        int64_t ldc, int npad, int nkb, int tmem_cols, int vec_ok, int ns, int b_resident, int hi_rna) {
+                        int64_t ldc, int npad, int nkb, int tmem_cols, int vec_ok, int ns, int b_resident, int hi_rna,
+                        const float* __restrict__ ep_bias, int ep_relu) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -733,6 +734,8 @@ gemm_tc_rows_tma_kernel(const __grid_constant__ TmaDesc tmap_a, int64_t M, int N
         mbar_wait(bar_acc_full(ab), (chunk_ctr >> 1) & 1);
         tc_fence_after();
         const bool add = ch > 0;
+        // fused epilogue of the layer's aggregate-first order (out = (A X) W + bias, ReLU): applied with the last K chunk
+        const bool fin_ep = (ch == chunks_per_tile - 1) && (ep_bias != nullptr || ep_relu != 0);
         for (int cb = 0; cb < n_cols; cb += 32) {
           uint32_t r[32];
           __syncwarp();
@@ -743,6 +746,12 @@ gemm_tc_rows_tma_kernel(const __grid_constant__ TmaDesc tmap_a, int64_t M, int N
           __syncwarp();
           const int q = lane & 7;
           const int col = cb + 4 * q;  // column inside this N tile
+          float bv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (fin_ep && ep_bias != nullptr) {
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2)
+              if (col + t2 < n_cols) bv[t2] = __ldg(ep_bias + n0 + col + t2);
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = 4 * i + (lane >> 3);
@@ -755,12 +764,23 @@ gemm_tc_rows_tma_kernel(const __grid_constant__ TmaDesc tmap_a, int64_t M, int N
                   const float4 p = *reinterpret_cast<const float4*>(dst);
                   v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
                 }
+                if (fin_ep) {
+                  v.x += bv[0]; v.y += bv[1]; v.z += bv[2]; v.w += bv[3];
+                  if (ep_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                }
                 *reinterpret_cast<float4*>(dst) = v;
               } else {
                 const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int t2 = 0; t2 < 4; ++t2)
-                  if (col + t2 < n_cols) dst[t2] = add ? dst[t2] + e[t2] : e[t2];
+                  if (col + t2 < n_cols) {
+                    float o = add ? dst[t2] + e[t2] : e[t2];
+                    if (fin_ep) {
+                      o += bv[t2];
+                      if (ep_relu) o = fmaxf(o, 0.f);
+                    }
+                    dst[t2] = o;
+                  }
               }
             }
           }
@@ -1358,9 +1378,11 @@ size_t gemm_tc_rows_workspace_bytes(int64_t m, int64_t n, int64_t k) {
 }
 
 int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t lda, const float* b, int64_t b_rs,
-                        int64_t b_cs, float* c, int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t st) {
+                        int64_t b_cs, float* c, int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t st,
+                        const float* ep_bias, int ep_relu, bool* ep_done) {
   GCNB_REQUIRE(ws != nullptr && ws_bytes >= gemm_tc_rows_workspace_bytes(m, n, k) && aligned16(ws),
                "gemm(tc rows): workspace too small or unaligned");
+  if (ep_done) *ep_done = false;  // only the TMA-fed kernel applies (bias, ReLU) itself; the caller finishes otherwise
   if (rows_kernel_choice() == 2) {
     const TmaPlan t = tma_plan(n, k);
     TmaDesc tmap;
@@ -1380,7 +1402,8 @@ int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t
         GCNB_TRY(allow_big_smem(reinterpret_cast<const void*>(gemm_tc_rows_tma_kernel<true>), 2));
         GCNB_CUDA(launch_pdl(gemm_tc_rows_tma_kernel<true>, dim3((unsigned)gx, (unsigned)t.n_tiles), dim3(kTmaThreads),
                              t.smem, st, tmap, m, (int)n, (int)k, (const float*)hi, (const float*)lo, c, ldc, t.npad, t.nkb,
-                             (int)tmem_cols_for(2 * t.npad), vec, t.ns, t.b_resident, (int)tma_hi_rna()));
+                             (int)tmem_cols_for(2 * t.npad), vec, t.ns, t.b_resident, (int)tma_hi_rna(), ep_bias, ep_relu));
+        if (ep_done) *ep_done = true;
         return GCNB_OK;
       }
       pack_b_kernel<false><<<pg, 256, 0, st>>>(k, n, t.npad, t.n_tiles, t.nkb, b, b_rs, b_cs, hi, lo);
@@ -1388,8 +1411,9 @@ int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t
       GCNB_TRY(allow_big_smem(reinterpret_cast<const void*>(gemm_tc_rows_tma_kernel<false>), 0));
       gemm_tc_rows_tma_kernel<false><<<dim3((unsigned)gx, (unsigned)t.n_tiles), kTmaThreads, t.smem, st>>>(
           tmap, m, (int)n, (int)k, hi, lo, c, ldc, t.npad, t.nkb, tmem_cols_for(2 * t.npad), vec, t.ns, t.b_resident,
-          tma_hi_rna());
+          tma_hi_rna(), ep_bias, ep_relu);
       GCNB_LAUNCH_CHECK();
+      if (ep_done) *ep_done = true;
       return GCNB_OK;
     }
   }

@@ -816,7 +816,7 @@ int spmm_set_tuning(int key, int value) {
     GCNB_REQUIRE(value >= 16 && value <= 1024, "set_tuning: stream row threshold must be 16..1024 bytes");
     spmm_stream_set(key, value);
   } else if (key == GCNB_TUNE_STREAM_BATCH) {
-    GCNB_REQUIRE(value == 0 || value == 8 || value == 16 || value == 32, "set_tuning: stream batch must be 0, 8, 16 or 32");
+    GCNB_REQUIRE(value == 0 || value == 2 || value == 4 || value == 8, "set_tuning: stream rows in flight must be 0, 2, 4 or 8");
     spmm_stream_set(key, value);
   } else {
     GCNB_REQUIRE(false, "set_tuning: unknown key %d", key);
@@ -867,7 +867,7 @@ int spmm_launch_t(const CsrView& a, const void* bv, int64_t ldb, int64_t f, cons
   // wide panel rows on graphs whose every row is non-empty: the streaming kernel (spmm_stream.cu), at most 64
   // 16-byte chunks per pass
   tuning_init();
-  if (g_spmm_kernel == 0 && spmm_stream_eligible(a, 16 * (int64_t)(nch < 64 ? nch : 64), nch < 64 ? nch : 64)) {
+  if (g_spmm_kernel == 0 && spmm_stream_eligible(a, 16 * (int64_t)(nch < 64 ? nch : 64), nch < 64 ? nch : 64, BF16)) {
     const int64_t pw = 64 * kE;
     for (int64_t f0 = 0; f0 < f; f0 += pw) {
       const int64_t fw = (f - f0 < pw) ? (f - f0) : pw;

@@ -81,21 +81,47 @@ def _layer_ws_bytes(lib, graph, fin, fout, precision):
     return v
 
 
+_ASSOCIATIONS = ("auto", "reference", "aggregate_first")
+
+
+def _aggregate_first(association, graph, xr, fin, fout, need_dx, need_dw):
+    """Which product comes first.  The reference computes adj @ (X @ W) (pygcn/layers.py:33-34); (adj @ X) @ W is the
+    same function and the same gradients to fp32 rounding, and its SpMMs gather rows of width fin instead of fout:
+    forward one SpMM either way; backward one SpMM of width fout in the reference order (dS = adj^T G, for dW and
+    dX), in the aggregate-first order none for dW = (adj X)^T G and one of width fin for dX = adj^T (G W^T).
+    "auto" picks the order whose SpMMs move fewer panel columns; ties keep the reference order."""
+    if association == "reference" or graph.dense_route:
+        return False
+    ok = xr.data_ptr() % 16 == 0 and _ld(xr) % 4 == 0 and _ld(xr) >= _ld4(fin)  # 16-byte gathers of X's rows
+    if association == "aggregate_first":
+        if not ok:
+            raise RuntimeError("association='aggregate_first' needs 16-byte aligned input rows (stride a multiple of 4)")
+        return True
+    cost_ref = fout * (2 if (need_dx or need_dw) else 1)
+    cost_agg = fin * (2 if need_dx else 1)
+    return ok and cost_agg < cost_ref
+
+
 class _GCNLayerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, graph, relu, precision, mask=None, mask_scale=1.0):
+    def forward(ctx, x, weight, bias, graph, relu, precision, mask=None, mask_scale=1.0, association="auto"):
         lib = _lib.load()
         dev = x.device
         fin, fout = weight.shape
         xr = _rowmajor(x)
         w = weight.contiguous()
         b = bias.contiguous() if bias is not None else None
-        support = torch.empty((graph.n_cols, _ld4(fout)), dtype=torch.float32, device=dev)
+        agg = _aggregate_first(association, graph, xr, fin, fout, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        if agg:  # A X, kept for dW = (A X)^T G
+            support = torch.empty((graph.n_rows, _ld4(fin)), dtype=torch.float32, device=dev)
+        else:
+            support = torch.empty((graph.n_cols, _ld4(fout)), dtype=torch.float32, device=dev)
         out = torch.empty((graph.n_rows, fout), dtype=torch.float32, device=dev)
+        flags = (_lib.LAYER_RELU if relu else 0) | (_lib.LAYER_AGG_FIRST if agg else 0)
         with _on_device(dev):
             ws = _ws(_layer_ws_bytes(lib, graph, fin, fout, precision), dev)
             st = lib.gcnb_layer_forward(
-                graph._h, _ptr(xr), _ld(xr), _ptr(w), _ptr(b), fin, fout, _lib.LAYER_RELU if relu else 0, precision,
+                graph._h, _ptr(xr), _ld(xr), _ptr(w), _ptr(b), fin, fout, flags, precision,
                 _ptr(mask), mask_scale, _ptr(support), _ptr(out), _ptr(ws), ws.numel(),
                 torch.cuda.current_stream(dev).cuda_stream,
             )
@@ -108,7 +134,8 @@ class _GCNLayerFn(torch.autograd.Function):
         ctx.x_shape = tuple(x.shape)
         ctx.mask = mask
         ctx.mask_scale = mask_scale
-        ctx.save_for_backward(xr, w, out if relu else None)
+        ctx.agg = agg
+        ctx.save_for_backward(support if agg else xr, w, out if relu else None)
         return out
 
     @staticmethod
@@ -123,8 +150,12 @@ class _GCNLayerFn(torch.autograd.Function):
         need_db = ctx.has_bias and ctx.needs_input_grad[2]
         gr = _rowmajor(g)
         flags = (_lib.LAYER_RELU if ctx.relu else 0) | (_lib.LAYER_NEED_DX if need_dx else 0) | (
-            _lib.LAYER_NEED_DW if need_dw else 0) | (_lib.LAYER_NEED_DB if need_db else 0)
-        ds = torch.empty((graph.n_cols, _ld4(fout)), dtype=torch.float32, device=dev)
+            _lib.LAYER_NEED_DW if need_dw else 0) | (_lib.LAYER_NEED_DB if need_db else 0) | (
+            _lib.LAYER_AGG_FIRST if ctx.agg else 0)
+        if ctx.agg:  # scratch for G W^T, only on the way to dX
+            ds = torch.empty((graph.n_rows, _ld4(fin)), dtype=torch.float32, device=dev) if need_dx else None
+        else:
+            ds = torch.empty((graph.n_cols, _ld4(fout)), dtype=torch.float32, device=dev)
         masked = ctx.relu or ctx.mask is not None
         gm = torch.empty((graph.n_rows, fout), dtype=torch.float32, device=dev) if masked else None
         dw = torch.empty((fin, fout), dtype=torch.float32, device=dev) if need_dw else None
@@ -140,7 +171,7 @@ class _GCNLayerFn(torch.autograd.Function):
             )
         if st:
             _lib.check(st, "gcnb_layer_backward")
-        return dx, dw, db, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None
 
 
 def _ld8(f):
@@ -340,7 +371,8 @@ def _check_layer_args(x, graph, weight, bias):
             raise RuntimeError("bias must be a float32 [%d] tensor on %s" % (weight.shape[1], graph.device))
 
 
-def gcn_layer(input, adj, weight, bias=None, relu=False, precision="auto", dropout_mask=None, dropout_p=0.0):
+def gcn_layer(input, adj, weight, bias=None, relu=False, precision="auto", dropout_mask=None, dropout_p=0.0,
+              association="auto"):
     """`adj @ (input @ weight) + bias` (optionally followed by ReLU, then dropout) -- pygcn/layers.py:32-38.
 
     adj: torch sparse COO / sparse CSR / dense tensor, or a `Graph`.
@@ -350,7 +382,12 @@ def gcn_layer(input, adj, weight, bias=None, relu=False, precision="auto", dropo
     dropout_mask: optional keep-mask (bool/uint8 [n_rows, out_features]) fused into the same epilogue
     with scale 1/(1-dropout_p) -- upstream pygcn's `F.dropout` on the layer output (commented out in
     the fork, pygcn/models.py:50,54); the backward masks the incoming gradient the same way.
+    association: "auto" (default) computes (adj @ input) @ weight instead of the reference's adj @ (input @ weight)
+    when that moves fewer bytes through the SpMMs (in_features < out_features; see _aggregate_first) -- same result
+    to fp32 rounding; "reference" / "aggregate_first" force one order.
     """
+    if association not in _ASSOCIATIONS:
+        raise ValueError("association must be one of %s, got %r" % (_ASSOCIATIONS, association))
     graph = as_graph(adj)
     if input.dim() == 3:  # [B, N, Fin]: the batch shares the adjacency (pygcn/models.py:343-349)
         if dropout_mask is not None:
@@ -372,7 +409,7 @@ def gcn_layer(input, adj, weight, bias=None, relu=False, precision="auto", dropo
             raise RuntimeError("dropout_mask must be a [%d, %d] tensor on %s" % (graph.n_rows, weight.shape[1], graph.device))
         mask = dropout_mask.to(torch.uint8).contiguous()
         scale = 1.0 / (1.0 - dropout_p)
-    return _GCNLayerFn.apply(input, weight, bias, graph, bool(relu), _PRECISIONS[precision], mask, scale)
+    return _GCNLayerFn.apply(input, weight, bias, graph, bool(relu), _PRECISIONS[precision], mask, scale, association)
 
 
 class _SpmmFn(torch.autograd.Function):

@@ -26,15 +26,20 @@ class GraphConvolution(Module):
       precision  -- "auto" (default: tcgen05 3xTF32 when the product is large enough, fp32 CUDA
                     cores otherwise), "tf32x3" or "fp32" for the dense products; "bf16" = the reduced
                     tier (<= 2e-2): the panels the SpMM gathers are rounded to bf16, everything else fp32
+      association -- "auto" (default) computes (adj @ input) @ weight when in_features < out_features makes that the
+                    order with less SpMM traffic (same result to fp32 rounding, functional._aggregate_first);
+                    "reference" keeps adj @ (input @ weight) always, "aggregate_first" forces the other order
     """
 
-    def __init__(self, in_features, out_features, bias=True, *, fuse_relu=False, dropout=0.0, precision="auto"):
+    def __init__(self, in_features, out_features, bias=True, *, fuse_relu=False, dropout=0.0, precision="auto",
+                 association="auto"):
         super().__init__()
         self.in_features = in_features
         self.out_features = out_features
         self.fuse_relu = fuse_relu
         self.dropout = dropout
         self.precision = precision
+        self.association = association
         self.weight = Parameter(torch.empty(in_features, out_features, dtype=torch.float32))
         if bias:
             self.bias = Parameter(torch.empty(out_features, dtype=torch.float32))
@@ -60,7 +65,8 @@ class GraphConvolution(Module):
             n_rows = adj.shape[0]
             mask = torch.rand(n_rows, self.out_features, device=input.device) >= p
         return gcn_layer(input, adj, self.weight, self.bias, relu=getattr(self, "fuse_relu", False),
-                         precision=getattr(self, "precision", "auto"), dropout_mask=mask, dropout_p=p)
+                         precision=getattr(self, "precision", "auto"), dropout_mask=mask, dropout_p=p,
+                         association=getattr(self, "association", "auto"))
 
     def __repr__(self):
         return "%s (%s -> %s)" % (self.__class__.__name__, self.in_features, self.out_features)

@@ -430,10 +430,13 @@ def spmm_kernel(P, request):
 
     lib = _lib.load()
     name, variant = request.param if isinstance(request.param, tuple) else (request.param, -1)
-    if name == "stream":  # the streaming kernel wherever the view is eligible (auto keeps it for big graphs); variant = batch
+    if name == "stream":  # the streaming kernel wherever the view is eligible (auto keeps it for big graphs);
+        # variant = gathered rows in flight per lane, paired with one of the L2 hint modes (2 -> 2, 4 -> 1, 8 -> 0)
         _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_KERNEL, 0), "set_tuning")
         _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_STREAM, 2), "set_tuning")
         _lib.check(lib.gcnb_set_tuning(_lib.TUNE_STREAM_BATCH, max(variant, 0)), "set_tuning")
+        _lib.check(lib.gcnb_set_tuning(_lib.TUNE_STREAM_HINT, {2: 2, 4: 1, 8: 0}.get(variant, 0)), "set_tuning")
+        _lib.check(lib.gcnb_set_tuning(_lib.TUNE_STREAM_HOT_MB, 1), "set_tuning")  # small graphs: some hot, some cold columns
     else:
         _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_STREAM, 0 if name != "auto" else 1), "set_tuning")
         _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_KERNEL, _KERNELS[name]), "set_tuning")
@@ -443,11 +446,13 @@ def spmm_kernel(P, request):
     lib.gcnb_set_tuning(_lib.TUNE_SPMM_GROUP_VARIANT, -1)
     lib.gcnb_set_tuning(_lib.TUNE_SPMM_STREAM, 1)
     lib.gcnb_set_tuning(_lib.TUNE_STREAM_BATCH, 0)
+    lib.gcnb_set_tuning(_lib.TUNE_STREAM_HINT, 0)
+    lib.gcnb_set_tuning(_lib.TUNE_STREAM_HOT_MB, 48)
 
 
 @pytest.mark.parametrize("spmm_kernel", ["auto", "rows", "group", "tma", ("group", 0), ("group", 1), ("group", 2), ("group", 3),
-                                         ("group", 4), ("group", 7), ("group", 13), ("group", 14), "stream", ("stream", 8),
-                                         ("stream", 32)], indirect=True)
+                                         ("group", 4), ("group", 7), ("group", 13), ("group", 14), "stream", ("stream", 2),
+                                         ("stream", 4), ("stream", 8)], indirect=True)
 @pytest.mark.parametrize("fin,fout", [(64, 32), (5, 1), (9, 3), (16, 7), (33, 47), (100, 256), (20, 600)])
 def test_layer_vs_oracle_widths_and_long_rows(P, fin, fout, spmm_kernel):
     n = 6000
@@ -486,6 +491,54 @@ def test_layer_vs_oracle_widths_and_long_rows(P, fin, fout, spmm_kernel):
     gm = O.relu_backward(g, o2)
     dw2, db2, dx2, _ = O.c_layer_backward(x, w, True, idx, val, n, gm)
     assert err(layer2.weight.grad, dw2) < TOL and err(layer2.bias.grad, db2) < TOL and err(xt2.grad, dx2) < TOL
+
+
+@pytest.mark.parametrize("association", ["reference", "aggregate_first", "auto"])
+@pytest.mark.parametrize("fin,fout,relu,need_dx", [(16, 64, False, True), (100, 256, True, False), (100, 256, True, True),
+                                                   (5, 9, True, True), (33, 47, False, False), (64, 32, True, True)])
+def test_layer_association_orders_match_the_oracle(P, association, fin, fout, relu, need_dx):
+    """adj @ (X @ W) (the reference's order, pygcn/layers.py:33-34) and (adj @ X) @ W (what "auto" picks when
+    in_features < out_features) are the same layer: output, dW, db and dX against the oracle, fused ReLU and a
+    dropout mask included; dX only when the input asks for it."""
+    n = 5000
+    src, dst = _powerlaw_graph(n, 40000, seed=fin + fout, hub_deg=2100)
+    idx, val = O.build_normalized_adjacency(src, dst, n)
+    gr = P.Graph.from_edges(cu(src), cu(dst), n)
+    x = rng_inputs(3, (n, fin))
+    g = rng_inputs(4, (n, fout))
+    torch.manual_seed(7)
+    layer = P.GraphConvolution(fin, fout, fuse_relu=relu, association=association).to(dev())
+    if association == "aggregate_first" and fin % 4 != 0:  # rows of X are not 16-byte aligned: only "auto" may decline
+        with pytest.raises(RuntimeError, match="aligned"):
+            layer(cu(x), gr)
+        return
+    w = layer.weight.detach().cpu().numpy()
+    b = layer.bias.detach().cpu().numpy()
+    xt = cu(x).requires_grad_(need_dx)
+    out = layer(xt, gr)
+    out.backward(cu(g))
+    _, o_ref = O.c_layer_forward(x, w, b, idx, val, n)
+    if relu:
+        o2 = out.detach().cpu().numpy()
+        assert err(out, np.maximum(o_ref, 0)) < TOL
+        gm = O.relu_backward(g, o2)
+    else:
+        assert err(out, o_ref) < TOL
+        gm = g
+    dw, db, dx, _ = O.c_layer_backward(x, w, True, idx, val, n, gm)
+    assert err(layer.weight.grad, dw) < TOL and err(layer.bias.grad, db) < TOL
+    if need_dx:
+        assert err(xt.grad, dx) < TOL
+    else:
+        assert xt.grad is None
+    # dropout mask epilogue in either order
+    keep = torch.rand(n, fout, device=dev()) > 0.4
+    o_m = P.gcn_layer(cu(x), gr, layer.weight.detach(), layer.bias.detach(), relu=relu, dropout_mask=keep, dropout_p=0.4,
+                      association=association)
+    want = (np.maximum(o_ref, 0) if relu else o_ref) * keep.cpu().numpy() / 0.6
+    assert err(o_m, want) < TOL
+    with pytest.raises(ValueError):
+        P.gcn_layer(cu(x), gr, layer.weight.detach(), association="sideways")
 
 
 # ------------------------------------------------------------------ bf16 panel tier (north_star: 2e-2)
@@ -535,7 +588,7 @@ def test_to_bf16_is_round_to_nearest_even_with_zero_padding(P, f):
 
 
 @pytest.mark.parametrize("spmm_kernel", ["auto", "rows", "group", ("group", 0), ("group", 1), ("group", 3), ("group", 13),
-                                         ("group", 14), "stream", ("stream", 16)], indirect=True)
+                                         ("group", 14), "stream", ("stream", 2)], indirect=True)
 @pytest.mark.parametrize("f", [1, 3, 7, 8, 24, 32, 47, 64, 100, 256, 600, 1100])
 def test_spmm_bf16_panel_equals_fp32_kernel_on_the_rounded_panel(P, f, spmm_kernel):
     """gcnb_spmm_bf16 gathers bf16 rows and accumulates in fp32: on a panel that is already bf16-representable
@@ -560,7 +613,7 @@ def test_spmm_bf16_panel_equals_fp32_kernel_on_the_rounded_panel(P, f, spmm_kern
         assert err(got, full.cpu().numpy()) < TOL_BF16
 
 
-@pytest.mark.parametrize("spmm_kernel", ["stream", ("stream", 8), ("stream", 16), ("stream", 32)], indirect=True)
+@pytest.mark.parametrize("spmm_kernel", ["stream", ("stream", 2), ("stream", 4), ("stream", 8)], indirect=True)
 @pytest.mark.parametrize("f", [4, 48, 100, 256, 300])
 def test_stream_spmm_item_boundaries_and_epilogues(P, f, spmm_kernel):
     """The streaming SpMM (spmm_stream.cu) on a CSR whose rows start and end exactly on the 1024-entry item

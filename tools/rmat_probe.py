@@ -3,7 +3,7 @@ with the vertex labels as generated, relabelled by descending degree, or shuffle
 column order is worth.  Development tool; also the command ncu wraps (one width, one relabelling).
 
     python tools/rmat_probe.py [--widths 256,100,48] [--relabel none,degree,random] [--bf16] [--reps 5] [--workload products]
-                               [--sweep stream:hot_mb:hint:batch,...]   e.g. 0:0:0:0,1:48:2:0,1:96:1:16
+                               [--sweep stream:hot_mb:hint:batch,...]   e.g. 0:0:0:0,2:48:0:0,2:96:2:8  (batch = gathered rows in flight per lane: 0 auto, 2 / 4 / 8)
 --sweep: every configuration of the streaming kernel (gcnb_set_tuning: GCNB_TUNE_SPMM_STREAM, _HOT_MB, _HINT, _BATCH) in
 one process on the same graph; --fwd-only skips the transposed launch; --check compares with torch's CUDA CSR product.
 """
