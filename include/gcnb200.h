@@ -185,6 +185,13 @@ int gcnb_gemm(int64_t m, int64_t n, int64_t k, const float* d_a, int64_t a_rs, i
               const float* d_b, int64_t b_rs, int64_t b_cs, float* d_c, int64_t ldc, int precision,
               void* d_ws, size_t ws_bytes, void* stream);
 size_t gcnb_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k, int precision);
+/* The same product followed by  c = relu?(c + bias[j])  -- `+ self.bias` (pygcn/layers.py:36) and the caller's F.relu
+ * (models.py:49) for the aggregate-first order (A X) W + b (GCNB_LAYER_AGG_FIRST), where the dense product comes
+ * last.  The TMA-fed tcgen05 kernel applies it in its epilogue; other routes add one in-place pass over c.
+ * d_bias may be NULL; workspace as gcnb_gemm. */
+int gcnb_gemm_ex(int64_t m, int64_t n, int64_t k, const float* d_a, int64_t a_rs, int64_t a_cs, const float* d_b,
+                 int64_t b_rs, int64_t b_cs, float* d_c, int64_t ldc, const float* d_bias, int relu, int precision,
+                 void* d_ws, size_t ws_bytes, void* stream);
 
 /* d_out[0:f] = sum_rows g[r, 0:f]  (AddBackward0 of `output + self.bias`, layers.py:36).
  * If d_y != NULL the ReLU mask of the fused epilogue is applied first and the masked
@@ -225,7 +232,9 @@ int gcnb_layer_forward(const gcnb_graph* g, const float* d_x, int64_t ldx, const
 
 /* backward: db = colsum(G) ; dS = A^T G ; dW = X^T dS ; dX = dS W^T
  *   d_g [n_rows, fout] ld ldg ; d_y = forward output (only read with GCNB_LAYER_RELU)
- *   d_ds [n_cols, ld4(fout)] scratch ; d_gm [n_rows, fout] scratch (only with RELU or a dropout mask)
+ *   d_ds [n_cols, ld4(fout)] scratch ; d_gm [n_rows, ld4(fout)] scratch or NULL: when given, G (masked by the ReLU /
+ *   dropout mask, or as it is) is staged there with 16-byte aligned rows for the SpMM and the dW product -- required with
+ *   RELU or a dropout mask, and what to pass when d_g's rows are not 16-byte aligned (fout % 4 != 0)
  *   d_mask / mask_scale: the same keep-mask the forward used (G is masked before anything else)
  *   d_dw [fin, fout], d_db [fout], d_dx [n_cols, fin] ld lddx: written when requested */
 int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_t ldx, const float* d_w,
@@ -283,11 +292,6 @@ int gcnb_peer_wait(const uint32_t* d_flag, const uint32_t* d_epoch, void* stream
 int gcnb_peer_wait_lag(const uint32_t* d_word, const uint32_t* d_epoch, uint32_t lag, void* stream);
 /* copy-engine transfer to / from mapped peer memory: cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) */
 int gcnb_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
-/* NVLS multicast push (exchange "nvls", pygcn_b200/dist.py::MulticastExchange): `bytes` of src (local) stored to the
- * multicast address mc_dst with multimem.st -- the NVSwitch replicates every store into the same offset of every
- * rank's symmetric buffer.  The caller brackets it with device barriers over all ranks (slots free / slots landed).
- * Nothing in the reference (single-GPU). */
-int gcnb_multimem_push(void* mc_dst, const void* src, size_t bytes, int ctas, void* stream);
 int gcnb_peer_ack(uint32_t* peer_ack, const uint32_t* d_epoch, void* stream);
 
 /* Tuning knobs (process-wide, not thread-safe against concurrent launches; for tests and benchmarks).

@@ -65,6 +65,8 @@ SIGNATURES = {
     "gcnb_spmm_workspace_bytes": (c_sz, [c_vp, c_int, c_i64]),
     "gcnb_gemm": (c_int, [c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_int,
                           c_vp, c_sz, c_vp]),
+    "gcnb_gemm_ex": (c_int, [c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_int, c_int,
+                             c_vp, c_sz, c_vp]),
     "gcnb_gemm_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
     "gcnb_colsum": (c_int, [c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "gcnb_colsum_workspace_bytes": (c_sz, [c_i64, c_i64]),
@@ -84,7 +86,6 @@ SIGNATURES = {
     "gcnb_peer_wait": (c_int, [c_vp, c_vp, c_vp]),
     "gcnb_peer_wait_lag": (c_int, [c_vp, c_vp, ctypes.c_uint32, c_vp]),
     "gcnb_peer_copy": (c_int, [c_vp, c_vp, c_sz, c_vp]),
-    "gcnb_multimem_push": (c_int, [c_vp, c_vp, c_sz, c_int, c_vp]),
     "gcnb_fresh_bn_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "gcnb_fresh_bn_forward": (c_int, [c_i64, c_i64, c_vp, c_i64, c_int, ctypes.c_float, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz,
                                       c_vp]),

@@ -266,6 +266,13 @@ extern "C" int gcnb_gemm(int64_t m, int64_t n, int64_t k, const float* d_a, int6
                        (cudaStream_t)stream);
 }
 
+extern "C" int gcnb_gemm_ex(int64_t m, int64_t n, int64_t k, const float* d_a, int64_t a_rs, int64_t a_cs,
+                            const float* d_b, int64_t b_rs, int64_t b_cs, float* d_c, int64_t ldc, const float* d_bias,
+                            int relu, int precision, void* d_ws, size_t ws_bytes, void* stream) {
+  return gemm_dispatch_ep(m, n, k, d_a, a_rs, a_cs, d_b, b_rs, b_cs, d_c, ldc, precision, d_ws, ws_bytes, (cudaStream_t)stream,
+                          make_epilogue(d_bias, relu != 0, false, nullptr, 0, 1.f));
+}
+
 extern "C" size_t gcnb_gemm_workspace_bytes(int64_t m, int64_t n, int64_t k, int precision) {
   return gemm_ws(m, n, k, precision);
 }
@@ -380,24 +387,28 @@ extern "C" int gcnb_layer_backward(const gcnb_graph* g, const float* d_x, int64_
   int64_t gld = ldg;
   // db = colsum(G) ; with the fused ReLU the mask is applied first: G <- G * [y > 0]
   const bool masked = relu || d_mask != nullptr;
+  // d_gm [n_rows, ld4(fout)]: the staged copy of G the SpMM / dW product read -- the masked gradient, or a plain copy
+  // when the caller's G has rows that are not 16-byte aligned (fout = 47: the scalar SpMM is 20x slower than one
+  // extra pass over G)
+  const int64_t lds_ = ceil_div(fout, 4) * 4;
+  const bool stage = d_gm != nullptr;
   // Without a mask, db = colsum(G) rides in the narrow dW kernel (third operand, gemm_skinny.cu): G and dS have the
   // same number of rows when the adjacency is square, so the pass over (X, dS) adds G's column sums for free.
-  const int64_t lds_ = ceil_div(fout, 4) * 4;
-  const bool fuse_db = !agg_first && !masked && need_db && need_dw && precision != GCNB_GEMM_TF32X3 && g->n_rows == g->n_cols &&
+  const bool fuse_db = !agg_first && !masked && !stage && need_db && need_dw && precision != GCNB_GEMM_TF32X3 && g->n_rows == g->n_cols &&
                        d_db != nullptr && ldg % 4 == 0 && (reinterpret_cast<uintptr_t>(d_g) & 15u) == 0 &&
                        gemm_skinny_tn_eligible(fin, fout, g->n_cols, d_x, ldx, d_ds, lds_) &&
                        g_bytes >= gemm_skinny_tn_workspace_bytes(fin, fout, g->n_cols);
-  if (!fuse_db && (masked || need_db)) {
+  if (!fuse_db && (masked || need_db || stage)) {
     float* db = d_db;
     GCNB_REQUIRE(db != nullptr || !need_db, "layer_backward: db requested but null");
     if (db == nullptr) db = reinterpret_cast<float*>(ws_gemm);  // discard
     // with ReLU + dropout the forward output y is 0 wherever relu clipped or the mask dropped, and
     // scale * relu(.) > 0 elsewhere, so [y > 0] is still the ReLU mask for the kept entries
-    GCNB_TRY(colsum_launch(g->n_rows, fout, d_g, ldg, relu ? d_y : nullptr, fout, masked ? d_gm : nullptr,
-                           fout, db, ws_col, c_bytes, st, d_mask, fout, mask_scale));
-    if (masked) {
+    GCNB_TRY(colsum_launch(g->n_rows, fout, d_g, ldg, relu ? d_y : nullptr, fout, stage ? d_gm : nullptr,
+                           lds_, db, ws_col, c_bytes, st, d_mask, fout, mask_scale));
+    if (stage) {
       gsrc = d_gm;
-      gld = fout;
+      gld = lds_;
     }
   }
   if (!need_dw && !need_dx) return GCNB_OK;

@@ -17,7 +17,9 @@ colsum_partial_kernel(int64_t n_rows, int f, int cw, int64_t rows_per_block,
                       int64_t ldy, float* __restrict__ gm, int64_t ldgm,
                       float* __restrict__ partial, const uint8_t* __restrict__ mask, int64_t ld_mask,
                       float mask_scale) {
-  __shared__ float red[kThreads];
+  // (fp64 accumulators: a column of the upstream gradient is 10^6 terms of either sign that cancel to ~sqrt(N) of
+  // their mass; the kernel is memory-bound, the DADDs are free, and db then carries fp32 rounding of the RESULT only)
+  __shared__ double red[kThreads];
   const int tx = threadIdx.x % cw;  // column lane
   const int ty = threadIdx.x / cw;  // row lane
   const int rl = kThreads / cw;
@@ -25,10 +27,10 @@ colsum_partial_kernel(int64_t n_rows, int f, int cw, int64_t rows_per_block,
   const int64_t r1 = (r0 + rows_per_block < n_rows) ? (r0 + rows_per_block) : n_rows;
   for (int j0 = 0; j0 < f; j0 += cw) {
     const int j = j0 + tx;
-    float acc = 0.f;
+    double acc = 0.0;
     if (j < f) {
       int64_t r = r0 + ty;
-      float a4[4] = {0.f, 0.f, 0.f, 0.f};
+      double a4[4] = {0.0, 0.0, 0.0, 0.0};
       for (; r + 3 * rl < r1; r += 4 * rl) {  // four rows in flight per thread
         float v[4];
 #pragma unroll
@@ -60,9 +62,9 @@ colsum_partial_kernel(int64_t n_rows, int f, int cw, int64_t rows_per_block,
     red[threadIdx.x] = acc;
     __syncthreads();
     if (ty == 0 && j < f) {
-      float s = 0.f;
+      double s = 0.0;
       for (int t = 0; t < rl; ++t) s += red[t * cw + tx];
-      partial[(int64_t)blockIdx.x * f + j] = s;
+      partial[(int64_t)blockIdx.x * f + j] = (float)s;
     }
     __syncthreads();
   }
@@ -77,7 +79,7 @@ colsum_vec_kernel(int64_t n_rows, int f4, int cw, int64_t rows_per_block, const 
                   const float4* __restrict__ y, int64_t ldy4, float4* __restrict__ gm, int64_t ldgm4,
                   float4* __restrict__ partial, unsigned int* __restrict__ ticket, float* __restrict__ out,
                   const uchar4* __restrict__ mask, int64_t ld_mask4, float mask_scale) {
-  __shared__ float4 red[kThreads];
+  __shared__ double red[kThreads][4];  // fp64 accumulation, see colsum_partial_kernel
   __shared__ bool is_last;
   const int tx = threadIdx.x % cw;  // float4 column chunk
   const int ty = threadIdx.x / cw;  // row lane
@@ -99,37 +101,30 @@ colsum_vec_kernel(int64_t n_rows, int f4, int cw, int64_t rows_per_block, const 
     if (gm != nullptr) gm[r * ldgm4 + tx] = v;  // masked gradient, or a plain copy when y == NULL
     return v;
   };
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
   if (tx < f4) {
-    float4 a[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     int64_t r = r0 + ty;
     for (; r + 3 * rl < r1; r += 4 * rl) {
       float4 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) v[u] = load(r + u * rl);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { a[u].x += v[u].x; a[u].y += v[u].y; a[u].z += v[u].z; a[u].w += v[u].w; }
+      for (int u = 0; u < 4; ++u) { acc[0] += v[u].x; acc[1] += v[u].y; acc[2] += v[u].z; acc[3] += v[u].w; }
     }
     for (; r < r1; r += rl) {
       const float4 v = load(r);
-      a[0].x += v.x; a[0].y += v.y; a[0].z += v.z; a[0].w += v.w;
+      acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
     }
-    acc.x = (a[0].x + a[1].x) + (a[2].x + a[3].x);
-    acc.y = (a[0].y + a[1].y) + (a[2].y + a[3].y);
-    acc.z = (a[0].z + a[1].z) + (a[2].z + a[3].z);
-    acc.w = (a[0].w + a[1].w) + (a[2].w + a[3].w);
   }
-  red[threadIdx.x] = acc;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) red[threadIdx.x][c] = acc[c];
   __syncthreads();
   if (ty == 0 && tx < f4) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = 0; t < rl; ++t) {
-      const float4 v = red[t * cw + tx];
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    }
-    partial[(int64_t)blockIdx.x * f4 + tx] = s;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int t = 0; t < rl; ++t)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[c] += red[t * cw + tx][c];
+    partial[(int64_t)blockIdx.x * f4 + tx] = make_float4((float)s[0], (float)s[1], (float)s[2], (float)s[3]);
   }
   __threadfence();
   __syncthreads();
@@ -138,22 +133,23 @@ colsum_vec_kernel(int64_t n_rows, int f4, int cw, int64_t rows_per_block, const 
   if (!is_last) return;
   __threadfence();
   // final pass: row lane ty adds the partials of blocks ty, ty + rl, ... ; then the lanes in order
-  acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) acc[c] = 0.0;
   if (tx < f4) {
     for (int b = ty; b < (int)gridDim.x; b += rl) {
       const float4 v = partial[(int64_t)b * f4 + tx];
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
     }
   }
-  red[threadIdx.x] = acc;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) red[threadIdx.x][c] = acc[c];
   __syncthreads();
   if (ty == 0 && tx < f4) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = 0; t < rl; ++t) {
-      const float4 v = red[t * cw + tx];
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    }
-    reinterpret_cast<float4*>(out)[tx] = s;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int t = 0; t < rl; ++t)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[c] += red[t * cw + tx][c];
+    reinterpret_cast<float4*>(out)[tx] = make_float4((float)s[0], (float)s[1], (float)s[2], (float)s[3]);
   }
 }
 

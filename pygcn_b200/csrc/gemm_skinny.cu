@@ -129,7 +129,7 @@ skinny_tn_kernel(int64_t R, int Mo, int N, const float* __restrict__ x, int64_t 
   float (*gs)[2][kStageRows][32] = reinterpret_cast<float (*)[2][kStageRows][32]>(
       skinny_smem + kWarps * 2 * kStageRows * (MMAX + 32));  // only touched when GSUM
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float gacc = 0.f;
+  double gacc = 0.0;  // fp64: a column sum of G cancels to ~sqrt(rows) of its mass (elementwise.cu)
   float acc[MMAX];
 #pragma unroll
   for (int k = 0; k < MMAX; ++k) acc[k] = 0.f;
@@ -174,7 +174,7 @@ skinny_tn_kernel(int64_t R, int Mo, int N, const float* __restrict__ x, int64_t 
 #pragma unroll 2
     for (int r = 0; r < kStageRows; ++r) {
       const float yv = ys[warp][buf][r][lane];  // zero-filled past N and past R
-      if constexpr (GSUM) gacc += gs[warp][buf][r][lane];
+      if constexpr (GSUM) gacc += (double)gs[warp][buf][r][lane];
 #pragma unroll
       for (int q = 0; q < M4; ++q) {
         const float4 xv = *reinterpret_cast<const float4*>(&xs[warp][buf][r][4 * q]);  // broadcast
@@ -198,7 +198,7 @@ skinny_tn_kernel(int64_t R, int Mo, int N, const float* __restrict__ x, int64_t 
         const float prev = (wv == 0) ? 0.f : tile[k * 32 + lane];
         tile[k * 32 + lane] = prev + acc[k];
       }
-      if constexpr (GSUM) tile[MMAX * 32 + lane] = ((wv == 0) ? 0.f : tile[MMAX * 32 + lane]) + gacc;
+      if constexpr (GSUM) tile[MMAX * 32 + lane] = ((wv == 0) ? 0.f : tile[MMAX * 32 + lane]) + (float)gacc;
     }
     __syncthreads();
   }

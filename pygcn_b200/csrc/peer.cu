@@ -16,6 +16,7 @@
 //   * consumer side (compute stream): wait kernel spins (bounded) on flag[q] >= epoch, the SpMM over
 //     column block q runs, an ack kernel writes ack[p] = epoch into rank q's ack words.
 // All state (epochs, counters) lives in device memory, so the whole step can be CUDA-graph replayed.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -24,7 +25,25 @@ namespace gcnb {
 namespace {
 
 constexpr int kPushThreads = 256;
-constexpr uint32_t kPeerSpinLimit = 1u << 26;  // ~ seconds; a protocol bug traps instead of hanging the GPU
+// Polls before a waiting kernel gives up with __trap (a protocol bug must not hang the GPU): 2^26 polls of >= 64 ns are
+// a minute or more.  The exchange needs the ranks in lock step -- a rank that stalls longer than this on the host (a
+// checkpoint, a data-loader hiccup) kills its peers' contexts -- so DistGraphConvolution(exchange="auto") never picks it
+// (dist.py); GCNB_PEER_SPIN_LIMIT=<polls> changes the limit, 0 waits for ever.
+__device__ unsigned long long d_peer_spin_limit = 1ull << 26;
+
+int peer_spin_limit_init() {
+  static bool done[64] = {};
+  int dev = 0;
+  GCNB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || done[dev]) return GCNB_OK;
+  const char* e = getenv("GCNB_PEER_SPIN_LIMIT");
+  if (e) {
+    unsigned long long v = strtoull(e, nullptr, 10);
+    GCNB_CUDA(cudaMemcpyToSymbol(d_peer_spin_limit, &v, sizeof(v)));
+  }
+  done[dev] = true;
+  return GCNB_OK;
+}
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
@@ -35,10 +54,11 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void spin_until_ge(const uint32_t* p, uint32_t want) {
-  uint32_t spins = 0;
+  unsigned long long spins = 0;
+  const unsigned long long limit = d_peer_spin_limit;
   while ((int32_t)(ld_acquire_sys(p) - want) < 0) {
     __nanosleep(64);
-    if (++spins > kPeerSpinLimit) __trap();
+    if (limit != 0 && ++spins > limit) __trap();
   }
 }
 
@@ -150,6 +170,7 @@ extern "C" int gcnb_peer_epoch_bump(uint32_t* d_epoch, uint32_t* d_counters, int
 extern "C" int gcnb_peer_push(const void* d_src, size_t bytes, int n_peers, void* const* peer_dst,
                               uint32_t* const* peer_flag, const uint32_t* const* local_ack, const uint32_t* d_epoch,
                               uint32_t* d_counters, int n_ctas, void* stream) {
+  GCNB_TRY(peer_spin_limit_init());
   GCNB_REQUIRE(n_peers >= 0 && n_peers <= GCNB_MAX_PEERS, "peer_push: at most %d peers", GCNB_MAX_PEERS);
   if (n_peers == 0 || bytes == 0) return GCNB_OK;
   GCNB_REQUIRE(d_src && peer_dst && peer_flag && local_ack && d_epoch && d_counters, "peer_push: null argument");
@@ -171,6 +192,7 @@ extern "C" int gcnb_peer_push(const void* d_src, size_t bytes, int n_peers, void
 }
 
 extern "C" int gcnb_peer_wait(const uint32_t* d_flag, const uint32_t* d_epoch, void* stream) {
+  GCNB_TRY(peer_spin_limit_init());
   GCNB_REQUIRE(d_flag && d_epoch, "peer_wait: null argument");
   wait_flag_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_flag, d_epoch, 0u);
   GCNB_LAUNCH_CHECK();
@@ -178,6 +200,7 @@ extern "C" int gcnb_peer_wait(const uint32_t* d_flag, const uint32_t* d_epoch, v
 }
 
 extern "C" int gcnb_peer_wait_lag(const uint32_t* d_word, const uint32_t* d_epoch, uint32_t lag, void* stream) {
+  GCNB_TRY(peer_spin_limit_init());
   GCNB_REQUIRE(d_word && d_epoch, "peer_wait_lag: null argument");
   wait_flag_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_word, d_epoch, lag);
   GCNB_LAUNCH_CHECK();
@@ -187,34 +210,6 @@ extern "C" int gcnb_peer_wait_lag(const uint32_t* d_word, const uint32_t* d_epoc
 extern "C" int gcnb_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
   GCNB_REQUIRE(dst && src, "peer_copy: null argument");
   if (bytes) GCNB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
-  return GCNB_OK;
-}
-
-// ---------------------------------------------------------------------------------------------- NVLS multicast push
-// One store per 16 bytes to a MULTICAST address (an NVSwitch multicast object bound to the same offset of every
-// rank's symmetric buffer): the switch replicates it into all peers' memory, so an all-gather costs each GPU one
-// slot of egress instead of world - 1.  Written in round 1 after the multi-GPU minutes were spent: not yet run.
-__global__ void __launch_bounds__(512)
-multimem_push_kernel(float4* __restrict__ mc_dst, const float4* __restrict__ src, size_t n16) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
-    const float4 v = src[i];
-    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_dst + i), "f"(v.x), "f"(v.y),
-                 "f"(v.z), "f"(v.w)
-                 : "memory");
-  }
-}
-
-extern "C" int gcnb_multimem_push(void* mc_dst, const void* src, size_t bytes, int ctas, void* stream) {
-  GCNB_REQUIRE(mc_dst && src, "multimem_push: null argument");
-  GCNB_REQUIRE(bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(mc_dst) & 15u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0,
-               "multimem_push: 16-byte aligned addresses and size required");
-  if (bytes == 0) return GCNB_OK;
-  if (ctas < 1) ctas = 1;
-  if (ctas > 8 * kNumSMs) ctas = 8 * kNumSMs;
-  multimem_push_kernel<<<ctas, 512, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(mc_dst),
-                                                               reinterpret_cast<const float4*>(src), bytes / 16);
-  GCNB_LAUNCH_CHECK();
   return GCNB_OK;
 }
 

@@ -318,7 +318,12 @@ bool spmm_stream_eligible(const CsrView& a, int64_t row_bytes, int nch, bool bf1
   // auto (same profile): fp32 panel rows of >= 256 bytes on graphs with enough items to fill the machine.  Narrower rows
   // (F = 48: 2.9 ms against 1.9 ms) and bf16 panels (F = 100: 4.7 against 2.6 ms) stay on the row / group kernels: there
   // the gathers, not the row bookkeeping, are the smaller part of the work
-  return !bf16 && row_bytes >= g_stream_min_row && a.n_stream_items >= 2 * kNumSMs * kStreamWarps;
+  // ... and only on graphs with skewed row lengths.  On a regular graph (Reddit shape: every row ~490 entries, panel
+  // half L2-resident) the row kernels' 40 resident warps gather at 19 TB/s, this kernel's 16 at 9.4
+  // (profiles/r02_bench_products_v1.json: 12.5 against 6.1-7.3 ms); its gain is the balance and the missing per-row
+  // start-up where rows of 1 and of 90 000 entries mix (products shape: 6.5 against 7.1 ms)
+  const bool skewed = a.n_rows > 0 && a.max_degree >= 16 * (a.nnz / a.n_rows + 1);
+  return !bf16 && skewed && row_bytes >= g_stream_min_row && a.n_stream_items >= 2 * kNumSMs * kStreamWarps;
 }
 
 size_t spmm_stream_workspace_bytes(const CsrView& a, int64_t f) {

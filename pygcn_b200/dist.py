@@ -109,8 +109,6 @@ class DistGraph:
         self.phases = None
         self.fwd_blocks = None
         self.bwd_blocks = None
-        # exchange "nccl": ship only the rows each block really holds (allgather_slots); off = padded all-gather
-        self.exact_slots = os.environ.get("GCNB_DIST_EXACT_SLOTS", "0") == "1"
 
     def n_rows(self, q=None):
         q = self.rank if q is None else q
@@ -295,6 +293,19 @@ class CudaOps:
         self._lib.check(st, "gcnb_gemm")
         return out
 
+    def gemm_bias_act(self, a, b, bias=None, relu=False):
+        """relu?(a @ b + bias): gcnb_gemm_ex (the epilogue rides in the TMA-fed tcgen05 kernel when that runs)."""
+        m, k = a.shape
+        n = b.shape[1]
+        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            ws = self.F._ws(self.lib.gcnb_gemm_workspace_bytes(m, n, k, self.precision), a.device)
+            st = self.lib.gcnb_gemm_ex(m, n, k, a.data_ptr(), a.stride(0), a.stride(1), b.data_ptr(), b.stride(0),
+                                       b.stride(1), out.data_ptr(), max(n, 1), bias.data_ptr() if bias is not None else None,
+                                       1 if relu else 0, self.precision, ws.data_ptr(), ws.numel(), self._sp(a.device))
+        self._lib.check(st, "gcnb_gemm_ex")
+        return out
+
     def spmm_block(self, block, dense, out, accumulate, bias=None, relu=False):
         """out (+)= block @ dense (+ bias) (relu)."""
         f = dense.shape[1]
@@ -325,34 +336,6 @@ class CudaOps:
 
     def empty(self, shape, like):
         return torch.empty(shape, dtype=torch.float32, device=like.device)
-
-    # -- the bf16 panel tier (precision="bf16", <= 2e-2): the exchanged panel is rounded once and gathered at half the bytes
-    def to_bf16(self, panel):
-        """[rows, f] fp32 -> [rows, 8 * ceil(f / 8)] bf16 (round to nearest even, zero padded): gcnb_to_bf16."""
-        rows, f = panel.shape
-        ld8 = (f + 7) // 8 * 8
-        out = torch.empty((rows, ld8), dtype=torch.bfloat16, device=panel.device)
-        with torch.cuda.device(panel.device):
-            st = self.lib.gcnb_to_bf16(rows, f, panel.data_ptr(), panel.stride(0) if rows > 1 else f, out.data_ptr(), ld8,
-                                       self._sp(panel.device))
-        self._lib.check(st, "gcnb_to_bf16")
-        return out
-
-    def empty_bf16(self, shape, like):
-        return torch.empty(shape, dtype=torch.bfloat16, device=like.device)
-
-    def spmm_block_bf16(self, block, dense, f, out, accumulate, bias=None, relu=False):
-        """out (+)= block @ dense[:, :f] (+ bias) (relu) with a bf16 panel `dense` [n_cols, ld8]: gcnb_spmm_bf16
-        (fp32 accumulation and output)."""
-        flags = (self._lib.SPMM_ACCUMULATE if accumulate else 0) | (self._lib.SPMM_RELU if relu else 0)
-        with torch.cuda.device(dense.device):
-            ws = self.F._ws(self.lib.gcnb_spmm_workspace_bytes(block._h, 0, f), dense.device)
-            st = self.lib.gcnb_spmm_bf16(block._h, flags, dense.data_ptr(), dense.stride(0) if dense.shape[0] > 1 else
-                                         dense.shape[1], f, bias.data_ptr() if bias is not None else None, out.data_ptr(),
-                                         out.stride(0) if out.shape[0] > 1 else f, ws.data_ptr(), ws.numel(),
-                                         self._sp(dense.device))
-        self._lib.check(st, "gcnb_spmm_bf16")
-        return out
 
     # -- build-time helpers of the halo exchange (HaloPlan): blocks as CSR tensors and back
     def block_csr(self, block):
@@ -534,76 +517,6 @@ class CollectiveExchange:
         pass
 
 
-class MulticastExchange:
-    """Exchange "nvls" (opt-in; written after round 1's multi-GPU minutes were spent -- NOT yet run on hardware):
-    gathered [world * pad_rows, f] lives in torch's symmetric memory (torch.distributed._symmetric_memory: a cuMem
-    allocation every peer maps, bound to an NVLS multicast object -- plumbing), and the all-gather is OUR kernel:
-    every rank stores its slot once to the multicast address (gcnb_multimem_push, multimem.st) and the NVSwitch
-    replicates it into all ranks' buffers, so a GPU sends one slot instead of world - 1 and the exchange is bounded
-    by its ingress alone.  allgather() = barrier (every rank is done reading the previous contents) -> push ->
-    barrier (every slot has landed); both barriers are the symmetric-memory handle's device barriers on the current
-    stream, the whole sequence is stream-ordered and capturable."""
-
-    PUSH_CTAS = int(os.environ.get("GCNB_NVLS_PUSH_CTAS", "64"))
-
-    def __init__(self, rank, world, pad_rows, f, device, group=None):
-        from . import _lib
-
-        self._lib = _lib
-        self.lib = _lib.load()
-        self.rank, self.world, self.pad_rows, self.f, self.device = rank, world, pad_rows, f, device
-        self.slot_bytes = pad_rows * f * 4
-        ok, why = 1, ""
-        self.hdl = None
-        try:
-            import torch.distributed._symmetric_memory as symm
-
-            pg = group if group is not None else dist.group.WORLD
-            self._group_name = pg.group_name
-            with torch.cuda.device(device):
-                self.gathered = symm.empty((world * pad_rows, f), dtype=torch.float32, device=device)
-                self.hdl = symm.rendezvous(self.gathered, pg)
-            if not int(self.hdl.multicast_ptr):  # 0 when the group has no NVLS multicast object
-                ok, why = 0, "no NVLS multicast support for this group"
-        except Exception as e:  # every rank must learn it (collective below)
-            ok, why = 0, repr(e)
-        flag = torch.tensor([float(ok)], device=device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        if flag.item() < 1:
-            raise PeerExchangeUnavailable("multicast exchange unavailable on at least one rank (%s)" % (why or "peer"))
-        self.mc_slot = int(self.hdl.multicast_ptr) + rank * self.slot_bytes
-        self.my_slot = self.gathered[rank * pad_rows:(rank + 1) * pad_rows]
-
-    def allgather(self):
-        """Every rank's my_slot -> every rank's gathered, in stream order on the current stream."""
-        if os.environ.get("GCNB_NVLS_LIBRARY_PUSH") == "1":
-            # debugging aid for the first hardware run: torch's own multimem all-gather over the same symmetric
-            # buffer (barrier, multimem.st, barrier in one library kernel) -- tells a bug in our push from an
-            # environment without NVLS.  Never the product path.
-            torch.ops.symm_mem.multimem_all_gather_out(self.my_slot.clone(), self._group_name, self.gathered)
-            return
-        with torch.cuda.device(self.device):
-            self.hdl.barrier(channel=0)  # nobody still reads the slots of the previous exchange
-            self._lib.check(self.lib.gcnb_multimem_push(self.mc_slot, self.my_slot.data_ptr(), self.slot_bytes, self.PUSH_CTAS,
-                                                        ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
-                            "gcnb_multimem_push")
-            self.hdl.barrier(channel=1)  # every slot has landed everywhere
-
-    def close(self):
-        self.hdl = None
-        self.gathered = self.my_slot = None
-
-
-def dist_spmm_gathered(ops, dgraph, diag, remote, exch, bias=None, relu=False):
-    """out_p over an exchange object that gathers in place (MulticastExchange): this rank's slot is already in
-    exch.my_slot; the diagonal block (if the row block is split) runs before the exchange."""
-    out = ops.empty((dgraph.n_rows(), exch.f), exch.gathered)
-    if dgraph.split:
-        ops.spmm_block(diag, exch.my_slot, out, False)
-    exch.allgather()
-    return ops.spmm_block(remote, exch.gathered, out, dgraph.split, bias, relu)
-
-
 def dist_spmm_pipelined(ops, dgraph, blocks, exch, bias=None, relu=False):
     """out_p = sum_i blocks[i] @ gathered (+ bias) (relu) over the phases of dgraph.phases (groups of
     source ranks p, p+1, ...): this rank's slot is already in exch.my_slot; every other slot is consumed
@@ -698,123 +611,24 @@ def dist_spmm_halo(ops, dgraph, plan, diag, panel, bias=None, relu=False, group=
     return ops.spmm_block(plan.block, compact, out, dgraph.split, bias, relu)
 
 
-class _Works:
-    """wait() on a list of request objects (batch_isend_irecv) like on one collective's work handle."""
-
-    def __init__(self, reqs):
-        self.reqs = reqs
-
-    def wait(self):
-        for r in self.reqs:
-            r.wait()
-
-
-def allgather_slots(gathered, panel, dgraph, group=None, async_op=False):
-    """Every rank's slot `panel` [pad_rows, w] -> gathered [world * pad_rows, w] on every rank.
-
-    Default: one all_gather_into_tensor of the padded slots.  With dgraph.exact_slots (opt-in: DistGraph.exact_slots =
-    True or GCNB_DIST_EXACT_SLOTS=1) only the rows a block really holds travel: one grouped batch of point-to-point
-    sends / receives (the same slot to every peer, every peer's n_q rows into its place), which is what skewed
-    partitions need -- on a products-shaped R-MAT graph the padded slots are 3x the real rows (tools/halo_fraction.py).
-    The layout of `gathered` (source q at row q * pad_rows) is the same either way, so the blocks do not change."""
-    if not getattr(dgraph, "exact_slots", False):
-        return dist.all_gather_into_tensor(gathered, panel, group=group, async_op=async_op)
-    world, p, pad = dgraph.world, dgraph.rank, dgraph.pad_rows
-    n_p = dgraph.n_rows()
-    if n_p:
-        gathered[p * pad: p * pad + n_p].copy_(panel[:n_p])
-    ops_ = []
-    for k in range(1, world):
-        dst, src = (p + k) % world, (p - k) % world
-        if n_p:
-            ops_.append(dist.P2POp(dist.isend, panel[:n_p], dst if group is None else dist.get_global_rank(group, dst), group))
-        n_s = dgraph.n_rows(src)
-        if n_s:
-            ops_.append(dist.P2POp(dist.irecv, gathered[src * pad: src * pad + n_s],
-                                   src if group is None else dist.get_global_rank(group, src), group))
-    works = _Works(dist.batch_isend_irecv(ops_) if ops_ else [])
-    if async_op:
-        return works
-    works.wait()
-    return None
-
-
-def chunk_columns(f, chunks):
-    """Column ranges [(c0, c1), ...] that cut a width-f panel into at most `chunks` pieces whose
-    boundaries are multiples of 4 floats (gathered rows stay 16-byte aligned); fewer pieces when f
-    is too narrow to give every piece at least 8 columns."""
-    chunks = max(1, min(int(chunks), f // 8 if f >= 8 else 1))
-    quads = (f + 3) // 4
-    cuts = [min(f, 4 * ((quads * k + chunks - 1) // chunks)) for k in range(chunks + 1)]
-    cuts[-1] = f
-    return [(cuts[k], cuts[k + 1]) for k in range(chunks) if cuts[k + 1] > cuts[k]]
-
-
-def dist_spmm_chunked(ops, dgraph, block, panel, chunks, bias=None, relu=False, group=None):
-    """The unsplit row block against the all-gathered panel, pipelined over COLUMN chunks of the panel:
-    every chunk's all-gather is issued at once (they queue on the communicator's stream), and the SpMM
-    over chunk k (width f/chunks, its own slice of the output, bias slice and ReLU fused) starts when
-    that chunk has landed -- while chunk k+1 is still on the wire.  No extra kernels, no protocol state:
-    the exchange stays NCCL's, only its granularity changes.  The price is the adjacency's index stream,
-    read once per chunk instead of once, and narrower gathered rows."""
-    world = dgraph.world
-    f = panel.shape[1]
-    out = ops.empty((dgraph.n_rows(), f), panel)
-    pending = []
-    for c0, c1 in chunk_columns(f, chunks):
-        send = panel[:, c0:c1].contiguous()
-        gathered = ops.empty((world * dgraph.pad_rows, c1 - c0), panel)
-        work = allgather_slots(gathered, send, dgraph, group, async_op=True)
-        pending.append((c0, c1, gathered, work, send))
-    for c0, c1, gathered, work, _send in pending:
-        work.wait()
-        ops.spmm_block(block, gathered, out[:, c0:c1], False, bias[c0:c1] if bias is not None else None, relu)
-    return out
-
-
-def dist_spmm(ops, dgraph, diag, remote, panel, bias=None, relu=False, group=None, chunks=1):
+def dist_spmm(ops, dgraph, diag, remote, panel, bias=None, relu=False, group=None):
     """out_p = diag @ panel[:n_p] + remote @ allgather(panel) (+ bias) (relu).
 
     `panel` is this rank's [pad_rows, F] slot (rows past n_p are padding nobody references).  The
     all-gather of the slots (NCCL over NVLink, on the communicator's stream) runs while the
-    diagonal block is multiplied; the remote block is accumulated once the panel has landed.
-    chunks > 1 (unsplit row blocks only): dist_spmm_chunked."""
+    diagonal block is multiplied; the remote block is accumulated once the panel has landed."""
     world = dgraph.world
-    if world > 1 and not dgraph.split and chunks > 1 and len(chunk_columns(panel.shape[1], chunks)) > 1:
-        return dist_spmm_chunked(ops, dgraph, remote, panel, chunks, bias, relu, group)
     out = ops.empty((dgraph.n_rows(), panel.shape[1]), panel)
     if world == 1:
         return ops.spmm_block(diag, panel, out, False, bias, relu)
     gathered = ops.empty((world * dgraph.pad_rows, panel.shape[1]), panel)
     if not dgraph.split:  # no locality to exploit: one pass over the whole row block
-        allgather_slots(gathered, panel, dgraph, group)
+        dist.all_gather_into_tensor(gathered, panel, group=group)
         return ops.spmm_block(remote, gathered, out, False, bias, relu)
-    work = allgather_slots(gathered, panel, dgraph, group, async_op=True)
+    work = dist.all_gather_into_tensor(gathered, panel, group=group, async_op=True)
     ops.spmm_block(diag, panel, out, False)
     work.wait()
     return ops.spmm_block(remote, gathered, out, True, bias, relu)
-
-
-def dist_spmm_bf16(ops, dgraph, diag, remote, panel, bias=None, relu=False, group=None):
-    """dist_spmm with the exchanged panel in bf16 (DistGraphConvolution(precision="bf16"), the <= 2e-2 tier; opt-in, a
-    composition of measured kernels -- gcnb_to_bf16, gcnb_spmm_bf16 -- not yet run over NCCL): this rank's slot is rounded
-    to bf16 once, the all-gather moves HALF the bytes (the exchange is what bounds the multi-GPU step),
-    and the SpMM gathers half the bytes per row; accumulation, bias, ReLU and the output stay fp32.  Every rank rounds
-    the same values the single-GPU bf16 tier rounds, so the result equals that tier's to summation order."""
-    world = dgraph.world
-    f = panel.shape[1]
-    out = ops.empty((dgraph.n_rows(), f), panel)
-    send = ops.to_bf16(panel)
-    if world == 1:
-        return ops.spmm_block_bf16(diag, send, f, out, False, bias, relu)
-    gathered = ops.empty_bf16((world * dgraph.pad_rows, send.shape[1]), panel)
-    if not dgraph.split:
-        allgather_slots(gathered, send, dgraph, group)
-        return ops.spmm_block_bf16(remote, gathered, f, out, False, bias, relu)
-    work = allgather_slots(gathered, send, dgraph, group, async_op=True)
-    ops.spmm_block_bf16(diag, send, f, out, False)
-    work.wait()
-    return ops.spmm_block_bf16(remote, gathered, f, out, True, bias, relu)
 
 
 def halo_plans(ops, dgraph, group=None):
@@ -826,117 +640,159 @@ def halo_plans(ops, dgraph, group=None):
     return plans
 
 
-def dist_layer_forward(ops, dgraph, x, w, b, relu=False, group=None, exch=None, chunks=1, bf16=False):
-    """Row block of  A (X W) + b  (pygcn/layers.py:33-36) for this rank.  With `exch` (an exchange
-    object for [pad_rows, Fout] panels) the per-source-block pipelined scheme is used; `chunks` > 1
-    pipelines the NCCL exchange over column chunks of the panel instead (dist_spmm_chunked)."""
-    if exch is not None and exch != "halo" and dgraph.world > 1:
-        ops.gemm(x, w, out=exch.my_slot)             # X_p W straight into this rank's slot
-        if hasattr(exch, "allgather"):  # gathers in place (MulticastExchange)
-            return dist_spmm_gathered(ops, dgraph, dgraph.fwd_diag, dgraph.fwd_remote, exch, b, relu)
-        return dist_spmm_pipelined(ops, dgraph, dgraph.fwd_blocks, exch, b, relu)
-    support = ops.empty((dgraph.pad_rows, w.shape[1]), x)
+def halo_fraction(ops, dgraph, group=None):
+    """Largest share, over ranks and directions, of the all-gathered remote rows a rank actually reads (collective)."""
+    frac = getattr(dgraph, "_halo_fraction", None)
+    if frac is None:
+        plans = halo_plans(ops, dgraph, group)
+        mine = max(p.rows_received / max(p.rows_all_gather, 1) for p in plans)
+        t = torch.tensor([mine], dtype=torch.float64, device=plans[0].block.device if hasattr(plans[0].block, "device") else "cpu")
+        if dgraph.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        frac = dgraph._halo_fraction = float(t.item())
+    return frac
+
+
+def exchanged_spmm(ops, dgraph, transpose, panel, exch, bias=None, relu=False, group=None):
+    """Rows p of  A @ P  (transpose: A^T @ P) for the row-partitioned panel P whose rows of this rank are `panel`
+    [n_p, F]: the exchange step of the layer.  exch: None / "nccl" = all-gather of the padded slots, "halo" = needed
+    rows only, or a PeerExchange (pipelined per-source blocks over NVLink peer memory)."""
+    diag, remote = (dgraph.bwd_diag, dgraph.bwd_remote) if transpose else (dgraph.fwd_diag, dgraph.fwd_remote)
+    n_p, f = dgraph.n_rows(), panel.shape[1]
+    if f % 4 != 0 and (exch is None or isinstance(exch, str)):
+        # panel rows must be 16-byte aligned for the vector gathers (47 classes): exchange a zero-padded panel (the peer
+        # exchange's slots are laid out by the exchange object itself)
+        f4 = (f + 3) // 4 * 4
+        wide = ops.empty((panel.shape[0], f4), panel)
+        wide.zero_()
+        wide[:, :f].copy_(panel)
+        b4 = None
+        if bias is not None:
+            b4 = ops.empty((f4,), panel)
+            b4.zero_()
+            b4[:f].copy_(bias)
+        return exchanged_spmm(ops, dgraph, transpose, wide, exch, b4, relu, group)[:, :f]
+    if dgraph.world == 1:
+        out = ops.empty((n_p, f), panel)
+        return ops.spmm_block(diag, panel, out, False, bias, relu)
+    if exch == "halo":
+        return dist_spmm_halo(ops, dgraph, halo_plans(ops, dgraph, group)[1 if transpose else 0], diag, panel, bias, relu, group)
+    if exch is not None and exch != "nccl":  # PeerExchange: the panel goes into this rank's slot, blocks follow the phases
+        exch.my_slot[:n_p].copy_(panel[:n_p])
+        return dist_spmm_pipelined(ops, dgraph, dgraph.bwd_blocks if transpose else dgraph.fwd_blocks, exch, bias, relu)
+    if panel.shape[0] != dgraph.pad_rows:  # the all-gather moves equal slots
+        slot = ops.empty((dgraph.pad_rows, f), panel)
+        slot[:n_p].copy_(panel[:n_p])
+        panel = slot
+    return dist_spmm(ops, dgraph, diag, remote, panel, bias, relu, group)
+
+
+def aggregate_first(fin, fout, need_dx, need_dw=True):
+    """The association order of functional._aggregate_first for the row-partitioned layer: (A X) W when its SpMMs --
+    and here its EXCHANGES, one per SpMM -- move fewer panel columns than A (X W)'s."""
+    cost_ref = fout * (2 if (need_dx or need_dw) else 1)
+    cost_agg = fin * (2 if need_dx else 1)
+    return fin % 4 == 0 and cost_agg < cost_ref
+
+
+def dist_layer_forward(ops, dgraph, x, w, b, relu=False, group=None, exch=None, agg=False):
+    """Row block of  A (X W) + b  (pygcn/layers.py:33-36) for this rank; agg: (A X) W + b, the exchanged panel is X.
+    Returns (out, what backward needs beside it: A X for the aggregate-first order, else None)."""
+    if agg:
+        ax = exchanged_spmm(ops, dgraph, False, x, exch, None, False, group)
+        return ops.gemm_bias_act(ax, w, b, relu), ax
+    if exch is not None and not isinstance(exch, str) and dgraph.world > 1:
+        ops.gemm(x, w, out=exch.my_slot)             # X_p W straight into this rank's slot of the peer exchange
+        return dist_spmm_pipelined(ops, dgraph, dgraph.fwd_blocks, exch, b, relu), None
+    support = ops.empty((dgraph.pad_rows if exch != "halo" else x.shape[0], w.shape[1]), x)
     ops.gemm(x, w, out=support)
-    if exch == "halo" and dgraph.world > 1:
-        return dist_spmm_halo(ops, dgraph, halo_plans(ops, dgraph, group)[0], dgraph.fwd_diag, support, b, relu, group)
-    if bf16:
-        return dist_spmm_bf16(ops, dgraph, dgraph.fwd_diag, dgraph.fwd_remote, support, b, relu, group)
-    return dist_spmm(ops, dgraph, dgraph.fwd_diag, dgraph.fwd_remote, support, b, relu, group, chunks)
+    return exchanged_spmm(ops, dgraph, False, support, exch, b, relu, group), None
 
 
-def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=True, group=None, exch=None, chunks=1,
-                        bf16=False):
-    """(dX rows of this rank or None, dW, db): dW/db are already summed over ranks."""
+def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=True, group=None, exch=None, agg=False, ax=None,
+                        reduce=True):
+    """(dX rows of this rank or None, dW, db): dW/db are summed over ranks when `reduce` (one all-reduce)."""
     fin, fout = w.shape
-    if exch is not None and exch != "halo" and dgraph.world > 1:
-        db, _ = ops.colsum(g, y, exch.my_slot)       # local part of db; G (masked) staged into this rank's slot
-        if hasattr(exch, "allgather"):  # gathers in place (MulticastExchange)
-            ds = dist_spmm_gathered(ops, dgraph, dgraph.bwd_diag, dgraph.bwd_remote, exch)
-        else:
-            ds = dist_spmm_pipelined(ops, dgraph, dgraph.bwd_blocks, exch)  # rows p of A^T G
+    db, gm = ops.colsum(g, y)                        # local part of db; G masked by [y > 0] when the ReLU is fused
+    if agg:
+        dw = ops.gemm(ax.t(), gm)                    # (A X)_p^T G_p: no exchange at all for dW
+        ds = None
     else:
-        gm = ops.empty((dgraph.pad_rows, fout), g)
-        db, _ = ops.colsum(g, y, gm)                 # local part of db; G (masked) staged into its slot
-        if exch == "halo" and dgraph.world > 1:
-            ds = dist_spmm_halo(ops, dgraph, halo_plans(ops, dgraph, group)[1], dgraph.bwd_diag, gm, None, False, group)
-        elif bf16:
-            ds = dist_spmm_bf16(ops, dgraph, dgraph.bwd_diag, dgraph.bwd_remote, gm, None, False, group)
-        else:
-            ds = dist_spmm(ops, dgraph, dgraph.bwd_diag, dgraph.bwd_remote, gm, None, False, group, chunks)  # rows p of A^T G
-    dw = ops.gemm(x.t(), ds)                         # local part of X^T dS
-    if dgraph.world > 1:
+        ds = exchanged_spmm(ops, dgraph, True, gm, exch, None, False, group)   # rows p of A^T G
+        dw = ops.gemm(x.t(), ds)                     # local part of X^T dS
+    if dgraph.world > 1 and reduce:
         flat = torch.cat([dw.reshape(-1), db.reshape(-1)])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         dw = flat[: fin * fout].reshape(fin, fout)
         db = flat[fin * fout:]
-    dx = ops.gemm(ds, w.t()) if need_dx else None
+    dx = None
+    if need_dx:
+        dx = exchanged_spmm(ops, dgraph, True, ops.gemm(gm, w.t()), exch, None, False, group) if agg else ops.gemm(ds, w.t())
     return dx, dw, (db if has_bias else None)
 
 
 class _DistGCNLayerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, dgraph, relu, ops, group, exch_f=None, exch_b=None, chunks=1, bf16=False):
-        out = dist_layer_forward(ops, dgraph, x, weight, bias, relu, group, exch_f, chunks, bf16)
-        ctx.dgraph, ctx.relu, ctx.ops, ctx.group, ctx.exch_b, ctx.chunks = dgraph, relu, ops, group, exch_b, chunks
-        ctx.bf16 = bf16
+    def forward(ctx, x, weight, bias, dgraph, relu, ops, group, exch_f=None, exch_b=None, association="auto"):
+        fin, fout = weight.shape
+        agg = association == "aggregate_first" or (
+            association == "auto" and aggregate_first(fin, fout, ctx.needs_input_grad[0], ctx.needs_input_grad[1]))
+        out, ax = dist_layer_forward(ops, dgraph, x, weight, bias, relu, group, exch_f, agg)
+        ctx.dgraph, ctx.relu, ctx.ops, ctx.group, ctx.exch_b, ctx.agg = dgraph, relu, ops, group, exch_b, agg
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(x, weight, out if relu else None)
+        ctx.save_for_backward(ax if agg else x, weight, out if relu else None)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
         x, w, y = ctx.saved_tensors
-        dx, dw, db = dist_layer_backward(ctx.ops, ctx.dgraph, x, w, g.contiguous(), y, ctx.needs_input_grad[0],
-                                         ctx.has_bias, ctx.group, ctx.exch_b, ctx.chunks, ctx.bf16)
-        return dx, dw, db, None, None, None, None, None, None, None, None
+        dx, dw, db = dist_layer_backward(ctx.ops, ctx.dgraph, None if ctx.agg else x, w, g.contiguous(), y,
+                                         ctx.needs_input_grad[0], ctx.has_bias, ctx.group, ctx.exch_b, ctx.agg,
+                                         x if ctx.agg else None)
+        return dx, dw, db, None, None, None, None, None, None, None
 
 
 class DistGraphConvolution(torch.nn.Module):
     """`GraphConvolution` over a row-partitioned graph: forward(x_local, dist_graph) -> out_local.
     Parameters are replicated (same seed on every rank = same init as the reference layer);
-    `.grad` of weight/bias comes out already all-reduced."""
+    `.grad` of weight/bias comes out already all-reduced.
+
+    exchange: "nccl"  all-gather of the padded panel slots, overlapped with the diagonal block when the row block is split;
+              "halo"  only the rows a rank reads travel (HaloPlan): on a power-law graph a third of them;
+              "peer"  own push kernel over NVLink peer memory, per-source blocks consumed as they land (2 GPUs);
+              "auto"  halo when a rank reads less than HALO_MAX_FRACTION of the remote rows, else nccl."""
+
+    HALO_MAX_FRACTION = 0.7
 
     def __init__(self, in_features, out_features, bias=True, *, fuse_relu=False, precision="auto", group=None,
-                 exchange="auto", nccl_chunks=None):
+                 exchange="auto", association="auto"):
         super().__init__()
         from .layers import GraphConvolution
 
-        if exchange not in ("auto", "peer", "nccl", "nvls", "halo"):
-            raise ValueError("exchange must be 'auto', 'peer', 'nccl', 'nvls' or 'halo'")
+        if exchange not in ("auto", "peer", "nccl", "halo"):
+            raise ValueError("exchange must be 'auto', 'peer', 'nccl' or 'halo'")
+        if precision == "bf16":
+            raise ValueError("the row-partitioned layer has no bf16 panel tier (single-GPU GraphConvolution only)")
         self.inner = GraphConvolution(in_features, out_features, bias, fuse_relu=fuse_relu, precision=precision)
         self.group = group
         self.exchange = exchange
-        # exchange "nccl" on an unsplit row block: number of column chunks the panel all-gather is pipelined
-        # over (dist_spmm_chunked); 1 = one all-gather, then one SpMM (the measured default)
-        self.nccl_chunks = int(os.environ.get("GCNB_DIST_NCCL_CHUNKS", "1")) if nccl_chunks is None else int(nccl_chunks)
-        if self.nccl_chunks < 1:
-            raise ValueError("nccl_chunks must be >= 1")
+        self.association = association
         self._ops = None
         self._exch = None  # (dgraph id, forward exchange, backward exchange): per layer, so that a slot is
         #                    never overwritten by another layer's panel while a peer still reads it
 
-    @staticmethod
-    def resolve_exchange(exchange, world):
-        """'auto': measured on 8 x B200 (profiles/r01_dist_probe8.txt, r01_bench_n*_peer/nccl.json): the
-        pipelined peer-memory exchange wins at 2 GPUs (0.325 vs 0.380 ms/step); from 4 GPUs on its 2
-        small kernels per peer wait for SM slots behind the SpMM's CTAs and the phase-split SpMM costs
-        +38 %, so one NCCL all-gather + one SpMM is faster (0.704 vs 0.853 ms at 8)."""
-        if exchange == "auto":
-            return "peer" if world == 2 else "nccl"
-        return exchange
+    def resolve_exchange(self, dgraph):
+        if self.exchange != "auto" or dgraph.world == 1:
+            return self.exchange if self.exchange != "auto" else "nccl"
+        return "halo" if halo_fraction(self._ops, dgraph, self.group) < self.HALO_MAX_FRACTION else "nccl"
 
     def _exchanges(self, dgraph, dev):
-        kind = self.resolve_exchange(self.exchange, dgraph.world)
-        if self.inner.precision == "bf16":  # bf16 panels travel through the all-gather exchange only (dist_spmm_bf16)
-            if self.exchange not in ("auto", "nccl") or self.nccl_chunks != 1:
-                raise ValueError("precision='bf16' of the row-partitioned layer needs exchange 'auto' / 'nccl' and nccl_chunks=1")
-            return None, None
-        if kind == "halo" and dgraph.world > 1:
-            return "halo", "halo"  # needed-rows-only exchange: the plans live on the DistGraph (halo_plans)
-        if dgraph.world == 1 or kind == "nccl" or (kind == "peer" and dgraph.fwd_blocks is None):
-            return None, None
-        cls = MulticastExchange if kind == "nvls" else PeerExchange
+        kind = self.resolve_exchange(dgraph)
+        if dgraph.world == 1 or kind in ("nccl", "halo"):
+            return kind, kind
+        if dgraph.fwd_blocks is None:
+            raise RuntimeError("exchange='peer' needs a DistGraph cut per source rank (DistGraph.from_graph(per_source=True))")
         if self._exch is None or self._exch[0] is not dgraph:
             if self._exch is not None:
                 self._exch[1].close()
@@ -944,16 +800,16 @@ class DistGraphConvolution(torch.nn.Module):
                 self._exch = None
             f = self.inner.out_features
             try:
-                ef = cls(dgraph.rank, dgraph.world, dgraph.pad_rows, f, dev, self.group)
+                ef = PeerExchange(dgraph.rank, dgraph.world, dgraph.pad_rows, f, dev, self.group)
                 try:
-                    eb = cls(dgraph.rank, dgraph.world, dgraph.pad_rows, f, dev, self.group)
+                    eb = PeerExchange(dgraph.rank, dgraph.world, dgraph.pad_rows, f, dev, self.group)
                 except PeerExchangeUnavailable:
                     ef.close()
                     raise
             except PeerExchangeUnavailable as e:  # agreed on by all ranks: use the NCCL exchange from now on
                 sys.stderr.write("pygcn_b200.dist: %s; falling back to exchange='nccl'\n" % e)
                 self.exchange = "nccl"
-                return None, None
+                return "nccl", "nccl"
             self._exch = (dgraph, ef, eb)
         return self._exch[1], self._exch[2]
 
@@ -971,14 +827,16 @@ class DistGraphConvolution(torch.nn.Module):
         if not input.is_cuda:
             raise RuntimeError("DistGraphConvolution runs on CUDA devices only (no CPU fallback)")
         ef, eb = self._exchanges(dgraph, input.device)
+        assoc = self.association if isinstance(ef, str) else "reference"  # the peer exchange's slots are Fout wide
         return _DistGCNLayerFn.apply(input.contiguous(), self.inner.weight, self.inner.bias, dgraph,
-                                     self.inner.fuse_relu, self._ops, self.group, ef, eb, self.nccl_chunks,
-                                     self.inner.precision == "bf16")
+                                     self.inner.fuse_relu, self._ops, self.group, ef, eb, assoc)
 
 
 # ---------------------------------------------------------------------------- bench entry (N > 1)
 def bench_main(args, wl):
-    """`bench.py --gpus N` under torchrun: weak scaling, N x the single-GPU CBG graph, row-partitioned."""
+    """`bench.py --gpus N` under torchrun: the workload's graph row-partitioned over N GPUs (fixed total size: strong
+    scaling), the workload's whole model per step.  One JSON line on rank 0, with a parity gate against the
+    single-GPU layer and an fp64 run of the reference's lines (graphs that fit one GPU)."""
     import bench as B
     import pygcn_b200 as P
     from . import _lib
@@ -991,83 +849,104 @@ def bench_main(args, wl):
     lib = _lib.load()
     _lib.check(lib.gcnb_check_device(), "gcnb_check_device")
     sampler = B.ClockSampler(local_rank) if rank == 0 else None
-
+    timer = B.Timer(torch, lib, _lib, dev)
+    dims, relu = wl["dims"], wl["relu"]
+    layers_n = len(dims) - 1
     partitioned = bool(wl.get("partitioned"))
+    exchange = os.environ.get("GCNB_DIST_EXCHANGE", "auto")
+    # cost of a row against a stored entry when cutting the row blocks: the dense products and element-wise passes
+    # scale with rows, the SpMMs with entries (products-shaped 3-layer step on one GPU: ~0.33 ns per entry, ~4 ns per row)
+    row_weight = float(os.environ.get("GCNB_DIST_ROW_WEIGHT", "12" if layers_n > 1 else "0"))
+    split_env = os.environ.get("GCNB_DIST_SPLIT", "auto")
+    split = None if split_env == "auto" else split_env == "1"
+
     t0 = time.perf_counter()
+    full = None
     if partitioned:
-        # fixed total size (BASELINE configs[4]): the whole adjacency never exists on one GPU, every rank builds its
-        # row block of A and A^T from the replicated edge list; the exchange is the NCCL all-gather
+        # the whole adjacency never exists on one GPU: every rank builds its row block of A and A^T from the
+        # replicated edge list (drawn on the device: 752 M edges)
         n_global = wl["n"]
-        exchange = "nccl"
         gen = torch.Generator(device=dev).manual_seed(0)
         src = torch.randint(0, n_global, (wl["n_raw"],), generator=gen, device=dev, dtype=torch.int32)
         dst = torch.randint(0, n_global, (wl["n_raw"],), generator=gen, device=dev, dtype=torch.int32)
-        dgraph = build_partitioned(src, dst, n_global, rank, world)
+        dgraph = build_partitioned(src, dst, n_global, rank, world, row_weight=row_weight)
         nnz_global = dgraph.nnz_global
         del src, dst
         torch.cuda.empty_cache()
-        args.no_cuda_graph = True  # a captured step would pin a second 58 GB gathered panel in the graph's pool
+        if exchange == "auto":
+            exchange = "nccl"  # uniform graph: a rank reads ~96 % of every slot (tools/halo_fraction.py)
     else:
-        n_global = wl["n"] * world
-        wlg = dict(wl, n=n_global)
-        exchange = DistGraphConvolution.resolve_exchange(os.environ.get("GCNB_DIST_EXCHANGE", "auto"), world)
-        full = B.make_graph(P, torch, wlg, dev)          # same seed on every rank: identical global graph
-        dgraph = DistGraph.from_graph(full, rank, world, per_source=(exchange == "peer"))
+        src, dst, n_global = B.make_edges(torch, wl, 0)      # CPU generator, same seed on every rank: the single-GPU arm's graph
+        full = P.Graph.from_edges(src.to(dev), dst.to(dev), n_global)
+        del src, dst
+        if split is None and exchange in ("auto", "halo"):
+            split = True  # the diagonal block's SpMM runs while the halo rows are on the wire
+        dgraph = DistGraph.from_graph(full, rank, world, split=split, row_weight=row_weight)
         nnz_global = full.nnz
-        del full
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
-    n_local = dgraph.n_rows()
-    fin, fout = wl["fin"], wl["fout"]
+    r0, r1 = dgraph.bounds[rank], dgraph.bounds[rank + 1]
+    n_local = r1 - r0
 
-    torch.manual_seed(42)
-    layer = DistGraphConvolution(fin, fout, exchange=exchange).to(dev)
+    params = B.init_params(torch, dims)
+    layers = torch.nn.ModuleList([DistGraphConvolution(a, b, fuse_relu=relu, exchange=exchange) for a, b in zip(dims[:-1], dims[1:])])
+    with torch.no_grad():
+        for l, (w, b) in zip(layers, params):
+            l.inner.weight.copy_(w)
+            l.inner.bias.copy_(b)
+    layers = layers.to(dev)
     gen = torch.Generator(device="cpu")
-    x_host = torch.randn(n_local, fin, generator=gen.manual_seed(1 + rank)).pin_memory()
-    g_host = torch.randn(n_local, fout, generator=gen.manual_seed(100 + rank)).pin_memory()
+    if partitioned:  # 57 GB of features: every rank draws its own rows
+        x_host = torch.randn(n_local, dims[0], generator=gen.manual_seed(1 + rank)).pin_memory()
+        g_host = torch.randn(n_local, dims[-1], generator=gen.manual_seed(100 + rank)).pin_memory()
+        x_full = g_full = None
+    else:            # the single-GPU arm's X and G, this rank's rows
+        x_full = torch.randn(n_global, dims[0], generator=gen.manual_seed(1))
+        g_full = torch.randn(n_global, dims[-1], generator=gen.manual_seed(2))
+        x_host, g_host = x_full[r0:r1].clone().pin_memory(), g_full[r0:r1].clone().pin_memory()
     x, g = x_host.to(dev), g_host.to(dev)
-    flush_buf = torch.empty(B.L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
-    def flush():
-        _lib.check(lib.gcnb_l2_flush(ctypes.c_void_p(flush_buf.data_ptr()), flush_buf.numel(),
-                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "l2_flush")
+    def run(xx, gg):
+        for l in layers:
+            l.inner.weight.grad = None
+            l.inner.bias.grad = None
+        h = xx
+        for l in layers:
+            h = l(h, dgraph)
+        h.backward(gg)
+        return h
 
-    def step():
-        layer.inner.weight.grad = None
-        layer.inner.bias.grad = None
-        out = layer(x, dgraph)
-        out.backward(g)
+    def step_eager():
+        return run(x, g)
 
     if sampler:
         sampler.start()
     warm = max(args.warmup, 3)
     for _ in range(warm):
-        flush()
-        step()
+        step_eager()
     torch.cuda.synchronize()
     dist.barrier()
-    if layer._exch is None and exchange in ("peer", "nvls"):
-        exchange = "nccl"  # requested peer / multicast exchange was not available (agreed on by all ranks)
+    c0 = lib.gcnb_launch_count()
+    step_eager()
+    launches_per_step = int(lib.gcnb_launch_count() - c0)
+    resolved = [l.resolve_exchange(dgraph) for l in layers]
 
-    # capture the step (kernels + NCCL all-gathers / all-reduce) in a CUDA graph: removes the Python
-    # and launch gaps from the device time, like the single-GPU arm.  All ranks must agree.
+    # capture the step (kernels + NCCL sends / receives / all-reduces) in a CUDA graph: removes the Python and launch
+    # gaps from the device time, like the single-GPU arm.  All ranks must agree.
     cg = None
-    if not args.no_cuda_graph:
+    if not args.no_cuda_graph and not partitioned and os.environ.get("GCNB_DIST_CUDA_GRAPH", "1") == "1":
         ok = torch.ones(1, device=dev)
         try:
             s_ = torch.cuda.Stream()
             s_.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s_):
                 for _ in range(2):
-                    step()
+                    step_eager()
             torch.cuda.current_stream().wait_stream(s_)
             torch.cuda.synchronize()
-            layer.inner.weight.grad = None
-            layer.inner.bias.grad = None
             cg = torch.cuda.CUDAGraph()
             with torch.cuda.graph(cg):
-                out_static = layer(x, dgraph)
-                out_static.backward(g)
+                step_eager()
             torch.cuda.synchronize()
         except Exception as e:  # pragma: no cover
             sys.stderr.write("rank %d: CUDA graph capture failed (%r); timing eager launches\n" % (rank, e))
@@ -1077,12 +956,10 @@ def bench_main(args, wl):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if ok.item() == 0:
             cg = None
-    eager_step = step
-    if cg is not None:
-        step = cg.replay
-        for _ in range(warm):
-            flush()
-            step()
+    step = cg.replay if cg is not None else step_eager
+    for _ in range(warm):
+        timer.flush()
+        step()
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
@@ -1091,7 +968,7 @@ def bench_main(args, wl):
     if sampler:
         sampler.in_region = True
     for i in range(args.steps):
-        flush()
+        timer.flush()
         ev[i][0].record()
         step()
         ev[i][1].record()
@@ -1101,206 +978,151 @@ def bench_main(args, wl):
     if sampler:
         sampler.in_region = False
     total_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev, dtype=torch.float64)
+    mine_ms = total_ms.clone()
     dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     ms_per_step = total_ms.item() / args.steps
-    value = nnz_global / (ms_per_step * 1e-3)
+    value = layers_n * nnz_global / (ms_per_step * 1e-3)
+    per_rank = [torch.zeros_like(mine_ms) for _ in range(world)]
+    dist.all_gather(per_rank, mine_ms)
 
-    # end to end from pinned host buffers, per rank; max over ranks.  As in the single-GPU arm the inputs are
-    # double-buffered: step i+1's H2D copies run on a copy stream while step i computes; every step still copies
-    # its own X and G in and reads dW / db back inside the timed region.  No L2 flush here: one step touches the
-    # row block's index stream and the gathered panel, more than the L2 holds.
-    def e2e_sequential():
-        total = 0.0
-        for i in range(2 + args.steps):
-            flush()
-            torch.cuda.synchronize()
-            dist.barrier()
-            t0 = time.perf_counter()
-            xd = x_host.to(dev, non_blocking=True)
-            gd = g_host.to(dev, non_blocking=True)
-            layer.inner.weight.grad = None
-            layer.inner.bias.grad = None
-            o = layer(xd, dgraph)
-            o.backward(gd)
-            layer.inner.weight.grad.cpu()
-            layer.inner.bias.grad.cpu()
-            torch.cuda.synchronize()
-            if i >= 2:
-                total += time.perf_counter() - t0
-        return total
+    # ---- end to end from pinned host buffers, the single-GPU arm's method at every N: step i+1's H2D copies run on a
+    # copy stream while step i computes; every step copies its own X and G rows in and reads every dW / db back
+    copy_stream = torch.cuda.Stream()
+    bufs = [(torch.empty_like(x), torch.empty_like(g)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_pipelined():
-        copy_stream = torch.cuda.Stream()
-        bufs = [(torch.empty_like(x), torch.empty_like(g)) for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        done = [torch.cuda.Event() for _ in range(2)]
+    def prefetch(i):
+        b = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[b])
+            bufs[b][0].copy_(x_host, non_blocking=True)
+            bufs[b][1].copy_(g_host, non_blocking=True)
+            ready[b].record(copy_stream)
 
-        def prefetch(i):
+    def e2e_loop(k):
+        for b in range(2):
+            done[b].record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        prefetch(0)
+        for i in range(k):
+            if i + 1 < k:
+                prefetch(i + 1)
             b = i % 2
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(done[b])  # the step that last read this buffer pair has finished
-                bufs[b][0].copy_(x_host, non_blocking=True)
-                bufs[b][1].copy_(g_host, non_blocking=True)
-                ready[b].record(copy_stream)
+            torch.cuda.current_stream().wait_event(ready[b])
+            run(bufs[b][0], bufs[b][1])
+            done[b].record()
+            [(l.inner.weight.grad.cpu(), l.inner.bias.grad.cpu()) for l in layers]
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
 
-        def loop(k):
-            for b in range(2):
-                done[b].record()
-            torch.cuda.synchronize()
-            dist.barrier()
-            t0 = time.perf_counter()
-            prefetch(0)
-            for i in range(k):
-                if i + 1 < k:
-                    prefetch(i + 1)
-                b = i % 2
-                torch.cuda.current_stream().wait_event(ready[b])
-                layer.inner.weight.grad = None
-                layer.inner.bias.grad = None
-                o = layer(bufs[b][0], dgraph)
-                o.backward(bufs[b][1])
-                done[b].record()
-                layer.inner.weight.grad.cpu()  # the step's result, read back every step (synchronises)
-                layer.inner.bias.grad.cpu()
-            torch.cuda.synchronize()
-            return time.perf_counter() - t0
-
-        loop(3)
-        return loop(args.steps)
-
-    e2e_how = "wall clock over K eager steps of layer(x_dev, dist_graph); backward; grads.cpu(); max over ranks; "
-    # (the pipelined loop was written after the round's multi-GPU minutes were spent: opt-in until it has run once)
-    if partitioned or os.environ.get("GCNB_BENCH_E2E", "sequential") != "pipelined":
-        e2e_s = e2e_sequential()  # (a second pair of 7 GB input buffers is not worth it at the papers size)
-        e2e_how += "inputs copied from pinned host memory at the start of every step"
-    else:
-        try:
-            e2e_s = e2e_pipelined()
-            e2e_how += "inputs double-buffered from pinned host memory on a copy stream"
-        except Exception as e:  # pragma: no cover  (same code and shapes on every rank: all ranks take this path together)
-            sys.stderr.write("rank %d: pipelined e2e loop failed (%r); timing the sequential loop\n" % (rank, e))
-            torch.cuda.synchronize()
-            e2e_s = e2e_sequential()
-            e2e_how += "inputs copied from pinned host memory at the start of every step"
-    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    e2e_loop(2)
+    e2e_t = torch.tensor([e2e_loop(args.steps)], device=dev, dtype=torch.float64)
     dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = nnz_global / (e2e_t.item() / args.steps)
+    e2e_value = layers_n * nnz_global / (e2e_t.item() / args.steps)
+    del bufs
     if sampler:
         sampler.stop()
 
-    # opt-in side measurement (GCNB_BENCH_DIST_BF16=1; written after the round's multi-GPU minutes were spent): the same
-    # step with bf16 panels -- half the all-gather bytes, half the gathered bytes -- as eager launches, max over ranks
-    bf16_tier = None
-    if os.environ.get("GCNB_BENCH_DIST_BF16") == "1" and not partitioned:
+    # ---- parity gate: this rank's rows of the output and the all-reduced gradients against (a) the single-GPU layer
+    # of this package on the whole graph and (b) an fp64 run of the reference's lines, both on this GPU.  Rule as in
+    # the single-GPU arm: error against fp64 <= max(1e-5, 2 x the single-GPU step's error against fp64).
+    parity = None
+    if not partitioned:
         try:
-            layer16 = DistGraphConvolution(fin, fout, exchange="nccl", precision="bf16").to(dev)
-            layer16.inner.load_state_dict(layer.inner.state_dict())
+            o_d = step_eager().detach().clone()
+            g_d = [(l.inner.weight.grad.clone(), l.inner.bias.grad.clone()) for l in layers]
+            single = B.build_stack(P, torch, dims, relu, params, dev)
+            xf, gf = x_full.to(dev), g_full.to(dev)
+            o_s = B.stack_step(single, xf, full, gf).detach()
+            g_s = [(l.weight.grad.clone(), l.bias.grad.clone()) for l in single]
+            o64, g64, _ = B.torch_reference_lines(torch, full, params, relu, xf, gf, "csr", 1, dtype=torch.float64)
 
-            def step16():
-                layer16.inner.weight.grad = None
-                layer16.inner.bias.grad = None
-                layer16(x, dgraph).backward(g)
+            def nerr(a, b):
+                return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+            errs = {"dist_vs_fp64": {"out": nerr(o_d.double(), o64[r0:r1])}, "single_gpu_vs_fp64": {"out": nerr(o_s[r0:r1].double(), o64[r0:r1])},
+                    "dist_vs_single_gpu": {"out": nerr(o_d, o_s[r0:r1])}}
+            for i, ((dw, db), (sw, sb), (w64, b64)) in enumerate(zip(g_d, g_s, g64), 1):
+                for nm, a_, s__, d_ in (("dW%d" % i, dw, sw, w64), ("db%d" % i, db, sb, b64)):
+                    errs["dist_vs_fp64"][nm] = nerr(a_.double(), d_)
+                    errs["single_gpu_vs_fp64"][nm] = nerr(s__.double(), d_)
+                    errs["dist_vs_single_gpu"][nm] = nerr(a_, s__)
+            okv = torch.tensor([1.0 if all(v <= max(1e-5, 2 * errs["single_gpu_vs_fp64"][k]) for k, v in errs["dist_vs_fp64"].items())
+                                else 0.0], device=dev)
+            worst = torch.tensor([max(errs["dist_vs_fp64"].values())], device=dev, dtype=torch.float64)
+            dist.all_reduce(okv, op=dist.ReduceOp.MIN)
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+            parity = {"ok": bool(okv.item() == 1.0), "tolerance": 1e-5, "worst_dist_vs_fp64_over_ranks": worst.item(),
+                      "rule": "dist_vs_fp64 <= max(1e-5, 2 * single_gpu_vs_fp64) on every rank, norm-wise max|a-b| / max|b|",
+                      "rank0": errs}
+            del single, xf, gf, o_s, g_s, o64, g64, o_d, g_d
+        except Exception as e:  # pragma: no cover
+            parity = {"ok": False, "error": repr(e)}
+        torch.cuda.empty_cache()
 
-            for _ in range(warm):
-                flush()
-                step16()
-            torch.cuda.synchronize()
-            dist.barrier()
-            ev16 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-            for a_, b_ in ev16:
-                flush()
-                a_.record()
-                step16()
-                b_.record()
-            torch.cuda.synchronize()
-            t16 = torch.tensor([sum(a_.elapsed_time(b_) for a_, b_ in ev16)], device=dev, dtype=torch.float64)
-            dist.all_reduce(t16, op=dist.ReduceOp.MAX)
-            eager_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-            for a_, b_ in eager_ev:  # the fp32 step as eager launches too, for a like-for-like ratio
-                flush()
-                a_.record()
-                eager_step()
-                b_.record()
-            torch.cuda.synchronize()
-            t32 = torch.tensor([sum(a_.elapsed_time(b_) for a_, b_ in eager_ev)], device=dev, dtype=torch.float64)
-            dist.all_reduce(t32, op=dist.ReduceOp.MAX)
-            bf16_tier = {"ms_per_step_eager": t16.item() / args.steps, "fp32_ms_per_step_eager": t32.item() / args.steps,
-                         "value": nnz_global / (t16.item() / args.steps * 1e-3), "unit": "edges/s", "tolerance": 0.02,
-                         "what": "DistGraphConvolution(precision='bf16'): bf16 slots all-gathered (half the bytes), "
-                                 "gcnb_spmm_bf16 over the gathered panel, everything else fp32"}
-        except Exception as e:  # pragma: no cover  (same code on every rank)
-            sys.stderr.write("rank %d: bf16 side tier failed (%r)\n" % (rank, e))
-            torch.cuda.synchronize()
-
-    # dominant kernel on rank 0: the SpMM over its diagonal block, timed alone
-    blk = dgraph.fwd_diag if dgraph.split else dgraph.fwd_remote
+    # ---- the exchange alone and the dominant SpMM alone on this rank, at the widest panel of the model
+    fw = max(f for (_, f, _, _) in B.spmm_plan(dims))
     ops = CudaOps()
-    sup = torch.randn(blk.n_cols, fout, device=dev)
-    outb = torch.empty(n_local, fout, device=dev)
-    tms = []
-    for it in range(3 + args.steps):
-        flush()
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        ops.spmm_block(blk, sup, outb, False)
-        b_.record()
-        if it >= 3:
-            tms.append((a, b_))
-    torch.cuda.synchronize()
-    spmm_ms = sum(a.elapsed_time(b_) for a, b_ in tms) / len(tms)
-    alg = B.algorithmic_bytes_spmm(blk.nnz, n_local, fout)
+    panel = torch.randn(n_local if resolved[0] == "halo" else dgraph.pad_rows, fw, device=dev)
+    kind = "halo" if "halo" in resolved else "nccl"
+
+    def exchange_and_spmm():
+        exchanged_spmm(ops, dgraph, False, panel, kind)
+    ex_ms = timer.time(exchange_and_spmm, max(3, min(args.steps, 10)))[0]
+    blk = dgraph.fwd_remote if kind == "nccl" else halo_plans(ops, dgraph)[0].block
+    dense = torch.randn(blk.n_cols, fw, device=dev)
+    outb = torch.empty(n_local, fw, device=dev)
+    sp_ms = timer.time(lambda: ops.spmm_block(blk, dense, outb, False), max(3, min(args.steps, 10)))[0]
+    t2 = torch.tensor([ex_ms, sp_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    halo = None
+    if kind == "halo":
+        pl = halo_plans(ops, dgraph)
+        rows = torch.tensor([pl[0].rows_received, pl[0].rows_all_gather, n_local, dgraph.fwd_diag.nnz if dgraph.split else 0,
+                             pl[0].block.nnz], device=dev, dtype=torch.float64)
+        allrows = [torch.zeros_like(rows) for _ in range(world)]
+        dist.all_gather(allrows, rows)
+        halo = {"rows_received_per_rank": [int(r[0].item()) for r in allrows], "rows_an_all_gather_would_move": int(allrows[0][1].item()),
+                "rows_owned_per_rank": [int(r[2].item()) for r in allrows],
+                "stored_entries_diag_block": [int(r[3].item()) for r in allrows], "stored_entries_halo_block": [int(r[4].item()) for r in allrows]}
     peak, peak_src = B.peaks()
-    achieved = alg / (spmm_ms * 1e-3) / 1e9
-    # our kernels per step (the claim behind "gpu_launches"; NCCL's and torch's own kernels are not counted): pack W,
-    # X.W, colsum(G), dW, split-K reduce = 5, plus per SpMM (forward, transposed) the products over the row block --
-    # one, two for a split block, one per phase of the peer exchange -- and the peer protocol's epoch bump, push and a
-    # wait + ack per remote source
-    if exchange == "peer" and dgraph.phases is not None:
-        per_spmm = len(dgraph.phases) + 2 + 2 * (world - 1)
-    else:
-        per_spmm = 2 if dgraph.split else 1
-    launches_per_step = 5 + 2 * per_spmm
+    alg = B.algorithmic_bytes_spmm(blk.nnz, n_local, fw)
     if rank == 0:
+        cfg = B.config_of(wl, nnz_global, n_global)
+        cfg.update({"partition": "1-D row blocks, cost = stored entries + %g x rows" % row_weight, "bounds": dgraph.bounds,
+                    "row_block_split": dgraph.split, "exchange": resolved, "cuda_graph": cg is not None,
+                    "graph_build_s": build_s, "l2": "flushed between timed steps (512 MiB write)",
+                    "association": [o for (_, _, _, o) in B.spmm_plan(dims)], "halo": halo,
+                    "exchange_note": "halo: every rank sends each peer only the panel rows that peer's block reads (selection SpMM "
+                                     "packs them, grouped NCCL send / recv into a compact panel) while the diagonal block's SpMM "
+                                     "runs; nccl: all-gather of the padded slots; dW / db: one NCCL all-reduce per layer"})
         line = {
-            "metric": "gcn_layer_fwd_bwd_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world,
+            "metric": B.METRIC, "value": value, "unit": "edges/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong" if partitioned else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"] + ((" over %d GPUs (row-partitioned by nnz, partitioned build)" % world)
-                                                  if partitioned else
-                                                  " x %d GPUs (N=%d, row-partitioned by nnz)" % (world, n_global)),
-                       "nnz": nnz_global, "n": n_global, "in_features": fin, "out_features": fout,
-                       "input_requires_grad": False, "l2": "flushed between timed steps (512 MiB write)",
-                       "cuda_graph": cg is not None, "graph_build_s": build_s, "bounds": dgraph.bounds,
-                       "row_block_split": dgraph.split,
-                       "exchange": ("peer: own push kernel over NVLink peer memory (P2P stores + release flags), one "
-                                    "column block per source rank consumed as its slot lands; NCCL all-reduce of dW,db"
-                                    if exchange == "peer" else
-                                    "nvls: own multimem.st push of each rank's slot to the NVLS multicast address of a "
-                                    "symmetric buffer, device barriers, then the SpMM over the row block; NCCL "
-                                    "all-reduce of dW,db" if exchange == "nvls" else
-                                    "halo: needed-rows-only exchange (selection SpMM packs the rows each peer reads, grouped "
-                                    "send / recv into a compact panel), then the SpMM over the renumbered row block; NCCL "
-                                    "all-reduce of dW,db" if exchange == "halo" else
-                                    "nccl: all-gather of the X.W / G panels, then the SpMM over the row block; "
-                                    "all-reduce of dW,db"),
-                       "nccl_chunks": layer.nccl_chunks},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg,
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": (x_host.numel() + g_host.numel()) * 4,
-                    "d2h_bytes_per_step": (fin * fout + fout) * 4, "ms_per_step": e2e_t.item() / args.steps * 1e3,
-                    "how": e2e_how},
-            "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "spmm_group_kernel<LPR=8,U=4,24 CTAs/SM,W=2,SE=16> on rank 0's %s" % ("diagonal block" if dgraph.split else "row block (all-gathered panel)"),
-                         "algorithmic_bytes_per_launch": alg, "kernel_ms": spmm_ms, "peak_source": peak_src},
+                    "d2h_bytes_per_step": sum(w.numel() + b.numel() for w, b in params) * 4,
+                    "ms_per_step": e2e_t.item() / args.steps * 1e3,
+                    "how": "wall clock over K steps through DistGraphConvolution (max over ranks); every step's X and G rows "
+                           "copied from pinned host memory (double-buffered on a copy stream), every dW / db read back; bytes are rank 0's"},
+            "parity": parity,
+            "per_rank_ms_per_step": [t.item() / args.steps for t in per_rank],
+            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+            "roofline": {"bound": "hbm", "achieved": alg / (t2[1].item() * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (t2[1].item() * 1e-3) / 1e9 / peak, "traffic": None,
+                         "kernel": "CSR SpMM over rank 0's row block (width %d), slowest rank's time" % fw,
+                         "algorithmic_bytes_per_launch": alg, "kernel_ms": t2[1].item(), "peak_source": peak_src,
+                         "exchange_plus_spmm_ms": t2[0].item(), "exchange_share": max(0.0, 1.0 - t2[1].item() / max(t2[0].item(), 1e-9))},
         }
-        if bf16_tier is not None:
-            line["bf16_tier"] = bf16_tier
         print(json.dumps(line), flush=True)
     # a captured graph that holds NCCL kernels must go before the communicator does
     del step, cg
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
-    sys.stdout.flush()
-    sys.stderr.flush()
-    os._exit(0)  # skip communicator teardown: it can block behind graph-captured collectives
+    dist.destroy_process_group()
+    return 0

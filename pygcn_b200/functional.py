@@ -156,8 +156,10 @@ class _GCNLayerFn(torch.autograd.Function):
             ds = torch.empty((graph.n_rows, _ld4(fin)), dtype=torch.float32, device=dev) if need_dx else None
         else:
             ds = torch.empty((graph.n_cols, _ld4(fout)), dtype=torch.float32, device=dev)
-        masked = ctx.relu or ctx.mask is not None
-        gm = torch.empty((graph.n_rows, fout), dtype=torch.float32, device=dev) if masked else None
+        # the copy of G the SpMM / dW product read: the masked gradient, or G itself re-laid with 16-byte aligned rows
+        # when the caller's are not (fout = 47)
+        staged = ctx.relu or ctx.mask is not None or _ld(gr) % 4 != 0 or gr.data_ptr() % 16 != 0
+        gm = torch.empty((graph.n_rows, _ld4(fout)), dtype=torch.float32, device=dev) if staged else None
         dw = torch.empty((fin, fout), dtype=torch.float32, device=dev) if need_dw else None
         db = torch.empty((fout,), dtype=torch.float32, device=dev) if need_db else None
         dx = torch.empty((graph.n_cols, fin), dtype=torch.float32, device=dev) if need_dx else None

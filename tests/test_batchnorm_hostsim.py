@@ -60,7 +60,8 @@ def sim(tmp_path_factory):
         probe, "hostsim_vec4_loads.fetch_add(1, std::memory_order_relaxed); " + probe)
     cpp = d / "batchnorm_hostsim.cpp"
     cpp.write_text(src + '\n#include <stdarg.h>\nnamespace gcnb { static thread_local char g_err[512];\n'
-                   'void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); } }\n'
+                   'void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); }\n'
+                   'void count_launch() {} }\n'
                    'extern "C" const char* hostsim_last_error() { return gcnb::g_err; }\n'
                    'extern "C" long hostsim_take_vec4_loads() { return hostsim_vec4_loads.exchange(0); }\n')
     so = d / "libbn_hostsim.so"

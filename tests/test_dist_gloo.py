@@ -43,6 +43,14 @@ class NumpyOps:
         out[: r.shape[0]] = r
         return out
 
+    def gemm_bias_act(self, a, b, bias=None, relu=False):
+        r = a.numpy() @ b.numpy()
+        if bias is not None:
+            r = r + bias.numpy()
+        if relu:
+            r = np.maximum(r, 0)
+        return torch.from_numpy(r.astype(np.float32))
+
     def spmm_block(self, block, dense, out, accumulate, bias=None, relu=False):
         acc = out.numpy().copy() if accumulate else np.zeros(out.shape, np.float32)
         np.add.at(acc, block.row, block.val[:, None] * dense.numpy()[block.col])
@@ -61,20 +69,6 @@ class NumpyOps:
 
     def empty(self, shape, like):
         return torch.full(shape, float("nan"), dtype=torch.float32)  # padding must never be read
-
-    # the bf16 panel tier (dist_spmm_bf16): torch's cast is the same round-to-nearest-even as gcnb_to_bf16
-    def to_bf16(self, panel):
-        rows, f = panel.shape
-        out = torch.zeros((rows, (f + 7) // 8 * 8), dtype=torch.bfloat16)
-        out[:, :f] = panel.to(torch.bfloat16)
-        return out
-
-    def empty_bf16(self, shape, like):
-        return torch.full(shape, float("nan"), dtype=torch.bfloat16)
-
-    def spmm_block_bf16(self, block, dense, f, out, accumulate, bias=None, relu=False):
-        assert dense.dtype == torch.bfloat16
-        return self.spmm_block(block, dense[:, :f].to(torch.float32), out, accumulate, bias, relu)
 
     # build-time helpers of the halo exchange (dist.HaloPlan)
     def block_csr(self, block):
@@ -98,21 +92,7 @@ class NumpyOps:
         return self.block_from_csr(torch.arange(k + 1), ids.long(), torch.ones(k), k, n_cols)
 
 
-class InPlaceGather:
-    """Stand-in for dist.MulticastExchange on CPU: same interface (gathered, my_slot, f, allgather()), the all-gather
-    itself done by gloo."""
-
-    def __init__(self, rank, world, pad_rows, f):
-        self.f = f
-        self.gathered = torch.full((world * pad_rows, f), float("nan"), dtype=torch.float32)
-        self.my_slot = self.gathered[rank * pad_rows:(rank + 1) * pad_rows]
-        self.my_slot.zero_()
-
-    def allgather(self):
-        dist.all_gather_into_tensor(self.gathered, self.my_slot.clone())
-
-
-def _problem(n=300, seed=3, fout=5):
+def _problem(n=300, seed=3, fout=5, fin=12):
     rs = np.random.default_rng(seed)
     src = (n * rs.random(4000) ** 2).astype(np.int64)  # skewed degrees: nnz balance != row balance
     dst = rs.integers(0, n, 4000)
@@ -124,12 +104,12 @@ def _problem(n=300, seed=3, fout=5):
     return n, idx, val, x, g, w, b
 
 
-def _worker(rank, world, port, outdir, relu, split=True, pipelined=False, chunks=1, exact=False, bf16=False):
+def _worker(rank, world, port, outdir, relu, split=True, exchange="nccl", agg=False, fin=12):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        n, idx, val, x, g, w, b = _problem(fout=_fout(chunks))
+        n, idx, val, x, g, w, b = _problem(fin=fin)
         bounds = D.partition_rows_by_nnz(O.coo_to_csr(idx, n), world)
         r0, r1 = bounds[rank], bounds[rank + 1]
         tidx = np.vstack([idx[1], idx[0]])
@@ -139,35 +119,25 @@ def _worker(rank, world, port, outdir, relu, split=True, pipelined=False, chunks
             blocks.append(HostBlock(ii, val, r0, r1, c0=r0, c1=r1) if split else None)
             blocks.append(HostBlock(ii, val, r0, r1, bounds=bounds, pad=pad, exclude=rank if split else -1))
         dg = D.DistGraph(rank, world, bounds, pad, *blocks, 0, idx.shape[1], split)
-        dg.exact_slots = exact  # only the rows a block holds travel (allgather_slots), padding stays NaN
         ops = NumpyOps()
         xt, gt = torch.from_numpy(x[r0:r1].copy()), torch.from_numpy(g[r0:r1].copy())
         wt, bt = torch.from_numpy(w), torch.from_numpy(b)
-        ef = eb = None
-        if pipelined is True:  # one column block per source rank, consumed in the order p, p+1, ... (exchange "peer")
+        ef = eb = exchange
+        if exchange == "pipelined":  # one column block per source rank, consumed in the order p, p+1, ... (exchange "peer")
             dg.phases = D.exchange_phases(rank, world)
             dg.fwd_blocks = [HostBlock(idx, val, r0, r1, bounds=bounds, pad=pad, only=qs) for qs in dg.phases]
             dg.bwd_blocks = [HostBlock(tidx, val, r0, r1, bounds=bounds, pad=pad, only=qs) for qs in dg.phases]
             ef = D.CollectiveExchange(rank, world, pad, w.shape[1], xt)
             eb = D.CollectiveExchange(rank, world, pad, w.shape[1], xt)
-        if pipelined == "halo":  # needed-rows-only exchange (dist.HaloPlan / dist_spmm_halo)
-            ef = eb = "halo"
-        if pipelined == "gathered":  # the in-place all-gather route of exchange "nvls" (dist_spmm_gathered)
-            ef = InPlaceGather(rank, world, pad, w.shape[1])
-            eb = InPlaceGather(rank, world, pad, w.shape[1])
-        out = D.dist_layer_forward(ops, dg, xt, wt, bt, relu=relu, exch=ef, chunks=chunks, bf16=bf16)
-        dx, dw, db = D.dist_layer_backward(ops, dg, xt, wt, gt, out if relu else None, True, True, exch=eb, chunks=chunks,
-                                           bf16=bf16)
+        out, ax = D.dist_layer_forward(ops, dg, xt, wt, bt, relu=relu, exch=ef, agg=agg)
+        assert (ax is not None) == agg
+        dx, dw, db = D.dist_layer_backward(ops, dg, None if agg else xt, wt, gt, out if relu else None, True, True, exch=eb,
+                                           agg=agg, ax=ax)
+        frac = D.halo_fraction(ops, dg) if exchange == "halo" else -1.0
         np.savez(os.path.join(outdir, "r%d.npz" % rank), out=out.numpy(), dx=dx.numpy(), dw=dw.numpy(), db=db.numpy(),
-                 bounds=np.array(bounds))
+                 bounds=np.array(bounds), frac=frac)
     finally:
         dist.destroy_process_group()
-
-
-def _fout(chunks):
-    """Panel width of the test problem: 5 columns normally, 37 (uneven 16-byte-aligned pieces) when the
-    exchange is cut into column chunks."""
-    return 5 if chunks == 1 else 37
 
 
 def _free_port():
@@ -178,28 +148,19 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,relu,split,chunks", [(2, True, False, 1), (3, False, True, 1), (4, True, False, 2)])
-def test_exact_size_slot_exchange_matches_single_process_oracle(world, relu, split, chunks):
-    """The grouped point-to-point exchange that ships every block's real rows only (dist.allgather_slots with
-    exact_slots) under the unsplit, split and column-chunked schemes; the nnz-balanced blocks of the skewed test graph
-    hold different row counts, and the padding rows of the gathered buffers stay NaN."""
-    test_row_partitioned_layer_matches_single_process_oracle(world, relu, split, False, chunks, exact=True)
-
-
-@pytest.mark.parametrize("world,relu,split,pipelined,chunks", [
-    (2, False, True, False, 1), (2, True, False, False, 1), (3, False, True, False, 1), (2, True, False, True, 1),
-    (3, False, False, True, 1), (4, True, False, True, 1),
-    # the all-gather exchange pipelined over column chunks of the panel (dist_spmm_chunked), 37-column panels
-    (2, True, False, False, 2), (3, False, False, False, 4),
-    # the in-place gathered route (exchange "nvls"), unsplit and split row blocks
-    (2, True, False, "gathered", 1), (3, False, True, "gathered", 1),
+@pytest.mark.parametrize("world,relu,split,exchange,agg", [
+    (2, False, True, "nccl", False), (2, True, False, "nccl", False), (3, False, True, "nccl", False),
+    (2, True, False, "pipelined", False), (3, False, False, "pipelined", False), (4, True, False, "pipelined", False),
     # the needed-rows-only exchange: unsplit (own slot at the front of the compact panel) and split row blocks
-    (2, True, False, "halo", 1), (3, False, True, "halo", 1), (4, True, False, "halo", 1)])
-def test_row_partitioned_layer_matches_single_process_oracle(world, relu, split, pipelined, chunks, exact=False):
+    (2, True, False, "halo", False), (3, False, True, "halo", False), (4, True, False, "halo", False),
+    # the aggregate-first order (A X) W + b: the exchanged panel is X (forward) and G W^T (backward, for dX); dW needs
+    # no exchange
+    (2, True, True, "nccl", True), (3, False, False, "nccl", True), (3, True, True, "halo", True), (4, False, False, "halo", True)])
+def test_row_partitioned_layer_matches_single_process_oracle(world, relu, split, exchange, agg):
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_worker, args=(world, _free_port(), d, relu, split, pipelined, chunks, exact), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), d, relu, split, exchange, agg), nprocs=world, join=True)
         parts = [np.load(os.path.join(d, "r%d.npz" % r)) for r in range(world)]
-    n, idx, val, x, g, w, b = _problem(fout=_fout(chunks))
+    n, idx, val, x, g, w, b = _problem()
     _, o_ref = O.c_layer_forward(x, w, b, idx, val, n)
     gm = g
     if relu:
@@ -214,19 +175,17 @@ def test_row_partitioned_layer_matches_single_process_oracle(world, relu, split,
     for p in parts:  # all-reduced: every rank holds the full gradient
         assert O.normwise_err(p["dw"], dw) < 1e-5 and O.normwise_err(p["db"], db) < 1e-5
     assert list(parts[0]["bounds"]) == list(parts[-1]["bounds"])
+    if exchange == "halo":  # every rank agrees on the largest share of remote rows any rank reads
+        assert len({float(p["frac"]) for p in parts}) == 1 and 0.0 < float(parts[0]["frac"]) <= 1.0
 
 
-def test_chunk_columns_are_aligned_and_cover_the_panel():
-    for f in (1, 5, 7, 8, 16, 20, 32, 37, 47, 64, 256, 600):
-        for chunks in (1, 2, 3, 4, 8):
-            cc = D.chunk_columns(f, chunks)
-            assert cc[0][0] == 0 and cc[-1][1] == f and 1 <= len(cc) <= chunks
-            assert all(a[1] == b[0] for a, b in zip(cc, cc[1:]))          # contiguous, in order
-            assert all(c0 % 4 == 0 and c1 > c0 for c0, c1 in cc)          # 16-byte aligned starts, no empty piece
-            assert len(cc) == 1 or min(c1 - c0 for c0, c1 in cc[:-1]) >= 8  # no sliver pieces
-    assert D.chunk_columns(32, 2) == [(0, 16), (16, 32)]
-    assert D.chunk_columns(37, 4) == [(0, 12), (12, 20), (20, 32), (32, 37)]
-    assert D.chunk_columns(5, 4) == [(0, 5)]
+def test_aggregate_first_rule_of_the_partitioned_layer():
+    """(A X) W when that moves fewer panel columns through the exchanges: in_features < out_features with an input
+    that needs no gradient halves again what the reference order costs (no backward exchange at all)."""
+    assert D.aggregate_first(100, 256, need_dx=False) and D.aggregate_first(100, 256, need_dx=True)
+    assert not D.aggregate_first(256, 256, True) and not D.aggregate_first(256, 47, True) and not D.aggregate_first(602, 256, False)
+    assert D.aggregate_first(64, 48, need_dx=False) and not D.aggregate_first(64, 32, need_dx=False)  # 64 < 2 * 48; tie keeps the reference order
+    assert not D.aggregate_first(5, 9, False)  # rows of X must be 16-byte aligned
 
 
 def test_exchange_phases_cover_every_source_once_own_slot_first():
@@ -264,43 +223,11 @@ def test_partition_balances_nnz_and_exchange_is_a_matching():
     assert D.partition_rows_by_nnz(np.array([0, 2, 5]), 4)[-1] == 2
 
 
-@pytest.mark.parametrize("world,relu,split,exact", [(2, True, False, False), (3, False, True, False), (4, True, False, True)])
-def test_bf16_panel_tier_of_the_row_partitioned_layer(world, relu, split, exact):
-    """dist_spmm_bf16 (DistGraphConvolution(precision="bf16")): each rank rounds its slot to bf16 once, the all-gather
-    moves the bf16 slots (half the bytes), the SpMM accumulates in fp32.  Equal (<= 1e-5) to the single-process layer
-    with the same two panels rounded -- support forward, the masked gradient backward -- and within 2e-2 of the fp32
-    layer (north_star's bf16 tolerance); unsplit, split and exact-size-slot exchanges."""
-    with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_worker, args=(world, _free_port(), d, relu, split, False, 1, exact, True), nprocs=world, join=True)
-        parts = [np.load(os.path.join(d, "r%d.npz" % r)) for r in range(world)]
-    n, idx, val, x, g, w, b = _problem()
-    rnd = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).to(torch.float32).numpy()
-    a = np.zeros((n, n), np.float64)
-    np.add.at(a, (idx[0], idx[1]), val.astype(np.float64))
-    o_t = a @ rnd(x @ w).astype(np.float64) + b            # the tier: bf16(support) gathered, fp32 everything else
-    gm = g
-    if relu:
-        gm = np.where(o_t > 0, g, 0).astype(np.float32)
-        o_t = np.maximum(o_t, 0)
-    ds_t = a.T @ rnd(gm).astype(np.float64)
-    dw_t, db_t, dx_t = x.T.astype(np.float64) @ ds_t, gm.sum(0), ds_t @ w.T.astype(np.float64)
-    out = np.concatenate([p["out"] for p in parts])
-    dxs = np.concatenate([p["dx"] for p in parts])
-    assert O.normwise_err(out, o_t) < 1e-5 and O.normwise_err(dxs, dx_t) < 1e-5
-    for p in parts:
-        assert O.normwise_err(p["dw"], dw_t) < 1e-5 and O.normwise_err(p["db"], db_t) < 1e-5
-    _, o_ref = O.c_layer_forward(x, w, b, idx, val, n)      # and the fp32 layer within the tier's tolerance
-    g32 = O.relu_backward(g, o_ref) if relu else g
-    dw, db, dx, _ = O.c_layer_backward(x, w, True, idx, val, n, g32)
-    assert O.normwise_err(out, np.maximum(o_ref, 0) if relu else o_ref) < 2e-2
-    assert O.normwise_err(dxs, dx) < 2e-2 and O.normwise_err(parts[0]["dw"], dw) < 2e-2
-
-
-@pytest.mark.parametrize("bf16", [False, True])
-def test_autograd_function_of_the_partitioned_layer_at_world_1(bf16):
+@pytest.mark.parametrize("association", ["reference", "aggregate_first", "auto"])
+def test_autograd_function_of_the_partitioned_layer_at_world_1(association):
     """_DistGCNLayerFn (what DistGraphConvolution.forward calls) end to end through torch autograd with the numpy
     backend at world size 1 -- no process group needed: argument / gradient arity, ctx plumbing, needs_input_grad,
-    the fused-ReLU mask, both precision tiers."""
+    the fused-ReLU mask, both association orders."""
     n, idx, val, x, g, w, b = _problem()
     tidx = np.vstack([idx[1], idx[0]])
     bounds = [0, n]
@@ -310,15 +237,15 @@ def test_autograd_function_of_the_partitioned_layer_at_world_1(bf16):
     xt = torch.from_numpy(x.copy()).requires_grad_(True)
     wt = torch.from_numpy(w.copy()).requires_grad_(True)
     bt = torch.from_numpy(b.copy()).requires_grad_(True)
-    out = D._DistGCNLayerFn.apply(xt, wt, bt, dg, True, NumpyOps(), None, None, None, 1, bf16)
+    out = D._DistGCNLayerFn.apply(xt, wt, bt, dg, True, NumpyOps(), None, None, None, association)
     out.backward(torch.from_numpy(g))
     _, o_ref = O.c_layer_forward(x, w, b, idx, val, n)
     dw, db, dx, _ = O.c_layer_backward(x, w, True, idx, val, n, O.relu_backward(g, o_ref))
-    tol = 2e-2 if bf16 else 1e-5
+    tol = 1e-5
     assert O.normwise_err(out.detach().numpy(), np.maximum(o_ref, 0)) < tol
     assert O.normwise_err(wt.grad.numpy(), dw) < tol and O.normwise_err(xt.grad.numpy(), dx) < tol
     assert O.normwise_err(bt.grad.numpy(), db) < tol
     x2 = torch.from_numpy(x.copy())  # input without grad: no dX is computed
-    out2 = D._DistGCNLayerFn.apply(x2, wt, None, dg, False, NumpyOps(), None, None, None, 1, bf16)
+    out2 = D._DistGCNLayerFn.apply(x2, wt, None, dg, False, NumpyOps(), None, None, None, association)
     out2.sum().backward()
     assert x2.grad is None and out2.shape == (n, w.shape[1])

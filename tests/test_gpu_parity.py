@@ -1066,34 +1066,6 @@ def test_row_partition_blocks_emulated_on_one_gpu(P, world):
         assert torch.equal(dl.inner.weight.grad, layer.weight.grad)
 
 
-@pytest.mark.parametrize("f,chunks", [(32, 2), (40, 3), (47, 4), (256, 2)])
-def test_column_chunked_row_block_spmm_equals_one_pass(P, f, chunks):
-    """The SpMMs dist_spmm_chunked runs between its chunked all-gathers (pygcn_b200/dist.py): the unsplit row
-    block against contiguous column chunks of the gathered panel, each into its column slice of the output with
-    its slice of the bias and the fused ReLU, must equal the one-pass SpMM over the whole panel."""
-    from pygcn_b200 import dist as D
-
-    n, world = 6000, 4
-    src, dst = _powerlaw_graph(n, 50000, seed=f, hub_deg=2500)
-    gr = P.Graph.from_edges(cu(src), cu(dst), n)
-    dg = D.DistGraph.from_graph(gr, 0, world, split=False)  # rank 0 owns the hub row (chunked long-row path)
-    blk = dg.fwd_remote
-    assert blk.n_long_chunks > 0
-    gen = torch.Generator(device=dev()).manual_seed(f)
-    panel = torch.randn(world * dg.pad_rows, f, generator=gen, device=dev())
-    bias = torch.randn(f, generator=gen, device=dev())
-    ops = D.CudaOps("fp32")
-    one = torch.empty(dg.n_rows(), f, device=dev())
-    ops.spmm_block(blk, panel, one, False, bias, True)
-    cc = D.chunk_columns(f, chunks)
-    assert len(cc) == chunks
-    out = torch.full((dg.n_rows(), f), float("nan"), device=dev())
-    for c0, c1 in cc:
-        ops.spmm_block(blk, panel[:, c0:c1].contiguous(), out[:, c0:c1], False, bias[c0:c1], True)
-    assert not torch.isnan(out).any()
-    assert ((out - one).abs().max() / one.abs().max()).item() < TOL
-
-
 # ------------------------------------------------------------------ error behaviour (SURVEY.md 8b)
 def test_errors(P, golden):
     layer = P.GraphConvolution(4, 3)

@@ -1,6 +1,6 @@
 """Summarise an .ncu-rep (ncu --set full) into the small JSON committed under profiles/.
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep "description of the command" > profiles/x.json
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep "description of the command" [workload] > profiles/x.json
 """
 import csv
 import json
@@ -38,7 +38,7 @@ def main(path, source):
     def nbytes(rec, key):
         m = rec.get(key)
         return float(m["value"].replace(",", "")) * UNIT.get(m["unit"], 1.0) if m else None
-    res = {"source": source, "launches": launches}
+    res = {"source": source, "workload": sys.argv[3] if len(sys.argv) > 3 else "cbg", "launches": launches}
     if launches:
         l0 = launches[0]
         rd, wr = nbytes(l0, "dram__bytes_read.sum"), nbytes(l0, "dram__bytes_write.sum")

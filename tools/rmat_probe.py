@@ -33,7 +33,9 @@ def main():
     lib = _lib.load()
     flush_buf = torch.empty(B.L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    src0, dst0, n = B.make_edges(torch, wl, 0, device=dev)
+    # --cpu-edges: the bench's own seeded edge list (CPU generator) instead of a device-drawn graph of the same family
+    src0, dst0, n = B.make_edges(torch, wl, 0, device="cpu" if "--cpu-edges" in sys.argv else dev)
+    src0, dst0 = src0.to(dev), dst0.to(dev)
     for how in relabels:
         src, dst = src0.long(), dst0.long()
         if how == "degree":
