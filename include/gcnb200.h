@@ -294,6 +294,28 @@ int gcnb_peer_wait_lag(const uint32_t* d_word, const uint32_t* d_epoch, uint32_t
 int gcnb_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
 int gcnb_peer_ack(uint32_t* peer_ack, const uint32_t* d_epoch, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Row-partitioned layer, exchange step (nothing in the reference: it is single-GPU).
+ * Needed-rows-only ("halo") exchange of a dense panel over an NCCL communicator the CALLER owns
+ * (nccl_comm = an ncclComm_t; from torch: ProcessGroupNCCL._comm_ptr()).  NCCL is bound at run time.
+ * gcnb_halo_create : h_send_counts / h_recv_counts [world] rows per peer (0 for the rank itself); d_send_rows the
+ *                    local panel row ids to send, grouped by destination rank in rank order (copied);
+ *                    h_recv_offsets [world] = first row of source q's rows in the compact panel.
+ * gcnb_halo_pack   : d_sendbuf [send rows, f] <- the rows of d_panel (ld ldp) every peer reads, one kernel.
+ * gcnb_halo_exchange: one grouped ncclSend / ncclRecv round on `stream`: d_compact [.., f] contiguous receives
+ *                    source q's rows at row h_recv_offsets[q].  Both calls are stream-ordered and graph-capturable.
+ * ---------------------------------------------------------------------------------- */
+typedef struct gcnb_halo gcnb_halo;
+int gcnb_halo_create(int rank, int world, const int64_t* h_send_counts, const int32_t* d_send_rows,
+                     const int64_t* h_recv_counts, const int64_t* h_recv_offsets, void* stream, gcnb_halo** out);
+void gcnb_halo_free(gcnb_halo* h);
+int64_t gcnb_halo_send_rows(const gcnb_halo* h);
+int64_t gcnb_halo_recv_rows(const gcnb_halo* h);
+int gcnb_halo_nccl_available(void); /* 1 when libnccl.so.2 could be bound */
+int gcnb_halo_pack(const gcnb_halo* h, const float* d_panel, int64_t ldp, int64_t f, float* d_sendbuf, void* stream);
+int gcnb_halo_exchange(const gcnb_halo* h, void* nccl_comm, const float* d_sendbuf, int64_t f, float* d_compact,
+                       void* stream);
+
 /* Tuning knobs (process-wide, not thread-safe against concurrent launches; for tests and benchmarks).
  *   GCNB_TUNE_SPMM_KERNEL: 0 auto (default), 1 warp-per-row shuffle kernel, 2 group-per-row kernel,
  *                          3 TMA-staged warp-per-row kernel

@@ -95,6 +95,14 @@ SIGNATURES = {
                                          c_vp, ctypes.POINTER(c_vp)]),
     "gcnb_peer_ack": (c_int, [c_vp, c_vp, c_vp]),
     "gcnb_launch_count": (ctypes.c_longlong, []),
+    "gcnb_halo_create": (c_int, [c_int, c_int, ctypes.POINTER(c_i64), c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_vp,
+                                 ctypes.POINTER(c_vp)]),
+    "gcnb_halo_free": (None, [c_vp]),
+    "gcnb_halo_send_rows": (c_i64, [c_vp]),
+    "gcnb_halo_recv_rows": (c_i64, [c_vp]),
+    "gcnb_halo_nccl_available": (c_int, []),
+    "gcnb_halo_pack": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "gcnb_halo_exchange": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
 }
 
 _lock = threading.Lock()

@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libgcnb200.so")
 
-SOURCES = ["api.cu", "spmm.cu", "spmm_stream.cu", "gemm_simt.cu", "gemm_skinny.cu", "gemm_tc.cu", "elementwise.cu", "graph_build.cu", "peer.cu", "batchnorm.cu"]
+SOURCES = ["api.cu", "spmm.cu", "spmm_stream.cu", "gemm_simt.cu", "gemm_skinny.cu", "gemm_tc.cu", "elementwise.cu", "graph_build.cu", "peer.cu", "batchnorm.cu", "dist.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -45,7 +45,7 @@ def _digest(paths):
         with open(p, "rb") as f:
             h.update(os.path.relpath(p, ROOT).encode())  # relative: the digest must not depend on where the tree lives
             h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS).replace(ROOT, ".").encode())  # (the -I paths are absolute: keep the tree's location out)
     return h.hexdigest()
 
 
@@ -68,10 +68,24 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile every .cu to an object (in parallel) and link the shared library."""
+    """Compile every .cu to an object (in parallel) and link the shared library.  One builder at a time: the ranks of
+    a torchrun job that all find a stale library queue on a file lock and the late ones find it fresh."""
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
+    import fcntl
+
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     nvcc = _nvcc()
     srcs = _sources()
 
@@ -87,10 +101,12 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"]
+    tmp = LIB + ".tmp.%d" % os.getpid()  # link beside, then rename: a reader never sees a half-written library
+    cmd = [nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcuda", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    os.replace(tmp, LIB)
     with open(os.path.join(LIBDIR, "build.stamp"), "w") as f:
         f.write(_digest(srcs + _headers()))
     return LIB

@@ -328,7 +328,7 @@ class CudaOps:
         with torch.cuda.device(g.device):
             ws = self.F._ws(self.lib.gcnb_colsum_workspace_bytes(n, f), g.device)
             st = self.lib.gcnb_colsum(n, f, g.data_ptr(), g.stride(0) if n > 1 else f,
-                                      y.data_ptr() if y is not None else None, f,
+                                      y.data_ptr() if y is not None else None, (y.stride(0) if n > 1 else f) if y is not None else f,
                                       gm.data_ptr() if gm is not None else None, f, out.data_ptr(), ws.data_ptr(),
                                       ws.numel(), self._sp(g.device))
         self._lib.check(st, "gcnb_colsum")
@@ -336,6 +336,64 @@ class CudaOps:
 
     def empty(self, shape, like):
         return torch.empty(shape, dtype=torch.float32, device=like.device)
+
+    # -- the halo exchange through the library's own C ABI (csrc/dist.cu): one pack kernel + one grouped ncclSend /
+    # ncclRecv round on an NCCL communicator of ours, on a side stream so that the diagonal block's SpMM overlaps it
+    _halo_group = None  # (process group kept alive, ncclComm_t as int): one per process, made on first use (collective)
+
+    @classmethod
+    def halo_comm(cls, device):
+        if cls._halo_group is None:
+            pg = dist.new_group(backend="nccl")          # its own communicator: never interleaves with torch's collectives
+            t = torch.zeros(1, device=device)
+            dist.all_reduce(t, group=pg)                  # NCCL communicators are created lazily: force it now
+            torch.cuda.synchronize(device)
+            cls._halo_group = (pg, int(pg._get_backend(torch.device(device))._comm_ptr()))
+        return cls._halo_group[1]
+
+    def halo_create(self, plan, dgraph, device):
+        """gcnb_halo handle of a HaloPlan (rows to send grouped by destination rank, receive offsets into the compact
+        panel) + the side stream the exchange runs on.  None when NCCL could not be bound."""
+        if not self.lib.gcnb_halo_nccl_available():
+            return None
+        world, p = dgraph.world, dgraph.rank
+        i64 = ctypes.c_int64 * world
+        send = [int(plan.give[r].numel()) if r != p else 0 for r in range(world)]
+        recv = [int(plan.need[q].numel()) if q != p else 0 for q in range(world)]
+        offs = [int(plan.offset[q]) if q != p else 0 for q in range(world)]
+        rows = [plan.give[r].to(torch.int32) for r in range(world) if r != p and plan.give[r].numel()]
+        send_rows = torch.cat(rows).contiguous() if rows else torch.zeros(1, dtype=torch.int32, device=device)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            st = self.lib.gcnb_halo_create(p, world, i64(*send), send_rows.data_ptr(), i64(*recv), i64(*offs),
+                                           self._sp(device), ctypes.byref(h))
+        self._lib.check(st, "gcnb_halo_create")
+        import weakref
+
+        weakref.finalize(plan, self.lib.gcnb_halo_free, h)
+        return {"h": h, "comm": self.halo_comm(device), "stream": torch.cuda.Stream(device=device), "send_rows": sum(send)}
+
+    def halo_exchange_async(self, c, panel, compact):
+        """Pack on the current stream, exchange on the side stream; returns the event the consumer waits for."""
+        dev = panel.device
+        f = panel.shape[1]
+        main = torch.cuda.current_stream(dev)
+        sendbuf = torch.empty((max(c["send_rows"], 1), f), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = self.lib.gcnb_halo_pack(c["h"], panel.data_ptr(), panel.stride(0) if panel.shape[0] > 1 else f, f,
+                                         sendbuf.data_ptr(), self._sp(dev))
+            self._lib.check(st, "gcnb_halo_pack")
+            side = c["stream"]
+            side.wait_stream(main)                        # the packed rows (and the compact panel's allocation) are ready
+            sendbuf.record_stream(side)
+            compact.record_stream(side)
+            with torch.cuda.stream(side):
+                st = self.lib.gcnb_halo_exchange(c["h"], ctypes.c_void_p(c["comm"]), sendbuf.data_ptr(), f, compact.data_ptr(),
+                                                 ctypes.c_void_p(side.cuda_stream))
+                self._lib.check(st, "gcnb_halo_exchange")
+                done = torch.cuda.Event()
+                done.record(side)
+        return done
 
     # -- build-time helpers of the halo exchange (HaloPlan): blocks as CSR tensors and back
     def block_csr(self, block):
@@ -578,6 +636,9 @@ class HaloPlan:
         self.block = ops.block_from_csr(rowptr, new_col, val, n_p, self.n_compact)
         self.rows_received = off - self.own
         self.rows_all_gather = (world - 1) * pad
+        # the product path: the library's own exchange (gcnb_halo_*, csrc/dist.cu) over an NCCL communicator of its own;
+        # backends without it (the numpy backend of the CPU tests) use torch.distributed's grouped send / recv below
+        self.c = ops.halo_create(self, dgraph, col.device) if hasattr(ops, "halo_create") and world > 1 else None
 
 
 def dist_spmm_halo(ops, dgraph, plan, diag, panel, bias=None, relu=False, group=None):
@@ -588,6 +649,14 @@ def dist_spmm_halo(ops, dgraph, plan, diag, panel, bias=None, relu=False, group=
     p, world = dgraph.rank, dgraph.world
     out = ops.empty((dgraph.n_rows(), f), panel)
     compact = ops.empty((plan.n_compact, f), panel)
+    if getattr(plan, "c", None) is not None:
+        done = ops.halo_exchange_async(plan.c, panel, compact)      # pack kernel + grouped ncclSend / ncclRecv, side stream
+        if dgraph.split:
+            ops.spmm_block(diag, panel, out, False)                 # runs while the halo rows are on the wire
+        else:
+            compact[: panel.shape[0]].copy_(panel)                  # own slot at the front of the compact panel
+        torch.cuda.current_stream(panel.device).wait_event(done)
+        return ops.spmm_block(plan.block, compact, out, dgraph.split, bias, relu)
     sends, p2p = [], []
     for k in range(1, world):
         r = (p + k) % world
@@ -671,7 +740,7 @@ def exchanged_spmm(ops, dgraph, transpose, panel, exch, bias=None, relu=False, g
             b4 = ops.empty((f4,), panel)
             b4.zero_()
             b4[:f].copy_(bias)
-        return exchanged_spmm(ops, dgraph, transpose, wide, exch, b4, relu, group)[:, :f]
+        return exchanged_spmm(ops, dgraph, transpose, wide, exch, b4, relu, group)[:, :f].contiguous()
     if dgraph.world == 1:
         out = ops.empty((n_p, f), panel)
         return ops.spmm_block(diag, panel, out, False, bias, relu)
@@ -1049,8 +1118,8 @@ def bench_main(args, wl):
                     errs["dist_vs_fp64"][nm] = nerr(a_.double(), d_)
                     errs["single_gpu_vs_fp64"][nm] = nerr(s__.double(), d_)
                     errs["dist_vs_single_gpu"][nm] = nerr(a_, s__)
-            okv = torch.tensor([1.0 if all(v <= max(1e-5, 2 * errs["single_gpu_vs_fp64"][k]) for k, v in errs["dist_vs_fp64"].items())
-                                else 0.0], device=dev)
+            okv = torch.tensor([1.0 if errs["dist_vs_fp64"]["out"] <= 1e-5 and all(
+                v <= max(1e-5, 2 * errs["single_gpu_vs_fp64"][k]) for k, v in errs["dist_vs_fp64"].items()) else 0.0], device=dev)
             worst = torch.tensor([max(errs["dist_vs_fp64"].values())], device=dev, dtype=torch.float64)
             dist.all_reduce(okv, op=dist.ReduceOp.MIN)
             dist.all_reduce(worst, op=dist.ReduceOp.MAX)

@@ -168,7 +168,13 @@ def test_models_generator_forward_backward(both, inputs, capsys):
     outs = []
     with torch.autograd.set_detect_anomaly(True):
         for m in (ms, md, m64):
-            h = m.MLPLayers.register_forward_hook(lambda mod, inp, out: captured.append(out.detach().clone()))
+            orig = m.MLPLayers.forward  # (models.py:370 calls .forward directly: module hooks do not fire)
+
+            def spy(inp, orig=orig):
+                out = orig(inp)
+                captured.append(out.detach().clone())
+                return out
+            m.MLPLayers.forward = spy
             if m is m64:
                 with double_default():
                     o = m(x.double(), adj.double())
@@ -176,7 +182,7 @@ def test_models_generator_forward_backward(both, inputs, capsys):
             else:
                 o = m(x, adj)
                 o.sum().backward(retain_graph=True)
-            h.remove()
+            m.MLPLayers.forward = orig
             assert o.shape == (N, 1)
             outs.append(o)
     capsys.readouterr()  # models.py:371 prints statistics

@@ -40,9 +40,11 @@ def main():
     dgs = D.DistGraph.from_graph(full, rank, world, split=True, bounds=dgu.bounds)
     r0, r1 = dgu.bounds[rank], dgu.bounds[rank + 1]
     for exchange in os.environ.get("GCNB_DIST_CHECK_EXCHANGES", "nccl,halo,peer").split(","):
-        for fin, fout in ((64, 32), (32, 96)):
+        for fin, fout in ((64, 32), (32, 96), (64, 47)):  # (47: panel rows padded to 16 bytes for the exchange)
             for dgraph, what in ((dgu, "unsplit"), (dgs, "split")):
-                if exchange == "peer" and (what == "split" or fin < fout):
+                if (fin, fout) == (64, 47) and what == "unsplit":
+                    continue
+                if exchange == "peer" and (what == "split" or fin < fout or fout % 4):
                     continue  # the peer exchange consumes per-source blocks of the unsplit row block, reference order
                 x = torch.randn(n, fin, generator=gen, device=dev)
                 g = torch.randn(n, fout, generator=gen, device=dev)
@@ -68,7 +70,14 @@ def main():
                     "dW": ((layer.inner.weight.grad - ref.weight.grad).abs().max() / ref.weight.grad.abs().max()).item(),
                     "db": ((layer.inner.bias.grad - ref.bias.grad).abs().max() / ref.bias.grad.abs().max()).item(),
                 }
-                good = all(v < 2e-5 for v in errs.values())  # (dW / db: sums over ranks in another order)
+                # out / dX to the layer's bar.  dW / db: a ReLU output within rounding of zero may flip its mask between
+                # the two evaluations, and one flipped entry of G moves a column sum of ~sqrt(N) by ~1 / sqrt(N): allow
+                # a few flips (they show as 1e-3-sized errors; a wrong exchange or a missing all-reduce shows as O(1))
+                flips = ((out > 0) != (o_ref[r0:r1] > 0)).sum()
+                dist.all_reduce(flips)
+                slack = 2e-5 + float(flips.item()) * 4.0 / (n ** 0.5)
+                good = errs["out"] < 2e-5 and errs["dX"] < max(2e-5, slack) and errs["dW"] < slack and errs["db"] < slack
+                errs["mask_flips"] = float(flips.item())
                 ok = ok and good
                 # CUDA-graph replay of the step (kernels + NCCL sends / receives / all-reduce), then timing (fresh leaf:
                 # an AccumulateGrad node born on the default stream would pull the legacy stream into the capture)

@@ -8,3 +8,6 @@ timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 \
   bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_products_n${N}.json 2> gpurun_out/r2_bench_products_n${N}.err
 tail -c 1500 gpurun_out/r2_bench_products_n${N}.err; head -c 3000 gpurun_out/r2_bench_products_n${N}.json
+if [ "$N" = 2 ]; then
+  timeout 200 python tools/debug_ref_models.py > gpurun_out/r2_debug_ref_models.txt 2>&1; tail -12 gpurun_out/r2_debug_ref_models.txt | cut -c1-200
+fi

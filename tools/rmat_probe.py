@@ -2,7 +2,7 @@
 with the vertex labels as generated, relabelled by descending degree, or shuffled -- what the locality of the row /
 column order is worth.  Development tool; also the command ncu wraps (one width, one relabelling).
 
-    python tools/rmat_probe.py [--widths 256,100,48] [--relabel none,degree,random] [--bf16] [--reps 5] [--workload products]
+    python tools/rmat_probe.py [--widths 256,100,48] [--relabel none,degree,random,rows] [--bf16] [--reps 5] [--workload products]
                                [--sweep stream:hot_mb:hint:batch,...]   e.g. 0:0:0:0,2:48:0:0,2:96:2:8  (batch = gathered rows in flight per lane: 0 auto, 2 / 4 / 8)
 --sweep: every configuration of the streaming kernel (gcnb_set_tuning: GCNB_TUNE_SPMM_STREAM, _HOT_MB, _HINT, _BATCH) in
 one process on the same graph; --fwd-only skips the transposed launch; --check compares with torch's CUDA CSR product.
@@ -48,6 +48,15 @@ def main():
             newid = torch.randperm(n, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
             src, dst = newid[src], newid[dst]
         graph = P.Graph.from_edges(src.int(), dst.int(), n)
+        if how == "rows":  # rows processed in order of descending length, columns (= the panel) left as they are
+            coo = graph.to_sparse_coo()
+            idx, val = coo._indices(), coo._values()
+            deg = torch.bincount(idx[0], minlength=n)
+            order = torch.argsort(deg, descending=True, stable=True)
+            newrow = torch.empty_like(order)
+            newrow[order] = torch.arange(n, device=dev)
+            graph = P.Graph.from_torch(torch.sparse_coo_tensor(torch.stack([newrow[idx[0]], idx[1]]), val, (n, n)))
+            del coo, idx, val
         print("relabel=%s graph %r bins %s long_chunks %d max_degree %d" % (how, graph, graph.bin_rows, graph.n_long_chunks,
                                                                             graph.max_degree), flush=True)
         for f in widths:
