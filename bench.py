@@ -766,6 +766,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the brief runs of the other single-GPU configs")
+    ap.add_argument("--quick", action="store_true", help="N > 1: device-timed step only (no end-to-end loop, no parity gate): tuning runs")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -1430,11 +1430,8 @@ int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t
   // keep the packed B resident when it costs no occupancy (<= 40 KB on top of the 64 KB of A stages)
   const int b_resident = ((size_t)p.nkb * 2 * p.npad * 128 <= 40 * 1024) ? 1 : 0;
   const uint32_t smem = smem_layout(p.npad, &L, b_resident ? p.nkb : 2) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GCNB_CUDA(cudaFuncSetAttribute(gemm_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  // (the opt-in is per device and cheap: set it before every launch rather than remember it per process)
+  GCNB_CUDA(cudaFuncSetAttribute(gemm_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int64_t m_tiles = ceil_div(m, BM);
   const int vec_ok_ = (ldc % 4 == 0) && aligned16(c) && (p.npad % 4 == 0);
   if (b_resident && rows_kernel_choice() >= 1) {
@@ -1443,11 +1440,7 @@ int gemm_tc_rows_launch(int64_t m, int64_t n, int64_t k, const float* a, int64_t
     int ns = (int)((200 * 1024 - b_total) / (2 * kTileBytes));
     if (ns > 4) ns = 4;
     const uint32_t smem_ws = (uint32_t)(ns * 2 * kTileBytes + ((b_total + 1023) & ~(size_t)1023) + 1024 + 1024);
-    static bool ws_attr = false;
-    if (!ws_attr) {
-      GCNB_CUDA(cudaFuncSetAttribute(gemm_tc_rows_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      ws_attr = true;
-    }
+    GCNB_CUDA(cudaFuncSetAttribute(gemm_tc_rows_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int64_t gxw = kNumSMs / p.n_tiles;
     if (gxw < 1) gxw = 1;
     if (gxw > m_tiles) gxw = m_tiles;
@@ -1523,12 +1516,8 @@ int gemm_tc_tn_launch(int64_t m, int64_t n, int64_t r, const float* x, int64_t l
   dim3 grid((unsigned)p.splits, (unsigned)p.m_tiles);
 #define GCNB_TN_LAUNCH(NBQ_, MN_)                                                                                  \
   do {                                                                                                             \
-    static bool attr_set = false;                                                                                  \
-    if (!attr_set) {                                                                                               \
-      GCNB_CUDA(cudaFuncSetAttribute(gemm_tc_tn_kernel<NBQ_, MN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                     227 * 1024));                                                                 \
-      attr_set = true;                                                                                             \
-    }                                                                                                              \
+    GCNB_CUDA(cudaFuncSetAttribute(gemm_tc_tn_kernel<NBQ_, MN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                   227 * 1024));                                                                   \
     gemm_tc_tn_kernel<NBQ_, MN_><<<grid, kThreads, smem, st>>>(r, (int)m, (int)n, x, ldx, y, ldy, dst, dst_ld,     \
                                                                stride, p.rows_per_split, p.npad,                   \
                                                                tmem_cols_for(p.npad), vec_ok);                     \

@@ -65,6 +65,36 @@ def partition_rows_by_nnz(rowptr, world, row_weight=0.0):
     return bounds
 
 
+def balanced_node_partition(row_len, world):
+    """A 1-D partition of the NODES in which every block holds the same number of rows AND (nearly) the same number of
+    stored entries: nodes sorted by row length, dealt to the ranks in snake order (0 .. P-1, P-1 .. 0, ...), each
+    rank's nodes kept in ascending id order.
+
+    Contiguous row blocks cannot give both on a power-law graph (products-shaped R-MAT, 2 ranks: the block with half
+    the entries holds 30 % of the rows), and the layer step alternates phases that scale with rows (dense products,
+    element-wise passes) and with entries (SpMMs), separated by exchanges that synchronise the ranks -- so the step
+    costs the sum over phases of the slowest rank, and a partition that balances only the total helps nobody
+    (profiles/r02_dist_tune_n2.txt: 33 ms at 2 GPUs against 35 ms at one).
+
+    row_len: 1-D integer tensor [N] (any device).  Returns (new_id int64 [N]: node i becomes row new_id[i] of the
+    relabelled graph; bounds [world + 1]: rank p owns relabelled rows bounds[p] .. bounds[p + 1])."""
+    rl = torch.as_tensor(row_len).to(torch.int64)
+    n = rl.numel()
+    order = torch.argsort(rl, descending=True, stable=True)
+    k = torch.arange(n, device=rl.device)
+    lap, pos = torch.div(k, world, rounding_mode="floor"), k % world
+    owner_sorted = torch.where(lap % 2 == 0, pos, world - 1 - pos)
+    owner = torch.empty(n, dtype=torch.int64, device=rl.device)
+    owner[order] = owner_sorted
+    counts = torch.bincount(owner, minlength=world)
+    bounds = [0] + [int(v) for v in torch.cumsum(counts, 0).cpu()]
+    # within a rank: ascending original id (a stable sort of the owners keeps it)
+    by_owner = torch.argsort(owner, stable=True)
+    new_id = torch.empty(n, dtype=torch.int64, device=rl.device)
+    new_id[by_owner] = k
+    return new_id, bounds
+
+
 def exchange_phases(rank, world):
     """Consumption order of the source ranks for the pipelined exchange, grouped into phases:
     [[p], [p+1, p+2], [p+3, p+4], ..., [last]] (mod world).  One SpMM per phase: this rank's own slot
@@ -926,6 +956,7 @@ def bench_main(args, wl):
     # cost of a row against a stored entry when cutting the row blocks: the dense products and element-wise passes
     # scale with rows, the SpMMs with entries (products-shaped 3-layer step on one GPU: ~0.33 ns per entry, ~4 ns per row)
     row_weight = float(os.environ.get("GCNB_DIST_ROW_WEIGHT", "12" if layers_n > 1 else "0"))
+    balance = os.environ.get("GCNB_DIST_BALANCE", "1") == "1"  # balanced_node_partition instead of contiguous row blocks
     split_env = os.environ.get("GCNB_DIST_SPLIT", "auto")
     split = None if split_env == "auto" else split_env == "1"
 
@@ -946,12 +977,25 @@ def bench_main(args, wl):
             exchange = "nccl"  # uniform graph: a rank reads ~96 % of every slot (tools/halo_fraction.py)
     else:
         src, dst, n_global = B.make_edges(torch, wl, 0)      # CPU generator, same seed on every rank: the single-GPU arm's graph
-        full = P.Graph.from_edges(src.to(dev), dst.to(dev), n_global)
-        del src, dst
-        if split is None and exchange in ("auto", "halo"):
-            split = True  # the diagonal block's SpMM runs while the halo rows are on the wire
-        dgraph = DistGraph.from_graph(full, rank, world, split=split, row_weight=row_weight)
+        src, dst = src.to(dev), dst.to(dev)
+        full = P.Graph.from_edges(src, dst, n_global)        # kept for the parity gate (the single-GPU layer on this GPU)
         nnz_global = full.nnz
+        if split is None and exchange in ("auto", "halo"):
+            split = False  # one pass over [own rows | halo rows] (profiles/r02_dist_tune_n2.txt: 33.2 vs 33.4 ms split)
+        if balance:
+            # nodes dealt to the ranks by row length: every rank owns N / P rows and ~nnz / P stored entries; the graph
+            # is rebuilt with the nodes renumbered rank by rank (same entries, same values), rank p owns new rows
+            # bounds[p] .. bounds[p + 1] = the original nodes `mine`
+            rp = full.csr()[0].long()
+            new_id, bounds = balanced_node_partition(rp[1:] - rp[:-1], world)
+            relabelled = P.Graph.from_edges(new_id[src.long()].int(), new_id[dst.long()].int(), n_global)
+            dgraph = DistGraph.from_graph(relabelled, rank, world, bounds=bounds, split=split)
+            mine = torch.argsort(new_id)[bounds[rank]:bounds[rank + 1]].cpu()  # original ids of this rank's rows, in row order
+            del relabelled, rp
+        else:
+            dgraph = DistGraph.from_graph(full, rank, world, split=split, row_weight=row_weight)
+            mine = torch.arange(dgraph.bounds[rank], dgraph.bounds[rank + 1])
+        del src, dst
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
     r0, r1 = dgraph.bounds[rank], dgraph.bounds[rank + 1]
@@ -972,7 +1016,7 @@ def bench_main(args, wl):
     else:            # the single-GPU arm's X and G, this rank's rows
         x_full = torch.randn(n_global, dims[0], generator=gen.manual_seed(1))
         g_full = torch.randn(n_global, dims[-1], generator=gen.manual_seed(2))
-        x_host, g_host = x_full[r0:r1].clone().pin_memory(), g_full[r0:r1].clone().pin_memory()
+        x_host, g_host = x_full[mine].clone().pin_memory(), g_full[mine].clone().pin_memory()
     x, g = x_host.to(dev), g_host.to(dev)
 
     def run(xx, gg):
@@ -1087,8 +1131,10 @@ def bench_main(args, wl):
         torch.cuda.synchronize()
         return time.perf_counter() - t0
 
-    e2e_loop(2)
-    e2e_t = torch.tensor([e2e_loop(args.steps)], device=dev, dtype=torch.float64)
+    quick = bool(getattr(args, "quick", False))
+    if not quick:
+        e2e_loop(2)
+    e2e_t = torch.tensor([e2e_loop(args.steps) if not quick else float("nan")], device=dev, dtype=torch.float64)
     dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = layers_n * nnz_global / (e2e_t.item() / args.steps)
     del bufs
@@ -1099,7 +1145,7 @@ def bench_main(args, wl):
     # of this package on the whole graph and (b) an fp64 run of the reference's lines, both on this GPU.  Rule as in
     # the single-GPU arm: error against fp64 <= max(1e-5, 2 x the single-GPU step's error against fp64).
     parity = None
-    if not partitioned:
+    if not partitioned and not quick:
         try:
             o_d = step_eager().detach().clone()
             g_d = [(l.inner.weight.grad.clone(), l.inner.bias.grad.clone()) for l in layers]
@@ -1111,8 +1157,9 @@ def bench_main(args, wl):
 
             def nerr(a, b):
                 return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
-            errs = {"dist_vs_fp64": {"out": nerr(o_d.double(), o64[r0:r1])}, "single_gpu_vs_fp64": {"out": nerr(o_s[r0:r1].double(), o64[r0:r1])},
-                    "dist_vs_single_gpu": {"out": nerr(o_d, o_s[r0:r1])}}
+            rows_ = mine.to(dev)
+            errs = {"dist_vs_fp64": {"out": nerr(o_d.double(), o64[rows_])}, "single_gpu_vs_fp64": {"out": nerr(o_s[rows_].double(), o64[rows_])},
+                    "dist_vs_single_gpu": {"out": nerr(o_d, o_s[rows_])}}
             for i, ((dw, db), (sw, sb), (w64, b64)) in enumerate(zip(g_d, g_s, g64), 1):
                 for nm, a_, s__, d_ in (("dW%d" % i, dw, sw, w64), ("db%d" % i, db, sb, b64)):
                     errs["dist_vs_fp64"][nm] = nerr(a_.double(), d_)
@@ -1160,7 +1207,10 @@ def bench_main(args, wl):
     alg = B.algorithmic_bytes_spmm(blk.nnz, n_local, fw)
     if rank == 0:
         cfg = B.config_of(wl, nnz_global, n_global)
-        cfg.update({"partition": "1-D row blocks, cost = stored entries + %g x rows" % row_weight, "bounds": dgraph.bounds,
+        cfg.update({"partition": ("1-D partition of the nodes, dealt by row length: equal rows and ~equal stored entries per rank "
+                                  "(dist.balanced_node_partition)" if (balance and not partitioned) else
+                                  "1-D contiguous row blocks, cost = stored entries + %g x rows" % row_weight),
+                    "bounds": dgraph.bounds,
                     "row_block_split": dgraph.split, "exchange": resolved, "cuda_graph": cg is not None,
                     "graph_build_s": build_s, "l2": "flushed between timed steps (512 MiB write)",
                     "association": [o for (_, _, _, o) in B.spmm_plan(dims)], "halo": halo,

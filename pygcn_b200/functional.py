@@ -394,9 +394,9 @@ def gcn_layer(input, adj, weight, bias=None, relu=False, precision="auto", dropo
     if input.dim() == 3:  # [B, N, Fin]: the batch shares the adjacency (pygcn/models.py:343-349)
         if dropout_mask is not None:
             raise NotImplementedError("the fused dropout mask is not available for batched input")
-        _check_layer_args(input[0], graph, weight, bias)
         if input.shape[0] == 0:
             return input.new_empty((0, graph.n_rows, weight.shape[1]))
+        _check_layer_args(input[0], graph, weight, bias)
         return _GCNLayerBatchedFn.apply(input, weight, bias, graph, bool(relu), _PRECISIONS[precision])
     _check_layer_args(input, graph, weight, bias)
     if precision == "bf16" and not graph.dense_route:

@@ -77,7 +77,7 @@ def average_visits(poi_cbg_visits_list):
     return avg
 
 
-def load_adj_files(msa_name, mob_data_root, output_root, device, msa_name_full=None, product=None, save=True):
+def load_adj_files(msa_name, mob_data_root, output_root, device, msa_name_full=None, product=None, save=False):
     """`utils.load_adj(msa_name, mob_data_root, output_root)` (pygcn/utils.py:93-132) with its three file levels, the
     O(N^2 M) double loop replaced by the device product: returns (adj fp32 [n_cbg, n_cbg] on `device`, n_cbg).
 
@@ -85,8 +85,9 @@ def load_adj_files(msa_name, mob_data_root, output_root, device, msa_name_full=N
       2. else `<output_root>/avg_array_<msa>.npy`      -> adj = avg^T avg on the device (functional.load_adj);
       3. else `<mob_data_root>/<msa>/<full name>_2020-03-01_to_2020-05-02.pkl` -> average (utils.py:116-120), saved as
          avg_array_<msa>.npy like utils.py:121, then 2.
-    With save=True the adjacency is written to adj_<msa>.npy in float64 like utils.py:129 does, so the reference's own
-    loader finds it.  `msa_name_full` replaces the reference's constants.MSA_NAME_FULL_DICT lookup (utils.py:99; that
+    save=True (off by default) also writes the results back: avg_array_<msa>.npy like utils.py:121, and the adjacency under
+    its OWN name adj_<msa>.gcnb200.npy -- never the reference's cache adj_<msa>.npy, which the reference trusts as its
+    fp64 double-loop result (this product is an fp32 / 3xTF32 device product, ~1e-6 from it and not bit-symmetric).  `msa_name_full` replaces the reference's constants.MSA_NAME_FULL_DICT lookup (utils.py:99; that
     table lives outside this path).  `product(avg fp32 device tensor) -> adj` defaults to functional.load_adj."""
     dev = torch.device(device)
     adj_path = os.path.join(output_root, "adj_%s.npy" % msa_name)
@@ -113,5 +114,5 @@ def load_adj_files(msa_name, mob_data_root, output_root, device, msa_name_full=N
         from .functional import load_adj as product
     adj = product(torch.from_numpy(np.ascontiguousarray(avg, dtype=np.float32)).to(dev))
     if save:
-        np.save(adj_path, adj.detach().cpu().numpy().astype(np.float64))
+        np.save(os.path.join(output_root, "adj_%s.gcnb200.npy" % msa_name), adj.detach().cpu().numpy().astype(np.float64))
     return adj, int(avg.shape[1])

@@ -38,6 +38,8 @@ class GraphConvolution(Module):
         self.out_features = out_features
         self.fuse_relu = fuse_relu
         self.dropout = dropout
+        if dropout and precision == "bf16":
+            raise ValueError("the fused dropout mask is not available in the bf16 panel tier (precision='bf16')")
         self.precision = precision
         self.association = association
         self.weight = Parameter(torch.empty(in_features, out_features, dtype=torch.float32))
@@ -61,7 +63,10 @@ class GraphConvolution(Module):
         pygcn/models.py:343-349) -> [B, N, out_features]."""
         p = getattr(self, "dropout", 0.0)
         mask = None
-        if p > 0.0 and self.training and input.dim() == 2:
+        if p > 0.0 and self.training and input.dim() != 2:
+            raise NotImplementedError("dropout > 0 with batched input [B, N, F]: the fused mask is per [N, F] output "
+                                      "(apply F.dropout to the result, or call the layer per sample)")
+        if p > 0.0 and self.training:
             n_rows = adj.shape[0]
             mask = torch.rand(n_rows, self.out_features, device=input.device) >= p
         return gcn_layer(input, adj, self.weight, self.bias, relu=getattr(self, "fuse_relu", False),

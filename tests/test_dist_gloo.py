@@ -188,6 +188,32 @@ def test_aggregate_first_rule_of_the_partitioned_layer():
     assert not D.aggregate_first(5, 9, False)  # rows of X must be 16-byte aligned
 
 
+def test_balanced_node_partition_gives_equal_rows_and_entries():
+    """dist.balanced_node_partition on power-law row lengths: a permutation; every rank owns N / P rows (+- 1) and a
+    share of the stored entries within one long row of the mean; nodes of a rank stay in ascending id order."""
+    rs = np.random.default_rng(9)
+    n = 5000
+    rl = (rs.pareto(1.2, n) * 3).astype(np.int64) + 1
+    rl[7] = 20000
+    for world in (1, 2, 3, 8):
+        new_id, bounds = D.balanced_node_partition(torch.from_numpy(rl), world)
+        new_id = new_id.numpy()
+        assert sorted(new_id.tolist()) == list(range(n)) and bounds[0] == 0 and bounds[-1] == n and len(bounds) == world + 1
+        rows = np.diff(bounds)
+        assert rows.max() - rows.min() <= 1
+        owner = np.searchsorted(np.asarray(bounds), new_id, side="right") - 1
+        ent = np.bincount(owner, weights=rl, minlength=world)
+        assert ent.max() - ent.min() <= rl.max()  # the one 20000-entry row cannot be split: everything else evens out
+        rl2 = np.minimum(rl, 300)  # without a row that outweighs a whole share, the entries even out to a few rows' worth
+        nid2, b2 = D.balanced_node_partition(torch.from_numpy(rl2), world)
+        own2 = np.searchsorted(np.asarray(b2), nid2.numpy(), side="right") - 1
+        ent2 = np.bincount(own2, weights=rl2, minlength=world)
+        assert ent2.max() - ent2.min() <= 2 * rl2.max()
+        for p in range(world):
+            ids = np.nonzero(owner == p)[0]
+            assert (np.diff(new_id[ids]) > 0).all()  # ascending ids -> ascending rows inside a rank
+
+
 def test_exchange_phases_cover_every_source_once_own_slot_first():
     for world in (1, 2, 3, 4, 5, 8, 16):
         for rank in range(world):

@@ -75,17 +75,22 @@ def test_load_adj_files_walks_the_three_levels_of_utils_load_adj(tmp_path, golde
 
     with pytest.raises(ValueError):
         IO.load_adj_files("SanFrancisco", str(root), str(out), "cpu", product=product)  # no full name for the pickle
-    adj, n = IO.load_adj_files("SanFrancisco", str(root), str(out), "cpu", msa_name_full=full, product=product)
-    assert n == c["adj"].shape[0] and adj.dtype == torch.float32 and calls == [tuple(c["hours"].shape[1:])]
+    adj0, _ = IO.load_adj_files("SanFrancisco", str(root), str(out), "cpu", msa_name_full=full, product=product)
+    assert sorted(os.listdir(out)) == []  # the default leaves the reference's cache directory untouched
+    adj, n = IO.load_adj_files("SanFrancisco", str(root), str(out), "cpu", msa_name_full=full, product=product, save=True)
+    assert torch.equal(adj, adj0)
+    assert n == c["adj"].shape[0] and adj.dtype == torch.float32 and calls == [tuple(c["hours"].shape[1:])] * 2
     assert O.normwise_err(adj.numpy(), c["adj"]) < 1e-5
     avg_o, _ = O.cbg_adjacency(c["hours"])
     assert np.array_equal(np.load(out / "avg_array_SanFrancisco.npy"), avg_o)       # utils.py:116-121, float64
-    assert np.load(out / "adj_SanFrancisco.npy").dtype == np.float64               # utils.py:123,129
+    # the device product is saved under its own name: adj_<msa>.npy stays the reference's fp64 double-loop cache
+    assert np.load(out / "adj_SanFrancisco.gcnb200.npy").dtype == np.float64 and not os.path.exists(out / "adj_SanFrancisco.npy")
+    np.save(out / "adj_SanFrancisco.npy", c["adj"])                                 # (what the reference itself writes, utils.py:129)
     adj1, n1 = IO.load_adj_files("SanFrancisco", "/nonexistent", str(out), "cpu", product=product)  # level 1: cache hit
-    assert n1 == n and torch.equal(adj1, adj) and len(calls) == 1
+    assert n1 == n and O.normwise_err(adj1.numpy(), c["adj"]) < 1e-6 and len(calls) == 2
     os.remove(out / "adj_SanFrancisco.npy")
     adj2, _ = IO.load_adj_files("SanFrancisco", "/nonexistent", str(out), "cpu", product=product, save=False)  # level 2
-    assert torch.equal(adj2, adj) and len(calls) == 2 and not os.path.exists(out / "adj_SanFrancisco.npy")
+    assert torch.equal(adj2, adj) and len(calls) == 3 and not os.path.exists(out / "adj_SanFrancisco.npy")
     assert np.array_equal(IO.average_visits(hours), avg_o)
     with pytest.raises(ValueError):
         IO.average_visits([])
