@@ -1178,6 +1178,21 @@ def bench_main(args, wl):
             parity = {"ok": False, "error": repr(e)}
         torch.cuda.empty_cache()
 
+    if partitioned and not quick:
+        # no GPU holds the whole graph: the gate is what a row-normalised adjacency must satisfy at any size -- every row
+        # of A sums to one, through the real exchange (a panel of ones) and the real row block
+        try:
+            ones = torch.ones(n_local, 4, device=dev)
+            rs = exchanged_spmm(CudaOps(), dgraph, False, ones, "nccl")
+            dev_max = torch.tensor([(rs - 1).abs().max().item()], device=dev, dtype=torch.float64)
+            dist.all_reduce(dev_max, op=dist.ReduceOp.MAX)
+            parity = {"ok": bool(dev_max.item() < 1e-5), "what": "max |rowsum(A) - 1| over all ranks through the exchanged SpMM",
+                      "row_sums_max_deviation": dev_max.item(), "tolerance": 1e-5}
+            del ones, rs
+        except Exception as e:  # pragma: no cover
+            parity = {"ok": False, "error": repr(e)}
+        torch.cuda.empty_cache()
+
     # ---- the exchange alone and the dominant SpMM alone on this rank, at the widest panel of the model
     fw = max(f for (_, f, _, _) in B.spmm_plan(dims))
     ops = CudaOps()
