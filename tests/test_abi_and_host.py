@@ -76,7 +76,8 @@ def test_tuning_knobs_validate_their_values(lib):
                                (_lib.TUNE_STREAM_HOT_MB, (0, 48, 126), (-1, 127)),
                                (_lib.TUNE_STREAM_HINT, (0, 1, 2), (-1, 3)),
                                (_lib.TUNE_STREAM_MIN_ROW_BYTES, (16, 256, 1024), (8, 2048)),
-                               (_lib.TUNE_STREAM_BATCH, (0, 2, 4, 8), (3, 16))):
+                               (_lib.TUNE_STREAM_BATCH, (0, 2, 4, 8), (3, 16)),
+                               (_lib.TUNE_STREAM_ORDER, (0, 1), (-1, 2))):
             for v in good:
                 assert lib.gcnb_set_tuning(key, v) == 0, (key, v, _lib.last_error())
             for v in bad:
@@ -91,6 +92,31 @@ def test_tuning_knobs_validate_their_values(lib):
         lib.gcnb_set_tuning(_lib.TUNE_STREAM_HINT, 0)
         lib.gcnb_set_tuning(_lib.TUNE_STREAM_MIN_ROW_BYTES, 256)
         lib.gcnb_set_tuning(_lib.TUNE_STREAM_BATCH, 0)
+        lib.gcnb_set_tuning(_lib.TUNE_STREAM_ORDER, 0)
+
+
+def test_halo_plan_entry_points_validate_on_the_host(lib):
+    """gcnb_halo_create (the exchange step of the row-partitioned layer, csrc/dist.cu): argument checks run before any
+    CUDA call, an empty plan needs no device memory, NCCL is bound at run time (the library has no link-time
+    dependency on it: `ldd` must not list libnccl)."""
+    import ctypes
+    import subprocess
+
+    from pygcn_b200 import _lib
+
+    i64 = ctypes.c_int64 * 3
+    h = ctypes.c_void_p()
+    assert lib.gcnb_halo_create(1, 3, i64(0, 0, 0), None, i64(0, 0, 0), i64(0, 0, 0), None, ctypes.byref(h)) == 0
+    assert lib.gcnb_halo_send_rows(h) == 0 and lib.gcnb_halo_recv_rows(h) == 0
+    assert lib.gcnb_halo_pack(h, None, 8, 8, None, None) == 0  # nothing to send: a no-op
+    lib.gcnb_halo_free(h)
+    for args in ((3, 3, i64(0, 0, 0)), (0, 3, i64(5, 0, 0)), (0, 3, i64(0, -1, 0))):  # bad rank; rows to itself; negative
+        assert lib.gcnb_halo_create(args[0], args[1], args[2], None, i64(0, 0, 0), i64(0, 0, 0), None, ctypes.byref(h)) != 0
+        assert "halo_create" in _lib.last_error()
+    assert lib.gcnb_halo_exchange(None, None, None, 8, None, None) != 0 and "halo_exchange" in _lib.last_error()
+    assert lib.gcnb_halo_nccl_available() in (0, 1)
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libnccl" not in out
 
 
 def test_fresh_bn_entry_points_validate_before_launching(lib):

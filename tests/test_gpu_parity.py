@@ -437,6 +437,7 @@ def spmm_kernel(P, request):
         _lib.check(lib.gcnb_set_tuning(_lib.TUNE_STREAM_BATCH, max(variant, 0)), "set_tuning")
         _lib.check(lib.gcnb_set_tuning(_lib.TUNE_STREAM_HINT, {2: 2, 4: 1, 8: 0}.get(variant, 0)), "set_tuning")
         _lib.check(lib.gcnb_set_tuning(_lib.TUNE_STREAM_HOT_MB, 1), "set_tuning")  # small graphs: some hot, some cold columns
+        _lib.check(lib.gcnb_set_tuning(_lib.TUNE_STREAM_ORDER, 1 if variant == 4 else 0), "set_tuning")  # sorted item order
     else:
         _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_STREAM, 0 if name != "auto" else 1), "set_tuning")
         _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_KERNEL, _KERNELS[name]), "set_tuning")
@@ -448,6 +449,7 @@ def spmm_kernel(P, request):
     lib.gcnb_set_tuning(_lib.TUNE_STREAM_BATCH, 0)
     lib.gcnb_set_tuning(_lib.TUNE_STREAM_HINT, 0)
     lib.gcnb_set_tuning(_lib.TUNE_STREAM_HOT_MB, 48)
+    lib.gcnb_set_tuning(_lib.TUNE_STREAM_ORDER, 0)
 
 
 @pytest.mark.parametrize("spmm_kernel", ["auto", "rows", "group", "tma", ("group", 0), ("group", 1), ("group", 2), ("group", 3),
@@ -1064,6 +1066,44 @@ def test_row_partition_blocks_emulated_on_one_gpu(P, world):
         o2.backward(g)
         assert torch.equal(o2, ref_out) and torch.allclose(xt2.grad, xt.grad, rtol=0, atol=0)
         assert torch.equal(dl.inner.weight.grad, layer.weight.grad)
+
+
+def test_halo_pack_and_gemm_ex_through_the_c_abi(P):
+    """Two entry points of round 2 called directly: gcnb_halo_pack (rows every peer reads -> one send buffer, vector
+    and scalar copies) and gcnb_gemm_ex (product + bias + ReLU; the TMA-fed tcgen05 kernel's fused epilogue on the big
+    shape, the in-place pass on the small one)."""
+    import ctypes
+
+    from pygcn_b200 import _lib
+
+    lib = _lib.load()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    gen = torch.Generator(device=dev()).manual_seed(3)
+    for f, ld in ((256, 256), (100, 104), (47, 47)):
+        panel = torch.randn(5000, ld, generator=gen, device=dev())
+        rows = [torch.randint(0, 5000, (k,), generator=gen, device=dev(), dtype=torch.int32) for k in (700, 0, 1234)]
+        i64 = ctypes.c_int64 * 4
+        h = ctypes.c_void_p()
+        send = i64(700, 0, 0, 1234)  # this rank is 1 of 4
+        cat = torch.cat(rows).contiguous()
+        _lib.check(lib.gcnb_halo_create(1, 4, send, cat.data_ptr(), i64(0, 0, 0, 0), i64(0, 0, 0, 0), st, ctypes.byref(h)), "halo_create")
+        assert lib.gcnb_halo_send_rows(h) == 1934
+        buf = torch.full((1934, f), float("nan"), device=dev())
+        _lib.check(lib.gcnb_halo_pack(h, panel.data_ptr(), ld, f, buf.data_ptr(), st), "halo_pack")
+        assert torch.equal(buf, panel[cat.long(), :f])
+        lib.gcnb_halo_free(h)
+    for m, k, n in ((300000, 100, 256), (500, 9, 7)):
+        a = torch.randn(m, k, generator=gen, device=dev())
+        w = torch.randn(k, n, generator=gen, device=dev())
+        b = torch.randn(n, generator=gen, device=dev())
+        out = torch.empty(m, n, device=dev())
+        ws = torch.empty(max(int(lib.gcnb_gemm_workspace_bytes(m, n, k, _lib.GEMM_AUTO)), 256), dtype=torch.uint8, device=dev())
+        for relu in (0, 1):
+            _lib.check(lib.gcnb_gemm_ex(m, n, k, a.data_ptr(), k, 1, w.data_ptr(), n, 1, out.data_ptr(), n, b.data_ptr(), relu,
+                                        _lib.GEMM_AUTO, ws.data_ptr(), ws.numel(), st), "gemm_ex")
+            want = (a.double() @ w.double() + b.double())
+            want = torch.relu(want) if relu else want
+            assert err(out, want.float().cpu().numpy()) < TOL
 
 
 # ------------------------------------------------------------------ error behaviour (SURVEY.md 8b)
