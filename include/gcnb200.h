@@ -339,9 +339,6 @@ int gcnb_halo_exchange(const gcnb_halo* h, void* nccl_comm, const float* d_sendb
 #define GCNB_TUNE_STREAM_HINT 6
 #define GCNB_TUNE_STREAM_MIN_ROW_BYTES 7
 #define GCNB_TUNE_STREAM_BATCH 8
-/*   GCNB_TUNE_STREAM_ORDER (GCNB_STREAM_ORDER): 0 (default) items in storage order, 1 items sorted by the number of rows
- *   they touch (the items inside hub rows first) */
-#define GCNB_TUNE_STREAM_ORDER 9
 int gcnb_set_tuning(int key, int value);
 
 /* L2 flush helper for benchmarks: writes `bytes` of d_buf. */

@@ -28,7 +28,6 @@ GEMM_FP32, GEMM_TF32X3, GEMM_AUTO = 0, 1, 2
 LAYER_RELU, LAYER_NEED_DX, LAYER_NEED_DW, LAYER_NEED_DB, LAYER_AGG_FIRST = 1, 2, 4, 8, 16
 TUNE_SPMM_KERNEL, TUNE_SPMM_GROUP_VARIANT, TUNE_PDL = 1, 2, 3
 TUNE_SPMM_STREAM, TUNE_STREAM_HOT_MB, TUNE_STREAM_HINT, TUNE_STREAM_MIN_ROW_BYTES, TUNE_STREAM_BATCH = 4, 5, 6, 7, 8
-TUNE_STREAM_ORDER = 9
 
 
 class GraphInfo(ctypes.Structure):

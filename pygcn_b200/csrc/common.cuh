@@ -95,10 +95,6 @@ struct CsrView {
   // word, the heat class of the column (bits 27..30, kPairClassShift) and an end-of-row flag (bit 31).
   int64_t n_stream_items = 0;
   const uint32_t* stream_items = nullptr;
-  // optional processing order of the items (GCNB_TUNE_STREAM_ORDER): items sorted by the number of rows they touch,
-  // so that the items inside hub rows (whose gathers are mostly cold panel rows) run first and the items full of
-  // short rows (whose few entries mostly point at hubs) run together afterwards
-  const uint32_t* stream_order = nullptr;
   bool pair_tagged = false;
 };
 
@@ -225,8 +221,6 @@ struct gcnb_graph {
   int32_t* t_long_chunk_ptr = nullptr;
   uint32_t* stream_items = nullptr;
   uint32_t* t_stream_items = nullptr;
-  uint32_t* stream_order = nullptr;
-  uint32_t* t_stream_order = nullptr;
   gcnb::CsrView fwd, bwd;
   int64_t device_bytes = 0;
 };

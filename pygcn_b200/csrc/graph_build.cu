@@ -472,17 +472,6 @@ __global__ void stream_items_kernel(int64_t n_items, int64_t n, const int32_t* _
   items[i] = (uint32_t)lo | (rowptr[lo] < e ? 0x80000000u : 0u);
 }
 
-// key[i] = rows item i touches (next item's first row - this item's first row), ids[i] = i
-__global__ void stream_item_keys_kernel(int64_t n_items, int64_t n_rows, const uint32_t* __restrict__ items,
-                                        uint32_t* __restrict__ key, uint32_t* __restrict__ ids) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_items) return;
-  const uint32_t r0 = items[i] & 0x7fffffffu;
-  const uint32_t r1 = (i + 1 < n_items) ? (items[i + 1] & 0x7fffffffu) : (uint32_t)n_rows;
-  key[i] = r1 - r0;
-  ids[i] = (uint32_t)i;
-}
-
 int build_pairs(gcnb_graph* g, const int32_t* col, const float* val, uint2** out, cudaStream_t st) {
   GCNB_TRY(graph_alloc(g, out, g->nnz + 2));  // + slack: stages are copied two entries at a time
   GCNB_CUDA(cudaMemsetAsync(*out, 0, (size_t)(g->nnz + 2) * sizeof(uint2), st));
@@ -495,14 +484,12 @@ int build_pairs(gcnb_graph* g, const int32_t* col, const float* val, uint2** out
 
 // Tags `pair` (n_rows x n_cols view, CSR rowptr / col) and builds the view's stream items.
 int build_stream_schedule(gcnb_graph* g, const int32_t* rowptr, const int32_t* col, int64_t n_rows, int64_t n_cols,
-                          uint2* pair, CsrView* view, uint32_t** items_out, uint32_t** order_out, cudaStream_t st) {
+                          uint2* pair, CsrView* view, uint32_t** items_out, cudaStream_t st) {
   const int64_t nnz = g->nnz;
   view->pair_tagged = false;
   view->n_stream_items = 0;
   view->stream_items = nullptr;
-  view->stream_order = nullptr;
   *items_out = nullptr;
-  *order_out = nullptr;
   if (nnz == 0 || n_cols > (1ll << kPairColBits) || n_rows == 0) return GCNB_OK;
   // heat classes: class c = among the 1024 * 2^c most referenced columns (strictly more references than the
   // column at that rank)
@@ -538,23 +525,6 @@ int build_stream_schedule(gcnb_graph* g, const int32_t* rowptr, const int32_t* c
   GCNB_LAUNCH_CHECK();
   view->n_stream_items = n_items;
   view->stream_items = *items_out;
-  // processing order: stable sort of the item ids by the number of rows an item touches
-  DevBuf key, key_out, ids;
-  GCNB_TRY(key.alloc((size_t)n_items * 4));
-  GCNB_TRY(key_out.alloc((size_t)n_items * 4));
-  GCNB_TRY(ids.alloc((size_t)n_items * 4));
-  GCNB_TRY(graph_alloc(g, order_out, n_items));
-  stream_item_keys_kernel<<<blocks_for(n_items), kT, 0, st>>>(n_items, n_rows, *items_out, key.as<uint32_t>(), ids.as<uint32_t>());
-  GCNB_LAUNCH_CHECK();
-  size_t tb2 = 0;
-  GCNB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb2, key.as<uint32_t>(), key_out.as<uint32_t>(), ids.as<uint32_t>(),
-                                            *order_out, (int)n_items, 0, 32, st));
-  DevBuf temp2;
-  GCNB_TRY(temp2.alloc(tb2));
-  GCNB_CUDA(cub::DeviceRadixSort::SortPairs(temp2.p, tb2, key.as<uint32_t>(), key_out.as<uint32_t>(), ids.as<uint32_t>(),
-                                            *order_out, (int)n_items, 0, 32, st));
-  GCNB_CUDA(cudaStreamSynchronize(st));
-  view->stream_order = *order_out;
   return GCNB_OK;
 }
 
@@ -624,7 +594,7 @@ int finalize(gcnb_graph* g, const int32_t* rows, cudaStream_t st, bool with_tran
     g->fwd.pair = g->pair;
     g->bwd = CsrView();
     GCNB_TRY(build_schedule(g, g->rowptr, g->n_rows, &g->fwd, &g->long_rows, &g->long_chunk_ptr, st));
-    GCNB_TRY(build_stream_schedule(g, g->rowptr, g->col, g->n_rows, g->n_cols, g->pair, &g->fwd, &g->stream_items, &g->stream_order, st));
+    GCNB_TRY(build_stream_schedule(g, g->rowptr, g->col, g->n_rows, g->n_cols, g->pair, &g->fwd, &g->stream_items, st));
     GCNB_CUDA(cudaStreamSynchronize(st));
     return GCNB_OK;
   }
@@ -689,8 +659,8 @@ int finalize(gcnb_graph* g, const int32_t* rows, cudaStream_t st, bool with_tran
   g->bwd.pair = g->t_pair;
   GCNB_TRY(build_schedule(g, g->rowptr, g->n_rows, &g->fwd, &g->long_rows, &g->long_chunk_ptr, st));
   GCNB_TRY(build_schedule(g, g->t_rowptr, g->n_cols, &g->bwd, &g->t_long_rows, &g->t_long_chunk_ptr, st));
-  GCNB_TRY(build_stream_schedule(g, g->rowptr, g->col, g->n_rows, g->n_cols, g->pair, &g->fwd, &g->stream_items, &g->stream_order, st));
-  GCNB_TRY(build_stream_schedule(g, g->t_rowptr, g->t_col, g->n_cols, g->n_rows, g->t_pair, &g->bwd, &g->t_stream_items, &g->t_stream_order, st));
+  GCNB_TRY(build_stream_schedule(g, g->rowptr, g->col, g->n_rows, g->n_cols, g->pair, &g->fwd, &g->stream_items, st));
+  GCNB_TRY(build_stream_schedule(g, g->t_rowptr, g->t_col, g->n_cols, g->n_rows, g->t_pair, &g->bwd, &g->t_stream_items, st));
   GCNB_CUDA(cudaStreamSynchronize(st));
   return GCNB_OK;
 }
@@ -981,8 +951,6 @@ extern "C" void gcnb_graph_free(gcnb_graph* g) {
   cudaFree(g->t_long_chunk_ptr);
   cudaFree(g->stream_items);
   cudaFree(g->t_stream_items);
-  cudaFree(g->stream_order);
-  cudaFree(g->t_stream_order);
   cudaFree(g->dense_fwd);
   cudaFree(g->dense_bwd);
   if (cur != g->device) cudaSetDevice(cur);

@@ -818,9 +818,6 @@ int spmm_set_tuning(int key, int value) {
   } else if (key == GCNB_TUNE_STREAM_BATCH) {
     GCNB_REQUIRE(value == 0 || value == 2 || value == 4 || value == 8, "set_tuning: stream rows in flight must be 0, 2, 4 or 8");
     spmm_stream_set(key, value);
-  } else if (key == GCNB_TUNE_STREAM_ORDER) {
-    GCNB_REQUIRE(value == 0 || value == 1, "set_tuning: stream item order must be 0 or 1");
-    spmm_stream_set(key, value);
   } else {
     GCNB_REQUIRE(false, "set_tuning: unknown key %d", key);
   }

@@ -117,15 +117,14 @@ __device__ __forceinline__ void store_out4(float* out_row, int64_t row, int q, i
 // U = gathered rows in flight per lane, HINT = 0 plain loads, 1 hot rows evict_last, 2 + the other rows evict_first.
 template <int CH, bool BF16, int U, int HINT>
 __global__ void __launch_bounds__(kStreamWarps * 32, (CH * U >= 16) ? 3 : 5)
-spmm_stream_kernel(int nnz, int n_items, const uint32_t* __restrict__ items, const uint32_t* __restrict__ order,
-                   const uint2* __restrict__ pair, const void* __restrict__ b, uint32_t ldb_bytes, int f, Epilogue ep,
-                   float* __restrict__ out, int64_t ldo, int vec_out, float* __restrict__ partial, int ldp, int hot_class_max) {
+spmm_stream_kernel(int nnz, int n_items, const uint32_t* __restrict__ items, const uint2* __restrict__ pair,
+                   const void* __restrict__ b, uint32_t ldb_bytes, int f, Epilogue ep, float* __restrict__ out,
+                   int64_t ldo, int vec_out, float* __restrict__ partial, int ldp, int hot_class_max) {
   constexpr int A = BF16 ? 2 : 1;       // float4 accumulators per chunk
   constexpr int kElems = BF16 ? 8 : 4;  // panel elements per chunk
   const int lane = threadIdx.x & 31;
-  const int slot = blockIdx.x * kStreamWarps + (threadIdx.x >> 5);
-  if (slot >= n_items) return;
-  const int item = order != nullptr ? (int)__ldg(order + slot) : slot;  // (processing order of the items, common.cuh)
+  const int item = blockIdx.x * kStreamWarps + (threadIdx.x >> 5);
+  if (item >= n_items) return;
   const uint64_t pol_stream = policy_evict_first();
   uint64_t pol_hot = 0, pol_cold = 0;
   if constexpr (HINT >= 1) pol_hot = policy_evict_last();
@@ -259,7 +258,6 @@ int g_stream_hot_mb = -1;    // L2 budget for the rows of the hot classes (MB)
 int g_stream_hint = -1;      // 0 no hints, 1 hot rows evict_last, 2 + cold rows evict_first
 int g_stream_min_row = -1;   // auto: smallest panel row (bytes) that takes this kernel
 int g_stream_batch = -1;     // 0 auto, else gathered rows in flight per lane (2 / 4 / 8)
-int g_stream_order = -1;     // 0 items in storage order, 1 items sorted by the rows they touch (hub items first)
 
 void stream_init() {
   if (g_stream_mode >= 0) return;
@@ -273,8 +271,6 @@ void stream_init() {
   g_stream_min_row = e ? atoi(e) : 256;
   e = getenv("GCNB_STREAM_BATCH");
   g_stream_batch = e ? atoi(e) : 0;
-  e = getenv("GCNB_STREAM_ORDER");
-  g_stream_order = e ? atoi(e) : 0;
 }
 
 template <int CH, bool BF16, int U, int HINT>
@@ -282,8 +278,8 @@ int launch_stream_t(const CsrView& a, const void* b, int64_t ldb_bytes, int f, c
                     bool vec_out, float* partial, int ldp, int hot_class_max, cudaStream_t st) {
   const int grid = (int)ceil_div(a.n_stream_items, kStreamWarps);
   spmm_stream_kernel<CH, BF16, U, HINT><<<grid, kStreamWarps * 32, 0, st>>>(
-      (int)a.nnz, (int)a.n_stream_items, a.stream_items, g_stream_order > 0 ? a.stream_order : nullptr, a.pair, b,
-      (uint32_t)ldb_bytes, f, ep, out, ldo, vec_out ? 1 : 0, partial, ldp, hot_class_max);
+      (int)a.nnz, (int)a.n_stream_items, a.stream_items, a.pair, b, (uint32_t)ldb_bytes, f, ep, out, ldo, vec_out ? 1 : 0,
+      partial, ldp, hot_class_max);
   GCNB_LAUNCH_CHECK();
   if (a.n_stream_items > 1) {
     spmm_stream_fixup_kernel<<<(unsigned)ceil_div(a.n_stream_items - 1, 8), 256, 0, st>>>(
@@ -309,7 +305,6 @@ void spmm_stream_set(int key, int value) {
   else if (key == GCNB_TUNE_STREAM_HINT) g_stream_hint = value;
   else if (key == GCNB_TUNE_STREAM_MIN_ROW_BYTES) g_stream_min_row = value;
   else if (key == GCNB_TUNE_STREAM_BATCH) g_stream_batch = value;
-  else if (key == GCNB_TUNE_STREAM_ORDER) g_stream_order = value;
 }
 
 // nch = 16-byte chunks per panel row.  The view needs tagged pairs and items, and no empty row (an empty row has no

@@ -76,8 +76,7 @@ def test_tuning_knobs_validate_their_values(lib):
                                (_lib.TUNE_STREAM_HOT_MB, (0, 48, 126), (-1, 127)),
                                (_lib.TUNE_STREAM_HINT, (0, 1, 2), (-1, 3)),
                                (_lib.TUNE_STREAM_MIN_ROW_BYTES, (16, 256, 1024), (8, 2048)),
-                               (_lib.TUNE_STREAM_BATCH, (0, 2, 4, 8), (3, 16)),
-                               (_lib.TUNE_STREAM_ORDER, (0, 1), (-1, 2))):
+                               (_lib.TUNE_STREAM_BATCH, (0, 2, 4, 8), (3, 16))):
             for v in good:
                 assert lib.gcnb_set_tuning(key, v) == 0, (key, v, _lib.last_error())
             for v in bad:
@@ -92,7 +91,6 @@ def test_tuning_knobs_validate_their_values(lib):
         lib.gcnb_set_tuning(_lib.TUNE_STREAM_HINT, 0)
         lib.gcnb_set_tuning(_lib.TUNE_STREAM_MIN_ROW_BYTES, 256)
         lib.gcnb_set_tuning(_lib.TUNE_STREAM_BATCH, 0)
-        lib.gcnb_set_tuning(_lib.TUNE_STREAM_ORDER, 0)
 
 
 def test_halo_plan_entry_points_validate_on_the_host(lib):

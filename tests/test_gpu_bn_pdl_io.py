@@ -204,10 +204,12 @@ def test_graph_from_cites_and_load_adj_files_on_the_device(tmp_path, golden):
     out.mkdir()
     with open(root / "SanFrancisco" / ("X" + IO.CBG_PICKLE_SUFFIX), "wb") as f:
         pickle.dump([sp.csr_matrix(h) for h in c["hours"]], f)
-    adj, n = IO.load_adj_files("SanFrancisco", str(root), str(out), dev(), msa_name_full="X")
+    adj, n = IO.load_adj_files("SanFrancisco", str(root), str(out), dev(), msa_name_full="X", save=True)
     assert n == c["adj"].shape[0] and adj.is_cuda and adj.dtype == torch.float32
     assert _normwise(adj.cpu(), torch.from_numpy(c["adj"])) < 1e-5
-    adj1, _ = IO.load_adj_files("SanFrancisco", "/nonexistent", str(out), dev())
+    # saved under its own name, never as the reference's fp64 cache adj_<msa>.npy; the averaged visits are cached like utils.py:121
+    assert os.path.exists(out / "adj_SanFrancisco.gcnb200.npy") and not os.path.exists(out / "adj_SanFrancisco.npy")
+    adj1, _ = IO.load_adj_files("SanFrancisco", "/nonexistent", str(out), dev())  # level 2: from avg_array_<msa>.npy
     assert torch.equal(adj1, adj)
 
 

@@ -437,7 +437,6 @@ def spmm_kernel(P, request):
         _lib.check(lib.gcnb_set_tuning(_lib.TUNE_STREAM_BATCH, max(variant, 0)), "set_tuning")
         _lib.check(lib.gcnb_set_tuning(_lib.TUNE_STREAM_HINT, {2: 2, 4: 1, 8: 0}.get(variant, 0)), "set_tuning")
         _lib.check(lib.gcnb_set_tuning(_lib.TUNE_STREAM_HOT_MB, 1), "set_tuning")  # small graphs: some hot, some cold columns
-        _lib.check(lib.gcnb_set_tuning(_lib.TUNE_STREAM_ORDER, 1 if variant == 4 else 0), "set_tuning")  # sorted item order
     else:
         _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_STREAM, 0 if name != "auto" else 1), "set_tuning")
         _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_KERNEL, _KERNELS[name]), "set_tuning")
@@ -449,7 +448,6 @@ def spmm_kernel(P, request):
     lib.gcnb_set_tuning(_lib.TUNE_STREAM_BATCH, 0)
     lib.gcnb_set_tuning(_lib.TUNE_STREAM_HINT, 0)
     lib.gcnb_set_tuning(_lib.TUNE_STREAM_HOT_MB, 48)
-    lib.gcnb_set_tuning(_lib.TUNE_STREAM_ORDER, 0)
 
 
 @pytest.mark.parametrize("spmm_kernel", ["auto", "rows", "group", "tma", ("group", 0), ("group", 1), ("group", 2), ("group", 3),

@@ -70,10 +70,9 @@ def main():
             for cfg in opt("--sweep", "default").split(","):
               if cfg != "default":
                   vals = [int(v) for v in cfg.split(":")]
-                  for key, v in zip((_lib.TUNE_SPMM_STREAM, _lib.TUNE_STREAM_HOT_MB, _lib.TUNE_STREAM_HINT, _lib.TUNE_STREAM_BATCH,
-                                     _lib.TUNE_STREAM_ORDER), vals):
+                  for key, v in zip((_lib.TUNE_SPMM_STREAM, _lib.TUNE_STREAM_HOT_MB, _lib.TUNE_STREAM_HINT, _lib.TUNE_STREAM_BATCH), vals):
                       _lib.check(lib.gcnb_set_tuning(key, v), "set_tuning")
-              print(" config stream:hot_mb:hint:batch[:order] = %s" % cfg)
+              print(" config stream:hot_mb:hint:batch = %s" % cfg)
               for prec in (("fp32", "bf16") if bf16 else ("fp32",)):
                   if prec == "bf16":
                       ld8 = (f + 7) // 8 * 8
