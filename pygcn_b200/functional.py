@@ -180,14 +180,39 @@ def _ld8(f):
     return (f + 7) // 8 * 8
 
 
+def _gemm(lib, m, n, k, a, a_rs, a_cs, b, b_rs, b_cs, out, ldc, dev, sp, bias=None, relu=False):
+    """out[m, n] (ld ldc) = a b (+ bias) (relu) through gcnb_gemm / gcnb_gemm_ex, precision "auto"."""
+    auto = _lib.GEMM_AUTO
+    ws = _ws(lib.gcnb_gemm_workspace_bytes(m, n, k, auto), dev)
+    if bias is None and not relu:
+        _lib.check(lib.gcnb_gemm(m, n, k, _ptr(a), a_rs, a_cs, _ptr(b), b_rs, b_cs, _ptr(out), ldc, auto, _ptr(ws), ws.numel(), sp),
+                   "gcnb_gemm")
+    else:
+        _lib.check(lib.gcnb_gemm_ex(m, n, k, _ptr(a), a_rs, a_cs, _ptr(b), b_rs, b_cs, _ptr(out), ldc, _ptr(bias), 1 if relu else 0,
+                                    auto, _ptr(ws), ws.numel(), sp), "gcnb_gemm_ex")
+    return out
+
+
+def _spmm_bf16_panel(lib, graph, flags, src, f, bias, out, ldo, dev, sp):
+    """out = A (or A^T) @ bf16(src[:, :f]) (+ bias) (relu): the panel is rounded once (gcnb_to_bf16) and gathered at half
+    the bytes per row (gcnb_spmm_bf16); accumulation and output fp32."""
+    rows = src.shape[0]
+    panel = torch.empty((rows, _ld8(f)), dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.gcnb_to_bf16(rows, f, _ptr(src), _ld(src), _ptr(panel), _ld8(f), sp), "gcnb_to_bf16")
+    ws = _ws(lib.gcnb_spmm_workspace_bytes(graph._h, flags & _lib.SPMM_TRANSPOSE, f), dev)
+    _lib.check(lib.gcnb_spmm_bf16(graph._h, flags, _ptr(panel), _ld8(f), f, _ptr(bias), _ptr(out), ldo, _ptr(ws), ws.numel(), sp),
+               "gcnb_spmm_bf16")
+    return out
+
+
 class _GCNLayerBf16Fn(torch.autograd.Function):
     """The layer with bf16 PANELS (precision="bf16", the <= 2e-2 tier of BASELINE's north_star): the operand the
-    SpMM gathers -- support = X W forward, the (masked) upstream gradient backward -- is rounded to bf16 once
-    (gcnb_to_bf16) and gathered at half the bytes per row (gcnb_spmm_bf16); X, W, the dense products, the
-    accumulation of the SpMM, bias, ReLU and every output stay fp32."""
+    SpMM gathers -- support = X W (or X itself in the aggregate-first order) forward, the (masked) upstream gradient (or
+    G W^T) backward -- is rounded to bf16 once and gathered at half the bytes per row; X, W, the dense products, the
+    accumulation of the SpMM, bias, ReLU and every output stay fp32.  Same association rule as the fp32 tier."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, graph, relu):
+    def forward(ctx, x, weight, bias, graph, relu, association="auto"):
         lib = _lib.load()
         dev = x.device
         fin, fout = weight.shape
@@ -195,69 +220,73 @@ class _GCNLayerBf16Fn(torch.autograd.Function):
         w = weight.contiguous()
         b = bias.contiguous() if bias is not None else None
         n = graph.n_cols
-        support = torch.empty((n, _ld4(fout)), dtype=torch.float32, device=dev)
-        panel = torch.empty((n, _ld8(fout)), dtype=torch.bfloat16, device=dev)
+        agg = association == "aggregate_first" or (association == "auto" and fin * (2 if ctx.needs_input_grad[0] else 1) < fout * (
+            2 if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) else 1))
         out = torch.empty((graph.n_rows, fout), dtype=torch.float32, device=dev)
-        auto = _lib.GEMM_AUTO
         with _on_device(dev):
             sp = _stream_ptr(dev)
-            ws = _ws(lib.gcnb_gemm_workspace_bytes(n, fout, fin, auto), dev)
-            _lib.check(lib.gcnb_gemm(n, fout, fin, _ptr(xr), _ld(xr), 1, _ptr(w), fout, 1, _ptr(support), _ld4(fout), auto,
-                                     _ptr(ws), ws.numel(), sp), "gcnb_gemm")
-            _lib.check(lib.gcnb_to_bf16(n, fout, _ptr(support), _ld4(fout), _ptr(panel), _ld8(fout), sp), "gcnb_to_bf16")
-            ws2 = _ws(lib.gcnb_spmm_workspace_bytes(graph._h, 0, fout), dev)
-            _lib.check(lib.gcnb_spmm_bf16(graph._h, _lib.SPMM_RELU if relu else 0, _ptr(panel), _ld8(fout), fout, _ptr(b),
-                                          _ptr(out), fout, _ptr(ws2), ws2.numel(), sp), "gcnb_spmm_bf16")
-        ctx.graph, ctx.relu, ctx.has_bias = graph, relu, bias is not None
-        ctx.save_for_backward(xr, w, out if relu else None)
+            if agg:  # out = (A bf16(X)) W + b
+                ax = torch.empty((graph.n_rows, _ld4(fin)), dtype=torch.float32, device=dev)
+                if _ld4(fin) != fin:
+                    ax.zero_()
+                _spmm_bf16_panel(lib, graph, 0, xr, fin, None, ax, _ld4(fin), dev, sp)
+                _gemm(lib, graph.n_rows, fout, fin, ax, _ld4(fin), 1, w, fout, 1, out, fout, dev, sp, b, relu)
+                keep = ax
+            else:    # out = A bf16(X W) + b
+                support = torch.empty((n, _ld4(fout)), dtype=torch.float32, device=dev)
+                _gemm(lib, n, fout, fin, xr, _ld(xr), 1, w, fout, 1, support, _ld4(fout), dev, sp)
+                _spmm_bf16_panel(lib, graph, _lib.SPMM_RELU if relu else 0, support[:, :fout], fout, b, out, fout, dev, sp)
+                keep = xr
+        ctx.graph, ctx.relu, ctx.has_bias, ctx.agg = graph, relu, bias is not None, agg
+        ctx.save_for_backward(keep, w, out if relu else None)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
         lib = _lib.load()
-        xr, w, y = ctx.saved_tensors
+        xk, w, y = ctx.saved_tensors  # xk = X, or A X in the aggregate-first order
         graph = ctx.graph
         dev = g.device
         fin, fout = w.shape
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         need_db = ctx.has_bias and ctx.needs_input_grad[2]
         gr = _rowmajor(g)
-        auto = _lib.GEMM_AUTO
         dx = dw = db = None
         with _on_device(dev):
             sp = _stream_ptr(dev)
             gsrc = gr
-            if ctx.relu or need_db:
-                gm = torch.empty((graph.n_rows, fout), dtype=torch.float32, device=dev) if ctx.relu else None
+            staged = ctx.relu or _ld(gr) % 4 != 0 or gr.data_ptr() % 16 != 0  # (aligned rows for the dense products)
+            if staged or need_db:
+                gm = torch.empty((graph.n_rows, _ld4(fout)), dtype=torch.float32, device=dev) if staged else None
                 db = torch.empty((fout,), dtype=torch.float32, device=dev)
                 ws = _ws(lib.gcnb_colsum_workspace_bytes(graph.n_rows, fout), dev)
                 _lib.check(lib.gcnb_colsum(graph.n_rows, fout, _ptr(gr), _ld(gr), _ptr(y) if ctx.relu else None, fout,
-                                           _ptr(gm), fout, _ptr(db), _ptr(ws), ws.numel(), sp), "gcnb_colsum")
+                                           _ptr(gm), _ld4(fout), _ptr(db), _ptr(ws), ws.numel(), sp), "gcnb_colsum")
                 if gm is not None:
-                    gsrc = gm
+                    gsrc = gm[:, :fout]
                 if not need_db:
                     db = None
-            if need_dw or need_dx:
-                panel = torch.empty((graph.n_rows, _ld8(fout)), dtype=torch.bfloat16, device=dev)
-                _lib.check(lib.gcnb_to_bf16(graph.n_rows, fout, _ptr(gsrc), _ld(gsrc), _ptr(panel), _ld8(fout), sp),
-                           "gcnb_to_bf16")
-                ds = torch.empty((graph.n_cols, _ld4(fout)), dtype=torch.float32, device=dev)
-                ws = _ws(lib.gcnb_spmm_workspace_bytes(graph._h, _lib.SPMM_TRANSPOSE, fout), dev)
-                _lib.check(lib.gcnb_spmm_bf16(graph._h, _lib.SPMM_TRANSPOSE, _ptr(panel), _ld8(fout), fout, None, _ptr(ds),
-                                              _ld4(fout), _ptr(ws), ws.numel(), sp), "gcnb_spmm_bf16(transpose)")
-                n = graph.n_cols
+            n = graph.n_cols
+            if ctx.agg:
+                if need_dw:  # dW = (A X)^T G: no SpMM
+                    dw = torch.empty((fin, fout), dtype=torch.float32, device=dev)
+                    _gemm(lib, fin, fout, graph.n_rows, xk, 1, _ld(xk), gsrc, _ld(gsrc), 1, dw, fout, dev, sp)
+                if need_dx:  # dX = A^T bf16(G W^T)
+                    t = torch.empty((graph.n_rows, _ld4(fin)), dtype=torch.float32, device=dev)
+                    _gemm(lib, graph.n_rows, fin, fout, gsrc, _ld(gsrc), 1, w, 1, fout, t, _ld4(fin), dev, sp)
+                    dx = torch.empty((n, fin), dtype=torch.float32, device=dev)
+                    _spmm_bf16_panel(lib, graph, _lib.SPMM_TRANSPOSE, t[:, :fin], fin, None, dx, fin, dev, sp)
+            elif need_dw or need_dx:
+                ds = torch.empty((n, _ld4(fout)), dtype=torch.float32, device=dev)
+                _spmm_bf16_panel(lib, graph, _lib.SPMM_TRANSPOSE, gsrc, fout, None, ds, _ld4(fout), dev, sp)
                 if need_dw:
                     dw = torch.empty((fin, fout), dtype=torch.float32, device=dev)
-                    ws = _ws(lib.gcnb_gemm_workspace_bytes(fin, fout, n, auto), dev)
-                    _lib.check(lib.gcnb_gemm(fin, fout, n, _ptr(xr), 1, _ld(xr), _ptr(ds), _ld4(fout), 1, _ptr(dw), fout,
-                                             auto, _ptr(ws), ws.numel(), sp), "gcnb_gemm(dW)")
+                    _gemm(lib, fin, fout, n, xk, 1, _ld(xk), ds, _ld4(fout), 1, dw, fout, dev, sp)
                 if need_dx:
                     dx = torch.empty((n, fin), dtype=torch.float32, device=dev)
-                    ws = _ws(lib.gcnb_gemm_workspace_bytes(n, fin, fout, auto), dev)
-                    _lib.check(lib.gcnb_gemm(n, fin, fout, _ptr(ds), _ld4(fout), 1, _ptr(w), 1, fout, _ptr(dx), fin, auto,
-                                             _ptr(ws), ws.numel(), sp), "gcnb_gemm(dX)")
-        return dx, dw, db, None, None
+                    _gemm(lib, n, fin, fout, ds, _ld4(fout), 1, w, 1, fout, dx, fin, dev, sp)
+        return dx, dw, db, None, None, None
 
 
 class _GCNLayerBatchedFn(torch.autograd.Function):
@@ -402,7 +431,7 @@ def gcn_layer(input, adj, weight, bias=None, relu=False, precision="auto", dropo
     if precision == "bf16" and not graph.dense_route:
         if dropout_mask is not None:
             raise NotImplementedError("the fused dropout mask is not available in the bf16 panel tier")
-        return _GCNLayerBf16Fn.apply(input, weight, bias, graph, bool(relu))
+        return _GCNLayerBf16Fn.apply(input, weight, bias, graph, bool(relu), association)
     mask, scale = None, 1.0
     if dropout_mask is not None:
         if not 0.0 <= dropout_p < 1.0:
