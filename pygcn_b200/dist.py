@@ -671,19 +671,33 @@ class HaloPlan:
         self.c = ops.halo_create(self, dgraph, col.device) if hasattr(ops, "halo_create") and world > 1 else None
 
 
-def dist_spmm_halo(ops, dgraph, plan, diag, panel, bias=None, relu=False, group=None):
+def halo_compact(ops, dgraph, transpose, f, like, exch, group=None):
+    """The compact panel [own slot | halo rows] of an unsplit row block, allocated BEFORE the panel is produced: the
+    producer (X W, the staged masked G, G W^T) writes its rows straight into the own slot `compact[:n_p]` and the
+    exchange skips the copy (1.25 GB read + written per exchange at 2 GPUs and F = 256).  None when the exchange is
+    not "halo", the row block is split (its compact panel has no own slot) or the width needs padding."""
+    if exch != "halo" or dgraph.world == 1 or dgraph.split or f % 4 != 0:
+        return None
+    plan = halo_plans(ops, dgraph, group)[1 if transpose else 0]
+    return ops.empty((plan.n_compact, f), like)
+
+
+def dist_spmm_halo(ops, dgraph, plan, diag, panel, bias=None, relu=False, group=None, compact=None):
     """out_p with the needed-rows-only exchange: every peer r gets pack[r] @ panel (the rows of this rank it reads),
     this rank receives need[q] rows from every source q into the compact panel, then one SpMM over the renumbered
-    block (after the diagonal block when the row block is split)."""
+    block (after the diagonal block when the row block is split).  compact: the panel already IS compact[:n_p]
+    (halo_compact)."""
     f = panel.shape[1]
     p, world = dgraph.rank, dgraph.world
     out = ops.empty((dgraph.n_rows(), f), panel)
-    compact = ops.empty((plan.n_compact, f), panel)
+    in_place = compact is not None
+    if not in_place:
+        compact = ops.empty((plan.n_compact, f), panel)
     if getattr(plan, "c", None) is not None:
         done = ops.halo_exchange_async(plan.c, panel, compact)      # pack kernel + grouped ncclSend / ncclRecv, side stream
         if dgraph.split:
             ops.spmm_block(diag, panel, out, False)                 # runs while the halo rows are on the wire
-        else:
+        elif not in_place:
             compact[: panel.shape[0]].copy_(panel)                  # own slot at the front of the compact panel
         torch.cuda.current_stream(panel.device).wait_event(done)
         return ops.spmm_block(plan.block, compact, out, dgraph.split, bias, relu)
@@ -703,7 +717,7 @@ def dist_spmm_halo(ops, dgraph, plan, diag, panel, bias=None, relu=False, group=
     reqs = dist.batch_isend_irecv(p2p) if p2p else []
     if dgraph.split:
         ops.spmm_block(diag, panel, out, False)           # runs while the halo rows are on the wire
-    else:
+    elif not in_place:
         compact[: panel.shape[0]].copy_(panel)            # own slot at the front of the compact panel
     for rq in reqs:
         rq.wait()
@@ -752,7 +766,7 @@ def halo_fraction(ops, dgraph, group=None):
     return frac
 
 
-def exchanged_spmm(ops, dgraph, transpose, panel, exch, bias=None, relu=False, group=None):
+def exchanged_spmm(ops, dgraph, transpose, panel, exch, bias=None, relu=False, group=None, compact=None):
     """Rows p of  A @ P  (transpose: A^T @ P) for the row-partitioned panel P whose rows of this rank are `panel`
     [n_p, F]: the exchange step of the layer.  exch: None / "nccl" = all-gather of the padded slots, "halo" = needed
     rows only, or a PeerExchange (pipelined per-source blocks over NVLink peer memory)."""
@@ -775,7 +789,8 @@ def exchanged_spmm(ops, dgraph, transpose, panel, exch, bias=None, relu=False, g
         out = ops.empty((n_p, f), panel)
         return ops.spmm_block(diag, panel, out, False, bias, relu)
     if exch == "halo":
-        return dist_spmm_halo(ops, dgraph, halo_plans(ops, dgraph, group)[1 if transpose else 0], diag, panel, bias, relu, group)
+        return dist_spmm_halo(ops, dgraph, halo_plans(ops, dgraph, group)[1 if transpose else 0], diag, panel, bias, relu, group,
+                              compact)
     if exch is not None and exch != "nccl":  # PeerExchange: the panel goes into this rank's slot, blocks follow the phases
         exch.my_slot[:n_p].copy_(panel[:n_p])
         return dist_spmm_pipelined(ops, dgraph, dgraph.bwd_blocks if transpose else dgraph.fwd_blocks, exch, bias, relu)
@@ -803,21 +818,28 @@ def dist_layer_forward(ops, dgraph, x, w, b, relu=False, group=None, exch=None, 
     if exch is not None and not isinstance(exch, str) and dgraph.world > 1:
         ops.gemm(x, w, out=exch.my_slot)             # X_p W straight into this rank's slot of the peer exchange
         return dist_spmm_pipelined(ops, dgraph, dgraph.fwd_blocks, exch, b, relu), None
-    support = ops.empty((dgraph.pad_rows if exch != "halo" else x.shape[0], w.shape[1]), x)
+    compact = halo_compact(ops, dgraph, False, w.shape[1], x, exch, group)
+    if compact is not None:
+        support = compact[: x.shape[0]]              # X_p W lands in the own slot of the compact panel
+    else:
+        support = ops.empty((dgraph.pad_rows if exch != "halo" else x.shape[0], w.shape[1]), x)
     ops.gemm(x, w, out=support)
-    return exchanged_spmm(ops, dgraph, False, support, exch, b, relu, group), None
+    return exchanged_spmm(ops, dgraph, False, support, exch, b, relu, group, compact), None
 
 
 def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=True, group=None, exch=None, agg=False, ax=None,
                         reduce=True):
     """(dX rows of this rank or None, dW, db): dW/db are summed over ranks when `reduce` (one all-reduce)."""
     fin, fout = w.shape
-    db, gm = ops.colsum(g, y)                        # local part of db; G masked by [y > 0] when the ReLU is fused
+    compact = None if agg else halo_compact(ops, dgraph, True, fout, g, exch, group)
+    # local part of db; G masked by [y > 0] when the ReLU is fused (staged into the compact panel's own slot when the
+    # exchange takes it from there)
+    db, gm = ops.colsum(g, y, compact[: g.shape[0]] if compact is not None else None)
     if agg:
         dw = ops.gemm(ax.t(), gm)                    # (A X)_p^T G_p: no exchange at all for dW
         ds = None
     else:
-        ds = exchanged_spmm(ops, dgraph, True, gm, exch, None, False, group)   # rows p of A^T G
+        ds = exchanged_spmm(ops, dgraph, True, gm, exch, None, False, group, compact)   # rows p of A^T G
         dw = ops.gemm(x.t(), ds)                     # local part of X^T dS
     if dgraph.world > 1 and reduce:
         flat = torch.cat([dw.reshape(-1), db.reshape(-1)])
@@ -825,8 +847,12 @@ def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=Tru
         dw = flat[: fin * fout].reshape(fin, fout)
         db = flat[fin * fout:]
     dx = None
-    if need_dx:
-        dx = exchanged_spmm(ops, dgraph, True, ops.gemm(gm, w.t()), exch, None, False, group) if agg else ops.gemm(ds, w.t())
+    if need_dx and agg:
+        compact = halo_compact(ops, dgraph, True, fin, g, exch, group)
+        gw = ops.gemm(gm, w.t(), out=compact[: g.shape[0]] if compact is not None else None)
+        dx = exchanged_spmm(ops, dgraph, True, gw, exch, None, False, group, compact)
+    elif need_dx:
+        dx = ops.gemm(ds, w.t())
     return dx, dw, (db if has_bias else None)
 
 

@@ -104,12 +104,12 @@ def _problem(n=300, seed=3, fout=5, fin=12):
     return n, idx, val, x, g, w, b
 
 
-def _worker(rank, world, port, outdir, relu, split=True, exchange="nccl", agg=False, fin=12):
+def _worker(rank, world, port, outdir, relu, split=True, exchange="nccl", agg=False, fin=12, fout=5):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        n, idx, val, x, g, w, b = _problem(fin=fin)
+        n, idx, val, x, g, w, b = _problem(fin=fin, fout=fout)
         bounds = D.partition_rows_by_nnz(O.coo_to_csr(idx, n), world)
         r0, r1 = bounds[rank], bounds[rank + 1]
         tidx = np.vstack([idx[1], idx[0]])
@@ -146,6 +146,26 @@ def _free_port():
     p = s.getsockname()[1]
     s.close()
     return p
+
+
+@pytest.mark.parametrize("world,relu,exchange", [(2, True, "halo"), (4, False, "halo"), (3, True, "nccl")])
+def test_unsplit_halo_exchange_with_the_panel_produced_in_the_compact_buffer(world, relu, exchange):
+    """Widths that need no padding (8): X W, the staged masked G (and G W^T in the aggregate-first order, fin = 12
+    above) are written straight into the own slot of the compact panel (dist.halo_compact) -- same results."""
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(world, _free_port(), d, relu, False, exchange, False, 12, 8), nprocs=world, join=True)
+        parts = [np.load(os.path.join(d, "r%d.npz" % r)) for r in range(world)]
+    n, idx, val, x, g, w, b = _problem(fout=8)
+    _, o_ref = O.c_layer_forward(x, w, b, idx, val, n)
+    gm = g
+    if relu:
+        gm = O.relu_backward(g, o_ref)
+        o_ref = np.maximum(o_ref, 0)
+    dw, db, dx, _ = O.c_layer_backward(x, w, True, idx, val, n, gm)
+    assert O.normwise_err(np.concatenate([p["out"] for p in parts]), o_ref) < 1e-5
+    assert O.normwise_err(np.concatenate([p["dx"] for p in parts]), dx) < 1e-5
+    for p in parts:
+        assert O.normwise_err(p["dw"], dw) < 1e-5 and O.normwise_err(p["db"], db) < 1e-5
 
 
 @pytest.mark.parametrize("world,relu,split,exchange,agg", [

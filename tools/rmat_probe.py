@@ -5,7 +5,8 @@ column order is worth.  Development tool; also the command ncu wraps (one width,
     python tools/rmat_probe.py [--widths 256,100,48] [--relabel none,degree,random,rows] [--bf16] [--reps 5] [--workload products]
                                [--sweep stream:hot_mb:hint:batch,...]   e.g. 0:0:0:0,2:48:0:0,2:96:2:8  (batch = gathered rows in flight per lane: 0 auto, 2 / 4 / 8)
 --sweep: every configuration of the streaming kernel (gcnb_set_tuning: GCNB_TUNE_SPMM_STREAM, _HOT_MB, _HINT, _BATCH) in
-one process on the same graph; --fwd-only skips the transposed launch; --check compares with torch's CUDA CSR product.
+one process on the same graph; --slices 1,2,4: the panel in K column slices, one launch each (what narrower gathered
+rows are worth in L2 hits: profiles/r02_rmat_probe_column_slices_old_kernels.txt); --fwd-only skips the transposed launch; --check compares with torch's CUDA CSR product.
 """
 import ctypes
 import os
@@ -73,7 +74,10 @@ def main():
                   for key, v in zip((_lib.TUNE_SPMM_STREAM, _lib.TUNE_STREAM_HOT_MB, _lib.TUNE_STREAM_HINT, _lib.TUNE_STREAM_BATCH), vals):
                       _lib.check(lib.gcnb_set_tuning(key, v), "set_tuning")
               print(" config stream:hot_mb:hint:batch = %s" % cfg)
-              for prec in (("fp32", "bf16") if bf16 else ("fp32",)):
+              for slices in [int(v) for v in opt("--slices", "1").split(",")]:
+               if slices > 1:
+                  print(" slices %d" % slices)
+               for prec in (("fp32", "bf16") if bf16 else ("fp32",)):
                   if prec == "bf16":
                       ld8 = (f + 7) // 8 * 8
                       panel = torch.empty(n, ld8, dtype=torch.bfloat16, device=dev)
@@ -91,9 +95,11 @@ def main():
                                                             ctypes.c_void_p(out.data_ptr()), f, ctypes.c_void_p(ws.data_ptr()),
                                                             ws.numel(), st), "spmm_bf16")
                           else:
-                              _lib.check(lib.gcnb_spmm(graph._h, tflag, ctypes.c_void_p(s.data_ptr()), f, f, None,
-                                                       ctypes.c_void_p(out.data_ptr()), f, ctypes.c_void_p(ws.data_ptr()), ws.numel(), st),
-                                         "spmm")
+                              wsl = f // slices  # --slices K: the panel in K column slices, one launch each (L2 locality)
+                              for k in range(slices):
+                                  _lib.check(lib.gcnb_spmm(graph._h, tflag, ctypes.c_void_p(s.data_ptr() + 4 * k * wsl), f, wsl, None,
+                                                           ctypes.c_void_p(out.data_ptr() + 4 * k * wsl), f,
+                                                           ctypes.c_void_p(ws.data_ptr()), ws.numel(), st), "spmm")
                           b.record()
                           torch.cuda.synchronize()
                           if it >= 2:
