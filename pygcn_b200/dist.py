@@ -401,7 +401,11 @@ class CudaOps:
         import weakref
 
         weakref.finalize(plan, self.lib.gcnb_halo_free, h)
-        return {"h": h, "comm": self.halo_comm(device), "stream": torch.cuda.Stream(device=device), "send_rows": sum(send)}
+        # the side stream has HIGH priority: its pack-free exchange kernels (NCCL's send / recv CTAs) must get SM slots while
+        # a SpMM grid of the main stream is resident, not after that grid has been dispatched to the end
+        prio = -1 if os.environ.get("GCNB_DIST_SIDE_PRIORITY", "1") == "1" else 0
+        return {"h": h, "comm": self.halo_comm(device), "stream": torch.cuda.Stream(device=device, priority=prio),
+                "send_rows": sum(send)}
 
     def halo_exchange_async(self, c, panel, compact):
         """Pack on the current stream, exchange on the side stream; returns the event the consumer waits for."""
@@ -682,25 +686,16 @@ def halo_compact(ops, dgraph, transpose, f, like, exch, group=None):
     return ops.empty((plan.n_compact, f), like)
 
 
-def dist_spmm_halo(ops, dgraph, plan, diag, panel, bias=None, relu=False, group=None, compact=None):
-    """out_p with the needed-rows-only exchange: every peer r gets pack[r] @ panel (the rows of this rank it reads),
-    this rank receives need[q] rows from every source q into the compact panel, then one SpMM over the renumbered
-    block (after the diagonal block when the row block is split).  compact: the panel already IS compact[:n_p]
-    (halo_compact)."""
+def _halo_start(ops, dgraph, plan, panel, compact, group=None):
+    """Starts the exchange of one panel (this rank's rows `panel`, halo rows into `compact`) and returns the callable
+    that makes the caller wait for the halo rows: a stream wait on the exchange's event (library path: pack kernel on
+    the current stream, grouped ncclSend / ncclRecv on the side stream), or the completion of the grouped
+    torch.distributed send / recv (backends without the library: the CPU tests)."""
     f = panel.shape[1]
     p, world = dgraph.rank, dgraph.world
-    out = ops.empty((dgraph.n_rows(), f), panel)
-    in_place = compact is not None
-    if not in_place:
-        compact = ops.empty((plan.n_compact, f), panel)
     if getattr(plan, "c", None) is not None:
-        done = ops.halo_exchange_async(plan.c, panel, compact)      # pack kernel + grouped ncclSend / ncclRecv, side stream
-        if dgraph.split:
-            ops.spmm_block(diag, panel, out, False)                 # runs while the halo rows are on the wire
-        elif not in_place:
-            compact[: panel.shape[0]].copy_(panel)                  # own slot at the front of the compact panel
-        torch.cuda.current_stream(panel.device).wait_event(done)
-        return ops.spmm_block(plan.block, compact, out, dgraph.split, bias, relu)
+        done = ops.halo_exchange_async(plan.c, panel, compact)
+        return lambda: torch.cuda.current_stream(panel.device).wait_event(done)
     sends, p2p = [], []
     for k in range(1, world):
         r = (p + k) % world
@@ -715,13 +710,72 @@ def dist_spmm_halo(ops, dgraph, plan, diag, panel, bias=None, relu=False, group=
             p2p.append(dist.P2POp(dist.irecv, compact[plan.offset[q]: plan.offset[q] + n_q],
                                   q if group is None else dist.get_global_rank(group, q), group))
     reqs = dist.batch_isend_irecv(p2p) if p2p else []
+
+    def finish(sends=sends):  # (the send buffers live until the requests are done)
+        for rq in reqs:
+            rq.wait()
+    return finish
+
+
+def dist_spmm_halo(ops, dgraph, plan, diag, panel, bias=None, relu=False, group=None, compact=None):
+    """out_p with the needed-rows-only exchange: every peer r gets pack[r] @ panel (the rows of this rank it reads),
+    this rank receives need[q] rows from every source q into the compact panel, then one SpMM over the renumbered
+    block (after the diagonal block when the row block is split).  compact: the panel already IS compact[:n_p]
+    (halo_compact)."""
+    f = panel.shape[1]
+    out = ops.empty((dgraph.n_rows(), f), panel)
+    in_place = compact is not None
+    if not in_place:
+        compact = ops.empty((plan.n_compact, f), panel)
+    finish = _halo_start(ops, dgraph, plan, panel, compact, group)
     if dgraph.split:
         ops.spmm_block(diag, panel, out, False)           # runs while the halo rows are on the wire
     elif not in_place:
         compact[: panel.shape[0]].copy_(panel)            # own slot at the front of the compact panel
-    for rq in reqs:
-        rq.wait()
+    finish()
     return ops.spmm_block(plan.block, compact, out, dgraph.split, bias, relu)
+
+
+# Column chunks of the exchanged panel (unsplit row blocks, halo exchange): chunk k + 1 is produced and packed while
+# chunk k is on the wire, and chunk k is aggregated while chunk k + 1 is on the wire.  Only where a chunk is still a
+# wide gather (>= 128 columns: the streaming SpMM at 512-byte rows costs what half a 1 KB-row launch costs; narrower
+# chunks lose more in the SpMM than the overlap returns -- profiles/r02_rmat_probe_column_slices_old_kernels.txt).
+CHUNK_MIN_COLS = int(os.environ.get("GCNB_DIST_CHUNK_MIN_COLS", "128"))
+CHUNKS_MAX = int(os.environ.get("GCNB_DIST_CHUNKS", "2"))
+
+
+def column_chunks(f):
+    """[(c0, c1)] column ranges of the pipelined exchange: at most CHUNKS_MAX, each a multiple of 4 columns and at least
+    CHUNK_MIN_COLS wide; one range = not pipelined."""
+    k = max(1, min(CHUNKS_MAX, f // max(CHUNK_MIN_COLS, 4)))
+    if k == 1 or f % 4 != 0:
+        return [(0, f)]
+    w = -(-(f // 4) // k) * 4
+    return [(c, min(c + w, f)) for c in range(0, f, w)]
+
+
+def chunked_halo_applies(ops, dgraph, f, exch):
+    return exch == "halo" and dgraph.world > 1 and not dgraph.split and len(column_chunks(f)) > 1
+
+
+def dist_spmm_halo_chunked(ops, dgraph, transpose, f, like, produce, bias=None, relu=False, group=None):
+    """Rows p of A @ P (transpose: A^T @ P) where the rank's rows of P are PRODUCED chunk by chunk: produce(c0, c1, dst)
+    writes columns [c0, c1) of this rank's rows into dst [n_p, c1 - c0] -- the own slot of that chunk's compact panel.
+    Order on the current stream: produce 0, pack 0, produce 1, pack 1, ..., wait 0, SpMM 0, wait 1, SpMM 1, ...; the
+    exchanges follow one another on the side stream."""
+    plan = halo_plans(ops, dgraph, group)[1 if transpose else 0]
+    n_p = dgraph.n_rows()
+    out = ops.empty((n_p, f), like)
+    pending = []
+    for c0, c1 in column_chunks(f):
+        compact = ops.empty((plan.n_compact, c1 - c0), like)
+        own = compact[:n_p]
+        produce(c0, c1, own)
+        pending.append((c0, c1, compact, _halo_start(ops, dgraph, plan, own, compact, group)))
+    for c0, c1, compact, finish in pending:
+        finish()
+        ops.spmm_block(plan.block, compact, out[:, c0:c1], False, bias[c0:c1] if bias is not None else None, relu)
+    return out
 
 
 def dist_spmm(ops, dgraph, diag, remote, panel, bias=None, relu=False, group=None):
@@ -813,11 +867,18 @@ def dist_layer_forward(ops, dgraph, x, w, b, relu=False, group=None, exch=None, 
     """Row block of  A (X W) + b  (pygcn/layers.py:33-36) for this rank; agg: (A X) W + b, the exchanged panel is X.
     Returns (out, what backward needs beside it: A X for the aggregate-first order, else None)."""
     if agg:
-        ax = exchanged_spmm(ops, dgraph, False, x, exch, None, False, group)
+        if chunked_halo_applies(ops, dgraph, x.shape[1], exch):
+            ax = dist_spmm_halo_chunked(ops, dgraph, False, x.shape[1], x, lambda c0, c1, dst: dst.copy_(x[:, c0:c1]),
+                                        None, False, group)
+        else:
+            ax = exchanged_spmm(ops, dgraph, False, x, exch, None, False, group)
         return ops.gemm_bias_act(ax, w, b, relu), ax
     if exch is not None and not isinstance(exch, str) and dgraph.world > 1:
         ops.gemm(x, w, out=exch.my_slot)             # X_p W straight into this rank's slot of the peer exchange
         return dist_spmm_pipelined(ops, dgraph, dgraph.fwd_blocks, exch, b, relu), None
+    if chunked_halo_applies(ops, dgraph, w.shape[1], exch):   # X_p W[:, chunk] while the previous chunk is on the wire
+        return dist_spmm_halo_chunked(ops, dgraph, False, w.shape[1], x, lambda c0, c1, dst: ops.gemm(x, w[:, c0:c1], out=dst),
+                                      b, relu, group), None
     compact = halo_compact(ops, dgraph, False, w.shape[1], x, exch, group)
     if compact is not None:
         support = compact[: x.shape[0]]              # X_p W lands in the own slot of the compact panel
@@ -831,6 +892,14 @@ def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=Tru
                         reduce=True):
     """(dX rows of this rank or None, dW, db): dW/db are summed over ranks when `reduce` (one all-reduce)."""
     fin, fout = w.shape
+    if not agg and chunked_halo_applies(ops, dgraph, fout, exch):
+        # the masked gradient staged chunk by chunk into the compact panels (its column sums = that chunk of db)
+        dbs = []
+        ds = dist_spmm_halo_chunked(
+            ops, dgraph, True, fout, g,
+            lambda c0, c1, dst: dbs.append(ops.colsum(g[:, c0:c1], y[:, c0:c1] if y is not None else None, dst)[0]),
+            None, False, group)
+        return _finish_backward(ops, dgraph, x, w, torch.cat(dbs), None, ds, need_dx, has_bias, group, exch, False, None, reduce)
     compact = None if agg else halo_compact(ops, dgraph, True, fout, g, exch, group)
     # local part of db; G masked by [y > 0] when the ReLU is fused (staged into the compact panel's own slot when the
     # exchange takes it from there)
@@ -840,6 +909,13 @@ def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=Tru
         ds = None
     else:
         ds = exchanged_spmm(ops, dgraph, True, gm, exch, None, False, group, compact)   # rows p of A^T G
+    return _finish_backward(ops, dgraph, x, w, db, gm, ds, need_dx, has_bias, group, exch, agg, dw if agg else None, reduce)
+
+
+def _finish_backward(ops, dgraph, x, w, db, gm, ds, need_dx, has_bias, group, exch, agg, dw, reduce):
+    """dW (reference order: X_p^T dS_p), the all-reduce of dW / db, dX."""
+    fin, fout = w.shape
+    if not agg:
         dw = ops.gemm(x.t(), ds)                     # local part of X^T dS
     if dgraph.world > 1 and reduce:
         flat = torch.cat([dw.reshape(-1), db.reshape(-1)])
@@ -847,9 +923,12 @@ def dist_layer_backward(ops, dgraph, x, w, g, y=None, need_dx=True, has_bias=Tru
         dw = flat[: fin * fout].reshape(fin, fout)
         db = flat[fin * fout:]
     dx = None
-    if need_dx and agg:
-        compact = halo_compact(ops, dgraph, True, fin, g, exch, group)
-        gw = ops.gemm(gm, w.t(), out=compact[: g.shape[0]] if compact is not None else None)
+    if need_dx and agg and chunked_halo_applies(ops, dgraph, fin, exch):
+        dx = dist_spmm_halo_chunked(ops, dgraph, True, fin, gm, lambda c0, c1, dst: ops.gemm(gm, w[c0:c1].t(), out=dst),
+                                    None, False, group)
+    elif need_dx and agg:
+        compact = halo_compact(ops, dgraph, True, fin, gm, exch, group)
+        gw = ops.gemm(gm, w.t(), out=compact[: gm.shape[0]] if compact is not None else None)
         dx = exchanged_spmm(ops, dgraph, True, gw, exch, None, False, group, compact)
     elif need_dx:
         dx = ops.gemm(ds, w.t())
@@ -1225,8 +1304,13 @@ def bench_main(args, wl):
     panel = torch.randn(n_local if resolved[0] == "halo" else dgraph.pad_rows, fw, device=dev)
     kind = "halo" if "halo" in resolved else "nccl"
 
-    def exchange_and_spmm():
-        exchanged_spmm(ops, dgraph, False, panel, kind)
+    chunked = chunked_halo_applies(ops, dgraph, fw, kind)
+
+    def exchange_and_spmm():  # as the layer runs it: in column chunks where that applies (the producer here is a copy)
+        if chunked:
+            dist_spmm_halo_chunked(ops, dgraph, False, fw, panel, lambda c0, c1, dst: dst.copy_(panel[:, c0:c1]))
+        else:
+            exchanged_spmm(ops, dgraph, False, panel, kind)
     ex_ms = timer.time(exchange_and_spmm, max(3, min(args.steps, 10)))[0]
     blk = dgraph.fwd_remote if kind == "nccl" else halo_plans(ops, dgraph)[0].block
     dense = torch.randn(blk.n_cols, fw, device=dev)
@@ -1276,7 +1360,7 @@ def bench_main(args, wl):
                          "frac": alg / (t2[1].item() * 1e-3) / 1e9 / peak, "traffic": None,
                          "kernel": "CSR SpMM over rank 0's row block (width %d), slowest rank's time" % fw,
                          "algorithmic_bytes_per_launch": alg, "kernel_ms": t2[1].item(), "peak_source": peak_src,
-                         "exchange_plus_spmm_ms": t2[0].item(), "exchange_share": max(0.0, 1.0 - t2[1].item() / max(t2[0].item(), 1e-9))},
+                         "exchange_plus_spmm_ms": t2[0].item(), "exchange_column_chunks": column_chunks(fw) if chunked else None, "exchange_share": max(0.0, 1.0 - t2[1].item() / max(t2[0].item(), 1e-9))},
         }
         print(json.dumps(line), flush=True)
     # a captured graph that holds NCCL kernels must go before the communicator does

@@ -104,10 +104,12 @@ def _problem(n=300, seed=3, fout=5, fin=12):
     return n, idx, val, x, g, w, b
 
 
-def _worker(rank, world, port, outdir, relu, split=True, exchange="nccl", agg=False, fin=12, fout=5):
+def _worker(rank, world, port, outdir, relu, split=True, exchange="nccl", agg=False, fin=12, fout=5, chunk_min=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    if chunk_min is not None:  # pipelined exchange in column chunks of >= chunk_min columns (the product default is 128)
+        D.CHUNK_MIN_COLS = chunk_min
     try:
         n, idx, val, x, g, w, b = _problem(fin=fin, fout=fout)
         bounds = D.partition_rows_by_nnz(O.coo_to_csr(idx, n), world)
@@ -148,12 +150,29 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,relu,exchange", [(2, True, "halo"), (4, False, "halo"), (3, True, "nccl")])
-def test_unsplit_halo_exchange_with_the_panel_produced_in_the_compact_buffer(world, relu, exchange):
+def test_column_chunks_of_the_pipelined_exchange():
+    assert D.column_chunks(256) == [(0, 128), (128, 256)]
+    assert D.column_chunks(100) == [(0, 100)] and D.column_chunks(47) == [(0, 47)] and D.column_chunks(128) == [(0, 128)]
+    assert D.column_chunks(260) == [(0, 132), (132, 260)]
+    old = D.CHUNK_MIN_COLS
+    try:
+        D.CHUNK_MIN_COLS = 4
+        assert D.column_chunks(12) == [(0, 8), (8, 12)] and D.column_chunks(8) == [(0, 4), (4, 8)]
+        assert D.column_chunks(6) == [(0, 6)]  # not a multiple of 4: one chunk
+    finally:
+        D.CHUNK_MIN_COLS = old
+
+
+@pytest.mark.parametrize("world,relu,exchange,agg,chunk_min", [
+    (2, True, "halo", False, None), (4, False, "halo", False, None), (3, True, "nccl", False, None),
+    # the pipelined exchange: X W / the staged masked G / X / G W^T produced, packed and sent in two column chunks
+    (2, True, "halo", False, 4), (3, False, "halo", False, 4), (4, True, "halo", True, 4), (2, False, "halo", True, 4)])
+def test_unsplit_halo_exchange_with_the_panel_produced_in_the_compact_buffer(world, relu, exchange, agg, chunk_min):
     """Widths that need no padding (8): X W, the staged masked G (and G W^T in the aggregate-first order, fin = 12
-    above) are written straight into the own slot of the compact panel (dist.halo_compact) -- same results."""
+    above) are written straight into the own slot of the compact panel (dist.halo_compact) -- same results; and the
+    same through dist_spmm_halo_chunked."""
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_worker, args=(world, _free_port(), d, relu, False, exchange, False, 12, 8), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), d, relu, False, exchange, agg, 12, 8, chunk_min), nprocs=world, join=True)
         parts = [np.load(os.path.join(d, "r%d.npz" % r)) for r in range(world)]
     n, idx, val, x, g, w, b = _problem(fout=8)
     _, o_ref = O.c_layer_forward(x, w, b, idx, val, n)

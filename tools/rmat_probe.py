@@ -68,12 +68,17 @@ def main():
                 csr = graph.to_sparse_coo().coalesce().to_sparse_csr()
                 ref = torch.sparse.mm(csr, s)
                 del csr
-            for cfg in opt("--sweep", "default").split(","):
-              if cfg != "default":
+            for cfg in opt("--sweep", "default").split(",") + ["gv%s" % v for v in opt("--group-variants", "").split(",") if v]:
+              if cfg.startswith("gv"):  # --group-variants 0,2,13,-2: the group-per-row kernel's variants (narrow panels), streaming
+                  # kernel off; -2 = the warp-per-row kernel
+                  _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_STREAM, 0), "set_tuning")
+                  _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_KERNEL, 2 if int(cfg[2:]) >= -1 else 1), "set_tuning")
+                  _lib.check(lib.gcnb_set_tuning(_lib.TUNE_SPMM_GROUP_VARIANT, max(int(cfg[2:]), -1)), "set_tuning")
+              elif cfg != "default":
                   vals = [int(v) for v in cfg.split(":")]
                   for key, v in zip((_lib.TUNE_SPMM_STREAM, _lib.TUNE_STREAM_HOT_MB, _lib.TUNE_STREAM_HINT, _lib.TUNE_STREAM_BATCH), vals):
                       _lib.check(lib.gcnb_set_tuning(key, v), "set_tuning")
-              print(" config stream:hot_mb:hint:batch = %s" % cfg)
+              print(" config stream:hot_mb:hint:batch (gvN = group variant N) = %s" % cfg)
               for slices in [int(v) for v in opt("--slices", "1").split(",")]:
                if slices > 1:
                   print(" slices %d" % slices)
