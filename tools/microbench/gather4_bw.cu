@@ -9,6 +9,7 @@
 //     rows       table rows (48000 = L2 resident at 1 KB rows, 2400000 = the products panel)
 //     hot_rows / hot_pct: hot_pct % of the references fall on the first hot_rows rows (0 0 = uniform)
 //     box_rows   second box dimension of the tensor map (1 = what CuTe encodes for gather4)
+//     persist_mb > 0: cudaLimitPersistingL2CacheSize of that size + a persisting access-policy window over the hot rows
 // Prints: correctness of the gather4 kernel against the register kernel (same partial sums), then time and TB/s of both.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -189,6 +190,7 @@ int main(int argc, char** argv) {
   const long hot_rows = atol(argv[6]);
   const int hot_pct = atoi(argv[7]);
   const int box_rows = argc > 8 ? atoi(argv[8]) : 1;
+  const int persist_mb = argc > 9 ? atoi(argv[9]) : 0;  // > 0: L2 persisting carve-out of that size + an access policy window over the hot rows
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
@@ -238,6 +240,20 @@ int main(int argc, char** argv) {
                                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed: %d\n", (int)r); return 1; }
 
+  if (persist_mb > 0 && hot_rows > 0) {
+    // Are pinned hub rows worth anything?  The hot rows are the first hot_rows rows of the table: one contiguous window,
+    // hitProp = persisting (they stay in the carve-out), everything else streams.
+    printf("persistingL2CacheMaxSize %d MB, accessPolicyMaxWindowSize %d MB, L2 %d MB\n", prop.persistingL2CacheMaxSize >> 20,
+           prop.accessPolicyMaxWindowSize >> 20, prop.l2CacheSize >> 20);
+    CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_mb << 20));
+    cudaStreamAttrValue av = {};
+    av.accessPolicyWindow.base_ptr = t;
+    av.accessPolicyWindow.num_bytes = (size_t)hot_rows * ld * 4;
+    av.accessPolicyWindow.hitRatio = 1.0f;
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CK(cudaStreamSetAttribute(0, cudaStreamAttributeAccessPolicyWindow, &av));
+  }
   const int ch = (w / 4 + 31) / 32;
   auto run_g4 = [&]() {
     if (ch == 1) {
