@@ -197,7 +197,9 @@ def config_of(wl, nnz, n):
     """The `config` both arms print (identical by construction: same seeded edge list, same model)."""
     return {"workload": wl["name"], "n": n, "nnz": nnz, "layers": wl["dims"], "relu_after_every_layer": bool(wl["relu"]),
             "edges_per_step": (nnz * (len(wl["dims"]) - 1)) if nnz else None, "input_requires_grad": False,
-            "graph_seed": 0, "edge_generator": "torch CPU Generator (same edge list in both arms)"}
+            "graph_seed": 0, "edge_generator": "torch CPU Generator (same edge list in both arms)",
+            "l2": "GPU arms: L2 flushed between timed steps (512 MiB write; one step touches > 10x the L2); "
+                  "CPU reference arm: host caches as they are"}
 
 
 def peaks():
@@ -723,17 +725,17 @@ def run_ours(args, wl):
                "alt_csr_edges_per_s": r.get("alt_csr_edges_per_s"), "alt_1thread_edges_per_s": r.get("alt_1thread_edges_per_s"),
                "cpu_model": r["cpu_model"]}
 
-    cfg = config_of(wl, nnz, n)
-    cfg.update({"l2": "flushed between timed steps (512 MiB write); one step touches > 10x the L2",
-                "cuda_graph": res["cuda_graph"], "graph_build_s": res["graph_build_s"],
-                "host_edge_generation_s": res["host_edge_generation_s"], "bins": res["bins"],
-                "long_chunks": res["long_chunks"], "max_degree": res["max_degree"],
-                "association": [s["order"] for s in res["spmm"]]})
+    cfg = config_of(wl, nnz, n)  # the same object as the reference arm's, key for key
+    run = {"cuda_graph": res["cuda_graph"], "graph_build_s": res["graph_build_s"],
+           "host_edge_generation_s": res["host_edge_generation_s"], "bins": res["bins"],
+           "long_chunks": res["long_chunks"], "max_degree": res["max_degree"],
+           "association": [s["order"] for s in res["spmm"]]}
     line = {
         "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": 1,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": cfg,
+        "run": run,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3,

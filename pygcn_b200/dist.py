@@ -1331,13 +1331,14 @@ def bench_main(args, wl):
     peak, peak_src = B.peaks()
     alg = B.algorithmic_bytes_spmm(blk.nnz, n_local, fw)
     if rank == 0:
-        cfg = B.config_of(wl, nnz_global, n_global)
-        cfg.update({"partition": ("1-D partition of the nodes, dealt by row length: equal rows and ~equal stored entries per rank "
+        cfg = B.config_of(wl, nnz_global, n_global)  # the same object as the reference arm's, key for key
+        run = {}
+        run.update({"partition": ("1-D partition of the nodes, dealt by row length: equal rows and ~equal stored entries per rank "
                                   "(dist.balanced_node_partition)" if (balance and not partitioned) else
                                   "1-D contiguous row blocks, cost = stored entries + %g x rows" % row_weight),
                     "bounds": dgraph.bounds,
                     "row_block_split": dgraph.split, "exchange": resolved, "cuda_graph": cg is not None,
-                    "graph_build_s": build_s, "l2": "flushed between timed steps (512 MiB write)",
+                    "graph_build_s": build_s,
                     "association": [o for (_, _, _, o) in B.spmm_plan(dims)], "halo": halo,
                     "exchange_note": "halo: every rank sends each peer only the panel rows that peer's block reads (selection SpMM "
                                      "packs them, grouped NCCL send / recv into a compact panel) while the diagonal block's SpMM "
@@ -1347,6 +1348,7 @@ def bench_main(args, wl):
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg,
+            "run": run,
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": (x_host.numel() + g_host.numel()) * 4,
                     "d2h_bytes_per_step": sum(w.numel() + b.numel() for w, b in params) * 4,

@@ -10,7 +10,7 @@ run() { # name, env...
 import json
 try:
     d=json.loads(open('gpurun_out/r2_tune_n${N}_$name.json').read().strip().splitlines()[-1])
-    print('$name', 'ms', round(d['ms_per_step'],2), 'split', d['config']['row_block_split'], d['config']['partition'][:40], 'exch+spmm', round(d['roofline']['exchange_plus_spmm_ms'],2), 'spmm', round(d['roofline']['kernel_ms'],2), 'graph', d['config']['cuda_graph'], 'halo', d['config']['halo'])
+    print('$name', 'ms', round(d['ms_per_step'],2), 'split', d.get('run', d['config'])['row_block_split'], d.get('run', d['config'])['partition'][:40], 'exch+spmm', round(d['roofline']['exchange_plus_spmm_ms'],2), 'spmm', round(d['roofline']['kernel_ms'],2), 'graph', d.get('run', d['config'])['cuda_graph'], 'halo', d.get('run', d['config'])['halo'])
 except Exception as e:
     print('$name failed', e)
     print(open('gpurun_out/r2_tune_n${N}_$name.err').read()[-1500:])

@@ -11,7 +11,7 @@ run() { # name, env...
 import json
 try:
     d=json.loads(open('gpurun_out/r2_tune_n${N}_$name.json').read().strip().splitlines()[-1])
-    print('$name', 'ms', round(d['ms_per_step'],2), 'split', d['config']['row_block_split'], 'exch+spmm', round(d['roofline']['exchange_plus_spmm_ms'],2), 'spmm', round(d['roofline']['kernel_ms'],2), 'chunks', d['roofline'].get('exchange_column_chunks'))
+    print('$name', 'ms', round(d['ms_per_step'],2), 'split', d.get('run', d['config'])['row_block_split'], 'exch+spmm', round(d['roofline']['exchange_plus_spmm_ms'],2), 'spmm', round(d['roofline']['kernel_ms'],2), 'chunks', d['roofline'].get('exchange_column_chunks'))
 except Exception as e:
     print('$name failed', e)
     print(open('gpurun_out/r2_tune_n${N}_$name.err').read()[-1500:])
