@@ -752,6 +752,35 @@ gemm_tc_rows_tma_kernel(const __grid_constant__ TmaDesc tmap_a, int64_t M, int N
             for (int t2 = 0; t2 < 4; ++t2)
               if (col + t2 < n_cols) bv[t2] = __ldg(ep_bias + n0 + col + t2);
           }
+          // Fast path (every tile but the last rows / an N that is not a multiple of 32 / unaligned C): whole 32 x 32 block,
+          // 128-bit stores, no per-store predicates.  The general loop below costs ~40 instructions and several
+          // dependent branches per store and made the epilogue the bottleneck of every 256-wide product (7.9 us per
+          // 128 x 256 tile whatever K: profiles/r02_gemm_k_sweep.txt).
+          if (vec_ok && m0 + 32 <= M && cb + 32 <= n_cols) {  // (warp-uniform)
+            const float* sp = stg + (lane >> 3) * kEpiLd + 4 * q;
+            float* dp = c + (m0 + (lane >> 3)) * ldc + n0 + col;
+            if (!add && !fin_ep) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(dp + (int64_t)(4 * i) * ldc) = *reinterpret_cast<const float4*>(sp + 4 * i * kEpiLd);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 v = *reinterpret_cast<const float4*>(sp + 4 * i * kEpiLd);
+                float* dst = dp + (int64_t)(4 * i) * ldc;
+                if (add) {
+                  const float4 p = *reinterpret_cast<const float4*>(dst);
+                  v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+                }
+                if (fin_ep) {
+                  v.x += bv[0]; v.y += bv[1]; v.z += bv[2]; v.w += bv[3];
+                  if (ep_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                }
+                *reinterpret_cast<float4*>(dst) = v;
+              }
+            }
+            continue;
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = 4 * i + (lane >> 3);
