@@ -752,48 +752,31 @@ gemm_tc_rows_tma_kernel(const __grid_constant__ TmaDesc tmap_a, int64_t M, int N
             for (int t2 = 0; t2 < 4; ++t2)
               if (col + t2 < n_cols) bv[t2] = __ldg(ep_bias + n0 + col + t2);
           }
-          // Fast path (every tile but the one holding the last rows, or an unaligned C): 128-bit stores without per-store
-          // predicates.  The general loop below costs ~40 instructions and several dependent branches per store and
-          // made the epilogue the floor of every 256-wide product (7.9 us per 128 x 256 tile whatever K:
-          // profiles/r02_gemm_k_sweep.txt).  Lanes diverge only in a ragged last column block (47 classes).
-          if (vec_ok && m0 + 32 <= M) {  // (warp-uniform)
+          // Fast path (whole 32 x 32 blocks of an aligned C): 128-bit stores without per-store predicates.  The general
+          // loop below costs ~40 instructions and several dependent branches per store and made the epilogue the
+          // floor of every 256-wide product (7.9 us per 128 x 256 tile whatever K: profiles/r02_gemm_k_sweep.txt); it
+          // keeps the last rows and a ragged last column block (47 classes).
+          if (vec_ok && m0 + 32 <= M && cb + 32 <= n_cols) {  // (warp-uniform)
             const float* sp = stg + (lane >> 3) * kEpiLd + 4 * q;
             float* dp = c + (m0 + (lane >> 3)) * ldc + n0 + col;
-            if (col + 4 <= n_cols) {
-              if (!add && !fin_ep) {
+            if (!add && !fin_ep) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  *reinterpret_cast<float4*>(dp + (int64_t)(4 * i) * ldc) = *reinterpret_cast<const float4*>(sp + 4 * i * kEpiLd);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  float4 v = *reinterpret_cast<const float4*>(sp + 4 * i * kEpiLd);
-                  float* dst = dp + (int64_t)(4 * i) * ldc;
-                  if (add) {
-                    const float4 p = *reinterpret_cast<const float4*>(dst);
-                    v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
-                  }
-                  if (fin_ep) {
-                    v.x += bv[0]; v.y += bv[1]; v.z += bv[2]; v.w += bv[3];
-                    if (ep_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                  }
-                  *reinterpret_cast<float4*>(dst) = v;
-                }
-              }
-            } else if (col < n_cols) {  // the 1 .. 3 last columns of a width that is not a multiple of 4
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(dp + (int64_t)(4 * i) * ldc) = *reinterpret_cast<const float4*>(sp + 4 * i * kEpiLd);
+            } else {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float4 v = *reinterpret_cast<const float4*>(sp + 4 * i * kEpiLd);
-                const float e[4] = {v.x, v.y, v.z, v.w};
+                float4 v = *reinterpret_cast<const float4*>(sp + 4 * i * kEpiLd);
                 float* dst = dp + (int64_t)(4 * i) * ldc;
-                for (int t2 = 0; col + t2 < n_cols; ++t2) {
-                  float o = add ? dst[t2] + e[t2] : e[t2];
-                  if (fin_ep) {
-                    o += bv[t2];
-                    if (ep_relu) o = fmaxf(o, 0.f);
-                  }
-                  dst[t2] = o;
+                if (add) {
+                  const float4 p = *reinterpret_cast<const float4*>(dst);
+                  v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
                 }
+                if (fin_ep) {
+                  v.x += bv[0]; v.y += bv[1]; v.z += bv[2]; v.w += bv[3];
+                  if (ep_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                }
+                *reinterpret_cast<float4*>(dst) = v;
               }
             }
             continue;
@@ -998,30 +981,21 @@ gemm_tc_tn_tma_kernel(const __grid_constant__ TmaDesc tmap_x, const __grid_const
         // loads first, then the adds, then the stores.  In the general loop below every group waits for its own load
         // behind a chain of predicates (~700 cycles each): a drain of a 128 x 256 tile then outlasts the 16 K blocks
         // of MMAs it is meant to hide behind.
-        if (vec_ok && m0 + warp * 32 + 32 <= M) {  // (warp-uniform; lanes diverge only in a ragged last column block)
+        if (vec_ok && m0 + warp * 32 + 32 <= M && cb + 32 <= N) {  // (warp-uniform)
           const float* sp = stg + (lane >> 3) * kEpiLd + 4 * q;
           float* dp = cdst + (int64_t)(m0 + warp * 32 + (lane >> 3)) * ldc + col;
           float4 v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(sp + 4 * i * kEpiLd);
-          if (col + 4 <= N) {
-            if (add) {
-              float4 pv[8];
+          if (add) {
+            float4 pv[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) pv[i] = *reinterpret_cast<const float4*>(dp + (int64_t)(4 * i) * ldc);
+            for (int i = 0; i < 8; ++i) pv[i] = *reinterpret_cast<const float4*>(dp + (int64_t)(4 * i) * ldc);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { v[i].x += pv[i].x; v[i].y += pv[i].y; v[i].z += pv[i].z; v[i].w += pv[i].w; }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(dp + (int64_t)(4 * i) * ldc) = v[i];
-          } else if (col < N) {  // the 1 .. 3 columns of a width that is not a multiple of 4 (47 classes)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-              float* dst = dp + (int64_t)(4 * i) * ldc;
-              for (int t2 = 0; col + t2 < N; ++t2) dst[t2] = add ? dst[t2] + e[t2] : e[t2];
-            }
+            for (int i = 0; i < 8; ++i) { v[i].x += pv[i].x; v[i].y += pv[i].y; v[i].z += pv[i].z; v[i].w += pv[i].w; }
           }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(dp + (int64_t)(4 * i) * ldc) = v[i];
           continue;
         }
 #pragma unroll
